@@ -1,0 +1,114 @@
+/*
+ * mplb.h -- C ABI of the B200-native validity-check library (libmplb.so).
+ *
+ * This is the drop-in boundary for the reference's scenario validity interface
+ * (BerkeleyAutomation/mplambda, paths relative to the reference root):
+ *
+ *   include/mpl/demo/se3_rigid_body_scenario.hpp:51-64    ctor (mesh load, BVH build)   -> mplb_scene_create_se3*
+ *   include/mpl/demo/se3_rigid_body_scenario.hpp:119-126  isValid(const State&)         -> mplb_check_states
+ *   include/mpl/demo/se3_rigid_body_scenario.hpp:134-178  isValid(from, to)             -> mplb_check_edges
+ *   include/mpl/demo/load_mesh.hpp:232-293                MeshLoad<...>::load           -> mplb_mesh_load_collada
+ *   include/mpl/demo/fetch_scenario.hpp:48-63,105-173     FetchScenario ctor / isValid  -> mplb_scene_create_fetch, mplb_check_states/_edges
+ *   include/mpl/prrt.hpp:61,66-68 / pcforest.hpp:80-87,107  nigh insert/nearest/nearest(k) -> mplb_nn_*
+ *
+ * Plain pointers and sizes only; no C++/torch types.  Every function returns MPLB_OK (0) or a
+ * negative error code, and mplb_last_error() holds a thread-local message.  There is no CPU
+ * fallback: without a CUDA device every compute entry point fails with MPLB_ERR_CUDA.
+ *
+ * Threading: a scene is immutable after creation; mplb_check_* may be called concurrently from
+ * any number of host threads on the same scene (the reference calls isValid from OpenMP planner
+ * threads, prrt.hpp:140-152) -- each call borrows a private stream + staging context.
+ */
+#ifndef MPLB_H
+#define MPLB_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPLB_OK 0
+#define MPLB_ERR_INVALID (-1) /* bad argument (the C++ wrapper throws std::invalid_argument) */
+#define MPLB_ERR_IO (-2)      /* mesh file missing / unparsable (load_mesh.hpp:250-254)        */
+#define MPLB_ERR_CUDA (-3)    /* no device, CUDA failure, or kernel overflow flag               */
+#define MPLB_ERR_NOMEM (-4)
+
+typedef struct mplb_scene mplb_scene;
+typedef struct mplb_nn mplb_nn;
+
+const char *mplb_last_error(void);
+/* number of visible CUDA devices (0 when none / no driver) */
+int mplb_device_count(void);
+
+/* ---------------------------------------------------------------------------------------- */
+/* Mesh import: replaces MeshLoad<Mesh>::load(name, shiftToCenter, identityRootTransform)
+ * (load_mesh.hpp:232-293).  Emits the triangle soup visitTriangles (load_mesh.hpp:50-89) feeds
+ * to addTriangle: float64 [n][3][3].  *tris is malloc'd; release with mplb_free.  center[3]
+ * (optional) receives the subtracted centroid (zero when shift_to_center == 0). */
+int mplb_mesh_load_collada(const char *path, int shift_to_center, int identity_root_transform,
+                           double **tris, size_t *ntris, double center[3]);
+void mplb_free(void *p);
+
+/* ---------------------------------------------------------------------------------------- */
+/* SE(3) rigid-body scene: replaces SE3RigidBodyScenario's constructor
+ * (se3_rigid_body_scenario.hpp:51-64).  Triangles are the robot mesh (already shifted to its
+ * centre, as load(robotMesh, true, false) does) and the environment mesh, float64 [n][3][3].
+ * so3_weight/l2_weight are the template weights of nigh::SE3Space<S,50,1> (line 15-18) and
+ * check_resolution the ctor argument (invStepSize_ = 1/checkResolution, line 63). */
+int mplb_scene_create_se3(const double *env_tris, size_t n_env, const double *robot_tris,
+                          size_t n_robot, double so3_weight, double l2_weight,
+                          double check_resolution, int device, mplb_scene **out);
+/* Convenience: the same from the two .dae paths, exactly like the reference ctor. */
+int mplb_scene_create_se3_files(const char *env_path, const char *robot_path, double so3_weight,
+                                double l2_weight, double check_resolution, int device,
+                                mplb_scene **out);
+void mplb_scene_destroy(mplb_scene *scene);
+
+/* State layouts (host or device, float64):
+ *   SE3  : [n][7] = qx,qy,qz,qw,tx,ty,tz   (std::tuple<Quaterniond,Vector3d>, Eigen coeff order)
+ *   Fetch: [n][8] = torso_lift, shoulder_pan, ... wrist_roll (fetch_robot.hpp:80-99)
+ * mplb_scene_state_dim returns 7 or 8. */
+int mplb_scene_state_dim(const mplb_scene *scene);
+
+/* isValid(q) for n states; valid[i] = 1 iff state i is collision free.  HOST buffers; includes
+ * the H2D/D2H copies.  n == 1 is the reference's single call (se3...:119-126). */
+int mplb_check_states(mplb_scene *scene, const double *states, size_t n, uint8_t *valid);
+
+/* isValid(from, to) for n edges (se3...:134-178): valid[i] = isValid(to_i) AND every
+ * interpolated state at i/steps, steps = ceil(distance(from,to)/checkResolution).  `from` is
+ * assumed valid like the reference's assert.  states_checked (optional) receives the number of
+ * states actually evaluated on the device (<= sum of steps thanks to early exit). */
+int mplb_check_edges(mplb_scene *scene, const double *from, const double *to, size_t n,
+                     uint8_t *valid, uint64_t *states_checked);
+
+/* Device-resident variants: all pointers are device memory on the scene's device; work is
+ * enqueued on `stream` (a cudaStream_t passed as void*; NULL = the default stream) and NOT
+ * synchronised.  steps/offsets for edges are computed by mplb_edges_plan on the host. */
+int mplb_check_states_device(mplb_scene *scene, const double *d_states, size_t n,
+                             uint8_t *d_valid, void *stream);
+/* Host-side plan of an edge batch: steps[i] = ceil(distance*invStep) exactly as
+ * se3...:139 (host libm, bit-identical to the CPU path). */
+int mplb_edges_plan(mplb_scene *scene, const double *from, const double *to, size_t n,
+                    uint32_t *steps);
+int mplb_check_edges_device(mplb_scene *scene, const double *d_from, const double *d_to,
+                            const uint32_t *d_steps, size_t n, uint32_t max_steps,
+                            uint8_t *d_valid, void *stream);
+
+/* Space::distance (nigh SE3Space / L1Space) on the host, used by the wrappers' isGoal. */
+double mplb_distance(const mplb_scene *scene, const double *a, const double *b);
+
+typedef struct {
+    uint64_t checks;      /* states evaluated (isValid(q) equivalents, the reference's calls_) */
+    uint64_t bv_tests;    /* OBB-OBB tests executed on the device                              */
+    uint64_t tri_tests;   /* FP32 filtered triangle-triangle tests                             */
+    uint64_t exact_tests; /* FP64 exact re-evaluations of uncertain triangle pairs             */
+    uint64_t launches;    /* kernels launched                                                  */
+    uint64_t env_tris, robot_tris, env_nodes, robot_nodes;
+} mplb_stats_t;
+int mplb_scene_stats(mplb_scene *scene, mplb_stats_t *out, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPLB_H */

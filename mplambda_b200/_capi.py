@@ -1,0 +1,80 @@
+"""ctypes binding of libmplb.so -- the same C ABI (include/mplb.h) a cgo/JNI/C++ caller binds.
+
+The library is built in-tree by mplambda_b200/build.py (nvcc, sm_100a).  There is no Python or
+CPU fallback: if the shared object is missing, loading raises.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+OK, ERR_INVALID, ERR_IO, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("checks", "bv_tests", "tri_tests", "exact_tests", "launches",
+                                           "env_tris", "robot_tris", "env_nodes", "robot_nodes")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class MplbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libmplb error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+dp = C.POINTER(C.c_double)
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+i64p = C.POINTER(C.c_int64)
+
+_SIGNATURES = {
+    "mplb_last_error": (C.c_char_p, []),
+    "mplb_device_count": (C.c_int, []),
+    "mplb_mesh_load_collada": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(dp), C.POINTER(C.c_size_t), dp]),
+    "mplb_free": (None, [C.c_void_p]),
+    "mplb_scene_create_se3": (C.c_int, [dp, C.c_size_t, dp, C.c_size_t, C.c_double, C.c_double, C.c_double,
+                                        C.c_int, C.POINTER(C.c_void_p)]),
+    "mplb_scene_create_se3_files": (C.c_int, [C.c_char_p, C.c_char_p, C.c_double, C.c_double, C.c_double, C.c_int,
+                                              C.POINTER(C.c_void_p)]),
+    "mplb_scene_destroy": (None, [C.c_void_p]),
+    "mplb_scene_state_dim": (C.c_int, [C.c_void_p]),
+    "mplb_check_states": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mplb_check_edges": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, u64p]),
+    "mplb_check_states_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "mplb_edges_plan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mplb_check_edges_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32,
+                                          C.c_void_p, C.c_void_p]),
+    "mplb_distance": (C.c_double, [C.c_void_p, dp, dp]),
+    "mplb_scene_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats), C.c_int]),
+}
+
+
+def lib_path():
+    return _build.LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise ImportError("libmplb.so is not built (%s); run `python -m mplambda_b200.build` -- "
+                              "there is no fallback implementation" % path)
+        L = C.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        raise MplbError(rc, lib().mplb_last_error().decode("utf-8", "replace"))

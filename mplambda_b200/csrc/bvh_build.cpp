@@ -1,0 +1,211 @@
+// Host-side construction of the flat OBB hierarchy that stays resident in HBM.
+//
+// Plays the role of fcl::BVHModel<OBBRSS>::beginModel/addTriangle/endModel as called from the
+// reference's mesh loader (include/mpl/demo/load_mesh.hpp:275-284) -- but the layout is chosen
+// for the device: 64-byte nodes read as four 128-bit loads, one triangle per leaf, siblings
+// adjacent, median splits so that depth (and with it the per-warp pair stack) is bounded.
+// The collision verdict does not depend on the hierarchy (boxes only cull; the leaf test is
+// the reference's 17-axis triangle-triangle predicate), so this need not be FCL's tree.
+#include "mplb_host.hpp"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+namespace mplb {
+namespace {
+
+struct V3 { double x, y, z; };
+inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator*(V3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+inline double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline double norm(V3 a) { return std::sqrt(dot(a, a)); }
+
+// symmetric 3x3 eigen decomposition (cyclic Jacobi); columns of V are eigenvectors
+void eigenSym3(const double Ain[3][3], double w[3], double V[3][3]) {
+    double a[3][3];
+    std::memcpy(a, Ain, sizeof(a));
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) V[i][j] = i == j;
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        double off = std::fabs(a[0][1]) + std::fabs(a[0][2]) + std::fabs(a[1][2]);
+        double diag = std::fabs(a[0][0]) + std::fabs(a[1][1]) + std::fabs(a[2][2]);
+        if (off <= 1e-18 * diag || off == 0) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (a[p][q] == 0) continue;
+                double th = (a[q][q] - a[p][p]) / (2 * a[p][q]);
+                double t = (th >= 0 ? 1.0 : -1.0) / (std::fabs(th) + std::sqrt(th * th + 1));
+                double c = 1 / std::sqrt(t * t + 1), s = t * c;
+                for (int k = 0; k < 3; ++k) {
+                    double x = a[k][p], y = a[k][q];
+                    a[k][p] = c * x - s * y; a[k][q] = s * x + c * y;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    double x = a[p][k], y = a[q][k];
+                    a[p][k] = c * x - s * y; a[q][k] = s * x + c * y;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    double x = V[k][p], y = V[k][q];
+                    V[k][p] = c * x - s * y; V[k][q] = s * x + c * y;
+                }
+            }
+    }
+    for (int i = 0; i < 3; ++i) w[i] = a[i][i];
+}
+
+struct Box { V3 axis[3]; V3 center; double ext[3]; };
+
+struct Builder {
+    const V3 *verts;  // 3 per triangle
+    std::vector<int> prim;
+    std::vector<V3> centroid;
+    std::vector<Box> boxes;
+    std::vector<int> link;
+    int depth = 0;
+
+    Box fit(int first, int n) const {
+        // PCA of the triangle vertices
+        V3 mean{0, 0, 0};
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < 3; ++k) mean = mean + verts[3 * prim[first + i] + k];
+        mean = mean * (1.0 / (3.0 * n));
+        double C[3][3] = {{0}};
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < 3; ++k) {
+                V3 d = verts[3 * prim[first + i] + k] - mean;
+                double v[3] = {d.x, d.y, d.z};
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b) C[a][b] += v[a] * v[b];
+            }
+        double w[3], E[3][3];
+        eigenSym3(C, w, E);
+        int order[3] = {0, 1, 2};
+        std::sort(order, order + 3, [&](int a, int b) { return w[a] > w[b]; });
+        Box bx;
+        V3 a0{E[0][order[0]], E[1][order[0]], E[2][order[0]]};
+        V3 a1{E[0][order[1]], E[1][order[1]], E[2][order[1]]};
+        double l0 = norm(a0);
+        a0 = l0 > 0 ? a0 * (1 / l0) : V3{1, 0, 0};
+        a1 = a1 - a0 * dot(a0, a1);
+        double l1 = norm(a1);
+        if (!(l1 > 1e-12)) {
+            V3 t = std::fabs(a0.x) < 0.9 ? V3{1, 0, 0} : V3{0, 1, 0};
+            a1 = cross(a0, t);
+            l1 = norm(a1);
+        }
+        a1 = a1 * (1 / l1);
+        V3 a2 = cross(a0, a1);
+        bx.axis[0] = a0; bx.axis[1] = a1; bx.axis[2] = a2;
+        double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < 3; ++k) {
+                V3 p = verts[3 * prim[first + i] + k];
+                for (int a = 0; a < 3; ++a) {
+                    double d = dot(bx.axis[a], p);
+                    lo[a] = std::min(lo[a], d);
+                    hi[a] = std::max(hi[a], d);
+                }
+            }
+        bx.center = {0, 0, 0};
+        for (int a = 0; a < 3; ++a) {
+            bx.ext[a] = 0.5 * (hi[a] - lo[a]);
+            bx.center = bx.center + bx.axis[a] * (0.5 * (hi[a] + lo[a]));
+        }
+        return bx;
+    }
+
+    void build(int node, int first, int n, int d) {
+        boxes[node] = fit(first, n);
+        depth = std::max(depth, d);
+        if (n == 1) {
+            link[node] = -(prim[first] + 1);
+            return;
+        }
+        // median split of centroids along the longest box axis
+        const Box &bx = boxes[node];
+        int ax = 0;
+        if (bx.ext[1] > bx.ext[ax]) ax = 1;
+        if (bx.ext[2] > bx.ext[ax]) ax = 2;
+        V3 dir = bx.axis[ax];
+        int half = n / 2;
+        std::nth_element(prim.begin() + first, prim.begin() + first + half, prim.begin() + first + n,
+                         [&](int a, int b) {
+                             double pa = dot(dir, centroid[a]), pb = dot(dir, centroid[b]);
+                             return pa < pb || (pa == pb && a < b);
+                         });
+        int fc = (int)boxes.size();
+        boxes.resize(fc + 2);
+        link.resize(fc + 2);
+        link[node] = fc;
+        build(fc, first, half, d + 1);
+        build(fc + 1, first + half, n - half, d + 1);
+    }
+};
+
+inline float roundUp(double v) {
+    float f = (float)v;
+    if ((double)f < v) f = std::nextafterf(f, INFINITY);
+    return f;
+}
+
+}  // namespace
+
+FlatBvh buildBvh(const double *tris, size_t n) {
+    FlatBvh out;
+    out.tris64.assign(tris, tris + 9 * n);
+    out.tris32.resize(n);
+    for (size_t i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k) {
+            for (int d = 0; d < 3; ++d) {
+                double v = tris[9 * i + 3 * k + d];
+                out.tris32[i].v[k][d] = (float)v;
+                out.absMax = std::max(out.absMax, std::fabs(v));
+            }
+            out.tris32[i].v[k][3] = 0.f;
+            const double *p = &tris[9 * i + 3 * k];
+            out.radius = std::max(out.radius, std::sqrt(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]));
+        }
+    if (n == 0) return out;
+
+    Builder b;
+    b.verts = reinterpret_cast<const V3 *>(tris);
+    b.prim.resize(n);
+    std::iota(b.prim.begin(), b.prim.end(), 0);
+    b.centroid.resize(n);
+    for (size_t i = 0; i < n; ++i)
+        b.centroid[i] = (b.verts[3 * i] + b.verts[3 * i + 1] + b.verts[3 * i + 2]) * (1.0 / 3.0);
+    b.boxes.reserve(2 * n);
+    b.link.reserve(2 * n);
+    b.boxes.resize(1);
+    b.link.resize(1);
+    b.build(0, 0, (int)n, 0);
+    out.depth = b.depth;
+
+    out.nodes.resize(b.boxes.size());
+    for (size_t i = 0; i < b.boxes.size(); ++i) {
+        const Box &bx = b.boxes[i];
+        BvhNode &nd = out.nodes[i];
+        const double c[3] = {bx.center.x, bx.center.y, bx.center.z};
+        // Rounding the axes and centre to FP32 moves the box by at most ~eps32*(|c| + |ext|);
+        // grow the half extents by a few times that so the FP32 box still contains the FP64 one.
+        double slack = 8.0 * FLT_EPSILON *
+                       (std::fabs(c[0]) + std::fabs(c[1]) + std::fabs(c[2]) + bx.ext[0] + bx.ext[1] + bx.ext[2]);
+        for (int k = 0; k < 3; ++k) {
+            nd.q[k][0] = (float)bx.axis[k].x;
+            nd.q[k][1] = (float)bx.axis[k].y;
+            nd.q[k][2] = (float)bx.axis[k].z;
+            nd.q[k][3] = (float)c[k];
+            nd.q[3][k] = roundUp(bx.ext[k] + slack);
+        }
+        int l = b.link[i];
+        std::memcpy(&nd.q[3][3], &l, sizeof(int));
+    }
+    return out;
+}
+
+}  // namespace mplb

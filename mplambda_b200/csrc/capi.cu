@@ -1,0 +1,449 @@
+// C-ABI of libmplb.so (declared in include/mplb.h): scene lifetime, host<->device staging,
+// per-call streams.  No CPU fallback: without a CUDA device every compute entry point fails.
+#include "../../include/mplb.h"
+#include "mplb_host.hpp"
+#include "se3_device.cuh"
+#include "scene_impl.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace mplb {
+
+thread_local std::string gLastError;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    gLastError = buf;
+    return code;
+}
+
+#define MPLB_CUDA(expr)                                                                             \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(MPLB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- device buffer that only grows
+int DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return MPLB_OK;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    size_t want = std::max(bytes, (size_t)4096);
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) return fail(MPLB_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    cap = want;
+    return MPLB_OK;
+}
+DevBuf::~DevBuf() {
+    if (ptr) cudaFree(ptr);
+}
+
+CallCtx::~CallCtx() {
+    if (hCtr) cudaFreeHost(hCtr);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+CallCtx *SceneBase::acquire() {
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (!freeCtx.empty()) {
+            CallCtx *c = freeCtx.back();
+            freeCtx.pop_back();
+            return c;
+        }
+    }
+    auto *c = new CallCtx();
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost((void **)&c->hCtr, sizeof(DevCounters)) != cudaSuccess ||
+        c->ctr.reserve(sizeof(DevCounters)) != MPLB_OK || c->work.reserve(64) != MPLB_OK) {
+        delete c;
+        return nullptr;
+    }
+    return c;
+}
+void SceneBase::release(CallCtx *c) {
+    std::lock_guard<std::mutex> g(mu);
+    freeCtx.push_back(c);
+}
+SceneBase::~SceneBase() {
+    for (auto *c : freeCtx) delete c;
+}
+
+namespace {
+
+int bitsFor(size_t n) {
+    int b = 1;
+    while (((size_t)1 << b) < n) ++b;
+    return b;
+}
+
+template <typename T>
+int upload(DevBuf &buf, const std::vector<T> &v) {
+    int rc = buf.reserve(v.size() * sizeof(T) + 16);
+    if (rc != MPLB_OK) return rc;
+    if (!v.empty()) MPLB_CUDA(cudaMemcpy(buf.ptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return MPLB_OK;
+}
+
+int selectDevice(int device, int *numSms) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(MPLB_ERR_CUDA, "no CUDA device available (%s); libmplb has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(MPLB_ERR_INVALID, "device %d out of range [0,%d)", device, count);
+    MPLB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MPLB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(MPLB_ERR_CUDA, "device %d is sm_%d%d; libmplb is built for sm_100a only", device, prop.major, prop.minor);
+    *numSms = prop.multiProcessorCount;
+    return MPLB_OK;
+}
+
+}  // namespace
+
+struct Se3Scene : SceneBase {
+    double so3w = 50, l2w = 1, invStep = 10;
+    SceneDev dev{};
+    DevBuf robotNodes, envNodes, robotTris, envTris, robotTris64, envTris64;
+    size_t nEnvTris = 0, nRobotTris = 0;
+
+    Se3Scene() { stateDim = 7; }
+
+    double distance(const double *a, const double *b) const {
+        // nigh SE3Space<S,so3w,l2w> [EXT]: so3w * acos(|qa . qb|) + l2w * ||ta - tb||
+        double d = std::fabs(((a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]) + a[3] * b[3]);
+        double so3 = d < 1.0 ? std::acos(d) : 0.0;
+        double dx = a[4] - b[4], dy = a[5] - b[5], dz = a[6] - b[6];
+        return so3w * so3 + l2w * std::sqrt((dx * dx + dy * dy) + dz * dz);
+    }
+    // se3_rigid_body_scenario.hpp:139
+    uint64_t edgeSteps(const double *a, const double *b) const {
+        return (uint64_t)std::ceil(distance(a, b) * invStep);
+    }
+};
+
+static int createSe3(const double *envTris, size_t nEnv, const double *robotTris, size_t nRobot, double so3w,
+                     double l2w, double res, int device, mplb_scene **out) {
+    if (!out) return fail(MPLB_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if ((nEnv && !envTris) || (nRobot && !robotTris)) return fail(MPLB_ERR_INVALID, "null triangle array");
+    if (!(res > 0)) return fail(MPLB_ERR_INVALID, "check_resolution must be > 0");
+    for (size_t i = 0; i < 9 * nEnv; ++i)
+        if (!std::isfinite(envTris[i])) return fail(MPLB_ERR_INVALID, "non-finite environment vertex");
+    for (size_t i = 0; i < 9 * nRobot; ++i)
+        if (!std::isfinite(robotTris[i])) return fail(MPLB_ERR_INVALID, "non-finite robot vertex");
+    int numSms = 0;
+    int rc = selectDevice(device, &numSms);
+    if (rc != MPLB_OK) return rc;
+
+    FlatBvh env = buildBvh(envTris, nEnv), robot = buildBvh(robotTris, nRobot);
+    auto sc = std::make_unique<Se3Scene>();
+    sc->device = device;
+    sc->numSms = numSms;
+    sc->so3w = so3w;
+    sc->l2w = l2w;
+    sc->invStep = 1 / res;
+    sc->nEnvTris = nEnv;
+    sc->nRobotTris = nRobot;
+    if ((rc = upload(sc->robotNodes, robot.nodes)) || (rc = upload(sc->envNodes, env.nodes)) ||
+        (rc = upload(sc->robotTris, robot.tris32)) || (rc = upload(sc->envTris, env.tris32)) ||
+        (rc = upload(sc->robotTris64, robot.tris64)) || (rc = upload(sc->envTris64, env.tris64)))
+        return rc;
+    if ((rc = sc->globalCtr.reserve(sizeof(DevCounters))) || (rc = sc->globalWork.reserve(64))) return rc;
+    MPLB_CUDA(cudaMemset(sc->globalCtr.ptr, 0, sizeof(DevCounters)));
+    SceneDev &d = sc->dev;
+    d.robotNodes = (const float4 *)sc->robotNodes.ptr;
+    d.envNodes = (const float4 *)sc->envNodes.ptr;
+    d.robotTris = (const float4 *)sc->robotTris.ptr;
+    d.envTris = (const float4 *)sc->envTris.ptr;
+    d.robotTris64 = (const double *)sc->robotTris64.ptr;
+    d.envTris64 = (const double *)sc->envTris64.ptr;
+    d.nRobotNodes = (int)robot.nodes.size();
+    d.nEnvNodes = (int)env.nodes.size();
+    d.bitsA = bitsFor(std::max<size_t>(2, robot.nodes.size()));
+    d.bitsB = bitsFor(std::max<size_t>(2, env.nodes.size()));
+    d.wide = (6 + d.bitsA + d.bitsB) > 32;
+    if (6 + d.bitsA + d.bitsB > 64) return fail(MPLB_ERR_INVALID, "meshes too large for the pair encoding");
+    // se3_kernels.cu: the pair LIFO throttles itself to depth-first order near its soft cap and
+    // then grows by at most one entry per hierarchy level
+    if (robot.depth + env.depth > 60)
+        return fail(MPLB_ERR_INVALID, "hierarchy too deep for the device pair stack (%d + %d levels)", robot.depth,
+                    env.depth);
+    d.envRadius = std::nextafterf((float)env.radius, INFINITY);
+    d.robotRadius = std::nextafterf((float)robot.radius, INFINITY);
+    sc->envNodeCount = env.nodes.size();
+    sc->robotNodeCount = robot.nodes.size();
+    *out = reinterpret_cast<mplb_scene *>(static_cast<SceneBase *>(sc.release()));
+    return MPLB_OK;
+}
+
+static int finishCall(SceneBase *sc, CallCtx *c, size_t checks, uint64_t *statesOut) {
+    cudaError_t e = cudaMemcpyAsync(c->hCtr, c->ctr.ptr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return fail(MPLB_ERR_CUDA, "device work failed: %s", cudaGetErrorString(e));
+    if (c->hCtr->overflow) return fail(MPLB_ERR_CUDA, "device pair stack overflow (hierarchy depth bound violated)");
+    sc->hBv += c->hCtr->bvTests;
+    sc->hTri += c->hCtr->triTests;
+    sc->hExact += c->hCtr->exactTests;
+    sc->hChecks += checks ? checks : c->hCtr->states;
+    if (statesOut) *statesOut = c->hCtr->states;
+    return MPLB_OK;
+}
+
+struct CtxGuard {
+    SceneBase *sc;
+    CallCtx *c;
+    ~CtxGuard() {
+        if (c) sc->release(c);
+    }
+};
+
+static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t *valid) {
+    MPLB_CUDA(cudaSetDevice(sc->device));
+    CallCtx *c = sc->acquire();
+    if (!c) return fail(MPLB_ERR_CUDA, "could not create a call context (stream / pinned memory)");
+    CtxGuard g{sc, c};
+    int rc;
+    if ((rc = c->in0.reserve(n * 7 * sizeof(double))) || (rc = c->out.reserve(n))) return rc;
+    MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(DevCounters), c->stream));
+    MPLB_CUDA(cudaMemcpyAsync(c->in0.ptr, states, n * 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    MPLB_CUDA(launchCheckStates(sc->dev, (const double *)c->in0.ptr, n, (uint8_t *)c->out.ptr,
+                                (DevCounters *)c->ctr.ptr, (unsigned *)c->work.ptr, sc->numSms, c->stream));
+    sc->hLaunches += 1;
+    MPLB_CUDA(cudaMemcpyAsync(valid, c->out.ptr, n, cudaMemcpyDeviceToHost, c->stream));
+    return finishCall(sc, c, n, nullptr);
+}
+
+static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, size_t n, uint8_t *valid,
+                         uint64_t *statesChecked) {
+    MPLB_CUDA(cudaSetDevice(sc->device));
+    CallCtx *c = sc->acquire();
+    if (!c) return fail(MPLB_ERR_CUDA, "could not create a call context (stream / pinned memory)");
+    CtxGuard g{sc, c};
+    c->hSteps.resize(n);
+    uint32_t maxSteps = 0;
+    for (size_t i = 0; i < n; ++i) {
+        uint64_t s = sc->edgeSteps(from + 7 * i, to + 7 * i);
+        if (!(s < (1ull << 31)))
+            return fail(MPLB_ERR_INVALID, "edge %zu needs %llu interpolation steps (limit 2^31); non-finite state?", i,
+                        (unsigned long long)s);
+        c->hSteps[i] = (uint32_t)s;
+        maxSteps = std::max(maxSteps, (uint32_t)s);
+    }
+    int rc;
+    const size_t sb = n * 7 * sizeof(double);
+    if ((rc = c->in0.reserve(sb)) || (rc = c->in1.reserve(sb)) || (rc = c->steps.reserve(n * 4)) ||
+        (rc = c->dead.reserve(n * 4)) || (rc = c->out.reserve(n)))
+        return rc;
+    MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(DevCounters), c->stream));
+    MPLB_CUDA(cudaMemcpyAsync(c->in0.ptr, from, sb, cudaMemcpyHostToDevice, c->stream));
+    MPLB_CUDA(cudaMemcpyAsync(c->in1.ptr, to, sb, cudaMemcpyHostToDevice, c->stream));
+    MPLB_CUDA(cudaMemcpyAsync(c->steps.ptr, c->hSteps.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+    MPLB_CUDA(launchCheckEdges(sc->dev, (const double *)c->in0.ptr, (const double *)c->in1.ptr,
+                               (const unsigned *)c->steps.ptr, n, maxSteps, (unsigned *)c->dead.ptr,
+                               (uint8_t *)c->out.ptr, (DevCounters *)c->ctr.ptr, (unsigned long long *)c->work.ptr,
+                               sc->numSms, c->stream));
+    sc->hLaunches += 2;
+    MPLB_CUDA(cudaMemcpyAsync(valid, c->out.ptr, n, cudaMemcpyDeviceToHost, c->stream));
+    return finishCall(sc, c, 0, statesChecked);
+}
+
+}  // namespace mplb
+
+using namespace mplb;
+
+static SceneBase *base(mplb_scene *s) { return reinterpret_cast<SceneBase *>(s); }
+static const SceneBase *base(const mplb_scene *s) { return reinterpret_cast<const SceneBase *>(s); }
+
+extern "C" {
+
+const char *mplb_last_error(void) { return gLastError.c_str(); }
+
+int mplb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void mplb_free(void *p) { std::free(p); }
+
+int mplb_mesh_load_collada(const char *path, int shift_to_center, int identity_root_transform, double **tris,
+                           size_t *ntris, double center[3]) {
+    if (!path || !tris || !ntris) return fail(MPLB_ERR_INVALID, "null argument");
+    *tris = nullptr;
+    *ntris = 0;
+    try {
+        TriangleSoup s = loadCollada(path, shift_to_center != 0, identity_root_transform != 0);
+        double *buf = (double *)std::malloc(std::max<size_t>(1, s.tris.size()) * sizeof(double));
+        if (!buf) return fail(MPLB_ERR_NOMEM, "out of memory");
+        std::memcpy(buf, s.tris.data(), s.tris.size() * sizeof(double));
+        *tris = buf;
+        *ntris = s.size();
+        if (center) std::memcpy(center, s.center, sizeof(s.center));
+        return MPLB_OK;
+    } catch (const std::invalid_argument &e) {
+        return fail(MPLB_ERR_IO, "%s", e.what());
+    } catch (const std::exception &e) {
+        return fail(MPLB_ERR_IO, "%s", e.what());
+    }
+}
+
+int mplb_scene_create_se3(const double *env_tris, size_t n_env, const double *robot_tris, size_t n_robot,
+                          double so3_weight, double l2_weight, double check_resolution, int device,
+                          mplb_scene **out) {
+    try {
+        return createSe3(env_tris, n_env, robot_tris, n_robot, so3_weight, l2_weight, check_resolution, device, out);
+    } catch (const std::exception &e) {
+        return fail(MPLB_ERR_INVALID, "%s", e.what());
+    }
+}
+
+int mplb_scene_create_se3_files(const char *env_path, const char *robot_path, double so3_weight, double l2_weight,
+                                double check_resolution, int device, mplb_scene **out) {
+    if (!env_path || !robot_path) return fail(MPLB_ERR_INVALID, "null path");
+    try {
+        // se3_rigid_body_scenario.hpp:58-59: env load(false,false), robot load(true,false)
+        TriangleSoup env = loadCollada(env_path, false, false);
+        TriangleSoup robot = loadCollada(robot_path, true, false);
+        return createSe3(env.tris.data(), env.size(), robot.tris.data(), robot.size(), so3_weight, l2_weight,
+                         check_resolution, device, out);
+    } catch (const std::invalid_argument &e) {
+        return fail(MPLB_ERR_IO, "%s", e.what());
+    } catch (const std::exception &e) {
+        return fail(MPLB_ERR_INVALID, "%s", e.what());
+    }
+}
+
+void mplb_scene_destroy(mplb_scene *scene) {
+    if (!scene) return;
+    SceneBase *b = base(scene);
+    cudaSetDevice(b->device);
+    cudaDeviceSynchronize();
+    delete b;
+}
+
+int mplb_scene_state_dim(const mplb_scene *scene) { return scene ? base(scene)->stateDim : 0; }
+
+int mplb_check_states(mplb_scene *scene, const double *states, size_t n, uint8_t *valid) {
+    if (!scene) return fail(MPLB_ERR_INVALID, "scene is null");
+    if (n == 0) return MPLB_OK;
+    if (!states || !valid) return fail(MPLB_ERR_INVALID, "null buffer");
+    if (auto *s = dynamic_cast<Se3Scene *>(base(scene))) return se3CheckStates(s, states, n, valid);
+    return fail(MPLB_ERR_INVALID, "unsupported scene kind");
+}
+
+int mplb_check_edges(mplb_scene *scene, const double *from, const double *to, size_t n, uint8_t *valid,
+                     uint64_t *states_checked) {
+    if (!scene) return fail(MPLB_ERR_INVALID, "scene is null");
+    if (states_checked) *states_checked = 0;
+    if (n == 0) return MPLB_OK;
+    if (!from || !to || !valid) return fail(MPLB_ERR_INVALID, "null buffer");
+    if (auto *s = dynamic_cast<Se3Scene *>(base(scene))) return se3CheckEdges(s, from, to, n, valid, states_checked);
+    return fail(MPLB_ERR_INVALID, "unsupported scene kind");
+}
+
+int mplb_check_states_device(mplb_scene *scene, const double *d_states, size_t n, uint8_t *d_valid, void *stream) {
+    if (!scene) return fail(MPLB_ERR_INVALID, "scene is null");
+    if (n == 0) return MPLB_OK;
+    if (!d_states || !d_valid) return fail(MPLB_ERR_INVALID, "null buffer");
+    auto *s = dynamic_cast<Se3Scene *>(base(scene));
+    if (!s) return fail(MPLB_ERR_INVALID, "unsupported scene kind");
+    MPLB_CUDA(cudaSetDevice(s->device));
+    MPLB_CUDA(launchCheckStates(s->dev, d_states, n, d_valid, (DevCounters *)s->globalCtr.ptr,
+                                (unsigned *)s->globalWork.ptr, s->numSms, (cudaStream_t)stream));
+    s->hLaunches += 1;
+    s->hChecks += n;
+    return MPLB_OK;
+}
+
+int mplb_edges_plan(mplb_scene *scene, const double *from, const double *to, size_t n, uint32_t *steps) {
+    if (!scene) return fail(MPLB_ERR_INVALID, "scene is null");
+    if (n == 0) return MPLB_OK;
+    if (!from || !to || !steps) return fail(MPLB_ERR_INVALID, "null buffer");
+    auto *s = dynamic_cast<Se3Scene *>(base(scene));
+    if (!s) return fail(MPLB_ERR_INVALID, "unsupported scene kind");
+    for (size_t i = 0; i < n; ++i) {
+        uint64_t st = s->edgeSteps(from + 7 * i, to + 7 * i);
+        if (!(st < (1ull << 31))) return fail(MPLB_ERR_INVALID, "edge %zu: step count out of range", i);
+        steps[i] = (uint32_t)st;
+    }
+    return MPLB_OK;
+}
+
+int mplb_check_edges_device(mplb_scene *scene, const double *d_from, const double *d_to, const uint32_t *d_steps,
+                            size_t n, uint32_t max_steps, uint8_t *d_valid, void *stream) {
+    if (!scene) return fail(MPLB_ERR_INVALID, "scene is null");
+    if (n == 0) return MPLB_OK;
+    if (!d_from || !d_to || !d_steps || !d_valid) return fail(MPLB_ERR_INVALID, "null buffer");
+    auto *s = dynamic_cast<Se3Scene *>(base(scene));
+    if (!s) return fail(MPLB_ERR_INVALID, "unsupported scene kind");
+    MPLB_CUDA(cudaSetDevice(s->device));
+    {
+        // the dead-flag scratch is shared by device-side callers: serialise their use of it
+        std::lock_guard<std::mutex> g(s->mu);
+        int rc = s->globalDead.reserve(n * 4);
+        if (rc != MPLB_OK) return rc;
+    }
+    MPLB_CUDA(launchCheckEdges(s->dev, d_from, d_to, d_steps, n, max_steps, (unsigned *)s->globalDead.ptr, d_valid,
+                               (DevCounters *)s->globalCtr.ptr, (unsigned long long *)s->globalWork.ptr, s->numSms,
+                               (cudaStream_t)stream));
+    s->hLaunches += 2;
+    return MPLB_OK;
+}
+
+double mplb_distance(const mplb_scene *scene, const double *a, const double *b) {
+    if (!scene || !a || !b) return NAN;
+    if (auto *s = dynamic_cast<const Se3Scene *>(base(scene))) return s->distance(a, b);
+    return NAN;
+}
+
+int mplb_scene_stats(mplb_scene *scene, mplb_stats_t *out, int reset) {
+    if (!scene || !out) return fail(MPLB_ERR_INVALID, "null argument");
+    SceneBase *b = base(scene);
+    MPLB_CUDA(cudaSetDevice(b->device));
+    MPLB_CUDA(cudaDeviceSynchronize());
+    DevCounters g{};
+    MPLB_CUDA(cudaMemcpy(&g, b->globalCtr.ptr, sizeof(g), cudaMemcpyDeviceToHost));
+    if (g.overflow) return fail(MPLB_ERR_CUDA, "device pair stack overflow (hierarchy depth bound violated)");
+    std::memset(out, 0, sizeof(*out));
+    out->checks = b->hChecks + g.states;
+    out->bv_tests = b->hBv + g.bvTests;
+    out->tri_tests = b->hTri + g.triTests;
+    out->exact_tests = b->hExact + g.exactTests;
+    out->launches = b->hLaunches;
+    out->env_nodes = b->envNodeCount;
+    out->robot_nodes = b->robotNodeCount;
+    if (auto *s = dynamic_cast<Se3Scene *>(b)) {
+        out->env_tris = s->nEnvTris;
+        out->robot_tris = s->nRobotTris;
+    }
+    if (reset) {
+        MPLB_CUDA(cudaMemset(b->globalCtr.ptr, 0, sizeof(DevCounters)));
+        b->hChecks = b->hBv = b->hTri = b->hExact = b->hLaunches = 0;
+    }
+    return MPLB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,36 @@
+// Device-side scene description and launch entry points shared by the C-ABI and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace mplb {
+
+// Flat, immutable, HBM-resident scene (built once on the host by bvh_build.cpp).
+struct SceneDev {
+    const float4 *robotNodes;   // 4 x float4 per node (mplb_host.hpp: BvhNode)
+    const float4 *envNodes;
+    const float4 *robotTris;    // 3 x float4 per triangle (FP32 filter copy)
+    const float4 *envTris;
+    const double *robotTris64;  // 9 doubles per triangle (exact re-evaluation)
+    const double *envTris64;
+    int nRobotNodes, nEnvNodes;
+    int bitsA, bitsB;           // bits needed for a robot / env node index
+    int wide;                   // 1: pair entries need 64 bits
+    float envRadius;            // max |vertex| of the environment
+    float robotRadius;          // max |vertex| of the (centred) robot
+};
+
+struct DevCounters {
+    unsigned long long bvTests, triTests, exactTests, states;
+    unsigned overflow, pad;
+};
+
+cudaError_t launchCheckStates(const SceneDev &sc, const double *dStates, size_t n, uint8_t *dValid,
+                              DevCounters *dCtr, unsigned *dWork, int numSms, cudaStream_t stream);
+
+cudaError_t launchCheckEdges(const SceneDev &sc, const double *dFrom, const double *dTo, const unsigned *dSteps,
+                             size_t n, unsigned maxSteps, unsigned *dDead, uint8_t *dValid, DevCounters *dCtr,
+                             unsigned long long *dWork, int numSms, cudaStream_t stream);
+
+}  // namespace mplb

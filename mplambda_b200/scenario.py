@@ -1,0 +1,176 @@
+"""Host-side mirror of the reference's scenario interface over the C ABI.
+
+`SE3RigidBodyScenario` keeps the names, argument meaning and error behaviour of
+`mpl::demo::SE3RigidBodyScenario<S,50,1>` (reference include/mpl/demo/se3_rigid_body_scenario.hpp:15-179)
+so that planner code written against the Scenario concept (prrt.hpp:52-76, pcforest.hpp:80-104)
+reads the same; the batched methods (`check_states`, `check_edges`) are what the hot path adds
+underneath the unchanged one-at-a-time calls.  All validity work happens in libmplb.so on the
+GPU; nothing here computes a verdict.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _capi
+
+
+def load_collada(path, shift_to_center=False, identity_root_transform=False):
+    """MeshLoad::load (load_mesh.hpp:232-293) -> (triangles float64 [n,3,3], centre [3])."""
+    L = _capi.lib()
+    ptr = _capi.dp()
+    n = C.c_size_t()
+    center = (C.c_double * 3)()
+    _capi.check(L.mplb_mesh_load_collada(str(path).encode(), int(shift_to_center), int(identity_root_transform),
+                                         C.byref(ptr), C.byref(n), center))
+    try:
+        tris = np.ctypeslib.as_array(ptr, shape=(n.value * 9,)).copy().reshape(-1, 3, 3)
+    finally:
+        L.mplb_free(ptr)
+    return tris, np.array(center[:])
+
+
+def _f64(a, cols):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if a.ndim == 1:
+        a = a.reshape(1, -1)
+    if a.ndim != 2 or a.shape[1] != cols:
+        raise ValueError("expected [n,%d] states, got %s" % (cols, a.shape))
+    return a
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class SE3Space:
+    """nigh::SE3Space<S, so3weight, l2weight> distance (se3_rigid_body_scenario.hpp:18)."""
+
+    def __init__(self, scenario):
+        self._sc = scenario
+
+    def distance(self, a, b):
+        a, b = _f64(a, 7), _f64(b, 7)
+        return _capi.lib().mplb_distance(self._sc._h, a.ctypes.data_as(_capi.dp), b.ctypes.data_as(_capi.dp))
+
+    @staticmethod
+    def dimensions():
+        return 6
+
+
+class SE3RigidBodyScenario:
+    """State = (qx,qy,qz,qw,tx,ty,tz) float64, the Eigen coefficient order of
+    std::tuple<Quaterniond, Vector3d> (se3...:18-19)."""
+
+    multiGoal = True  # se3...:88
+
+    def __init__(self, envMesh, robotMesh, goal, min, max, checkResolution=0.1, so3weight=50.0, l2weight=1.0,
+                 device=0):
+        L = _capi.lib()
+        self._h = C.c_void_p()
+        self.goal_ = np.asarray(goal, dtype=np.float64).reshape(7)
+        self.min_ = np.asarray(min, dtype=np.float64).reshape(3)
+        self.max_ = np.asarray(max, dtype=np.float64).reshape(3)
+        self.goalRadius_ = 0.1  # se3...:39
+        self.invStepSize_ = 1.0 / checkResolution  # se3...:63
+        self.device = device
+        if isinstance(envMesh, (str, bytes)) or hasattr(envMesh, "__fspath__"):
+            rc = L.mplb_scene_create_se3_files(str(envMesh).encode(), str(robotMesh).encode(), so3weight, l2weight,
+                                               checkResolution, device, C.byref(self._h))
+        else:
+            env = np.ascontiguousarray(envMesh, dtype=np.float64).reshape(-1, 3, 3)
+            rob = np.ascontiguousarray(robotMesh, dtype=np.float64).reshape(-1, 3, 3)
+            rc = L.mplb_scene_create_se3(env.ctypes.data_as(_capi.dp), len(env), rob.ctypes.data_as(_capi.dp),
+                                         len(rob), so3weight, l2weight, checkResolution, device, C.byref(self._h))
+        if rc in (_capi.ERR_IO, _capi.ERR_INVALID):
+            # load_mesh.hpp:250-254 throws std::invalid_argument
+            raise ValueError(L.mplb_last_error().decode("utf-8", "replace"))
+        _capi.check(rc)
+        self._space = SE3Space(self)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            _capi.lib().mplb_scene_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- the Scenario concept ---------------------------------------------------------------
+    @staticmethod
+    def scale(q):
+        return q  # se3...:90-92
+
+    def space(self):
+        return self._space
+
+    @staticmethod
+    def maxSteering():
+        return math.inf  # se3...:98-100
+
+    def sampleGoal(self, rng=None):
+        return self.goal_.copy()  # se3...:102-105
+
+    def randomSample(self, rng):
+        """se3...:107-113 with randomize.hpp:12-38; rng is a numpy Generator."""
+        a, b, c = rng.uniform(0, 1), rng.uniform(0, 2 * math.pi), rng.uniform(0, 2 * math.pi)
+        q = np.empty(7)
+        q[0] = math.sqrt(1 - a) * math.sin(b)
+        q[1] = math.sqrt(1 - a) * math.cos(b)
+        q[2] = math.sqrt(a) * math.sin(c)
+        q[3] = math.sqrt(a) * math.cos(c)
+        for i in range(3):
+            q[4 + i] = rng.uniform(self.min_[i], self.max_[i])
+        return q
+
+    def isGoal(self, q):
+        return self._space.distance(self.goal_, q) <= self.goalRadius_  # se3...:115-117
+
+    def isValid(self, q, to=None):
+        """isValid(q) (se3...:119-126) or isValid(from, to) (se3...:134-178)."""
+        if to is None:
+            return bool(self.check_states(q)[0])
+        return bool(self.check_edges(q, to)[0])
+
+    # ---- batched entry points (what the GPU path adds) ---------------------------------------
+    def check_states(self, states):
+        s = _f64(states, 7)
+        out = np.empty(len(s), dtype=np.uint8)
+        _capi.check(_capi.lib().mplb_check_states(self._h, _ptr(s), len(s), _ptr(out)))
+        return out.astype(bool)
+
+    def check_edges(self, frm, to, return_states_checked=False):
+        a, b = _f64(frm, 7), _f64(to, 7)
+        if a.shape != b.shape:
+            raise ValueError("from/to shape mismatch")
+        out = np.empty(len(a), dtype=np.uint8)
+        checked = C.c_uint64()
+        _capi.check(_capi.lib().mplb_check_edges(self._h, _ptr(a), _ptr(b), len(a), _ptr(out), C.byref(checked)))
+        if return_states_checked:
+            return out.astype(bool), checked.value
+        return out.astype(bool)
+
+    def edge_steps(self, frm, to):
+        a, b = _f64(frm, 7), _f64(to, 7)
+        steps = np.empty(len(a), dtype=np.uint32)
+        _capi.check(_capi.lib().mplb_edges_plan(self._h, _ptr(a), _ptr(b), len(a), _ptr(steps)))
+        return steps
+
+    # raw-pointer variants for device-resident batches (pointers from torch tensors' data_ptr())
+    def check_states_ptr(self, host_states_ptr, n, host_valid_ptr):
+        _capi.check(_capi.lib().mplb_check_states(self._h, host_states_ptr, n, host_valid_ptr))
+
+    def check_states_device(self, d_states_ptr, n, d_valid_ptr, stream=0):
+        _capi.check(_capi.lib().mplb_check_states_device(self._h, d_states_ptr, n, d_valid_ptr, stream))
+
+    def check_edges_device(self, d_from, d_to, d_steps, n, max_steps, d_valid, stream=0):
+        _capi.check(_capi.lib().mplb_check_edges_device(self._h, d_from, d_to, d_steps, n, int(max_steps), d_valid,
+                                                        stream))
+
+    def stats(self, reset=False):
+        st = _capi.Stats()
+        _capi.check(_capi.lib().mplb_scene_stats(self._h, C.byref(st), int(reset)))
+        return st.as_dict()

@@ -1,0 +1,147 @@
+"""GPU: CUDA path (through the C ABI) vs the FP64 oracle on the same seeded inputs.
+Bar: bit-exact verdicts (the device resolves every uncertain FP32 triangle test in FP64 with
+the oracle's operation order, so there is no epsilon band to excuse)."""
+import os
+
+import numpy as np
+import pytest
+
+import mplambda_b200 as M
+from mplambda_b200.workload import SE3_SCENES, SEED, se3_poses
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def make(scenes, name, res=0.1):
+    env, robot = scenes[name]
+    sc = SE3_SCENES[name]
+    return M.SE3RigidBodyScenario(env, robot, sc["goal"], sc["min"], sc["max"], res)
+
+
+@pytest.mark.parametrize("name", ["twistycool", "cubicles", "home", "alpha15"])
+def test_known_answers(name, scenes, golden):
+    s = make(scenes, name)
+    want = golden[name + "_valid"]
+    P = se3_poses(len(want), SE3_SCENES[name]["min"], SE3_SCENES[name]["max"], SEED)
+    got = s.check_states(P)
+    assert (got == want).all(), "mismatches at %s" % np.nonzero(got != want)[0][:10]
+    # single-state calls (the reference's isValid(q)) agree with the batch
+    for i in range(0, 64, 7):
+        assert s.isValid(P[i]) == bool(want[i])
+
+
+@pytest.mark.parametrize("name,n", [("twistycool", 200000), ("cubicles", 100000), ("home", 100000),
+                                    ("alpha15", 100000), ("apartment", 20000)])
+def test_states_match_oracle(name, n, scenes, oracle):
+    env, robot = scenes[name]
+    sc = SE3_SCENES[name]
+    s = make(scenes, name)
+    P = se3_poses(n, sc["min"], sc["max"], SEED + 11)
+    got = s.check_states(P)
+    want = oracle.SE3Oracle(env, robot).check_states(P, oracle.BVH)
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, "%d/%d verdicts differ, first %s" % (len(bad), n, bad[:10])
+    st = s.stats()
+    assert st["checks"] == n and st["bv_tests"] > 0
+
+
+def test_scripted_states_and_reference_paths(scenes):
+    for name, sc in SE3_SCENES.items():
+        s = make(scenes, name)
+        assert s.isValid(sc["start"]) and s.isValid(sc["goal"]), name
+    s = make(scenes, "twistycool")
+    paths = np.load(os.path.join(GOLDEN, "paths.npz"))
+    for k in paths.files:
+        w = paths[k]
+        assert s.check_states(w).all()
+        assert s.check_edges(w[:-1], w[1:]).all()
+        assert all(s.isValid(a, b) for a, b in zip(w[:-1], w[1:]))
+
+
+@pytest.mark.parametrize("name", ["twistycool", "cubicles", "home"])
+def test_edges_known_answers(name, scenes, golden):
+    s = make(scenes, name)
+    A, B = golden[name + "_edge_from"], golden[name + "_edge_to"]
+    assert (s.edge_steps(A, B) == golden[name + "_edge_steps"]).all()
+    got, checked = s.check_edges(A, B, return_states_checked=True)
+    assert (got == golden[name + "_edge_valid"]).all()
+    assert 0 < checked <= int(golden[name + "_edge_steps"].astype(np.int64).sum()) + len(A)
+
+
+@pytest.mark.parametrize("name,n", [("twistycool", 3000), ("cubicles", 1500), ("alpha15", 1500)])
+def test_edges_match_oracle(name, n, scenes, oracle):
+    env, robot = scenes[name]
+    sc = SE3_SCENES[name]
+    s = make(scenes, name)
+    orc = oracle.SE3Oracle(env, robot, check_resolution=0.1)
+    A = se3_poses(3 * n, sc["min"], sc["max"], SEED + 21)
+    A = A[s.check_states(A)][:n]
+    B = se3_poses(len(A), sc["min"], sc["max"], SEED + 22)
+    for i in range(0, len(A), 2):     # half short hops so that many edges are fully valid
+        B[i] = orc.interpolate(A[i], B[i], 0.003)
+    got = s.check_edges(A, B)
+    want = orc.check_edges(A, B, oracle.BVH)
+    assert (got == want).all(), np.nonzero(got != want)[0][:10]
+    assert 0.05 < want.mean() < 0.95
+    # edge verdict == valid(to) AND all interpolated states (order independence)
+    steps = s.edge_steps(A, B)
+    for i in np.nonzero(want)[0][:5]:
+        ts = np.arange(1, steps[i]) / float(steps[i])
+        states = np.array([orc.interpolate(A[i], B[i], t) for t in ts] + [B[i]])
+        assert s.check_states(states).all()
+
+
+def test_edge_cases(scenes):
+    tri = np.array([[[0, 0, 0], [1, 0, 0], [0, 1, 0.0]]])
+    ident = [0, 0, 0, 1, 0, 0, 0.0]
+    s = M.SE3RigidBodyScenario(tri, tri, ident, [0, 0, 0], [1, 1, 1], 0.1)
+    q = np.array([ident, [0, 0, 0, 1, 1.0, 0, 0], [0, 0, 0, 1, 1.0 + 1e-9, 0, 0], [0, 0, 0, 1, 5.0, 0, 0]])
+    assert s.check_states(q).tolist() == [False, False, True, True]   # touching counts as collision
+    assert s.check_states(np.zeros((0, 7))).shape == (0,)
+    assert s.check_edges(np.zeros((0, 7)), np.zeros((0, 7))).shape == (0,)
+    # from == to: steps == 0, only `to` is checked
+    assert s.isValid(q[3], q[3]) and not s.isValid(q[0], q[0])
+    # an edge that sweeps through the obstacle is invalid although both ends are valid
+    a = np.array([0, 0, 0, 1, -3.0, 0.2, 0.0]); b = np.array([0, 0, 0, 1, 3.0, 0.2, 0.0])
+    assert s.isValid(a) and s.isValid(b) and not s.isValid(a, b)
+    # empty environment: everything is valid
+    e = M.SE3RigidBodyScenario(np.zeros((0, 3, 3)), tri, ident, [0, 0, 0], [1, 1, 1], 0.1)
+    assert e.check_states(q).all() and e.isValid(a, b)
+    # ragged batch sizes around the 64-state chunk
+    env, robot = scenes["twistycool"]
+    t = M.SE3RigidBodyScenario(env, robot, ident, [0, 0, 0], [1, 1, 1], 0.1)
+    P = se3_poses(200, SE3_SCENES["twistycool"]["min"], SE3_SCENES["twistycool"]["max"], 99)
+    full = t.check_states(P)
+    for n in (1, 2, 31, 32, 33, 63, 64, 65, 127, 129):
+        assert (t.check_states(P[:n]) == full[:n]).all()
+
+
+def test_concurrent_callers(scenes, golden):
+    import threading
+    s = make(scenes, "twistycool")
+    want = golden["twistycool_valid"]
+    P = se3_poses(len(want), SE3_SCENES["twistycool"]["min"], SE3_SCENES["twistycool"]["max"], SEED)
+    errs = []
+
+    def work(k):
+        for r in range(20):
+            lo = (k * 37 + r * 101) % 3000
+            if not (s.check_states(P[lo:lo + 500]) == want[lo:lo + 500]).all():
+                errs.append((k, r))
+    th = [threading.Thread(target=work, args=(k,)) for k in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs
+
+
+def test_device_resident_batch(scenes, golden):
+    import torch
+    s = make(scenes, "twistycool")
+    want = golden["twistycool_valid"]
+    P = se3_poses(len(want), SE3_SCENES["twistycool"]["min"], SE3_SCENES["twistycool"]["max"], SEED)
+    d = torch.from_numpy(P).cuda()
+    out = torch.empty(len(P), dtype=torch.uint8, device="cuda")
+    s.check_states_device(d.data_ptr(), len(P), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert (out.cpu().numpy().astype(bool) == want).all()
