@@ -162,8 +162,10 @@ FlatBvh buildBvh(const double *tris, size_t n) {
     for (size_t i = 0; i < n; ++i)
         for (int k = 0; k < 3; ++k) {
             for (int d = 0; d < 3; ++d) {
+                // vertex 0 as is, vertices 1 and 2 as FP64 differences to vertex 0 (edge vectors):
+                // the device filter then only pays the big-cancellation error once per pair
                 double v = tris[9 * i + 3 * k + d];
-                out.tris32[i].v[k][d] = (float)v;
+                out.tris32[i].v[k][d] = (float)(k == 0 ? v : v - tris[9 * i + d]);
                 out.absMax = std::max(out.absMax, std::fabs(v));
             }
             out.tris32[i].v[k][3] = 0.f;

@@ -25,7 +25,8 @@ struct alignas(16) BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "node must be 64 bytes");
 
-// One triangle for the FP32 filter: 48 bytes = 3 x float4 (xyz + pad).
+// One triangle for the FP32 filter: 48 bytes = 3 x float4 (xyz + pad):
+//   v[0] = vertex 0, v[1] = vertex 1 - vertex 0, v[2] = vertex 2 - vertex 0 (differences formed in FP64).
 struct alignas(16) TriF32 {
     float v[3][4];
 };

@@ -47,14 +47,7 @@ struct WarpSmem {
     E stack[kStackCap];
     E triq[kQueueCap];
     E exq[kQueueCap];
-    float4 xf[kChunk][4];  // R rows + T in .w of rows? see storeSlot
-};
-
-struct Slot {
-    float r[9];
-    float t[3];
-    float slack;  // OBB test slack
-    float eta;    // absolute error bound of FP32 relative coordinates
+    float4 xf[kChunk][4];  // per slot: rows of (R | T), then (slack, eta, -, -); see makeSlot
 };
 
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
@@ -246,49 +239,59 @@ __device__ __forceinline__ bool obbOverlap(const float4 a0, const float4 a1, con
 enum TriVerdict : int { kTriNo = 0, kTriYes = 1, kTriUnsure = 2 };
 
 struct AxisState {
-    bool sep;     // some axis separates beyond the error bound -> certainly disjoint
-    bool unsure;  // some axis is within the error bound of separating
+    bool sep;     // some axis separates beyond its error bound -> certainly disjoint
+    bool unsure;  // some axis is within its error bound of separating
 };
 
-__device__ __forceinline__ void axisTest(F3 ax, F3 p2, F3 p3, F3 q1, F3 q2, F3 q3, float E, AxisState &st) {
+__device__ __forceinline__ float absMax(F3 a) { return fmaxf(fabsf(a.x), fmaxf(fabsf(a.y), fabsf(a.z))); }
+
+// One separating axis.  E = |ax|_1 * S + K bounds |gap32 - gap64| (see triTriFilter).
+__device__ __forceinline__ void axisTest(F3 ax, F3 p2, F3 p3, F3 q1, F3 q2, F3 q3, float S, float K, AxisState &st) {
     // p1 is the origin of the relative frame: its projection is exactly 0
-    float P2 = dot(ax, p2), P3 = dot(ax, p3);
-    float Q1 = dot(ax, q1), Q2 = dot(ax, q2), Q3 = dot(ax, q3);
-    float mx1 = fmaxf(0.f, fmaxf(P2, P3)), mn1 = fminf(0.f, fminf(P2, P3));
-    float mx2 = fmaxf(Q1, fmaxf(Q2, Q3)), mn2 = fminf(Q1, fminf(Q2, Q3));
-    float g = fmaxf(mn1 - mx2, mn2 - mx1);  // > 0 <=> this axis separates
+    const float P2 = dot(ax, p2), P3 = dot(ax, p3);
+    const float Q1 = dot(ax, q1), Q2 = dot(ax, q2), Q3 = dot(ax, q3);
+    const float mx1 = fmaxf(0.f, fmaxf(P2, P3)), mn1 = fminf(0.f, fminf(P2, P3));
+    const float mx2 = fmaxf(Q1, fmaxf(Q2, Q3)), mn2 = fminf(Q1, fminf(Q2, Q3));
+    const float g = fmaxf(mn1 - mx2, mn2 - mx1);  // > 0 <=> this axis separates
+    const float E = fmaf(fabsf(ax.x) + fabsf(ax.y) + fabsf(ax.z), S, K);
     st.sep |= g > E;
     st.unsure |= g >= -E;
 }
 
-// Error-bounded FP32 version of the 17-axis test.  With U = max |relative coordinate| and eta
-// the absolute error of those coordinates, the FP32 gap of an axis differs from the FP64 one by
-// at most Ea (axes that are one cross product: n1, m1, e x f) or Eg (two cross products:
-// e x n1, f x m1); see DESIGN.md "FP32 filter".  Certain answers need no FP64 work.
-__device__ __forceinline__ int triTriFilter(F3 P1, F3 P2, F3 P3, F3 Q1, F3 Q2, F3 Q3, float eta) {
-    F3 p2 = P2 - P1, p3 = P3 - P1, q1 = Q1 - P1, q2 = Q2 - P1, q3 = Q3 - P1;
-    float U = fmaxf(fmaxf(fmaxf(fabsf(p2.x), fabsf(p2.y)), fmaxf(fabsf(p2.z), fabsf(p3.x))),
-                    fmaxf(fabsf(p3.y), fabsf(p3.z)));
-    U = fmaxf(U, fmaxf(fmaxf(fabsf(q1.x), fabsf(q1.y)), fabsf(q1.z)));
-    U = fmaxf(U, fmaxf(fmaxf(fabsf(q2.x), fabsf(q2.y)), fabsf(q2.z)));
-    U = fmaxf(U, fmaxf(fmaxf(fabsf(q3.x), fabsf(q3.y)), fabsf(q3.z)));
-    const float u2 = U * U;
-    const float Ea = u2 * fmaf(480.f * FLT_EPSILON, U, 144.f * eta);
-    const float Eg = u2 * U * fmaf(2688.f * FLT_EPSILON, U, 768.f * eta);
-    F3 e[3] = {p2, p3 - p2, f3(-p3.x, -p3.y, -p3.z)};
-    F3 f[3] = {q2 - q1, q3 - q2, q1 - q3};
-    F3 n1 = cross(e[0], e[1]), m1 = cross(f[0], f[1]);
+// Error-bounded FP32 version of the 17-axis test (FCL axis order).  Inputs: robot triangle as
+// (P1, p2 = P2-P1, p3 = P3-P1) and environment triangle as (Q1, F1 = Q2-Q1, F2 = Q3-Q1), the
+// differences formed in FP64 on the host, so that only q1 = R*Q1 + T - P1 carries the large
+// cancellation error eta; edge vectors only carry relative rounding.  With
+//   Me, Mf = max |component| of the robot / environment edge vectors, U = max |relative coord|,
+// the FP32 gap of an axis differs from the FP64 specification's gap by at most
+//   E = |ax|_1 * (eta + 79 eps U) + 6 U * (abs. error of the axis components)
+// where the axis error is 20 eps Me^2 (n1), 132 eps Mf^2 (m1), 76 eps Me Mf (e x f),
+// 64 eps Me^3 (e x n1), 400 eps Mf^3 (f x m1); derivation in DESIGN.md "FP32 filter", numerical
+// check in tests/test_filter_bound.py.  eps = FLT_EPSILON = 2 * unit roundoff (2x safety).
+// Certain answers need no FP64 work; kTriUnsure pairs are re-evaluated exactly.
+__device__ __forceinline__ int triTriFilter(F3 p2, F3 p3, F3 q1, F3 f1, F3 f2, float eta) {
+    const F3 q2 = f3(q1.x + f1.x, q1.y + f1.y, q1.z + f1.z), q3 = f3(q1.x + f2.x, q1.y + f2.y, q1.z + f2.z);
+    const F3 e[3] = {p2, p3 - p2, f3(-p3.x, -p3.y, -p3.z)};
+    const F3 f[3] = {f1, f2 - f1, f3(-f2.x, -f2.y, -f2.z)};
+    const float Me = fmaxf(absMax(e[0]), fmaxf(absMax(e[1]), absMax(e[2])));
+    const float Mf = fmaxf(absMax(f[0]), fmaxf(absMax(f[1]), absMax(f[2])));
+    const float U = fmaxf(fmaxf(fmaxf(absMax(p2), absMax(p3)), fmaxf(absMax(q1), absMax(q2))), absMax(q3));
+    const float S = fmaf(79.f * FLT_EPSILON, U, eta);
+    const float eu = FLT_EPSILON * U;
+    const float Kn = 120.f * eu * Me * Me, Km = 792.f * eu * Mf * Mf, Kef = 456.f * eu * Me * Mf;
+    const float Kg = 384.f * eu * Me * Me * Me, Kh = 2400.f * eu * Mf * Mf * Mf;
+    const F3 n1 = cross(e[0], e[1]), m1 = cross(f[0], f[1]);
     AxisState st{false, false};
-    axisTest(n1, p2, p3, q1, q2, q3, Ea, st);
-    axisTest(m1, p2, p3, q1, q2, q3, Ea, st);
+    axisTest(n1, p2, p3, q1, q2, q3, S, Kn, st);
+    axisTest(m1, p2, p3, q1, q2, q3, S, Km, st);
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) axisTest(cross(e[i], f[j]), p2, p3, q1, q2, q3, Ea, st);
+        for (int j = 0; j < 3; ++j) axisTest(cross(e[i], f[j]), p2, p3, q1, q2, q3, S, Kef, st);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) axisTest(cross(e[i], n1), p2, p3, q1, q2, q3, Eg, st);
+    for (int i = 0; i < 3; ++i) axisTest(cross(e[i], n1), p2, p3, q1, q2, q3, S, Kg, st);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) axisTest(cross(f[i], m1), p2, p3, q1, q2, q3, Eg, st);
+    for (int i = 0; i < 3; ++i) axisTest(cross(f[i], m1), p2, p3, q1, q2, q3, S, Kh, st);
     if (st.sep) return kTriNo;
     return st.unsure ? kTriUnsure : kTriYes;
 }
@@ -337,13 +340,15 @@ __device__ unsigned long long drainPool(WarpSmem<E> &sm, const SceneDev &sc, con
                 const float4 p1 = ldg4(tp), p2 = ldg4(tp + 1), p3 = ldg4(tp + 2);
                 const float4 w1 = ldg4(tq), w2 = ldg4(tq + 1), w3 = ldg4(tq + 2);
                 const float4 x0 = sm.xf[slot][0], x1 = sm.xf[slot][1], x2 = sm.xf[slot][2], x3 = sm.xf[slot][3];
-                auto xf = [&](const float4 w) {
-                    return f3(fmaf(x0.x, w.x, fmaf(x0.y, w.y, fmaf(x0.z, w.z, x0.w))),
-                              fmaf(x1.x, w.x, fmaf(x1.y, w.y, fmaf(x1.z, w.z, x1.w))),
-                              fmaf(x2.x, w.x, fmaf(x2.y, w.y, fmaf(x2.z, w.z, x2.w))));
+                // q1 = R*Q1 + T - P1 ; env edge vectors are only rotated
+                const F3 q1 = f3(fmaf(x0.x, w1.x, fmaf(x0.y, w1.y, fmaf(x0.z, w1.z, x0.w))) - p1.x,
+                                 fmaf(x1.x, w1.x, fmaf(x1.y, w1.y, fmaf(x1.z, w1.z, x1.w))) - p1.y,
+                                 fmaf(x2.x, w1.x, fmaf(x2.y, w1.y, fmaf(x2.z, w1.z, x2.w))) - p1.z);
+                auto rot = [&](const float4 w) {
+                    return f3(fmaf(x0.x, w.x, fmaf(x0.y, w.y, x0.z * w.z)), fmaf(x1.x, w.x, fmaf(x1.y, w.y, x1.z * w.z)),
+                              fmaf(x2.x, w.x, fmaf(x2.y, w.y, x2.z * w.z)));
                 };
-                verdict = triTriFilter(f3(p1.x, p1.y, p1.z), f3(p2.x, p2.y, p2.z), f3(p3.x, p3.y, p3.z), xf(w1),
-                                       xf(w2), xf(w3), x3.y);
+                verdict = triTriFilter(f3(p2.x, p2.y, p2.z), f3(p3.x, p3.y, p3.z), q1, rot(w2), rot(w3), x3.y);
             }
             nTri += __popc(__ballot_sync(kFull, act));
             hitLo |= __reduce_or_sync(kFull, (verdict == kTriYes && slot < 32) ? 1u << slot : 0u);
