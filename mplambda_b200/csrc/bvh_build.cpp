@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -67,6 +68,8 @@ struct Builder {
     std::vector<Box> boxes;
     std::vector<int> link;
     int depth = 0;
+    int maxDepth = 30;   // hard bound on root->leaf edges
+    int strategy = 1;    // 0: centroid median on the longest axis, 1: surface-area sweep
 
     Box fit(int first, int n) const {
         // PCA of the triangle vertices
@@ -119,6 +122,92 @@ struct Builder {
         return bx;
     }
 
+    // Partition prim[first, first+n) in place and return the size of the left part.
+    //
+    // Quality split: sweep the triangles sorted by centroid along each box axis and take the
+    // partition that minimises area(left) * n_left + area(right) * n_right, areas measured as
+    // axis-aligned boxes in this node's frame (a surface-area heuristic: what matters for the
+    // pair traversal is how rarely the children overlap a query box).  When the remaining depth
+    // budget only just fits a balanced subtree the split falls back to the centroid median, so
+    // the tree never exceeds maxDepth (the device pair stack is sized from it).
+    int chooseSplit(const Box &bx, int first, int n, int d) {
+        int levelsNeeded = 0;
+        while ((1 << levelsNeeded) < n) ++levelsNeeded;
+        const bool mustBalance = strategy == 0 || d + levelsNeeded + 1 >= maxDepth;
+        auto medianSplit = [&](int ax) {
+            V3 dir = bx.axis[ax];
+            int half = n / 2;
+            std::nth_element(prim.begin() + first, prim.begin() + first + half, prim.begin() + first + n,
+                             [&](int a, int b) {
+                                 double pa = dot(dir, centroid[a]), pb = dot(dir, centroid[b]);
+                                 return pa < pb || (pa == pb && a < b);
+                             });
+            return half;
+        };
+        int longest = 0;
+        if (bx.ext[1] > bx.ext[longest]) longest = 1;
+        if (bx.ext[2] > bx.ext[longest]) longest = 2;
+        if (mustBalance || n <= 2) return medianSplit(longest);
+
+        // per-triangle bounds in the node frame
+        std::vector<double> lo(3 * (size_t)n), hi(3 * (size_t)n), cen(3 * (size_t)n);
+        for (int i = 0; i < n; ++i) {
+            const int t = prim[first + i];
+            for (int a = 0; a < 3; ++a) {
+                double mn = DBL_MAX, mx = -DBL_MAX;
+                for (int k = 0; k < 3; ++k) {
+                    double v = dot(bx.axis[a], verts[3 * t + k]);
+                    mn = std::min(mn, v);
+                    mx = std::max(mx, v);
+                }
+                lo[3 * i + a] = mn;
+                hi[3 * i + a] = mx;
+                cen[3 * i + a] = dot(bx.axis[a], centroid[t]);
+            }
+        }
+        auto area = [](const double *l, const double *h) {
+            double dx = h[0] - l[0], dy = h[1] - l[1], dz = h[2] - l[2];
+            return dx * dy + dy * dz + dz * dx;
+        };
+        double bestCost = DBL_MAX;
+        int bestAxis = -1, bestCount = 0;
+        std::vector<int> order(n), bestOrder;
+        std::vector<double> rightArea(n + 1);
+        for (int a = 0; a < 3; ++a) {
+            std::iota(order.begin(), order.end(), 0);
+            std::sort(order.begin(), order.end(), [&](int x, int y) {
+                return cen[3 * x + a] < cen[3 * y + a] || (cen[3 * x + a] == cen[3 * y + a] && prim[first + x] < prim[first + y]);
+            });
+            double l[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, h[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+            for (int i = n - 1; i >= 1; --i) {
+                for (int k = 0; k < 3; ++k) {
+                    l[k] = std::min(l[k], lo[3 * order[i] + k]);
+                    h[k] = std::max(h[k], hi[3 * order[i] + k]);
+                }
+                rightArea[i] = area(l, h);
+            }
+            double l2[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, h2[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+            for (int i = 1; i < n; ++i) {
+                for (int k = 0; k < 3; ++k) {
+                    l2[k] = std::min(l2[k], lo[3 * order[i - 1] + k]);
+                    h2[k] = std::max(h2[k], hi[3 * order[i - 1] + k]);
+                }
+                double cost = area(l2, h2) * i + rightArea[i] * (n - i);
+                if (cost < bestCost) {
+                    bestCost = cost;
+                    bestAxis = a;
+                    bestCount = i;
+                    bestOrder = order;
+                }
+            }
+        }
+        if (bestAxis < 0) return medianSplit(longest);
+        std::vector<int> tmp(n);
+        for (int i = 0; i < n; ++i) tmp[i] = prim[first + bestOrder[i]];
+        std::copy(tmp.begin(), tmp.end(), prim.begin() + first);
+        return bestCount;
+    }
+
     void build(int node, int first, int n, int d) {
         boxes[node] = fit(first, n);
         depth = std::max(depth, d);
@@ -126,18 +215,8 @@ struct Builder {
             link[node] = -(prim[first] + 1);
             return;
         }
-        // median split of centroids along the longest box axis
         const Box &bx = boxes[node];
-        int ax = 0;
-        if (bx.ext[1] > bx.ext[ax]) ax = 1;
-        if (bx.ext[2] > bx.ext[ax]) ax = 2;
-        V3 dir = bx.axis[ax];
-        int half = n / 2;
-        std::nth_element(prim.begin() + first, prim.begin() + first + half, prim.begin() + first + n,
-                         [&](int a, int b) {
-                             double pa = dot(dir, centroid[a]), pb = dot(dir, centroid[b]);
-                             return pa < pb || (pa == pb && a < b);
-                         });
+        int half = chooseSplit(bx, first, n, d);
         int fc = (int)boxes.size();
         boxes.resize(fc + 2);
         link.resize(fc + 2);
@@ -175,6 +254,7 @@ FlatBvh buildBvh(const double *tris, size_t n) {
     if (n == 0) return out;
 
     Builder b;
+    if (const char *e = std::getenv("MPLB_BVH_SPLIT")) b.strategy = std::atoi(e);
     b.verts = reinterpret_cast<const V3 *>(tris);
     b.prim.resize(n);
     std::iota(b.prim.begin(), b.prim.end(), 0);

@@ -190,6 +190,8 @@ static int createSe3(const double *envTris, size_t nEnv, const double *robotTris
                     env.depth);
     d.envRadius = std::nextafterf((float)env.radius, INFINITY);
     d.robotRadius = std::nextafterf((float)robot.radius, INFINITY);
+    d.triBatchMin = 32;
+    if (const char *e = std::getenv("MPLB_TRI_BATCH")) d.triBatchMin = std::max(1, std::min(32, std::atoi(e)));
     sc->envNodeCount = env.nodes.size();
     sc->robotNodeCount = robot.nodes.size();
     *out = reinterpret_cast<mplb_scene *>(static_cast<SceneBase *>(sc.release()));

@@ -19,6 +19,7 @@ struct SceneDev {
     int wide;                   // 1: pair entries need 64 bits
     float envRadius;            // max |vertex| of the environment
     float robotRadius;          // max |vertex| of the (centred) robot
+    int triBatchMin;            // leaf pairs queued before a triangle batch runs (<= 32)
 };
 
 struct DevCounters {

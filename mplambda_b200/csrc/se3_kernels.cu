@@ -323,7 +323,7 @@ __device__ unsigned long long drainPool(WarpSmem<E> &sm, const SceneDev &sc, con
     int nt = 0, nx = 0;
     for (;;) {
         if (EDGE && (hitLo | hitHi)) break;
-        if (nt >= 32 || (top == 0 && nt > 0)) {
+        if (nt >= sc.triBatchMin || (top < 32 && nt > 0)) {
             // ---- triangle-triangle batch (FP32 filter)
             const int n = min(32, nt);
             const bool act0 = (int)lane < n;
@@ -361,7 +361,7 @@ __device__ unsigned long long drainPool(WarpSmem<E> &sm, const SceneDev &sc, con
             }
             if (nx < 32) continue;
         }
-        if (nx >= 32 || (top == 0 && nt == 0 && nx > 0)) {
+        if (nx >= 32 || (top < 32 && nt == 0 && nx > 0)) {
             // ---- exact FP64 batch
             const int n = min(32, nx);
             const bool act0 = (int)lane < n;
