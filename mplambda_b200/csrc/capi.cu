@@ -182,14 +182,25 @@ static int createSe3(const double *envTris, size_t nEnv, const double *robotTris
     d.bitsA = bitsFor(std::max<size_t>(2, robot.nodes.size()));
     d.bitsB = bitsFor(std::max<size_t>(2, env.nodes.size()));
     d.wide = (6 + d.bitsA + d.bitsB) > 32;
-    if (6 + d.bitsA + d.bitsB > 64) return fail(MPLB_ERR_INVALID, "meshes too large for the pair encoding");
-    // se3_kernels.cu: the pair LIFO throttles itself to depth-first order near its soft cap and
-    // then grows by at most one entry per hierarchy level
+    if (d.bitsA + d.bitsB > 32) return fail(MPLB_ERR_INVALID, "meshes too large for the 32-bit node pair encoding");
+    // se3_kernels.cu: a lane's depth-first LIFO holds at most depthA + depthB + 2 pairs (kStackDepth = 64)
     if (robot.depth + env.depth > 60)
         return fail(MPLB_ERR_INVALID, "hierarchy too deep for the device pair stack (%d + %d levels)", robot.depth,
                     env.depth);
     d.envRadius = std::nextafterf((float)env.radius, INFINITY);
     d.robotRadius = std::nextafterf((float)robot.radius, INFINITY);
+    d.stackLevels = (robot.depth + env.depth + 2 + 3) & ~3;
+    {
+        // entry layout of se3_kernels.cu: robotIdx | envIdx << bitsA | descendRobot << 31, the index on
+        // the descended side being that node's first child
+        auto linkOf = [](const FlatBvh &b) { int l = -1; if (!b.nodes.empty()) std::memcpy(&l, &b.nodes[0].q[3][3], 4); return l; };
+        auto sizeOf = [](const FlatBvh &b) { if (b.nodes.empty()) return 0.f; const float *e = b.nodes[0].q[3]; return e[0] * e[0] + e[1] * e[1] + e[2] * e[2]; };
+        const int lr = linkOf(robot), le = linkOf(env);
+        const bool descendRobot = le < 0 || (lr >= 0 && sizeOf(robot) > sizeOf(env));
+        d.rootEntry = (lr < 0 && le < 0) ? 0u
+                      : descendRobot ? ((unsigned)lr | 0u << d.bitsA | 0x80000000u) : (0u | (unsigned)le << d.bitsA);
+    }
+    if (d.bitsA + d.bitsB > 31) return fail(MPLB_ERR_INVALID, "meshes too large for the 31-bit node pair encoding");
     d.triBatchMin = 32;
     if (const char *e = std::getenv("MPLB_TRI_BATCH")) d.triBatchMin = std::max(1, std::min(32, std::atoi(e)));
     sc->envNodeCount = env.nodes.size();
@@ -202,7 +213,7 @@ static int finishCall(SceneBase *sc, CallCtx *c, size_t checks, uint64_t *states
     cudaError_t e = cudaMemcpyAsync(c->hCtr, c->ctr.ptr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) return fail(MPLB_ERR_CUDA, "device work failed: %s", cudaGetErrorString(e));
-    if (c->hCtr->overflow) return fail(MPLB_ERR_CUDA, "device pair stack overflow (hierarchy depth bound violated)");
+    if (c->hCtr->overflow) return fail(MPLB_ERR_CUDA, "device traversal bookkeeping error (pair stack / slot accounting)");
     sc->hBv += c->hCtr->bvTests;
     sc->hTri += c->hCtr->triTests;
     sc->hExact += c->hCtr->exactTests;
@@ -428,7 +439,7 @@ int mplb_scene_stats(mplb_scene *scene, mplb_stats_t *out, int reset) {
     MPLB_CUDA(cudaDeviceSynchronize());
     DevCounters g{};
     MPLB_CUDA(cudaMemcpy(&g, b->globalCtr.ptr, sizeof(g), cudaMemcpyDeviceToHost));
-    if (g.overflow) return fail(MPLB_ERR_CUDA, "device pair stack overflow (hierarchy depth bound violated)");
+    if (g.overflow) return fail(MPLB_ERR_CUDA, "device traversal bookkeeping error (pair stack / slot accounting)");
     std::memset(out, 0, sizeof(*out));
     out->checks = b->hChecks + g.states;
     out->bv_tests = b->hBv + g.bvTests;

@@ -20,6 +20,8 @@ struct SceneDev {
     float envRadius;            // max |vertex| of the environment
     float robotRadius;          // max |vertex| of the (centred) robot
     int triBatchMin;            // leaf pairs queued before a triangle batch runs (<= 32)
+    int stackLevels;            // per-lane LIFO levels = depthA + depthB + 2 (rounded up)
+    unsigned rootEntry;         // LIFO entry that expands the root pair (se3_kernels.cu)
 };
 
 struct DevCounters {

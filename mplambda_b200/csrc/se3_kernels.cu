@@ -7,21 +7,21 @@
 // i.e. fcl::collide(robotMesh, tf(q), envMesh, Identity) per state ([EXT] FCL: OBB hierarchy
 // traversal + 17-axis triangle-triangle separating-axis test, first contact wins).
 //
-// Execution model (one warp = one cooperative work pool):
-//   * a warp owns a chunk of 64 states (64 consecutive poses, or 64 interpolated states of one
-//     edge in bit-reversed -- coarse-to-fine -- order) and expands them to FP32 (R,T) slots in
-//     shared memory;
-//   * (slot, robotNode, envNode) pairs live in a per-warp LIFO in shared memory; every
-//     iteration the 32 lanes pop 32 pairs -- of whatever states -- run one OBB-OBB SAT each
-//     and push the surviving child pairs with a ballot/popc prefix, so lanes stay busy no
-//     matter how uneven the per-state traversal depth is;
-//   * leaf-leaf survivors go to a second queue and are tested 32 at a time with an
+// Execution model (one warp = one streaming work pool over 64 state slots in shared memory):
+//   * states are expanded 32 at a time (FP64 quaternion/slerp math -> FP32 (R|T) slot) into free
+//     slots; a lane that runs out of work adopts the next ready slot, so all 32 lanes stay busy
+//     however uneven the per-state traversal depth is, and every state is still searched
+//     depth-first (first contact is found after few box tests, as in the reference's recursion);
+//   * each lane owns a private LIFO of (robotNode, envNode) pairs in shared memory.  One step
+//     pops a pair known to overlap, loads the two children of the larger box and runs both
+//     OBB-OBB separating-axis tests; survivors are pushed nearest-centre-first;
+//   * leaf-leaf survivors go to a warp-shared queue and are tested 32 at a time with an
 //     error-bounded FP32 17-axis SAT; the rare pairs whose FP32 verdict is not certain go to a
 //     third queue and are re-evaluated in FP64 with exactly the oracle's operation order
 //     (__dmul_rn/__dadd_rn: no FMA contraction), which is what makes verdicts bit-identical to
 //     the FP64 CPU path instead of "equal up to an epsilon band";
-//   * per-state hit bits are warp-uniform registers (ballot + reduce_or); for edges the first
-//     hit abandons the chunk and marks the edge dead so later chunks of it are skipped.
+//   * hit/ready/free slot sets are warp-uniform bit masks maintained with ballot/reduce_or; a
+//     slot is recycled once its search is over and none of its leaf pairs is still queued.
 // Node and triangle fetches are 128-bit read-only loads (4 per 64-byte node, 3 per triangle);
 // the hierarchy is small enough to live in L1/L2, HBM only sees states
 // in and verdict bytes out.
@@ -33,21 +33,42 @@ namespace mplb {
 namespace {
 
 constexpr int kWarpsPerCta = 8;
-constexpr int kChunk = 64;          // states per work item
-constexpr int kStackCap = 1024;     // pair LIFO entries per warp
-// Above this fill level a warp pops fewer pairs per iteration (down to one: plain depth-first
-// search, which grows by at most one entry per level), so the LIFO cannot overflow as long as
-// depthA + depthB <= kStackCap - kStackSoftCap (checked at scene creation).
-constexpr int kStackSoftCap = kStackCap - 72;
+constexpr int kSlots = 64;          // state slots per warp
 constexpr int kQueueCap = 96;       // leaf / exact queue entries per warp
 constexpr unsigned kFull = 0xffffffffu;
 
+// Per-warp shared memory, carved from the dynamic allocation at run time: the LIFO only gets as
+// many levels as the scene's hierarchies need (depthA + depthB + 2), which keeps the footprint
+// small enough for L1 to hold the hot part of the hierarchy.
 template <typename E>
 struct WarpSmem {
-    E stack[kStackCap];
-    E triq[kQueueCap];
-    E exq[kQueueCap];
-    float4 xf[kChunk][4];  // per slot: rows of (R | T), then (slack, eta, -, -); see makeSlot
+    unsigned (*stack)[32];            // [level][lane]: robotIdx | envIdx << bitsA | descendRobot << 31  (bank = lane)
+    float4 (*xf)[4];                  // per slot: rows of (R | T), then (slack, eta, -, -); see makeSlot
+    unsigned *tag0, *tag1;            // what the slot is (state index, or edge + sample)
+    int *pending;                     // leaf pairs of the slot still sitting in triq/exq
+    int *workers;                     // lanes currently searching the slot (work stealing splits a search)
+    unsigned *list;                   // scratch: compacted slot / lane lists
+    E *triq;                          // slot | robotTri << 6 | envTri << (6 + bitsA)
+    E *exq;
+
+    static __host__ __device__ size_t bytes(int levels) {
+        return (size_t)levels * 128 + kSlots * 64 + kSlots * 20 + 2 * kQueueCap * sizeof(E);
+    }
+    __device__ void carve(unsigned char *base, int levels) {
+        stack = reinterpret_cast<unsigned(*)[32]>(base);
+        base += (size_t)levels * 128;
+        xf = reinterpret_cast<float4(*)[4]>(base);
+        base += kSlots * 64;
+        triq = reinterpret_cast<E *>(base);
+        base += kQueueCap * sizeof(E);
+        exq = reinterpret_cast<E *>(base);
+        base += kQueueCap * sizeof(E);
+        tag0 = reinterpret_cast<unsigned *>(base);
+        tag1 = tag0 + kSlots;
+        pending = reinterpret_cast<int *>(tag1 + kSlots);
+        workers = pending + kSlots;
+        list = reinterpret_cast<unsigned *>(workers + kSlots);
+    }
 };
 
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
@@ -180,14 +201,15 @@ __device__ __forceinline__ F3 cross(F3 a, F3 b) {
 
 // OBB-OBB separating-axis test (Gottschalk's 15 axes).  Conservative: `slack` exceeds the FP32
 // evaluation error of either side, so a pair is only culled when the exact boxes are disjoint.
-// A = robot node (robot frame), B = env node (env frame), (R,T) maps env -> robot frame.
+// A and B are boxes in their own frames, (R,T) = rows x0..x2 maps B's frame into A's.
 __device__ __forceinline__ bool obbOverlap(const float4 a0, const float4 a1, const float4 a2, const float4 ae,
                                            const float4 b0, const float4 b1, const float4 b2, const float4 be,
-                                           const float4 x0, const float4 x1, const float4 x2, float slack) {
+                                           const float4 x0, const float4 x1, const float4 x2, float slack, float &dist2) {
     // env centre in the robot frame, relative to the robot box centre, in the robot box axes
     float cx = fmaf(x0.x, b0.w, fmaf(x0.y, b1.w, fmaf(x0.z, b2.w, x0.w))) - a0.w;
     float cy = fmaf(x1.x, b0.w, fmaf(x1.y, b1.w, fmaf(x1.z, b2.w, x1.w))) - a1.w;
     float cz = fmaf(x2.x, b0.w, fmaf(x2.y, b1.w, fmaf(x2.z, b2.w, x2.w))) - a2.w;
+    dist2 = fmaf(cx, cx, fmaf(cy, cy, cz * cz));
     float T[3] = {fmaf(a0.x, cx, fmaf(a0.y, cy, a0.z * cz)), fmaf(a1.x, cx, fmaf(a1.y, cy, a1.z * cz)),
                   fmaf(a2.x, cx, fmaf(a2.y, cy, a2.z * cz))};
     // RB_j = R * b_j
@@ -302,7 +324,7 @@ __device__ __forceinline__ unsigned bitrev(unsigned j, int bits) { return bits ?
 
 template <typename E>
 struct Codec {
-    int shA, shB;  // entry = slot | a << 6 | b << shB
+    int shB;  // entry = slot | a << 6 | b << shB
     __device__ __forceinline__ E pack(unsigned slot, unsigned a, unsigned b) const {
         return (E)slot | ((E)a << 6) | ((E)b << shB);
     }
@@ -311,28 +333,355 @@ struct Codec {
     __device__ __forceinline__ unsigned b(E e) const { return (unsigned)(e >> shB); }
 };
 
-// One warp drains its pool: returns the 64-bit hit mask of the chunk (bit s = slot s collides).
-// EDGE: stop at the first hit (the whole chunk belongs to one edge).
-template <typename E, bool EDGE, typename StateFn>
-__device__ unsigned long long drainPool(WarpSmem<E> &sm, const SceneDev &sc, const Codec<E> cd, int top,
-                                        StateFn &&stateOf, unsigned long long &nBv, unsigned long long &nTri,
-                                        unsigned long long &nExact, unsigned &overflow) {
+struct Masks64 {
+    unsigned lo, hi;
+    __device__ __forceinline__ bool test(unsigned s) const { return ((s < 32 ? lo >> s : hi >> (s - 32)) & 1u) != 0; }
+    __device__ __forceinline__ int count() const { return __popc(lo) + __popc(hi); }
+};
+
+// OR over the warp of (1 << slot) for the lanes with pred
+__device__ __forceinline__ Masks64 slotBits(bool pred, unsigned slot) {
+    Masks64 m;
+    m.lo = __reduce_or_sync(kFull, (pred && slot < 32) ? 1u << slot : 0u);
+    m.hi = __reduce_or_sync(kFull, (pred && slot >= 32) ? 1u << (slot - 32) : 0u);
+    return m;
+}
+
+struct WarpCounters {
+    unsigned long long bv = 0, tri = 0, exact = 0, states = 0;
+    unsigned error = 0;
+};
+
+// ---- work sources ----------------------------------------------------------------------------
+// A source hands out states in batches of up to 32 (warp-uniform control flow), names each with
+// a (tag0, tag1) pair kept in the slot, can rebuild the FP64 state from the tags (exact path)
+// and is told the verdict when the slot retires.
+
+// isValid(q) over an array: states are taken in index order from a global counter.
+struct StateSource {
+    const double *states;
+    unsigned long long n;
+    uint8_t *valid;
+    unsigned long long *counter;
+    unsigned long long base = 0;
+    bool exhausted = false;
+
+    __device__ int acquire(int want, unsigned lane) {
+        unsigned long long b = 0;
+        if (lane == 0) b = atomicAdd(counter, (unsigned long long)want);
+        b = __shfl_sync(kFull, b, 0);
+        if (b >= n) {
+            exhausted = true;
+            return 0;
+        }
+        base = b;
+        if (n - b <= (unsigned long long)want) {
+            exhausted = true;
+            return (int)(n - b);
+        }
+        return want;
+    }
+    __device__ void load(int rank, double s[7], unsigned &t0, unsigned &t1) const {
+        const unsigned long long i = base + rank;
+        t0 = (unsigned)i;
+        t1 = (unsigned)(i >> 32);
+        stateOf(t0, t1, s);
+    }
+    __device__ void stateOf(unsigned t0, unsigned t1, double s[7]) const {
+        const double *src = states + 7 * (((unsigned long long)t1 << 32) | t0);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) s[k] = __ldg(src + k);
+    }
+    __device__ void retire(unsigned t0, unsigned t1, bool hit) const {
+        valid[((unsigned long long)t1 << 32) | t0] = hit ? 0 : 1;
+    }
+    template <typename SM>
+    __device__ void onHit(Masks64, SM &, Masks64 &, const Masks64 &) {}
+};
+
+// isValid(from,to) over an array of edges.  Work items are (chunk c, edge e), c-major: chunk 0
+// of every edge (its 64 coarsest samples, `to` included) is handed out before any chunk 1, so an
+// edge that dies early never expands its fine samples.  Sample j of an edge: j = 0 is `to`
+// itself (se3...:136); otherwise i = bitrev_L(j), 2^L > steps, is the interpolated state at
+// t = i * (1/steps) (se3...:146,159) and exists when i < steps.
+struct EdgeSource {
+    const double *from, *to;
+    const unsigned *steps;
+    unsigned long long nEdges, nItems;
+    unsigned grab;
+    unsigned *dead;
+    unsigned long long *counter;
+    bool exhausted = false;
+    // current grab of items and the live ones among them
+    unsigned long long first = 0;
+    unsigned liveMask = 0;
+    // current item
+    bool have = false;
+    unsigned curEdge = 0, curChunk = 0, curBits = 0, curSteps = 0, pos = 0;
+    // last acquire
+    unsigned lastMask = 0, lastPos = 0;
+
+    __device__ bool nextItem(unsigned lane) {
+        for (;;) {
+            while (liveMask) {
+                const int src = __ffs(liveMask) - 1;
+                liveMask &= liveMask - 1;
+                const unsigned long long it = first + src;
+                curEdge = (unsigned)(it % nEdges);
+                curChunk = (unsigned)(it / nEdges);
+                if (((volatile unsigned *)dead)[curEdge]) continue;
+                curSteps = __ldg(steps + curEdge);
+                curBits = curSteps ? 32 - __clz(curSteps) : 0;
+                pos = 0;
+                have = true;
+                return true;
+            }
+            unsigned long long f = 0;
+            if (lane == 0) f = atomicAdd(counter, (unsigned long long)grab);
+            f = __shfl_sync(kFull, f, 0);
+            if (f >= nItems) {
+                exhausted = true;
+                return false;
+            }
+            first = f;
+            bool live = false;
+            const unsigned long long item = f + lane;
+            if (lane < grab && item < nItems) {
+                const unsigned long long e = item % nEdges;
+                const unsigned c = (unsigned)(item / nEdges);
+                const unsigned st = __ldg(steps + e);
+                const unsigned bits = st ? 32 - __clz(st) : 0;
+                live = c < max(1u, (1u << bits) >> 6) && !((volatile unsigned *)dead)[e];
+            }
+            liveMask = __ballot_sync(kFull, live);
+        }
+    }
+    __device__ int acquire(int want, unsigned lane) {
+        for (;;) {
+            if (!have && !nextItem(lane)) return 0;
+            if (pos >= 64) {
+                have = false;
+                continue;
+            }
+            const unsigned j = curChunk * 64 + pos + lane;
+            const bool ok = pos + lane < 64 && (j == 0 || (j < (1u << curBits) && bitrev(j, curBits) < curSteps));
+            const unsigned m = __ballot_sync(kFull, ok);
+            const int avail = __popc(m);
+            if (avail == 0) {
+                pos += 32;
+                continue;
+            }
+            lastPos = pos;
+            if (avail <= want) {
+                lastMask = m;
+                pos += 32;
+                return avail;
+            }
+            const unsigned cut = __fns(m, 0, want + 1);  // first sample NOT taken
+            lastMask = m & ((1u << cut) - 1u);
+            pos += cut;
+            return want;
+        }
+    }
+    __device__ void load(int rank, double s[7], unsigned &t0, unsigned &t1) const {
+        t0 = curEdge;
+        t1 = curChunk * 64 + lastPos + __fns(lastMask, 0, rank + 1);
+        stateOf(t0, t1, s);
+    }
+    __device__ void stateOf(unsigned t0, unsigned t1, double s[7]) const {
+        const double *b = to + 7 * (size_t)t0;
+        if (t1 == 0) {
+#pragma unroll
+            for (int k = 0; k < 7; ++k) s[k] = __ldg(b + k);
+            return;
+        }
+        const double *a = from + 7 * (size_t)t0;
+        double fa[7], fb[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            fa[k] = __ldg(a + k);
+            fb[k] = __ldg(b + k);
+        }
+        const unsigned st = __ldg(steps + t0);
+        const unsigned bits = 32 - __clz(st);
+        const double delta = __ddiv_rn(1.0, (double)st);
+        interpolateD(fa, fb, dmul((double)bitrev(t1, bits), delta), s);
+    }
+    __device__ void retire(unsigned t0, unsigned, bool hit) const {
+        if (hit) dead[t0] = 1u;
+    }
+    // a sample of an edge collided: drop the rest of that edge held by this warp
+    template <typename SM>
+    __device__ void onHit(Masks64 fresh, SM &sm, Masks64 &hit, const Masks64 &inUse) {
+        const unsigned lane = threadIdx.x & 31u;
+        while (fresh.lo | fresh.hi) {
+            unsigned s;
+            if (fresh.lo) {
+                s = __ffs(fresh.lo) - 1;
+                fresh.lo &= fresh.lo - 1;
+            } else {
+                s = 32 + __ffs(fresh.hi) - 1;
+                fresh.hi &= fresh.hi - 1;
+            }
+            const unsigned e = sm.tag0[s];
+            if (have && curEdge == e) have = false;
+            if (lane == 0) dead[e] = 1u;
+            const bool k0 = inUse.test(lane) && sm.tag0[lane] == e;
+            const bool k1 = inUse.test(lane + 32) && sm.tag0[lane + 32] == e;
+            hit.lo |= __ballot_sync(kFull, k0);
+            hit.hi |= __ballot_sync(kFull, k1);
+        }
+    }
+};
+
+// ---- the per-warp engine -----------------------------------------------------------------------
+
+template <typename E, typename Source>
+__device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCounters &cnt) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned ltMask = (1u << lane) - 1u;
-    unsigned hitLo = 0, hitHi = 0;
-    int nt = 0, nx = 0;
+    const Codec<E> cd{6 + sc.bitsA};
+    const int bitsA = sc.bitsA;
+    const unsigned maskA = (1u << bitsA) - 1u;
+    Masks64 freeM{~0u, ~0u}, readyM{0, 0}, hitM{0, 0}, doneM{0, 0};
+    // this lane's LIFO holds entries [bot, sp); thieves take from the bottom (the largest subtree)
+    int nt = 0, nx = 0, sp = 0, bot = 0, mySlot = -1;
+    const int triMin = sc.triBatchMin;
+    unsigned idleSpins = 0;
+    // compact the set bits of a 64-slot mask into sm.list (lane s looks after slots s and s + 32)
+    auto buildList = [&](const Masks64 &m) {
+        if ((m.lo >> lane) & 1u) sm.list[__popc(m.lo & ltMask)] = lane;
+        if ((m.hi >> lane) & 1u) sm.list[__popc(m.lo) + __popc(m.hi & ltMask)] = lane + 32;
+        __syncwarp();
+    };
+
     for (;;) {
-        if (EDGE && (hitLo | hitHi)) break;
-        if (nt >= sc.triBatchMin || (top < 32 && nt > 0)) {
-            // ---- triangle-triangle batch (FP32 filter)
+        // ---- a lane whose LIFO ran dry leaves its slot; the last one out ends the slot's search
+        {
+            const bool fin = mySlot >= 0 && sp == bot;
+            bool last = false;
+            if (fin) last = atomicSub(&sm.workers[mySlot], 1) == 1;
+            const Masks64 d = slotBits(last, (unsigned)mySlot);
+            doneM.lo |= d.lo;
+            doneM.hi |= d.hi;
+            if (fin) {
+                mySlot = -1;
+                sp = bot = 0;
+            }
+        }
+        // ---- retire finished slots whose queued leaf pairs are all resolved
+        {
+            const bool r0 = ((doneM.lo >> lane) & 1u) && sm.pending[lane] == 0;
+            const bool r1 = ((doneM.hi >> lane) & 1u) && sm.pending[lane + 32] == 0;
+            if (r0) src.retire(sm.tag0[lane], sm.tag1[lane], (hitM.lo >> lane) & 1u);
+            if (r1) src.retire(sm.tag0[lane + 32], sm.tag1[lane + 32], (hitM.hi >> lane) & 1u);
+            const unsigned m0 = __ballot_sync(kFull, r0), m1 = __ballot_sync(kFull, r1);
+            freeM.lo |= m0; doneM.lo &= ~m0; hitM.lo &= ~m0;
+            freeM.hi |= m1; doneM.hi &= ~m1; hitM.hi &= ~m1;
+        }
+        int nActive = __popc(__ballot_sync(kFull, sp > bot));
+        unsigned needMask = __ballot_sync(kFull, mySlot < 0);
+        // ---- expand a batch of new states into free slots (all lanes convert in parallel)
+        if (!src.exhausted && readyM.count() < __popc(needMask)) {
+            const int nfree = freeM.count();
+            if (nfree >= 16 || (nfree > 0 && nActive <= 16)) {
+                const int got = src.acquire(min(32, nfree), lane);
+                buildList(freeM);
+                const bool take = (int)lane < got;
+                unsigned slot = 0;
+                if (take) {
+                    slot = sm.list[lane];
+                    double s[7];
+                    unsigned t0, t1;
+                    src.load((int)lane, s, t0, t1);
+                    makeSlot(s, sc, sm.xf[slot]);
+                    sm.tag0[slot] = t0;
+                    sm.tag1[slot] = t1;
+                    sm.pending[slot] = 0;
+                }
+                const Masks64 t = slotBits(take, slot);
+                freeM.lo &= ~t.lo; freeM.hi &= ~t.hi;
+                readyM.lo |= t.lo; readyM.hi |= t.hi;
+                cnt.states += got;
+                __syncwarp();
+            }
+        }
+        // ---- idle lanes adopt ready slots
+        if (needMask && (readyM.lo | readyM.hi)) {
+            buildList(readyM);
+            const int rank = __popc(needMask & ltMask);
+            const bool take = mySlot < 0 && rank < readyM.count();
+            unsigned slot = 0;
+            if (take) {
+                slot = sm.list[rank];
+                mySlot = (int)slot;
+                sm.workers[slot] = 1;
+                if (sc.nRobotNodes > 0 && sc.nEnvNodes > 0 && (sc.nRobotNodes > 1 || sc.nEnvNodes > 1)) {
+                    sm.stack[0][lane] = sc.rootEntry;  // root pair, expanded without testing itself
+                    bot = 0;
+                    sp = 1;
+                }
+            }
+            if (sc.nRobotNodes == 1 && sc.nEnvNodes == 1) {  // two single-triangle meshes: straight to the leaf test
+                const unsigned m = __ballot_sync(kFull, take);
+                if (take) {
+                    sm.triq[nt + __popc(m & ltMask)] = cd.pack(slot, 0, 0);
+                    sm.pending[slot] = 1;
+                }
+                nt += __popc(m);
+            }
+            const Masks64 t = slotBits(take, slot);
+            readyM.lo &= ~t.lo; readyM.hi &= ~t.hi;
+            __syncwarp();
+            needMask = __ballot_sync(kFull, mySlot < 0);
+        }
+        // ---- work stealing: lanes still idle take the bottom pair (the largest pending subtree) of
+        //      lanes that have at least two, and join that slot's search
+        if (needMask) {
+            const bool canGive = sp - bot >= 2;
+            const unsigned donors = __ballot_sync(kFull, canGive);
+            const int k = min(__popc(needMask), __popc(donors));
+            if (k > 0) {
+                const int donorRank = __popc(donors & ltMask);
+                const bool give = canGive && donorRank < k;
+                if (give) sm.list[donorRank] = lane;
+                __syncwarp();
+                const int idleRank = __popc(needMask & ltMask);
+                const bool steal = mySlot < 0 && idleRank < k;
+                const unsigned dl = steal ? sm.list[idleRank] : lane;
+                const int dbot = __shfl_sync(kFull, bot, dl), dslot = __shfl_sync(kFull, mySlot, dl);
+                if (steal) {
+                    sm.stack[0][lane] = sm.stack[dbot][dl];
+                    bot = 0;
+                    sp = 1;
+                    mySlot = dslot;
+                    atomicAdd(&sm.workers[dslot], 1);
+                }
+                if (give) ++bot;
+                __syncwarp();
+            }
+        }
+        nActive = __popc(__ballot_sync(kFull, sp > bot));
+        if (nActive == 0 && nt == 0 && nx == 0) {
+            const bool busy = __any_sync(kFull, mySlot >= 0) || (doneM.lo | doneM.hi) || (readyM.lo | readyM.hi);
+            if (!busy && src.exhausted) break;
+            if (++idleSpins > 4096u) {  // bookkeeping bug guard: report instead of hanging the device
+                cnt.error = 1;
+                break;
+            }
+            continue;
+        }
+        idleSpins = 0;
+
+        // ---- triangle-triangle batch (FP32 filter)
+        auto triBatch = [&]() {
             const int n = min(32, nt);
             const bool act0 = (int)lane < n;
-            E en = act0 ? sm.triq[nt - 1 - lane] : 0;
+            const E en = act0 ? sm.triq[nt - 1 - lane] : (E)0;
             nt -= n;
             __syncwarp();
             const unsigned slot = cd.slot(en);
-            const bool dead = slot < 32 ? (hitLo >> slot) & 1u : (hitHi >> (slot - 32)) & 1u;
-            const bool act = act0 && !dead;
+            const bool act = act0 && !hitM.test(slot);
             int verdict = kTriNo;
             if (act) {
                 const float4 *tp = sc.robotTris + 3 * (size_t)cd.a(en);
@@ -350,243 +699,189 @@ __device__ unsigned long long drainPool(WarpSmem<E> &sm, const SceneDev &sc, con
                 };
                 verdict = triTriFilter(f3(p2.x, p2.y, p2.z), f3(p3.x, p3.y, p3.z), q1, rot(w2), rot(w3), x3.y);
             }
-            nTri += __popc(__ballot_sync(kFull, act));
-            hitLo |= __reduce_or_sync(kFull, (verdict == kTriYes && slot < 32) ? 1u << slot : 0u);
-            hitHi |= __reduce_or_sync(kFull, (verdict == kTriYes && slot >= 32) ? 1u << (slot - 32) : 0u);
+            cnt.tri += __popc(__ballot_sync(kFull, act));
+            if (act0 && verdict != kTriUnsure) atomicSub(&sm.pending[slot], 1);
+            const Masks64 fresh = slotBits(verdict == kTriYes, slot);
             const unsigned mu = __ballot_sync(kFull, verdict == kTriUnsure);
             if (mu) {
                 if (verdict == kTriUnsure) sm.exq[nx + __popc(mu & ltMask)] = en;
                 nx += __popc(mu);
-                __syncwarp();
             }
-            if (nx < 32) continue;
-        }
-        if (nx >= 32 || (top < 32 && nt == 0 && nx > 0)) {
-            // ---- exact FP64 batch
+            __syncwarp();
+            if (fresh.lo | fresh.hi) {
+                hitM.lo |= fresh.lo;
+                hitM.hi |= fresh.hi;
+                src.onHit(fresh, sm, hitM, Masks64{~freeM.lo, ~freeM.hi});
+            }
+        };
+        // ---- exact FP64 batch
+        auto exactBatch = [&]() {
             const int n = min(32, nx);
             const bool act0 = (int)lane < n;
-            E en = act0 ? sm.exq[nx - 1 - lane] : 0;
+            const E en = act0 ? sm.exq[nx - 1 - lane] : (E)0;
             nx -= n;
             __syncwarp();
             const unsigned slot = cd.slot(en);
-            const bool dead = slot < 32 ? (hitLo >> slot) & 1u : (hitHi >> (slot - 32)) & 1u;
-            const bool act = act0 && !dead;
+            const bool act = act0 && !hitM.test(slot);
             bool hit = false;
             if (act) {
                 double s[7];
-                stateOf(slot, s);
+                src.stateOf(sm.tag0[slot], sm.tag1[slot], s);
                 XformD X;
                 stateToRelD(s, X);
                 hit = triTriExact(sc.robotTris64 + 9 * (size_t)cd.a(en), sc.envTris64 + 9 * (size_t)cd.b(en), X);
             }
-            nExact += __popc(__ballot_sync(kFull, act));
-            hitLo |= __reduce_or_sync(kFull, (hit && slot < 32) ? 1u << slot : 0u);
-            hitHi |= __reduce_or_sync(kFull, (hit && slot >= 32) ? 1u << (slot - 32) : 0u);
-            continue;
-        }
-        if (top == 0) break;
-        // ---- OBB-OBB batch
-        const int n = min(min(32, top), max(1, kStackSoftCap - top));
-        const bool act0 = (int)lane < n;
-        E en = act0 ? sm.stack[top - 1 - lane] : 0;
-        top -= n;
-        __syncwarp();
-        const unsigned slot = cd.slot(en);
-        const bool dead = slot < 32 ? (hitLo >> slot) & 1u : (hitHi >> (slot - 32)) & 1u;
-        const bool act = act0 && !dead;
-        bool ov = false, leafA = false, leafB = false, descendA = false;
-        int linkA = 0, linkB = 0;
-        const unsigned na = cd.a(en), nb = cd.b(en);
-        if (act) {
-            const float4 *pa = sc.robotNodes + 4 * (size_t)na;
-            const float4 *pb = sc.envNodes + 4 * (size_t)nb;
-            const float4 a0 = ldg4(pa), a1 = ldg4(pa + 1), a2 = ldg4(pa + 2), ae = ldg4(pa + 3);
-            const float4 b0 = ldg4(pb), b1 = ldg4(pb + 1), b2 = ldg4(pb + 2), be = ldg4(pb + 3);
-            const float4 x0 = sm.xf[slot][0], x1 = sm.xf[slot][1], x2 = sm.xf[slot][2], x3 = sm.xf[slot][3];
-            ov = obbOverlap(a0, a1, a2, ae, b0, b1, b2, be, x0, x1, x2, x3.x);
-            linkA = __float_as_int(ae.w);
-            linkB = __float_as_int(be.w);
-            leafA = linkA < 0;
-            leafB = linkB < 0;
-            const float szA = fmaf(ae.x, ae.x, fmaf(ae.y, ae.y, ae.z * ae.z));
-            const float szB = fmaf(be.x, be.x, fmaf(be.y, be.y, be.z * be.z));
-            descendA = leafB || (!leafA && szA > szB);
-        }
-        nBv += __popc(__ballot_sync(kFull, act));
-        const bool toTri = ov && leafA && leafB;
-        const bool toBv = ov && !toTri;
-        const unsigned mt = __ballot_sync(kFull, toTri);
-        const unsigned mb = __ballot_sync(kFull, toBv);
-        if (toTri) sm.triq[nt + __popc(mt & ltMask)] = cd.pack(slot, (unsigned)(-(linkA + 1)), (unsigned)(-(linkB + 1)));
-        nt += __popc(mt);
-        if (top + 2 * __popc(mb) > kStackCap) {
-            overflow = 1;  // cannot happen with the builder's depth bound; reported, never ignored
-            break;
-        }
-        if (toBv) {
-            const int pos = top + 2 * __popc(mb & ltMask);
-            if (descendA) {
-                sm.stack[pos] = cd.pack(slot, (unsigned)linkA + 1, nb);
-                sm.stack[pos + 1] = cd.pack(slot, (unsigned)linkA, nb);
-            } else {
-                sm.stack[pos] = cd.pack(slot, na, (unsigned)linkB + 1);
-                sm.stack[pos + 1] = cd.pack(slot, na, (unsigned)linkB);
+            cnt.exact += __popc(__ballot_sync(kFull, act));
+            if (act0) atomicSub(&sm.pending[slot], 1);
+            const Masks64 fresh = slotBits(hit, slot);
+            __syncwarp();
+            if (fresh.lo | fresh.hi) {
+                hitM.lo |= fresh.lo;
+                hitM.hi |= fresh.hi;
+                src.onHit(fresh, sm, hitM, Masks64{~freeM.lo, ~freeM.hi});
             }
+        };
+        // The queues hold at most 31 leftovers plus what one step can add (64 leaf pairs, 32 unsure
+        // pairs per triangle batch): drain them down below a batch before stepping again.
+        while (nt >= triMin || (nt > 0 && nActive <= 16)) {
+            triBatch();
+            while (nx >= 32) exactBatch();
         }
-        top += 2 * __popc(mb);
-        __syncwarp();
+        if (nx > 0 && nActive <= 16) exactBatch();
+        // ---- one depth-first step per lane: pop a pair, test both children of the larger box
+        if (nActive) {
+            bool act = sp > bot;
+            const unsigned slot = (unsigned)max(mySlot, 0);
+            if (act && hitM.test(slot)) {  // decided meanwhile (leaf test, another lane, or a sibling sample of the edge)
+                sp = bot;
+                act = false;
+            }
+            bool ov0 = false, ov1 = false, leaf0 = false, leaf1 = false, descendA = false;
+            float d0 = 0.f, d1 = 0.f, sz0 = 0.f, sz1 = 0.f, szF = 0.f;
+            unsigned fixedIdx = 0, child = 0;
+            int link0 = 0, link1 = 0, fixedLink = 0;
+            if (act) {
+                // entry: robotIdx | envIdx << bitsA | descendRobot << 31, where the index on the
+                // descended side already is that node's first child: every load below is
+                // independent of the others (one memory round trip per step)
+                const unsigned en = sm.stack[--sp][lane];
+                descendA = (en >> 31) != 0;
+                const unsigned r = en & maskA, e = (en & 0x7fffffffu) >> bitsA;
+                child = descendA ? r : e;
+                fixedIdx = descendA ? e : r;
+                const float4 *pc = (descendA ? sc.robotNodes : sc.envNodes) + 4 * (size_t)child;
+                const float4 *pf = (descendA ? sc.envNodes : sc.robotNodes) + 4 * (size_t)fixedIdx;
+                const float4 f0 = ldg4(pf), f1 = ldg4(pf + 1), f2 = ldg4(pf + 2), fe = ldg4(pf + 3);
+                const float4 c00 = ldg4(pc), c01 = ldg4(pc + 1), c02 = ldg4(pc + 2), c0e = ldg4(pc + 3);
+                const float4 c10 = ldg4(pc + 4), c11 = ldg4(pc + 5), c12 = ldg4(pc + 6), c1e = ldg4(pc + 7);
+                const float4 x0 = sm.xf[slot][0], x1 = sm.xf[slot][1], x2 = sm.xf[slot][2], x3 = sm.xf[slot][3];
+                // The fixed box is always the first argument.  (R|T) maps env -> robot coordinates; when
+                // the fixed box is the environment's the test runs in its frame with the inverse map
+                // (R^T | -R^T T), so no per-role shuffling of the 3 x 16 node floats is needed.
+                const float4 y0 = descendA ? make_float4(x0.x, x1.x, x2.x, -fmaf(x0.x, x0.w, fmaf(x1.x, x1.w, x2.x * x2.w))) : x0;
+                const float4 y1 = descendA ? make_float4(x0.y, x1.y, x2.y, -fmaf(x0.y, x0.w, fmaf(x1.y, x1.w, x2.y * x2.w))) : x1;
+                const float4 y2 = descendA ? make_float4(x0.z, x1.z, x2.z, -fmaf(x0.z, x0.w, fmaf(x1.z, x1.w, x2.z * x2.w))) : x2;
+                ov0 = obbOverlap(f0, f1, f2, fe, c00, c01, c02, c0e, y0, y1, y2, x3.x, d0);
+                ov1 = obbOverlap(f0, f1, f2, fe, c10, c11, c12, c1e, y0, y1, y2, x3.x, d1);
+                link0 = __float_as_int(c0e.w);
+                link1 = __float_as_int(c1e.w);
+                fixedLink = __float_as_int(fe.w);
+                const bool fixedLeaf = fixedLink < 0;
+                leaf0 = fixedLeaf && link0 < 0;
+                leaf1 = fixedLeaf && link1 < 0;
+                sz0 = fmaf(c0e.x, c0e.x, fmaf(c0e.y, c0e.y, c0e.z * c0e.z));
+                sz1 = fmaf(c1e.x, c1e.x, fmaf(c1e.y, c1e.y, c1e.z * c1e.z));
+                szF = fmaf(fe.x, fe.x, fmaf(fe.y, fe.y, fe.z * fe.z));
+            }
+            cnt.bv += 2ull * __popc(__ballot_sync(kFull, act));
+            // leaf-leaf survivors -> shared triangle queue
+            const bool t0 = ov0 && leaf0, t1 = ov1 && leaf1;
+            const unsigned m0 = __ballot_sync(kFull, t0), m1 = __ballot_sync(kFull, t1);
+            if (m0 | m1) {
+                const unsigned fixedTri = (unsigned)(-(fixedLink + 1));
+                if (t0) {
+                    const unsigned ct = (unsigned)(-(link0 + 1));
+                    sm.triq[nt + __popc(m0 & ltMask)] = descendA ? cd.pack(slot, ct, fixedTri) : cd.pack(slot, fixedTri, ct);
+                }
+                if (t1) {
+                    const unsigned ct = (unsigned)(-(link1 + 1));
+                    sm.triq[nt + __popc(m0) + __popc(m1 & ltMask)] = descendA ? cd.pack(slot, ct, fixedTri) : cd.pack(slot, fixedTri, ct);
+                }
+                if (t0 || t1) atomicAdd(&sm.pending[slot], (t0 ? 1 : 0) + (t1 ? 1 : 0));
+                nt += __popc(m0) + __popc(m1);
+                if (nt > kQueueCap) cnt.error = 1;  // cannot happen (see the drain loop above); never silent
+            }
+            // inner survivors -> own LIFO, farther one first so the nearer one is searched first.
+            // The pushed entry already names the first child of whichever box the next step splits:
+            // the larger one unless it is a leaf ([EXT] FCL's firstOverSecond rule).
+            const bool s0 = ov0 && !leaf0, s1 = ov1 && !leaf1;
+            if (s0 || s1) {
+                auto entryFor = [&](unsigned childIdx, int childLink, float childSz) {
+                    // robot side / env side of the surviving pair
+                    const int linkR = descendA ? childLink : fixedLink, linkE = descendA ? fixedLink : childLink;
+                    const unsigned idxR = descendA ? childIdx : fixedIdx, idxE = descendA ? fixedIdx : childIdx;
+                    const float szR = descendA ? childSz : szF, szE = descendA ? szF : childSz;
+                    const bool nextA = linkE < 0 || (linkR >= 0 && szR > szE);
+                    return nextA ? ((unsigned)linkR | idxE << bitsA | 0x80000000u) : (idxR | (unsigned)linkE << bitsA);
+                };
+                const unsigned e0 = entryFor(child, link0, sz0), e1 = entryFor(child + 1, link1, sz1);
+                if (s0 && s1) {
+                    const bool zeroFirst = d0 > d1;  // push the farther first
+                    sm.stack[sp][lane] = zeroFirst ? e0 : e1;
+                    sm.stack[sp + 1][lane] = zeroFirst ? e1 : e0;
+                    sp += 2;
+                } else {
+                    sm.stack[sp][lane] = s0 ? e0 : e1;
+                    sp += 1;
+                }
+            }
+            __syncwarp();
+        }
     }
-    return ((unsigned long long)hitHi << 32) | hitLo;
 }
 
 template <typename E>
-__device__ __forceinline__ WarpSmem<E> &warpSmem() {
+__device__ __forceinline__ WarpSmem<E> warpSmem(int levels) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    return reinterpret_cast<WarpSmem<E> *>(smemRaw)[threadIdx.x >> 5];
+    WarpSmem<E> sm;
+    sm.carve(smemRaw + (threadIdx.x >> 5) * WarpSmem<E>::bytes(levels), levels);
+    sm.pending[threadIdx.x & 31u] = 0;
+    sm.pending[(threadIdx.x & 31u) + 32] = 0;
+    __syncwarp();
+    return sm;
 }
 
-// isValid(q) for a batch: one work item = 64 consecutive states.
+__device__ __forceinline__ void flushCounters(const WarpCounters &c, DevCounters *ctr, bool countStates) {
+    if ((threadIdx.x & 31u) == 0) {
+        atomicAdd(&ctr->bvTests, c.bv);
+        atomicAdd(&ctr->triTests, c.tri);
+        atomicAdd(&ctr->exactTests, c.exact);
+        if (countStates) atomicAdd(&ctr->states, c.states);
+        if (c.error) atomicExch(&ctr->overflow, 1u);
+    }
+}
+
 template <typename E>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
 checkStatesKernel(SceneDev sc, const double *__restrict__ states, unsigned long long n, uint8_t *__restrict__ valid,
-                  DevCounters *ctr, unsigned *workCounter) {
-    WarpSmem<E> &sm = warpSmem<E>();
-    const unsigned lane = threadIdx.x & 31u;
-    const Codec<E> cd{6, 6 + sc.bitsA};
-    const unsigned long long nChunks = (n + kChunk - 1) / kChunk;
-    unsigned long long nBv = 0, nTri = 0, nExact = 0;
-    unsigned overflow = 0;
-    const bool haveGeom = sc.nRobotNodes > 0 && sc.nEnvNodes > 0;
-    for (;;) {
-        unsigned long long ck = 0;
-        if (lane == 0) ck = atomicAdd(workCounter, 1u);
-        ck = __shfl_sync(kFull, ck, 0);
-        if (ck >= nChunks) break;
-        const unsigned long long base = ck * kChunk;
-        int top = 0;
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const unsigned slot = r * 32 + lane;
-            const bool ok = base + slot < n;
-            if (ok && haveGeom) {
-                double s[7];
-                const double *src = states + 7 * (base + slot);
-#pragma unroll
-                for (int k = 0; k < 7; ++k) s[k] = __ldg(src + k);
-                makeSlot(s, sc, sm.xf[slot]);
-            }
-            const unsigned m = __ballot_sync(kFull, ok && haveGeom);
-            if (ok && haveGeom) sm.stack[top + __popc(m & ((1u << lane) - 1u))] = cd.pack(slot, 0, 0);
-            top += __popc(m);
-        }
-        __syncwarp();
-        auto stateOf = [&](unsigned slot, double *s) {
-            const double *src = states + 7 * (base + slot);
-#pragma unroll
-            for (int k = 0; k < 7; ++k) s[k] = __ldg(src + k);
-        };
-        const unsigned long long hits = drainPool<E, false>(sm, sc, cd, top, stateOf, nBv, nTri, nExact, overflow);
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const unsigned slot = r * 32 + lane;
-            if (base + slot < n) valid[base + slot] = (uint8_t)(((hits >> slot) & 1ull) ? 0 : 1);
-        }
-        __syncwarp();
-    }
-    if (lane == 0) {
-        atomicAdd(&ctr->bvTests, nBv);
-        atomicAdd(&ctr->triTests, nTri);
-        atomicAdd(&ctr->exactTests, nExact);
-        if (overflow) atomicExch(&ctr->overflow, 1u);
-    }
+                  DevCounters *ctr, unsigned long long *workCounter) {
+    WarpSmem<E> sm = warpSmem<E>(sc.stackLevels);
+    StateSource src{states, n, valid, workCounter};
+    WarpCounters cnt;
+    runWarp<E>(sm, sc, src, cnt);
+    flushCounters(cnt, ctr, false);
 }
 
-// isValid(from,to) for a batch of edges.  Work items are (chunk c, edge e), c-major: chunk 0 of
-// every edge (the coarsest 64 samples incl. `to`) runs before any chunk 1, so an edge that dies
-// early never expands its fine samples.  States of chunk c: j = 64c + slot, i = bitrev_L(j)
-// with 2^L > steps; j = 0 is `to` itself (se3...:136), i in [1, steps-1] are the interpolated
-// states at t = i * (1/steps) (se3...:146,159).
 template <typename E>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
 checkEdgesKernel(SceneDev sc, const double *__restrict__ from, const double *__restrict__ to,
                  const unsigned *__restrict__ steps, unsigned long long nEdges, unsigned maxChunks, unsigned grab,
                  unsigned *dead, DevCounters *ctr, unsigned long long *workCounter) {
-    WarpSmem<E> &sm = warpSmem<E>();
-    const unsigned lane = threadIdx.x & 31u;
-    const Codec<E> cd{6, 6 + sc.bitsA};
-    const unsigned long long nItems = nEdges * maxChunks;
-    unsigned long long nBv = 0, nTri = 0, nExact = 0, nStates = 0;
-    unsigned overflow = 0;
-    const bool haveGeom = sc.nRobotNodes > 0 && sc.nEnvNodes > 0;
-    for (;;) {
-        unsigned long long first = 0;
-        if (lane == 0) first = atomicAdd(workCounter, (unsigned long long)grab);
-        first = __shfl_sync(kFull, first, 0);
-        if (first >= nItems) break;
-        // each lane inspects one item of the grab; live ones are processed one after another
-        const unsigned long long item = first + lane;
-        bool live = false;
-        unsigned myBits = 0;
-        if (lane < grab && item < nItems && haveGeom) {
-            const unsigned long long e = item % nEdges;
-            const unsigned c = (unsigned)(item / nEdges);
-            const unsigned st = __ldg(steps + e);
-            myBits = st ? 32 - __clz(st) : 0;  // 2^bits > steps
-            const unsigned nch = max(1u, (1u << myBits) >> 6);
-            live = c < nch && !((volatile unsigned *)dead)[e];
-        }
-        unsigned liveMask = __ballot_sync(kFull, live);
-        while (liveMask) {
-            const int src = __ffs(liveMask) - 1;
-            liveMask &= liveMask - 1;
-            const unsigned long long it = first + src;
-            const unsigned long long e = it % nEdges;
-            const unsigned c = (unsigned)(it / nEdges);
-            const unsigned bits = __shfl_sync(kFull, myBits, src);
-            const unsigned st = __ldg(steps + e);
-            const double *fr = from + 7 * e, *tt = to + 7 * e;
-            double a[7], b[7];
-#pragma unroll
-            for (int k = 0; k < 7; ++k) { a[k] = __ldg(fr + k); b[k] = __ldg(tt + k); }
-            const double delta = __ddiv_rn(1.0, (double)st);
-            auto stateOf = [&](unsigned slot, double *s) {
-                const unsigned j = c * kChunk + slot;
-                if (j == 0) {
-#pragma unroll
-                    for (int k = 0; k < 7; ++k) s[k] = b[k];
-                } else {
-                    interpolateD(a, b, dmul((double)bitrev(j, bits), delta), s);
-                }
-            };
-            int top = 0;
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const unsigned slot = r * 32 + lane;
-                const unsigned j = c * kChunk + slot;
-                const bool ok = j == 0 || (j < (1u << bits) && bitrev(j, bits) < st);
-                if (ok) {
-                    double s[7];
-                    stateOf(slot, s);
-                    makeSlot(s, sc, sm.xf[slot]);
-                }
-                const unsigned m = __ballot_sync(kFull, ok);
-                if (ok) sm.stack[top + __popc(m & ((1u << lane) - 1u))] = cd.pack(slot, 0, 0);
-                top += __popc(m);
-            }
-            __syncwarp();
-            nStates += top;
-            const unsigned long long hits = drainPool<E, true>(sm, sc, cd, top, stateOf, nBv, nTri, nExact, overflow);
-            if (hits && lane == 0) dead[e] = 1u;
-            __syncwarp();
-        }
-    }
-    if (lane == 0) {
-        atomicAdd(&ctr->bvTests, nBv);
-        atomicAdd(&ctr->triTests, nTri);
-        atomicAdd(&ctr->exactTests, nExact);
-        atomicAdd(&ctr->states, nStates);
-        if (overflow) atomicExch(&ctr->overflow, 1u);
-    }
+    WarpSmem<E> sm = warpSmem<E>(sc.stackLevels);
+    EdgeSource src{from, to, steps, nEdges, nEdges * maxChunks, grab, dead, workCounter};
+    WarpCounters cnt;
+    runWarp<E>(sm, sc, src, cnt);
+    flushCounters(cnt, ctr, true);
 }
 
 __global__ void deadToValidKernel(const unsigned *__restrict__ dead, unsigned long long n, uint8_t *__restrict__ valid) {
@@ -595,7 +890,7 @@ __global__ void deadToValidKernel(const unsigned *__restrict__ dead, unsigned lo
 }
 
 template <typename E>
-size_t smemBytes() { return sizeof(WarpSmem<E>) * kWarpsPerCta; }
+size_t smemBytes(const SceneDev &sc) { return WarpSmem<E>::bytes(sc.stackLevels) * kWarpsPerCta; }
 
 template <typename K>
 int gridFor(K kernel, size_t smem, int numSms) {
@@ -605,6 +900,38 @@ int gridFor(K kernel, size_t smem, int numSms) {
     return perSm * numSms;
 }
 
+template <typename E>
+cudaError_t launchStatesT(const SceneDev &sc, const double *dStates, size_t n, uint8_t *dValid, DevCounters *dCtr,
+                          unsigned long long *dWork, int numSms, cudaStream_t stream) {
+    auto k = checkStatesKernel<E>;
+    const size_t smem = smemBytes<E>(sc);
+    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    int grid = gridFor(k, smem, numSms);
+    // a warp wants at least ~2 refills of 32 states to be worth launching
+    const unsigned long long warpsWanted = (n + 63) / 64;
+    grid = (int)std::min<unsigned long long>(grid, (warpsWanted + kWarpsPerCta - 1) / kWarpsPerCta);
+    k<<<std::max(grid, 1), kWarpsPerCta * 32, smem, stream>>>(sc, dStates, n, dValid, dCtr, dWork);
+    return cudaGetLastError();
+}
+
+template <typename E>
+cudaError_t launchEdgesT(const SceneDev &sc, const double *dFrom, const double *dTo, const unsigned *dSteps, size_t n,
+                         unsigned maxChunks, unsigned *dDead, DevCounters *dCtr, unsigned long long *dWork, int numSms,
+                         cudaStream_t stream) {
+    auto k = checkEdgesKernel<E>;
+    const size_t smem = smemBytes<E>(sc);
+    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    int grid = gridFor(k, smem, numSms);
+    const unsigned long long nItems = (unsigned long long)n * maxChunks;
+    const unsigned grab = (unsigned)std::min<unsigned long long>(
+        32, std::max<unsigned long long>(1, nItems / (4ull * grid * kWarpsPerCta)));
+    grid = (int)std::min<unsigned long long>(grid, (nItems + kWarpsPerCta - 1) / kWarpsPerCta);
+    k<<<std::max(grid, 1), kWarpsPerCta * 32, smem, stream>>>(sc, dFrom, dTo, dSteps, n, maxChunks, grab, dDead, dCtr, dWork);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 cudaError_t launchCheckStates(const SceneDev &sc, const double *dStates, size_t n, uint8_t *dValid,
@@ -612,23 +939,8 @@ cudaError_t launchCheckStates(const SceneDev &sc, const double *dStates, size_t 
     if (n == 0) return cudaSuccess;
     cudaError_t err = cudaMemsetAsync(dWork, 0, sizeof(unsigned long long), stream);
     if (err != cudaSuccess) return err;
-    const unsigned long long nChunks = (n + kChunk - 1) / kChunk;
-    if (sc.wide) {
-        auto k = checkStatesKernel<unsigned long long>;
-        const size_t smem = smemBytes<unsigned long long>();
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int grid = gridFor(k, smem, numSms);
-        grid = (int)min((unsigned long long)grid, (nChunks + kWarpsPerCta - 1) / kWarpsPerCta);
-        k<<<grid, kWarpsPerCta * 32, smem, stream>>>(sc, dStates, n, dValid, dCtr, dWork);
-    } else {
-        auto k = checkStatesKernel<unsigned>;
-        const size_t smem = smemBytes<unsigned>();
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int grid = gridFor(k, smem, numSms);
-        grid = (int)min((unsigned long long)grid, (nChunks + kWarpsPerCta - 1) / kWarpsPerCta);
-        k<<<grid, kWarpsPerCta * 32, smem, stream>>>(sc, dStates, n, dValid, dCtr, dWork);
-    }
-    return cudaGetLastError();
+    return sc.wide ? launchStatesT<unsigned long long>(sc, dStates, n, dValid, dCtr, (unsigned long long *)dWork, numSms, stream)
+                   : launchStatesT<unsigned>(sc, dStates, n, dValid, dCtr, (unsigned long long *)dWork, numSms, stream);
 }
 
 cudaError_t launchCheckEdges(const SceneDev &sc, const double *dFrom, const double *dTo, const unsigned *dSteps,
@@ -641,27 +953,8 @@ cudaError_t launchCheckEdges(const SceneDev &sc, const double *dFrom, const doub
     if (err != cudaSuccess) return err;
     const unsigned bits = maxSteps ? 32 - __builtin_clz(maxSteps) : 0;
     const unsigned maxChunks = std::max(1u, (1u << bits) >> 6);
-    const unsigned long long nItems = (unsigned long long)n * maxChunks;
-    int grid;
-    unsigned grab;
-    if (sc.wide) {
-        auto k = checkEdgesKernel<unsigned long long>;
-        const size_t smem = smemBytes<unsigned long long>();
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        grid = gridFor(k, smem, numSms);
-        grab = (unsigned)std::min<unsigned long long>(32, std::max<unsigned long long>(1, nItems / (4ull * grid * kWarpsPerCta)));
-        grid = (int)std::min<unsigned long long>(grid, (nItems + kWarpsPerCta - 1) / kWarpsPerCta);
-        k<<<grid, kWarpsPerCta * 32, smem, stream>>>(sc, dFrom, dTo, dSteps, n, maxChunks, grab, dDead, dCtr, dWork);
-    } else {
-        auto k = checkEdgesKernel<unsigned>;
-        const size_t smem = smemBytes<unsigned>();
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        grid = gridFor(k, smem, numSms);
-        grab = (unsigned)std::min<unsigned long long>(32, std::max<unsigned long long>(1, nItems / (4ull * grid * kWarpsPerCta)));
-        grid = (int)std::min<unsigned long long>(grid, (nItems + kWarpsPerCta - 1) / kWarpsPerCta);
-        k<<<grid, kWarpsPerCta * 32, smem, stream>>>(sc, dFrom, dTo, dSteps, n, maxChunks, grab, dDead, dCtr, dWork);
-    }
-    err = cudaGetLastError();
+    err = sc.wide ? launchEdgesT<unsigned long long>(sc, dFrom, dTo, dSteps, n, maxChunks, dDead, dCtr, dWork, numSms, stream)
+                  : launchEdgesT<unsigned>(sc, dFrom, dTo, dSteps, n, maxChunks, dDead, dCtr, dWork, numSms, stream);
     if (err != cudaSuccess) return err;
     deadToValidKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dDead, n, dValid);
     return cudaGetLastError();
