@@ -108,6 +108,26 @@ typedef struct {
 } mplb_stats_t;
 int mplb_scene_stats(mplb_scene *scene, mplb_stats_t *out, int reset);
 
+/* ---------------------------------------------------------------------------------------- */
+/* Nearest neighbour: replaces nigh::Nigh<Node*,Space,NodeKey,Concurrent,...> as used by the
+ * planners (prrt.hpp:42,61,67,115; pcforest.hpp:51,81,86,107,193).  Keys are the scaled states
+ * (Scenario::scale).  metric 0 = SE3Space<double,so3w,l2w> on 7-double keys, metric 1 =
+ * L1Space<double,dim>.  Indices are insertion order; ties go to the lowest index. */
+int mplb_nn_create(int metric, int dim, double so3_weight, double l2_weight, int device,
+                   mplb_nn **out);
+void mplb_nn_destroy(mplb_nn *nn);
+int mplb_nn_insert(mplb_nn *nn, const double *keys, size_t n); /* host keys [n][dim] */
+size_t mplb_nn_size(const mplb_nn *nn);
+/* nearest(q): idx[i] = -1 and dist = +inf when the structure is empty */
+int mplb_nn_nearest(mplb_nn *nn, const double *queries, size_t nq, int64_t *idx, double *dist);
+/* nearest(nbh, q, k): [nq][k] ascending by (distance, index), padded with -1 / +inf */
+int mplb_nn_knearest(mplb_nn *nn, const double *queries, size_t nq, int k, int64_t *idx,
+                     double *dist);
+/* device-resident 1-NN: queries/idx/dist are device pointers, enqueued on `stream`, not synchronised;
+ * d_dist holds the device-evaluated distance (CUDA acos: may differ from the host value in the last bit) */
+int mplb_nn_nearest_device(mplb_nn *nn, const double *d_queries, size_t nq, int64_t *d_idx,
+                           double *d_dist, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

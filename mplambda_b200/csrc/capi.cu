@@ -57,6 +57,8 @@ DevBuf::~DevBuf() {
 
 CallCtx::~CallCtx() {
     if (hCtr) cudaFreeHost(hCtr);
+    for (auto e : events) cudaEventDestroy(e);
+    if (copyStream) cudaStreamDestroy(copyStream);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -71,6 +73,7 @@ CallCtx *SceneBase::acquire() {
     }
     auto *c = new CallCtx();
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMallocHost((void **)&c->hCtr, sizeof(DevCounters)) != cudaSuccess ||
         c->ctr.reserve(sizeof(DevCounters)) != MPLB_OK || c->work.reserve(64) != MPLB_OK) {
         delete c;
@@ -230,6 +233,18 @@ struct CtxGuard {
     }
 };
 
+// Large host batches are cut into stages so that the PCIe copy of stage k+1 overlaps the kernel
+// of stage k (input is 56 B/state, the kernel needs ~1 ns/state: the copy is the longer leg).
+static size_t pipelineStages(size_t n) {
+    static const long forced = [] {
+        const char *e = std::getenv("MPLB_PIPELINE_STAGES");
+        return e ? std::atol(e) : 0L;
+    }();
+    if (forced > 0) return std::min<size_t>((size_t)forced, std::max<size_t>(1, n));
+    const size_t minStage = 1u << 18;  // smaller launches lose more to their tails than the overlap wins
+    return std::max<size_t>(1, std::min<size_t>(8, n / minStage));
+}
+
 static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t *valid) {
     MPLB_CUDA(cudaSetDevice(sc->device));
     CallCtx *c = sc->acquire();
@@ -237,12 +252,30 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
     CtxGuard g{sc, c};
     int rc;
     if ((rc = c->in0.reserve(n * 7 * sizeof(double))) || (rc = c->out.reserve(n))) return rc;
+    const size_t stages = pipelineStages(n);
+    while (c->events.size() < stages) {
+        cudaEvent_t e;
+        MPLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->events.push_back(e);
+    }
     MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(DevCounters), c->stream));
-    MPLB_CUDA(cudaMemcpyAsync(c->in0.ptr, states, n * 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    MPLB_CUDA(launchCheckStates(sc->dev, (const double *)c->in0.ptr, n, (uint8_t *)c->out.ptr,
-                                (DevCounters *)c->ctr.ptr, (unsigned *)c->work.ptr, sc->numSms, c->stream));
-    sc->hLaunches += 1;
-    MPLB_CUDA(cudaMemcpyAsync(valid, c->out.ptr, n, cudaMemcpyDeviceToHost, c->stream));
+    const size_t per = (n + stages - 1) / stages;
+    double *dIn = (double *)c->in0.ptr;
+    uint8_t *dOut = (uint8_t *)c->out.ptr;
+    for (size_t k = 0; k < stages; ++k) {
+        const size_t lo = k * per, cnt = std::min(per, n - std::min(n, lo));
+        if (cnt == 0) break;
+        cudaStream_t cs = stages > 1 ? c->copyStream : c->stream;
+        MPLB_CUDA(cudaMemcpyAsync(dIn + 7 * lo, states + 7 * lo, cnt * 7 * sizeof(double), cudaMemcpyHostToDevice, cs));
+        if (stages > 1) {
+            MPLB_CUDA(cudaEventRecord(c->events[k], cs));
+            MPLB_CUDA(cudaStreamWaitEvent(c->stream, c->events[k], 0));
+        }
+        MPLB_CUDA(launchCheckStates(sc->dev, dIn + 7 * lo, cnt, dOut + lo, (DevCounters *)c->ctr.ptr,
+                                    (unsigned *)c->work.ptr, sc->numSms, c->stream));
+        sc->hLaunches += 1;
+        MPLB_CUDA(cudaMemcpyAsync(valid + lo, dOut + lo, cnt, cudaMemcpyDeviceToHost, c->stream));
+    }
     return finishCall(sc, c, n, nullptr);
 }
 

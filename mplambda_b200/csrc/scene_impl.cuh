@@ -26,7 +26,9 @@ struct DevBuf {
 // Everything one in-flight host call needs; borrowed from the scene so that concurrent callers
 // (the reference's OpenMP planner threads, prrt.hpp:140-152) never share a stream or a buffer.
 struct CallCtx {
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // kernels + verdict read-back
+    cudaStream_t copyStream = nullptr;  // host->device input copies of pipelined batches
+    std::vector<cudaEvent_t> events;    // one per pipeline stage
     DevBuf in0, in1, steps, dead, out, ctr, work, aux0, aux1;
     DevCounters *hCtr = nullptr;  // pinned
     std::vector<uint32_t> hSteps;

@@ -1,0 +1,85 @@
+"""GPU: nearest-neighbour kernels (C ABI mplb_nn_*) vs the oracle's exact brute force.
+Bar: indices bit-exact (ties to the lowest index), k-NN order identical; distances are
+recomputed on the host with the CPU path's arithmetic, so they are bit-exact too."""
+import numpy as np
+import pytest
+
+import mplambda_b200 as M
+from mplambda_b200.workload import se3_poses
+
+pytestmark = pytest.mark.gpu
+
+LO, HI = [-300, -200, -100], [300, 200, 100]
+
+
+@pytest.mark.parametrize("n,nq", [(1, 5), (7, 3), (1000, 257), (16384, 4096), (100003, 513)])
+def test_se3_nearest_matches_oracle(n, nq, oracle):
+    keys = se3_poses(n, LO, HI, 31)
+    qs = se3_poses(nq, LO, HI, 32)
+    nn = M.Nigh(M.nn.SE3)
+    assert nn.size() == 0
+    idx, dist = nn.nearest(qs[:2])
+    assert (idx == -1).all() and np.isinf(dist).all()            # empty structure: no neighbour
+    # insert in two batches (the planner inserts incrementally)
+    assert nn.insert(keys[: n // 2]) == 0
+    assert nn.insert(keys[n // 2:]) == n // 2
+    assert nn.size() == n
+    idx, dist = nn.nearest(qs)
+    widx, wdist = oracle.nn_nearest(keys, qs)
+    assert (idx == widx).all()
+    assert (dist == wdist).all()
+
+
+@pytest.mark.parametrize("n,nq,k", [(50, 20, 7), (5000, 300, 32), (20000, 1000, 45), (10, 4, 16)])
+def test_se3_knearest_matches_oracle(n, nq, k, oracle):
+    keys = se3_poses(n, LO, HI, 41)
+    qs = se3_poses(nq, LO, HI, 42)
+    nn = M.Nigh(M.nn.SE3)
+    nn.insert(keys)
+    idx, dist = nn.knearest(qs, k)
+    widx, wdist = oracle.nn_knearest(keys, qs, k)
+    assert (idx == widx).all()
+    assert (dist == wdist).all()
+    assert (np.diff(dist[:, :min(k, n)], axis=1) >= 0).all()      # ascending: pcforest.hpp:523-524 relies on it
+
+
+def test_l1_scaled_keys_and_ties(oracle):
+    rng = np.random.default_rng(3)
+    scale = np.array([10, 4, 2, 1, 1, 1, 1, 1.0])                 # FetchScenario::scale (fetch_scenario.hpp:42-45)
+    keys = rng.uniform(-2, 2, size=(3000, 8)) * scale
+    keys = np.concatenate([keys, keys[:100]])                     # exact duplicates: ties go to the lowest index
+    qs = np.concatenate([rng.uniform(-2, 2, size=(500, 8)) * scale, keys[:100]])
+    nn = M.Nigh(M.nn.L1, dim=8)
+    nn.insert(keys)
+    idx, dist = nn.nearest(qs)
+    widx, wdist = oracle.nn_nearest(keys, qs, metric="l1")
+    assert (idx == widx).all() and (dist == wdist).all()
+    assert (idx[-100:] == np.arange(100)).all() and (dist[-100:] == 0).all()
+    kidx, kdist = nn.knearest(qs, 9)
+    wkidx, wkdist = oracle.nn_knearest(keys, qs, 9, metric="l1")
+    assert (kidx == wkidx).all() and (kdist == wkdist).all()
+
+
+def test_device_resident_queries(oracle):
+    import torch
+    keys = se3_poses(30000, LO, HI, 51)
+    qs = se3_poses(2000, LO, HI, 52)
+    nn = M.Nigh(M.nn.SE3)
+    nn.insert(keys)
+    dq = torch.from_numpy(qs).cuda()
+    di = torch.empty(len(qs), dtype=torch.int64, device="cuda")
+    dd = torch.empty(len(qs), dtype=torch.float64, device="cuda")
+    nn.nearest_device(dq.data_ptr(), len(qs), di.data_ptr(), dd.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    widx, wdist = oracle.nn_nearest(keys, qs)
+    assert (di.cpu().numpy() == widx).all()
+    np.testing.assert_allclose(dd.cpu().numpy(), wdist, rtol=4e-16, atol=0)
+
+
+def test_bad_arguments():
+    nn = M.Nigh(M.nn.SE3)
+    nn.insert(se3_poses(10, LO, HI, 1))
+    with pytest.raises(M.MplbError):
+        nn.knearest(se3_poses(2, LO, HI, 2), 65)
+    with pytest.raises(ValueError):
+        nn.insert(np.zeros((3, 5)))
