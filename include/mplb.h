@@ -63,6 +63,17 @@ int mplb_scene_create_se3(const double *env_tris, size_t n_env, const double *ro
 int mplb_scene_create_se3_files(const char *env_path, const char *robot_path, double so3_weight,
                                 double l2_weight, double check_resolution, int device,
                                 mplb_scene **out);
+
+/* Fetch scene: replaces FetchScenario's constructor (fetch_scenario.hpp:48-63).  env_tris is the
+ * environment mesh as load(envMesh, false, true) yields it (identity root transform), env_frame the
+ * row-major 3x4 [R|t] of `envFrame`; the 12 collision primitives and link origins are the constants of
+ * fetch_robot.hpp:38-53,217-274.  States are the 8 joint values (fetch_robot.hpp:80-99); isValid(q) =
+ * !selfCollision && !inCollisionWith(env) (fetch_scenario.hpp:105-118); edges use the unscaled L1
+ * distance and linear interpolation (fetch_scenario.hpp:120-173). */
+int mplb_scene_create_fetch(const double *env_tris, size_t n_env, const double env_frame[12],
+                            double check_resolution, int device, mplb_scene **out);
+int mplb_scene_create_fetch_file(const char *env_path, const double env_frame[12],
+                                 double check_resolution, int device, mplb_scene **out);
 void mplb_scene_destroy(mplb_scene *scene);
 
 /* State layouts (host or device, float64):

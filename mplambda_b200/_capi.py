@@ -42,6 +42,8 @@ _SIGNATURES = {
                                         C.c_int, C.POINTER(C.c_void_p)]),
     "mplb_scene_create_se3_files": (C.c_int, [C.c_char_p, C.c_char_p, C.c_double, C.c_double, C.c_double, C.c_int,
                                               C.POINTER(C.c_void_p)]),
+    "mplb_scene_create_fetch": (C.c_int, [dp, C.c_size_t, dp, C.c_double, C.c_int, C.POINTER(C.c_void_p)]),
+    "mplb_scene_create_fetch_file": (C.c_int, [C.c_char_p, dp, C.c_double, C.c_int, C.POINTER(C.c_void_p)]),
     "mplb_scene_destroy": (None, [C.c_void_p]),
     "mplb_scene_state_dim": (C.c_int, [C.c_void_p]),
     "mplb_check_states": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

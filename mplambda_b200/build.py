@@ -6,9 +6,9 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmplb.so")
-SOURCES = ["capi.cu", "se3_kernels.cu", "nn_capi.cu", "nn_kernels.cu", "bvh_build.cpp", "collada.cpp"]
+SOURCES = ["capi.cu", "se3_kernels.cu", "nn_capi.cu", "nn_kernels.cu", "fetch_capi.cu", "fetch_kernels.cu", "bvh_build.cpp", "collada.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-O3,-Wall", "--shared", "-cudart", "shared"]
+              "-Xcompiler", "-fPIC,-O3,-Wall,-ffp-contract=off", "--shared", "-cudart", "shared"]
 
 
 def _nvcc():

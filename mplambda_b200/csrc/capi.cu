@@ -32,13 +32,6 @@ int fail(int code, const char *fmt, ...) {
     return code;
 }
 
-#define MPLB_CUDA(expr)                                                                             \
-    do {                                                                                            \
-        cudaError_t e_ = (expr);                                                                    \
-        if (e_ != cudaSuccess)                                                                      \
-            return fail(MPLB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
-
 // ---- device buffer that only grows
 int DevBuf::reserve(size_t bytes) {
     if (bytes <= cap) return MPLB_OK;
@@ -89,20 +82,10 @@ SceneBase::~SceneBase() {
     for (auto *c : freeCtx) delete c;
 }
 
-namespace {
-
 int bitsFor(size_t n) {
     int b = 1;
     while (((size_t)1 << b) < n) ++b;
     return b;
-}
-
-template <typename T>
-int upload(DevBuf &buf, const std::vector<T> &v) {
-    int rc = buf.reserve(v.size() * sizeof(T) + 16);
-    if (rc != MPLB_OK) return rc;
-    if (!v.empty()) MPLB_CUDA(cudaMemcpy(buf.ptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-    return MPLB_OK;
 }
 
 int selectDevice(int device, int *numSms) {
@@ -121,8 +104,6 @@ int selectDevice(int device, int *numSms) {
     return MPLB_OK;
 }
 
-}  // namespace
-
 struct Se3Scene : SceneBase {
     double so3w = 50, l2w = 1, invStep = 10;
     SceneDev dev{};
@@ -130,8 +111,18 @@ struct Se3Scene : SceneBase {
     size_t nEnvTris = 0, nRobotTris = 0;
 
     Se3Scene() { stateDim = 7; }
+    int checkStates(const double *states, size_t n, uint8_t *valid) override;
+    int checkEdges(const double *from, const double *to, size_t n, uint8_t *valid, uint64_t *statesChecked) override;
+    int planEdges(const double *from, const double *to, size_t n, uint32_t *steps) const override {
+        for (size_t i = 0; i < n; ++i) {
+            uint64_t st = edgeSteps(from + 7 * i, to + 7 * i);
+            if (!(st < (1ull << 31))) return fail(MPLB_ERR_INVALID, "edge %zu: step count out of range", i);
+            steps[i] = (uint32_t)st;
+        }
+        return MPLB_OK;
+    }
 
-    double distance(const double *a, const double *b) const {
+    double distance(const double *a, const double *b) const override {
         // nigh SE3Space<S,so3w,l2w> [EXT]: so3w * acos(|qa . qb|) + l2w * ||ta - tb||
         double d = std::fabs(((a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]) + a[3] * b[3]);
         double so3 = d < 1.0 ? std::acos(d) : 0.0;
@@ -225,14 +216,6 @@ static int finishCall(SceneBase *sc, CallCtx *c, size_t checks, uint64_t *states
     return MPLB_OK;
 }
 
-struct CtxGuard {
-    SceneBase *sc;
-    CallCtx *c;
-    ~CtxGuard() {
-        if (c) sc->release(c);
-    }
-};
-
 // Large host batches are cut into stages so that the PCIe copy of stage k+1 overlaps the kernel
 // of stage k (input is 56 B/state, the kernel needs ~1 ns/state: the copy is the longer leg).
 static size_t pipelineStages(size_t n) {
@@ -311,6 +294,11 @@ static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, siz
     sc->hLaunches += 2;
     MPLB_CUDA(cudaMemcpyAsync(valid, c->out.ptr, n, cudaMemcpyDeviceToHost, c->stream));
     return finishCall(sc, c, 0, statesChecked);
+}
+
+int Se3Scene::checkStates(const double *states, size_t n, uint8_t *valid) { return se3CheckStates(this, states, n, valid); }
+int Se3Scene::checkEdges(const double *from, const double *to, size_t n, uint8_t *valid, uint64_t *statesChecked) {
+    return se3CheckEdges(this, from, to, n, valid, statesChecked);
 }
 
 }  // namespace mplb
@@ -396,8 +384,7 @@ int mplb_check_states(mplb_scene *scene, const double *states, size_t n, uint8_t
     if (!scene) return fail(MPLB_ERR_INVALID, "scene is null");
     if (n == 0) return MPLB_OK;
     if (!states || !valid) return fail(MPLB_ERR_INVALID, "null buffer");
-    if (auto *s = dynamic_cast<Se3Scene *>(base(scene))) return se3CheckStates(s, states, n, valid);
-    return fail(MPLB_ERR_INVALID, "unsupported scene kind");
+    return base(scene)->checkStates(states, n, valid);
 }
 
 int mplb_check_edges(mplb_scene *scene, const double *from, const double *to, size_t n, uint8_t *valid,
@@ -406,8 +393,7 @@ int mplb_check_edges(mplb_scene *scene, const double *from, const double *to, si
     if (states_checked) *states_checked = 0;
     if (n == 0) return MPLB_OK;
     if (!from || !to || !valid) return fail(MPLB_ERR_INVALID, "null buffer");
-    if (auto *s = dynamic_cast<Se3Scene *>(base(scene))) return se3CheckEdges(s, from, to, n, valid, states_checked);
-    return fail(MPLB_ERR_INVALID, "unsupported scene kind");
+    return base(scene)->checkEdges(from, to, n, valid, states_checked);
 }
 
 int mplb_check_states_device(mplb_scene *scene, const double *d_states, size_t n, uint8_t *d_valid, void *stream) {
@@ -428,14 +414,7 @@ int mplb_edges_plan(mplb_scene *scene, const double *from, const double *to, siz
     if (!scene) return fail(MPLB_ERR_INVALID, "scene is null");
     if (n == 0) return MPLB_OK;
     if (!from || !to || !steps) return fail(MPLB_ERR_INVALID, "null buffer");
-    auto *s = dynamic_cast<Se3Scene *>(base(scene));
-    if (!s) return fail(MPLB_ERR_INVALID, "unsupported scene kind");
-    for (size_t i = 0; i < n; ++i) {
-        uint64_t st = s->edgeSteps(from + 7 * i, to + 7 * i);
-        if (!(st < (1ull << 31))) return fail(MPLB_ERR_INVALID, "edge %zu: step count out of range", i);
-        steps[i] = (uint32_t)st;
-    }
-    return MPLB_OK;
+    return base(scene)->planEdges(from, to, n, steps);
 }
 
 int mplb_check_edges_device(mplb_scene *scene, const double *d_from, const double *d_to, const uint32_t *d_steps,
@@ -461,8 +440,7 @@ int mplb_check_edges_device(mplb_scene *scene, const double *d_from, const doubl
 
 double mplb_distance(const mplb_scene *scene, const double *a, const double *b) {
     if (!scene || !a || !b) return NAN;
-    if (auto *s = dynamic_cast<const Se3Scene *>(base(scene))) return s->distance(a, b);
-    return NAN;
+    return base(scene)->distance(a, b);
 }
 
 int mplb_scene_stats(mplb_scene *scene, mplb_stats_t *out, int reset) {

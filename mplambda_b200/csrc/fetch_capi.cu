@@ -1,0 +1,303 @@
+// C-ABI of the Fetch scenario (include/mplb.h: mplb_scene_create_fetch*): replaces FetchScenario's
+// constructor and validity methods (reference include/mpl/demo/fetch_scenario.hpp:48-63,105-173).
+#include "../../include/mplb.h"
+#include "fetch_device.cuh"
+#include "mplb_host.hpp"
+#include "scene_impl.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <vector>
+
+namespace mplb {
+namespace {
+
+// ---- Origin(xyz, rpy) of fetch_robot.hpp:23-35 with Eigen's arithmetic ([EXT]): AngleAxis products go
+// through quaternions, then Quaternion::toRotationMatrix.  Same operation order as the CPU path.
+void quatFromAA(double angle, int axis, double q[4]) {
+    const double h = 0.5 * angle, s = std::sin(h);
+    q[0] = q[1] = q[2] = 0;
+    q[axis] = s;
+    q[3] = std::cos(h);
+}
+void quatMul(const double a[4], const double b[4], double r[4]) {
+    r[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+    r[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+    r[1] = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+    r[2] = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+}
+void originFrame(double tx, double ty, double tz, double roll, double pitch, double yaw, double out[12]) {
+    double qz[4], qy[4], qx[4], a[4], q[4];
+    quatFromAA(yaw, 2, qz);
+    quatFromAA(pitch, 1, qy);
+    quatFromAA(roll, 0, qx);
+    quatMul(qz, qy, a);
+    quatMul(a, qx, q);
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double tx2 = 2 * x, ty2 = 2 * y, tz2 = 2 * z;
+    const double twx = tx2 * w, twy = ty2 * w, twz = tz2 * w;
+    const double txx = tx2 * x, txy = ty2 * x, txz = tz2 * x;
+    const double tyy = ty2 * y, tyz = tz2 * y, tzz = tz2 * z;
+    out[0] = 1 - (tyy + tzz); out[1] = txy - twz;       out[2] = txz + twy;        out[3] = tx;
+    out[4] = txy + twz;       out[5] = 1 - (txx + tzz); out[6] = tyz - twx;        out[7] = ty;
+    out[8] = txz - twy;       out[9] = tyz + twx;       out[10] = 1 - (txx + tyy); out[11] = tz;
+}
+
+constexpr size_t kBatch = 1u << 16;  // states per launch group (frames scratch: 144 doubles per state)
+
+}  // namespace
+
+struct FetchScene : SceneBase {
+    double invStep = 100;
+    FetchSceneDev dev{};
+    DevBuf envNodes, envTris64;
+    size_t nEnvTris = 0;
+    std::atomic<uint64_t> hPairTests{0}, hLeafTests{0};
+
+    FetchScene() { stateDim = 8; }
+
+    // nigh L1Space<S,8>, unscaled (fetch_scenario.hpp:127)
+    double distance(const double *a, const double *b) const override {
+        double s = 0;
+        for (int i = 0; i < 8; ++i) s += std::fabs(a[i] - b[i]);
+        return s;
+    }
+    uint64_t edgeSteps(const double *a, const double *b) const { return (uint64_t)std::ceil(distance(a, b) * invStep); }
+    int planEdges(const double *from, const double *to, size_t n, uint32_t *steps) const override {
+        for (size_t i = 0; i < n; ++i) {
+            const uint64_t st = edgeSteps(from + 8 * i, to + 8 * i);
+            if (!(st < (1ull << 31))) return fail(MPLB_ERR_INVALID, "edge %zu: step count out of range", i);
+            steps[i] = (uint32_t)st;
+        }
+        return MPLB_OK;
+    }
+
+    int reserveScratch(CallCtx *c, size_t n) {
+        int rc;
+        if ((rc = c->aux0.reserve(n * 144 * sizeof(double))) || (rc = c->aux1.reserve(n)) ||
+            (rc = c->aux2.reserve(n * sizeof(unsigned))))
+            return rc;
+        return MPLB_OK;
+    }
+
+    int finish(CallCtx *c) {
+        FetchCounters h{};
+        cudaError_t e = cudaMemcpyAsync(&h, c->ctr.ptr, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) return fail(MPLB_ERR_CUDA, "device work failed: %s", cudaGetErrorString(e));
+        if (h.error) return fail(MPLB_ERR_CUDA, "device traversal bookkeeping error (Fetch stack / MPR iteration guard)");
+        hBv += h.bvTests;
+        hPairTests += h.pairTests;
+        hLeafTests += h.leafTests;
+        hTri += h.leafTests;
+        return MPLB_OK;
+    }
+
+    int checkStates(const double *states, size_t n, uint8_t *valid) override {
+        MPLB_CUDA(cudaSetDevice(device));
+        CallCtx *c = acquire();
+        if (!c) return fail(MPLB_ERR_CUDA, "could not create a call context (stream / pinned memory)");
+        CtxGuard g{this, c};
+        const size_t nb = std::min(n, kBatch);
+        int rc;
+        if ((rc = c->in0.reserve(nb * 8 * sizeof(double))) || (rc = c->out.reserve(nb)) || (rc = reserveScratch(c, nb)))
+            return rc;
+        MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(FetchCounters), c->stream));
+        for (size_t lo = 0; lo < n; lo += kBatch) {
+            const size_t cnt = std::min(kBatch, n - lo);
+            MPLB_CUDA(cudaMemcpyAsync(c->in0.ptr, states + 8 * lo, cnt * 8 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            MPLB_CUDA(launchFetchStates(dev, (const double *)c->in0.ptr, cnt, (double *)c->aux0.ptr,
+                                        (unsigned char *)c->aux1.ptr, (unsigned *)c->aux2.ptr, (uint8_t *)c->out.ptr,
+                                        (FetchCounters *)c->ctr.ptr, c->stream));
+            hLaunches += 3;
+            MPLB_CUDA(cudaMemcpyAsync(valid + lo, c->out.ptr, cnt, cudaMemcpyDeviceToHost, c->stream));
+        }
+        hChecks += n;
+        return finish(c);
+    }
+
+    // isValid(from,to) (fetch_scenario.hpp:120-173): verdict = valid(to) AND every interpolated sample.
+    // Pass 1 tests `to` and up to 15 evenly spread samples of every edge; pass 2 the remaining samples
+    // of the edges still alive (the device skips samples of edges that died meanwhile).
+    int checkEdges(const double *from, const double *to, size_t n, uint8_t *valid, uint64_t *statesChecked) override {
+        MPLB_CUDA(cudaSetDevice(device));
+        CallCtx *c = acquire();
+        if (!c) return fail(MPLB_ERR_CUDA, "could not create a call context (stream / pinned memory)");
+        CtxGuard g{this, c};
+        c->hSteps.resize(n);
+        int rc = planEdges(from, to, n, c->hSteps.data());
+        if (rc != MPLB_OK) return rc;
+        const size_t sb = n * 8 * sizeof(double);
+        if ((rc = c->in0.reserve(sb)) || (rc = c->in1.reserve(sb)) || (rc = c->steps.reserve(n * 4)) ||
+            (rc = c->dead.reserve(n * 4)) || (rc = c->aux3.reserve(kBatch * 8)) || (rc = reserveScratch(c, kBatch)))
+            return rc;
+        MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(FetchCounters), c->stream));
+        MPLB_CUDA(cudaMemsetAsync(c->dead.ptr, 0, n * 4, c->stream));
+        MPLB_CUDA(cudaMemcpyAsync(c->in0.ptr, from, sb, cudaMemcpyHostToDevice, c->stream));
+        MPLB_CUDA(cudaMemcpyAsync(c->in1.ptr, to, sb, cudaMemcpyHostToDevice, c->stream));
+        MPLB_CUDA(cudaMemcpyAsync(c->steps.ptr, c->hSteps.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+
+        std::vector<unsigned long long> items;
+        std::vector<unsigned> dead(n, 0);
+        items.reserve(kBatch);
+        uint64_t launched = 0;
+        auto flush = [&]() -> int {
+            if (items.empty()) return MPLB_OK;
+            // the item buffer is reused: wait for the previous group before overwriting it
+            MPLB_CUDA(cudaStreamSynchronize(c->stream));
+            MPLB_CUDA(cudaMemcpyAsync(c->aux3.ptr, items.data(), items.size() * 8, cudaMemcpyHostToDevice, c->stream));
+            MPLB_CUDA(launchFetchEdgeItems(dev, (const double *)c->in0.ptr, (const double *)c->in1.ptr,
+                                           (const unsigned *)c->steps.ptr, (const unsigned long long *)c->aux3.ptr,
+                                           items.size(), (unsigned *)c->dead.ptr, (double *)c->aux0.ptr,
+                                           (unsigned char *)c->aux1.ptr, (unsigned *)c->aux2.ptr,
+                                           (FetchCounters *)c->ctr.ptr, c->stream));
+            hLaunches += 3;
+            launched += items.size();
+            MPLB_CUDA(cudaStreamSynchronize(c->stream));
+            items.clear();
+            return MPLB_OK;
+        };
+        auto refreshDead = [&]() -> int {
+            MPLB_CUDA(cudaMemcpyAsync(dead.data(), c->dead.ptr, n * 4, cudaMemcpyDeviceToHost, c->stream));
+            MPLB_CUDA(cudaStreamSynchronize(c->stream));
+            return MPLB_OK;
+        };
+        auto isCoarse = [](uint32_t k, uint32_t st) {  // k = round-down(j * st / 16) for some j in 1..15
+            if (st < 2) return false;
+            for (uint32_t j = 1; j < 16; ++j)
+                if ((uint64_t)j * st / 16 == k) return k >= 1 && k < st;
+            return false;
+        };
+        // pass 1
+        for (size_t e = 0; e < n; ++e) {
+            const uint32_t st = c->hSteps[e];
+            items.push_back(((unsigned long long)e << 32) | st);  // `to`
+            uint32_t prev = 0;
+            for (uint32_t j = 1; j < 16 && st >= 2; ++j) {
+                const uint32_t k = (uint32_t)((uint64_t)j * st / 16);
+                if (k >= 1 && k < st && k != prev) items.push_back(((unsigned long long)e << 32) | k);
+                prev = k;
+            }
+            if (items.size() + 16 > kBatch && (rc = flush())) return rc;
+        }
+        if ((rc = flush()) || (rc = refreshDead())) return rc;
+        // pass 2
+        size_t sinceRefresh = 0;
+        for (size_t e = 0; e < n; ++e) {
+            if (dead[e]) continue;
+            const uint32_t st = c->hSteps[e];
+            for (uint32_t k = 1; k < st; ++k) {
+                if (isCoarse(k, st)) continue;
+                items.push_back(((unsigned long long)e << 32) | k);
+                if (items.size() == kBatch) {
+                    if ((rc = flush())) return rc;
+                    if (++sinceRefresh >= 4) {
+                        if ((rc = refreshDead())) return rc;
+                        sinceRefresh = 0;
+                        if (dead[e]) break;
+                    }
+                }
+            }
+        }
+        if ((rc = flush()) || (rc = refreshDead())) return rc;
+        for (size_t e = 0; e < n; ++e) valid[e] = dead[e] ? 0 : 1;
+        hChecks += launched;
+        if (statesChecked) *statesChecked = launched;
+        return finish(c);
+    }
+};
+
+static int createFetch(const double *envTris, size_t nEnv, const double envFrame[12], double res, int device,
+                       mplb_scene **out) {
+    if (!out) return fail(MPLB_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (nEnv && !envTris) return fail(MPLB_ERR_INVALID, "null triangle array");
+    if (!envFrame) return fail(MPLB_ERR_INVALID, "null environment frame");
+    if (!(res > 0)) return fail(MPLB_ERR_INVALID, "check_resolution must be > 0");
+    for (size_t i = 0; i < 9 * nEnv; ++i)
+        if (!std::isfinite(envTris[i])) return fail(MPLB_ERR_INVALID, "non-finite environment vertex");
+    for (int i = 0; i < 12; ++i)
+        if (!std::isfinite(envFrame[i])) return fail(MPLB_ERR_INVALID, "non-finite environment frame");
+    int numSms = 0;
+    int rc = selectDevice(device, &numSms);
+    if (rc != MPLB_OK) return rc;
+    FlatBvh env = buildBvh(envTris, nEnv);
+    if (env.depth > 36) return fail(MPLB_ERR_INVALID, "environment hierarchy too deep (%d levels)", env.depth);
+    auto sc = std::make_unique<FetchScene>();
+    sc->device = device;
+    sc->numSms = numSms;
+    sc->invStep = 1 / res;
+    sc->nEnvTris = nEnv;
+    if ((rc = upload(sc->envNodes, env.nodes)) || (rc = upload(sc->envTris64, env.tris64))) return rc;
+    if ((rc = sc->globalCtr.reserve(sizeof(DevCounters)))) return rc;
+    MPLB_CUDA(cudaMemset(sc->globalCtr.ptr, 0, sizeof(DevCounters)));
+    FetchSceneDev &d = sc->dev;
+    d.envNodes = (const float4 *)sc->envNodes.ptr;
+    d.envTris64 = (const double *)sc->envTris64.ptr;
+    d.nEnvNodes = (int)env.nodes.size();
+    std::memcpy(d.envFrame, envFrame, sizeof(d.envFrame));
+    // fetch_robot.hpp:217-274 (link -> geometry origins), geometry order of fetch_robot.hpp:38-53
+    originFrame(0, 0, 0.1975, 0, 0, 0, d.origins + 12 * 0);
+    originFrame(-0.09, 0, 0.31, 0, 0, 0, d.origins + 12 * 1);
+    originFrame(0, 0, -0.025, 0, 0, 0, d.origins + 12 * 2);
+    originFrame(0, -0.0025, 0, 1.5708, 0, 0, d.origins + 12 * 3);
+    originFrame(-0.04, 0, 0, 0, 1.5708, 0, d.origins + 12 * 4);
+    originFrame(0, 0, 0, 1.5708, 0, 0, d.origins + 12 * 5);
+    originFrame(-0.04, 0, 0, 0, 1.5708, 0, d.origins + 12 * 6);
+    originFrame(0, -0.01, 0, 1.5708, 0, 0, d.origins + 12 * 7);
+    originFrame(-0.045, 0, 0, 0, 1.5708, 0, d.origins + 12 * 8);
+    originFrame(0, 0, 0, 0, 0, 0, d.origins + 12 * 9);  // gripper: the link frame itself
+    originFrame(0.053125, 0, 0.603001417713939, 0, 0, 0, d.origins + 12 * 10);
+    originFrame(0.053125, 0, 0.603001417713939 + 0.115 / 2, 0, 0, 0, d.origins + 12 * 11);
+    // fetch_robot.hpp:38-53
+    d.shapes[0] = {2, 0.29, (0.32 - 0.02) / 2, 0};
+    d.shapes[1] = {0, (0.18 + 0.08) / 2, 0.34 / 2, 1.5 / 2};
+    d.shapes[2] = {1, 0.0525, 0.29 / 2, 0};
+    d.shapes[3] = {2, 0.06, 0.145 / 2, 0};
+    d.shapes[4] = {1, 0.0525, 0.24 / 2, 0};
+    d.shapes[5] = {2, 0.0525, 0.14 / 2, 0};
+    d.shapes[6] = {1, 0.0525, 0.215 / 2, 0};
+    d.shapes[7] = {2, 0.0525, 0.155 / 2, 0};
+    d.shapes[8] = {1, 0.0525, 0.09 / 2, 0};
+    d.shapes[9] = {0, (0.12 + 0.0625 * 2) / 2, 0.125 / 2, 0.075 / 2};
+    d.shapes[10] = {1, 0.085 * 1.1, (0.04 * 1.1) / 2, 0};
+    d.shapes[11] = {2, 0.24 * 1.05, (0.115 * 1.05) / 2, 0};
+    sc->envNodeCount = env.nodes.size();
+    sc->robotNodeCount = 12;
+    *out = reinterpret_cast<mplb_scene *>(static_cast<SceneBase *>(sc.release()));
+    return MPLB_OK;
+}
+
+}  // namespace mplb
+
+using namespace mplb;
+
+extern "C" {
+
+int mplb_scene_create_fetch(const double *env_tris, size_t n_env, const double env_frame[12], double check_resolution,
+                            int device, mplb_scene **out) {
+    try {
+        return createFetch(env_tris, n_env, env_frame, check_resolution, device, out);
+    } catch (const std::exception &e) {
+        return fail(MPLB_ERR_INVALID, "%s", e.what());
+    }
+}
+
+int mplb_scene_create_fetch_file(const char *env_path, const double env_frame[12], double check_resolution, int device,
+                                 mplb_scene **out) {
+    if (!env_path) return fail(MPLB_ERR_INVALID, "null path");
+    try {
+        // fetch_scenario.hpp:54: MeshLoad<Mesh>::load(envMesh, false, true)
+        TriangleSoup env = loadCollada(env_path, false, true);
+        return createFetch(env.tris.data(), env.size(), env_frame, check_resolution, device, out);
+    } catch (const std::invalid_argument &e) {
+        return fail(MPLB_ERR_IO, "%s", e.what());
+    } catch (const std::exception &e) {
+        return fail(MPLB_ERR_INVALID, "%s", e.what());
+    }
+}
+
+}  // extern "C"

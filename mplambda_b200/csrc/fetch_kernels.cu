@@ -1,0 +1,601 @@
+// Fetch 8-DOF arm validity kernels for sm_100a.
+//
+// Device replacement for the work behind FetchScenario::isValid (reference
+// include/mpl/demo/fetch_scenario.hpp:105-173):
+//   FetchRobot::fk() + tf*Link()      include/mpl/demo/fetch_robot.hpp:217-315   (12 geometry frames)
+//   FetchRobot::selfCollision()       include/mpl/demo/fetch_robot.hpp:502-584   (24 ordered shape pairs + floor)
+//   FetchRobot::inCollisionWith()     include/mpl/demo/fetch_robot.hpp:586-647   (12 shapes vs the environment mesh)
+// whose arithmetic is FCL + libccd ([EXT]): shape pairs go through libccd's MPR boolean test
+// (ccdMPRIntersect) with FCL's support functions, Box x Box through FCL's boxBox2, mesh-vs-shape
+// through an OBB hierarchy traversal with an MPR shape-triangle leaf test.
+//
+// Everything that decides a verdict runs in FP64 with the oracle's operation order (no FMA
+// contraction: __dmul_rn/__dadd_rn, IEEE sqrt/div), so verdicts are bit-identical to the CPU path
+// up to CUDA's sin/cos in the forward kinematics (<= 2 ulp).  FP32 is only used for conservative
+// culling: an OBB-OBB separating-axis prefilter in front of each MPR pair and the environment
+// hierarchy traversal, both with a slack far above the FP32 error, so they can only skip tests
+// whose answer is "disjoint".
+//
+// Kernel A (one thread per state): FK -> 12 frames (kept for kernel B), 24 pair tests with early
+// exit, floor clearance.  Kernel B (one thread per (state, shape)): depth-first traversal of the
+// environment hierarchy with a private stack, exact MPR at the leaves, first hit wins.
+#include "fetch_device.cuh"
+#include "device_math.cuh"
+
+#include <cfloat>
+
+namespace mplb {
+namespace {
+
+struct FrameD { double R[3][3]; double t[3]; };
+
+// ---- Eigen-order frame algebra (oracle/mplb_oracle_fetch.inc: frame_translate / frame_rotate / frame_mul)
+__device__ void frameTranslate(FrameD &f, double x, double y, double z) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        f.t[i] = dadd(f.t[i], dadd(dadd(dmul(f.R[i][0], x), dmul(f.R[i][1], y)), dmul(f.R[i][2], z)));
+}
+__device__ void mat3Mul(const double A[3][3], const double B[3][3], double C[3][3]) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            C[i][j] = dadd(dadd(dmul(A[i][0], B[0][j]), dmul(A[i][1], B[1][j])), dmul(A[i][2], B[2][j]));
+}
+// Eigen AngleAxis::toRotationMatrix about a unit coordinate axis, then linear *= M
+__device__ void frameRotate(FrameD &f, double angle, int axis) {
+    double ax[3] = {0, 0, 0};
+    ax[axis] = 1;
+    double s, c;
+    sincos(angle, &s, &c);
+    const double sa[3] = {dmul(s, ax[0]), dmul(s, ax[1]), dmul(s, ax[2])};
+    const double omc = dsub(1, c);
+    const double c1[3] = {dmul(omc, ax[0]), dmul(omc, ax[1]), dmul(omc, ax[2])};
+    double M[3][3], tmp;
+    tmp = dmul(c1[0], ax[1]); M[0][1] = dsub(tmp, sa[2]); M[1][0] = dadd(tmp, sa[2]);
+    tmp = dmul(c1[0], ax[2]); M[0][2] = dadd(tmp, sa[1]); M[2][0] = dsub(tmp, sa[1]);
+    tmp = dmul(c1[1], ax[2]); M[1][2] = dsub(tmp, sa[0]); M[2][1] = dadd(tmp, sa[0]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) M[i][i] = dadd(dmul(c1[i], ax[i]), c);
+    double L[3][3];
+    mat3Mul(f.R, M, L);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) f.R[i][j] = L[i][j];
+}
+__device__ void frameMul(const FrameD &a, const double *b /* row-major 3x4 */, FrameD &r) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            r.R[i][j] = dadd(dadd(dmul(a.R[i][0], b[0 + j]), dmul(a.R[i][1], b[4 + j])), dmul(a.R[i][2], b[8 + j]));
+        r.t[i] = dadd(dadd(dadd(dmul(a.R[i][0], b[3]), dmul(a.R[i][1], b[7])), dmul(a.R[i][2], b[11])), a.t[i]);
+    }
+}
+
+// ---- libccd objects ([EXT] fcl gjk_libccd-inl.h), mirror of the oracle's ccd_obj
+struct CcdObj {
+    int kind;  // 0 box, 1 capsule, 2 cylinder, 3 triangle
+    double pos[3], rot[4], rotInv[4];
+    double a, b, c;
+    D3 p[3], cen;
+};
+
+constexpr double kCcdEps = DBL_EPSILON;
+__device__ __forceinline__ bool ccdIsZero(double x) { return fabs(x) < kCcdEps; }
+__device__ __forceinline__ bool ccdEq(double a, double b) {
+    const double ab = fabs(dsub(a, b));
+    if (ab < kCcdEps) return true;
+    a = fabs(a);
+    b = fabs(b);
+    return b > a ? ab < dmul(kCcdEps, b) : ab < dmul(kCcdEps, a);
+}
+__device__ __forceinline__ bool ccdVecEq(D3 a, D3 b) { return ccdEq(a.x, b.x) && ccdEq(a.y, b.y) && ccdEq(a.z, b.z); }
+__device__ __forceinline__ double ccdSign(double x) { return ccdIsZero(x) ? 0.0 : (x < 0 ? -1.0 : 1.0); }
+__device__ __forceinline__ D3 d3add(D3 a, D3 b) { return {dadd(a.x, b.x), dadd(a.y, b.y), dadd(a.z, b.z)}; }
+__device__ __forceinline__ D3 ccdNormalize(D3 v) {
+    const double d = __ddiv_rn(1.0, __dsqrt_rn(d3dot(v, v)));
+    return {dmul(v.x, d), dmul(v.y, d), dmul(v.z, d)};
+}
+__device__ __forceinline__ D3 d3neg(D3 v) { return {dmul(v.x, -1.0), dmul(v.y, -1.0), dmul(v.z, -1.0)}; }
+// ccdQuatRotVec (libccd 2.1)
+__device__ D3 quatRot(D3 v, const double q[4]) {
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double c1x = dadd(dsub(dmul(y, v.z), dmul(z, v.y)), dmul(w, v.x));
+    const double c1y = dadd(dsub(dmul(z, v.x), dmul(x, v.z)), dmul(w, v.y));
+    const double c1z = dadd(dsub(dmul(x, v.y), dmul(y, v.x)), dmul(w, v.z));
+    const double c2x = dsub(dmul(y, c1z), dmul(z, c1y));
+    const double c2y = dsub(dmul(z, c1x), dmul(x, c1z));
+    const double c2z = dsub(dmul(x, c1y), dmul(y, c1x));
+    return {dadd(v.x, dmul(2, c2x)), dadd(v.y, dmul(2, c2y)), dadd(v.z, dmul(2, c2z))};
+}
+// Eigen Quaternion(Matrix3) [EXT]
+__device__ void quatFromR(const double m[3][3], double q[4]) {
+    double t = dadd(dadd(m[0][0], m[1][1]), m[2][2]);
+    if (t > 0) {
+        t = __dsqrt_rn(dadd(t, 1.0));
+        q[3] = dmul(0.5, t);
+        t = __ddiv_rn(0.5, t);
+        q[0] = dmul(dsub(m[2][1], m[1][2]), t);
+        q[1] = dmul(dsub(m[0][2], m[2][0]), t);
+        q[2] = dmul(dsub(m[1][0], m[0][1]), t);
+    } else {
+        int i = 0;
+        if (m[1][1] > m[0][0]) i = 1;
+        if (m[2][2] > m[i][i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = __dsqrt_rn(dadd(dsub(dsub(m[i][i], m[j][j]), m[k][k]), 1.0));
+        q[i] = dmul(0.5, t);
+        t = __ddiv_rn(0.5, t);
+        q[3] = dmul(dsub(m[k][j], m[j][k]), t);
+        q[j] = dmul(dadd(m[j][i], m[i][j]), t);
+        q[k] = dmul(dadd(m[k][i], m[i][k]), t);
+    }
+}
+__device__ void objSetFrame(CcdObj &o, const FrameD &f) {
+    o.pos[0] = f.t[0]; o.pos[1] = f.t[1]; o.pos[2] = f.t[2];
+    quatFromR(f.R, o.rot);
+    const double len2 = dadd(dadd(dadd(dmul(o.rot[0], o.rot[0]), dmul(o.rot[1], o.rot[1])), dmul(o.rot[2], o.rot[2])),
+                             dmul(o.rot[3], o.rot[3]));
+    const double s = __ddiv_rn(1.0, len2);
+    o.rotInv[0] = dmul(-o.rot[0], s);
+    o.rotInv[1] = dmul(-o.rot[1], s);
+    o.rotInv[2] = dmul(-o.rot[2], s);
+    o.rotInv[3] = dmul(o.rot[3], s);
+}
+__device__ D3 objSupport(const CcdObj &o, D3 dir_) {
+    const D3 dir = quatRot(dir_, o.rotInv);
+    D3 v;
+    if (o.kind == 0) {
+        v = {dmul(ccdSign(dir.x), o.a), dmul(ccdSign(dir.y), o.b), dmul(ccdSign(dir.z), o.c)};
+    } else if (o.kind == 1) {
+        D3 n = ccdNormalize(dir);
+        n = {dmul(n.x, o.a), dmul(n.y, o.a), dmul(n.z, o.a)};
+        v = dir.z > 0 ? D3{dadd(0, n.x), dadd(0, n.y), dadd(o.b, n.z)} : D3{dadd(0, n.x), dadd(0, n.y), dadd(-o.b, n.z)};
+    } else if (o.kind == 2) {
+        const double zdist = __dsqrt_rn(dadd(dmul(dir.x, dir.x), dmul(dir.y, dir.y)));
+        if (ccdIsZero(zdist)) {
+            v = {0, 0, dmul(ccdSign(dir.z), o.b)};
+        } else {
+            const double rad = __ddiv_rn(o.a, zdist);
+            v = {dmul(rad, dir.x), dmul(rad, dir.y), dmul(ccdSign(dir.z), o.b)};
+        }
+    } else {
+        double maxdot = -DBL_MAX;
+        v = o.p[0];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const D3 p = {dsub(o.p[i].x, o.cen.x), dsub(o.p[i].y, o.cen.y), dsub(o.p[i].z, o.cen.z)};
+            const double d = d3dot(dir, p);
+            if (d > maxdot) {
+                v = o.p[i];
+                maxdot = d;
+            }
+        }
+    }
+    v = quatRot(v, o.rot);
+    return {dadd(v.x, o.pos[0]), dadd(v.y, o.pos[1]), dadd(v.z, o.pos[2])};
+}
+__device__ D3 objCenter(const CcdObj &o) {
+    if (o.kind != 3) return {o.pos[0], o.pos[1], o.pos[2]};
+    const D3 c = quatRot(o.cen, o.rot);
+    return {dadd(c.x, o.pos[0]), dadd(c.y, o.pos[1]), dadd(c.z, o.pos[2])};
+}
+__device__ D3 minkSupport(const CcdObj &o1, const CcdObj &o2, D3 dir) {
+    const D3 a = objSupport(o1, dir);
+    const D3 b = objSupport(o2, d3neg(dir));
+    return d3sub(a, b);
+}
+
+// ---- [EXT] libccd ccdMPRIntersect (discoverPortal + refinePortal), statement for statement as the oracle
+__device__ int mprDiscoverPortal(const CcdObj &o1, const CcdObj &o2, D3 P[4]) {
+    const D3 origin = {0, 0, 0};
+    D3 dir, va, vb;
+    double dot;
+    P[0] = d3sub(objCenter(o1), objCenter(o2));
+    if (ccdVecEq(P[0], origin)) P[0] = d3add(P[0], D3{dmul(kCcdEps, 10.0), 0, 0});
+    dir = ccdNormalize(d3neg(P[0]));
+    P[1] = minkSupport(o1, o2, dir);
+    dot = d3dot(P[1], dir);
+    if (ccdIsZero(dot) || dot < 0) return -1;
+    dir = d3cross(P[0], P[1]);
+    if (ccdIsZero(d3dot(dir, dir))) return ccdVecEq(P[1], origin) ? 1 : 2;
+    dir = ccdNormalize(dir);
+    P[2] = minkSupport(o1, o2, dir);
+    dot = d3dot(P[2], dir);
+    if (ccdIsZero(dot) || dot < 0) return -1;
+    va = d3sub(P[1], P[0]);
+    vb = d3sub(P[2], P[0]);
+    dir = ccdNormalize(d3cross(va, vb));
+    dot = d3dot(dir, P[0]);
+    if (dot > 0) {
+        const D3 t = P[1];
+        P[1] = P[2];
+        P[2] = t;
+        dir = d3neg(dir);
+    }
+    for (int guard = 0; guard < 10000; ++guard) {
+        bool cont = false;
+        P[3] = minkSupport(o1, o2, dir);
+        dot = d3dot(P[3], dir);
+        if (ccdIsZero(dot) || dot < 0) return -1;
+        va = d3cross(P[1], P[3]);
+        dot = d3dot(va, P[0]);
+        if (dot < 0 && !ccdIsZero(dot)) {
+            P[2] = P[3];
+            cont = true;
+        }
+        if (!cont) {
+            va = d3cross(P[3], P[2]);
+            dot = d3dot(va, P[0]);
+            if (dot < 0 && !ccdIsZero(dot)) {
+                P[1] = P[3];
+                cont = true;
+            }
+        }
+        if (!cont) return 0;
+        va = d3sub(P[1], P[0]);
+        vb = d3sub(P[2], P[0]);
+        dir = ccdNormalize(d3cross(va, vb));
+    }
+    return -2;
+}
+__device__ int mprRefinePortal(const CcdObj &o1, const CcdObj &o2, D3 P[4], double tol) {
+    for (int guard = 0; guard < 10000; ++guard) {
+        const D3 dir = ccdNormalize(d3cross(d3sub(P[2], P[1]), d3sub(P[3], P[1])));
+        double dot = d3dot(dir, P[1]);
+        if (ccdIsZero(dot) || dot > 0) return 0;
+        const D3 v4 = minkSupport(o1, o2, dir);
+        dot = d3dot(v4, dir);
+        if (!(ccdIsZero(dot) || dot > 0)) return -1;
+        {
+            const double dv1 = d3dot(P[1], dir), dv2 = d3dot(P[2], dir), dv3 = d3dot(P[3], dir), dv4 = d3dot(v4, dir);
+            double d1 = dsub(dv4, dv1);
+            const double d2 = dsub(dv4, dv2), d3 = dsub(dv4, dv3);
+            d1 = fmin(d1, d2);
+            d1 = fmin(d1, d3);
+            if (ccdEq(d1, tol) || d1 < tol) return -1;
+        }
+        {
+            const D3 v4v0 = d3cross(v4, P[0]);
+            dot = d3dot(P[1], v4v0);
+            if (dot > 0) {
+                dot = d3dot(P[2], v4v0);
+                if (dot > 0) P[1] = v4; else P[3] = v4;
+            } else {
+                dot = d3dot(P[3], v4v0);
+                if (dot > 0) P[2] = v4; else P[1] = v4;
+            }
+        }
+    }
+    return -2;
+}
+// 1 intersect, 0 disjoint, -1 iteration guard tripped (reported, never silent)
+__device__ __noinline__ int mprIntersect(const CcdObj &o1, const CcdObj &o2) {
+    D3 P[4];
+    const int res = mprDiscoverPortal(o1, o2, P);
+    if (res == -2) return -1;
+    if (res < 0) return 0;
+    if (res > 0) return 1;
+    const int r = mprRefinePortal(o1, o2, P, 1e-6);
+    if (r == -2) return -1;
+    return r == 0 ? 1 : 0;
+}
+
+// ---- [EXT] fcl boxBox2 reduced to its boolean result
+__device__ bool boxBoxIntersect(const FetchShape &s1, const FrameD &f1, const FetchShape &s2, const FrameD &f2) {
+    const double p[3] = {dsub(f2.t[0], f1.t[0]), dsub(f2.t[1], f1.t[1]), dsub(f2.t[2], f1.t[2])};
+    double pp[3], R[3][3], Q[3][3];
+    const double A[3] = {s1.a, s1.b, s1.c}, B[3] = {s2.a, s2.b, s2.c};
+    for (int i = 0; i < 3; ++i) pp[i] = dadd(dadd(dmul(f1.R[0][i], p[0]), dmul(f1.R[1][i], p[1])), dmul(f1.R[2][i], p[2]));
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            R[i][j] = dadd(dadd(dmul(f1.R[0][i], f2.R[0][j]), dmul(f1.R[1][i], f2.R[1][j])), dmul(f1.R[2][i], f2.R[2][j]));
+            Q[i][j] = fabs(R[i][j]);
+        }
+    for (int i = 0; i < 3; ++i)
+        if (dsub(fabs(pp[i]), dadd(dadd(dadd(dmul(Q[i][0], B[0]), dmul(Q[i][1], B[1])), dmul(Q[i][2], B[2])), A[i])) > 0)
+            return false;
+    for (int j = 0; j < 3; ++j) {
+        const double tmp = dadd(dadd(dmul(f2.R[0][j], p[0]), dmul(f2.R[1][j], p[1])), dmul(f2.R[2][j], p[2]));
+        if (dsub(fabs(tmp), dadd(dadd(dadd(dmul(Q[0][j], A[0]), dmul(Q[1][j], A[1])), dmul(Q[2][j], A[2])), B[j])) > 0)
+            return false;
+    }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Q[i][j] = dadd(Q[i][j], 1e-6);
+    for (int i = 0; i < 3; ++i) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+        for (int j = 0; j < 3; ++j) {
+            const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+            const double tmp = dsub(dmul(pp[i2], R[i1][j]), dmul(pp[i1], R[i2][j]));
+            const double s2 = dsub(fabs(tmp), dadd(dadd(dadd(dmul(A[i1], Q[i2][j]), dmul(A[i2], Q[i1][j])), dmul(B[j1], Q[i][j2])),
+                                                   dmul(B[j2], Q[i][j1])));
+            if (s2 > kCcdEps) return false;
+        }
+    }
+    return true;
+}
+
+// ---- conservative FP32 culling helpers -------------------------------------------------------------
+// half extents of the shape's oriented box ([EXT] fcl computeBV for Box / Capsule / Cylinder)
+__device__ __forceinline__ void shapeExtents(const FetchShape &s, float e[3]) {
+    if (s.type == 0) { e[0] = (float)s.a; e[1] = (float)s.b; e[2] = (float)s.c; }
+    else if (s.type == 1) { e[0] = (float)s.a; e[1] = (float)s.a; e[2] = (float)(s.b + s.a); }
+    else { e[0] = (float)s.a; e[1] = (float)s.a; e[2] = (float)s.b; }
+}
+constexpr float kCullSlack = 1e-4f;  // metres; FP32 error of these tests is ~1e-6
+
+// boxes of two shapes given by their world frames: certainly disjoint?
+__device__ bool shapeBoxesDisjoint(const FetchShape &s1, const FrameD &f1, const FetchShape &s2, const FrameD &f2) {
+    float e1[3], e2[3];
+    shapeExtents(s1, e1);
+    shapeExtents(s2, e2);
+    // box axes are the frame's columns; express box 2 in frame 1: R = R1^T R2, T = R1^T (t2 - t1)
+    const float4 a0 = make_float4(1, 0, 0, 0), a1 = make_float4(0, 1, 0, 0), a2 = make_float4(0, 0, 1, 0);
+    const float4 ae = make_float4(e1[0] * 1.00001f, e1[1] * 1.00001f, e1[2] * 1.00001f, 0);
+    const float4 be = make_float4(e2[0] * 1.00001f, e2[1] * 1.00001f, e2[2] * 1.00001f, 0);
+    float R[3][3], T[3];
+    const float d[3] = {(float)(f2.t[0] - f1.t[0]), (float)(f2.t[1] - f1.t[1]), (float)(f2.t[2] - f1.t[2])};
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j)
+            R[i][j] = (float)f1.R[0][i] * (float)f2.R[0][j] + (float)f1.R[1][i] * (float)f2.R[1][j] + (float)f1.R[2][i] * (float)f2.R[2][j];
+        T[i] = (float)f1.R[0][i] * d[0] + (float)f1.R[1][i] * d[1] + (float)f1.R[2][i] * d[2];
+    }
+    float dist2;
+    return !obbOverlap(a0, a1, a2, ae, a0, a1, a2, be, make_float4(R[0][0], R[0][1], R[0][2], T[0]),
+                       make_float4(R[1][0], R[1][1], R[1][2], T[1]), make_float4(R[2][0], R[2][1], R[2][2], T[2]), kCullSlack,
+                       dist2);
+}
+
+__device__ void makeShapeObj(const FetchShape &s, const FrameD &f, CcdObj &o) {
+    o.kind = s.type;
+    o.a = s.a; o.b = s.b; o.c = s.c;
+    objSetFrame(o, f);
+}
+
+// fetch_robot.hpp:508-577 pair order (indices into the geometry list of fetch_robot.hpp:38-53)
+__constant__ unsigned char kSelfPairs[24][2] = {
+    {0, 6}, {0, 7}, {0, 8}, {0, 9}, {1, 6}, {1, 7}, {1, 8}, {1, 9}, {2, 6}, {2, 7}, {2, 8}, {2, 9},
+    {3, 8}, {4, 8}, {4, 9}, {4, 11}, {5, 11}, {6, 11}, {7, 10}, {7, 11}, {8, 10}, {8, 11}, {9, 10}, {9, 11}};
+
+__device__ void loadFrame(const double *src, FrameD &f) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) f.R[i][j] = src[4 * i + j];
+        f.t[i] = src[4 * i + 3];
+    }
+}
+__device__ void storeFrame(double *dst, const FrameD &f) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) dst[4 * i + j] = f.R[i][j];
+        dst[4 * i + 3] = f.t[i];
+    }
+}
+
+// one thread per state: FK, self collision (24 pairs, early exit), floor clearance.
+// `states` are explicit joint vectors, or (edgeItems != nullptr) samples of edges: item = (edge, i)
+// with state = from + (to - from) * (i * (1/steps)), i == steps meaning `to` itself.
+__global__ void __launch_bounds__(128)
+fetchSelfKernel(FetchSceneDev sc, const double *__restrict__ states, const double *__restrict__ from,
+                const double *__restrict__ to, const unsigned *__restrict__ steps,
+                const unsigned long long *__restrict__ edgeItems, const unsigned *__restrict__ dead, unsigned long long n,
+                double *__restrict__ frames /* [n][12][12] */, unsigned char *__restrict__ selfHit, FetchCounters *ctr) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double q[8];
+    if (edgeItems) {
+        const unsigned long long it = edgeItems[i];
+        const unsigned e = (unsigned)(it >> 32), k = (unsigned)it;
+        if (dead[e]) {
+            selfHit[i] = 2;  // edge already decided: skip
+            return;
+        }
+        const unsigned st = steps[e];
+        if (k >= st) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) q[j] = to[8 * (size_t)e + j];
+        } else {
+            // interpolate.hpp:9-16: a + (b - a) * t with t = i * delta (fetch_scenario.hpp:146,151)
+            const double t = dmul((double)k, __ddiv_rn(1.0, (double)st));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double a = from[8 * (size_t)e + j], b = to[8 * (size_t)e + j];
+                q[j] = dadd(a, dmul(dsub(b, a), t));
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) q[j] = states[8 * i + j];
+    }
+
+    // fk(): fetch_robot.hpp:276-315
+    FrameD F[12];
+    FrameD cur;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) cur.R[a][b] = a == b ? 1.0 : 0.0;
+        cur.t[a] = 0;
+    }
+    frameMul(cur, sc.origins + 12 * 0, F[0]);           // base
+    frameTranslate(cur, -0.086875, 0, 0.37743);         // torsoLiftJointOrigin
+    frameTranslate(cur, 0, 0, q[0]);                    // torsoLiftLink
+    frameMul(cur, sc.origins + 12 * 1, F[1]);           // torsoLift box
+    frameMul(cur, sc.origins + 12 * 10, F[10]);         // neck
+    frameMul(cur, sc.origins + 12 * 11, F[11]);         // head
+    frameTranslate(cur, 0.119525, 0, 0.34858);
+    frameRotate(cur, q[1], 2);                          // shoulderPanLink
+    frameMul(cur, sc.origins + 12 * 2, F[2]);
+    frameTranslate(cur, 0.117, 0, 0.0599999999999999);
+    frameRotate(cur, q[2], 1);                          // shoulderLiftLink
+    frameMul(cur, sc.origins + 12 * 3, F[3]);
+    frameTranslate(cur, 0.219, 0, 0);
+    frameRotate(cur, q[3], 0);                          // upperarmRollLink
+    frameMul(cur, sc.origins + 12 * 4, F[4]);
+    frameTranslate(cur, 0.133, 0, 0);
+    frameRotate(cur, q[4], 1);                          // elbowFlexLink
+    frameMul(cur, sc.origins + 12 * 5, F[5]);
+    frameTranslate(cur, 0.197, 0, 0);
+    frameRotate(cur, q[5], 0);                          // forearmRollLink
+    frameMul(cur, sc.origins + 12 * 6, F[6]);
+    frameTranslate(cur, 0.1245, 0, 0);
+    frameRotate(cur, q[6], 1);                          // wristFlexLink
+    frameMul(cur, sc.origins + 12 * 7, F[7]);
+    frameTranslate(cur, 0.1385, 0, 0);
+    frameRotate(cur, q[7], 0);                          // wristRollLink
+    frameMul(cur, sc.origins + 12 * 8, F[8]);
+    frameTranslate(cur, 0.16645, 0, 0);                 // gripperAxis
+    const double gripperAxisZ = cur.t[2];
+    frameTranslate(cur, -0.09, 0, 0.0025);              // gripperLink == gripper geometry frame
+    F[9] = cur;
+
+    double *out = frames + i * 144;
+    for (int g = 0; g < 12; ++g) storeFrame(out + 12 * g, F[g]);
+
+    // selfCollision(): fetch_robot.hpp:502-584
+    unsigned pairTests = 0;
+    int hit = 0;
+    for (int k = 0; k < 24 && !hit; ++k) {
+        const int a = kSelfPairs[k][0], b = kSelfPairs[k][1];
+        const FetchShape &sa = sc.shapes[a], &sb = sc.shapes[b];
+        if (shapeBoxesDisjoint(sa, F[a], sb, F[b])) continue;
+        ++pairTests;
+        if (sa.type == 0 && sb.type == 0) {
+            hit = boxBoxIntersect(sa, F[a], sb, F[b]) ? 1 : 0;
+        } else {
+            CcdObj o1, o2;
+            makeShapeObj(sa, F[a], o1);
+            makeShapeObj(sb, F[b], o2);
+            const int r = mprIntersect(o1, o2);
+            if (r < 0) atomicExch(&ctr->error, 1u);
+            hit = r == 1;
+        }
+    }
+    if (!hit && gripperAxisZ < 0.30) hit = 1;  // floorClearance_, fetch_robot.hpp:105,580
+    selfHit[i] = (unsigned char)hit;
+    if (pairTests) atomicAdd(&ctr->pairTests, (unsigned long long)pairTests);
+}
+
+// one thread per (state, geometry): environment hierarchy vs the shape's box, MPR at the leaves
+__global__ void __launch_bounds__(128)
+fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsigned char *__restrict__ selfHit,
+               unsigned long long n, unsigned *__restrict__ envHit, FetchCounters *ctr) {
+    const unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned long long i = tid / 12;
+    const int g = (int)(tid % 12);
+    if (i >= n || selfHit[i] || sc.nEnvNodes == 0) return;
+    FrameD f;
+    loadFrame(frames + i * 144 + 12 * g, f);
+    const FetchShape &s = sc.shapes[g];
+    float e[3];
+    shapeExtents(s, e);
+    // shape box in world coordinates: axes = columns of f.R
+    const float4 a0 = make_float4((float)f.R[0][0], (float)f.R[1][0], (float)f.R[2][0], (float)f.t[0]);
+    const float4 a1 = make_float4((float)f.R[0][1], (float)f.R[1][1], (float)f.R[2][1], (float)f.t[1]);
+    const float4 a2 = make_float4((float)f.R[0][2], (float)f.R[1][2], (float)f.R[2][2], (float)f.t[2]);
+    const float4 ae = make_float4(e[0] * 1.00001f, e[1] * 1.00001f, e[2] * 1.00001f, 0);
+    const float4 x0 = make_float4((float)sc.envFrame[0], (float)sc.envFrame[1], (float)sc.envFrame[2], (float)sc.envFrame[3]);
+    const float4 x1 = make_float4((float)sc.envFrame[4], (float)sc.envFrame[5], (float)sc.envFrame[6], (float)sc.envFrame[7]);
+    const float4 x2 = make_float4((float)sc.envFrame[8], (float)sc.envFrame[9], (float)sc.envFrame[10], (float)sc.envFrame[11]);
+    // obbOverlap expects A's centre in the .w of its axis rows, in A's own frame: use world = A frame with
+    // identity-like handling by passing the box axes/centre directly (A frame == world here)
+    CcdObj shapeObj;
+    bool haveObj = false;
+    int stack[40];
+    int sp = 0;
+    stack[sp++] = 0;
+    unsigned bv = 0, leaf = 0;
+    bool hit = false;
+    while (sp > 0 && !hit) {
+        const int node = stack[--sp];
+        const float4 *pn = sc.envNodes + 4 * (size_t)node;
+        const float4 b0 = ldg4(pn), b1 = ldg4(pn + 1), b2 = ldg4(pn + 2), be = ldg4(pn + 3);
+        ++bv;
+        float dist2;
+        if (!obbOverlap(a0, a1, a2, ae, b0, b1, b2, be, x0, x1, x2, kCullSlack, dist2)) continue;
+        const int link = __float_as_int(be.w);
+        if (link >= 0) {
+            if (sp + 2 > 40) {
+                atomicExch(&ctr->error, 1u);
+                break;
+            }
+            stack[sp++] = link + 1;
+            stack[sp++] = link;
+            continue;
+        }
+        // leaf: exact shape-triangle MPR ([EXT] GJKSolver_libccd::shapeTriangleIntersect)
+        if (!haveObj) {
+            makeShapeObj(s, f, shapeObj);
+            haveObj = true;
+        }
+        const double *tp = sc.envTris64 + 9 * (size_t)(-(link + 1));
+        CcdObj tri;
+        tri.kind = 3;
+        tri.a = tri.b = tri.c = 0;
+        tri.p[0] = {tp[0], tp[1], tp[2]};
+        tri.p[1] = {tp[3], tp[4], tp[5]};
+        tri.p[2] = {tp[6], tp[7], tp[8]};
+        tri.cen = {__ddiv_rn(dadd(dadd(tp[0], tp[3]), tp[6]), 3.0), __ddiv_rn(dadd(dadd(tp[1], tp[4]), tp[7]), 3.0),
+                   __ddiv_rn(dadd(dadd(tp[2], tp[5]), tp[8]), 3.0)};
+        FrameD ef;
+        loadFrame(sc.envFrame, ef);
+        objSetFrame(tri, ef);
+        ++leaf;
+        const int r = mprIntersect(shapeObj, tri);
+        if (r < 0) atomicExch(&ctr->error, 1u);
+        hit = r == 1;
+    }
+    if (hit) envHit[i] = 1u;
+    atomicAdd(&ctr->bvTests, (unsigned long long)bv);
+    if (leaf) atomicAdd(&ctr->leafTests, (unsigned long long)leaf);
+}
+
+__global__ void fetchCombineKernel(const unsigned char *__restrict__ selfHit, const unsigned *__restrict__ envHit,
+                                   unsigned long long n, uint8_t *__restrict__ valid) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i < n) valid[i] = (selfHit[i] || envHit[i]) ? 0 : 1;
+}
+
+// edge samples: any colliding sample kills its edge
+__global__ void fetchEdgeReduceKernel(const unsigned char *__restrict__ selfHit, const unsigned *__restrict__ envHit,
+                                      const unsigned long long *__restrict__ edgeItems, unsigned long long n,
+                                      unsigned *__restrict__ dead, FetchCounters *ctr) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (selfHit[i] == 2) return;
+    if (selfHit[i] || envHit[i]) dead[(unsigned)(edgeItems[i] >> 32)] = 1u;
+}
+
+}  // namespace
+
+cudaError_t launchFetchStates(const FetchSceneDev &sc, const double *dStates, size_t n, double *dFrames,
+                              unsigned char *dSelfHit, unsigned *dEnvHit, uint8_t *dValid, FetchCounters *dCtr,
+                              cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(dEnvHit, 0, n * sizeof(unsigned), stream);
+    if (e != cudaSuccess) return e;
+    fetchSelfKernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(sc, dStates, nullptr, nullptr, nullptr, nullptr, nullptr, n,
+                                                                     dFrames, dSelfHit, dCtr);
+    fetchEnvKernel<<<(unsigned)((n * 12 + 127) / 128), 128, 0, stream>>>(sc, dFrames, dSelfHit, n, dEnvHit, dCtr);
+    fetchCombineKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dSelfHit, dEnvHit, n, dValid);
+    return cudaGetLastError();
+}
+
+cudaError_t launchFetchEdgeItems(const FetchSceneDev &sc, const double *dFrom, const double *dTo, const unsigned *dSteps,
+                                 const unsigned long long *dItems, size_t nItems, unsigned *dDead, double *dFrames,
+                                 unsigned char *dSelfHit, unsigned *dEnvHit, FetchCounters *dCtr, cudaStream_t stream) {
+    if (nItems == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(dEnvHit, 0, nItems * sizeof(unsigned), stream);
+    if (e != cudaSuccess) return e;
+    fetchSelfKernel<<<(unsigned)((nItems + 127) / 128), 128, 0, stream>>>(sc, nullptr, dFrom, dTo, dSteps, dItems, dDead, nItems,
+                                                                          dFrames, dSelfHit, dCtr);
+    fetchEnvKernel<<<(unsigned)((nItems * 12 + 127) / 128), 128, 0, stream>>>(sc, dFrames, dSelfHit, nItems, dEnvHit, dCtr);
+    fetchEdgeReduceKernel<<<(unsigned)((nItems + 255) / 256), 256, 0, stream>>>(dSelfHit, dEnvHit, dItems, nItems, dDead, dCtr);
+    return cudaGetLastError();
+}
+
+}  // namespace mplb

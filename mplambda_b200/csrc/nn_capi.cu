@@ -11,13 +11,6 @@
 
 using namespace mplb;
 
-#define MPLB_CUDA(expr)                                                                             \
-    do {                                                                                            \
-        cudaError_t e_ = (expr);                                                                    \
-        if (e_ != cudaSuccess)                                                                      \
-            return fail(MPLB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
-
 struct mplb_nn {
     int device = 0, numSms = 0, metric = 0, dim = 7;
     double so3w = 50, l2w = 1;

@@ -29,7 +29,7 @@ struct CallCtx {
     cudaStream_t stream = nullptr;      // kernels + verdict read-back
     cudaStream_t copyStream = nullptr;  // host->device input copies of pipelined batches
     std::vector<cudaEvent_t> events;    // one per pipeline stage
-    DevBuf in0, in1, steps, dead, out, ctr, work, aux0, aux1;
+    DevBuf in0, in1, steps, dead, out, ctr, work, aux0, aux1, aux2, aux3;
     DevCounters *hCtr = nullptr;  // pinned
     std::vector<uint32_t> hSteps;
     ~CallCtx();
@@ -48,6 +48,38 @@ struct SceneBase {
     CallCtx *acquire();
     void release(CallCtx *c);
     virtual ~SceneBase();
+    // per-kind implementations of the generic entry points (capi.cu dispatches through these)
+    virtual int checkStates(const double *states, size_t n, uint8_t *valid) = 0;
+    virtual int checkEdges(const double *from, const double *to, size_t n, uint8_t *valid, uint64_t *statesChecked) = 0;
+    virtual double distance(const double *a, const double *b) const = 0;
+    virtual int planEdges(const double *from, const double *to, size_t n, uint32_t *steps) const = 0;
 };
+
+struct CtxGuard {
+    SceneBase *sc;
+    CallCtx *c;
+    ~CtxGuard() {
+        if (c) sc->release(c);
+    }
+};
+
+#define MPLB_CUDA(expr)                                                                             \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return ::mplb::fail(-3, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+int selectDevice(int device, int *numSms);
+int bitsFor(size_t n);
+
+template <typename T>
+int upload(DevBuf &buf, const std::vector<T> &v) {
+    int rc = buf.reserve(v.size() * sizeof(T) + 16);
+    if (rc != 0) return rc;
+    if (!v.empty()) MPLB_CUDA(cudaMemcpy(buf.ptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
 
 }  // namespace mplb

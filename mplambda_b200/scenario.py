@@ -174,3 +174,97 @@ class SE3RigidBodyScenario:
         st = _capi.Stats()
         _capi.check(_capi.lib().mplb_scene_stats(self._h, C.byref(st), int(reset)))
         return st.as_dict()
+
+
+class L1Space:
+    """nigh::L1Space<S, 8> distance (fetch_scenario.hpp:19)."""
+
+    def __init__(self, scenario):
+        self._sc = scenario
+
+    def distance(self, a, b):
+        a, b = _f64(a, 8), _f64(b, 8)
+        return _capi.lib().mplb_distance(self._sc._h, a.ctypes.data_as(_capi.dp), b.ctypes.data_as(_capi.dp))
+
+    @staticmethod
+    def dimensions():
+        return 8
+
+
+class FetchScenario:
+    """Mirror of mpl::demo::FetchScenario<S> (reference include/mpl/demo/fetch_scenario.hpp:11-177) for
+    the validity part of the Scenario concept.  State = 8 joint values (fetch_robot.hpp:80-99).
+    Goal sampling / isGoal go through the IK solver in the reference (fetch_scenario.hpp:84-103): out of
+    scope here."""
+
+    multiGoal = True
+    _SCALE = np.array([10.0, 4, 2, 1, 1, 1, 1, 1])   # fetch_scenario.hpp:42-45
+
+    def __init__(self, envFrame, envMesh, goal=None, goalTol=None, checkResolution=0.01, device=0):
+        L = _capi.lib()
+        self._h = C.c_void_p()
+        frame = np.ascontiguousarray(np.asarray(envFrame, dtype=np.float64).reshape(3, 4))
+        self.envFrame_ = frame
+        self.goal_, self.goalTol_ = goal, goalTol
+        self.invStepSize_ = 1.0 / checkResolution
+        if isinstance(envMesh, (str, bytes)) or hasattr(envMesh, "__fspath__"):
+            rc = L.mplb_scene_create_fetch_file(str(envMesh).encode(), frame.ctypes.data_as(_capi.dp), checkResolution,
+                                                device, C.byref(self._h))
+        else:
+            env = np.ascontiguousarray(envMesh, dtype=np.float64).reshape(-1, 3, 3)
+            rc = L.mplb_scene_create_fetch(env.ctypes.data_as(_capi.dp), len(env), frame.ctypes.data_as(_capi.dp),
+                                           checkResolution, device, C.byref(self._h))
+        if rc in (_capi.ERR_IO, _capi.ERR_INVALID):
+            raise ValueError(L.mplb_last_error().decode("utf-8", "replace"))
+        _capi.check(rc)
+        self._space = L1Space(self)
+
+    close = SE3RigidBodyScenario.close
+    __del__ = SE3RigidBodyScenario.__del__
+    stats = SE3RigidBodyScenario.stats
+
+    @classmethod
+    def scale(cls, q):
+        return np.asarray(q, dtype=np.float64) * cls._SCALE   # fetch_scenario.hpp:75-77
+
+    def space(self):
+        return self._space
+
+    @staticmethod
+    def maxSteering():
+        return math.inf
+
+    def randomSample(self, rng):
+        """FetchRobot::randomConfig (fetch_robot.hpp:163-175)."""
+        from .workload import FETCH_JOINT_MAX, FETCH_JOINT_MIN
+        lo = np.maximum(FETCH_JOINT_MIN, -4 * math.pi)
+        hi = np.minimum(FETCH_JOINT_MAX, 4 * math.pi)
+        return np.array([rng.uniform(lo[i], hi[i]) for i in range(8)])
+
+    def isValid(self, q, to=None):
+        if to is None:
+            return bool(self.check_states(q)[0])
+        return bool(self.check_edges(q, to)[0])
+
+    def check_states(self, states):
+        s = _f64(states, 8)
+        out = np.empty(len(s), dtype=np.uint8)
+        _capi.check(_capi.lib().mplb_check_states(self._h, _ptr(s), len(s), _ptr(out)))
+        return out.astype(bool)
+
+    def check_edges(self, frm, to, return_states_checked=False):
+        a, b = _f64(frm, 8), _f64(to, 8)
+        if a.shape != b.shape:
+            raise ValueError("from/to shape mismatch")
+        out = np.empty(len(a), dtype=np.uint8)
+        checked = C.c_uint64()
+        _capi.check(_capi.lib().mplb_check_edges(self._h, _ptr(a), _ptr(b), len(a), _ptr(out), C.byref(checked)))
+        if return_states_checked:
+            return out.astype(bool), checked.value
+        return out.astype(bool)
+
+    def edge_steps(self, frm, to):
+        a, b = _f64(frm, 8), _f64(to, 8)
+        steps = np.empty(len(a), dtype=np.uint32)
+        _capi.check(_capi.lib().mplb_edges_plan(self._h, _ptr(a), _ptr(b), len(a), _ptr(steps)))
+        return steps

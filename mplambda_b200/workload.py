@@ -85,3 +85,49 @@ SE3_SCENES = {
                  min=_f32([-383.802642822, -371.469055176, -0.196851730347]),
                  max=_f32([324.997131348, 337.893371582, 142.332290649])),
 }
+
+
+# ---- Fetch (fetch_robot.hpp:109-175, scripts/fetch_task_00{1,2}.sh) -------------------------------
+FETCH_JOINT_MIN = np.array([0.0, -1.6056, -1.221, -np.inf, -2.251, -np.inf, -2.16, -np.inf])
+FETCH_JOINT_MAX = np.array([0.38615, 1.6056, 1.518, np.inf, 2.251, np.inf, 2.16, np.inf])
+FETCH_SCALE = np.array([10.0, 4, 2, 1, 1, 1, 1, 1])          # FetchScenario::scale (fetch_scenario.hpp:42-45)
+
+
+def frame_from_option(v):
+    """--env-frame x,y,z,rx,ry,rz -> 3x4 [R|t]: axis-angle vector as parsed by
+    OptionParser<Eigen::Transform> (app_options.hpp:83-94), Eigen AngleAxis::toRotationMatrix."""
+    v = np.array(_f32(v))
+    f = np.zeros((3, 4))
+    f[:, :3] = np.eye(3)
+    axis = v[3:6]
+    angle = float(np.sqrt(axis @ axis))
+    if abs(angle) > 1e-6:
+        a = axis / angle
+        s, c = math.sin(angle), math.cos(angle)
+        sa, c1 = s * a, (1 - c) * a
+        R = np.empty((3, 3))
+        t = c1[0] * a[1]; R[0, 1] = t - sa[2]; R[1, 0] = t + sa[2]
+        t = c1[0] * a[2]; R[0, 2] = t + sa[1]; R[2, 0] = t - sa[1]
+        t = c1[1] * a[2]; R[1, 2] = t - sa[0]; R[2, 1] = t + sa[0]
+        for i in range(3):
+            R[i, i] = c1[i] * a[i] + c
+        f[:, :3] = R
+    f[:, 3] = v[:3]
+    return f
+
+
+FETCH_TASKS = {
+    "fetch_task_001": dict(env_frame=[0.57, -0.90, 0.00, 0, 0, -1.570796326794897],
+                           start=_f32([0.1, 1.570796326794897, 1.570796326794897, 0, 1.570796326794897, 0,
+                                       1.570796326794897, 0])),
+    "fetch_task_002": dict(env_frame=[0.48, 1.09, 0.00, 0, 0, -1.570796326794897],
+                           start=_f32([0.18132, 0.249076, 0.153913, 1.47009, 1.48902, -0.125871, -1.74715, -1.45724])),
+}
+
+
+def fetch_configs(n, seed=SEED, start=0):
+    """[n,8] joint vectors distributed as FetchRobot::randomConfig (fetch_robot.hpp:163-175): each joint
+    uniform in [max(jointMin,-4pi), min(jointMax,4pi)]."""
+    lo = np.maximum(FETCH_JOINT_MIN, -4 * math.pi)
+    hi = np.minimum(FETCH_JOINT_MAX, 4 * math.pi)
+    return lo + uniforms(n, seed, 8, start) * (hi - lo)

@@ -557,3 +557,5 @@ void orc_nn_knearest(const double *keys, size_t n, int dim, int metric, double s
         for (int r = cnt; r < k; ++r) { od[r] = INFINITY; oi[r] = -1; }
     }
 }
+
+#include "mplb_oracle_fetch.inc"

@@ -81,6 +81,22 @@ void orc_nn_knearest(const double *keys, size_t n, int dim, int metric, double s
 
 int orc_omp_max_threads(void);
 
+/* ---- Fetch (fetch_robot.hpp / fetch_scenario.hpp); state = 8 joint values (fetch_robot.hpp:80-99) ---- */
+/* 12 geometry frames (row-major 3x4 [R|t]) in the order of fetch_robot.hpp:38-53, and gripperAxis z */
+void orc_fetch_fk(const double q[8], double frames[12][12], double *gripper_axis_z);
+/* 0 none, 1..24 colliding pair (order of fetch_robot.hpp:508-577), 25 floor clearance (:580) */
+int orc_fetch_self_collision(const double q[8]);
+int orc_fetch_is_valid(const orc_mesh *env, const double env_frame[12], const double q[8], int *why,
+                       orc_counters *ctr);
+void orc_fetch_check_states(const orc_mesh *env, const double env_frame[12], const double *states, size_t n,
+                            uint8_t *valid, int threads, orc_counters *ctr);
+double orc_fetch_distance(const double a[8], const double b[8]);
+uint64_t orc_fetch_edge_steps(const double a[8], const double b[8], double inv_step);
+int orc_fetch_check_edge(const orc_mesh *env, const double env_frame[12], const double from[8], const double to[8],
+                         double inv_step, orc_counters *ctr);
+void orc_fetch_check_edges(const orc_mesh *env, const double env_frame[12], const double *from, const double *to,
+                           size_t n, double inv_step, uint8_t *valid, int threads, orc_counters *ctr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,7 @@ _SO = os.path.join(_HERE, "_build", "libmplb_oracle.so")
 
 
 def build(force=False):
-    srcs = [os.path.join(_HERE, f) for f in ("mplb_oracle.c", "mplb_oracle_fetch.c", "mplb_oracle.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("mplb_oracle.c", "mplb_oracle_fetch.inc", "mplb_oracle.h", "Makefile")]
     if (not force and os.path.exists(_SO)
             and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs)):
         return _SO
@@ -53,6 +53,17 @@ def lib():
         L.orc_nn_nearest.argtypes = [dp, C.c_size_t, C.c_int, C.c_int, C.c_double, C.c_double, dp, C.c_size_t, i64p, dp, C.c_int]
         L.orc_nn_knearest.argtypes = [dp, C.c_size_t, C.c_int, C.c_int, C.c_double, C.c_double, dp, C.c_size_t, C.c_int, i64p, dp, C.c_int]
         L.orc_omp_max_threads.restype = C.c_int
+        ip = C.POINTER(C.c_int)
+        L.orc_fetch_fk.argtypes = [dp, dp, dp]
+        L.orc_fetch_self_collision.argtypes = [dp]
+        L.orc_fetch_is_valid.argtypes = [C.c_void_p, dp, dp, ip, cp]
+        L.orc_fetch_check_states.argtypes = [C.c_void_p, dp, dp, C.c_size_t, u8p, C.c_int, cp]
+        L.orc_fetch_distance.restype = C.c_double
+        L.orc_fetch_distance.argtypes = [dp, dp]
+        L.orc_fetch_edge_steps.restype = C.c_uint64
+        L.orc_fetch_edge_steps.argtypes = [dp, dp, C.c_double]
+        L.orc_fetch_check_edge.argtypes = [C.c_void_p, dp, dp, dp, C.c_double, cp]
+        L.orc_fetch_check_edges.argtypes = [C.c_void_p, dp, dp, dp, C.c_size_t, C.c_double, u8p, C.c_int, cp]
         _lib = L
     return _lib
 
@@ -144,3 +155,48 @@ def nn_knearest(keys, queries, k, metric="se3", so3w=50.0, l2w=1.0, threads=0):
     lib().orc_nn_knearest(_dp(keys), len(keys), dim, 0 if metric == "se3" else 1, so3w, l2w, _dp(queries),
                           len(queries), k, idx.ctypes.data_as(C.POINTER(C.c_int64)), _dp(dist), threads)
     return idx, dist
+
+
+class FetchOracle:
+    """FP64 restatement of FetchScenario's validity methods (fetch_scenario.hpp:105-173,
+    fetch_robot.hpp:276-315,502-647).  env_frame: 3x4 [R|t] of the environment mesh."""
+
+    def __init__(self, env_tris, env_frame, check_resolution=0.01):
+        self.env = Mesh(env_tris)
+        self.frame = _f64(env_frame, (12,))
+        self.inv_step = 1.0 / check_resolution
+
+    @staticmethod
+    def fk(q):
+        frames = np.empty((12, 12))
+        gz = C.c_double()
+        lib().orc_fetch_fk(_dp(_f64(q, (8,))), _dp(frames), C.byref(gz))
+        return frames.reshape(12, 3, 4), gz.value
+
+    @staticmethod
+    def self_collision(q):
+        return lib().orc_fetch_self_collision(_dp(_f64(q, (8,))))
+
+    def why(self, q):
+        w = C.c_int()
+        lib().orc_fetch_is_valid(self.env.h, _dp(self.frame), _dp(_f64(q, (8,))), C.byref(w), None)
+        return w.value
+
+    def check_states(self, states, threads=0, counters=None):
+        s = _f64(states, (-1, 8))
+        out = np.empty(len(s), dtype=np.uint8)
+        ctr = counters if counters is not None else Counters()
+        lib().orc_fetch_check_states(self.env.h, _dp(self.frame), _dp(s), len(s),
+                                     out.ctypes.data_as(C.POINTER(C.c_uint8)), threads, C.byref(ctr))
+        return out.astype(bool)
+
+    def check_edges(self, frm, to, threads=0, counters=None):
+        a, b = _f64(frm, (-1, 8)), _f64(to, (-1, 8))
+        out = np.empty(len(a), dtype=np.uint8)
+        ctr = counters if counters is not None else Counters()
+        lib().orc_fetch_check_edges(self.env.h, _dp(self.frame), _dp(a), _dp(b), len(a), self.inv_step,
+                                    out.ctypes.data_as(C.POINTER(C.c_uint8)), threads, C.byref(ctr))
+        return out.astype(bool)
+
+    def edge_steps(self, a, b):
+        return lib().orc_fetch_edge_steps(_dp(_f64(a, (8,))), _dp(_f64(b, (8,))), self.inv_step)

@@ -1,0 +1,79 @@
+"""GPU: Fetch validity kernels (FK + MPR self collision + mesh-vs-shape) through the C ABI vs the
+FP64 oracle.  Bar: bit-exact verdicts (the device runs the same FP64 operation sequence; only the FK's
+sin/cos come from CUDA's libm)."""
+import os
+
+import numpy as np
+import pytest
+
+import mplambda_b200 as M
+from mplambda_b200.workload import FETCH_TASKS, SEED, fetch_configs, frame_from_option
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def autolab(scenes):
+    return scenes["autolab"][0]
+
+
+@pytest.mark.parametrize("task", sorted(FETCH_TASKS))
+def test_known_answers(task, autolab):
+    g = np.load(os.path.join(GOLDEN, "fetch_verdicts.npz"))
+    s = M.FetchScenario(frame_from_option(FETCH_TASKS[task]["env_frame"]), autolab, checkResolution=0.01)
+    Q = fetch_configs(4096, SEED)
+    got = s.check_states(Q)
+    want = g[task + "_valid"]
+    assert (got == want).all(), np.nonzero(got != want)[0][:10]
+    assert s.isValid(FETCH_TASKS[task]["start"])
+    for i in range(0, 40, 3):
+        assert s.isValid(Q[i]) == bool(want[i])
+
+
+def test_states_match_oracle(autolab, oracle):
+    frame = frame_from_option(FETCH_TASKS["fetch_task_001"]["env_frame"])
+    s = M.FetchScenario(frame, autolab, checkResolution=0.01)
+    Q = fetch_configs(200000, SEED + 3)
+    got = s.check_states(Q)
+    want = oracle.FetchOracle(autolab, frame, 0.01).check_states(Q)
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, "%d verdicts differ, first %s" % (len(bad), bad[:10])
+    assert 0.3 < want.mean() < 0.7
+
+
+def test_recorded_paths_and_edges(autolab, oracle):
+    frame = frame_from_option(FETCH_TASKS["fetch_task_001"]["env_frame"])
+    s = M.FetchScenario(frame, autolab, checkResolution=0.01)
+    orc = oracle.FetchOracle(autolab, frame, 0.01)
+    paths = np.load(os.path.join(GOLDEN, "fetch_paths.npz"))
+    for name in paths.files:
+        P = paths[name]
+        assert (s.check_states(P) == orc.check_states(P)).all(), name
+        assert (s.edge_steps(P[:-1], P[1:]) == [orc.edge_steps(a, b) for a, b in zip(P[:-1], P[1:])]).all()
+        assert (s.check_edges(P[:-1], P[1:]) == orc.check_edges(P[:-1], P[1:])).all(), name
+    P = paths["makePath010"]
+    assert s.check_edges(P[:-1], P[1:]).all() and all(s.isValid(a, b) for a, b in zip(P[:-1], P[1:]))
+
+
+def test_random_edges_match_oracle(autolab, oracle):
+    frame = frame_from_option(FETCH_TASKS["fetch_task_002"]["env_frame"])
+    s = M.FetchScenario(frame, autolab, checkResolution=0.01)
+    orc = oracle.FetchOracle(autolab, frame, 0.01)
+    Q = fetch_configs(3000, SEED + 9)
+    Q = Q[s.check_states(Q)]
+    n = 300
+    A, B = Q[:n], Q[n:2 * n].copy()
+    B[::2] = A[::2] + (B[::2] - A[::2]) * 0.03        # short hops: many fully valid edges
+    got, checked = s.check_edges(A, B, return_states_checked=True)
+    want = orc.check_edges(A, B)
+    assert (got == want).all(), np.nonzero(got != want)[0][:10]
+    assert 0.1 < want.mean() < 0.9 and checked > 0
+    assert s.isValid(A[0], A[0])                       # steps == 0: only `to`
+
+
+def test_empty_environment_only_self_collision(oracle):
+    s = M.FetchScenario(np.hstack([np.eye(3), np.zeros((3, 1))]), np.zeros((0, 3, 3)), checkResolution=0.01)
+    Q = fetch_configs(20000, SEED + 1)
+    want = np.array([oracle.FetchOracle.self_collision(q) == 0 for q in Q])
+    assert (s.check_states(Q) == want).all()

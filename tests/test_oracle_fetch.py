@@ -1,0 +1,98 @@
+"""CPU: the Fetch oracle (FK, libccd MPR, box-box, mesh-vs-shape restatement) against what the
+repository holds.  PARITY UNPINNED: no golden vectors exist; the anchors are
+  * test/fetch_robot_jacobian_test.cpp's use of fk(): reproduced as closed-form frame checks;
+  * the scripted start states (scripts/fetch_task_00{1,2}.sh) must be valid;
+  * src/mpl_fetch.cpp:36-220 holds ten joint-space paths recorded by the authors; six of them
+    (003,004,005,008,009,010) validate completely (every waypoint, every discretised edge at
+    resolution 0.01) under the task-001 environment frame, three more up to their last edge
+    (the approach into the grasp), 001 predates the current environment."""
+import os
+
+import numpy as np
+import pytest
+
+from mplambda_b200.workload import FETCH_TASKS, SEED, fetch_configs, frame_from_option
+from conftest import GOLDEN
+
+
+@pytest.fixture(scope="module")
+def autolab(scenes):
+    return scenes["autolab"][0]
+
+
+def test_fk_closed_form(oracle):
+    # all joints zero: the arm points along +x; chain of the translations in fetch_robot.hpp:280-304
+    frames, gz = oracle.FetchOracle.fk(np.zeros(8))
+    x = -0.086875 + 0.119525 + 0.117 + 0.219 + 0.133 + 0.197 + 0.1245 + 0.1385 + 0.16645
+    z = 0.37743 + 0.34858 + 0.0599999999999999
+    assert abs(gz - z) < 1e-15
+    np.testing.assert_allclose(frames[9][:, 3], [x - 0.09, 0, z + 0.0025], atol=1e-15)   # gripper link
+    np.testing.assert_allclose(frames[9][:, :3], np.eye(3), atol=1e-15)
+    np.testing.assert_allclose(frames[0][:, 3], [0, 0, 0.1975], atol=0)                   # base cylinder
+    # torso lift moves everything above it by q[0]
+    f2, gz2 = oracle.FetchOracle.fk(np.array([0.2, 0, 0, 0, 0, 0, 0, 0.0]))
+    assert abs(gz2 - gz - 0.2) < 1e-15
+    # shoulder pan by 90 degrees turns the arm towards +y
+    f3, _ = oracle.FetchOracle.fk(np.array([0, np.pi / 2, 0, 0, 0, 0, 0, 0.0]))
+    arm = x - (-0.086875 + 0.119525) - 0.09
+    np.testing.assert_allclose(f3[9][:, 3], [-0.086875 + 0.119525, arm, z + 0.0025], atol=1e-12)
+    # every frame is a rigid transform
+    for q in fetch_configs(50, SEED):
+        fr, _ = oracle.FetchOracle.fk(q)
+        for f in fr:
+            np.testing.assert_allclose(f[:, :3] @ f[:, :3].T, np.eye(3), atol=1e-12)
+
+
+def test_scripted_starts_valid(autolab, oracle):
+    for task, cfg in FETCH_TASKS.items():
+        orc = oracle.FetchOracle(autolab, frame_from_option(cfg["env_frame"]), 0.01)
+        assert orc.check_states(np.array([cfg["start"]]))[0], task
+        assert oracle.FetchOracle.self_collision(np.array(cfg["start"])) == 0
+
+
+def test_self_collision_cases(oracle):
+    sc = oracle.FetchOracle.self_collision
+    assert sc(np.array([0.1, np.pi / 2, np.pi / 2, 0, np.pi / 2, 0, np.pi / 2, 0])) == 0     # restConfig
+    assert sc(np.zeros(8)) == 0                                                            # arm straight out
+    assert sc(np.array([0.0, 0, 1.5, 0, 0, 0, 0, 0])) != 0                                 # arm down into the base
+    codes = np.array([sc(q) for q in fetch_configs(2000, SEED)])
+    assert (codes == 25).any() and (codes == 0).any() and ((codes >= 1) & (codes <= 24)).any()   # floor / free / pairs
+    assert sc(np.array([0.0, 0, -1.2, 0, 2.2, 0, 2.0, 0])) != 0                            # folded back into the body
+
+
+def test_recorded_paths(autolab, oracle):
+    paths = np.load(os.path.join(GOLDEN, "fetch_paths.npz"))
+    orc = oracle.FetchOracle(autolab, frame_from_option(FETCH_TASKS["fetch_task_001"]["env_frame"]), 0.01)
+    for name in ("makePath003", "makePath004", "makePath005", "makePath008", "makePath009", "makePath010"):
+        P = paths[name]
+        assert orc.check_states(P).all(), name
+        assert orc.check_edges(P[:-1], P[1:]).all(), name
+    for name in ("makePath002", "makePath006", "makePath007"):
+        P = paths[name]
+        assert orc.check_states(P).all(), name
+        assert orc.check_edges(P[:-2], P[1:-1]).all(), name
+
+
+def test_known_answers_are_stable(autolab, oracle):
+    g = np.load(os.path.join(GOLDEN, "fetch_verdicts.npz"))
+    Q = fetch_configs(4096, SEED)
+    for task, cfg in FETCH_TASKS.items():
+        orc = oracle.FetchOracle(autolab, frame_from_option(cfg["env_frame"]), 0.01)
+        assert (orc.check_states(Q) == g[task + "_valid"]).all()
+    fk = np.array([oracle.FetchOracle.fk(q)[0] for q in Q[:64]])
+    assert (fk == g["fk_frames"]).all()
+
+
+def test_edge_semantics(autolab, oracle):
+    orc = oracle.FetchOracle(autolab, frame_from_option(FETCH_TASKS["fetch_task_001"]["env_frame"]), 0.01)
+    Q = fetch_configs(400, SEED + 5)
+    Q = Q[orc.check_states(Q)]
+    A, B = Q[:20], Q[20:40].copy()
+    B[::2] = A[::2] + (B[::2] - A[::2]) * 0.02
+    got = orc.check_edges(A, B)
+    for a, b, v in zip(A, B, got):
+        s = orc.edge_steps(a, b)
+        ts = np.arange(1, s) / float(s) if s >= 2 else np.zeros(0)
+        states = np.array([a + (b - a) * t for t in ts] + [b])
+        assert bool(orc.check_states(states).all()) == bool(v)
+    assert got.any() and not got.all()

@@ -72,6 +72,31 @@ def main():
         paths[f.replace(".", "_")] = np.concatenate([rows[:, 3:7], rows[:, 0:3]], axis=1)
     np.savez_compressed(os.path.join(OUT, "paths.npz"), **paths)
 
+    # src/mpl_fetch.cpp:36-220: ten joint-space solution paths the reference's authors recorded
+    import re
+    src = open(os.path.join(REF, "src", "mpl_fetch.cpp")).read()
+    fp = {}
+    for m in re.finditer(r"std::vector<T> (makePath\d+)\(\) \{(.*?)return P;", src, re.S):
+        rows = [[float(x) for x in r.split(",")] for r in re.findall(r"addPath\(P, ([^)]*)\)", m.group(2))]
+        P = np.array(rows)
+        if "std::reverse" in m.group(2):
+            P = P[::-1].copy()
+        fp[m.group(1)] = P
+    np.savez_compressed(os.path.join(OUT, "fetch_paths.npz"), **fp)
+
+    # Fetch known answers from the oracle for the seeded configuration stream (both task frames)
+    from mplambda_b200.workload import FETCH_TASKS, fetch_configs, frame_from_option
+    fg = {}
+    Q = fetch_configs(4096, SEED)
+    for task, cfg in FETCH_TASKS.items():
+        orc = O.FetchOracle(autolab, frame_from_option(cfg["env_frame"]), 0.01)
+        fg[task + "_valid"] = orc.check_states(Q)
+        fg[task + "_why"] = np.array([orc.why(q) for q in Q[:1024]], dtype=np.int32)
+        print(task, "valid frac", fg[task + "_valid"].mean())
+    fk = np.array([O.FetchOracle.fk(q)[0] for q in Q[:64]])
+    fg["fk_frames"] = fk
+    np.savez_compressed(os.path.join(OUT, "fetch_verdicts.npz"), **fg)
+
 
 if __name__ == "__main__":
     main()
