@@ -42,6 +42,14 @@ def load_scene(name):
     return d["env"], d["robot"]
 
 
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1: ignore it for the CPU arm)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -105,7 +113,7 @@ def cpu_baseline(env, robot, poses, threads, target_seconds=12.0):
     """Oracle O2 (FCL traversal order, first-hit exit) on a bounded sample sized for ~10-20 s."""
     from oracle import oracle_py as O
     orc = O.SE3Oracle(env, robot)
-    threads = threads or O.lib().orc_omp_max_threads()
+    threads = threads or host_threads()
     orc.check_states(poses[:8192], O.BVH, threads=threads)   # warm-up
     n = len(poses)
     ctr = O.Counters()
@@ -132,7 +140,7 @@ def run_reference(args, rank, world):
     env, robot = load_scene(args.workload)
     sc = SE3_SCENES[args.workload]
     orc = O.SE3Oracle(env, robot)
-    threads = O.lib().orc_omp_max_threads()
+    threads = host_threads()
     sample = args.ref_sample
     batches = [se3_poses(sample, sc["min"], sc["max"], SEED, start=r * N_POSES) for r in range(ROTATE)]
     for w in range(args.warmup):

@@ -263,8 +263,12 @@ FlatBvh buildBvh(const double *tris, size_t n) {
         b.centroid[i] = (b.verts[3 * i] + b.verts[3 * i + 1] + b.verts[3 * i + 2]) * (1.0 / 3.0);
     b.boxes.reserve(2 * n);
     b.link.reserve(2 * n);
-    b.boxes.resize(1);
-    b.link.resize(1);
+    // node 1 is padding: every pair of children then starts at an even index, i.e. the two siblings
+    // (2 x 64 B) share one 128-byte line
+    b.boxes.resize(2);
+    b.link.resize(2);
+    b.boxes[1] = Box{{{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, {0, 0, 0}, {0, 0, 0}};
+    b.link[1] = -1;
     b.build(0, 0, (int)n, 0);
     out.depth = b.depth;
 

@@ -173,6 +173,8 @@ static int createSe3(const double *envTris, size_t nEnv, const double *robotTris
     d.envTris64 = (const double *)sc->envTris64.ptr;
     d.nRobotNodes = (int)robot.nodes.size();
     d.nEnvNodes = (int)env.nodes.size();
+    d.haveGeometry = nEnv > 0 && nRobot > 0;
+    d.bothRootsLeaf = nEnv == 1 && nRobot == 1;
     d.bitsA = bitsFor(std::max<size_t>(2, robot.nodes.size()));
     d.bitsB = bitsFor(std::max<size_t>(2, env.nodes.size()));
     d.wide = (6 + d.bitsA + d.bitsB) > 32;

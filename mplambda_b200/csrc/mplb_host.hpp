@@ -33,7 +33,7 @@ struct alignas(16) TriF32 {
 static_assert(sizeof(TriF32) == 48, "triangle must be 48 bytes");
 
 struct FlatBvh {
-    std::vector<BvhNode> nodes;   // 2n-1 nodes, root = 0, siblings adjacent
+    std::vector<BvhNode> nodes;   // 2n nodes: root = 0, node 1 is padding, sibling pairs start at even indices
     std::vector<TriF32> tris32;   // FP32 rounded copy, index = original triangle id
     std::vector<double> tris64;   // [n][9], the exact input
     int depth = 0;                // max root->leaf edge count

@@ -15,6 +15,8 @@ struct SceneDev {
     const double *robotTris64;  // 9 doubles per triangle (exact re-evaluation)
     const double *envTris64;
     int nRobotNodes, nEnvNodes;
+    int haveGeometry;           // both meshes non-empty
+    int bothRootsLeaf;          // both meshes are a single triangle
     int bitsA, bitsB;           // bits needed for a robot / env node index
     int wide;                   // 1: pair entries need 64 bits
     float envRadius;            // max |vertex| of the environment

@@ -33,9 +33,16 @@
 namespace mplb {
 namespace {
 
-constexpr int kWarpsPerCta = 8;
+#ifndef MPLB_WARPS_PER_CTA
+#define MPLB_WARPS_PER_CTA 8
+#endif
+#ifndef MPLB_MIN_CTAS
+#define MPLB_MIN_CTAS 2
+#endif
+constexpr int kWarpsPerCta = MPLB_WARPS_PER_CTA;
 constexpr int kSlots = 64;          // state slots per warp
 constexpr int kQueueCap = 96;       // leaf / exact queue entries per warp
+constexpr int kStepsPerRound = 4;   // depth-first steps between two rounds of slot bookkeeping
 constexpr unsigned kFull = 0xffffffffu;
 
 // Per-warp shared memory, carved from the dynamic allocation at run time: the LIFO only gets as
@@ -531,13 +538,13 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
                 slot = sm.list[rank];
                 mySlot = (int)slot;
                 sm.workers[slot] = 1;
-                if (sc.nRobotNodes > 0 && sc.nEnvNodes > 0 && (sc.nRobotNodes > 1 || sc.nEnvNodes > 1)) {
+                if (sc.haveGeometry && !sc.bothRootsLeaf) {
                     sm.stack[0][lane] = sc.rootEntry;  // root pair, expanded without testing itself
                     bot = 0;
                     sp = 1;
                 }
             }
-            if (sc.nRobotNodes == 1 && sc.nEnvNodes == 1) {  // two single-triangle meshes: straight to the leaf test
+            if (sc.bothRootsLeaf) {  // two single-triangle meshes: straight to the leaf test
                 const unsigned m = __ballot_sync(kFull, take);
                 if (take) {
                     sm.triq[nt + __popc(m & ltMask)] = cd.pack(slot, 0, 0);
@@ -663,8 +670,11 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
             while (nx >= 32) exactBatch();
         }
         if (nx > 0 && nActive <= 16) exactBatch();
-        // ---- one depth-first step per lane: pop a pair, test both children of the larger box
-        if (nActive) {
+        // ---- depth-first steps: each lane pops a pair and tests both children of the larger box.
+        //      A few steps run back to back before the slot bookkeeping above is revisited (a lane that
+        //      finishes early idles for at most kStepsPerRound - 1 steps; the leaf queue is re-checked
+        //      every step because one step can add 64 pairs to it).
+        for (int rep = 0; rep < kStepsPerRound && nActive && nt < 32; ++rep) {
             bool act = sp > bot;
             const unsigned slot = (unsigned)max(mySlot, 0);
             if (act && hitM.test(slot)) {  // decided meanwhile (leaf test, another lane, or a sibling sample of the edge)
@@ -740,17 +750,29 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
                     return nextA ? ((unsigned)linkR | idxE << bitsA | 0x80000000u) : (idxR | (unsigned)linkE << bitsA);
                 };
                 const unsigned e0 = entryFor(child, link0, sz0), e1 = entryFor(child + 1, link1, sz1);
+                unsigned top;
                 if (s0 && s1) {
                     const bool zeroFirst = d0 > d1;  // push the farther first
                     sm.stack[sp][lane] = zeroFirst ? e0 : e1;
-                    sm.stack[sp + 1][lane] = zeroFirst ? e1 : e0;
+                    sm.stack[sp + 1][lane] = top = zeroFirst ? e1 : e0;
                     sp += 2;
                 } else {
-                    sm.stack[sp][lane] = s0 ? e0 : e1;
+                    sm.stack[sp][lane] = top = s0 ? e0 : e1;
                     sp += 1;
+                }
+                // the pair this lane pops next: start pulling its three nodes towards L1 now (children
+                // pairs are 128-byte aligned, so one line holds both)
+                {
+                    const bool dA = (top >> 31) != 0;
+                    const unsigned r = top & maskA, e = (top & 0x7fffffffu) >> bitsA;
+                    const float4 *pc = dA ? sc.robotNodes + 4 * (size_t)r : sc.envNodes + 4 * (size_t)e;
+                    const float4 *pf = dA ? sc.envNodes + 4 * (size_t)e : sc.robotNodes + 4 * (size_t)r;
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pc));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
                 }
             }
             __syncwarp();
+            nActive = __popc(__ballot_sync(kFull, sp > bot));
         }
     }
 }
@@ -777,7 +799,7 @@ __device__ __forceinline__ void flushCounters(const WarpCounters &c, DevCounters
 }
 
 template <typename E>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MPLB_MIN_CTAS)
 checkStatesKernel(SceneDev sc, const double *__restrict__ states, unsigned long long n, uint8_t *__restrict__ valid,
                   DevCounters *ctr, unsigned long long *workCounter) {
     WarpSmem<E> sm = warpSmem<E>(sc.stackLevels);
@@ -788,7 +810,7 @@ checkStatesKernel(SceneDev sc, const double *__restrict__ states, unsigned long 
 }
 
 template <typename E>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MPLB_MIN_CTAS)
 checkEdgesKernel(SceneDev sc, const double *__restrict__ from, const double *__restrict__ to,
                  const unsigned *__restrict__ steps, unsigned long long nEdges, unsigned maxChunks, unsigned grab,
                  unsigned *dead, DevCounters *ctr, unsigned long long *workCounter) {
