@@ -282,16 +282,17 @@ static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, siz
     }
     int rc;
     const size_t sb = n * 7 * sizeof(double);
+    const size_t stackBytes = edgeStackBytes(sc->numSms);
     if ((rc = c->in0.reserve(sb)) || (rc = c->in1.reserve(sb)) || (rc = c->steps.reserve(n * 4)) ||
-        (rc = c->dead.reserve(n * 4)) || (rc = c->out.reserve(n)))
+        (rc = c->dead.reserve(n * 4)) || (rc = c->out.reserve(n)) || (rc = c->aux0.reserve(stackBytes)))
         return rc;
     MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(DevCounters), c->stream));
     MPLB_CUDA(cudaMemcpyAsync(c->in0.ptr, from, sb, cudaMemcpyHostToDevice, c->stream));
     MPLB_CUDA(cudaMemcpyAsync(c->in1.ptr, to, sb, cudaMemcpyHostToDevice, c->stream));
     MPLB_CUDA(cudaMemcpyAsync(c->steps.ptr, c->hSteps.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
     MPLB_CUDA(launchCheckEdges(sc->dev, (const double *)c->in0.ptr, (const double *)c->in1.ptr,
-                               (const unsigned *)c->steps.ptr, n, maxSteps, (unsigned *)c->dead.ptr,
-                               (uint8_t *)c->out.ptr, (DevCounters *)c->ctr.ptr, (unsigned long long *)c->work.ptr,
+                               (const unsigned *)c->steps.ptr, n, (unsigned *)c->dead.ptr, (uint8_t *)c->out.ptr,
+                               (DevCounters *)c->ctr.ptr, (unsigned long long *)c->work.ptr, c->aux0.ptr, stackBytes,
                                sc->numSms, c->stream));
     sc->hLaunches += 2;
     MPLB_CUDA(cudaMemcpyAsync(valid, c->out.ptr, n, cudaMemcpyDeviceToHost, c->stream));
@@ -432,10 +433,12 @@ int mplb_check_edges_device(mplb_scene *scene, const double *d_from, const doubl
         std::lock_guard<std::mutex> g(s->mu);
         int rc = s->globalDead.reserve(n * 4);
         if (rc != MPLB_OK) return rc;
+        if ((rc = s->globalStacks.reserve(edgeStackBytes(s->numSms))) != MPLB_OK) return rc;
     }
-    MPLB_CUDA(launchCheckEdges(s->dev, d_from, d_to, d_steps, n, max_steps, (unsigned *)s->globalDead.ptr, d_valid,
-                               (DevCounters *)s->globalCtr.ptr, (unsigned long long *)s->globalWork.ptr, s->numSms,
-                               (cudaStream_t)stream));
+    (void)max_steps;
+    MPLB_CUDA(launchCheckEdges(s->dev, d_from, d_to, d_steps, n, (unsigned *)s->globalDead.ptr, d_valid,
+                               (DevCounters *)s->globalCtr.ptr, (unsigned long long *)s->globalWork.ptr,
+                               s->globalStacks.ptr, edgeStackBytes(s->numSms), s->numSms, (cudaStream_t)stream));
     s->hLaunches += 2;
     return MPLB_OK;
 }

@@ -33,13 +33,16 @@ __device__ __forceinline__ F3 cross(F3 a, F3 b) {
     return {fmaf(a.y, b.z, -a.z * b.y), fmaf(a.z, b.x, -a.x * b.z), fmaf(a.x, b.y, -a.y * b.x)};
 }
 
-// OBB-OBB separating-axis test (Gottschalk's 15 axes).  Conservative: `slack` exceeds the FP32
-// evaluation error of either side, so a pair is only culled when the exact boxes are disjoint.
-// A and B are boxes in their own frames, (R,T) = rows x0..x2 maps B's frame into A's.
-__device__ __forceinline__ bool obbOverlap(const float4 a0, const float4 a1, const float4 a2, const float4 ae,
-                                           const float4 b0, const float4 b1, const float4 b2, const float4 be,
-                                           const float4 x0, const float4 x1, const float4 x2, float slack, float &dist2) {
-    // env centre in the robot frame, relative to the robot box centre, in the robot box axes
+// OBB-OBB separating-axis test (Gottschalk's 15 axes) as a gap: the largest amount by which any of the
+// axes separates the boxes (negative: every axis overlaps).  A and B are boxes in their own frames,
+// (R,T) = rows x0..x2 maps B's frame into A's.  The boxes overlap for a caller iff gap <= slack, with a
+// slack above the FP32 evaluation error (so a pair is only culled when the exact boxes are disjoint)
+// plus, for interval certificates, the reach of the motion.  Cross-product axes are not normalised
+// (|axis| <= 1), which only makes their gap smaller, i.e. the test more conservative.
+__device__ __forceinline__ float obbGap(const float4 a0, const float4 a1, const float4 a2, const float4 ae,
+                                        const float4 b0, const float4 b1, const float4 b2, const float4 be,
+                                        const float4 x0, const float4 x1, const float4 x2, float &dist2) {
+    // B's centre in A's frame, relative to A's centre, in A's box axes
     float cx = fmaf(x0.x, b0.w, fmaf(x0.y, b1.w, fmaf(x0.z, b2.w, x0.w))) - a0.w;
     float cy = fmaf(x1.x, b0.w, fmaf(x1.y, b1.w, fmaf(x1.z, b2.w, x1.w))) - a1.w;
     float cz = fmaf(x2.x, b0.w, fmaf(x2.y, b1.w, fmaf(x2.z, b2.w, x2.w))) - a2.w;
@@ -69,14 +72,14 @@ __device__ __forceinline__ bool obbOverlap(const float4 a0, const float4 a1, con
             }
     }
     const float ea[3] = {ae.x, ae.y, ae.z}, eb[3] = {be.x, be.y, be.z};
-    bool sep = false;
+    float gap = -3.0e38f;
 #pragma unroll
     for (int i = 0; i < 3; ++i)
-        sep |= fabsf(T[i]) > ea[i] + fmaf(eb[0], Bf[i][0], fmaf(eb[1], Bf[i][1], fmaf(eb[2], Bf[i][2], slack)));
+        gap = fmaxf(gap, fabsf(T[i]) - (ea[i] + fmaf(eb[0], Bf[i][0], fmaf(eb[1], Bf[i][1], eb[2] * Bf[i][2]))));
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         float s = fmaf(T[0], B[0][j], fmaf(T[1], B[1][j], T[2] * B[2][j]));
-        sep |= fabsf(s) > eb[j] + fmaf(ea[0], Bf[0][j], fmaf(ea[1], Bf[1][j], fmaf(ea[2], Bf[2][j], slack)));
+        gap = fmaxf(gap, fabsf(s) - (eb[j] + fmaf(ea[0], Bf[0][j], fmaf(ea[1], Bf[1][j], ea[2] * Bf[2][j]))));
     }
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -85,12 +88,17 @@ __device__ __forceinline__ bool obbOverlap(const float4 a0, const float4 a1, con
         for (int j = 0; j < 3; ++j) {
             const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
             float s = fmaf(T[i2], B[i1][j], -T[i1] * B[i2][j]);
-            float r = fmaf(ea[i1], Bf[i2][j], fmaf(ea[i2], Bf[i1][j], fmaf(eb[j1], Bf[i][j2], fmaf(eb[j2], Bf[i][j1], slack))));
-            sep |= fabsf(s) > r;
+            float r = fmaf(ea[i1], Bf[i2][j], fmaf(ea[i2], Bf[i1][j], fmaf(eb[j1], Bf[i][j2], eb[j2] * Bf[i][j1])));
+            gap = fmaxf(gap, fabsf(s) - r);
         }
     }
-    return !sep;
+    return gap;
 }
 
+__device__ __forceinline__ bool obbOverlap(const float4 a0, const float4 a1, const float4 a2, const float4 ae,
+                                           const float4 b0, const float4 b1, const float4 b2, const float4 be,
+                                           const float4 x0, const float4 x1, const float4 x2, float slack, float &dist2) {
+    return obbGap(a0, a1, a2, ae, b0, b1, b2, be, x0, x1, x2, dist2) <= slack;
+}
 
 }  // namespace mplb

@@ -34,8 +34,11 @@ struct DevCounters {
 cudaError_t launchCheckStates(const SceneDev &sc, const double *dStates, size_t n, uint8_t *dValid,
                               DevCounters *dCtr, unsigned *dWork, int numSms, cudaStream_t stream);
 
+// scratch for the per-warp interval LIFOs of checkEdgesKernel
+size_t edgeStackBytes(int numSms);
+
 cudaError_t launchCheckEdges(const SceneDev &sc, const double *dFrom, const double *dTo, const unsigned *dSteps,
-                             size_t n, unsigned maxSteps, unsigned *dDead, uint8_t *dValid, DevCounters *dCtr,
-                             unsigned long long *dWork, int numSms, cudaStream_t stream);
+                             size_t n, unsigned *dDead, uint8_t *dValid, DevCounters *dCtr, unsigned long long *dWork,
+                             void *dStacks, size_t stackBytes, int numSms, cudaStream_t stream);
 
 }  // namespace mplb

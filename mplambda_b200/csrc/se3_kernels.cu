@@ -42,6 +42,7 @@ namespace {
 constexpr int kWarpsPerCta = MPLB_WARPS_PER_CTA;
 constexpr int kSlots = 64;          // state slots per warp
 constexpr int kQueueCap = 96;       // leaf / exact queue entries per warp
+constexpr unsigned kPhaseBSub = 64;    // phase-B work items per edge (isValid(from,to), see EdgeSource)
 constexpr int kStepsPerRound = 4;   // depth-first steps between two rounds of slot bookkeeping
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -52,28 +53,33 @@ template <typename E>
 struct WarpSmem {
     unsigned (*stack)[32];            // [level][lane]: robotIdx | envIdx << bitsA | descendRobot << 31  (bank = lane)
     float4 (*xf)[4];                  // per slot: rows of (R | T), then (slack, eta, -, -); see makeSlot
-    unsigned *tag0, *tag1;            // what the slot is (state index, or edge + sample)
+    unsigned *tag0, *tag1, *tag2, *tag3;  // what the slot is (state index; or edge, sample, interval lo, hi)
     int *pending;                     // leaf pairs of the slot still sitting in triq/exq
     int *workers;                     // lanes currently searching the slot (work stealing splits a search)
     unsigned *list;                   // scratch: compacted slot / lane lists
+    uint4 *work;                      // scratch: up to 32 work descriptors of the current refill
     E *triq;                          // slot | robotTri << 6 | envTri << (6 + bitsA)
     E *exq;
 
     static __host__ __device__ size_t bytes(int levels) {
-        return (size_t)levels * 128 + kSlots * 64 + kSlots * 20 + 2 * kQueueCap * sizeof(E);
+        return (size_t)levels * 128 + kSlots * 64 + 32 * 16 + kSlots * 28 + 2 * kQueueCap * sizeof(E);
     }
     __device__ void carve(unsigned char *base, int levels) {
         stack = reinterpret_cast<unsigned(*)[32]>(base);
         base += (size_t)levels * 128;
         xf = reinterpret_cast<float4(*)[4]>(base);
         base += kSlots * 64;
+        work = reinterpret_cast<uint4 *>(base);
+        base += 32 * 16;
         triq = reinterpret_cast<E *>(base);
         base += kQueueCap * sizeof(E);
         exq = reinterpret_cast<E *>(base);
         base += kQueueCap * sizeof(E);
         tag0 = reinterpret_cast<unsigned *>(base);
         tag1 = tag0 + kSlots;
-        pending = reinterpret_cast<int *>(tag1 + kSlots);
+        tag2 = tag1 + kSlots;
+        tag3 = tag2 + kSlots;
+        pending = reinterpret_cast<int *>(tag3 + kSlots);
         workers = pending + kSlots;
         list = reinterpret_cast<unsigned *>(workers + kSlots);
     }
@@ -164,7 +170,9 @@ __device__ void interpolateD(const double *from, const double *to, double t, dou
 // FP32 fast path
 
 // Round the FP64 relative transform to the FP32 slot and derive the error parameters.
-__device__ void makeSlot(const double s[7], const SceneDev &sc, float4 *xf) {
+// extraSlack > 0 turns the slot into an interval certificate: every box test is inflated by the largest
+// displacement any robot point can have, relative to this pose, over the interval the slot stands for.
+__device__ void makeSlot(const double s[7], const SceneDev &sc, float4 *xf, float extraSlack = 0.f) {
     XformD X;
     stateToRelD(s, X);
     double qn = s[0] * s[0] + s[1] * s[1] + s[2] * s[2] + s[3] * s[3];
@@ -177,7 +185,7 @@ __device__ void makeSlot(const double s[7], const SceneDev &sc, float4 *xf) {
     xf[0] = make_float4((float)X.R[0][0], (float)X.R[0][1], (float)X.R[0][2], (float)X.T[0]);
     xf[1] = make_float4((float)X.R[1][0], (float)X.R[1][1], (float)X.R[1][2], (float)X.T[1]);
     xf[2] = make_float4((float)X.R[2][0], (float)X.R[2][1], (float)X.R[2][2], (float)X.T[2]);
-    xf[3] = make_float4(slack, eta, 0.f, 0.f);
+    xf[3] = make_float4(slack + extraSlack, eta, slack, 0.f);  // .z keeps the plain slack
 }
 
 enum TriVerdict : int { kTriNo = 0, kTriYes = 1, kTriUnsure = 2 };
@@ -288,7 +296,9 @@ struct StateSource {
     unsigned long long base = 0;
     bool exhausted = false;
 
-    __device__ int acquire(int want, unsigned lane) {
+    __device__ bool done() const { return exhausted; }
+    template <typename SM>
+    __device__ int acquire(int want, unsigned lane, SM &) {
         unsigned long long b = 0;
         if (lane == 0) b = atomicAdd(counter, (unsigned long long)want);
         b = __shfl_sync(kFull, b, 0);
@@ -303,54 +313,79 @@ struct StateSource {
         }
         return want;
     }
-    __device__ void load(int rank, double s[7], unsigned &t0, unsigned &t1) const {
+    // -> false when the item turned out to need no work
+    template <typename SM>
+    __device__ bool load(int rank, double s[7], unsigned t[4], float &extraSlack, const SM &) const {
         const unsigned long long i = base + rank;
-        t0 = (unsigned)i;
-        t1 = (unsigned)(i >> 32);
-        stateOf(t0, t1, s);
+        t[0] = (unsigned)i;
+        t[1] = (unsigned)(i >> 32);
+        t[2] = t[3] = 0;
+        extraSlack = 0.f;
+        stateOf(t[0], t[1], s);
+        return true;
     }
     __device__ void stateOf(unsigned t0, unsigned t1, double s[7]) const {
         const double *src = states + 7 * (((unsigned long long)t1 << 32) | t0);
 #pragma unroll
         for (int k = 0; k < 7; ++k) s[k] = __ldg(src + k);
     }
-    __device__ void retire(unsigned t0, unsigned t1, bool hit) const {
-        valid[((unsigned long long)t1 << 32) | t0] = hit ? 0 : 1;
+    // warp-collective: slots `lane` (r0) and `lane + 32` (r1) retire
+    template <typename SM>
+    __device__ void retire(SM &sm, unsigned lane, bool r0, bool r1, const Masks64 &hit, const Masks64 &, unsigned &) const {
+        if (r0) valid[((unsigned long long)sm.tag1[lane] << 32) | sm.tag0[lane]] = ((hit.lo >> lane) & 1u) ? 0 : 1;
+        if (r1) valid[((unsigned long long)sm.tag1[lane + 32] << 32) | sm.tag0[lane + 32]] = ((hit.hi >> lane) & 1u) ? 0 : 1;
     }
     template <typename SM>
     __device__ void onHit(Masks64, SM &, Masks64 &, const Masks64 &) {}
 };
 
-// isValid(from,to) over an array of edges.  Work items are (chunk c, edge e), c-major: chunk 0
-// of every edge (its 64 coarsest samples, `to` included) is handed out before any chunk 1, so an
-// edge that dies early never expands its fine samples.  Sample j of an edge: j = 0 is `to`
-// itself (se3...:136); otherwise i = bitrev_L(j), 2^L > steps, is the interpolated state at
-// t = i * (1/steps) (se3...:146,159) and exists when i < steps.
+// isValid(from,to) over an array of edges (se3...:134-178): verdict = valid(to) AND every interpolated
+// sample i in [1, steps-1] at t = i * (1/steps).  The samples are not enumerated one by one:
+//   phase A (item e):          `to` and the 63 coarsest samples (multiples of 2^(L-6), 2^L > steps) are
+//                              tested exactly; most invalid edges die here.
+//   phase B (item nEdges + e): each gap between two coarse samples is an INTERVAL [lo, hi].  One
+//                              traversal at its middle sample, with every box test inflated by the largest
+//                              displacement any robot point can have over the interval, either certifies all
+//                              of its samples free at once (no leaf pair came within reach), or tests the
+//                              middle sample exactly and hands the two halves back to the warp's interval
+//                              LIFO.  A sample is the middle of exactly one interval, so the worst case is
+//                              one traversal per sample (as plain enumeration) and the free-space case is
+//                              ~64 traversals per edge.  The verdict is the reference's discrete one.
+// Motion bound: translation is a lerp and Eigen's slerp turns at constant rate, so between samples i and m
+// a robot point x moves at most |i-m|/steps * (||dt|| + 2 theta |x|), theta = acos|qa.qb|.
 struct EdgeSource {
     const double *from, *to;
     const unsigned *steps;
-    unsigned long long nEdges, nItems;
+    unsigned long long nEdges;
     unsigned grab;
     unsigned *dead;
     unsigned long long *counter;
-    bool exhausted = false;
+    uint4 *stack;          // this warp's interval LIFO (global memory): (edge, lo, hi, -)
+    unsigned stackCap;
+    float robotRadius;
+    unsigned *errorFlag;
+    bool globalDone = false;
+    unsigned stackCount = 0;
     // current grab of items and the live ones among them
     unsigned long long first = 0;
     unsigned liveMask = 0;
     // current item
     bool have = false;
-    unsigned curEdge = 0, curChunk = 0, curBits = 0, curSteps = 0, pos = 0;
-    // last acquire
-    unsigned lastMask = 0, lastPos = 0;
+    unsigned curEdge = 0, curPhase = 0, curBits = 0, curSteps = 0, pos = 0;
 
+    __device__ bool done() const { return globalDone && stackCount == 0; }
+
+    // item space: [0, nEdges) phase A of edge e; then kPhaseBSub sub-items per edge, sub-item major (so that
+    // neighbouring items are different edges), each covering 64 / kPhaseBSub of the edge's 64 gaps
     __device__ bool nextItem(unsigned lane) {
+        const unsigned long long nItems = (1 + kPhaseBSub) * nEdges;
         for (;;) {
             while (liveMask) {
                 const int src = __ffs(liveMask) - 1;
                 liveMask &= liveMask - 1;
                 const unsigned long long it = first + src;
                 curEdge = (unsigned)(it % nEdges);
-                curChunk = (unsigned)(it / nEdges);
+                curPhase = (unsigned)(it / nEdges);   // 0: phase A, 1 + sub: phase B sub-item
                 if (((volatile unsigned *)dead)[curEdge]) continue;
                 curSteps = __ldg(steps + curEdge);
                 curBits = curSteps ? 32 - __clz(curSteps) : 0;
@@ -358,11 +393,12 @@ struct EdgeSource {
                 have = true;
                 return true;
             }
+            if (globalDone) return false;
             unsigned long long f = 0;
             if (lane == 0) f = atomicAdd(counter, (unsigned long long)grab);
             f = __shfl_sync(kFull, f, 0);
             if (f >= nItems) {
-                exhausted = true;
+                globalDone = true;
                 return false;
             }
             first = f;
@@ -370,67 +406,154 @@ struct EdgeSource {
             const unsigned long long item = f + lane;
             if (lane < grab && item < nItems) {
                 const unsigned long long e = item % nEdges;
-                const unsigned c = (unsigned)(item / nEdges);
                 const unsigned st = __ldg(steps + e);
                 const unsigned bits = st ? 32 - __clz(st) : 0;
-                live = c < max(1u, (1u << bits) >> 6) && !((volatile unsigned *)dead)[e];
+                live = !((volatile unsigned *)dead)[e] && (item < nEdges || bits > 6);  // phase B only if gaps exist
             }
             liveMask = __ballot_sync(kFull, live);
         }
     }
-    __device__ int acquire(int want, unsigned lane) {
-        for (;;) {
-            if (!have && !nextItem(lane)) return 0;
-            if (pos >= 64) {
+    // Up to `want` pieces of work as (edge, lo, hi) descriptors in sm.work[]: halves of intervals that could
+    // not be certified first (depth first, keeps the LIFO short), topped up from as many items as it takes,
+    // so that the FP64 state expansion runs on full warps.
+    template <typename SM>
+    __device__ int acquire(int want, unsigned lane, SM &sm) {
+        int count = min(want, (int)stackCount);
+        stackCount -= count;
+        if ((int)lane < count) sm.work[lane] = stack[stackCount + lane];
+        while (count < want) {
+            if (!have && !nextItem(lane)) break;
+            const unsigned span = curPhase == 0 ? 64u : 64u / kPhaseBSub;
+            if (pos >= span) {
                 have = false;
                 continue;
             }
-            const unsigned j = curChunk * 64 + pos + lane;
-            const bool ok = pos + lane < 64 && (j == 0 || (j < (1u << curBits) && bitrev(j, curBits) < curSteps));
-            const unsigned m = __ballot_sync(kFull, ok);
+            bool ok;
+            unsigned lo = 0, hi = 0;
+            const unsigned c = pos + lane;
+            if (curPhase == 0) {
+                ok = c < 64 && (c == 0 || (c < (1u << curBits) && bitrev(c, curBits) < curSteps));
+                lo = hi = c == 0 ? curSteps : bitrev(c, curBits);   // sample `steps` stands for `to`
+            } else {
+                const unsigned k = (curPhase - 1) * span + c, stride = 1u << (curBits - 6);
+                lo = k * stride + 1;
+                hi = min((k + 1) * stride - 1, curSteps - 1);
+                ok = c < span && lo <= hi;
+            }
+            unsigned m = __ballot_sync(kFull, ok);
             const int avail = __popc(m);
             if (avail == 0) {
                 pos += 32;
                 continue;
             }
-            lastPos = pos;
-            if (avail <= want) {
-                lastMask = m;
+            const int room = want - count;
+            if (avail > room) {
+                const unsigned cut = __fns(m, 0, room + 1);  // first candidate NOT taken
+                m &= (1u << cut) - 1u;
+                pos += cut;
+            } else {
                 pos += 32;
-                return avail;
             }
-            const unsigned cut = __fns(m, 0, want + 1);  // first sample NOT taken
-            lastMask = m & ((1u << cut) - 1u);
-            pos += cut;
-            return want;
+            if ((m >> lane) & 1u) sm.work[count + __popc(m & ((1u << lane) - 1u))] = make_uint4(curEdge, lo, hi, 0);
+            count += __popc(m);
         }
+        __syncwarp();
+        return count;
     }
-    __device__ void load(int rank, double s[7], unsigned &t0, unsigned &t1) const {
-        t0 = curEdge;
-        t1 = curChunk * 64 + lastPos + __fns(lastMask, 0, rank + 1);
-        stateOf(t0, t1, s);
-    }
-    __device__ void stateOf(unsigned t0, unsigned t1, double s[7]) const {
-        const double *b = to + 7 * (size_t)t0;
-        if (t1 == 0) {
+    // sample index `steps` stands for `to` itself
+    __device__ void sampleState(unsigned e, unsigned i, unsigned st, double s[7]) const {
+        const double *b = to + 7 * (size_t)e;
+        if (i >= st) {
 #pragma unroll
             for (int k = 0; k < 7; ++k) s[k] = __ldg(b + k);
             return;
         }
-        const double *a = from + 7 * (size_t)t0;
+        const double *a = from + 7 * (size_t)e;
         double fa[7], fb[7];
 #pragma unroll
         for (int k = 0; k < 7; ++k) {
             fa[k] = __ldg(a + k);
             fb[k] = __ldg(b + k);
         }
-        const unsigned st = __ldg(steps + t0);
-        const unsigned bits = 32 - __clz(st);
-        const double delta = __ddiv_rn(1.0, (double)st);
-        interpolateD(fa, fb, dmul((double)bitrev(t1, bits), delta), s);
+        interpolateD(fa, fb, dmul((double)i, __ddiv_rn(1.0, (double)st)), s);
     }
-    __device__ void retire(unsigned t0, unsigned, bool hit) const {
-        if (hit) dead[t0] = 1u;
+    template <typename SM>
+    __device__ bool load(int rank, double s[7], unsigned t[4], float &extraSlack, const SM &sm) const {
+        const uint4 w = sm.work[rank];
+        const unsigned e = w.x, lo = w.y, hi = w.z;
+        if (((volatile unsigned *)dead)[e]) return false;
+        const unsigned st = __ldg(steps + e);
+        const unsigned mid = lo + (hi - lo) / 2;
+        sampleState(e, mid, st, s);
+        extraSlack = 0.f;
+        if (hi > lo) {
+            const double *a = from + 7 * (size_t)e, *b = to + 7 * (size_t)e;
+            double qa[4], qb[4], d = 0, na = 0, nb = 0, dt2 = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                qa[k] = __ldg(a + k);
+                qb[k] = __ldg(b + k);
+                d += qa[k] * qb[k];
+                na += qa[k] * qa[k];
+                nb += qb[k] * qb[k];
+            }
+#pragma unroll
+            for (int k = 4; k < 7; ++k) {
+                const double x = __ldg(b + k) - __ldg(a + k);
+                dt2 += x * x;
+            }
+            // rotation matrices of non-unit quaternions scale: the bound below assumes rigid motion
+            const double scale = fmax(1.0, fmax(na, nb));
+            const double theta = acos(fmin(1.0, fabs(d) / sqrt(na * nb)));
+            const double reach = (double)max(hi - mid, mid - lo) / (double)st;
+            const double R = (double)robotRadius * scale;
+            double D = reach * (sqrt(dt2) + 2.0 * theta * R) + fabs(scale - 1.0) * 4.0 * R;
+            D = D * 1.000001 + 1e-6 * R;
+            extraSlack = __double2float_ru(D);
+        }
+        t[0] = e; t[1] = mid; t[2] = lo; t[3] = hi;
+        return true;
+    }
+    __device__ void stateOf(unsigned t0, unsigned t1, double s[7]) const { sampleState(t0, t1, __ldg(steps + t0), s); }
+
+    // warp-collective.  A hit kills the edge; an interval whose traversal reached leaf pairs (touched) and
+    // whose middle sample is free hands its two halves to the LIFO; anything else is finished.
+    template <typename SM>
+    __device__ void retire(SM &sm, unsigned lane, bool r0, bool r1, const Masks64 &hit, const Masks64 &touched,
+                           unsigned &error) {
+        unsigned cnt = 0;
+        uint4 kids[4];
+        auto one = [&](bool r, unsigned slot, bool isHit, bool isTouched) {
+            if (!r) return;
+            const unsigned e = sm.tag0[slot], mid = sm.tag1[slot], lo = sm.tag2[slot], hi = sm.tag3[slot];
+            if (isHit) {
+                dead[e] = 1u;
+                return;
+            }
+            if (hi > lo && isTouched && !((volatile unsigned *)dead)[e]) {
+                if (mid > lo) kids[cnt++] = make_uint4(e, lo, mid - 1, 0);
+                if (mid < hi) kids[cnt++] = make_uint4(e, mid + 1, hi, 0);
+            }
+        };
+        one(r0, lane, (hit.lo >> lane) & 1u, (touched.lo >> lane) & 1u);
+        one(r1, lane + 32, (hit.hi >> lane) & 1u, (touched.hi >> lane) & 1u);
+        // exclusive prefix of cnt over the warp
+        unsigned incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned v = __shfl_up_sync(kFull, incl, d);
+            if ((int)lane >= d) incl += v;
+        }
+        const unsigned total = __shfl_sync(kFull, incl, 31);
+        if (total == 0) return;
+        if (stackCount + total > stackCap) {
+            error = 1;  // reported by the host call; never silent
+            return;
+        }
+        const unsigned at = stackCount + incl - cnt;
+        for (unsigned k = 0; k < cnt; ++k) stack[at + k] = kids[k];
+        stackCount += total;
+        __syncwarp();
     }
     // a sample of an edge collided: drop the rest of that edge held by this warp
     template <typename SM>
@@ -465,7 +588,7 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
     const Codec<E> cd{6 + sc.bitsA};
     const int bitsA = sc.bitsA;
     const unsigned maskA = (1u << bitsA) - 1u;
-    Masks64 freeM{~0u, ~0u}, readyM{0, 0}, hitM{0, 0}, doneM{0, 0};
+    Masks64 freeM{~0u, ~0u}, readyM{0, 0}, hitM{0, 0}, doneM{0, 0}, touchedM{0, 0};  // touched: reached a leaf pair
     // this lane's LIFO holds entries [bot, sp); thieves take from the bottom (the largest subtree)
     int nt = 0, nx = 0, sp = 0, bot = 0, mySlot = -1;
     const int triMin = sc.triBatchMin;
@@ -495,36 +618,42 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
         {
             const bool r0 = ((doneM.lo >> lane) & 1u) && sm.pending[lane] == 0;
             const bool r1 = ((doneM.hi >> lane) & 1u) && sm.pending[lane + 32] == 0;
-            if (r0) src.retire(sm.tag0[lane], sm.tag1[lane], (hitM.lo >> lane) & 1u);
-            if (r1) src.retire(sm.tag0[lane + 32], sm.tag1[lane + 32], (hitM.hi >> lane) & 1u);
             const unsigned m0 = __ballot_sync(kFull, r0), m1 = __ballot_sync(kFull, r1);
-            freeM.lo |= m0; doneM.lo &= ~m0; hitM.lo &= ~m0;
-            freeM.hi |= m1; doneM.hi &= ~m1; hitM.hi &= ~m1;
+            if (m0 | m1) {
+                src.retire(sm, lane, r0, r1, hitM, touchedM, cnt.error);
+                freeM.lo |= m0; doneM.lo &= ~m0; hitM.lo &= ~m0; touchedM.lo &= ~m0;
+                freeM.hi |= m1; doneM.hi &= ~m1; hitM.hi &= ~m1; touchedM.hi &= ~m1;
+            }
         }
         int nActive = __popc(__ballot_sync(kFull, sp > bot));
         unsigned needMask = __ballot_sync(kFull, mySlot < 0);
         // ---- expand a batch of new states into free slots (all lanes convert in parallel)
-        if (!src.exhausted && readyM.count() < __popc(needMask)) {
+        if (!src.done() && needMask && !(readyM.lo | readyM.hi)) {
             const int nfree = freeM.count();
             if (nfree >= 16 || (nfree > 0 && nActive <= 16)) {
-                const int got = src.acquire(min(32, nfree), lane);
+                const int got = src.acquire(min(32, nfree), lane, sm);
                 buildList(freeM);
-                const bool take = (int)lane < got;
+                bool take = (int)lane < got;
                 unsigned slot = 0;
                 if (take) {
                     slot = sm.list[lane];
                     double s[7];
-                    unsigned t0, t1;
-                    src.load((int)lane, s, t0, t1);
-                    makeSlot(s, sc, sm.xf[slot]);
-                    sm.tag0[slot] = t0;
-                    sm.tag1[slot] = t1;
-                    sm.pending[slot] = 0;
+                    unsigned t[4];
+                    float extraSlack;
+                    take = src.load((int)lane, s, t, extraSlack, sm);
+                    if (take) {
+                        makeSlot(s, sc, sm.xf[slot], extraSlack);
+                        sm.tag0[slot] = t[0];
+                        sm.tag1[slot] = t[1];
+                        sm.tag2[slot] = t[2];
+                        sm.tag3[slot] = t[3];
+                        sm.pending[slot] = 0;
+                    }
                 }
                 const Masks64 t = slotBits(take, slot);
                 freeM.lo &= ~t.lo; freeM.hi &= ~t.hi;
                 readyM.lo |= t.lo; readyM.hi |= t.hi;
-                cnt.states += got;
+                cnt.states += __popc(__ballot_sync(kFull, take));
                 __syncwarp();
             }
         }
@@ -551,6 +680,8 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
                     sm.pending[slot] = 1;
                 }
                 nt += __popc(m);
+                const Masks64 tm = slotBits(take, slot);
+                touchedM.lo |= tm.lo; touchedM.hi |= tm.hi;
             }
             const Masks64 t = slotBits(take, slot);
             readyM.lo &= ~t.lo; readyM.hi &= ~t.hi;
@@ -586,7 +717,7 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
         nActive = __popc(__ballot_sync(kFull, sp > bot));
         if (nActive == 0 && nt == 0 && nx == 0) {
             const bool busy = __any_sync(kFull, mySlot >= 0) || (doneM.lo | doneM.hi) || (readyM.lo | readyM.hi);
-            if (!busy && src.exhausted) break;
+            if (!busy && src.done()) break;
             if (++idleSpins > 4096u) {  // bookkeeping bug guard: report instead of hanging the device
                 cnt.error = 1;
                 break;
@@ -681,7 +812,7 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
                 sp = bot;
                 act = false;
             }
-            bool ov0 = false, ov1 = false, leaf0 = false, leaf1 = false, descendA = false;
+            bool ov0 = false, ov1 = false, plain0 = false, plain1 = false, leaf0 = false, leaf1 = false, descendA = false;
             float d0 = 0.f, d1 = 0.f, sz0 = 0.f, sz1 = 0.f, szF = 0.f;
             unsigned fixedIdx = 0, child = 0;
             int link0 = 0, link1 = 0, fixedLink = 0;
@@ -706,8 +837,12 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
                 const float4 y0 = descendA ? make_float4(x0.x, x1.x, x2.x, -fmaf(x0.x, x0.w, fmaf(x1.x, x1.w, x2.x * x2.w))) : x0;
                 const float4 y1 = descendA ? make_float4(x0.y, x1.y, x2.y, -fmaf(x0.y, x0.w, fmaf(x1.y, x1.w, x2.y * x2.w))) : x1;
                 const float4 y2 = descendA ? make_float4(x0.z, x1.z, x2.z, -fmaf(x0.z, x0.w, fmaf(x1.z, x1.w, x2.z * x2.w))) : x2;
-                ov0 = obbOverlap(f0, f1, f2, fe, c00, c01, c02, c0e, y0, y1, y2, x3.x, d0);
-                ov1 = obbOverlap(f0, f1, f2, fe, c10, c11, c12, c1e, y0, y1, y2, x3.x, d1);
+                const float g0 = obbGap(f0, f1, f2, fe, c00, c01, c02, c0e, y0, y1, y2, d0);
+                const float g1 = obbGap(f0, f1, f2, fe, c10, c11, c12, c1e, y0, y1, y2, d1);
+                ov0 = g0 <= x3.x;   // within reach (plain slack, or inflated for an interval certificate)
+                ov1 = g1 <= x3.x;
+                plain0 = g0 <= x3.z;  // overlapping at this very sample
+                plain1 = g1 <= x3.z;
                 link0 = __float_as_int(c0e.w);
                 link1 = __float_as_int(c1e.w);
                 fixedLink = __float_as_int(fe.w);
@@ -720,7 +855,10 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
             }
             cnt.bv += 2ull * __popc(__ballot_sync(kFull, act));
             // leaf-leaf survivors -> shared triangle queue
-            const bool t0 = ov0 && leaf0, t1 = ov1 && leaf1;
+            // a leaf pair within reach means the interval cannot be certified (touched); only pairs that
+            // overlap at this very sample need the triangle test
+            const bool reach0 = ov0 && leaf0, reach1 = ov1 && leaf1;
+            const bool t0 = reach0 && plain0, t1 = reach1 && plain1;
             const unsigned m0 = __ballot_sync(kFull, t0), m1 = __ballot_sync(kFull, t1);
             if (m0 | m1) {
                 const unsigned fixedTri = (unsigned)(-(fixedLink + 1));
@@ -735,6 +873,13 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
                 if (t0 || t1) atomicAdd(&sm.pending[slot], (t0 ? 1 : 0) + (t1 ? 1 : 0));
                 nt += __popc(m0) + __popc(m1);
                 if (nt > kQueueCap) cnt.error = 1;  // cannot happen (see the drain loop above); never silent
+            }
+            if (__any_sync(kFull, reach0 || reach1)) {
+                // the rest of a touched interval's search only has to decide its middle sample: drop the inflation
+                if (reach0 || reach1)
+                    reinterpret_cast<float *>(&sm.xf[slot][3])[0] = reinterpret_cast<const float *>(&sm.xf[slot][3])[2];
+                const Masks64 tm = slotBits(reach0 || reach1, slot);
+                touchedM.lo |= tm.lo; touchedM.hi |= tm.hi;
             }
             // inner survivors -> own LIFO, farther one first so the nearer one is searched first.
             // The pushed entry already names the first child of whichever box the next step splits:
@@ -803,7 +948,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, MPLB_MIN_CTAS)
 checkStatesKernel(SceneDev sc, const double *__restrict__ states, unsigned long long n, uint8_t *__restrict__ valid,
                   DevCounters *ctr, unsigned long long *workCounter) {
     WarpSmem<E> sm = warpSmem<E>(sc.stackLevels);
-    StateSource src{states, n, valid, workCounter};
+    StateSource src;
+    src.states = states; src.n = n; src.valid = valid; src.counter = workCounter;
     WarpCounters cnt;
     runWarp<E>(sm, sc, src, cnt);
     flushCounters(cnt, ctr, false);
@@ -812,10 +958,16 @@ checkStatesKernel(SceneDev sc, const double *__restrict__ states, unsigned long 
 template <typename E>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MPLB_MIN_CTAS)
 checkEdgesKernel(SceneDev sc, const double *__restrict__ from, const double *__restrict__ to,
-                 const unsigned *__restrict__ steps, unsigned long long nEdges, unsigned maxChunks, unsigned grab,
-                 unsigned *dead, DevCounters *ctr, unsigned long long *workCounter) {
+                 const unsigned *__restrict__ steps, unsigned long long nEdges, unsigned grab, unsigned *dead,
+                 uint4 *stacks, unsigned stackCap, DevCounters *ctr, unsigned long long *workCounter) {
     WarpSmem<E> sm = warpSmem<E>(sc.stackLevels);
-    EdgeSource src{from, to, steps, nEdges, nEdges * maxChunks, grab, dead, workCounter};
+    EdgeSource src;
+    src.from = from; src.to = to; src.steps = steps; src.nEdges = nEdges; src.grab = grab; src.dead = dead;
+    src.counter = workCounter;
+    src.stack = stacks + (size_t)(blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)) * stackCap;
+    src.stackCap = stackCap;
+    src.robotRadius = sc.robotRadius;
+    src.errorFlag = &ctr->overflow;
     WarpCounters cnt;
     runWarp<E>(sm, sc, src, cnt);
     flushCounters(cnt, ctr, true);
@@ -852,20 +1004,25 @@ cudaError_t launchStatesT(const SceneDev &sc, const double *dStates, size_t n, u
     return cudaGetLastError();
 }
 
+constexpr unsigned kEdgeStackCap = 2048;   // interval LIFO entries per warp
+constexpr int kMaxCtasPerSm = 3;
+
 template <typename E>
 cudaError_t launchEdgesT(const SceneDev &sc, const double *dFrom, const double *dTo, const unsigned *dSteps, size_t n,
-                         unsigned maxChunks, unsigned *dDead, DevCounters *dCtr, unsigned long long *dWork, int numSms,
-                         cudaStream_t stream) {
+                         unsigned *dDead, DevCounters *dCtr, unsigned long long *dWork, uint4 *dStacks,
+                         size_t stackBytes, int numSms, cudaStream_t stream) {
     auto k = checkEdgesKernel<E>;
     const size_t smem = smemBytes<E>(sc);
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    int grid = gridFor(k, smem, numSms);
-    const unsigned long long nItems = (unsigned long long)n * maxChunks;
+    int grid = std::min(gridFor(k, smem, numSms), kMaxCtasPerSm * numSms);
+    const unsigned long long nItems = (1ull + kPhaseBSub) * n;   // phase A item + phase B sub-items per edge
     const unsigned grab = (unsigned)std::min<unsigned long long>(
         32, std::max<unsigned long long>(1, nItems / (4ull * grid * kWarpsPerCta)));
     grid = (int)std::min<unsigned long long>(grid, (nItems + kWarpsPerCta - 1) / kWarpsPerCta);
-    k<<<std::max(grid, 1), kWarpsPerCta * 32, smem, stream>>>(sc, dFrom, dTo, dSteps, n, maxChunks, grab, dDead, dCtr, dWork);
+    grid = std::max(grid, 1);
+    if ((size_t)grid * kWarpsPerCta * kEdgeStackCap * sizeof(uint4) > stackBytes) return cudaErrorInvalidValue;
+    k<<<grid, kWarpsPerCta * 32, smem, stream>>>(sc, dFrom, dTo, dSteps, n, grab, dDead, dStacks, kEdgeStackCap, dCtr, dWork);
     return cudaGetLastError();
 }
 
@@ -880,18 +1037,20 @@ cudaError_t launchCheckStates(const SceneDev &sc, const double *dStates, size_t 
                    : launchStatesT<unsigned>(sc, dStates, n, dValid, dCtr, (unsigned long long *)dWork, numSms, stream);
 }
 
+size_t edgeStackBytes(int numSms) {
+    return (size_t)numSms * kMaxCtasPerSm * kWarpsPerCta * kEdgeStackCap * sizeof(uint4);
+}
+
 cudaError_t launchCheckEdges(const SceneDev &sc, const double *dFrom, const double *dTo, const unsigned *dSteps,
-                             size_t n, unsigned maxSteps, unsigned *dDead, uint8_t *dValid, DevCounters *dCtr,
-                             unsigned long long *dWork, int numSms, cudaStream_t stream) {
+                             size_t n, unsigned *dDead, uint8_t *dValid, DevCounters *dCtr, unsigned long long *dWork,
+                             void *dStacks, size_t stackBytes, int numSms, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     cudaError_t err = cudaMemsetAsync(dWork, 0, sizeof(unsigned long long), stream);
     if (err != cudaSuccess) return err;
     err = cudaMemsetAsync(dDead, 0, sizeof(unsigned) * n, stream);
     if (err != cudaSuccess) return err;
-    const unsigned bits = maxSteps ? 32 - __builtin_clz(maxSteps) : 0;
-    const unsigned maxChunks = std::max(1u, (1u << bits) >> 6);
-    err = sc.wide ? launchEdgesT<unsigned long long>(sc, dFrom, dTo, dSteps, n, maxChunks, dDead, dCtr, dWork, numSms, stream)
-                  : launchEdgesT<unsigned>(sc, dFrom, dTo, dSteps, n, maxChunks, dDead, dCtr, dWork, numSms, stream);
+    err = sc.wide ? launchEdgesT<unsigned long long>(sc, dFrom, dTo, dSteps, n, dDead, dCtr, dWork, (uint4 *)dStacks, stackBytes, numSms, stream)
+                  : launchEdgesT<unsigned>(sc, dFrom, dTo, dSteps, n, dDead, dCtr, dWork, (uint4 *)dStacks, stackBytes, numSms, stream);
     if (err != cudaSuccess) return err;
     deadToValidKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dDead, n, dValid);
     return cudaGetLastError();

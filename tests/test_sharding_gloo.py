@@ -1,0 +1,87 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the N>1 path -- query sharding, verdict
+all-gather, best-solution exchange and the done flag (the collectives bench.py and sharded planners
+use with NCCL on GPUs)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mplambda_b200 import sharding
+
+
+def test_shard_bounds_cover_and_balance():
+    for n in (0, 1, 7, 64, 1000003):
+        for world in (1, 2, 4, 8):
+            b = [sharding.shard_bounds(n, r, world) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+    rng = np.random.default_rng(0)
+    steps = rng.integers(0, 9000, size=5000)
+    steps[:50] = 0
+    for world in (1, 2, 4, 8):
+        b = sharding.balanced_edge_bounds(steps, world)
+        assert b[0][0] == 0 and b[-1][1] == len(steps)
+        assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+        loads = [int((steps[lo:hi] + 1).sum()) for lo, hi in b]
+        assert max(loads) - min(loads) <= 2 * 9001
+    assert sharding.balanced_edge_bounds([], 4) == [(0, 0)] * 4
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # 1. sharded validity batch with a stand-in checker (the GPU entry point on a real box)
+        states = np.arange(101 * 7, dtype=np.float64).reshape(101, 7)
+        calls = []
+
+        def check(shard):
+            calls.append(len(shard))
+            return shard[:, 0] % 3 == 0
+        full = sharding.sharded_check(check, states)
+        assert (full == (states[:, 0] % 3 == 0)).all()
+        assert calls == [sharding.shard_bounds(101, rank, world)[1] - sharding.shard_bounds(101, rank, world)[0]]
+        # 2. solution exchange: nobody solved yet
+        ex = sharding.SolutionExchange(state_dim=7, max_waypoints=16)
+        assert ex.publish(float("inf"), None) == (float("inf"), -1, None)
+        # rank 1 has the cheaper path
+        path = np.full((3 + rank, 7), float(rank))
+        cost, who, best = ex.publish(10.0 - rank, path)
+        assert (cost, who) == (9.0, 1) and best.shape == (4, 7) and (best == 1.0).all()
+        # tie: lowest rank wins; only one rank has a solution: it wins
+        cost, who, best = ex.publish(5.0, path)
+        assert who == 0 and best.shape == (3, 7)
+        cost, who, best = ex.publish(float("inf") if rank == 0 else 7.5, path)
+        assert (cost, who) == (7.5, 1)
+        # 3. done flag (replaces the coordinator's Done broadcast)
+        assert ex.any_done(False) is False
+        assert ex.any_done(rank == 1) is True
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_exchange_over_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    assert res == {0: "ok", 1: "ok"}, res
