@@ -289,6 +289,7 @@ struct WarpCounters {
 
 // isValid(q) over an array: states are taken in index order from a global counter.
 struct StateSource {
+    static constexpr bool kIntervals = false;  // every slot is a single state
     const double *states;
     unsigned long long n;
     uint8_t *valid;
@@ -354,6 +355,7 @@ struct StateSource {
 // Motion bound: translation is a lerp and Eigen's slerp turns at constant rate, so between samples i and m
 // a robot point x moves at most |i-m|/steps * (||dt|| + 2 theta |x|), theta = acos|qa.qb|.
 struct EdgeSource {
+    static constexpr bool kIntervals = true;   // slots may stand for a whole interval of samples
     const double *from, *to;
     const unsigned *steps;
     unsigned long long nEdges;
@@ -841,8 +843,13 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
                 const float g1 = obbGap(f0, f1, f2, fe, c10, c11, c12, c1e, y0, y1, y2, d1);
                 ov0 = g0 <= x3.x;   // within reach (plain slack, or inflated for an interval certificate)
                 ov1 = g1 <= x3.x;
-                plain0 = g0 <= x3.z;  // overlapping at this very sample
-                plain1 = g1 <= x3.z;
+                if constexpr (Source::kIntervals) {
+                    plain0 = g0 <= x3.z;  // overlapping at this very sample
+                    plain1 = g1 <= x3.z;
+                } else {
+                    plain0 = ov0;
+                    plain1 = ov1;
+                }
                 link0 = __float_as_int(c0e.w);
                 link1 = __float_as_int(c1e.w);
                 fixedLink = __float_as_int(fe.w);
@@ -874,7 +881,7 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
                 nt += __popc(m0) + __popc(m1);
                 if (nt > kQueueCap) cnt.error = 1;  // cannot happen (see the drain loop above); never silent
             }
-            if (__any_sync(kFull, reach0 || reach1)) {
+            if (Source::kIntervals && __any_sync(kFull, reach0 || reach1)) {
                 // the rest of a touched interval's search only has to decide its middle sample: drop the inflation
                 if (reach0 || reach1)
                     reinterpret_cast<float *>(&sm.xf[slot][3])[0] = reinterpret_cast<const float *>(&sm.xf[slot][3])[2];

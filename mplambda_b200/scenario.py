@@ -129,6 +129,11 @@ class SE3RigidBodyScenario:
     def isGoal(self, q):
         return self._space.distance(self.goal_, q) <= self.goalRadius_  # se3...:115-117
 
+    def sample_batch(self, rng, n):
+        """n independent randomSample draws, vectorised (host side, feeds the batched entry points)."""
+        from .planner import se3_random_batch
+        return se3_random_batch(rng, n, self.min_, self.max_)
+
     def isValid(self, q, to=None):
         """isValid(q) (se3...:119-126) or isValid(from, to) (se3...:134-178)."""
         if to is None:

@@ -1,0 +1,55 @@
+"""The batch-issuing RRT (mplambda_b200/planner.py): planner logic on the CPU with the
+oracle as backend, and on the GPU with the real scenario -- both must build the SAME tree, because every
+verdict and every nearest neighbour is identical."""
+import numpy as np
+import pytest
+
+from mplambda_b200.planner import BatchedRRT
+from mplambda_b200.workload import SE3_SCENES
+from cpu_backend import CpuNN, CpuScenario
+
+
+def _check_path(path, sc, orc_scenario):
+    assert path is not None
+    np.testing.assert_array_equal(path[0], np.array(sc["start"]))
+    assert orc_scenario.isGoal(path[-1])
+    assert orc_scenario.check_states(path).all()
+    assert orc_scenario.check_edges(path[:-1], path[1:]).all()
+
+
+def test_cpu_backend_solves_cubicles(scenes):
+    env, robot = scenes["cubicles"]
+    sc = SE3_SCENES["cubicles"]
+    scen = CpuScenario(env, robot, sc)
+    rrt = BatchedRRT(scen, CpuNN(), sc["start"], batch=512, seed=3)
+    path = rrt.solve(time_limit=120)
+    _check_path(path, sc, scen)
+    assert rrt.stats["nodes"] == rrt.n > 1 and rrt.stats["edges_checked"] > 0
+
+
+def test_invalid_start_raises(scenes):
+    env, robot = scenes["cubicles"]
+    sc = SE3_SCENES["cubicles"]
+    scen = CpuScenario(env, robot, sc)
+    cand = scen.sample_batch(np.random.default_rng(0), 64)
+    bad = cand[~scen.check_states(cand)][0]
+    with pytest.raises(ValueError):                 # prrt.hpp:109-110
+        BatchedRRT(scen, CpuNN(), bad)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cubicles", "home"])
+def test_gpu_planner_matches_cpu_planner(name, scenes):
+    import mplambda_b200 as M
+    env, robot = scenes[name]
+    sc = SE3_SCENES[name]
+    g = M.SE3RigidBodyScenario(env, robot, sc["goal"], sc["min"], sc["max"], 0.1)
+    rg = BatchedRRT(g, M.Nigh(M.nn.SE3), sc["start"], batch=1024, seed=5)
+    pg = rg.solve(time_limit=120)
+    c = CpuScenario(env, robot, sc)
+    rc = BatchedRRT(c, CpuNN(), sc["start"], batch=1024, seed=5)
+    pc = rc.solve(time_limit=300)
+    _check_path(pg, sc, c)
+    assert rg.n == rc.n and rg.stats["iterations"] == rc.stats["iterations"]
+    np.testing.assert_array_equal(rg.nodes[:rg.n], rc.nodes[:rc.n])
+    np.testing.assert_array_equal(pg, pc)
