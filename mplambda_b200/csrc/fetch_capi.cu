@@ -75,11 +75,22 @@ struct FetchScene : SceneBase {
         return MPLB_OK;
     }
 
-    int reserveScratch(CallCtx *c, size_t n) {
+    int reserveScratch(CallCtx *c, size_t n, FetchScratch &w) {
         int rc;
+        const size_t pc = fetchPairCap(n), lc = fetchLeafCap(n);
         if ((rc = c->aux0.reserve(n * 144 * sizeof(double))) || (rc = c->aux1.reserve(n)) ||
-            (rc = c->aux2.reserve(n * sizeof(unsigned))))
+            (rc = c->aux2.reserve(n * sizeof(unsigned))) || (rc = c->aux4.reserve(pc * 8)) ||
+            (rc = c->aux5.reserve(lc * 8)) || (rc = c->aux6.reserve(n * sizeof(unsigned))) || (rc = c->work.reserve(64)))
             return rc;
+        w.frames = (double *)c->aux0.ptr;
+        w.selfHit = (unsigned char *)c->aux1.ptr;
+        w.envHit = (unsigned *)c->aux2.ptr;
+        w.survivors = (unsigned *)c->aux6.ptr;
+        w.pairItems = (unsigned long long *)c->aux4.ptr;
+        w.leafItems = (unsigned long long *)c->aux5.ptr;
+        w.pairCap = pc;
+        w.leafCap = lc;
+        w.counts = (unsigned *)c->work.ptr;
         return MPLB_OK;
     }
 
@@ -103,16 +114,16 @@ struct FetchScene : SceneBase {
         CtxGuard g{this, c};
         const size_t nb = std::min(n, kBatch);
         int rc;
-        if ((rc = c->in0.reserve(nb * 8 * sizeof(double))) || (rc = c->out.reserve(nb)) || (rc = reserveScratch(c, nb)))
+        FetchScratch w{};
+        if ((rc = c->in0.reserve(nb * 8 * sizeof(double))) || (rc = c->out.reserve(nb)) || (rc = reserveScratch(c, nb, w)))
             return rc;
         MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(FetchCounters), c->stream));
         for (size_t lo = 0; lo < n; lo += kBatch) {
             const size_t cnt = std::min(kBatch, n - lo);
             MPLB_CUDA(cudaMemcpyAsync(c->in0.ptr, states + 8 * lo, cnt * 8 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-            MPLB_CUDA(launchFetchStates(dev, (const double *)c->in0.ptr, cnt, (double *)c->aux0.ptr,
-                                        (unsigned char *)c->aux1.ptr, (unsigned *)c->aux2.ptr, (uint8_t *)c->out.ptr,
-                                        (FetchCounters *)c->ctr.ptr, c->stream));
-            hLaunches += 3;
+            MPLB_CUDA(launchFetchStates(dev, (const double *)c->in0.ptr, cnt, w, (uint8_t *)c->out.ptr,
+                                        (FetchCounters *)c->ctr.ptr, numSms, c->stream));
+            hLaunches += 6;
             MPLB_CUDA(cudaMemcpyAsync(valid + lo, c->out.ptr, cnt, cudaMemcpyDeviceToHost, c->stream));
         }
         hChecks += n;
@@ -131,8 +142,9 @@ struct FetchScene : SceneBase {
         int rc = planEdges(from, to, n, c->hSteps.data());
         if (rc != MPLB_OK) return rc;
         const size_t sb = n * 8 * sizeof(double);
+        FetchScratch w{};
         if ((rc = c->in0.reserve(sb)) || (rc = c->in1.reserve(sb)) || (rc = c->steps.reserve(n * 4)) ||
-            (rc = c->dead.reserve(n * 4)) || (rc = c->aux3.reserve(kBatch * 8)) || (rc = reserveScratch(c, kBatch)))
+            (rc = c->dead.reserve(n * 4)) || (rc = c->aux3.reserve(kBatch * 8)) || (rc = reserveScratch(c, kBatch, w)))
             return rc;
         MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(FetchCounters), c->stream));
         MPLB_CUDA(cudaMemsetAsync(c->dead.ptr, 0, n * 4, c->stream));
@@ -151,10 +163,9 @@ struct FetchScene : SceneBase {
             MPLB_CUDA(cudaMemcpyAsync(c->aux3.ptr, items.data(), items.size() * 8, cudaMemcpyHostToDevice, c->stream));
             MPLB_CUDA(launchFetchEdgeItems(dev, (const double *)c->in0.ptr, (const double *)c->in1.ptr,
                                            (const unsigned *)c->steps.ptr, (const unsigned long long *)c->aux3.ptr,
-                                           items.size(), (unsigned *)c->dead.ptr, (double *)c->aux0.ptr,
-                                           (unsigned char *)c->aux1.ptr, (unsigned *)c->aux2.ptr,
-                                           (FetchCounters *)c->ctr.ptr, c->stream));
-            hLaunches += 3;
+                                           items.size(), (unsigned *)c->dead.ptr, w, (FetchCounters *)c->ctr.ptr, numSms,
+                                           c->stream));
+            hLaunches += 6;
             launched += items.size();
             MPLB_CUDA(cudaStreamSynchronize(c->stream));
             items.clear();

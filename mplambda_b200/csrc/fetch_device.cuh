@@ -26,13 +26,25 @@ struct FetchCounters {
     unsigned error, pad;
 };
 
-cudaError_t launchFetchStates(const FetchSceneDev &sc, const double *dStates, size_t n, double *dFrames,
-                              unsigned char *dSelfHit, unsigned *dEnvHit, uint8_t *dValid, FetchCounters *dCtr,
-                              cudaStream_t stream);
+// per-call scratch (sized for the largest launch group of n states)
+struct FetchScratch {
+    double *frames;              // [n][12][12]
+    unsigned char *selfHit;      // [n]
+    unsigned *envHit;            // [n]
+    unsigned *survivors;         // [n] indices of the states that passed the self-collision tests
+    unsigned long long *pairItems, *leafItems;
+    size_t pairCap, leafCap;
+    unsigned *counts;            // [4]: pair list, leaf list, survivor list lengths, env item counter
+};
+inline size_t fetchPairCap(size_t n) { return n * 8; }
+inline size_t fetchLeafCap(size_t n) { return n * 16; }
+
+cudaError_t launchFetchStates(const FetchSceneDev &sc, const double *dStates, size_t n, const FetchScratch &w,
+                              uint8_t *dValid, FetchCounters *dCtr, int numSms, cudaStream_t stream);
 
 // items: (edge << 32) | sample index k; k >= steps[edge] means the edge's `to` state
 cudaError_t launchFetchEdgeItems(const FetchSceneDev &sc, const double *dFrom, const double *dTo, const unsigned *dSteps,
-                                 const unsigned long long *dItems, size_t nItems, unsigned *dDead, double *dFrames,
-                                 unsigned char *dSelfHit, unsigned *dEnvHit, FetchCounters *dCtr, cudaStream_t stream);
+                                 const unsigned long long *dItems, size_t nItems, unsigned *dDead, const FetchScratch &w,
+                                 FetchCounters *dCtr, int numSms, cudaStream_t stream);
 
 }  // namespace mplb

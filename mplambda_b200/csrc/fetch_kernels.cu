@@ -16,12 +16,16 @@
 // hierarchy traversal, both with a slack far above the FP32 error, so they can only skip tests
 // whose answer is "disjoint".
 //
-// Kernel A (one thread per state): FK -> 12 frames (kept for kernel B), 24 pair tests with early
-// exit, floor clearance.  Kernel B (one thread per (state, shape)): depth-first traversal of the
-// environment hierarchy with a private stack, exact MPR at the leaves, first hit wins.
+// Four kernels per batch, cheap FP32 culling and exact FP64 tests kept apart so that warps stay convergent:
+//   1 fetchFkKernel   (thread per state)            FK -> 12 frames, floor clearance, box culling of the 24 pairs
+//   2 fetchPairKernel (thread per surviving pair)   exact shape-shape test (MPR / box-box)
+//   3 fetchEnvKernel  (thread per state x shape)    FP32 traversal of the environment hierarchy
+//   4 fetchLeafKernel (thread per surviving leaf)   exact shape-triangle MPR
+// Survivors travel through device-side work lists; a full list degrades to inline exact tests.
 #include "fetch_device.cuh"
 #include "device_math.cuh"
 
+#include <algorithm>
 #include <cfloat>
 
 namespace mplb {
@@ -376,14 +380,60 @@ __device__ void storeFrame(double *dst, const FrameD &f) {
     }
 }
 
-// one thread per state: FK, self collision (24 pairs, early exit), floor clearance.
+// Work lists filled by the culling kernels and drained by the exact (FP64 MPR) kernels: separating the
+// cheap FP32 culling from the expensive exact tests keeps every warp of either kind convergent.
+struct WorkList {
+    unsigned long long *items;   // packed work descriptors
+    unsigned *count;             // number of items appended (may exceed capacity: overflow handled inline)
+    unsigned capacity;
+};
+__device__ __forceinline__ bool listPush(const WorkList &l, unsigned long long v) {
+    const unsigned at = atomicAdd(l.count, 1u);
+    if (at >= l.capacity) return false;
+    l.items[at] = v;
+    return true;
+}
+
+__device__ int exactPair(const FetchSceneDev &sc, const double *frames, unsigned long long state, int k) {
+    const int a = kSelfPairs[k][0], b = kSelfPairs[k][1];
+    const FetchShape &sa = sc.shapes[a], &sb = sc.shapes[b];
+    FrameD fa, fb;
+    loadFrame(frames + state * 144 + 12 * a, fa);
+    loadFrame(frames + state * 144 + 12 * b, fb);
+    if (sa.type == 0 && sb.type == 0) return boxBoxIntersect(sa, fa, sb, fb) ? 1 : 0;
+    CcdObj o1, o2;
+    makeShapeObj(sa, fa, o1);
+    makeShapeObj(sb, fb, o2);
+    return mprIntersect(o1, o2);
+}
+
+__device__ int exactLeaf(const FetchSceneDev &sc, const double *frames, unsigned long long state, int g, unsigned tri) {
+    FrameD f, ef;
+    loadFrame(frames + state * 144 + 12 * g, f);
+    loadFrame(sc.envFrame, ef);
+    CcdObj shapeObj, t;
+    makeShapeObj(sc.shapes[g], f, shapeObj);
+    const double *tp = sc.envTris64 + 9 * (size_t)tri;
+    t.kind = 3;
+    t.a = t.b = t.c = 0;
+    t.p[0] = {tp[0], tp[1], tp[2]};
+    t.p[1] = {tp[3], tp[4], tp[5]};
+    t.p[2] = {tp[6], tp[7], tp[8]};
+    t.cen = {__ddiv_rn(dadd(dadd(tp[0], tp[3]), tp[6]), 3.0), __ddiv_rn(dadd(dadd(tp[1], tp[4]), tp[7]), 3.0),
+             __ddiv_rn(dadd(dadd(tp[2], tp[5]), tp[8]), 3.0)};
+    objSetFrame(t, ef);
+    return mprIntersect(shapeObj, t);   // [EXT] GJKSolver_libccd::shapeTriangleIntersect
+}
+
+// Kernel 1, one thread per state: FK -> 12 frames, floor clearance, FP32 box culling of the 24 pairs.
 // `states` are explicit joint vectors, or (edgeItems != nullptr) samples of edges: item = (edge, i)
 // with state = from + (to - from) * (i * (1/steps)), i == steps meaning `to` itself.
 __global__ void __launch_bounds__(128)
-fetchSelfKernel(FetchSceneDev sc, const double *__restrict__ states, const double *__restrict__ from,
-                const double *__restrict__ to, const unsigned *__restrict__ steps,
-                const unsigned long long *__restrict__ edgeItems, const unsigned *__restrict__ dead, unsigned long long n,
-                double *__restrict__ frames /* [n][12][12] */, unsigned char *__restrict__ selfHit, FetchCounters *ctr) {
+fetchFkKernel(FetchSceneDev sc, const double *__restrict__ states, const double *__restrict__ from,
+              const double *__restrict__ to, const unsigned *__restrict__ steps,
+              const unsigned long long *__restrict__ edgeItems, const unsigned *__restrict__ dead, unsigned long long n,
+              double *__restrict__ frames /* [n][12][12] */, unsigned char *__restrict__ selfHit, WorkList pairs,
+              FetchCounters *ctr) {
     const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     double q[8];
@@ -412,146 +462,232 @@ fetchSelfKernel(FetchSceneDev sc, const double *__restrict__ states, const doubl
         for (int j = 0; j < 8; ++j) q[j] = states[8 * i + j];
     }
 
-    // fk(): fetch_robot.hpp:276-315
-    FrameD F[12];
-    FrameD cur;
+    // fk(): fetch_robot.hpp:276-315; every geometry frame goes straight to global memory
+    double *out = frames + i * 144;
+    FrameD cur, g;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
 #pragma unroll
         for (int b = 0; b < 3; ++b) cur.R[a][b] = a == b ? 1.0 : 0.0;
         cur.t[a] = 0;
     }
-    frameMul(cur, sc.origins + 12 * 0, F[0]);           // base
+    // conservative FP32 copy of each geometry box for the pair culling: centre + axes (columns of R)
+    float bx[12][12];
+    auto emit = [&](int gi) {
+        frameMul(cur, sc.origins + 12 * gi, g);
+        storeFrame(out + 12 * gi, g);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) bx[gi][3 * r + c] = (float)g.R[r][c];
+            bx[gi][9 + r] = (float)g.t[r];
+        }
+    };
+    emit(0);                                            // base
     frameTranslate(cur, -0.086875, 0, 0.37743);         // torsoLiftJointOrigin
     frameTranslate(cur, 0, 0, q[0]);                    // torsoLiftLink
-    frameMul(cur, sc.origins + 12 * 1, F[1]);           // torsoLift box
-    frameMul(cur, sc.origins + 12 * 10, F[10]);         // neck
-    frameMul(cur, sc.origins + 12 * 11, F[11]);         // head
+    emit(1); emit(10); emit(11);                        // torso box, neck, head
     frameTranslate(cur, 0.119525, 0, 0.34858);
     frameRotate(cur, q[1], 2);                          // shoulderPanLink
-    frameMul(cur, sc.origins + 12 * 2, F[2]);
+    emit(2);
     frameTranslate(cur, 0.117, 0, 0.0599999999999999);
     frameRotate(cur, q[2], 1);                          // shoulderLiftLink
-    frameMul(cur, sc.origins + 12 * 3, F[3]);
+    emit(3);
     frameTranslate(cur, 0.219, 0, 0);
     frameRotate(cur, q[3], 0);                          // upperarmRollLink
-    frameMul(cur, sc.origins + 12 * 4, F[4]);
+    emit(4);
     frameTranslate(cur, 0.133, 0, 0);
     frameRotate(cur, q[4], 1);                          // elbowFlexLink
-    frameMul(cur, sc.origins + 12 * 5, F[5]);
+    emit(5);
     frameTranslate(cur, 0.197, 0, 0);
     frameRotate(cur, q[5], 0);                          // forearmRollLink
-    frameMul(cur, sc.origins + 12 * 6, F[6]);
+    emit(6);
     frameTranslate(cur, 0.1245, 0, 0);
     frameRotate(cur, q[6], 1);                          // wristFlexLink
-    frameMul(cur, sc.origins + 12 * 7, F[7]);
+    emit(7);
     frameTranslate(cur, 0.1385, 0, 0);
     frameRotate(cur, q[7], 0);                          // wristRollLink
-    frameMul(cur, sc.origins + 12 * 8, F[8]);
+    emit(8);
     frameTranslate(cur, 0.16645, 0, 0);                 // gripperAxis
     const double gripperAxisZ = cur.t[2];
     frameTranslate(cur, -0.09, 0, 0.0025);              // gripperLink == gripper geometry frame
-    F[9] = cur;
+    emit(9);                                            // origin 9 is the identity
 
-    double *out = frames + i * 144;
-    for (int g = 0; g < 12; ++g) storeFrame(out + 12 * g, F[g]);
-
-    // selfCollision(): fetch_robot.hpp:502-584
-    unsigned pairTests = 0;
-    int hit = 0;
-    for (int k = 0; k < 24 && !hit; ++k) {
-        const int a = kSelfPairs[k][0], b = kSelfPairs[k][1];
-        const FetchShape &sa = sc.shapes[a], &sb = sc.shapes[b];
-        if (shapeBoxesDisjoint(sa, F[a], sb, F[b])) continue;
-        ++pairTests;
-        if (sa.type == 0 && sb.type == 0) {
-            hit = boxBoxIntersect(sa, F[a], sb, F[b]) ? 1 : 0;
-        } else {
-            CcdObj o1, o2;
-            makeShapeObj(sa, F[a], o1);
-            makeShapeObj(sb, F[b], o2);
-            const int r = mprIntersect(o1, o2);
-            if (r < 0) atomicExch(&ctr->error, 1u);
-            hit = r == 1;
+    // selfCollision(): fetch_robot.hpp:502-584.  The floor test is exact here; pairs whose boxes are not
+    // certainly disjoint go to the exact kernel (the verdict is an OR, so the order does not matter).
+    int hit = gripperAxisZ < 0.30 ? 1 : 0;              // floorClearance_, fetch_robot.hpp:105,580
+    if (!hit) {
+        for (int k = 0; k < 24; ++k) {
+            const int a = kSelfPairs[k][0], b = kSelfPairs[k][1];
+            float e1[3], e2[3];
+            shapeExtents(sc.shapes[a], e1);
+            shapeExtents(sc.shapes[b], e2);
+            const float *A = bx[a], *B = bx[b];
+            float R[3][3], T[3];
+            const float d[3] = {B[9] - A[9], B[10] - A[10], B[11] - A[11]};
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) R[r][c] = A[r] * B[c] + A[3 + r] * B[3 + c] + A[6 + r] * B[6 + c];
+                T[r] = A[r] * d[0] + A[3 + r] * d[1] + A[6 + r] * d[2];
+            }
+            float dist2;
+            const float4 u0 = make_float4(1, 0, 0, 0), u1 = make_float4(0, 1, 0, 0), u2 = make_float4(0, 0, 1, 0);
+            if (!obbOverlap(u0, u1, u2, make_float4(e1[0] * 1.00001f, e1[1] * 1.00001f, e1[2] * 1.00001f, 0), u0, u1, u2,
+                            make_float4(e2[0] * 1.00001f, e2[1] * 1.00001f, e2[2] * 1.00001f, 0),
+                            make_float4(R[0][0], R[0][1], R[0][2], T[0]), make_float4(R[1][0], R[1][1], R[1][2], T[1]),
+                            make_float4(R[2][0], R[2][1], R[2][2], T[2]), kCullSlack, dist2))
+                continue;
+            if (!listPush(pairs, (i << 8) | (unsigned)k)) {   // list full: decide it here
+                const int r = exactPair(sc, frames, i, k);
+                if (r < 0) atomicExch(&ctr->error, 1u);
+                if (r == 1) {
+                    hit = 1;
+                    break;
+                }
+            }
         }
     }
-    if (!hit && gripperAxisZ < 0.30) hit = 1;  // floorClearance_, fetch_robot.hpp:105,580
     selfHit[i] = (unsigned char)hit;
-    if (pairTests) atomicAdd(&ctr->pairTests, (unsigned long long)pairTests);
 }
 
-// one thread per (state, geometry): environment hierarchy vs the shape's box, MPR at the leaves
+// Kernel 2, one thread per listed (state, pair): exact shape-shape test
 __global__ void __launch_bounds__(128)
-fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsigned char *__restrict__ selfHit,
-               unsigned long long n, unsigned *__restrict__ envHit, FetchCounters *ctr) {
-    const unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    const unsigned long long i = tid / 12;
-    const int g = (int)(tid % 12);
-    if (i >= n || selfHit[i] || sc.nEnvNodes == 0) return;
-    FrameD f;
-    loadFrame(frames + i * 144 + 12 * g, f);
-    const FetchShape &s = sc.shapes[g];
-    float e[3];
-    shapeExtents(s, e);
-    // shape box in world coordinates: axes = columns of f.R
-    const float4 a0 = make_float4((float)f.R[0][0], (float)f.R[1][0], (float)f.R[2][0], (float)f.t[0]);
-    const float4 a1 = make_float4((float)f.R[0][1], (float)f.R[1][1], (float)f.R[2][1], (float)f.t[1]);
-    const float4 a2 = make_float4((float)f.R[0][2], (float)f.R[1][2], (float)f.R[2][2], (float)f.t[2]);
-    const float4 ae = make_float4(e[0] * 1.00001f, e[1] * 1.00001f, e[2] * 1.00001f, 0);
+fetchPairKernel(FetchSceneDev sc, const double *__restrict__ frames, WorkList pairs, unsigned char *selfHit,
+                FetchCounters *ctr) {
+    const unsigned n = min(*pairs.count, pairs.capacity);
+    unsigned tested = 0;
+    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const unsigned long long v = pairs.items[j];
+        const unsigned long long state = v >> 8;
+        if (selfHit[state]) continue;   // already colliding (floor, or another pair)
+        const int r = exactPair(sc, frames, state, (int)(v & 255));
+        ++tested;
+        if (r < 0) atomicExch(&ctr->error, 1u);
+        if (r == 1) selfHit[state] = 1;
+    }
+    if (tested) atomicAdd(&ctr->pairTests, (unsigned long long)tested);
+}
+
+__device__ __noinline__ int exactLeafSlow(const FetchSceneDev &sc, const double *frames, unsigned long long state, int g,
+                                          unsigned tri) {
+    return exactLeaf(sc, frames, state, g, tri);
+}
+
+// Kernel 3a: list the states that survived the self-collision tests (about half of a random batch)
+__global__ void fetchSurvivorsKernel(const unsigned char *__restrict__ selfHit, unsigned long long n, unsigned *list,
+                                     unsigned *count) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const bool keep = i < n && selfHit[i] == 0;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (!m) return;
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned base = 0;
+    if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(count, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (keep) list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned)i;
+}
+
+// Kernel 3b, persistent: every lane runs one depth-first traversal of the environment hierarchy (FP32 box
+// tests against one shape's box) at a time and takes the next (surviving state, geometry) item the moment
+// its stack runs dry, so lanes stay busy although traversal depths differ wildly.  Leaves that cannot be
+// culled go to the exact kernel.
+__global__ void __launch_bounds__(128)
+fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsigned *__restrict__ survivors,
+               const unsigned *__restrict__ nSurvivors, unsigned *__restrict__ envHit, WorkList leaves,
+               unsigned *itemCounter, FetchCounters *ctr) {
+    if (sc.nEnvNodes == 0) return;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned nItems = *nSurvivors * 12u;
     const float4 x0 = make_float4((float)sc.envFrame[0], (float)sc.envFrame[1], (float)sc.envFrame[2], (float)sc.envFrame[3]);
     const float4 x1 = make_float4((float)sc.envFrame[4], (float)sc.envFrame[5], (float)sc.envFrame[6], (float)sc.envFrame[7]);
     const float4 x2 = make_float4((float)sc.envFrame[8], (float)sc.envFrame[9], (float)sc.envFrame[10], (float)sc.envFrame[11]);
-    // obbOverlap expects A's centre in the .w of its axis rows, in A's own frame: use world = A frame with
-    // identity-like handling by passing the box axes/centre directly (A frame == world here)
-    CcdObj shapeObj;
-    bool haveObj = false;
     int stack[40];
     int sp = 0;
-    stack[sp++] = 0;
-    unsigned bv = 0, leaf = 0;
-    bool hit = false;
-    while (sp > 0 && !hit) {
-        const int node = stack[--sp];
-        const float4 *pn = sc.envNodes + 4 * (size_t)node;
-        const float4 b0 = ldg4(pn), b1 = ldg4(pn + 1), b2 = ldg4(pn + 2), be = ldg4(pn + 3);
-        ++bv;
-        float dist2;
-        if (!obbOverlap(a0, a1, a2, ae, b0, b1, b2, be, x0, x1, x2, kCullSlack, dist2)) continue;
-        const int link = __float_as_int(be.w);
-        if (link >= 0) {
-            if (sp + 2 > 40) {
-                atomicExch(&ctr->error, 1u);
-                break;
+    float4 a0, a1, a2, ae;
+    unsigned long long state = 0;
+    int g = 0;
+    unsigned bv = 0;
+    bool exhausted = false;
+    for (;;) {
+        // refill the lanes whose traversal is over
+        const unsigned need = __ballot_sync(0xffffffffu, sp == 0);
+        if (need && !exhausted) {
+            unsigned base = 0;
+            const int leader = __ffs(need) - 1;
+            if ((int)lane == leader) base = atomicAdd(itemCounter, (unsigned)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (base + __popc(need) >= nItems) exhausted = true;
+            if (sp == 0) {
+                const unsigned item = base + __popc(need & ((1u << lane) - 1u));
+                if (item < nItems) {
+                    state = survivors[item / 12u];
+                    g = (int)(item % 12u);
+                    const double *fp = frames + state * 144 + 12 * g;
+                    float e[3];
+                    shapeExtents(sc.shapes[g], e);
+                    // shape box in world coordinates: axes = columns of R
+                    a0 = make_float4((float)fp[0], (float)fp[4], (float)fp[8], (float)fp[3]);
+                    a1 = make_float4((float)fp[1], (float)fp[5], (float)fp[9], (float)fp[7]);
+                    a2 = make_float4((float)fp[2], (float)fp[6], (float)fp[10], (float)fp[11]);
+                    ae = make_float4(e[0] * 1.00001f, e[1] * 1.00001f, e[2] * 1.00001f, 0);
+                    stack[sp++] = 0;
+                }
             }
-            stack[sp++] = link + 1;
-            stack[sp++] = link;
+        }
+        if (__ballot_sync(0xffffffffu, sp > 0) == 0) {
+            if (exhausted) break;
             continue;
         }
-        // leaf: exact shape-triangle MPR ([EXT] GJKSolver_libccd::shapeTriangleIntersect)
-        if (!haveObj) {
-            makeShapeObj(s, f, shapeObj);
-            haveObj = true;
+        if (sp > 0) {
+            const int node = stack[--sp];
+            const float4 *pn = sc.envNodes + 4 * (size_t)node;
+            const float4 b0 = ldg4(pn), b1 = ldg4(pn + 1), b2 = ldg4(pn + 2), be = ldg4(pn + 3);
+            ++bv;
+            float dist2;
+            if (obbOverlap(a0, a1, a2, ae, b0, b1, b2, be, x0, x1, x2, kCullSlack, dist2)) {
+                const int link = __float_as_int(be.w);
+                if (link >= 0) {
+                    if (sp + 2 > 40) {
+                        atomicExch(&ctr->error, 1u);
+                        sp = 0;
+                    } else {
+                        stack[sp++] = link + 1;
+                        stack[sp++] = link;
+                    }
+                } else {
+                    const unsigned tri = (unsigned)(-(link + 1));
+                    if (!listPush(leaves, (state << 28) | ((unsigned long long)g << 24) | tri)) {   // list full: decide it here
+                        const int r = exactLeafSlow(sc, frames, state, g, tri);
+                        if (r < 0) atomicExch(&ctr->error, 1u);
+                        if (r == 1) {
+                            envHit[state] = 1u;
+                            sp = 0;
+                        }
+                    }
+                }
+            }
         }
-        const double *tp = sc.envTris64 + 9 * (size_t)(-(link + 1));
-        CcdObj tri;
-        tri.kind = 3;
-        tri.a = tri.b = tri.c = 0;
-        tri.p[0] = {tp[0], tp[1], tp[2]};
-        tri.p[1] = {tp[3], tp[4], tp[5]};
-        tri.p[2] = {tp[6], tp[7], tp[8]};
-        tri.cen = {__ddiv_rn(dadd(dadd(tp[0], tp[3]), tp[6]), 3.0), __ddiv_rn(dadd(dadd(tp[1], tp[4]), tp[7]), 3.0),
-                   __ddiv_rn(dadd(dadd(tp[2], tp[5]), tp[8]), 3.0)};
-        FrameD ef;
-        loadFrame(sc.envFrame, ef);
-        objSetFrame(tri, ef);
-        ++leaf;
-        const int r = mprIntersect(shapeObj, tri);
-        if (r < 0) atomicExch(&ctr->error, 1u);
-        hit = r == 1;
     }
-    if (hit) envHit[i] = 1u;
     atomicAdd(&ctr->bvTests, (unsigned long long)bv);
-    if (leaf) atomicAdd(&ctr->leafTests, (unsigned long long)leaf);
+}
+
+// Kernel 4, one thread per listed (state, geometry, triangle): exact shape-triangle test
+__global__ void __launch_bounds__(128)
+fetchLeafKernel(FetchSceneDev sc, const double *__restrict__ frames, WorkList leaves, unsigned *envHit,
+                FetchCounters *ctr) {
+    const unsigned n = min(*leaves.count, leaves.capacity);
+    unsigned tested = 0;
+    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const unsigned long long v = leaves.items[j];
+        const unsigned long long state = v >> 28;
+        if (envHit[state]) continue;
+        const int r = exactLeaf(sc, frames, state, (int)((v >> 24) & 15), (unsigned)(v & 0xffffff));
+        ++tested;
+        if (r < 0) atomicExch(&ctr->error, 1u);
+        if (r == 1) envHit[state] = 1u;
+    }
+    if (tested) atomicAdd(&ctr->leafTests, (unsigned long long)tested);
 }
 
 __global__ void fetchCombineKernel(const unsigned char *__restrict__ selfHit, const unsigned *__restrict__ envHit,
@@ -570,31 +706,45 @@ __global__ void fetchEdgeReduceKernel(const unsigned char *__restrict__ selfHit,
     if (selfHit[i] || envHit[i]) dead[(unsigned)(edgeItems[i] >> 32)] = 1u;
 }
 
+// the exact kernels' grids do not depend on the list lengths (grid-stride over the device-side counts)
+cudaError_t runFetch(const FetchSceneDev &sc, const double *dStates, const double *dFrom, const double *dTo,
+                     const unsigned *dSteps, const unsigned long long *dItems, const unsigned *dDead, size_t n,
+                     const FetchScratch &w, FetchCounters *dCtr, int numSms, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(w.envHit, 0, n * sizeof(unsigned), stream);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(w.counts, 0, 4 * sizeof(unsigned), stream);
+    if (e != cudaSuccess) return e;
+    WorkList pairs{w.pairItems, w.counts, (unsigned)std::min<size_t>(w.pairCap, 0xffffffffu)};
+    WorkList leaves{w.leafItems, w.counts + 1, (unsigned)std::min<size_t>(w.leafCap, 0xffffffffu)};
+    const int exactGrid = numSms * 8;
+    fetchFkKernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(sc, dStates, dFrom, dTo, dSteps, dItems, dDead, n, w.frames,
+                                                                   w.selfHit, pairs, dCtr);
+    fetchPairKernel<<<exactGrid, 128, 0, stream>>>(sc, w.frames, pairs, w.selfHit, dCtr);
+    fetchSurvivorsKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w.selfHit, n, w.survivors, w.counts + 2);
+    fetchEnvKernel<<<exactGrid, 128, 0, stream>>>(sc, w.frames, w.survivors, w.counts + 2, w.envHit, leaves, w.counts + 3, dCtr);
+    fetchLeafKernel<<<exactGrid, 128, 0, stream>>>(sc, w.frames, leaves, w.envHit, dCtr);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
-cudaError_t launchFetchStates(const FetchSceneDev &sc, const double *dStates, size_t n, double *dFrames,
-                              unsigned char *dSelfHit, unsigned *dEnvHit, uint8_t *dValid, FetchCounters *dCtr,
-                              cudaStream_t stream) {
+cudaError_t launchFetchStates(const FetchSceneDev &sc, const double *dStates, size_t n, const FetchScratch &w,
+                              uint8_t *dValid, FetchCounters *dCtr, int numSms, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(dEnvHit, 0, n * sizeof(unsigned), stream);
+    if (n >= (1ull << 36)) return cudaErrorInvalidValue;   // work descriptors keep 36 bits for the state index
+    cudaError_t e = runFetch(sc, dStates, nullptr, nullptr, nullptr, nullptr, nullptr, n, w, dCtr, numSms, stream);
     if (e != cudaSuccess) return e;
-    fetchSelfKernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(sc, dStates, nullptr, nullptr, nullptr, nullptr, nullptr, n,
-                                                                     dFrames, dSelfHit, dCtr);
-    fetchEnvKernel<<<(unsigned)((n * 12 + 127) / 128), 128, 0, stream>>>(sc, dFrames, dSelfHit, n, dEnvHit, dCtr);
-    fetchCombineKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dSelfHit, dEnvHit, n, dValid);
+    fetchCombineKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w.selfHit, w.envHit, n, dValid);
     return cudaGetLastError();
 }
 
 cudaError_t launchFetchEdgeItems(const FetchSceneDev &sc, const double *dFrom, const double *dTo, const unsigned *dSteps,
-                                 const unsigned long long *dItems, size_t nItems, unsigned *dDead, double *dFrames,
-                                 unsigned char *dSelfHit, unsigned *dEnvHit, FetchCounters *dCtr, cudaStream_t stream) {
+                                 const unsigned long long *dItems, size_t nItems, unsigned *dDead, const FetchScratch &w,
+                                 FetchCounters *dCtr, int numSms, cudaStream_t stream) {
     if (nItems == 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(dEnvHit, 0, nItems * sizeof(unsigned), stream);
+    cudaError_t e = runFetch(sc, nullptr, dFrom, dTo, dSteps, dItems, dDead, nItems, w, dCtr, numSms, stream);
     if (e != cudaSuccess) return e;
-    fetchSelfKernel<<<(unsigned)((nItems + 127) / 128), 128, 0, stream>>>(sc, nullptr, dFrom, dTo, dSteps, dItems, dDead, nItems,
-                                                                          dFrames, dSelfHit, dCtr);
-    fetchEnvKernel<<<(unsigned)((nItems * 12 + 127) / 128), 128, 0, stream>>>(sc, dFrames, dSelfHit, nItems, dEnvHit, dCtr);
-    fetchEdgeReduceKernel<<<(unsigned)((nItems + 255) / 256), 256, 0, stream>>>(dSelfHit, dEnvHit, dItems, nItems, dDead, dCtr);
+    fetchEdgeReduceKernel<<<(unsigned)((nItems + 255) / 256), 256, 0, stream>>>(w.selfHit, w.envHit, dItems, nItems, dDead, dCtr);
     return cudaGetLastError();
 }
 

@@ -29,7 +29,7 @@ struct CallCtx {
     cudaStream_t stream = nullptr;      // kernels + verdict read-back
     cudaStream_t copyStream = nullptr;  // host->device input copies of pipelined batches
     std::vector<cudaEvent_t> events;    // one per pipeline stage
-    DevBuf in0, in1, steps, dead, out, ctr, work, aux0, aux1, aux2, aux3;
+    DevBuf in0, in1, steps, dead, out, ctr, work, aux0, aux1, aux2, aux3, aux4, aux5, aux6;
     DevCounters *hCtr = nullptr;  // pinned
     std::vector<uint32_t> hSteps;
     ~CallCtx();
