@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("MPLB_LIB") or os.path.join(HERE, "libmplb.so")
 SOURCES = ["capi.cu", "se3_kernels.cu", "nn_capi.cu", "nn_kernels.cu", "fetch_capi.cu", "fetch_kernels.cu", "bvh_build.cpp", "collada.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-O3,-Wall,-ffp-contract=off", "--shared", "-cudart", "shared"]
+              "-Xcompiler", "-fPIC,-O3,-Wall,-ffp-contract=off,-fopenmp", "--shared", "-cudart", "shared", "-lgomp"]
 
 
 def _nvcc():

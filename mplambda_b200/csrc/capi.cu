@@ -272,13 +272,24 @@ static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, siz
     CtxGuard g{sc, c};
     c->hSteps.resize(n);
     uint32_t maxSteps = 0;
-    for (size_t i = 0; i < n; ++i) {
-        uint64_t s = sc->edgeSteps(from + 7 * i, to + 7 * i);
-        if (!(s < (1ull << 31)))
-            return fail(MPLB_ERR_INVALID, "edge %zu needs %llu interpolation steps (limit 2^31); non-finite state?", i,
-                        (unsigned long long)s);
-        c->hSteps[i] = (uint32_t)s;
-        maxSteps = std::max(maxSteps, (uint32_t)s);
+    {
+        // se3...:139 on the host (same libm as the CPU path); large batches use the host's cores
+        long long bad = -1;
+        uint32_t *hs = c->hSteps.data();
+#pragma omp parallel for schedule(static) if (n >= 8192) reduction(max : maxSteps)
+        for (long long i = 0; i < (long long)n; ++i) {
+            const uint64_t s = sc->edgeSteps(from + 7 * i, to + 7 * i);
+            if (!(s < (1ull << 31))) {
+#pragma omp critical
+                bad = i;
+                hs[i] = 0;
+                continue;
+            }
+            hs[i] = (uint32_t)s;
+            maxSteps = std::max(maxSteps, (uint32_t)s);
+        }
+        if (bad >= 0)
+            return fail(MPLB_ERR_INVALID, "edge %lld needs >= 2^31 interpolation steps; non-finite state?", bad);
     }
     int rc;
     const size_t sb = n * 7 * sizeof(double);

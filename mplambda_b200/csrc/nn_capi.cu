@@ -4,6 +4,7 @@
 #include "nn_device.cuh"
 #include "scene_impl.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <mutex>
@@ -17,12 +18,15 @@ struct mplb_nn {
     std::mutex mu;                 // calls on one structure are serialised
     size_t count = 0, capacity = 0;
     double *dKeys = nullptr;
+    float *dKeys32 = nullptr;      // FP32 copy for the candidate pass
+    double keysAbsMax = 0;         // largest |translation coordinate| (SE3) / |coordinate| (L1) inserted
     std::vector<double> hKeys;     // host mirror: reported distances are recomputed with host libm
     cudaStream_t stream = nullptr;
-    DevBuf queries, partDist, partIdx, dist, idx;
+    DevBuf queries, partDist, partIdx, dist, idx, partVal, thr;
 
     ~mplb_nn() {
         if (dKeys) cudaFree(dKeys);
+        if (dKeys32) cudaFree(dKeys32);
         if (stream) cudaStreamDestroy(stream);
     }
     // nigh SE3Space / L1Space distance, operation order of oracle/mplb_oracle.c
@@ -64,6 +68,7 @@ static int nnSearch(mplb_nn *nn, const double *queries, bool deviceQueries, size
     int rc;
     if (slices > 1 && ((rc = nn->partDist.reserve(nq * slices * k * 8)) || (rc = nn->partIdx.reserve(nq * slices * k * 8))))
         return rc;
+    if ((rc = nn->partVal.reserve(nq * slices * k * 4)) || (rc = nn->thr.reserve(nq * 4))) return rc;
     const double *dQ = queries;
     double *dDist = dist;
     long long *dIdx = (long long *)idx;
@@ -76,8 +81,10 @@ static int nnSearch(mplb_nn *nn, const double *queries, bool deviceQueries, size
         dDist = (double *)nn->dist.ptr;
         dIdx = (long long *)nn->idx.ptr;
     }
-    MPLB_CUDA(launchNnSearch(nn->dKeys, nn->count, nn->dim, nn->metric, nn->so3w, nn->l2w, dQ, nq, k, slices,
-                             (double *)nn->partDist.ptr, (long long *)nn->partIdx.ptr, dDist, dIdx, st));
+    MPLB_CUDA(launchNnSearch(nn->dKeys, nn->dKeys32, (std::isfinite(nn->keysAbsMax) ? std::nextafterf((float)nn->keysAbsMax, INFINITY) : INFINITY), nn->count, nn->dim,
+                             nn->metric, nn->so3w, nn->l2w, dQ, nq, k, slices, (float *)nn->partVal.ptr,
+                             (float *)nn->thr.ptr, (double *)nn->partDist.ptr, (long long *)nn->partIdx.ptr, dDist, dIdx,
+                             nullptr, st));
     if (deviceQueries) return MPLB_OK;
     MPLB_CUDA(cudaMemcpyAsync(idx, dIdx, nq * k * 8, cudaMemcpyDeviceToHost, st));
     MPLB_CUDA(cudaStreamSynchronize(st));
@@ -144,9 +151,29 @@ int mplb_nn_insert(mplb_nn *nn, const double *keys, size_t n) {
         if (nn->count) MPLB_CUDA(cudaMemcpy(p, nn->dKeys, nn->count * nn->dim * 8, cudaMemcpyDeviceToDevice));
         if (nn->dKeys) cudaFree(nn->dKeys);
         nn->dKeys = p;
+        float *p32 = nullptr;
+        e = cudaMalloc((void **)&p32, cap * nn->dim * 4);
+        if (e != cudaSuccess) return fail(MPLB_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", cap * nn->dim * 4, cudaGetErrorString(e));
+        if (nn->count) MPLB_CUDA(cudaMemcpy(p32, nn->dKeys32, nn->count * nn->dim * 4, cudaMemcpyDeviceToDevice));
+        if (nn->dKeys32) cudaFree(nn->dKeys32);
+        nn->dKeys32 = p32;
         nn->capacity = cap;
     }
+    for (size_t i = 0; i < n; ++i)
+        for (int d = (nn->metric == 0 ? 4 : 0); d < nn->dim; ++d) {
+            const double v = std::fabs(keys[i * nn->dim + d]);
+            if (!std::isfinite(v)) return fail(MPLB_ERR_INVALID, "non-finite key %zu", i);
+            if (std::isfinite(nn->keysAbsMax)) nn->keysAbsMax = std::max(nn->keysAbsMax, v);
+        }
+    if (nn->metric == 0)
+        for (size_t i = 0; i < n; ++i) {   // non-unit quaternion keys: the FP32 candidate bound does not hold -> all exact
+            const double *q = keys + i * 7;
+            const double qn = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+            if (!(std::fabs(qn - 1.0) < 1e-3)) nn->keysAbsMax = INFINITY;
+        }
     MPLB_CUDA(cudaMemcpy(nn->dKeys + nn->count * nn->dim, keys, n * nn->dim * 8, cudaMemcpyHostToDevice));
+    MPLB_CUDA(launchNnToFloat(nn->dKeys + nn->count * nn->dim, nn->dKeys32 + nn->count * nn->dim, n * nn->dim, nullptr));
+    MPLB_CUDA(cudaDeviceSynchronize());
     nn->hKeys.insert(nn->hKeys.end(), keys, keys + n * nn->dim);
     nn->count += n;
     return MPLB_OK;

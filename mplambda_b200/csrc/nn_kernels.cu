@@ -6,11 +6,16 @@
 // ([EXT] nigh), ties resolved to the lowest insertion index, k-NN sorted ascending.
 //
 // Brute force, tiled: a CTA owns 128 queries (one per thread, key in registers) and one slice of
-// the key set; key tiles are staged through shared memory with coalesced 128-bit loads and every
-// thread scans the tile (shared-memory broadcast reads).  Distances are evaluated in FP64 with the
-// oracle's operation order (no FMA contraction), so the L1 metric is bit-identical to the CPU
-// path and the SE3 metric differs at most in acos' last bit.  Slices give the grid enough CTAs
-// when there are few queries; a second kernel merges the per-slice candidate lists.
+// the key set; key tiles are staged through shared memory with coalesced loads and every thread
+// scans the tile (shared-memory broadcast reads).  Slices give the grid enough CTAs when there are
+// few queries; merge kernels combine the per-slice lists.
+//
+// Exactness at FP32 speed: pass 1 scans an FP32 copy of the keys and finds, per query, the k-th
+// smallest FP32 distance T.  With m bounding |d32 - d64| (acos amplifies the FP32 error of |q.q'|
+// by at most sqrt(2 delta) near 1; coordinates round at 2^-24 relative), every true k-nearest key
+// has d32 <= T + 2m, so pass 2 re-scans in FP32 and evaluates only those candidates in FP64 with
+// the oracle's operation order (no FMA contraction): the L1 metric is bit-identical to the CPU
+// path and the SE3 metric differs at most in acos' last bit; ties go to the lowest index.
 #include "nn_device.cuh"
 
 #include <cfloat>
@@ -39,58 +44,187 @@ __device__ __forceinline__ double nnDistance(const double *q, const double *key,
     return s;
 }
 
-// grid = (query blocks, slices).  out*: [nq][slices][k]
+__device__ __forceinline__ float sqrtApprox(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// acos on [0,1] as sqrt(1-x) * cubic (Abramowitz & Stegun 4.4.45, |error| <= 6.8e-5): cheap, and its error
+// is part of the candidate margin
+__device__ __forceinline__ float acosApprox(float x) {
+    const float p = fmaf(fmaf(fmaf(-0.0187293f, x, 0.0742610f), x, -0.2121144f), x, 1.5707288f);
+    return sqrtApprox(fmaxf(1.f - x, 0.f)) * p;
+}
+
+// FP32 estimate of the distance, only if it can be <= bound: most keys are rejected by their translation
+// alone (7 instructions) before any acos / sqrt.  -> true and d when d <= bound.
+__device__ __forceinline__ bool nnWithin32(const float *q, const float *key, int dim, int metric, float so3w, float l2w,
+                                           float bound, float &d) {
+    if (metric == 0) {
+        const float dx = key[4] - q[4], dy = key[5] - q[5], dz = key[6] - q[6];
+        const float t2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        if (l2w * l2w * t2 > bound * bound) return false;
+        const float x = fabsf(fmaf(key[3], q[3], fmaf(key[2], q[2], fmaf(key[1], q[1], key[0] * q[0]))));
+        const float so3 = x < 1.f ? acosApprox(x) : 0.f;
+        d = fmaf(so3w, so3, l2w * sqrtApprox(t2));
+        return d <= bound;
+    }
+    float sum = 0.f;
+    for (int i = 0; i < dim; ++i) sum += fabsf(key[i] - q[i]);
+    d = sum;
+    return d <= bound;
+}
+
+// bound of |d32 - d64| for one query (see the header comment); absMax = largest |coordinate| in play
+__device__ __forceinline__ float nnMargin(int dim, int metric, float so3w, float l2w, float absMax) {
+    if (metric == 0) return so3w * (2e-3f + 7e-5f) + l2w * 4e-6f * absMax + 1e-30f;
+    return (float)dim * 1e-6f * absMax + 1e-30f;
+}
+
+// Pass 1.  grid = (query blocks, slices).  outVal: [nq][slices][k] ascending FP32 distances (+inf padded)
 __global__ void __launch_bounds__(kNnThreads)
-nnScanKernel(const double *__restrict__ keys, unsigned long long n, int dim, int metric, double so3w, double l2w,
-             const double *__restrict__ queries, unsigned long long nq, int k, unsigned long long keysPerSlice,
-             double *__restrict__ outDist, long long *__restrict__ outIdx) {
-    __shared__ __align__(16) double tile[kNnTile * kNnMaxDim];
+nnBound32Kernel(const float *__restrict__ keys32, unsigned long long n, int dim, int metric, float so3w, float l2w,
+                const double *__restrict__ queries, unsigned long long nq, int k, unsigned long long keysPerSlice,
+                float *__restrict__ outVal) {
+    __shared__ __align__(16) float tile[kNnTile * kNnMaxDim];
     const unsigned long long qi = blockIdx.x * (unsigned long long)kNnThreads + threadIdx.x;
     const bool haveQuery = qi < nq;
-    double q[kNnMaxDim];
+    float q[kNnMaxDim];
 #pragma unroll
-    for (int i = 0; i < kNnMaxDim; ++i) q[i] = (haveQuery && i < dim) ? __ldg(queries + qi * dim + i) : 0.0;
-
-    double bestD[kNnMaxK];
-    long long bestI[kNnMaxK];
+    for (int i = 0; i < kNnMaxDim; ++i) q[i] = (haveQuery && i < dim) ? (float)__ldg(queries + qi * dim + i) : 0.f;
+    float best[kNnMaxK];
     int cnt = 0;
-    double d1 = INFINITY;   // k == 1 fast path
-    long long i1 = -1;
-
+    float b1 = INFINITY;
     const unsigned long long lo = blockIdx.y * keysPerSlice;
     const unsigned long long hi = min(n, lo + keysPerSlice);
     for (unsigned long long t0 = lo; t0 < hi; t0 += kNnTile) {
         const int tn = (int)min((unsigned long long)kNnTile, hi - t0);
         const int nd = tn * dim;
         __syncthreads();
-        {   // coalesced tile load (pairs of doubles when aligned)
-            const double *src = keys + t0 * dim;
-            for (int i = threadIdx.x; i < nd; i += kNnThreads) tile[i] = __ldg(src + i);
-        }
+        for (int i = threadIdx.x; i < nd; i += kNnThreads) tile[i] = __ldg(keys32 + t0 * dim + i);
         __syncthreads();
         if (!haveQuery) continue;
         if (k == 1) {
             for (int j = 0; j < tn; ++j) {
-                const double d = nnDistance(q, tile + j * dim, dim, metric, so3w, l2w);
+                float d;
+                if (nnWithin32(q, tile + j * dim, dim, metric, so3w, l2w, b1, d)) b1 = d;
+            }
+        } else {
+            for (int j = 0; j < tn; ++j) {
+                float d;
+                if (!nnWithin32(q, tile + j * dim, dim, metric, so3w, l2w, cnt == k ? best[k - 1] : INFINITY, d)) continue;
+                if (cnt == k && !(d < best[k - 1])) continue;
+                int pos = cnt < k ? cnt : k - 1;
+                while (pos > 0 && best[pos - 1] > d) {
+                    best[pos] = best[pos - 1];
+                    --pos;
+                }
+                best[pos] = d;
+                if (cnt < k) ++cnt;
+            }
+        }
+    }
+    if (!haveQuery) return;
+    float *ov = outVal + (qi * gridDim.y + blockIdx.y) * k;
+    if (k == 1) ov[0] = b1;
+    else
+        for (int r = 0; r < k; ++r) ov[r] = r < cnt ? best[r] : INFINITY;
+}
+
+// per query: k-th smallest FP32 distance over all slices, plus twice the error margin
+__global__ void nnThresholdKernel(const float *__restrict__ partVal, const double *__restrict__ queries,
+                                  unsigned long long nq, int slices, int k, int dim, int metric, float so3w, float l2w,
+                                  float keysAbsMax, float *__restrict__ thr) {
+    const unsigned long long qi = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    const float *v = partVal + qi * slices * k;
+    unsigned char head[256];
+    for (int s = 0; s < slices; ++s) head[s] = 0;
+    float kth = INFINITY;
+    for (int r = 0; r < k; ++r) {
+        int bs = -1;
+        float bd = INFINITY;
+        for (int s = 0; s < slices; ++s)
+            if (head[s] < k && v[s * k + head[s]] < bd) {
+                bd = v[s * k + head[s]];
+                bs = s;
+            }
+        if (bs < 0) {   // fewer than k keys: everything is a candidate
+            kth = INFINITY;
+            break;
+        }
+        ++head[bs];
+        kth = bd;
+    }
+    float absMax = keysAbsMax;
+    if (metric == 0) {   // the FP32 bound assumes unit quaternions; anything else is handled exactly
+        float qn = 0.f;
+        for (int i = 0; i < 4; ++i) qn += (float)queries[qi * dim + i] * (float)queries[qi * dim + i];
+        if (!(fabsf(qn - 1.f) < 1e-3f)) absMax = INFINITY;
+    }
+    for (int i = (metric == 0 ? 4 : 0); i < dim; ++i) absMax = fmaxf(absMax, fabsf((float)queries[qi * dim + i]) * 1.0000002f);
+    thr[qi] = kth + 2.f * nnMargin(dim, metric, so3w, l2w, absMax) + 8e-6f * fabsf(kth);
+}
+
+// Pass 2.  grid = (query blocks, slices).  FP32 re-scan; keys within the query's threshold are evaluated in
+// FP64.  out*: [nq][slices][k]
+__global__ void __launch_bounds__(kNnThreads)
+nnRefineKernel(const float *__restrict__ keys32, const double *__restrict__ keys, unsigned long long n, int dim, int metric,
+               double so3w, double l2w, const double *__restrict__ queries, const float *__restrict__ thr,
+               unsigned long long nq, int k, unsigned long long keysPerSlice, double *__restrict__ outDist,
+               long long *__restrict__ outIdx, unsigned long long *exactCount) {
+    __shared__ __align__(16) float tile[kNnTile * kNnMaxDim];
+    const unsigned long long qi = blockIdx.x * (unsigned long long)kNnThreads + threadIdx.x;
+    const bool haveQuery = qi < nq;
+    double q[kNnMaxDim];
+    float q32[kNnMaxDim];
+#pragma unroll
+    for (int i = 0; i < kNnMaxDim; ++i) {
+        q[i] = (haveQuery && i < dim) ? __ldg(queries + qi * dim + i) : 0.0;
+        q32[i] = (float)q[i];
+    }
+    const float limit = haveQuery ? thr[qi] : -1.f;
+    const float so3w32 = (float)so3w, l2w32 = (float)l2w;
+    double bestD[kNnMaxK];
+    long long bestI[kNnMaxK];
+    int cnt = 0;
+    double d1 = INFINITY;
+    long long i1 = -1;
+    unsigned exact = 0;
+    const unsigned long long lo = blockIdx.y * keysPerSlice;
+    const unsigned long long hi = min(n, lo + keysPerSlice);
+    for (unsigned long long t0 = lo; t0 < hi; t0 += kNnTile) {
+        const int tn = (int)min((unsigned long long)kNnTile, hi - t0);
+        const int nd = tn * dim;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nd; i += kNnThreads) tile[i] = __ldg(keys32 + t0 * dim + i);
+        __syncthreads();
+        if (!haveQuery) continue;
+        for (int j = 0; j < tn; ++j) {
+            float d32;
+            if (!nnWithin32(q32, tile + j * dim, dim, metric, so3w32, l2w32, limit, d32)) continue;
+            double key[kNnMaxDim];
+            const double *kp = keys + (t0 + j) * dim;
+            for (int i = 0; i < dim; ++i) key[i] = __ldg(kp + i);
+            const double d = nnDistance(q, key, dim, metric, so3w, l2w);
+            ++exact;
+            if (k == 1) {
                 if (d < d1) {
                     d1 = d;
                     i1 = (long long)(t0 + j);
                 }
+                continue;
             }
-        } else {
-            for (int j = 0; j < tn; ++j) {
-                const double d = nnDistance(q, tile + j * dim, dim, metric, so3w, l2w);
-                if (cnt == k && !(d < bestD[k - 1])) continue;
-                int pos = cnt < k ? cnt : k - 1;
-                while (pos > 0 && bestD[pos - 1] > d) {   // equal distances keep their (index) order
-                    bestD[pos] = bestD[pos - 1];
-                    bestI[pos] = bestI[pos - 1];
-                    --pos;
-                }
-                bestD[pos] = d;
-                bestI[pos] = (long long)(t0 + j);
-                if (cnt < k) ++cnt;
+            if (cnt == k && !(d < bestD[k - 1])) continue;
+            int pos = cnt < k ? cnt : k - 1;
+            while (pos > 0 && bestD[pos - 1] > d) {   // equal distances keep their (index) order
+                bestD[pos] = bestD[pos - 1];
+                bestI[pos] = bestI[pos - 1];
+                --pos;
             }
+            bestD[pos] = d;
+            bestI[pos] = (long long)(t0 + j);
+            if (cnt < k) ++cnt;
         }
     }
     if (!haveQuery) return;
@@ -105,6 +239,12 @@ nnScanKernel(const double *__restrict__ keys, unsigned long long n, int dim, int
             oi[r] = r < cnt ? bestI[r] : -1;
         }
     }
+    if (exactCount && exact) atomicAdd(exactCount, (unsigned long long)exact);
+}
+
+__global__ void nnToFloatKernel(const double *__restrict__ src, float *__restrict__ dst, unsigned long long n) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (float)src[i];
 }
 
 // one thread per query: merge `slices` ascending lists of length k into one (ties -> lower index)
@@ -148,19 +288,30 @@ int nnSlices(size_t nq, size_t n, int numSms) {
     return (int)std::min<size_t>(want, 256);
 }
 
-cudaError_t launchNnSearch(const double *dKeys, size_t n, int dim, int metric, double so3w, double l2w,
-                           const double *dQueries, size_t nq, int k, int slices, double *dPartDist,
-                           long long *dPartIdx, double *dDist, long long *dIdx, cudaStream_t stream) {
+cudaError_t launchNnToFloat(const double *dSrc, float *dDst, size_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    nnToFloatKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dSrc, dDst, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launchNnSearch(const double *dKeys, const float *dKeys32, float keysAbsMax, size_t n, int dim, int metric,
+                           double so3w, double l2w, const double *dQueries, size_t nq, int k, int slices,
+                           float *dPartVal, float *dThr, double *dPartDist, long long *dPartIdx, double *dDist,
+                           long long *dIdx, unsigned long long *dExactCount, cudaStream_t stream) {
     if (nq == 0) return cudaSuccess;
-    const size_t keysPerSlice = ((n + slices - 1) / slices + kNnTile - 1) / kNnTile * kNnTile;
+    const size_t keysPerSlice = std::max<size_t>(((n + slices - 1) / slices + kNnTile - 1) / kNnTile * kNnTile, kNnTile);
     dim3 grid((unsigned)((nq + kNnThreads - 1) / kNnThreads), (unsigned)slices);
+    nnBound32Kernel<<<grid, kNnThreads, 0, stream>>>(dKeys32, n, dim, metric, (float)so3w, (float)l2w, dQueries, nq, k,
+                                                     keysPerSlice, dPartVal);
+    nnThresholdKernel<<<(unsigned)((nq + 127) / 128), 128, 0, stream>>>(dPartVal, dQueries, nq, slices, k, dim, metric,
+                                                                        (float)so3w, (float)l2w, keysAbsMax, dThr);
     if (slices == 1) {
-        nnScanKernel<<<grid, kNnThreads, 0, stream>>>(dKeys, n, dim, metric, so3w, l2w, dQueries, nq, k,
-                                                      std::max<size_t>(keysPerSlice, kNnTile), dDist, dIdx);
+        nnRefineKernel<<<grid, kNnThreads, 0, stream>>>(dKeys32, dKeys, n, dim, metric, so3w, l2w, dQueries, dThr, nq, k,
+                                                        keysPerSlice, dDist, dIdx, dExactCount);
         return cudaGetLastError();
     }
-    nnScanKernel<<<grid, kNnThreads, 0, stream>>>(dKeys, n, dim, metric, so3w, l2w, dQueries, nq, k, keysPerSlice,
-                                                  dPartDist, dPartIdx);
+    nnRefineKernel<<<grid, kNnThreads, 0, stream>>>(dKeys32, dKeys, n, dim, metric, so3w, l2w, dQueries, dThr, nq, k,
+                                                    keysPerSlice, dPartDist, dPartIdx, dExactCount);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     nnMergeKernel<<<(unsigned)((nq + 127) / 128), 128, 0, stream>>>(dPartDist, dPartIdx, nq, slices, k, dDist, dIdx);

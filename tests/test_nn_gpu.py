@@ -83,3 +83,30 @@ def test_bad_arguments():
         nn.knearest(se3_poses(2, LO, HI, 2), 65)
     with pytest.raises(ValueError):
         nn.insert(np.zeros((3, 5)))
+
+
+def test_non_unit_quaternions_fall_back_to_exact(oracle):
+    keys = se3_poses(3000, LO, HI, 61)
+    keys[::3, :4] *= 1.7                      # scaled quaternions: |q.q'| may exceed 1, the FP32 bound is off
+    qs = se3_poses(300, LO, HI, 62)
+    qs[::2, :4] *= 0.6
+    nn = M.Nigh(M.nn.SE3)
+    nn.insert(keys)
+    idx, dist = nn.nearest(qs)
+    widx, wdist = oracle.nn_nearest(keys, qs)
+    assert (idx == widx).all() and (dist == wdist).all()
+
+
+def test_clustered_keys_near_ties(oracle):
+    # many keys within the FP32 margin of each other: the candidate pass must keep them all
+    rng = np.random.default_rng(7)
+    base = se3_poses(64, LO, HI, 63)
+    keys = np.repeat(base, 50, axis=0)
+    keys[:, 4:] += rng.normal(scale=1e-5, size=(len(keys), 3))
+    qs = base + 0.0
+    qs[:, 4:] += rng.normal(scale=1e-5, size=(len(qs), 3))
+    nn = M.Nigh(M.nn.SE3)
+    nn.insert(keys)
+    idx, dist = nn.knearest(qs, 20)
+    widx, wdist = oracle.nn_knearest(keys, qs, 20)
+    assert (idx == widx).all() and (dist == wdist).all()
