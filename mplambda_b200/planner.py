@@ -109,3 +109,32 @@ class BatchedRRT:
             out.append(self.nodes[i].copy())
             i = int(self.parent[i])
         return np.asarray(out[::-1])
+
+
+def path_cost(scenario, path):
+    sp = scenario.space()
+    return float(sum(sp.distance(a, b) for a, b in zip(path[:-1], path[1:])))
+
+
+def solve_sharded(make_planner, exchange, time_limit=60.0, sync_every=4):
+    """Independent planner instances, one per rank (the reference's lambdas: src/mpl_coordinator.cpp:591-600),
+    exchanging their outcome with collectives instead of the coordinator's TCP relays: every `sync_every`
+    iterations an all-reduce tells whether any shard has a solution (the Done broadcast,
+    mpl_coordinator.cpp:538-551); then the cheapest path wins and is broadcast to all shards
+    (gotPath, mpl_coordinator.cpp:573-589).  -> (cost, winning rank, path), identical on every rank.
+    make_planner(rank) must return a BatchedRRT (seeded per rank); exchange is a sharding.SolutionExchange."""
+    rrt = make_planner(exchange.rank)
+    t0 = time.perf_counter()
+    while True:
+        for _ in range(sync_every):
+            if rrt.solution < 0:
+                rrt.step()
+                rrt.stats["iterations"] += 1
+        timed_out = time.perf_counter() - t0 > time_limit
+        if exchange.any_done(rrt.solution >= 0 or timed_out):
+            break
+    rrt.stats["seconds"] = time.perf_counter() - t0
+    rrt.stats["nodes"] = rrt.n
+    path = rrt.path()
+    cost = path_cost(rrt.scenario, path) if path is not None else float("inf")
+    return exchange.publish(cost, path) + (rrt,)

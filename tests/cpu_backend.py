@@ -41,3 +41,18 @@ class CpuNN:
 
     def nearest(self, q):
         return O.nn_nearest(self.keys, q, threads=self.threads)
+
+
+class _Space:
+    def __init__(self, orc):
+        self.orc = orc
+
+    def distance(self, a, b):
+        return self.orc.distance(a, b)
+
+
+def _space(self):
+    return _Space(self.orc)
+
+
+CpuScenario.space = _space

@@ -85,3 +85,39 @@ def test_two_rank_exchange_over_gloo():
     res = dict(q.get(timeout=120) for _ in range(2))
     [p.join(timeout=60) for p in procs]
     assert res == {0: "ok", 1: "ok"}, res
+
+
+def _planner_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from cpu_backend import CpuNN, CpuScenario
+        from mplambda_b200.planner import BatchedRRT, solve_sharded
+        from mplambda_b200.workload import SE3_SCENES
+        d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scenes", "cubicles.npz"))
+        sc = SE3_SCENES["cubicles"]
+        scen = CpuScenario(d["env"], d["robot"], sc, threads=2)
+        ex = sharding.SolutionExchange(state_dim=7, max_waypoints=64)
+        cost, who, path, rrt = solve_sharded(lambda r: BatchedRRT(scen, CpuNN(2), sc["start"], batch=256, seed=100 + r),
+                                             ex, time_limit=120, sync_every=2)
+        ok = path is not None and scen.check_edges(path[:-1], path[1:]).all() and scen.isGoal(path[-1])
+        q.put((rank, (round(cost, 9), who, path.tobytes() if path is not None else None, bool(ok))))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_planners_agree_on_the_winner():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_planner_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=300) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    assert isinstance(res[0], tuple) and isinstance(res[1], tuple), res
+    assert res[0] == res[1]                  # same cost, same winner, same waypoints on both shards
+    assert res[0][3] is True and res[0][1] in (0, 1)
