@@ -125,6 +125,21 @@ public:
         if (rc != MPLB_OK) raise(rc);
         space_.scene_ = scene_;
     }
+    // the same scene from explicit triangle soups (float64 [n][3][3], robot already centred): what
+    // load(envMesh,false,false) / load(robotMesh,true,false) would have produced (se3...:58-59)
+    template <class Min, class Max>
+    SE3RigidBodyScenario(const double *envTris, std::size_t nEnv, const double *robotTris, std::size_t nRobot,
+                         const State &goal, const Min &min, const Max &max, S checkResolution, int device = 0)
+        : goal_(goal), invStepSize_(1 / checkResolution) {
+        for (int i = 0; i < 3; ++i) {
+            min_[i] = min[i];
+            max_[i] = max[i];
+        }
+        int rc = mplb_scene_create_se3(envTris, nEnv, robotTris, nRobot, double(so3weight), double(l2weight),
+                                       double(checkResolution), device, &scene_);
+        if (rc != MPLB_OK) raise(rc);
+        space_.scene_ = scene_;
+    }
     SE3RigidBodyScenario(const SE3RigidBodyScenario &) = delete;
     SE3RigidBodyScenario &operator=(const SE3RigidBodyScenario &) = delete;
     SE3RigidBodyScenario(SE3RigidBodyScenario &&o) noexcept
