@@ -353,7 +353,7 @@ def main():
                     "d2h_bytes_per_step": N_POSES, "ms_per_step": e2e_ms / args.steps,
                     "api": "mplb_check_states (pinned host buffers)",
                     "h2d_copy_alone_ms": h2d_ms, "h2d_gbs": N_POSES * 56 / (h2d_ms * 1e-3) / 1e9,
-                    "note": "the 56 B/pose input copy is the longer leg; the call pipelines it against the kernel"},
+                    "note": "the 56 B/pose input copy is the longer leg; the kernel runs underneath it and picks states up as they land"},
             "gpu_launches": int(st["launches"]),
             "clocks": clocks,
             "valid_fraction": valid_frac,

@@ -50,6 +50,7 @@ DevBuf::~DevBuf() {
 
 CallCtx::~CallCtx() {
     if (hCtr) cudaFreeHost(hCtr);
+    if (hWater) cudaFreeHost(hWater);
     for (auto e : events) cudaEventDestroy(e);
     if (copyStream) cudaStreamDestroy(copyStream);
     if (stream) cudaStreamDestroy(stream);
@@ -68,6 +69,7 @@ CallCtx *SceneBase::acquire() {
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMallocHost((void **)&c->hCtr, sizeof(DevCounters)) != cudaSuccess ||
+        cudaMallocHost((void **)&c->hWater, 64 * sizeof(unsigned long long)) != cudaSuccess ||
         c->ctr.reserve(sizeof(DevCounters)) != MPLB_OK || c->work.reserve(64) != MPLB_OK) {
         delete c;
         return nullptr;
@@ -218,16 +220,17 @@ static int finishCall(SceneBase *sc, CallCtx *c, size_t checks, uint64_t *states
     return MPLB_OK;
 }
 
-// Large host batches are cut into stages so that the PCIe copy of stage k+1 overlaps the kernel
-// of stage k (input is 56 B/state, the kernel needs ~1 ns/state: the copy is the longer leg).
-static size_t pipelineStages(size_t n) {
+// Large host batches stream in under the running kernel: the device input buffer is pre-filled with an
+// all-ones pattern, the kernel is launched right away and ONE host->device copy overwrites the buffer in
+// the background; the kernel hands out states in index order and each lane picks its state up when it has
+// landed.  The input is 56 B/state and the kernel needs ~1 ns/state, so the call costs about one
+// host->device copy of the batch.
+static bool streamBatch(size_t n) {
     static const long forced = [] {
-        const char *e = std::getenv("MPLB_PIPELINE_STAGES");
+        const char *e = std::getenv("MPLB_STREAM_MIN");
         return e ? std::atol(e) : 0L;
     }();
-    if (forced > 0) return std::min<size_t>((size_t)forced, std::max<size_t>(1, n));
-    const size_t minStage = 1u << 18;  // smaller launches lose more to their tails than the overlap wins
-    return std::max<size_t>(1, std::min<size_t>(8, n / minStage));
+    return n >= (size_t)(forced > 0 ? forced : 65536);
 }
 
 static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t *valid) {
@@ -236,32 +239,37 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
     if (!c) return fail(MPLB_ERR_CUDA, "could not create a call context (stream / pinned memory)");
     CtxGuard g{sc, c};
     int rc;
-    if ((rc = c->in0.reserve(n * 7 * sizeof(double))) || (rc = c->out.reserve(n))) return rc;
-    const size_t stages = pipelineStages(n);
-    while (c->events.size() < stages) {
-        cudaEvent_t e;
-        MPLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        c->events.push_back(e);
-    }
-    MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(DevCounters), c->stream));
-    const size_t per = (n + stages - 1) / stages;
+    const size_t bytes = n * 7 * sizeof(double);
+    if ((rc = c->in0.reserve(bytes)) || (rc = c->out.reserve(n))) return rc;
     double *dIn = (double *)c->in0.ptr;
     uint8_t *dOut = (uint8_t *)c->out.ptr;
-    for (size_t k = 0; k < stages; ++k) {
-        const size_t lo = k * per, cnt = std::min(per, n - std::min(n, lo));
-        if (cnt == 0) break;
-        cudaStream_t cs = stages > 1 ? c->copyStream : c->stream;
-        MPLB_CUDA(cudaMemcpyAsync(dIn + 7 * lo, states + 7 * lo, cnt * 7 * sizeof(double), cudaMemcpyHostToDevice, cs));
-        if (stages > 1) {
-            MPLB_CUDA(cudaEventRecord(c->events[k], cs));
-            MPLB_CUDA(cudaStreamWaitEvent(c->stream, c->events[k], 0));
+    const bool streamed = streamBatch(n);
+    MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(DevCounters), c->stream));
+    if (!streamed) {
+        MPLB_CUDA(cudaMemcpyAsync(dIn, states, bytes, cudaMemcpyHostToDevice, c->stream));
+        MPLB_CUDA(launchCheckStates(sc->dev, dIn, n, dOut, (DevCounters *)c->ctr.ptr, (unsigned *)c->work.ptr, sc->numSms,
+                                    c->stream));
+    } else {
+        if (c->events.empty()) {
+            cudaEvent_t e;
+            MPLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->events.push_back(e);
         }
-        MPLB_CUDA(launchCheckStates(sc->dev, dIn + 7 * lo, cnt, dOut + lo, (DevCounters *)c->ctr.ptr,
-                                    (unsigned *)c->work.ptr, sc->numSms, c->stream));
-        sc->hLaunches += 1;
-        MPLB_CUDA(cudaMemcpyAsync(valid + lo, dOut + lo, cnt, cudaMemcpyDeviceToHost, c->stream));
+        MPLB_CUDA(cudaMemsetAsync(dIn, 0xFF, bytes, c->copyStream));
+        MPLB_CUDA(cudaEventRecord(c->events[0], c->copyStream));
+        MPLB_CUDA(cudaStreamWaitEvent(c->stream, c->events[0], 0));
+        MPLB_CUDA(launchCheckStates(sc->dev, dIn, n, dOut, (DevCounters *)c->ctr.ptr, (unsigned *)c->work.ptr, sc->numSms,
+                                    c->stream, true));
+        MPLB_CUDA(cudaMemcpyAsync(dIn, states, bytes, cudaMemcpyHostToDevice, c->copyStream));
     }
-    return finishCall(sc, c, n, nullptr);
+    sc->hLaunches += 1;
+    MPLB_CUDA(cudaMemcpyAsync(valid, dOut, n, cudaMemcpyDeviceToHost, c->stream));
+    int frc = finishCall(sc, c, n, nullptr);
+    if (streamed) cudaStreamSynchronize(c->copyStream);
+    if (frc != MPLB_OK && streamed)
+        return fail(MPLB_ERR_CUDA, "%s (a streamed batch stalls when a state holds the reserved all-ones NaN pattern)",
+                    mplb_last_error());
+    return frc;
 }
 
 static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, size_t n, uint8_t *valid,

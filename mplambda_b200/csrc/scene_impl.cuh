@@ -31,6 +31,7 @@ struct CallCtx {
     std::vector<cudaEvent_t> events;    // one per pipeline stage
     DevBuf in0, in1, steps, dead, out, ctr, work, aux0, aux1, aux2, aux3, aux4, aux5, aux6;
     DevCounters *hCtr = nullptr;  // pinned
+    unsigned long long *hWater = nullptr;  // pinned: per-slice arrival marks of a streamed batch
     std::vector<uint32_t> hSteps;
     ~CallCtx();
 };

@@ -31,8 +31,11 @@ struct DevCounters {
     unsigned overflow, pad;
 };
 
+// streamed: dStates was pre-filled with the all-ones pattern and is being overwritten by a host->device copy
+// on another stream; the kernel picks each state up when it has landed (se3_kernels.cu: StateSource)
 cudaError_t launchCheckStates(const SceneDev &sc, const double *dStates, size_t n, uint8_t *dValid,
-                              DevCounters *dCtr, unsigned *dWork, int numSms, cudaStream_t stream);
+                              DevCounters *dCtr, unsigned *dWork, int numSms, cudaStream_t stream,
+                              bool streamed = false);
 
 // scratch for the per-warp interval LIFOs of checkEdgesKernel
 size_t edgeStackBytes(int numSms);

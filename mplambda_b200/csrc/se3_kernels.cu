@@ -294,6 +294,13 @@ struct StateSource {
     unsigned long long n;
     uint8_t *valid;
     unsigned long long *counter;
+    // Host batches stream in while the kernel runs (`streamed`): the input buffer is pre-filled with an
+    // all-ones pattern (a NaN no sampler produces) and ONE host->device copy overwrites it in the
+    // background; a lane picks its state up the moment none of its 7 doubles shows the pattern any more
+    // (aligned 8-byte words are never torn by the copy engine).  The wait is bounded: a copy that never
+    // arrives -- or a state that really holds the reserved pattern -- is reported, not spun on.
+    bool streamed = false;
+    unsigned stalled = 0;
     unsigned long long base = 0;
     bool exhausted = false;
 
@@ -308,11 +315,25 @@ struct StateSource {
             return 0;
         }
         base = b;
+        int got = want;
         if (n - b <= (unsigned long long)want) {
             exhausted = true;
-            return (int)(n - b);
+            got = (int)(n - b);
         }
-        return want;
+        if (streamed) {
+            // one lane watches the last word of the warp's batch (the copy engine fills the buffer front to
+            // back), backing off so that thousands of waiting warps do not crowd the L2 the copy writes into
+            if (lane == 0) {
+                const double *gate = states + 7 * (b + got) - 1;
+                unsigned ns = 500;
+                for (unsigned spins = 0; __double_as_longlong(__ldcv(gate)) == -1ll && spins < (1u << 18); ++spins) {
+                    __nanosleep(ns);
+                    ns = min(ns * 2, 8000u);
+                }
+            }
+            __syncwarp();
+        }
+        return got;
     }
     // -> false when the item turned out to need no work
     template <typename SM>
@@ -322,13 +343,35 @@ struct StateSource {
         t[1] = (unsigned)(i >> 32);
         t[2] = t[3] = 0;
         extraSlack = 0.f;
-        stateOf(t[0], t[1], s);
-        return true;
+        if (!streamed) {
+            stateOf(t[0], t[1], s);
+            return true;
+        }
+        const double *src = states + 7 * i;
+        for (unsigned spins = 0;; ++spins) {
+            bool here = true;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                s[k] = __ldcv(src + k);
+                here &= __double_as_longlong(s[k]) != -1ll;
+            }
+            if (here) return true;
+            if (spins >= (1u << 20)) {   // ~2 s
+                const_cast<StateSource *>(this)->stalled = 1;
+                return false;
+            }
+            __nanosleep(2000);
+        }
     }
     __device__ void stateOf(unsigned t0, unsigned t1, double s[7]) const {
         const double *src = states + 7 * (((unsigned long long)t1 << 32) | t0);
+        if (streamed) {   // freshly DMA-written memory: read through L2, not the non-coherent path
 #pragma unroll
-        for (int k = 0; k < 7; ++k) s[k] = __ldg(src + k);
+            for (int k = 0; k < 7; ++k) s[k] = __ldcg(src + k);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 7; ++k) s[k] = __ldg(src + k);
+        }
     }
     // warp-collective: slots `lane` (r0) and `lane + 32` (r1) retire
     template <typename SM>
@@ -952,13 +995,14 @@ __device__ __forceinline__ void flushCounters(const WarpCounters &c, DevCounters
 
 template <typename E>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MPLB_MIN_CTAS)
-checkStatesKernel(SceneDev sc, const double *__restrict__ states, unsigned long long n, uint8_t *__restrict__ valid,
-                  DevCounters *ctr, unsigned long long *workCounter) {
+checkStatesKernel(SceneDev sc, const double *states, unsigned long long n, uint8_t *__restrict__ valid,
+                  DevCounters *ctr, unsigned long long *workCounter, int streamed) {
     WarpSmem<E> sm = warpSmem<E>(sc.stackLevels);
     StateSource src;
-    src.states = states; src.n = n; src.valid = valid; src.counter = workCounter;
+    src.states = states; src.n = n; src.valid = valid; src.counter = workCounter; src.streamed = streamed != 0;
     WarpCounters cnt;
     runWarp<E>(sm, sc, src, cnt);
+    if (__any_sync(kFull, src.stalled != 0)) cnt.error = 1;
     flushCounters(cnt, ctr, false);
 }
 
@@ -998,7 +1042,7 @@ int gridFor(K kernel, size_t smem, int numSms) {
 
 template <typename E>
 cudaError_t launchStatesT(const SceneDev &sc, const double *dStates, size_t n, uint8_t *dValid, DevCounters *dCtr,
-                          unsigned long long *dWork, int numSms, cudaStream_t stream) {
+                          unsigned long long *dWork, bool streamed, int numSms, cudaStream_t stream) {
     auto k = checkStatesKernel<E>;
     const size_t smem = smemBytes<E>(sc);
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1007,7 +1051,7 @@ cudaError_t launchStatesT(const SceneDev &sc, const double *dStates, size_t n, u
     // a warp wants at least ~2 refills of 32 states to be worth launching
     const unsigned long long warpsWanted = (n + 63) / 64;
     grid = (int)std::min<unsigned long long>(grid, (warpsWanted + kWarpsPerCta - 1) / kWarpsPerCta);
-    k<<<std::max(grid, 1), kWarpsPerCta * 32, smem, stream>>>(sc, dStates, n, dValid, dCtr, dWork);
+    k<<<std::max(grid, 1), kWarpsPerCta * 32, smem, stream>>>(sc, dStates, n, dValid, dCtr, dWork, streamed ? 1 : 0);
     return cudaGetLastError();
 }
 
@@ -1036,12 +1080,12 @@ cudaError_t launchEdgesT(const SceneDev &sc, const double *dFrom, const double *
 }  // namespace
 
 cudaError_t launchCheckStates(const SceneDev &sc, const double *dStates, size_t n, uint8_t *dValid,
-                              DevCounters *dCtr, unsigned *dWork, int numSms, cudaStream_t stream) {
+                              DevCounters *dCtr, unsigned *dWork, int numSms, cudaStream_t stream, bool streamed) {
     if (n == 0) return cudaSuccess;
     cudaError_t err = cudaMemsetAsync(dWork, 0, sizeof(unsigned long long), stream);
     if (err != cudaSuccess) return err;
-    return sc.wide ? launchStatesT<unsigned long long>(sc, dStates, n, dValid, dCtr, (unsigned long long *)dWork, numSms, stream)
-                   : launchStatesT<unsigned>(sc, dStates, n, dValid, dCtr, (unsigned long long *)dWork, numSms, stream);
+    return sc.wide ? launchStatesT<unsigned long long>(sc, dStates, n, dValid, dCtr, (unsigned long long *)dWork, streamed, numSms, stream)
+                   : launchStatesT<unsigned>(sc, dStates, n, dValid, dCtr, (unsigned long long *)dWork, streamed, numSms, stream);
 }
 
 size_t edgeStackBytes(int numSms) {
