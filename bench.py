@@ -341,7 +341,7 @@ def main():
         line = {
             "metric": "collision checks/sec (pose batch)", "value": value, "unit": "checks/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 filter + f64 exact",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
             "data": "synthetic",
             "config": {"workload": "%s SE(3) rigid body, 2^20 uniformly sampled poses per GPU per step "
                                    "(randomize.hpp distribution, Philox seed 0x6d706c62)" % args.workload,

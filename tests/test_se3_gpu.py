@@ -145,3 +145,52 @@ def test_device_resident_batch(scenes, golden):
     s.check_states_device(d.data_ptr(), len(P), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert (out.cpu().numpy().astype(bool) == want).all()
+
+
+def test_full_size_batch_properties(scenes, oracle):
+    """BASELINE.json configs[1] at full size (2^20 Alpha 1.5 poses): size-independent properties plus the
+    oracle on a random subset."""
+    env, robot = scenes["alpha15"]
+    sc = SE3_SCENES["alpha15"]
+    s = make(scenes, "alpha15")
+    n = 1 << 20
+    P = se3_poses(n, sc["min"], sc["max"], SEED)
+    full = s.check_states(P)
+    assert 0.7 < full.mean() < 0.95
+    # a verdict depends on its own pose only: chunked calls, a permutation and a repeat give the same answers
+    parts = np.concatenate([s.check_states(P[lo:lo + 200001]) for lo in range(0, n, 200001)])
+    assert (parts == full).all()
+    perm = np.random.default_rng(0).permutation(n)
+    assert (s.check_states(P[perm]) == full[perm]).all()
+    assert (s.check_states(P) == full).all()
+    # q and -q are the same rotation (toRotationMatrix is even in q)
+    flipped = P[:100000].copy()
+    flipped[:, :4] *= -1
+    assert (s.check_states(flipped) == full[:100000]).all()
+    # oracle on a random subset
+    pick = np.random.default_rng(1).choice(n, 60000, replace=False)
+    want = oracle.SE3Oracle(env, robot).check_states(P[pick], oracle.BVH)
+    assert (full[pick] == want).all()
+
+
+def test_edge_batch_properties(scenes, oracle):
+    """Edge semantics at batch scale: a valid edge implies its `to` state and its samples are valid; an edge
+    whose `to` state collides is invalid; reversing a short valid edge keeps it valid."""
+    env, robot = scenes["cubicles"]
+    sc = SE3_SCENES["cubicles"]
+    s = make(scenes, "cubicles")
+    P = se3_poses(1 << 17, sc["min"], sc["max"], SEED + 40)
+    v = s.check_states(P)
+    A = P[v][:20000]
+    B = P[::-1][:len(A)].copy()
+    vb = s.check_states(B)
+    ok = s.check_edges(A, B)
+    assert not ok[~vb].any()                       # isValid(to) is part of the edge check (se3...:136)
+    orc = oracle.SE3Oracle(env, robot, check_resolution=0.1)
+    good = np.nonzero(ok)[0][:6]
+    for i in good:
+        st = int(s.edge_steps(A[i], B[i])[0])
+        states = np.array([orc.interpolate(A[i], B[i], k / st) for k in range(1, st)] + [B[i]])
+        assert s.check_states(states).all()
+    sub = np.nonzero(ok)[0][:2000]
+    assert (s.check_edges(B[sub], A[sub]) == orc.check_edges(B[sub], A[sub], oracle.BVH)).all()
