@@ -194,3 +194,35 @@ def test_edge_batch_properties(scenes, oracle):
         assert s.check_states(states).all()
     sub = np.nonzero(ok)[0][:2000]
     assert (s.check_edges(B[sub], A[sub]) == orc.check_edges(B[sub], A[sub], oracle.BVH)).all()
+
+
+def test_degenerate_configurations_match_brute_force(oracle):
+    """Touching, coplanar, parallel-edge and zero-area cases: the FP32 filter cannot decide these, the FP64
+    path has to reproduce the oracle's (FCL's) non-strict separating-axis semantics bit for bit."""
+    rng = np.random.default_rng(11)
+    unit = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0.0]])
+    env = np.array([unit,
+                    unit + [0, 0, 1.0],                                   # parallel plane
+                    [[2, 0, 0], [3, 0, 0], [2, 1, 0]],                    # coplanar neighbour
+                    [[0, 0, -1], [0, 0, 1], [0, 2, 0.0]],                 # crossing
+                    [[5, 5, 5], [5, 5, 5], [6, 5, 5.0]],                  # zero-area (like Apartment's 364)
+                    [[-1, -1, 0.5], [4, -1, 0.5], [-1, 4, 0.5]]])         # large triangle above
+    robot = np.array([unit * 0.5, [[0, 0, 0], [0.5, 0, 0], [0, 0, 0.5]], [[0.2, 0.2, -0.3], [0.2, 0.2, 0.3], [0.4, 0.1, 0.0]]])
+    s = M.SE3RigidBodyScenario(env, robot, [0, 0, 0, 1, 0, 0, 0], [-3, -3, -3], [6, 6, 6], 0.1)
+    orc = oracle.SE3Oracle(env, robot)
+    ident = np.array([0, 0, 0, 1.0])
+    rots = [ident, [1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [np.sqrt(.5), 0, 0, np.sqrt(.5)], [0, np.sqrt(.5), 0, np.sqrt(.5)],
+            [0, 0, np.sqrt(.5), np.sqrt(.5)], [.5, .5, .5, .5]]
+    grid = [-1.0, -0.5, 0.0, 0.25, 0.5, 1.0, 1.5, 2.0, 2.5, 3.0]
+    states = [np.concatenate([np.asarray(q, float), [x, y, z]]) for q in rots for x in grid for y in grid[:6] for z in (-0.5, 0.0, 0.5, 1.0, 1.5)]
+    # plus tiny perturbations around exactly-touching placements
+    base = np.array(states)
+    jitter = base[rng.choice(len(base), 3000)].copy()
+    jitter[:, 4:] += rng.choice([0, 1e-15, -1e-15, 1e-9, -1e-9, 1e-6, -1e-6], size=(3000, 3))
+    S = np.concatenate([base, jitter])
+    got = s.check_states(S)
+    want = orc.check_states(S, oracle.BRUTE)
+    assert (got == want).all(), np.nonzero(got != want)[0][:10]
+    assert 0.05 < want.mean() < 0.95
+    st = s.stats()
+    assert st["exact_tests"] > 0          # the exact path really was exercised
