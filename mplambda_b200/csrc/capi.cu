@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -70,7 +71,7 @@ CallCtx *SceneBase::acquire() {
         cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMallocHost((void **)&c->hCtr, sizeof(DevCounters)) != cudaSuccess ||
         cudaMallocHost((void **)&c->hWater, 64 * sizeof(unsigned long long)) != cudaSuccess ||
-        c->ctr.reserve(sizeof(DevCounters)) != MPLB_OK || c->work.reserve(64) != MPLB_OK) {
+        c->ctr.reserve(sizeof(DevCounters)) != MPLB_OK || c->work.reserve(128) != MPLB_OK) {
         delete c;
         return nullptr;
     }
@@ -164,7 +165,7 @@ static int createSe3(const double *envTris, size_t nEnv, const double *robotTris
         (rc = upload(sc->robotTris, robot.tris32)) || (rc = upload(sc->envTris, env.tris32)) ||
         (rc = upload(sc->robotTris64, robot.tris64)) || (rc = upload(sc->envTris64, env.tris64)))
         return rc;
-    if ((rc = sc->globalCtr.reserve(sizeof(DevCounters))) || (rc = sc->globalWork.reserve(64))) return rc;
+    if ((rc = sc->globalCtr.reserve(sizeof(DevCounters))) || (rc = sc->globalWork.reserve(128))) return rc;
     MPLB_CUDA(cudaMemset(sc->globalCtr.ptr, 0, sizeof(DevCounters)));
     SceneDev &d = sc->dev;
     d.robotNodes = (const float4 *)sc->robotNodes.ptr;
@@ -200,6 +201,8 @@ static int createSe3(const double *envTris, size_t nEnv, const double *robotTris
     }
     if (d.bitsA + d.bitsB > 31) return fail(MPLB_ERR_INVALID, "meshes too large for the 31-bit node pair encoding");
     d.triBatchMin = 32;
+    d.triEagerLanes = 16;
+    if (const char *e = std::getenv("MPLB_TRI_EAGER")) d.triEagerLanes = std::atoi(e);
     if (const char *e = std::getenv("MPLB_TRI_BATCH")) d.triBatchMin = std::max(1, std::min(32, std::atoi(e)));
     sc->envNodeCount = env.nodes.size();
     sc->robotNodeCount = robot.nodes.size();
@@ -211,6 +214,22 @@ static int finishCall(SceneBase *sc, CallCtx *c, size_t checks, uint64_t *states
     cudaError_t e = cudaMemcpyAsync(c->hCtr, c->ctr.ptr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) return fail(MPLB_ERR_CUDA, "device work failed: %s", cudaGetErrorString(e));
+#ifdef MPLB_WARP_TIMES
+    {
+        const DevCounters &k = *c->hCtr;
+        const double t0 = (double)~k.negStart;
+        std::fprintf(stderr, "[mplb warp times] first warp out of new work at %.1f us, first warp done %.1f us, last warp done %.1f us\n",
+                     ((double)~k.negFirstDry - t0) * 1e-3, ((double)~k.negFirstDone - t0) * 1e-3, ((double)k.lastDone - t0) * 1e-3);
+        std::vector<int> ord;
+        for (int w = 0; w < 4096; ++w)
+            if (k.warpDone[w]) ord.push_back(w);
+        std::sort(ord.begin(), ord.end(), [&](int a, int b) { return k.warpDone[a] > k.warpDone[b]; });
+        for (size_t i = 0; i < ord.size() && i < 6; ++i)
+            std::fprintf(stderr, "    warp %4d done %.1f us: states %u bv %u tri %u\n", ord[i], ((double)k.warpDone[ord[i]] - t0) * 1e-3,
+                         k.warpStates[ord[i]], k.warpBv[ord[i]], k.warpTri[ord[i]]);
+        if (!ord.empty()) std::fprintf(stderr, "    median warp done %.1f us (%zu warps)\n", ((double)k.warpDone[ord[ord.size() / 2]] - t0) * 1e-3, ord.size());
+    }
+#endif
     if (c->hCtr->overflow) return fail(MPLB_ERR_CUDA, "device traversal bookkeeping error (pair stack / slot accounting)");
     sc->hBv += c->hCtr->bvTests;
     sc->hTri += c->hCtr->triTests;
@@ -244,6 +263,12 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
     double *dIn = (double *)c->in0.ptr;
     uint8_t *dOut = (uint8_t *)c->out.ptr;
     const bool streamed = streamBatch(n);
+    // MPLB_TIMELINE=1: print where a streamed call's time goes (diagnostic)
+    static const bool timeline = std::getenv("MPLB_TIMELINE") != nullptr;
+    static thread_local cudaEvent_t tl[5] = {};
+    const auto h0 = std::chrono::steady_clock::now();
+    if (timeline && !tl[0])
+        for (auto &e : tl) cudaEventCreate(&e);
     MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(DevCounters), c->stream));
     if (!streamed) {
         MPLB_CUDA(cudaMemcpyAsync(dIn, states, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -255,17 +280,31 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
             MPLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             c->events.push_back(e);
         }
+        if (timeline) cudaEventRecord(tl[0], c->copyStream);
         MPLB_CUDA(cudaMemsetAsync(dIn, 0xFF, bytes, c->copyStream));
         MPLB_CUDA(cudaEventRecord(c->events[0], c->copyStream));
         MPLB_CUDA(cudaStreamWaitEvent(c->stream, c->events[0], 0));
+        if (timeline) cudaEventRecord(tl[1], c->stream);
         MPLB_CUDA(launchCheckStates(sc->dev, dIn, n, dOut, (DevCounters *)c->ctr.ptr, (unsigned *)c->work.ptr, sc->numSms,
                                     c->stream, true));
+        if (timeline) cudaEventRecord(tl[3], c->stream);
         MPLB_CUDA(cudaMemcpyAsync(dIn, states, bytes, cudaMemcpyHostToDevice, c->copyStream));
+        if (timeline) cudaEventRecord(tl[2], c->copyStream);
     }
     sc->hLaunches += 1;
     MPLB_CUDA(cudaMemcpyAsync(valid, dOut, n, cudaMemcpyDeviceToHost, c->stream));
+    if (timeline && streamed) cudaEventRecord(tl[4], c->stream);
     int frc = finishCall(sc, c, n, nullptr);
     if (streamed) cudaStreamSynchronize(c->copyStream);
+    if (timeline && streamed) {
+        float a, b, k, d;
+        cudaEventElapsedTime(&a, tl[0], tl[1]);
+        cudaEventElapsedTime(&b, tl[0], tl[2]);
+        cudaEventElapsedTime(&k, tl[0], tl[3]);
+        cudaEventElapsedTime(&d, tl[0], tl[4]);
+        std::fprintf(stderr, "[mplb timeline] n=%zu  pattern fill done %.3f ms, copy done %.3f, kernel done %.3f, verdicts back %.3f, host %.3f\n",
+                     n, a, b, k, d, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());
+    }
     if (frc != MPLB_OK && streamed)
         return fail(MPLB_ERR_CUDA, "%s (a streamed batch stalls when a state holds the reserved all-ones NaN pattern)",
                     mplb_last_error());
@@ -313,7 +352,7 @@ static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, siz
                                (const unsigned *)c->steps.ptr, n, (unsigned *)c->dead.ptr, (uint8_t *)c->out.ptr,
                                (DevCounters *)c->ctr.ptr, (unsigned long long *)c->work.ptr, c->aux0.ptr, stackBytes,
                                sc->numSms, c->stream));
-    sc->hLaunches += 2;
+    sc->hLaunches += 4;   // three passes + the verdict kernel
     MPLB_CUDA(cudaMemcpyAsync(valid, c->out.ptr, n, cudaMemcpyDeviceToHost, c->stream));
     return finishCall(sc, c, 0, statesChecked);
 }
@@ -458,7 +497,7 @@ int mplb_check_edges_device(mplb_scene *scene, const double *d_from, const doubl
     MPLB_CUDA(launchCheckEdges(s->dev, d_from, d_to, d_steps, n, (unsigned *)s->globalDead.ptr, d_valid,
                                (DevCounters *)s->globalCtr.ptr, (unsigned long long *)s->globalWork.ptr,
                                s->globalStacks.ptr, edgeStackBytes(s->numSms), s->numSms, (cudaStream_t)stream));
-    s->hLaunches += 2;
+    s->hLaunches += 4;
     return MPLB_OK;
 }
 

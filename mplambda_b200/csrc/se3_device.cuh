@@ -22,6 +22,7 @@ struct SceneDev {
     float envRadius;            // max |vertex| of the environment
     float robotRadius;          // max |vertex| of the (centred) robot
     int triBatchMin;            // leaf pairs queued before a triangle batch runs (<= 32)
+    int triEagerLanes;          // ... or any queued pair once at most this many lanes still search
     int stackLevels;            // per-lane LIFO levels = depthA + depthB + 2 (rounded up)
     unsigned rootEntry;         // LIFO entry that expands the root pair (se3_kernels.cu)
 };
@@ -29,6 +30,11 @@ struct SceneDev {
 struct DevCounters {
     unsigned long long bvTests, triTests, exactTests, states;
     unsigned overflow, pad;
+#ifdef MPLB_WARP_TIMES   // diagnostic build: when did the warps start / run out of new work / finish (globaltimer, ns)
+    unsigned long long negStart, negFirstDry, negFirstDone, lastDone;   // neg*: ~t, so that atomicMax finds the minimum
+    unsigned long long warpDone[4096];
+    unsigned warpStates[4096], warpBv[4096], warpTri[4096];
+#endif
 };
 
 // streamed: dStates was pre-filled with the all-ones pattern and is being overwritten by a host->device copy

@@ -43,6 +43,10 @@ constexpr int kWarpsPerCta = MPLB_WARPS_PER_CTA;
 constexpr int kSlots = 64;          // state slots per warp
 constexpr int kQueueCap = 96;       // leaf / exact queue entries per warp
 constexpr unsigned kPhaseBSub = 64;    // phase-B work items per edge (isValid(from,to), see EdgeSource)
+#ifndef MPLB_SPILL_KEEP
+#define MPLB_SPILL_KEEP 0
+#endif
+constexpr unsigned kSpillKeep = MPLB_SPILL_KEEP;    // interval pieces a warp keeps for itself once the item pool has drained
 constexpr int kStepsPerRound = 4;   // depth-first steps between two rounds of slot bookkeeping
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -303,36 +307,84 @@ struct StateSource {
     unsigned stalled = 0;
     unsigned long long base = 0;
     bool exhausted = false;
+    // Guided hand-out: a warp never takes more than its share of what is left (as of its previous
+    // acquire), so the last states of a batch -- and all of a small batch -- spread over every warp of the
+    // grid instead of queueing behind each other in a few (one warp tests ~32 box pairs per ~0.5 us, a
+    // heavy pose needs ~1000 of them).
+    unsigned long long crew = 1;   // guided divisor: warps in the grid x kGuidedShare
+    unsigned long long seen = 0;   // counter value at this warp's previous acquire
+#ifdef MPLB_WARP_TIMES
+    unsigned long long dryAt = ~0ull;
+#endif
 
-    __device__ bool done() const { return exhausted; }
+    // streamed batches: a claim [pendBase, pendBase + pendCount) that has not landed yet, and the adaptive
+    // claim size (halved when the warp had to wait for its data, doubled when the data was already there:
+    // a kernel that outruns the copy keeps its claims just ahead of the copy engine instead of queueing
+    // 64 states per warp behind it)
+    unsigned long long pendBase = 0;
+    int pendCount = 0, claim = 8;
+    unsigned waitSpins = 0, backoff = 1000;   // back-off in SM cycles
+    long long polledAt = 0;
+    bool waited = false;
+
+    __device__ bool done() const { return exhausted && pendCount == 0; }
+    __device__ bool waiting() const { return pendCount > 0; }
+    // mayBlock: the warp has nothing else to do (otherwise a claim that has not landed is simply retried later)
     template <typename SM>
-    __device__ int acquire(int want, unsigned lane, SM &) {
-        unsigned long long b = 0;
-        if (lane == 0) b = atomicAdd(counter, (unsigned long long)want);
-        b = __shfl_sync(kFull, b, 0);
-        if (b >= n) {
-            exhausted = true;
+    __device__ int acquire(int want, unsigned lane, SM &, bool mayBlock) {
+        if (pendCount == 0) {
+            if (exhausted) return 0;
+            const unsigned long long left = n - min(seen, n);
+            want = (int)min((unsigned long long)want, left / crew + 1);
+            if (streamed) want = min(want, claim);
+            unsigned long long b = 0;
+            if (lane == 0) b = atomicAdd(counter, (unsigned long long)want);
+            b = __shfl_sync(kFull, b, 0);
+            if (b >= n) {
+                exhausted = true;
+#ifdef MPLB_WARP_TIMES
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dryAt));
+#endif
+                return 0;
+            }
+            seen = b + want;
+            if (n - b <= (unsigned long long)want) {
+                exhausted = true;
+                want = (int)(n - b);
+            }
+            if (!streamed) {
+                base = b;
+                return want;
+            }
+            pendBase = b;
+            pendCount = want;
+            waited = false;
+        }
+        // one lane looks at the last word of the claim (the copy engine fills the buffer front to back), at
+        // most once per back-off period so that thousands of waiting warps do not crowd the L2 the copy
+        // writes into
+        if (waited && !mayBlock && clock64() - polledAt < (long long)backoff) return 0;
+        int here = 0;
+        if (lane == 0) here = __double_as_longlong(__ldcv(states + 7 * (pendBase + pendCount) - 1)) != -1ll;
+        here = __shfl_sync(kFull, here, 0);
+        if (!here) {
+            waited = true;
+            polledAt = clock64();
+            if (mayBlock) __nanosleep(backoff / 2);   // ~2 cycles per ns
+            backoff = min(backoff * 2, 16000u);
+            if (++waitSpins > (1u << 20)) {   // a copy that never arrives is reported, not spun on
+                stalled = 1;
+                pendCount = 0;
+                exhausted = true;
+            }
             return 0;
         }
-        base = b;
-        int got = want;
-        if (n - b <= (unsigned long long)want) {
-            exhausted = true;
-            got = (int)(n - b);
-        }
-        if (streamed) {
-            // one lane watches the last word of the warp's batch (the copy engine fills the buffer front to
-            // back), backing off so that thousands of waiting warps do not crowd the L2 the copy writes into
-            if (lane == 0) {
-                const double *gate = states + 7 * (b + got) - 1;
-                unsigned ns = 500;
-                for (unsigned spins = 0; __double_as_longlong(__ldcv(gate)) == -1ll && spins < (1u << 18); ++spins) {
-                    __nanosleep(ns);
-                    ns = min(ns * 2, 8000u);
-                }
-            }
-            __syncwarp();
-        }
+        waitSpins = 0;
+        backoff = 1000;
+        claim = waited ? max(claim / 2, 4) : min(claim * 2, 32);
+        base = pendBase;
+        const int got = pendCount;
+        pendCount = 0;
         return got;
     }
     // -> false when the item turned out to need no work
@@ -403,13 +455,24 @@ struct EdgeSource {
     const unsigned *steps;
     unsigned long long nEdges;
     unsigned grab;
+    unsigned long long crew = 1;   // warps in the grid x 2 (guided hand-out)
     unsigned *dead;
     unsigned long long *counter;
     uint4 *stack;          // this warp's interval LIFO (global memory): (edge, lo, hi, -)
     unsigned stackCap;
     float robotRadius;
     unsigned *errorFlag;
+    // Passes 2 and 3 of a call take explicit (edge, lo, hi) descriptors: what the warps of the previous
+    // pass spilled.  A warp that still holds pieces of a hard interval once the item pool has drained
+    // hands the surplus on instead of grinding through it alone while the rest of the grid has gone home
+    // (measured: one grazing 7905-step Cubicles edge kept two warps busy for 0.43 ms of a 0.48 ms launch).
+    const uint4 *descIn = nullptr;
+    unsigned long long nDesc = 0;
+    uint4 *spillOut = nullptr;
+    unsigned long long *spillCount = nullptr;
+    unsigned spillCap = 0;
     bool globalDone = false;
+    bool poolDry = false;   // the item counter has run past the last item (other warps may still hold work)
     unsigned stackCount = 0;
     // current grab of items and the live ones among them
     unsigned long long first = 0;
@@ -461,13 +524,41 @@ struct EdgeSource {
     // Up to `want` pieces of work as (edge, lo, hi) descriptors in sm.work[]: halves of intervals that could
     // not be certified first (depth first, keeps the LIFO short), topped up from as many items as it takes,
     // so that the FP64 state expansion runs on full warps.
+    __device__ bool waiting() const { return false; }
     template <typename SM>
-    __device__ int acquire(int want, unsigned lane, SM &sm) {
+    __device__ int acquire(int want, unsigned lane, SM &sm, bool) {
         int count = min(want, (int)stackCount);
         stackCount -= count;
         if ((int)lane < count) sm.work[lane] = stack[stackCount + lane];
+        // guided hand-out (as StateSource): new items are started only while the warp holds less than its
+        // share of what is left, so that a small batch -- and the end of a large one -- spreads over the grid
+        const unsigned long long nItems = descIn ? nDesc : (1 + kPhaseBSub) * nEdges;
+        const int share = (int)min((unsigned long long)want, (nItems - min(first, nItems)) / crew + 1);
+        if (!poolDry && count >= share) {   // busy with its own LIFO: still learn when the pool has drained
+            unsigned long long c = 0;
+            if (lane == 0) c = *(volatile unsigned long long *)counter;
+            poolDry = __shfl_sync(kFull, c, 0) >= nItems;
+        }
+        if (descIn) {
+            if (!globalDone && count < share) {
+                const int take = min(want, share) - count;
+                unsigned long long f = 0;
+                if (lane == 0) f = atomicAdd(counter, (unsigned long long)take);
+                f = __shfl_sync(kFull, f, 0);
+                if (f >= nDesc) {
+                    globalDone = poolDry = true;
+                } else {
+                    const int got = (int)min((unsigned long long)take, nDesc - f);
+                    if ((int)lane < got) sm.work[count + lane] = descIn[f + lane];
+                    count += got;
+                    first = f + got;
+                }
+            }
+            __syncwarp();
+            return count;
+        }
         while (count < want) {
-            if (!have && !nextItem(lane)) break;
+            if (!have && (count >= share || !nextItem(lane))) break;
             const unsigned span = curPhase == 0 ? 64u : 64u / kPhaseBSub;
             if (pos >= span) {
                 have = false;
@@ -567,7 +658,32 @@ struct EdgeSource {
     __device__ void retire(SM &sm, unsigned lane, bool r0, bool r1, const Masks64 &hit, const Masks64 &touched,
                            unsigned &error) {
         unsigned cnt = 0;
-        uint4 kids[4];
+        uint4 kids[28];
+        // With the item pool drained and little left on the LIFO the warp is latency bound (a hard interval
+        // is a chain of ~log2(length) traversals, ~50 us each): split each half `extra` more times then --
+        // the inner split points are tested as single samples next to the pieces, which skips the attempts
+        // to certify the larger pieces and shortens the chain (measured: 256 Cubicles edges 0.63 -> 0.50 ms
+        // with one extra level).
+        const int extra = !(poolDry || globalDone) ? 0 : stackCount < 8 ? 2 : stackCount < 32 ? 1 : 0;
+        auto half = [&](unsigned e, unsigned a, unsigned b) {   // a <= b
+            // pieces of [a, b] after `extra` bisections, points last (they are popped, and can kill the edge, first)
+            unsigned pa[4], pb[4], np = 1, pts[3], npts = 0;
+            pa[0] = a; pb[0] = b;
+            for (int lvl = 0; lvl < extra; ++lvl) {
+                const unsigned cur = np;
+                for (unsigned i = 0; i < cur; ++i) {
+                    const unsigned x = pa[i], y = pb[i];
+                    if (y - x < 2) continue;
+                    const unsigned m = x + (y - x) / 2;
+                    pts[npts++] = m;
+                    pb[i] = m - 1;       // m > x because y - x >= 2
+                    pa[np] = m + 1;      // m < y
+                    pb[np++] = y;
+                }
+            }
+            for (unsigned i = 0; i < np; ++i) kids[cnt++] = make_uint4(e, pa[i], pb[i], 0);
+            for (unsigned i = 0; i < npts; ++i) kids[cnt++] = make_uint4(e, pts[i], pts[i], 0);
+        };
         auto one = [&](bool r, unsigned slot, bool isHit, bool isTouched) {
             if (!r) return;
             const unsigned e = sm.tag0[slot], mid = sm.tag1[slot], lo = sm.tag2[slot], hi = sm.tag3[slot];
@@ -576,8 +692,8 @@ struct EdgeSource {
                 return;
             }
             if (hi > lo && isTouched && !((volatile unsigned *)dead)[e]) {
-                if (mid > lo) kids[cnt++] = make_uint4(e, lo, mid - 1, 0);
-                if (mid < hi) kids[cnt++] = make_uint4(e, mid + 1, hi, 0);
+                if (mid > lo) half(e, lo, mid - 1);
+                if (mid < hi) half(e, mid + 1, hi);
             }
         };
         one(r0, lane, (hit.lo >> lane) & 1u, (touched.lo >> lane) & 1u);
@@ -591,6 +707,16 @@ struct EdgeSource {
         }
         const unsigned total = __shfl_sync(kFull, incl, 31);
         if (total == 0) return;
+        if (spillOut && (poolDry || globalDone) && stackCount + total > kSpillKeep) {
+            unsigned long long pos = 0;
+            if (lane == 0) pos = atomicAdd(spillCount, (unsigned long long)total);
+            pos = __shfl_sync(kFull, pos, 0);
+            if (pos + total <= spillCap) {   // (a reservation past the end is undone; nobody succeeds meanwhile)
+                for (unsigned k = 0; k < cnt; ++k) spillOut[pos + incl - cnt + k] = kids[k];
+                return;
+            }
+            if (lane == 0) atomicAdd(spillCount, ~(unsigned long long)total + 1ull);
+        }
         if (stackCount + total > stackCap) {
             error = 1;  // reported by the host call; never silent
             return;
@@ -636,7 +762,7 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
     Masks64 freeM{~0u, ~0u}, readyM{0, 0}, hitM{0, 0}, doneM{0, 0}, touchedM{0, 0};  // touched: reached a leaf pair
     // this lane's LIFO holds entries [bot, sp); thieves take from the bottom (the largest subtree)
     int nt = 0, nx = 0, sp = 0, bot = 0, mySlot = -1;
-    const int triMin = sc.triBatchMin;
+    const int triMin = sc.triBatchMin, triEager = sc.triEagerLanes;
     unsigned idleSpins = 0;
     // compact the set bits of a 64-slot mask into sm.list (lane s looks after slots s and s + 32)
     auto buildList = [&](const Masks64 &m) {
@@ -676,7 +802,7 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
         if (!src.done() && needMask && !(readyM.lo | readyM.hi)) {
             const int nfree = freeM.count();
             if (nfree >= 16 || (nfree > 0 && nActive <= 16)) {
-                const int got = src.acquire(min(32, nfree), lane, sm);
+                const int got = src.acquire(min(32, nfree), lane, sm, nActive == 0 && nt == 0 && nx == 0);
                 buildList(freeM);
                 bool take = (int)lane < got;
                 unsigned slot = 0;
@@ -763,6 +889,7 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
         if (nActive == 0 && nt == 0 && nx == 0) {
             const bool busy = __any_sync(kFull, mySlot >= 0) || (doneM.lo | doneM.hi) || (readyM.lo | readyM.hi);
             if (!busy && src.done()) break;
+            if (src.waiting()) idleSpins = 0;   // a streamed claim that has not landed: the source bounds that wait itself
             if (++idleSpins > 4096u) {  // bookkeeping bug guard: report instead of hanging the device
                 cnt.error = 1;
                 break;
@@ -841,15 +968,17 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
         };
         // The queues hold at most 31 leftovers plus what one step can add (64 leaf pairs, 32 unsure
         // pairs per triangle batch): drain them down below a batch before stepping again.
-        while (nt >= triMin || (nt > 0 && nActive <= 16)) {
+        while (nt >= triMin || (nt > 0 && nActive <= triEager)) {
             triBatch();
             while (nx >= 32) exactBatch();
         }
-        if (nx > 0 && nActive <= 16) exactBatch();
+        if (nx > 0 && nActive <= triEager) exactBatch();
         // ---- depth-first steps: each lane pops a pair and tests both children of the larger box.
         //      A few steps run back to back before the slot bookkeeping above is revisited (a lane that
         //      finishes early idles for at most kStepsPerRound - 1 steps; the leaf queue is re-checked
-        //      every step because one step can add 64 pairs to it).
+        //      every step because one step can add 64 pairs to it).  Stealing more often than that does
+        //      not pay: it fans a colliding pose's search out over subtrees the nearest-first descent
+        //      would never have visited (measured: +65 % box tests on Alpha 1.5).
         for (int rep = 0; rep < kStepsPerRound && nActive && nt < 32; ++rep) {
             bool act = sp > bot;
             const unsigned slot = (unsigned)max(mySlot, 0);
@@ -996,12 +1125,24 @@ __device__ __forceinline__ void flushCounters(const WarpCounters &c, DevCounters
 template <typename E>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MPLB_MIN_CTAS)
 checkStatesKernel(SceneDev sc, const double *states, unsigned long long n, uint8_t *__restrict__ valid,
-                  DevCounters *ctr, unsigned long long *workCounter, int streamed) {
+                  DevCounters *ctr, unsigned long long *workCounter, int streamed, unsigned guidedShare) {
     WarpSmem<E> sm = warpSmem<E>(sc.stackLevels);
     StateSource src;
     src.states = states; src.n = n; src.valid = valid; src.counter = workCounter; src.streamed = streamed != 0;
+    src.crew = (unsigned long long)gridDim.x * kWarpsPerCta * guidedShare;
     WarpCounters cnt;
+#ifdef MPLB_WARP_TIMES
+    auto now = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    if ((threadIdx.x & 31u) == 0) atomicMax(&ctr->negStart, ~now());
+#endif
     runWarp<E>(sm, sc, src, cnt);
+#ifdef MPLB_WARP_TIMES
+    if ((threadIdx.x & 31u) == 0) {
+        atomicMax(&ctr->negFirstDry, ~src.dryAt);
+        atomicMax(&ctr->negFirstDone, ~now());
+        atomicMax(&ctr->lastDone, now());
+    }
+#endif
     if (__any_sync(kFull, src.stalled != 0)) cnt.error = 1;
     flushCounters(cnt, ctr, false);
 }
@@ -1010,17 +1151,40 @@ template <typename E>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MPLB_MIN_CTAS)
 checkEdgesKernel(SceneDev sc, const double *__restrict__ from, const double *__restrict__ to,
                  const unsigned *__restrict__ steps, unsigned long long nEdges, unsigned grab, unsigned *dead,
-                 uint4 *stacks, unsigned stackCap, DevCounters *ctr, unsigned long long *workCounter) {
+                 uint4 *stacks, unsigned stackCap, DevCounters *ctr, unsigned long long *workCounter,
+                 const uint4 *descIn, const unsigned long long *descCount, uint4 *spillOut,
+                 unsigned long long *spillCount, unsigned spillCap) {
+    if (descIn && *descCount == 0) return;   // nothing was spilled by the previous pass
     WarpSmem<E> sm = warpSmem<E>(sc.stackLevels);
     EdgeSource src;
     src.from = from; src.to = to; src.steps = steps; src.nEdges = nEdges; src.grab = grab; src.dead = dead;
+    src.crew = 2ull * gridDim.x * kWarpsPerCta;
     src.counter = workCounter;
+    src.descIn = descIn;
+    if (descIn) src.nDesc = min(*descCount, (unsigned long long)spillCap);
+    src.spillOut = spillOut; src.spillCount = spillCount; src.spillCap = spillCap;
     src.stack = stacks + (size_t)(blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)) * stackCap;
     src.stackCap = stackCap;
     src.robotRadius = sc.robotRadius;
     src.errorFlag = &ctr->overflow;
     WarpCounters cnt;
+#ifdef MPLB_WARP_TIMES
+    auto now = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+    if ((threadIdx.x & 31u) == 0) atomicMax(&ctr->negStart, ~now());
+#endif
     runWarp<E>(sm, sc, src, cnt);
+#ifdef MPLB_WARP_TIMES
+    if ((threadIdx.x & 31u) == 0) {
+        const unsigned w = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+        atomicMax(&ctr->lastDone, now());
+        if (w < 4096) {
+            ctr->warpDone[w] = now();
+            ctr->warpStates[w] = (unsigned)cnt.states;
+            ctr->warpBv[w] = (unsigned)cnt.bv;
+            ctr->warpTri[w] = (unsigned)cnt.tri;
+        }
+    }
+#endif
     flushCounters(cnt, ctr, true);
 }
 
@@ -1048,14 +1212,20 @@ cudaError_t launchStatesT(const SceneDev &sc, const double *dStates, size_t n, u
     cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     int grid = gridFor(k, smem, numSms);
-    // a warp wants at least ~2 refills of 32 states to be worth launching
-    const unsigned long long warpsWanted = (n + 63) / 64;
-    grid = (int)std::min<unsigned long long>(grid, (warpsWanted + kWarpsPerCta - 1) / kWarpsPerCta);
-    k<<<std::max(grid, 1), kWarpsPerCta * 32, smem, stream>>>(sc, dStates, n, dValid, dCtr, dWork, streamed ? 1 : 0);
+    // small batches are latency bound: one state per warp, spread over as many SMs as there are
+    grid = (int)std::min<unsigned long long>(grid, (n + kWarpsPerCta - 1) / kWarpsPerCta);
+    constexpr unsigned guidedShare = 2;   // a warp takes at most 1/(2 x warps) of what is left (1, 4, 8 measured no better)
+    k<<<std::max(grid, 1), kWarpsPerCta * 32, smem, stream>>>(sc, dStates, n, dValid, dCtr, dWork, streamed ? 1 : 0,
+                                                              guidedShare);
     return cudaGetLastError();
 }
 
 constexpr unsigned kEdgeStackCap = 2048;   // interval LIFO entries per warp
+#ifndef MPLB_EDGE_PASSES
+#define MPLB_EDGE_PASSES 3
+#endif
+constexpr int kEdgePasses = MPLB_EDGE_PASSES;   // <= 8
+constexpr unsigned kSpillCap = 1u << 18;   // descriptors one pass can hand to the next (beyond that a warp keeps its own)
 constexpr int kMaxCtasPerSm = 3;
 
 template <typename E>
@@ -1072,8 +1242,18 @@ cudaError_t launchEdgesT(const SceneDev &sc, const double *dFrom, const double *
         32, std::max<unsigned long long>(1, nItems / (4ull * grid * kWarpsPerCta)));
     grid = (int)std::min<unsigned long long>(grid, (nItems + kWarpsPerCta - 1) / kWarpsPerCta);
     grid = std::max(grid, 1);
-    if ((size_t)grid * kWarpsPerCta * kEdgeStackCap * sizeof(uint4) > stackBytes) return cudaErrorInvalidValue;
-    k<<<grid, kWarpsPerCta * 32, smem, stream>>>(sc, dFrom, dTo, dSteps, n, grab, dDead, dStacks, kEdgeStackCap, dCtr, dWork);
+    const size_t lifoBytes = (size_t)grid * kWarpsPerCta * kEdgeStackCap * sizeof(uint4);
+    if (lifoBytes + 2 * (size_t)kSpillCap * sizeof(uint4) > stackBytes) return cudaErrorInvalidValue;
+    // dWork: [p] item counter of pass p, [8 + p] number of descriptors spilled by pass p
+    uint4 *spill[2] = {dStacks + (stackBytes / sizeof(uint4) - 2 * (size_t)kSpillCap), nullptr};
+    spill[1] = spill[0] + kSpillCap;
+    const int threads = kWarpsPerCta * 32;
+    for (int p = 0; p < kEdgePasses; ++p) {
+        const bool last = p == kEdgePasses - 1;
+        k<<<grid, threads, smem, stream>>>(sc, dFrom, dTo, dSteps, n, grab, dDead, dStacks, kEdgeStackCap, dCtr, dWork + p,
+                                           p ? spill[(p - 1) & 1] : nullptr, p ? dWork + 8 + (p - 1) : nullptr,
+                                           last ? nullptr : spill[p & 1], last ? nullptr : dWork + 8 + p, kSpillCap);
+    }
     return cudaGetLastError();
 }
 
@@ -1089,14 +1269,14 @@ cudaError_t launchCheckStates(const SceneDev &sc, const double *dStates, size_t 
 }
 
 size_t edgeStackBytes(int numSms) {
-    return (size_t)numSms * kMaxCtasPerSm * kWarpsPerCta * kEdgeStackCap * sizeof(uint4);
+    return (size_t)numSms * kMaxCtasPerSm * kWarpsPerCta * kEdgeStackCap * sizeof(uint4) + 2 * (size_t)kSpillCap * sizeof(uint4);
 }
 
 cudaError_t launchCheckEdges(const SceneDev &sc, const double *dFrom, const double *dTo, const unsigned *dSteps,
                              size_t n, unsigned *dDead, uint8_t *dValid, DevCounters *dCtr, unsigned long long *dWork,
                              void *dStacks, size_t stackBytes, int numSms, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    cudaError_t err = cudaMemsetAsync(dWork, 0, sizeof(unsigned long long), stream);
+    cudaError_t err = cudaMemsetAsync(dWork, 0, 16 * sizeof(unsigned long long), stream);
     if (err != cudaSuccess) return err;
     err = cudaMemsetAsync(dDead, 0, sizeof(unsigned) * n, stream);
     if (err != cudaSuccess) return err;
