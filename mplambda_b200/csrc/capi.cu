@@ -138,6 +138,10 @@ struct Se3Scene : SceneBase {
     }
 };
 
+static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t *valid);
+static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, size_t n, uint8_t *valid,
+                         uint64_t *statesChecked);
+
 static int createSe3(const double *envTris, size_t nEnv, const double *robotTris, size_t nRobot, double so3w,
                      double l2w, double res, int device, mplb_scene **out) {
     if (!out) return fail(MPLB_ERR_INVALID, "out is null");
@@ -206,6 +210,14 @@ static int createSe3(const double *envTris, size_t nEnv, const double *robotTris
     if (const char *e = std::getenv("MPLB_TRI_BATCH")) d.triBatchMin = std::max(1, std::min(32, std::atoi(e)));
     sc->envNodeCount = env.nodes.size();
     sc->robotNodeCount = robot.nodes.size();
+    {
+        // first-use costs (kernel load, call context, interval scratch: ~0.1 s) belong to construction, not
+        // to the planner's first isValid
+        const double q[7] = {0, 0, 0, 1, 0, 0, 0};
+        uint8_t v;
+        if ((rc = se3CheckStates(sc.get(), q, 1, &v)) || (rc = se3CheckEdges(sc.get(), q, q, 1, &v, nullptr))) return rc;
+        sc->hChecks = sc->hBv = sc->hTri = sc->hExact = sc->hLaunches = 0;
+    }
     *out = reinterpret_cast<mplb_scene *>(static_cast<SceneBase *>(sc.release()));
     return MPLB_OK;
 }
@@ -319,6 +331,9 @@ static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, siz
     CtxGuard g{sc, c};
     c->hSteps.resize(n);
     uint32_t maxSteps = 0;
+    static const bool timeline = std::getenv("MPLB_TIMELINE") != nullptr;
+    const auto h0 = std::chrono::steady_clock::now();
+    auto sinceMs = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count(); };
     {
         // se3...:139 on the host (same libm as the CPU path); large batches use the host's cores
         long long bad = -1;
@@ -338,6 +353,7 @@ static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, siz
         if (bad >= 0)
             return fail(MPLB_ERR_INVALID, "edge %lld needs >= 2^31 interpolation steps; non-finite state?", bad);
     }
+    const double tPlan = sinceMs();
     int rc;
     const size_t sb = n * 7 * sizeof(double);
     const size_t stackBytes = edgeStackBytes(sc->numSms);
@@ -354,7 +370,11 @@ static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, siz
                                sc->numSms, c->stream));
     sc->hLaunches += 4;   // three passes + the verdict kernel
     MPLB_CUDA(cudaMemcpyAsync(valid, c->out.ptr, n, cudaMemcpyDeviceToHost, c->stream));
-    return finishCall(sc, c, 0, statesChecked);
+    const double tEnq = sinceMs();
+    rc = finishCall(sc, c, 0, statesChecked);
+    if (timeline)
+        std::fprintf(stderr, "[mplb timeline] %zu edges: steps planned %.3f ms, enqueued %.3f, done %.3f\n", n, tPlan, tEnq, sinceMs());
+    return rc;
 }
 
 int Se3Scene::checkStates(const double *states, size_t n, uint8_t *valid) { return se3CheckStates(this, states, n, valid); }

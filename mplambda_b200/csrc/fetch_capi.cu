@@ -278,6 +278,13 @@ static int createFetch(const double *envTris, size_t nEnv, const double envFrame
     d.shapes[11] = {2, 0.24 * 1.05, (0.115 * 1.05) / 2, 0};
     sc->envNodeCount = env.nodes.size();
     sc->robotNodeCount = 12;
+    {
+        // first-use costs (kernel load, call context, work lists) belong to construction
+        const double q[8] = {0.1, 0, 0, 0, 0, 0, 0, 0};
+        uint8_t v;
+        if ((rc = sc->checkStates(q, 1, &v)) || (rc = sc->checkEdges(q, q, 1, &v, nullptr))) return rc;
+        sc->hChecks = sc->hBv = sc->hTri = sc->hExact = sc->hLaunches = 0;
+    }
     *out = reinterpret_cast<mplb_scene *>(static_cast<SceneBase *>(sc.release()));
     return MPLB_OK;
 }
