@@ -7,6 +7,13 @@
 namespace mplb {
 
 __device__ __forceinline__ float4 ldg4(const float4 *p) { return __ldg(p); }
+// two consecutive float4 (32-byte aligned) with one 256-bit load (sm_100: LDG.E.256): one L1 tag lookup
+// per 32-byte sector instead of two -- the box-pair step is bound by L1TEX lookups, not by bytes
+__device__ __forceinline__ void ldg8(const float4 *p, float4 &a, float4 &b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
 
 // ---------------------------------------------------------------------------------------------
 // FP64 "specification" arithmetic: identical operation order to oracle/mplb_oracle.c.

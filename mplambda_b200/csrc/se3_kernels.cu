@@ -1001,9 +1001,10 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
                 fixedIdx = descendA ? e : r;
                 const float4 *pc = (descendA ? sc.robotNodes : sc.envNodes) + 4 * (size_t)child;
                 const float4 *pf = (descendA ? sc.envNodes : sc.robotNodes) + 4 * (size_t)fixedIdx;
-                const float4 f0 = ldg4(pf), f1 = ldg4(pf + 1), f2 = ldg4(pf + 2), fe = ldg4(pf + 3);
-                const float4 c00 = ldg4(pc), c01 = ldg4(pc + 1), c02 = ldg4(pc + 2), c0e = ldg4(pc + 3);
-                const float4 c10 = ldg4(pc + 4), c11 = ldg4(pc + 5), c12 = ldg4(pc + 6), c1e = ldg4(pc + 7);
+                float4 f0, f1, f2, fe, c00, c01, c02, c0e, c10, c11, c12, c1e;
+                ldg8(pf, f0, f1); ldg8(pf + 2, f2, fe);
+                ldg8(pc, c00, c01); ldg8(pc + 2, c02, c0e);
+                ldg8(pc + 4, c10, c11); ldg8(pc + 6, c12, c1e);
                 const float4 x0 = sm.xf[slot][0], x1 = sm.xf[slot][1], x2 = sm.xf[slot][2], x3 = sm.xf[slot][3];
                 // The fixed box is always the first argument.  (R|T) maps env -> robot coordinates; when
                 // the fixed box is the environment's the test runs in its frame with the inverse map
