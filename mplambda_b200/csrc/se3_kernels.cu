@@ -56,7 +56,9 @@ constexpr unsigned kFull = 0xffffffffu;
 template <typename E>
 struct WarpSmem {
     unsigned (*stack)[32];            // [level][lane]: robotIdx | envIdx << bitsA | descendRobot << 31  (bank = lane)
-    float4 (*xf)[4];                  // per slot: rows of (R | T), then (slack, eta, -, -); see makeSlot
+    float4 (*xf)[5];                  // per slot: rows of (R | T), then (slack, eta, -, -); see makeSlot.  80-byte
+                                      // stride: lanes reading row r of 32 different slots spread over all banks
+                                      // (a 64-byte stride puts them on two 16-byte bank groups: 16-way conflicts)
     unsigned *tag0, *tag1, *tag2, *tag3;  // what the slot is (state index; or edge, sample, interval lo, hi)
     int *pending;                     // leaf pairs of the slot still sitting in triq/exq
     int *workers;                     // lanes currently searching the slot (work stealing splits a search)
@@ -66,13 +68,13 @@ struct WarpSmem {
     E *exq;
 
     static __host__ __device__ size_t bytes(int levels) {
-        return (size_t)levels * 128 + kSlots * 64 + 32 * 16 + kSlots * 28 + 2 * kQueueCap * sizeof(E);
+        return (size_t)levels * 128 + kSlots * 80 + 32 * 16 + kSlots * 28 + 2 * kQueueCap * sizeof(E);
     }
     __device__ void carve(unsigned char *base, int levels) {
         stack = reinterpret_cast<unsigned(*)[32]>(base);
         base += (size_t)levels * 128;
-        xf = reinterpret_cast<float4(*)[4]>(base);
-        base += kSlots * 64;
+        xf = reinterpret_cast<float4(*)[5]>(base);
+        base += kSlots * 80;
         work = reinterpret_cast<uint4 *>(base);
         base += 32 * 16;
         triq = reinterpret_cast<E *>(base);
