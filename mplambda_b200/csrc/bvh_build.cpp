@@ -263,7 +263,7 @@ inline float roundUp(double v) {
 FlatBvh buildBvh(const double *tris, size_t n) {
     FlatBvh out;
     out.tris64.assign(tris, tris + 9 * n);
-    out.tris32.resize(n);
+    out.tris32.assign(n, TriF32{});
     for (size_t i = 0; i < n; ++i)
         for (int k = 0; k < 3; ++k) {
             for (int d = 0; d < 3; ++d) {

@@ -25,12 +25,13 @@ struct alignas(16) BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "node must be 64 bytes");
 
-// One triangle for the FP32 filter: 48 bytes = 3 x float4 (xyz + pad):
+// One triangle for the FP32 filter: 64 bytes = 4 x float4 (xyz + pad; the 4th is padding so that a triangle
+// is two aligned 32-byte sectors: one 256-bit and one 128-bit load):
 //   v[0] = vertex 0, v[1] = vertex 1 - vertex 0, v[2] = vertex 2 - vertex 0 (differences formed in FP64).
-struct alignas(16) TriF32 {
-    float v[3][4];
+struct alignas(32) TriF32 {
+    float v[4][4];
 };
-static_assert(sizeof(TriF32) == 48, "triangle must be 48 bytes");
+static_assert(sizeof(TriF32) == 64, "triangle must be 64 bytes");
 
 struct FlatBvh {
     std::vector<BvhNode> nodes;   // 2n nodes: root = 0, node 1 is padding, sibling pairs start at even indices

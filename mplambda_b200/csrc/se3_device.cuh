@@ -10,7 +10,7 @@ namespace mplb {
 struct SceneDev {
     const float4 *robotNodes;   // 4 x float4 per node (mplb_host.hpp: BvhNode)
     const float4 *envNodes;
-    const float4 *robotTris;    // 3 x float4 per triangle (FP32 filter copy)
+    const float4 *robotTris;    // 4 x float4 per triangle (FP32 filter copy; the 4th is padding)
     const float4 *envTris;
     const double *robotTris64;  // 9 doubles per triangle (exact re-evaluation)
     const double *envTris64;

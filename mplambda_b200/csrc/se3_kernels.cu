@@ -911,10 +911,12 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
             const bool act = act0 && !hitM.test(slot);
             int verdict = kTriNo;
             if (act) {
-                const float4 *tp = sc.robotTris + 3 * (size_t)cd.a(en);
-                const float4 *tq = sc.envTris + 3 * (size_t)cd.b(en);
-                const float4 p1 = ldg4(tp), p2 = ldg4(tp + 1), p3 = ldg4(tp + 2);
-                const float4 w1 = ldg4(tq), w2 = ldg4(tq + 1), w3 = ldg4(tq + 2);
+                const float4 *tp = sc.robotTris + 4 * (size_t)cd.a(en);
+                const float4 *tq = sc.envTris + 4 * (size_t)cd.b(en);
+                float4 p1, p2, w1, w2;
+                ldg8(tp, p1, p2);
+                ldg8(tq, w1, w2);
+                const float4 p3 = ldg4(tp + 2), w3 = ldg4(tq + 2);
                 const float4 x0 = sm.xf[slot][0], x1 = sm.xf[slot][1], x2 = sm.xf[slot][2], x3 = sm.xf[slot][3];
                 // q1 = R*Q1 + T - P1 ; env edge vectors are only rotated
                 const F3 q1 = f3(fmaf(x0.x, w1.x, fmaf(x0.y, w1.y, fmaf(x0.z, w1.z, x0.w))) - p1.x,
