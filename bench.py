@@ -379,7 +379,8 @@ def main():
                             "kernel": "checkStatesKernel", "kernel_ms": kms,
                             "algorithmic_bytes_per_check": bytes_per_check,
                             "note": "algorithmic bytes follow the reference's (FCL-order) traversal counts; the "
-                                    "hierarchy is cache resident so the binding resource is the FP32 pipe, not HBM"}
+                                    "hierarchy is cache resident (ncu: 64 MB of DRAM traffic per launch, L2 hit rate 97 %), so the fraction can exceed 1; "
+                                    "the units that bind are the L1 data pipe (63 %) and the issue slots (55 %), profiles/r1_states_alpha15_v3_ncu_summary.txt"}
         if world == 1 and not args.no_extras and not args.no_cpu_baseline:
             try:
                 line["extras"] = extras(local_rank)

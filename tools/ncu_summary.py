@@ -13,7 +13,12 @@ keys = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
         'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct', 'smsp__warps_eligible.avg.per_cycle_active',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__sass_average_branch_targets_threads_uniform.pct',
-        'launch__shared_mem_per_block_dynamic', 'smsp__cycles_active.avg']
+        'launch__shared_mem_per_block_dynamic', 'smsp__cycles_active.avg',
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum',
+        'l1tex__throughput.avg.pct_of_peak_sustained_active', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio']
 stall = [h for h in hdr if 'warp_issue_stalled' in h and h.endswith('per_warp_active.pct')]
 for k in keys + stall:
     if k in hdr:
