@@ -642,7 +642,9 @@ fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsign
         if (sp > 0) {
             const int node = stack[--sp];
             const float4 *pn = sc.envNodes + 4 * (size_t)node;
-            const float4 b0 = ldg4(pn), b1 = ldg4(pn + 1), b2 = ldg4(pn + 2), be = ldg4(pn + 3);
+            float4 b0, b1, b2, be;
+            ldg8(pn, b0, b1);
+            ldg8(pn + 2, b2, be);
             ++bv;
             float dist2;
             if (obbOverlap(a0, a1, a2, ae, b0, b1, b2, be, x0, x1, x2, kCullSlack, dist2)) {
