@@ -20,6 +20,7 @@ scaling, no data-path collective); time = max over ranks.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -188,6 +189,35 @@ def extras(local_rank):
                                        "sample": "first %d queries, brute force" % m},
                       "index_mismatches_vs_cpu": int((widx != idx[:m]).sum()),
                       "distance_mismatches_vs_cpu": int((wdist != dist[:m]).sum())}
+    # ---- config 4: the addNodeNear pattern batched (pcforest.hpp:512-566) on Home: k-NN of each new node in the
+    #      tree, then the motion from the node to each of its k neighbours
+    env, robot = load_scene("home")
+    s = M.SE3RigidBodyScenario(env, robot, sc["goal"], sc["min"], sc["max"], 0.1, device=local_rank)
+    tree = keys[s.check_states(keys)]
+    new = qs[s.check_states(qs)][:4096]
+    k = int(math.ceil(math.e * (7.0 / 6.0) * math.log(len(tree) + 1)))
+    nn2 = M.Nigh(M.nn.SE3, device=local_rank)
+    nn2.insert(tree)
+
+    def near_and_connect(q):
+        ki, _ = nn2.knearest(q, k)
+        frm = np.repeat(q, k, axis=0)
+        return ki, s.check_edges(frm, tree[ki.reshape(-1)])
+    near_and_connect(new[:64])
+    dt, (ki, ev) = best(lambda: near_and_connect(new), reps=2)
+    m = 48
+    orc = O.SE3Oracle(env, robot, check_resolution=0.1)
+    t = time.perf_counter()
+    wi, _ = O.nn_knearest(tree, new[:m], k, threads=thr)
+    wv = orc.check_edges(np.repeat(new[:m], k, axis=0), tree[wi.reshape(-1)], O.BVH, threads=thr)
+    dc = time.perf_counter() - t
+    out["knn_connect_home"] = {
+        "metric": "new nodes/sec through k-NN + k motion checks (PCForest addNodeNear pattern)", "value": len(new) / dt,
+        "unit": "nodes/s", "tree_nodes": int(len(tree)), "new_nodes": int(len(new)), "k": k, "edges": int(len(new) * k),
+        "edge_valid_fraction": float(ev.mean()), "ms": dt * 1e3,
+        "cpu_baseline": {"value": m / dc, "unit": "nodes/s", "cores": thr, "kind": "port", "sample": "first %d new nodes" % m},
+        "neighbour_mismatches_vs_cpu": int((wi != ki[:m]).sum()), "verdict_mismatches_vs_cpu": int((wv != ev[:m * k]).sum())}
+    s.close()
     # ---- Fetch: 2^18 random configurations, AUTOLAB environment, task-001 frame
     env = np.load(os.path.join(ROOT, "tests", "golden", "scenes", "autolab.npz"))["env"]
     frame = frame_from_option(FETCH_TASKS["fetch_task_001"]["env_frame"])
@@ -202,6 +232,18 @@ def extras(local_rank):
                            "cpu_baseline": {"value": m / dc, "unit": "checks/s", "cores": thr, "kind": "port",
                                             "sample": "first %d configurations" % m},
                            "verdict_mismatches_vs_cpu": int((w != v[:m]).sum())}
+    # ---- config 5 edges: 16,384 motions between random configurations (valid start), resolution 0.01
+    A = Q[v][:1 << 14]
+    B = fetch_configs(len(A), SEED + 1)
+    f.check_edges(A[:256], B[:256])
+    dt, ev = best(lambda: f.check_edges(A, B), reps=2)
+    m = 256
+    t = time.perf_counter(); w = O.FetchOracle(env, frame, 0.01).check_edges(A[:m], B[:m], threads=thr); dc = time.perf_counter() - t
+    out["fetch_edges"] = {"metric": "Fetch edge validity checks/sec (resolution 0.01)", "value": len(A) / dt, "unit": "edges/s",
+                          "edges": int(len(A)), "valid_fraction": float(ev.mean()), "ms": dt * 1e3,
+                          "cpu_baseline": {"value": m / dc, "unit": "edges/s", "cores": thr, "kind": "port",
+                                           "sample": "first %d edges" % m},
+                          "verdict_mismatches_vs_cpu": int((w != ev[:m]).sum())}
     return out
 
 

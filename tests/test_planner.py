@@ -53,3 +53,33 @@ def test_gpu_planner_matches_cpu_planner(name, scenes):
     assert rg.n == rc.n and rg.stats["iterations"] == rc.stats["iterations"]
     np.testing.assert_array_equal(rg.nodes[:rg.n], rc.nodes[:rc.n])
     np.testing.assert_array_equal(pg, pc)
+
+
+@pytest.mark.gpu
+def test_knn_then_connect_matches_oracle(scenes, oracle):
+    """BASELINE config 4 at test size: PCForest's addNodeNear (pcforest.hpp:512-566) batched -- the k nearest tree
+    nodes of each new node, then the motion from the node to each of them.  Neighbours and verdicts bit-exact."""
+    import math
+    import mplambda_b200 as M
+    from mplambda_b200.workload import SEED, se3_poses
+    sc = SE3_SCENES["home"]
+    env, robot = scenes["home"]
+    s = M.SE3RigidBodyScenario(env, robot, sc["goal"], sc["min"], sc["max"], 0.1)
+    pool = se3_poses(8192, sc["min"], sc["max"], SEED)
+    tree = pool[s.check_states(pool)][:1024]
+    cand = se3_poses(2048, sc["min"], sc["max"], SEED + 2)
+    new = cand[s.check_states(cand)][:40]
+    k = int(math.ceil(math.e * (7.0 / 6.0) * math.log(len(tree) + 1)))
+    assert k == 22
+    nn = M.Nigh(M.nn.SE3)
+    nn.insert(tree)
+    ki, kd = nn.knearest(new, k)
+    wi, wd = oracle.nn_knearest(tree, new, k)
+    assert (ki == wi).all() and (kd == wd).all()
+    assert (np.diff(kd, axis=1) >= 0).all()                      # ascending: pcforest.hpp:523-524 relies on it
+    frm = np.repeat(new, k, axis=0)
+    to = tree[ki.reshape(-1)]
+    got = s.check_edges(frm, to)
+    want = oracle.SE3Oracle(env, robot, check_resolution=0.1).check_edges(frm, to)
+    assert (got == want).all()
+    assert 0 < got.sum() < len(got)
