@@ -234,21 +234,24 @@ struct Builder {
         return bestCount;
     }
 
-    void build(int node, int first, int n, int d) {
+    // `base`: where this node's descendants start.  A subtree over n triangles has 2n - 2 nodes below its
+    // root, laid out depth first (children pair, left subtree, right subtree), so every index is known
+    // from the split counts alone and the two halves can be built by different threads with the same
+    // result as the serial order.
+    void build(int node, int first, int n, int d, int base) {
         boxes[node] = fit(first, n);
-        depth = std::max(depth, d);
         if (n == 1) {
             link[node] = -(prim[first] + 1);
+#pragma omp critical(mplb_bvh_depth)
+            depth = std::max(depth, d);
             return;
         }
-        const Box &bx = boxes[node];
-        int half = chooseSplit(bx, first, n, d);
-        int fc = (int)boxes.size();
-        boxes.resize(fc + 2);
-        link.resize(fc + 2);
+        const int half = chooseSplit(boxes[node], first, n, d);
+        const int fc = base;
         link[node] = fc;
-        build(fc, first, half, d + 1);
-        build(fc + 1, first + half, n - half, d + 1);
+#pragma omp task firstprivate(fc, first, half, d, base) if (n > 512)
+        build(fc, first, half, d + 1, base + 2);
+        build(fc + 1, first + half, n - half, d + 1, base + 2 * half);
     }
 };
 
@@ -287,15 +290,15 @@ FlatBvh buildBvh(const double *tris, size_t n) {
     b.centroid.resize(n);
     for (size_t i = 0; i < n; ++i)
         b.centroid[i] = (b.verts[3 * i] + b.verts[3 * i + 1] + b.verts[3 * i + 2]) * (1.0 / 3.0);
-    b.boxes.reserve(2 * n);
-    b.link.reserve(2 * n);
     // node 1 is padding: every pair of children then starts at an even index, i.e. the two siblings
     // (2 x 64 B) share one 128-byte line
-    b.boxes.resize(2);
-    b.link.resize(2);
+    b.boxes.resize(2 * n);
+    b.link.resize(2 * n);
     b.boxes[1] = Box{{{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, {0, 0, 0}, {0, 0, 0}};
     b.link[1] = -1;
-    b.build(0, 0, (int)n, 0);
+#pragma omp parallel if (n > 1024)
+#pragma omp single
+    b.build(0, 0, (int)n, 0, 2);
     out.depth = b.depth;
 
     out.nodes.resize(b.boxes.size());
