@@ -49,7 +49,16 @@ DevBuf::~DevBuf() {
     if (ptr) cudaFree(ptr);
 }
 
+constexpr size_t kStageBytes = 160 * 1024;                 // inputs of a small call
+constexpr size_t kCtlHeader = ((sizeof(DevCounters) + 127) / 128) * 128 + 128;   // counters, then 16 work counters
+constexpr size_t kCtlTail = 8 * 1024;                      // verdicts (1 B/state) or dead flags (4 B/edge)
+constexpr size_t kSmallStates = 2048, kSmallEdges = 1024;
+static_assert(kSmallStates * 56 <= kStageBytes && kSmallEdges * 116 <= kStageBytes, "staging too small");
+static_assert(kSmallStates <= kCtlTail && kSmallEdges * 4 <= kCtlTail, "control block too small");
+
 CallCtx::~CallCtx() {
+    if (hStage) cudaFreeHost(hStage);
+    if (hCtl) cudaFreeHost(hCtl);
     if (hCtr) cudaFreeHost(hCtr);
     if (hWater) cudaFreeHost(hWater);
     for (auto e : events) cudaEventDestroy(e);
@@ -71,6 +80,9 @@ CallCtx *SceneBase::acquire() {
         cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMallocHost((void **)&c->hCtr, sizeof(DevCounters)) != cudaSuccess ||
         cudaMallocHost((void **)&c->hWater, 64 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMallocHost((void **)&c->hStage, kStageBytes) != cudaSuccess ||
+        cudaMallocHost((void **)&c->hCtl, kCtlHeader + kCtlTail) != cudaSuccess ||
+        c->stage.reserve(kStageBytes) != MPLB_OK || c->ctl.reserve(kCtlHeader + kCtlTail) != MPLB_OK ||
         c->ctr.reserve(sizeof(DevCounters)) != MPLB_OK || c->work.reserve(128) != MPLB_OK) {
         delete c;
         return nullptr;
@@ -222,6 +234,16 @@ static int createSe3(const double *envTris, size_t nEnv, const double *robotTris
     return MPLB_OK;
 }
 
+static int account(SceneBase *sc, const DevCounters &k, size_t checks, uint64_t *statesOut) {
+    if (k.overflow) return fail(MPLB_ERR_CUDA, "device traversal bookkeeping error (pair stack / slot accounting)");
+    sc->hBv += k.bvTests;
+    sc->hTri += k.triTests;
+    sc->hExact += k.exactTests;
+    sc->hChecks += checks ? checks : k.states;
+    if (statesOut) *statesOut = k.states;
+    return MPLB_OK;
+}
+
 static int finishCall(SceneBase *sc, CallCtx *c, size_t checks, uint64_t *statesOut) {
     cudaError_t e = cudaMemcpyAsync(c->hCtr, c->ctr.ptr, sizeof(DevCounters), cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -242,13 +264,7 @@ static int finishCall(SceneBase *sc, CallCtx *c, size_t checks, uint64_t *states
         if (!ord.empty()) std::fprintf(stderr, "    median warp done %.1f us (%zu warps)\n", ((double)k.warpDone[ord[ord.size() / 2]] - t0) * 1e-3, ord.size());
     }
 #endif
-    if (c->hCtr->overflow) return fail(MPLB_ERR_CUDA, "device traversal bookkeeping error (pair stack / slot accounting)");
-    sc->hBv += c->hCtr->bvTests;
-    sc->hTri += c->hCtr->triTests;
-    sc->hExact += c->hCtr->exactTests;
-    sc->hChecks += checks ? checks : c->hCtr->states;
-    if (statesOut) *statesOut = c->hCtr->states;
-    return MPLB_OK;
+    return account(sc, *c->hCtr, checks, statesOut);
 }
 
 // Large host batches stream in under the running kernel: the device input buffer is pre-filled with an
@@ -271,6 +287,19 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
     CtxGuard g{sc, c};
     int rc;
     const size_t bytes = n * 7 * sizeof(double);
+    if (n <= kSmallStates) {
+        std::memcpy(c->hStage, states, bytes);
+        unsigned char *ctl = (unsigned char *)c->ctl.ptr;
+        MPLB_CUDA(cudaMemsetAsync(ctl, 0, kCtlHeader, c->stream));
+        MPLB_CUDA(cudaMemcpyAsync(c->stage.ptr, c->hStage, bytes, cudaMemcpyHostToDevice, c->stream));
+        MPLB_CUDA(launchCheckStates(sc->dev, (const double *)c->stage.ptr, n, ctl + kCtlHeader, (DevCounters *)ctl,
+                                    (unsigned *)(ctl + kCtlHeader - 128), sc->numSms, c->stream, false, true));
+        sc->hLaunches += 1;
+        MPLB_CUDA(cudaMemcpyAsync(c->hCtl, ctl, kCtlHeader + n, cudaMemcpyDeviceToHost, c->stream));
+        MPLB_CUDA(cudaStreamSynchronize(c->stream));
+        std::memcpy(valid, c->hCtl + kCtlHeader, n);
+        return account(sc, *(const DevCounters *)c->hCtl, n, nullptr);
+    }
     if ((rc = c->in0.reserve(bytes)) || (rc = c->out.reserve(n))) return rc;
     double *dIn = (double *)c->in0.ptr;
     uint8_t *dOut = (uint8_t *)c->out.ptr;
@@ -357,6 +386,28 @@ static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, siz
     int rc;
     const size_t sb = n * 7 * sizeof(double);
     const size_t stackBytes = edgeStackBytes(sc->numSms);
+    if (n <= kSmallEdges) {
+        if ((rc = c->aux0.reserve(stackBytes))) return rc;
+        std::memcpy(c->hStage, from, sb);
+        std::memcpy(c->hStage + sb, to, sb);
+        std::memcpy(c->hStage + 2 * sb, c->hSteps.data(), n * 4);
+        unsigned char *ctl = (unsigned char *)c->ctl.ptr, *in = (unsigned char *)c->stage.ptr;
+        MPLB_CUDA(cudaMemsetAsync(ctl, 0, kCtlHeader + n * 4, c->stream));
+        MPLB_CUDA(cudaMemcpyAsync(in, c->hStage, 2 * sb + n * 4, cudaMemcpyHostToDevice, c->stream));
+        MPLB_CUDA(launchCheckEdges(sc->dev, (const double *)in, (const double *)(in + sb), (const unsigned *)(in + 2 * sb), n,
+                                   (unsigned *)(ctl + kCtlHeader), nullptr, (DevCounters *)ctl,
+                                   (unsigned long long *)(ctl + kCtlHeader - 128), c->aux0.ptr, stackBytes, sc->numSms,
+                                   c->stream, true));
+        sc->hLaunches += 3;
+        MPLB_CUDA(cudaMemcpyAsync(c->hCtl, ctl, kCtlHeader + n * 4, cudaMemcpyDeviceToHost, c->stream));
+        MPLB_CUDA(cudaStreamSynchronize(c->stream));
+        const unsigned *dead = (const unsigned *)(c->hCtl + kCtlHeader);
+        for (size_t i = 0; i < n; ++i) valid[i] = dead[i] ? 0 : 1;
+        rc = account(sc, *(const DevCounters *)c->hCtl, 0, statesChecked);
+        if (timeline)
+            std::fprintf(stderr, "[mplb timeline] %zu edges (small call): steps planned %.3f ms, done %.3f\n", n, tPlan, sinceMs());
+        return rc;
+    }
     if ((rc = c->in0.reserve(sb)) || (rc = c->in1.reserve(sb)) || (rc = c->steps.reserve(n * 4)) ||
         (rc = c->dead.reserve(n * 4)) || (rc = c->out.reserve(n)) || (rc = c->aux0.reserve(stackBytes)))
         return rc;

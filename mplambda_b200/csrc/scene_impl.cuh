@@ -31,6 +31,11 @@ struct CallCtx {
     std::vector<cudaEvent_t> events;    // one per pipeline stage
     DevBuf in0, in1, steps, dead, out, ctr, work, aux0, aux1, aux2, aux3, aux4, aux5, aux6;
     DevCounters *hCtr = nullptr;  // pinned
+    // Small calls (the reference's scalar isValid) go through one pinned staging buffer each way and one
+    // device control block [DevCounters | 16 work counters | verdicts or dead flags]: one memset, one
+    // host->device copy, the kernels, one device->host copy.
+    unsigned char *hStage = nullptr, *hCtl = nullptr;   // pinned
+    DevBuf stage, ctl;
     unsigned long long *hWater = nullptr;  // pinned: per-slice arrival marks of a streamed batch
     std::vector<uint32_t> hSteps;
     ~CallCtx();

@@ -39,15 +39,17 @@ struct DevCounters {
 
 // streamed: dStates was pre-filled with the all-ones pattern and is being overwritten by a host->device copy
 // on another stream; the kernel picks each state up when it has landed (se3_kernels.cu: StateSource)
+// workZeroed: the caller has already zeroed the first work counter
 cudaError_t launchCheckStates(const SceneDev &sc, const double *dStates, size_t n, uint8_t *dValid,
                               DevCounters *dCtr, unsigned *dWork, int numSms, cudaStream_t stream,
-                              bool streamed = false);
+                              bool streamed = false, bool workZeroed = false);
 
 // scratch for the per-warp interval LIFOs of checkEdgesKernel
 size_t edgeStackBytes(int numSms);
 
 cudaError_t launchCheckEdges(const SceneDev &sc, const double *dFrom, const double *dTo, const unsigned *dSteps,
                              size_t n, unsigned *dDead, uint8_t *dValid, DevCounters *dCtr, unsigned long long *dWork,
-                             void *dStacks, size_t stackBytes, int numSms, cudaStream_t stream);
+                             void *dStacks, size_t stackBytes, int numSms, cudaStream_t stream, bool zeroed = false);
+// zeroed: dWork (16 counters) and dDead are already zero.  dValid == nullptr: leave the verdicts as dDead flags.
 
 }  // namespace mplb

@@ -29,6 +29,8 @@
 #include "device_math.cuh"
 
 #include <cfloat>
+#include <map>
+#include <mutex>
 
 namespace mplb {
 namespace {
@@ -1201,12 +1203,32 @@ __global__ void deadToValidKernel(const unsigned *__restrict__ dead, unsigned lo
 template <typename E>
 size_t smemBytes(const SceneDev &sc) { return WarpSmem<E>::bytes(sc.stackLevels) * kWarpsPerCta; }
 
+// Resident grid of `kernel` with `smem` bytes of dynamic shared memory on the current device.  The answer (and
+// the opt-in to that much shared memory) is cached per device and size: a scalar isValid(q) is one ~8 us
+// launch, two extra runtime calls in front of it are not free.
 template <typename K>
-int gridFor(K kernel, size_t smem, int numSms) {
-    int perSm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kWarpsPerCta * 32, smem);
-    if (perSm < 1) perSm = 1;
-    return perSm * numSms;
+cudaError_t gridFor(K kernel, size_t smem, int numSms, int *grid) {
+    static std::mutex mu;
+    static std::map<std::pair<int, size_t>, int> cache;
+    int dev = 0;
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find({dev, smem});
+    if (it == cache.end()) {
+        // the attribute is per device: keep it at the largest size any scene on this device needs
+        size_t most = smem;
+        for (const auto &kv : cache)
+            if (kv.first.first == dev) most = std::max(most, kv.first.second);
+        err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most);
+        if (err != cudaSuccess) return err;
+        int perSm = 0;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kWarpsPerCta * 32, smem);
+        if (err != cudaSuccess) return err;
+        it = cache.emplace(std::make_pair(dev, smem), std::max(perSm, 1) * numSms).first;
+    }
+    *grid = it->second;
+    return cudaSuccess;
 }
 
 template <typename E>
@@ -1214,9 +1236,9 @@ cudaError_t launchStatesT(const SceneDev &sc, const double *dStates, size_t n, u
                           unsigned long long *dWork, bool streamed, int numSms, cudaStream_t stream) {
     auto k = checkStatesKernel<E>;
     const size_t smem = smemBytes<E>(sc);
-    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int grid = 0;
+    cudaError_t err = gridFor(k, smem, numSms, &grid);
     if (err != cudaSuccess) return err;
-    int grid = gridFor(k, smem, numSms);
     // small batches are latency bound: one state per warp, spread over as many SMs as there are
     grid = (int)std::min<unsigned long long>(grid, (n + kWarpsPerCta - 1) / kWarpsPerCta);
     constexpr unsigned guidedShare = 2;   // a warp takes at most 1/(2 x warps) of what is left (1, 4, 8 measured no better)
@@ -1239,9 +1261,10 @@ cudaError_t launchEdgesT(const SceneDev &sc, const double *dFrom, const double *
                          size_t stackBytes, int numSms, cudaStream_t stream) {
     auto k = checkEdgesKernel<E>;
     const size_t smem = smemBytes<E>(sc);
-    cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int grid = 0;
+    cudaError_t err = gridFor(k, smem, numSms, &grid);
     if (err != cudaSuccess) return err;
-    int grid = std::min(gridFor(k, smem, numSms), kMaxCtasPerSm * numSms);
+    grid = std::min(grid, kMaxCtasPerSm * numSms);
     const unsigned long long nItems = (1ull + kPhaseBSub) * n;   // phase A item + phase B sub-items per edge
     const unsigned grab = (unsigned)std::min<unsigned long long>(
         32, std::max<unsigned long long>(1, nItems / (4ull * grid * kWarpsPerCta)));
@@ -1265,9 +1288,10 @@ cudaError_t launchEdgesT(const SceneDev &sc, const double *dFrom, const double *
 }  // namespace
 
 cudaError_t launchCheckStates(const SceneDev &sc, const double *dStates, size_t n, uint8_t *dValid,
-                              DevCounters *dCtr, unsigned *dWork, int numSms, cudaStream_t stream, bool streamed) {
+                              DevCounters *dCtr, unsigned *dWork, int numSms, cudaStream_t stream, bool streamed,
+                              bool workZeroed) {
     if (n == 0) return cudaSuccess;
-    cudaError_t err = cudaMemsetAsync(dWork, 0, sizeof(unsigned long long), stream);
+    cudaError_t err = workZeroed ? cudaSuccess : cudaMemsetAsync(dWork, 0, sizeof(unsigned long long), stream);
     if (err != cudaSuccess) return err;
     return sc.wide ? launchStatesT<unsigned long long>(sc, dStates, n, dValid, dCtr, (unsigned long long *)dWork, streamed, numSms, stream)
                    : launchStatesT<unsigned>(sc, dStates, n, dValid, dCtr, (unsigned long long *)dWork, streamed, numSms, stream);
@@ -1279,16 +1303,19 @@ size_t edgeStackBytes(int numSms) {
 
 cudaError_t launchCheckEdges(const SceneDev &sc, const double *dFrom, const double *dTo, const unsigned *dSteps,
                              size_t n, unsigned *dDead, uint8_t *dValid, DevCounters *dCtr, unsigned long long *dWork,
-                             void *dStacks, size_t stackBytes, int numSms, cudaStream_t stream) {
+                             void *dStacks, size_t stackBytes, int numSms, cudaStream_t stream, bool zeroed) {
     if (n == 0) return cudaSuccess;
-    cudaError_t err = cudaMemsetAsync(dWork, 0, 16 * sizeof(unsigned long long), stream);
-    if (err != cudaSuccess) return err;
-    err = cudaMemsetAsync(dDead, 0, sizeof(unsigned) * n, stream);
-    if (err != cudaSuccess) return err;
+    cudaError_t err = cudaSuccess;
+    if (!zeroed) {   // (small host calls zero their one control block -- counters, work counters, dead flags -- at once)
+        err = cudaMemsetAsync(dWork, 0, 16 * sizeof(unsigned long long), stream);
+        if (err != cudaSuccess) return err;
+        err = cudaMemsetAsync(dDead, 0, sizeof(unsigned) * n, stream);
+        if (err != cudaSuccess) return err;
+    }
     err = sc.wide ? launchEdgesT<unsigned long long>(sc, dFrom, dTo, dSteps, n, dDead, dCtr, dWork, (uint4 *)dStacks, stackBytes, numSms, stream)
                   : launchEdgesT<unsigned>(sc, dFrom, dTo, dSteps, n, dDead, dCtr, dWork, (uint4 *)dStacks, stackBytes, numSms, stream);
     if (err != cudaSuccess) return err;
-    deadToValidKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dDead, n, dValid);
+    if (dValid) deadToValidKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dDead, n, dValid);   // null: the caller reads dDead
     return cudaGetLastError();
 }
 
