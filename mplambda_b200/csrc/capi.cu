@@ -53,7 +53,7 @@ constexpr size_t kStageBytes = 160 * 1024;                 // inputs of a small 
 constexpr size_t kCtlHeader = ((sizeof(DevCounters) + 127) / 128) * 128 + 128;   // counters, then 16 work counters
 constexpr size_t kCtlTail = 8 * 1024;                      // verdicts (1 B/state) or dead flags (4 B/edge)
 constexpr size_t kSmallStates = 2048, kSmallEdges = 1024;
-static_assert(kSmallStates * 56 <= kStageBytes && kSmallEdges * 116 <= kStageBytes, "staging too small");
+static_assert(kSmallStates * 56 <= kStageBytes && kSmallEdges * (116 + 40) + 8 <= kStageBytes, "staging too small");
 static_assert(kSmallStates <= kCtlTail && kSmallEdges * 4 <= kCtlTail, "control block too small");
 
 CallCtx::~CallCtx() {
@@ -396,9 +396,9 @@ static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, siz
         MPLB_CUDA(cudaMemcpyAsync(in, c->hStage, 2 * sb + n * 4, cudaMemcpyHostToDevice, c->stream));
         MPLB_CUDA(launchCheckEdges(sc->dev, (const double *)in, (const double *)(in + sb), (const unsigned *)(in + 2 * sb), n,
                                    (unsigned *)(ctl + kCtlHeader), nullptr, (DevCounters *)ctl,
-                                   (unsigned long long *)(ctl + kCtlHeader - 128), c->aux0.ptr, stackBytes, sc->numSms,
-                                   c->stream, true));
-        sc->hLaunches += 3;
+                                   (unsigned long long *)(ctl + kCtlHeader - 128), c->aux0.ptr, stackBytes,
+                                   (double *)(in + ((2 * sb + n * 4 + 7) & ~(size_t)7)), sc->numSms, c->stream, true));
+        sc->hLaunches += 4;   // per-edge constants + three passes
         MPLB_CUDA(cudaMemcpyAsync(c->hCtl, ctl, kCtlHeader + n * 4, cudaMemcpyDeviceToHost, c->stream));
         MPLB_CUDA(cudaStreamSynchronize(c->stream));
         const unsigned *dead = (const unsigned *)(c->hCtl + kCtlHeader);
@@ -409,7 +409,8 @@ static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, siz
         return rc;
     }
     if ((rc = c->in0.reserve(sb)) || (rc = c->in1.reserve(sb)) || (rc = c->steps.reserve(n * 4)) ||
-        (rc = c->dead.reserve(n * 4)) || (rc = c->out.reserve(n)) || (rc = c->aux0.reserve(stackBytes)))
+        (rc = c->dead.reserve(n * 4)) || (rc = c->out.reserve(n)) || (rc = c->aux0.reserve(stackBytes)) ||
+        (rc = c->aux1.reserve(edgeConstBytes(n))))
         return rc;
     MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(DevCounters), c->stream));
     MPLB_CUDA(cudaMemcpyAsync(c->in0.ptr, from, sb, cudaMemcpyHostToDevice, c->stream));
@@ -418,8 +419,8 @@ static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, siz
     MPLB_CUDA(launchCheckEdges(sc->dev, (const double *)c->in0.ptr, (const double *)c->in1.ptr,
                                (const unsigned *)c->steps.ptr, n, (unsigned *)c->dead.ptr, (uint8_t *)c->out.ptr,
                                (DevCounters *)c->ctr.ptr, (unsigned long long *)c->work.ptr, c->aux0.ptr, stackBytes,
-                               sc->numSms, c->stream));
-    sc->hLaunches += 4;   // three passes + the verdict kernel
+                               (double *)c->aux1.ptr, sc->numSms, c->stream));
+    sc->hLaunches += 5;   // per-edge constants, three passes, the verdict kernel
     MPLB_CUDA(cudaMemcpyAsync(valid, c->out.ptr, n, cudaMemcpyDeviceToHost, c->stream));
     const double tEnq = sinceMs();
     rc = finishCall(sc, c, 0, statesChecked);
@@ -563,12 +564,14 @@ int mplb_check_edges_device(mplb_scene *scene, const double *d_from, const doubl
         int rc = s->globalDead.reserve(n * 4);
         if (rc != MPLB_OK) return rc;
         if ((rc = s->globalStacks.reserve(edgeStackBytes(s->numSms))) != MPLB_OK) return rc;
+        if ((rc = s->globalEdgeConst.reserve(edgeConstBytes(n))) != MPLB_OK) return rc;
     }
     (void)max_steps;
     MPLB_CUDA(launchCheckEdges(s->dev, d_from, d_to, d_steps, n, (unsigned *)s->globalDead.ptr, d_valid,
                                (DevCounters *)s->globalCtr.ptr, (unsigned long long *)s->globalWork.ptr,
-                               s->globalStacks.ptr, edgeStackBytes(s->numSms), s->numSms, (cudaStream_t)stream));
-    s->hLaunches += 4;
+                               s->globalStacks.ptr, edgeStackBytes(s->numSms), (double *)s->globalEdgeConst.ptr, s->numSms,
+                               (cudaStream_t)stream));
+    s->hLaunches += 5;
     return MPLB_OK;
 }
 

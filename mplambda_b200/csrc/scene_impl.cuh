@@ -47,7 +47,7 @@ struct SceneBase {
     int stateDim = 0;
     std::mutex mu;
     std::vector<CallCtx *> freeCtx;
-    DevBuf globalCtr, globalWork, globalDead, globalStacks;  // used by the *_device entry points
+    DevBuf globalCtr, globalWork, globalDead, globalStacks, globalEdgeConst;  // used by the *_device entry points
     std::atomic<uint64_t> hChecks{0}, hBv{0}, hTri{0}, hExact{0}, hLaunches{0};
     size_t envNodeCount = 0, robotNodeCount = 0;
 

@@ -49,7 +49,10 @@ size_t edgeStackBytes(int numSms);
 
 cudaError_t launchCheckEdges(const SceneDev &sc, const double *dFrom, const double *dTo, const unsigned *dSteps,
                              size_t n, unsigned *dDead, uint8_t *dValid, DevCounters *dCtr, unsigned long long *dWork,
-                             void *dStacks, size_t stackBytes, int numSms, cudaStream_t stream, bool zeroed = false);
+                             void *dStacks, size_t stackBytes, double *dEdgeConst, int numSms, cudaStream_t stream,
+                             bool zeroed = false);
+// dEdgeConst: edgeConstBytes(n) of scratch for the per-edge interpolation constants
+size_t edgeConstBytes(size_t n);
 // zeroed: dWork (16 counters) and dDead are already zero.  dValid == nullptr: leave the verdicts as dDead flags.
 
 }  // namespace mplb

@@ -154,16 +154,19 @@ __device__ __noinline__ bool triTriExact(const double *P, const double *Q, const
 }
 
 // interpolate.hpp:18-36 with Eigen's slerp; same statements as orc_se3_interpolate.  sin/acos are
-// CUDA's FP64 libdevice (<= 2 ulp from glibc's, see DESIGN.md "numerics").
-__device__ void interpolateD(const double *from, const double *to, double t, double out[7]) {
-    double d = dadd(dadd(dadd(dmul(from[0], to[0]), dmul(from[1], to[1])), dmul(from[2], to[2])),
-                    dmul(from[3], to[3]));
-    double absD = fabs(d), s0, s1;
-    if (absD >= 1.0 - DBL_EPSILON) {
+// CUDA's FP64 libdevice (<= 2 ulp from glibc's, see DESIGN.md "numerics").  What depends on the edge only
+// (d, theta = acos|d|, sin theta; and the two terms of the interval motion bound) is computed once per
+// edge by edgeConstKernel -- the same operations, hoisted: the per-sample conversion is the code every
+// warp of checkEdgesKernel keeps coming back to, and that kernel is bound by instruction fetch.
+constexpr int kEdgeConst = 5;   // doubles per edge: d, theta (< 0: linear blend), sin theta, motion per unit reach, scale term
+
+__device__ __forceinline__ void interpolateWith(const double *from, const double *to, double t, double d, double theta,
+                                                double sinTheta, double out[7]) {
+    double s0, s1;
+    if (theta < 0) {
         s0 = dsub(1.0, t);
         s1 = t;
     } else {
-        double theta = acos(absD), sinTheta = sin(theta);
         s0 = __ddiv_rn(sin(dmul(dsub(1.0, t), theta)), sinTheta);
         s1 = __ddiv_rn(sin(dmul(t, theta)), sinTheta);
     }
@@ -172,6 +175,41 @@ __device__ void interpolateD(const double *from, const double *to, double t, dou
     for (int i = 0; i < 4; ++i) out[i] = dadd(dmul(s0, from[i]), dmul(s1, to[i]));
 #pragma unroll
     for (int i = 4; i < 7; ++i) out[i] = dadd(from[i], dmul(dsub(to[i], from[i]), t));
+}
+
+__global__ void edgeConstKernel(const double *__restrict__ from, const double *__restrict__ to, unsigned long long n,
+                                float robotRadius, double *__restrict__ out) {
+    const unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const double *a = from + 7 * e, *b = to + 7 * e;
+    const double d = dadd(dadd(dadd(dmul(a[0], b[0]), dmul(a[1], b[1])), dmul(a[2], b[2])), dmul(a[3], b[3]));
+    const double absD = fabs(d);
+    double theta = -1.0, sinTheta = 0.0;
+    if (!(absD >= 1.0 - DBL_EPSILON)) {
+        theta = acos(absD);
+        sinTheta = sin(theta);
+    }
+    // Motion bound (EdgeSource::load): translation is a lerp and Eigen's slerp turns at constant rate, so over a
+    // fraction `reach` of the edge a robot point x moves at most reach * (||dt|| + 2 theta |x|)
+    double na = 0, nb = 0, dt2 = 0;
+    for (int k = 0; k < 4; ++k) {
+        na += a[k] * a[k];
+        nb += b[k] * b[k];
+    }
+    for (int k = 4; k < 7; ++k) {
+        const double x = b[k] - a[k];
+        dt2 += x * x;
+    }
+    // rotation matrices of non-unit quaternions scale: the bound assumes rigid motion
+    const double scale = fmax(1.0, fmax(na, nb));
+    const double thetaM = acos(fmin(1.0, absD / sqrt(na * nb)));
+    const double R = (double)robotRadius * scale;
+    double *o = out + kEdgeConst * e;
+    o[0] = d;
+    o[1] = theta;
+    o[2] = sinTheta;
+    o[3] = sqrt(dt2) + 2.0 * thetaM * R;
+    o[4] = fabs(scale - 1.0) * 4.0 * R * 1.000001 + 1e-6 * R;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -456,6 +494,7 @@ struct StateSource {
 struct EdgeSource {
     static constexpr bool kIntervals = true;   // slots may stand for a whole interval of samples
     const double *from, *to;
+    const double *edgeConst;   // kEdgeConst doubles per edge (edgeConstKernel)
     const unsigned *steps;
     unsigned long long nEdges;
     unsigned grab;
@@ -608,14 +647,14 @@ struct EdgeSource {
             for (int k = 0; k < 7; ++k) s[k] = __ldg(b + k);
             return;
         }
-        const double *a = from + 7 * (size_t)e;
+        const double *a = from + 7 * (size_t)e, *c = edgeConst + kEdgeConst * (size_t)e;
         double fa[7], fb[7];
 #pragma unroll
         for (int k = 0; k < 7; ++k) {
             fa[k] = __ldg(a + k);
             fb[k] = __ldg(b + k);
         }
-        interpolateD(fa, fb, dmul((double)i, __ddiv_rn(1.0, (double)st)), s);
+        interpolateWith(fa, fb, dmul((double)i, __ddiv_rn(1.0, (double)st)), __ldg(c), __ldg(c + 1), __ldg(c + 2), s);
     }
     template <typename SM>
     __device__ bool load(int rank, double s[7], unsigned t[4], float &extraSlack, const SM &sm) const {
@@ -627,29 +666,9 @@ struct EdgeSource {
         sampleState(e, mid, st, s);
         extraSlack = 0.f;
         if (hi > lo) {
-            const double *a = from + 7 * (size_t)e, *b = to + 7 * (size_t)e;
-            double qa[4], qb[4], d = 0, na = 0, nb = 0, dt2 = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                qa[k] = __ldg(a + k);
-                qb[k] = __ldg(b + k);
-                d += qa[k] * qb[k];
-                na += qa[k] * qa[k];
-                nb += qb[k] * qb[k];
-            }
-#pragma unroll
-            for (int k = 4; k < 7; ++k) {
-                const double x = __ldg(b + k) - __ldg(a + k);
-                dt2 += x * x;
-            }
-            // rotation matrices of non-unit quaternions scale: the bound below assumes rigid motion
-            const double scale = fmax(1.0, fmax(na, nb));
-            const double theta = acos(fmin(1.0, fabs(d) / sqrt(na * nb)));
+            const double *c = edgeConst + kEdgeConst * (size_t)e;
             const double reach = (double)max(hi - mid, mid - lo) / (double)st;
-            const double R = (double)robotRadius * scale;
-            double D = reach * (sqrt(dt2) + 2.0 * theta * R) + fabs(scale - 1.0) * 4.0 * R;
-            D = D * 1.000001 + 1e-6 * R;
-            extraSlack = __double2float_ru(D);
+            extraSlack = __double2float_ru((reach * __ldg(c + 3)) * 1.000001 + __ldg(c + 4));
         }
         t[0] = e; t[1] = mid; t[2] = lo; t[3] = hi;
         return true;
@@ -1018,8 +1037,27 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
                 const float4 y0 = descendA ? make_float4(x0.x, x1.x, x2.x, -fmaf(x0.x, x0.w, fmaf(x1.x, x1.w, x2.x * x2.w))) : x0;
                 const float4 y1 = descendA ? make_float4(x0.y, x1.y, x2.y, -fmaf(x0.y, x0.w, fmaf(x1.y, x1.w, x2.y * x2.w))) : x1;
                 const float4 y2 = descendA ? make_float4(x0.z, x1.z, x2.z, -fmaf(x0.z, x0.w, fmaf(x1.z, x1.w, x2.z * x2.w))) : x2;
-                const float g0 = obbGap(f0, f1, f2, fe, c00, c01, c02, c0e, y0, y1, y2, d0);
-                const float g1 = obbGap(f0, f1, f2, fe, c10, c11, c12, c1e, y0, y1, y2, d1);
+                float g0 = 0.f, g1 = 0.f;
+                if constexpr (Source::kIntervals) {
+                    // one copy of the ~200-instruction test, run twice: checkEdgesKernel is bound by instruction
+                    // fetch (ncu: stall_no_inst; its warps alternate between this loop and the FP64 sample
+                    // conversion), not by the dependent FMA chains the two inlined copies overlap (+9 %)
+                    float4 b0 = c00, b1 = c01, b2 = c02, be = c0e;
+#pragma unroll 1
+                    for (int k = 0; k < 2; ++k) {
+                        float dd;
+                        const float g = obbGap(f0, f1, f2, fe, b0, b1, b2, be, y0, y1, y2, dd);
+                        if (k == 0) {
+                            g0 = g; d0 = dd;
+                            b0 = c10; b1 = c11; b2 = c12; be = c1e;
+                        } else {
+                            g1 = g; d1 = dd;
+                        }
+                    }
+                } else {
+                    g0 = obbGap(f0, f1, f2, fe, c00, c01, c02, c0e, y0, y1, y2, d0);
+                    g1 = obbGap(f0, f1, f2, fe, c10, c11, c12, c1e, y0, y1, y2, d1);
+                }
                 ov0 = g0 <= x3.x;   // within reach (plain slack, or inflated for an interval certificate)
                 ov1 = g1 <= x3.x;
                 if constexpr (Source::kIntervals) {
@@ -1157,14 +1195,16 @@ checkStatesKernel(SceneDev sc, const double *states, unsigned long long n, uint8
 template <typename E>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MPLB_MIN_CTAS)
 checkEdgesKernel(SceneDev sc, const double *__restrict__ from, const double *__restrict__ to,
-                 const unsigned *__restrict__ steps, unsigned long long nEdges, unsigned grab, unsigned *dead,
+                 const double *__restrict__ edgeConst, const unsigned *__restrict__ steps, unsigned long long nEdges,
+                 unsigned grab, unsigned *dead,
                  uint4 *stacks, unsigned stackCap, DevCounters *ctr, unsigned long long *workCounter,
                  const uint4 *descIn, const unsigned long long *descCount, uint4 *spillOut,
                  unsigned long long *spillCount, unsigned spillCap) {
     if (descIn && *descCount == 0) return;   // nothing was spilled by the previous pass
     WarpSmem<E> sm = warpSmem<E>(sc.stackLevels);
     EdgeSource src;
-    src.from = from; src.to = to; src.steps = steps; src.nEdges = nEdges; src.grab = grab; src.dead = dead;
+    src.from = from; src.to = to; src.edgeConst = edgeConst; src.steps = steps; src.nEdges = nEdges; src.grab = grab;
+    src.dead = dead;
     src.crew = 2ull * gridDim.x * kWarpsPerCta;
     src.counter = workCounter;
     src.descIn = descIn;
@@ -1256,8 +1296,8 @@ constexpr unsigned kSpillCap = 1u << 18;   // descriptors one pass can hand to t
 constexpr int kMaxCtasPerSm = 3;
 
 template <typename E>
-cudaError_t launchEdgesT(const SceneDev &sc, const double *dFrom, const double *dTo, const unsigned *dSteps, size_t n,
-                         unsigned *dDead, DevCounters *dCtr, unsigned long long *dWork, uint4 *dStacks,
+cudaError_t launchEdgesT(const SceneDev &sc, const double *dFrom, const double *dTo, const double *dEdgeConst,
+                         const unsigned *dSteps, size_t n, unsigned *dDead, DevCounters *dCtr, unsigned long long *dWork, uint4 *dStacks,
                          size_t stackBytes, int numSms, cudaStream_t stream) {
     auto k = checkEdgesKernel<E>;
     const size_t smem = smemBytes<E>(sc);
@@ -1278,7 +1318,7 @@ cudaError_t launchEdgesT(const SceneDev &sc, const double *dFrom, const double *
     const int threads = kWarpsPerCta * 32;
     for (int p = 0; p < kEdgePasses; ++p) {
         const bool last = p == kEdgePasses - 1;
-        k<<<grid, threads, smem, stream>>>(sc, dFrom, dTo, dSteps, n, grab, dDead, dStacks, kEdgeStackCap, dCtr, dWork + p,
+        k<<<grid, threads, smem, stream>>>(sc, dFrom, dTo, dEdgeConst, dSteps, n, grab, dDead, dStacks, kEdgeStackCap, dCtr, dWork + p,
                                            p ? spill[(p - 1) & 1] : nullptr, p ? dWork + 8 + (p - 1) : nullptr,
                                            last ? nullptr : spill[p & 1], last ? nullptr : dWork + 8 + p, kSpillCap);
     }
@@ -1301,9 +1341,12 @@ size_t edgeStackBytes(int numSms) {
     return (size_t)numSms * kMaxCtasPerSm * kWarpsPerCta * kEdgeStackCap * sizeof(uint4) + 2 * (size_t)kSpillCap * sizeof(uint4);
 }
 
+size_t edgeConstBytes(size_t n) { return n * kEdgeConst * sizeof(double); }
+
 cudaError_t launchCheckEdges(const SceneDev &sc, const double *dFrom, const double *dTo, const unsigned *dSteps,
                              size_t n, unsigned *dDead, uint8_t *dValid, DevCounters *dCtr, unsigned long long *dWork,
-                             void *dStacks, size_t stackBytes, int numSms, cudaStream_t stream, bool zeroed) {
+                             void *dStacks, size_t stackBytes, double *dEdgeConst, int numSms, cudaStream_t stream,
+                             bool zeroed) {
     if (n == 0) return cudaSuccess;
     cudaError_t err = cudaSuccess;
     if (!zeroed) {   // (small host calls zero their one control block -- counters, work counters, dead flags -- at once)
@@ -1312,8 +1355,9 @@ cudaError_t launchCheckEdges(const SceneDev &sc, const double *dFrom, const doub
         err = cudaMemsetAsync(dDead, 0, sizeof(unsigned) * n, stream);
         if (err != cudaSuccess) return err;
     }
-    err = sc.wide ? launchEdgesT<unsigned long long>(sc, dFrom, dTo, dSteps, n, dDead, dCtr, dWork, (uint4 *)dStacks, stackBytes, numSms, stream)
-                  : launchEdgesT<unsigned>(sc, dFrom, dTo, dSteps, n, dDead, dCtr, dWork, (uint4 *)dStacks, stackBytes, numSms, stream);
+    edgeConstKernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(dFrom, dTo, n, sc.robotRadius, dEdgeConst);
+    err = sc.wide ? launchEdgesT<unsigned long long>(sc, dFrom, dTo, dEdgeConst, dSteps, n, dDead, dCtr, dWork, (uint4 *)dStacks, stackBytes, numSms, stream)
+                  : launchEdgesT<unsigned>(sc, dFrom, dTo, dEdgeConst, dSteps, n, dDead, dCtr, dWork, (uint4 *)dStacks, stackBytes, numSms, stream);
     if (err != cudaSuccess) return err;
     if (dValid) deadToValidKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dDead, n, dValid);   // null: the caller reads dDead
     return cudaGetLastError();
