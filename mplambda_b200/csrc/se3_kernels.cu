@@ -520,6 +520,7 @@ struct EdgeSource {
     // current grab of items and the live ones among them
     unsigned long long first = 0;
     unsigned liveMask = 0;
+    unsigned laneEdge = 0, lanePhase = 0, laneSteps = 0;   // this lane's item of the current grab
     // current item
     bool have = false;
     unsigned curEdge = 0, curPhase = 0, curBits = 0, curSteps = 0, pos = 0;
@@ -528,21 +529,21 @@ struct EdgeSource {
 
     // item space: [0, nEdges) phase A of edge e; then kPhaseBSub sub-items per edge, sub-item major (so that
     // neighbouring items are different edges), each covering 64 / kPhaseBSub of the edge's 64 gaps
+    // One 64-bit division per grab, none per item, no dependent global loads per item: lane l of the grab holds
+    // item first + l (its edge, phase and step count) and the warp walks the live ones by shuffle.
     __device__ bool nextItem(unsigned lane) {
         const unsigned long long nItems = (1 + kPhaseBSub) * nEdges;
         for (;;) {
-            while (liveMask) {
+            if (liveMask) {
                 const int src = __ffs(liveMask) - 1;
                 liveMask &= liveMask - 1;
-                const unsigned long long it = first + src;
-                curEdge = (unsigned)(it % nEdges);
-                curPhase = (unsigned)(it / nEdges);   // 0: phase A, 1 + sub: phase B sub-item
-                if (((volatile unsigned *)dead)[curEdge]) continue;
-                curSteps = __ldg(steps + curEdge);
+                curEdge = __shfl_sync(kFull, laneEdge, src);
+                curPhase = __shfl_sync(kFull, lanePhase, src);   // 0: phase A, 1 + sub: phase B sub-item
+                curSteps = __shfl_sync(kFull, laneSteps, src);
                 curBits = curSteps ? 32 - __clz(curSteps) : 0;
                 pos = 0;
                 have = true;
-                return true;
+                return true;   // (an edge that died since the grab is dropped when its descriptors are loaded)
             }
             if (globalDone) return false;
             unsigned long long f = 0;
@@ -553,14 +554,30 @@ struct EdgeSource {
                 return false;
             }
             first = f;
-            bool live = false;
-            const unsigned long long item = f + lane;
-            if (lane < grab && item < nItems) {
-                const unsigned long long e = item % nEdges;
-                const unsigned st = __ldg(steps + e);
-                const unsigned bits = st ? 32 - __clz(st) : 0;
-                live = !((volatile unsigned *)dead)[e] && (item < nEdges || bits > 6);  // phase B only if gaps exist
+            unsigned long long e;
+            unsigned ph;
+            if ((nItems >> 32) == 0) {
+                ph = (unsigned)f / (unsigned)nEdges;
+                e = (unsigned)f - ph * (unsigned)nEdges;
+            } else {
+                ph = (unsigned)(f / nEdges);
+                e = f % nEdges;
             }
+            e += lane;
+            while (e >= nEdges) {   // the grab runs into the next phase (lane < 32: more than once only for tiny batches)
+                e -= nEdges;
+                ++ph;
+            }
+            bool live = false;
+            unsigned st = 0;
+            if (lane < grab && f + lane < nItems) {
+                st = __ldg(steps + e);
+                const unsigned bits = st ? 32 - __clz(st) : 0;
+                live = !((volatile unsigned *)dead)[e] && (ph == 0 || bits > 6);  // phase B only if gaps exist
+            }
+            laneEdge = (unsigned)e;
+            lanePhase = ph;
+            laneSteps = st;
             liveMask = __ballot_sync(kFull, live);
         }
     }
