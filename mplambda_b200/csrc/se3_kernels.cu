@@ -296,7 +296,6 @@ __device__ __forceinline__ int triTriFilter(F3 p2, F3 p3, F3 q1, F3 f1, F3 f2, f
 
 // ---------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ unsigned bitrev(unsigned j, int bits) { return bits ? (__brev(j) >> (32 - bits)) : 0u; }
 
 template <typename E>
 struct Codec {
@@ -478,17 +477,15 @@ struct StateSource {
 };
 
 // isValid(from,to) over an array of edges (se3...:134-178): verdict = valid(to) AND every interpolated
-// sample i in [1, steps-1] at t = i * (1/steps).  The samples are not enumerated one by one:
-//   phase A (item e):          `to` and the 63 coarsest samples (multiples of 2^(L-6), 2^L > steps) are
-//                              tested exactly; most invalid edges die here.
-//   phase B (item nEdges + e): each gap between two coarse samples is an INTERVAL [lo, hi].  One
-//                              traversal at its middle sample, with every box test inflated by the largest
-//                              displacement any robot point can have over the interval, either certifies all
-//                              of its samples free at once (no leaf pair came within reach), or tests the
-//                              middle sample exactly and hands the two halves back to the warp's interval
-//                              LIFO.  A sample is the middle of exactly one interval, so the worst case is
-//                              one traversal per sample (as plain enumeration) and the free-space case is
-//                              ~64 traversals per edge.  The verdict is the reference's discrete one.
+// sample i in [1, steps-1] at t = i * (1/steps).  The samples are not enumerated one by one.  Per edge there
+// are 1 + 64 items: `to` itself, and the 64 equal INTERVALS [lo, hi] the samples [1, steps-1] are cut into
+// (handed out in bit-reversed order, so the first ones spread over the edge and most invalid edges die
+// early).  One traversal at an interval's middle sample, with every box test inflated by the largest
+// displacement any robot point can have over the interval, either certifies all of its samples free at once
+// (no leaf pair came within reach), or tests the middle sample exactly and hands the pieces left and right
+// of it back (to the warp's interval LIFO, or to the next pass).  A sample is the middle of exactly one
+// interval, so the worst case is one traversal per sample (as plain enumeration) and the free-space case is
+// 65 traversals per edge.  The verdict is the reference's discrete one.
 // Motion bound: translation is a lerp and Eigen's slerp turns at constant rate, so between samples i and m
 // a robot point x moves at most |i-m|/steps * (||dt|| + 2 theta |x|), theta = acos|qa.qb|.
 struct EdgeSource {
@@ -497,7 +494,6 @@ struct EdgeSource {
     const double *edgeConst;   // kEdgeConst doubles per edge (edgeConstKernel)
     const unsigned *steps;
     unsigned long long nEdges;
-    unsigned grab;
     unsigned long long crew = 1;   // warps in the grid x 2 (guided hand-out)
     unsigned *dead;
     unsigned long long *counter;
@@ -517,70 +513,10 @@ struct EdgeSource {
     bool globalDone = false;
     bool poolDry = false;   // the item counter has run past the last item (other warps may still hold work)
     unsigned stackCount = 0;
-    // current grab of items and the live ones among them
-    unsigned long long first = 0;
-    unsigned liveMask = 0;
-    unsigned laneEdge = 0, lanePhase = 0, laneSteps = 0;   // this lane's item of the current grab
-    // current item
-    bool have = false;
-    unsigned curEdge = 0, curPhase = 0, curBits = 0, curSteps = 0, pos = 0;
+    unsigned long long first = 0;   // item counter as of this warp's previous grab (guided share)
 
     __device__ bool done() const { return globalDone && stackCount == 0; }
 
-    // item space: [0, nEdges) phase A of edge e; then kPhaseBSub sub-items per edge, sub-item major (so that
-    // neighbouring items are different edges), each covering 64 / kPhaseBSub of the edge's 64 gaps
-    // One 64-bit division per grab, none per item, no dependent global loads per item: lane l of the grab holds
-    // item first + l (its edge, phase and step count) and the warp walks the live ones by shuffle.
-    __device__ bool nextItem(unsigned lane) {
-        const unsigned long long nItems = (1 + kPhaseBSub) * nEdges;
-        for (;;) {
-            if (liveMask) {
-                const int src = __ffs(liveMask) - 1;
-                liveMask &= liveMask - 1;
-                curEdge = __shfl_sync(kFull, laneEdge, src);
-                curPhase = __shfl_sync(kFull, lanePhase, src);   // 0: phase A, 1 + sub: phase B sub-item
-                curSteps = __shfl_sync(kFull, laneSteps, src);
-                curBits = curSteps ? 32 - __clz(curSteps) : 0;
-                pos = 0;
-                have = true;
-                return true;   // (an edge that died since the grab is dropped when its descriptors are loaded)
-            }
-            if (globalDone) return false;
-            unsigned long long f = 0;
-            if (lane == 0) f = atomicAdd(counter, (unsigned long long)grab);
-            f = __shfl_sync(kFull, f, 0);
-            if (f >= nItems) {
-                globalDone = true;
-                return false;
-            }
-            first = f;
-            unsigned long long e;
-            unsigned ph;
-            if ((nItems >> 32) == 0) {
-                ph = (unsigned)f / (unsigned)nEdges;
-                e = (unsigned)f - ph * (unsigned)nEdges;
-            } else {
-                ph = (unsigned)(f / nEdges);
-                e = f % nEdges;
-            }
-            e += lane;
-            while (e >= nEdges) {   // the grab runs into the next phase (lane < 32: more than once only for tiny batches)
-                e -= nEdges;
-                ++ph;
-            }
-            bool live = false;
-            unsigned st = 0;
-            if (lane < grab && f + lane < nItems) {
-                st = __ldg(steps + e);
-                const unsigned bits = st ? 32 - __clz(st) : 0;
-                live = !((volatile unsigned *)dead)[e] && (ph == 0 || bits > 6);  // phase B only if gaps exist
-            }
-            laneEdge = (unsigned)e;
-            lanePhase = ph;
-            laneSteps = st;
-            liveMask = __ballot_sync(kFull, live);
-        }
-    }
     // Up to `want` pieces of work as (edge, lo, hi) descriptors in sm.work[]: halves of intervals that could
     // not be certified first (depth first, keeps the LIFO short), topped up from as many items as it takes,
     // so that the FP64 state expansion runs on full warps.
@@ -617,41 +553,50 @@ struct EdgeSource {
             __syncwarp();
             return count;
         }
-        while (count < want) {
-            if (!have && (count >= share || !nextItem(lane))) break;
-            const unsigned span = curPhase == 0 ? 64u : 64u / kPhaseBSub;
-            if (pos >= span) {
-                have = false;
-                continue;
+        // implicit items: item f = (phase f / nEdges, edge f % nEdges), edge-minor so that neighbouring items are
+        // different edges.  Each lane turns one item into its descriptor: one division per grab, none per item.
+        for (int tries = 0; tries < 4 && count < share && !globalDone; ++tries) {
+            const int take = min(want, share) - count;
+            unsigned long long f = 0;
+            if (lane == 0) f = atomicAdd(counter, (unsigned long long)take);
+            f = __shfl_sync(kFull, f, 0);
+            if (f >= nItems) {
+                globalDone = poolDry = true;
+                break;
             }
-            bool ok;
+            first = f + take;
+            unsigned long long e;
+            unsigned ph;
+            if ((nItems >> 32) == 0) {
+                ph = (unsigned)f / (unsigned)nEdges;
+                e = (unsigned)f - ph * (unsigned)nEdges;
+            } else {
+                ph = (unsigned)(f / nEdges);
+                e = f % nEdges;
+            }
+            e += lane;
+            while (e >= nEdges) {   // the grab runs into the next phase (lane < 32: more than once only for tiny batches)
+                e -= nEdges;
+                ++ph;
+            }
+            bool ok = false;
             unsigned lo = 0, hi = 0;
-            const unsigned c = pos + lane;
-            if (curPhase == 0) {
-                ok = c < 64 && (c == 0 || (c < (1u << curBits) && bitrev(c, curBits) < curSteps));
-                lo = hi = c == 0 ? curSteps : bitrev(c, curBits);   // sample `steps` stands for `to`
-            } else {
-                const unsigned k = (curPhase - 1) * span + c, stride = 1u << (curBits - 6);
-                lo = k * stride + 1;
-                hi = min((k + 1) * stride - 1, curSteps - 1);
-                ok = c < span && lo <= hi;
+            if ((int)lane < take && f + lane < nItems && !((volatile unsigned *)dead)[e]) {
+                const unsigned st = __ldg(steps + e);
+                if (ph == 0) {   // sample `steps` stands for `to`
+                    lo = hi = st;
+                    ok = true;
+                } else {
+                    const unsigned long long m = st ? st - 1 : 0;   // samples 1 .. m
+                    const unsigned k = __brev(ph - 1) >> 26;         // 6-bit reversal: 0, 32, 16, 48, ...
+                    lo = 1u + (unsigned)((k * m) >> 6);
+                    hi = (unsigned)(((k + 1) * m) >> 6);
+                    ok = lo <= hi;
+                }
             }
-            unsigned m = __ballot_sync(kFull, ok);
-            const int avail = __popc(m);
-            if (avail == 0) {
-                pos += 32;
-                continue;
-            }
-            const int room = want - count;
-            if (avail > room) {
-                const unsigned cut = __fns(m, 0, room + 1);  // first candidate NOT taken
-                m &= (1u << cut) - 1u;
-                pos += cut;
-            } else {
-                pos += 32;
-            }
-            if ((m >> lane) & 1u) sm.work[count + __popc(m & ((1u << lane) - 1u))] = make_uint4(curEdge, lo, hi, 0);
-            count += __popc(m);
+            const unsigned mk = __ballot_sync(kFull, ok);
+            if (ok) sm.work[count + __popc(mk & ((1u << lane) - 1u))] = make_uint4((unsigned)e, lo, hi, 0);
+            count += __popc(mk);
         }
         __syncwarp();
         return count;
@@ -780,7 +725,6 @@ struct EdgeSource {
                 fresh.hi &= fresh.hi - 1;
             }
             const unsigned e = sm.tag0[s];
-            if (have && curEdge == e) have = false;
             if (lane == 0) dead[e] = 1u;
             const bool k0 = inUse.test(lane) && sm.tag0[lane] == e;
             const bool k1 = inUse.test(lane + 32) && sm.tag0[lane + 32] == e;
@@ -1213,14 +1157,14 @@ template <typename E>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MPLB_MIN_CTAS)
 checkEdgesKernel(SceneDev sc, const double *__restrict__ from, const double *__restrict__ to,
                  const double *__restrict__ edgeConst, const unsigned *__restrict__ steps, unsigned long long nEdges,
-                 unsigned grab, unsigned *dead,
+                 unsigned *dead,
                  uint4 *stacks, unsigned stackCap, DevCounters *ctr, unsigned long long *workCounter,
                  const uint4 *descIn, const unsigned long long *descCount, uint4 *spillOut,
                  unsigned long long *spillCount, unsigned spillCap) {
     if (descIn && *descCount == 0) return;   // nothing was spilled by the previous pass
     WarpSmem<E> sm = warpSmem<E>(sc.stackLevels);
     EdgeSource src;
-    src.from = from; src.to = to; src.edgeConst = edgeConst; src.steps = steps; src.nEdges = nEdges; src.grab = grab;
+    src.from = from; src.to = to; src.edgeConst = edgeConst; src.steps = steps; src.nEdges = nEdges;
     src.dead = dead;
     src.crew = 2ull * gridDim.x * kWarpsPerCta;
     src.counter = workCounter;
@@ -1323,8 +1267,6 @@ cudaError_t launchEdgesT(const SceneDev &sc, const double *dFrom, const double *
     if (err != cudaSuccess) return err;
     grid = std::min(grid, kMaxCtasPerSm * numSms);
     const unsigned long long nItems = (1ull + kPhaseBSub) * n;   // phase A item + phase B sub-items per edge
-    const unsigned grab = (unsigned)std::min<unsigned long long>(
-        32, std::max<unsigned long long>(1, nItems / (4ull * grid * kWarpsPerCta)));
     grid = (int)std::min<unsigned long long>(grid, (nItems + kWarpsPerCta - 1) / kWarpsPerCta);
     grid = std::max(grid, 1);
     const size_t lifoBytes = (size_t)grid * kWarpsPerCta * kEdgeStackCap * sizeof(uint4);
@@ -1335,7 +1277,7 @@ cudaError_t launchEdgesT(const SceneDev &sc, const double *dFrom, const double *
     const int threads = kWarpsPerCta * 32;
     for (int p = 0; p < kEdgePasses; ++p) {
         const bool last = p == kEdgePasses - 1;
-        k<<<grid, threads, smem, stream>>>(sc, dFrom, dTo, dEdgeConst, dSteps, n, grab, dDead, dStacks, kEdgeStackCap, dCtr, dWork + p,
+        k<<<grid, threads, smem, stream>>>(sc, dFrom, dTo, dEdgeConst, dSteps, n, dDead, dStacks, kEdgeStackCap, dCtr, dWork + p,
                                            p ? spill[(p - 1) & 1] : nullptr, p ? dWork + 8 + (p - 1) : nullptr,
                                            last ? nullptr : spill[p & 1], last ? nullptr : dWork + 8 + p, kSpillCap);
     }
