@@ -44,7 +44,11 @@ namespace {
 constexpr int kWarpsPerCta = MPLB_WARPS_PER_CTA;
 constexpr int kSlots = 64;          // state slots per warp
 constexpr int kQueueCap = 96;       // leaf / exact queue entries per warp
-constexpr unsigned kPhaseBSub = 64;    // phase-B work items per edge (isValid(from,to), see EdgeSource)
+#ifndef MPLB_EDGE_INTERVAL_BITS
+#define MPLB_EDGE_INTERVAL_BITS 5
+#endif
+constexpr unsigned kIntervalBits = MPLB_EDGE_INTERVAL_BITS;
+constexpr unsigned kPhaseBSub = 1u << kIntervalBits;    // intervals an edge's samples are cut into (see EdgeSource)
 #ifndef MPLB_SPILL_KEEP
 #define MPLB_SPILL_KEEP 0
 #endif
@@ -588,9 +592,9 @@ struct EdgeSource {
                     ok = true;
                 } else {
                     const unsigned long long m = st ? st - 1 : 0;   // samples 1 .. m
-                    const unsigned k = __brev(ph - 1) >> 26;         // 6-bit reversal: 0, 32, 16, 48, ...
-                    lo = 1u + (unsigned)((k * m) >> 6);
-                    hi = (unsigned)(((k + 1) * m) >> 6);
+                    const unsigned k = __brev(ph - 1) >> (32 - kIntervalBits);   // bit reversal: 0, 32, 16, 48, ...
+                    lo = 1u + (unsigned)((k * m) >> kIntervalBits);
+                    hi = (unsigned)(((k + 1) * m) >> kIntervalBits);
                     ok = lo <= hi;
                 }
             }
@@ -1266,7 +1270,7 @@ cudaError_t launchEdgesT(const SceneDev &sc, const double *dFrom, const double *
     cudaError_t err = gridFor(k, smem, numSms, &grid);
     if (err != cudaSuccess) return err;
     grid = std::min(grid, kMaxCtasPerSm * numSms);
-    const unsigned long long nItems = (1ull + kPhaseBSub) * n;   // phase A item + phase B sub-items per edge
+    const unsigned long long nItems = (1ull + kPhaseBSub) * n;   // `to` + the intervals of every edge
     grid = (int)std::min<unsigned long long>(grid, (nItems + kWarpsPerCta - 1) / kWarpsPerCta);
     grid = std::max(grid, 1);
     const size_t lifoBytes = (size_t)grid * kWarpsPerCta * kEdgeStackCap * sizeof(uint4);
