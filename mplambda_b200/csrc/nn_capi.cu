@@ -68,7 +68,9 @@ static int nnSearch(mplb_nn *nn, const double *queries, bool deviceQueries, size
     int rc;
     if (slices > 1 && ((rc = nn->partDist.reserve(nq * slices * k * 8)) || (rc = nn->partIdx.reserve(nq * slices * k * 8))))
         return rc;
-    if ((rc = nn->partVal.reserve(nq * slices * k * 4)) || (rc = nn->thr.reserve(nq * 4))) return rc;
+    // k == 1: [nq][slices] bounds; k > 1: [nq][k] sample distances + [nq][8] counts + [nq] chosen levels
+    if ((rc = nn->partVal.reserve(std::max<size_t>(nq * slices * k * 4, nq * ((size_t)k + 9) * 4))) || (rc = nn->thr.reserve(nq * 4)))
+        return rc;
     const double *dQ = queries;
     double *dDist = dist;
     long long *dIdx = (long long *)idx;
@@ -88,8 +90,10 @@ static int nnSearch(mplb_nn *nn, const double *queries, bool deviceQueries, size
     if (deviceQueries) return MPLB_OK;
     MPLB_CUDA(cudaMemcpyAsync(idx, dIdx, nq * k * 8, cudaMemcpyDeviceToHost, st));
     MPLB_CUDA(cudaStreamSynchronize(st));
-    // distances as the CPU path would report them (host libm, same operation order)
-    for (size_t i = 0; i < nq; ++i)
+    // distances as the CPU path would report them (host libm, same operation order); nq x k acos/sqrt calls are
+    // milliseconds on one core, so large batches use all of them
+#pragma omp parallel for schedule(static) if (nq * (size_t)k >= 16384)
+    for (long long i = 0; i < (long long)nq; ++i)
         for (int r = 0; r < k; ++r) {
             const int64_t j = idx[i * k + r];
             dist[i * k + r] = j < 0 ? INFINITY : nn->distance(nn->hKeys.data() + (size_t)j * nn->dim, queries + i * nn->dim);

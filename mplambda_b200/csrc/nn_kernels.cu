@@ -18,7 +18,9 @@
 // path and the SE3 metric differs at most in acos' last bit; ties go to the lowest index.
 #include "nn_device.cuh"
 
+#include <algorithm>
 #include <cfloat>
+#include <cmath>
 
 namespace mplb {
 namespace {
@@ -85,7 +87,8 @@ __device__ __forceinline__ float nnMargin(int dim, int metric, float so3w, float
 __global__ void __launch_bounds__(kNnThreads)
 nnBound32Kernel(const float *__restrict__ keys32, unsigned long long n, int dim, int metric, float so3w, float l2w,
                 const double *__restrict__ queries, unsigned long long nq, int k, unsigned long long keysPerSlice,
-                float *__restrict__ outVal) {
+                unsigned long long stride, float *__restrict__ outVal) {
+    // stride > 1: the scan runs over the sample {0, stride, 2 stride, ...} of the keys (n counts the sample)
     __shared__ __align__(16) float tile[kNnTile * kNnMaxDim];
     const unsigned long long qi = blockIdx.x * (unsigned long long)kNnThreads + threadIdx.x;
     const bool haveQuery = qi < nq;
@@ -101,7 +104,12 @@ nnBound32Kernel(const float *__restrict__ keys32, unsigned long long n, int dim,
         const int tn = (int)min((unsigned long long)kNnTile, hi - t0);
         const int nd = tn * dim;
         __syncthreads();
-        for (int i = threadIdx.x; i < nd; i += kNnThreads) tile[i] = __ldg(keys32 + t0 * dim + i);
+        if (stride == 1) {
+            for (int i = threadIdx.x; i < nd; i += kNnThreads) tile[i] = __ldg(keys32 + t0 * dim + i);
+        } else {
+            for (int i = threadIdx.x; i < nd; i += kNnThreads)
+                tile[i] = __ldg(keys32 + (t0 + i / dim) * stride * dim + i % dim);
+        }
         __syncthreads();
         if (!haveQuery) continue;
         if (k == 1) {
@@ -131,17 +139,88 @@ nnBound32Kernel(const float *__restrict__ keys32, unsigned long long n, int dim,
         for (int r = 0; r < k; ++r) ov[r] = r < cnt ? best[r] : INFINITY;
 }
 
+// k > 1, pass 1b.  grid = (query blocks, slices).  Sorted insertion per key is what made the k-NN bound pass 17x
+// slower than the 1-NN one (a warp pays for an insertion whenever any of its lanes inserts), and the pass only has
+// to produce a threshold with at least k keys under it.  So: the k-th smallest distance T0 over a strided SAMPLE
+// of the keys (nnBound32Kernel, cheap) is such a threshold -- with about k n / m keys under it -- and this kernel
+// COUNTS, over all keys, how many lie under each of kNnLevels fractions of T0 (registers only); the smallest
+// level that still holds k keys becomes the threshold of pass 2.
+constexpr int kNnLevels = 8;
+constexpr int kNnCandCap = 128;   // candidates a thread notes before it works them off (more simply means another round)
+
+__global__ void __launch_bounds__(kNnThreads)
+nnCountKernel(const float *__restrict__ keys32, unsigned long long n, int dim, int metric, float so3w, float l2w,
+              const double *__restrict__ queries, unsigned long long nq, int k, unsigned long long keysPerSlice,
+              const float *__restrict__ sampleVal, float ratio, unsigned *__restrict__ counts) {
+    __shared__ __align__(16) float tile[kNnTile * kNnMaxDim];
+    const unsigned long long qi = blockIdx.x * (unsigned long long)kNnThreads + threadIdx.x;
+    const bool haveQuery = qi < nq;
+    float q[kNnMaxDim];
+#pragma unroll
+    for (int i = 0; i < kNnMaxDim; ++i) q[i] = (haveQuery && i < dim) ? (float)__ldg(queries + qi * dim + i) : 0.f;
+    const float t0v = haveQuery ? sampleVal[qi * k + (k - 1)] : -1.f;   // +inf: the sample held fewer than k keys
+    float lev[kNnLevels];
+    unsigned cnt[kNnLevels];
+    {
+        float f = 1.f;
+#pragma unroll
+        for (int j = kNnLevels - 1; j >= 0; --j) {
+            lev[j] = t0v * f;
+            cnt[j] = 0;
+            f *= ratio;
+        }
+    }
+    const unsigned long long lo = blockIdx.y * keysPerSlice;
+    const unsigned long long hi = min(n, lo + keysPerSlice);
+    for (unsigned long long t0 = lo; t0 < hi; t0 += kNnTile) {
+        const int tn = (int)min((unsigned long long)kNnTile, hi - t0);
+        const int nd = tn * dim;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nd; i += kNnThreads) tile[i] = __ldg(keys32 + t0 * dim + i);
+        __syncthreads();
+        if (!haveQuery || !(t0v < INFINITY)) continue;
+        for (int j = 0; j < tn; ++j) {
+            float d;
+            if (!nnWithin32(q, tile + j * dim, dim, metric, so3w, l2w, t0v, d)) continue;
+#pragma unroll
+            for (int l = 0; l < kNnLevels; ++l) cnt[l] += d <= lev[l] ? 1u : 0u;
+        }
+    }
+    if (!haveQuery) return;
+#pragma unroll
+    for (int l = 0; l < kNnLevels; ++l)
+        if (cnt[l]) atomicAdd(counts + qi * kNnLevels + l, cnt[l]);
+}
+
+// k > 1: the smallest counted level that holds at least k keys (the last level, T0 itself, always does)
+__global__ void nnLevelKernel(const float *__restrict__ sampleVal, const unsigned *__restrict__ counts, float ratio,
+                              unsigned long long nq, int k, float *__restrict__ kth) {
+    const unsigned long long qi = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    const float t0v = sampleVal[qi * k + (k - 1)];
+    float best = t0v;
+    if (t0v < INFINITY) {
+        float f = 1.f;
+        for (int j = kNnLevels - 1; j >= 0; --j) {   // same products as nnCountKernel
+            if (counts[qi * kNnLevels + j] >= (unsigned)k) best = t0v * f;
+            f *= ratio;
+        }
+    }
+    kth[qi] = best;
+}
+
 // per query: k-th smallest FP32 distance over all slices, plus twice the error margin
 __global__ void nnThresholdKernel(const float *__restrict__ partVal, const double *__restrict__ queries,
                                   unsigned long long nq, int slices, int k, int dim, int metric, float so3w, float l2w,
-                                  float keysAbsMax, float *__restrict__ thr) {
+                                  float keysAbsMax, const float *__restrict__ kthIn, float *__restrict__ thr) {
     const unsigned long long qi = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     if (qi >= nq) return;
     const float *v = partVal + qi * slices * k;
     unsigned char head[256];
     for (int s = 0; s < slices; ++s) head[s] = 0;
     float kth = INFINITY;
-    for (int r = 0; r < k; ++r) {
+    if (kthIn) kth = kthIn[qi];   // k > 1: nnLevelKernel already chose a level with at least k keys under it
+    for (int r = 0; r < k && !kthIn; ++r) {
         int bs = -1;
         float bd = INFINITY;
         for (int s = 0; s < slices; ++s)
@@ -193,6 +272,29 @@ nnRefineKernel(const float *__restrict__ keys32, const double *__restrict__ keys
     unsigned exact = 0;
     const unsigned long long lo = blockIdx.y * keysPerSlice;
     const unsigned long long hi = min(n, lo + keysPerSlice);
+    unsigned cand[kNnCandCap];   // candidate keys of this slice, in index order (offsets from lo)
+    int nc = 0;
+    auto flush = [&]() {
+        for (int c = 0; c < nc; ++c) {
+            const unsigned long long ki = lo + cand[c];
+            double key[kNnMaxDim];
+            const double *kp = keys + ki * dim;
+            for (int i = 0; i < dim; ++i) key[i] = __ldg(kp + i);
+            const double d = nnDistance(q, key, dim, metric, so3w, l2w);
+            ++exact;
+            if (cnt == k && !(d < bestD[k - 1])) continue;
+            int pos = cnt < k ? cnt : k - 1;
+            while (pos > 0 && bestD[pos - 1] > d) {   // equal distances keep their (index) order
+                bestD[pos] = bestD[pos - 1];
+                bestI[pos] = bestI[pos - 1];
+                --pos;
+            }
+            bestD[pos] = d;
+            bestI[pos] = (long long)ki;
+            if (cnt < k) ++cnt;
+        }
+        nc = 0;
+    };
     for (unsigned long long t0 = lo; t0 < hi; t0 += kNnTile) {
         const int tn = (int)min((unsigned long long)kNnTile, hi - t0);
         const int nd = tn * dim;
@@ -203,30 +305,26 @@ nnRefineKernel(const float *__restrict__ keys32, const double *__restrict__ keys
         for (int j = 0; j < tn; ++j) {
             float d32;
             if (!nnWithin32(q32, tile + j * dim, dim, metric, so3w32, l2w32, limit, d32)) continue;
-            double key[kNnMaxDim];
-            const double *kp = keys + (t0 + j) * dim;
-            for (int i = 0; i < dim; ++i) key[i] = __ldg(kp + i);
-            const double d = nnDistance(q, key, dim, metric, so3w, l2w);
-            ++exact;
             if (k == 1) {
+                double key[kNnMaxDim];
+                const double *kp = keys + (t0 + j) * dim;
+                for (int i = 0; i < dim; ++i) key[i] = __ldg(kp + i);
+                const double d = nnDistance(q, key, dim, metric, so3w, l2w);
+                ++exact;
                 if (d < d1) {
                     d1 = d;
                     i1 = (long long)(t0 + j);
                 }
                 continue;
             }
-            if (cnt == k && !(d < bestD[k - 1])) continue;
-            int pos = cnt < k ? cnt : k - 1;
-            while (pos > 0 && bestD[pos - 1] > d) {   // equal distances keep their (index) order
-                bestD[pos] = bestD[pos - 1];
-                bestI[pos] = bestI[pos - 1];
-                --pos;
-            }
-            bestD[pos] = d;
-            bestI[pos] = (long long)(t0 + j);
-            if (cnt < k) ++cnt;
+            // k > 1: only note the candidate here (one store); the FP64 distances and the sorted insertions run
+            // once the scan is over, when every lane of the warp has its list to work through -- a lane that
+            // evaluates and inserts in the middle of the scan makes the other 31 wait
+            cand[nc++] = (unsigned)(t0 + j - lo);
+            if (nc == kNnCandCap) flush();
         }
     }
+    if (haveQuery && k > 1) flush();
     if (!haveQuery) return;
     double *od = outDist + (qi * gridDim.y + blockIdx.y) * k;
     long long *oi = outIdx + (qi * gridDim.y + blockIdx.y) * k;
@@ -301,10 +399,34 @@ cudaError_t launchNnSearch(const double *dKeys, const float *dKeys32, float keys
     if (nq == 0) return cudaSuccess;
     const size_t keysPerSlice = std::max<size_t>(((n + slices - 1) / slices + kNnTile - 1) / kNnTile * kNnTile, kNnTile);
     dim3 grid((unsigned)((nq + kNnThreads - 1) / kNnThreads), (unsigned)slices);
-    nnBound32Kernel<<<grid, kNnThreads, 0, stream>>>(dKeys32, n, dim, metric, (float)so3w, (float)l2w, dQueries, nq, k,
-                                                     keysPerSlice, dPartVal);
-    nnThresholdKernel<<<(unsigned)((nq + 127) / 128), 128, 0, stream>>>(dPartVal, dQueries, nq, slices, k, dim, metric,
-                                                                        (float)so3w, (float)l2w, keysAbsMax, dThr);
+    if (k == 1) {
+        nnBound32Kernel<<<grid, kNnThreads, 0, stream>>>(dKeys32, n, dim, metric, (float)so3w, (float)l2w, dQueries, nq, k,
+                                                         keysPerSlice, 1, dPartVal);
+        nnThresholdKernel<<<(unsigned)((nq + 127) / 128), 128, 0, stream>>>(dPartVal, dQueries, nq, slices, k, dim, metric,
+                                                                            (float)so3w, (float)l2w, keysAbsMax, nullptr, dThr);
+    } else {
+        // sample of ~16 k keys (the sorted insertions of the sample scan cost more than its distances: measured 2.5 ms
+        // for 3 277 sampled keys against 0.5 ms for counting over all 16 384); dPartVal: [nq][k] sample distances,
+        // then [nq][kNnLevels] counts, then [nq] chosen levels
+        const size_t want = (size_t)16 * k;
+        const size_t stride = std::max<size_t>(1, n / std::max<size_t>(want, 1));
+        const size_t m = (n + stride - 1) / stride;
+        const size_t sampleSlice = std::max<size_t>((m + kNnTile - 1) / kNnTile * kNnTile, kNnTile);
+        // levels: k ... k n / m keys expected under them, geometric; distances scale with count^(1/dimension)
+        const double R = std::max(1.0, (double)n / (double)m);
+        const float ratio = (float)std::pow(1.0 / R, 1.0 / ((kNnLevels - 1) * (metric == 0 ? 6.0 : (double)dim)));
+        unsigned *dCounts = (unsigned *)(dPartVal + nq * k);
+        float *dKth = (float *)(dCounts + nq * kNnLevels);
+        cudaError_t e0 = cudaMemsetAsync(dCounts, 0, nq * kNnLevels * sizeof(unsigned), stream);
+        if (e0 != cudaSuccess) return e0;
+        nnBound32Kernel<<<dim3(grid.x, 1), kNnThreads, 0, stream>>>(dKeys32, m, dim, metric, (float)so3w, (float)l2w, dQueries,
+                                                                    nq, k, sampleSlice, stride, dPartVal);
+        nnCountKernel<<<grid, kNnThreads, 0, stream>>>(dKeys32, n, dim, metric, (float)so3w, (float)l2w, dQueries, nq, k,
+                                                       keysPerSlice, dPartVal, ratio, dCounts);
+        nnLevelKernel<<<(unsigned)((nq + 127) / 128), 128, 0, stream>>>(dPartVal, dCounts, ratio, nq, k, dKth);
+        nnThresholdKernel<<<(unsigned)((nq + 127) / 128), 128, 0, stream>>>(dPartVal, dQueries, nq, 1, k, dim, metric,
+                                                                            (float)so3w, (float)l2w, keysAbsMax, dKth, dThr);
+    }
     if (slices == 1) {
         nnRefineKernel<<<grid, kNnThreads, 0, stream>>>(dKeys32, dKeys, n, dim, metric, so3w, l2w, dQueries, dThr, nq, k,
                                                         keysPerSlice, dDist, dIdx, dExactCount);
