@@ -121,6 +121,7 @@ int selectDevice(int device, int *numSms) {
 
 struct Se3Scene : SceneBase {
     double so3w = 50, l2w = 1, invStep = 10;
+    std::atomic<bool> streamingOff{false};   // set when a streamed batch's copy could not overlap its kernel
     SceneDev dev{};
     DevBuf robotNodes, envNodes, robotTris, envTris, robotTris64, envTris64;
     size_t nEnvTris = 0, nRobotTris = 0;
@@ -303,7 +304,7 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
     if ((rc = c->in0.reserve(bytes)) || (rc = c->out.reserve(n))) return rc;
     double *dIn = (double *)c->in0.ptr;
     uint8_t *dOut = (uint8_t *)c->out.ptr;
-    const bool streamed = streamBatch(n);
+    const bool streamed = streamBatch(n) && !sc->streamingOff.load(std::memory_order_relaxed);
     // MPLB_TIMELINE=1: print where a streamed call's time goes (diagnostic)
     static const bool timeline = std::getenv("MPLB_TIMELINE") != nullptr;
     static thread_local cudaEvent_t tl[5] = {};
@@ -346,9 +347,19 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
         std::fprintf(stderr, "[mplb timeline] n=%zu  pattern fill done %.3f ms, copy done %.3f, kernel done %.3f, verdicts back %.3f, host %.3f\n",
                      n, a, b, k, d, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());
     }
-    if (frc != MPLB_OK && streamed)
-        return fail(MPLB_ERR_CUDA, "%s (a streamed batch stalls when a state holds the reserved all-ones NaN pattern)",
-                    mplb_last_error());
+    if (streamed && c->hCtr->pad) {
+        // The copy never reached the waiting kernel: something (a profiler replaying or serialising launches, a
+        // debugger) keeps the two from overlapping.  Repeat this batch copy-then-kernel and stay with that.
+        sc->streamingOff.store(true, std::memory_order_relaxed);
+        if (frc == MPLB_OK) sc->hChecks -= n;   // counted again below
+        MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(DevCounters), c->stream));
+        MPLB_CUDA(cudaMemcpyAsync(dIn, states, bytes, cudaMemcpyHostToDevice, c->stream));
+        MPLB_CUDA(launchCheckStates(sc->dev, dIn, n, dOut, (DevCounters *)c->ctr.ptr, (unsigned *)c->work.ptr, sc->numSms,
+                                    c->stream));
+        sc->hLaunches += 1;
+        MPLB_CUDA(cudaMemcpyAsync(valid, dOut, n, cudaMemcpyDeviceToHost, c->stream));
+        return finishCall(sc, c, n, nullptr);
+    }
     return frc;
 }
 

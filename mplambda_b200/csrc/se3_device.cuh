@@ -29,7 +29,7 @@ struct SceneDev {
 
 struct DevCounters {
     unsigned long long bvTests, triTests, exactTests, states;
-    unsigned overflow, pad;
+    unsigned overflow, pad;   // pad: 1 = a streamed batch's input never arrived (see StateSource)
 #ifdef MPLB_WARP_TIMES   // diagnostic build: when did the warps start / run out of new work / finish (globaltimer, ns)
     unsigned long long negStart, negFirstDry, negFirstDone, lastDone;   // neg*: ~t, so that atomicMax finds the minimum
     unsigned long long warpDone[4096];

@@ -417,7 +417,7 @@ struct StateSource {
             polledAt = clock64();
             if (mayBlock) __nanosleep(backoff / 2);   // ~2 cycles per ns
             backoff = min(backoff * 2, 16000u);
-            if (++waitSpins > (1u << 20)) {   // a copy that never arrives is reported, not spun on
+            if (++waitSpins > (1u << 17)) {   // ~1 s: a copy that never arrives is reported, not spun on
                 stalled = 1;
                 pendCount = 0;
                 exhausted = true;
@@ -453,7 +453,7 @@ struct StateSource {
                 here &= __double_as_longlong(s[k]) != -1ll;
             }
             if (here) return true;
-            if (spins >= (1u << 20)) {   // ~2 s
+            if (spins >= (1u << 18)) {   // ~0.5 s
                 const_cast<StateSource *>(this)->stalled = 1;
                 return false;
             }
@@ -1153,7 +1153,9 @@ checkStatesKernel(SceneDev sc, const double *states, unsigned long long n, uint8
         atomicMax(&ctr->lastDone, now());
     }
 #endif
-    if (__any_sync(kFull, src.stalled != 0)) cnt.error = 1;
+    // a streamed batch whose copy did not arrive (e.g. a profiler serialising the kernel and the copy): reported
+    // separately so that the host repeats the batch copy-then-kernel instead of failing
+    if (__any_sync(kFull, src.stalled != 0) && (threadIdx.x & 31u) == 0) atomicExch(&ctr->pad, 1u);
     flushCounters(cnt, ctr, false);
 }
 
