@@ -165,6 +165,14 @@ public:
         return v;
     }
     mplb_scene *handle() const { return scene_; }
+
+    // nearest-neighbour key of a state (scale(q) as doubles) and the matching mplb_nn_create arguments
+    static constexpr int kKeyDim = kDOF;
+    static void key(const State &q, double *out) {
+        const State r = scale(q);
+        for (int i = 0; i < kDOF; ++i) out[i] = static_cast<double>(r[i]);
+    }
+    static int nnCreate(int device, mplb_nn **out) { return mplb_nn_create(1, kDOF, 0, 0, device, out); }
 };
 
 }  // namespace mplb::demo

@@ -227,6 +227,13 @@ public:
         return v;
     }
     mplb_scene *handle() const { return scene_; }
+
+    // nearest-neighbour key of a state (scale(q) as doubles) and the matching mplb_nn_create arguments, for
+    // planners that keep their nodes in an mplb_nn (include/mplb/batched_rrt.hpp)
+    static constexpr int kKeyDim = 7;
+    static void key(const State &q, double *out) { detail::pack<S>(scale(q), out); }
+    static State fromKey(const double *k) { return detail::unpack<S>(k); }
+    static int nnCreate(int device, mplb_nn **out) { return mplb_nn_create(0, 7, double(so3weight), double(l2weight), device, out); }
 };
 
 }  // namespace mplb::demo

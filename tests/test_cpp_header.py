@@ -63,3 +63,45 @@ def test_cpp_parity_on_gpu(tmp_path, scenes):
         paths.append(str(p))
     out = subprocess.run([str(exe)] + paths, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "PASSED" in out.stdout, out.stdout + out.stderr
+
+
+def _build_rrt(tmp_path):
+    exe = tmp_path / "rrt_test"
+    lib = M.lib_path()
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "rrt_test.cpp"), "-o", str(exe), lib,
+                           "-Wl,-rpath," + os.path.dirname(lib)])
+    return exe
+
+
+def test_cpp_planner_compiles(tmp_path):
+    exe = _build_rrt(tmp_path)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 2 and "usage" in out.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cubicles", "twistycool"])
+def test_cpp_planner_solves_and_path_is_valid(tmp_path, scenes, oracle, name):
+    """The C++ batch-issuing RRT (include/mplb/batched_rrt.hpp) end to end: the path it returns
+    starts at the start, ends in the goal region and every state and motion on it is valid under the oracle."""
+    import numpy as np
+    from mplambda_b200.workload import SE3_SCENES
+    exe = _build_rrt(tmp_path)
+    env, robot = scenes[name]
+    sc = SE3_SCENES[name]
+    np.ascontiguousarray(env, dtype=np.float64).tofile(tmp_path / "env.bin")
+    np.ascontiguousarray(robot, dtype=np.float64).tofile(tmp_path / "robot.bin")
+    nums = list(sc["start"]) + list(sc["goal"]) + list(sc["min"]) + list(sc["max"])
+    out = subprocess.run([str(exe), str(tmp_path / "env.bin"), str(tmp_path / "robot.bin")] + ["%.17g" % x for x in nums] +
+                         ["2048", "7", "60"], capture_output=True, text=True, timeout=180)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[0].startswith("solved")
+    path = np.array([[float(x) for x in ln.split()] for ln in lines[1:]])
+    assert len(path) == int(lines[0].split()[1]) >= 2
+    np.testing.assert_array_equal(path[0], np.array(sc["start"], dtype=np.float64))
+    orc = oracle.SE3Oracle(env, robot, check_resolution=0.1)
+    assert orc.distance(path[-1], np.array(sc["goal"], dtype=np.float64)) <= 0.1      # isGoal, se3...:100-104
+    assert orc.check_states(path).all()
+    assert orc.check_edges(path[:-1], path[1:]).all()
