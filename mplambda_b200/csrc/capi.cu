@@ -56,7 +56,13 @@ constexpr size_t kSmallStates = 2048, kSmallEdges = 1024;
 static_assert(kSmallStates * 56 <= kStageBytes && kSmallEdges * (116 + 40) + 8 <= kStageBytes, "staging too small");
 static_assert(kSmallStates <= kCtlTail && kSmallEdges * 4 <= kCtlTail, "control block too small");
 
+constexpr size_t kBounceBytes = 8u << 20;
+
 CallCtx::~CallCtx() {
+    for (int i = 0; i < 2; ++i) {
+        if (hBounce[i]) cudaFreeHost(hBounce[i]);
+        if (bounceDone[i]) cudaEventDestroy(bounceDone[i]);
+    }
     if (hStage) cudaFreeHost(hStage);
     if (hCtl) cudaFreeHost(hCtl);
     if (hCtr) cudaFreeHost(hCtr);
@@ -235,6 +241,40 @@ static int createSe3(const double *envTris, size_t nEnv, const double *robotTris
     return MPLB_OK;
 }
 
+// Host -> device copy of a caller's buffer on `stream`.  Pinned memory goes straight to the copy engine; pageable
+// memory is copied by all cores into two pinned bounce buffers, chunk i + 1 being filled while chunk i is on the wire.
+static int hostToDevice(CallCtx *c, void *dst, const void *src, size_t bytes, cudaStream_t stream) {
+    cudaPointerAttributes at{};
+    const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();   // (older drivers report plain malloc memory as an error)
+    static const bool off = std::getenv("MPLB_NO_BOUNCE") != nullptr;   // diagnostic: let the driver stage pageable memory
+    if (pinned || off || bytes < (1u << 20)) {
+        MPLB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+        return MPLB_OK;
+    }
+    for (int i = 0; i < 2; ++i)
+        if (!c->hBounce[i]) {
+            MPLB_CUDA(cudaMallocHost((void **)&c->hBounce[i], kBounceBytes));
+            MPLB_CUDA(cudaEventCreateWithFlags(&c->bounceDone[i], cudaEventDisableTiming));
+        }
+    int b = 0;
+    for (size_t off = 0; off < bytes; off += kBounceBytes, b ^= 1) {
+        const size_t len = std::min(kBounceBytes, bytes - off);
+        MPLB_CUDA(cudaEventSynchronize(c->bounceDone[b]));   // the buffer's previous chunk has left
+        const unsigned char *s = (const unsigned char *)src + off;
+        unsigned char *d = c->hBounce[b];
+        const long long parts = (long long)((len + (1u << 20) - 1) >> 20);
+#pragma omp parallel for schedule(static)
+        for (long long p = 0; p < parts; ++p) {
+            const size_t lo = (size_t)p << 20, n = std::min((size_t)1 << 20, len - lo);
+            std::memcpy(d + lo, s + lo, n);
+        }
+        MPLB_CUDA(cudaMemcpyAsync((unsigned char *)dst + off, d, len, cudaMemcpyHostToDevice, stream));
+        MPLB_CUDA(cudaEventRecord(c->bounceDone[b], stream));
+    }
+    return MPLB_OK;
+}
+
 static int account(SceneBase *sc, const DevCounters &k, size_t checks, uint64_t *statesOut) {
     if (k.overflow) return fail(MPLB_ERR_CUDA, "device traversal bookkeeping error (pair stack / slot accounting)");
     sc->hBv += k.bvTests;
@@ -313,7 +353,7 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
         for (auto &e : tl) cudaEventCreate(&e);
     MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(DevCounters), c->stream));
     if (!streamed) {
-        MPLB_CUDA(cudaMemcpyAsync(dIn, states, bytes, cudaMemcpyHostToDevice, c->stream));
+        if ((rc = hostToDevice(c, dIn, states, bytes, c->stream))) return rc;
         MPLB_CUDA(launchCheckStates(sc->dev, dIn, n, dOut, (DevCounters *)c->ctr.ptr, (unsigned *)c->work.ptr, sc->numSms,
                                     c->stream));
     } else {
@@ -330,7 +370,7 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
         MPLB_CUDA(launchCheckStates(sc->dev, dIn, n, dOut, (DevCounters *)c->ctr.ptr, (unsigned *)c->work.ptr, sc->numSms,
                                     c->stream, true));
         if (timeline) cudaEventRecord(tl[3], c->stream);
-        MPLB_CUDA(cudaMemcpyAsync(dIn, states, bytes, cudaMemcpyHostToDevice, c->copyStream));
+        if ((rc = hostToDevice(c, dIn, states, bytes, c->copyStream))) return rc;
         if (timeline) cudaEventRecord(tl[2], c->copyStream);
     }
     sc->hLaunches += 1;
@@ -424,8 +464,7 @@ static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, siz
         (rc = c->aux1.reserve(edgeConstBytes(n))))
         return rc;
     MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(DevCounters), c->stream));
-    MPLB_CUDA(cudaMemcpyAsync(c->in0.ptr, from, sb, cudaMemcpyHostToDevice, c->stream));
-    MPLB_CUDA(cudaMemcpyAsync(c->in1.ptr, to, sb, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = hostToDevice(c, c->in0.ptr, from, sb, c->stream)) || (rc = hostToDevice(c, c->in1.ptr, to, sb, c->stream))) return rc;
     MPLB_CUDA(cudaMemcpyAsync(c->steps.ptr, c->hSteps.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
     MPLB_CUDA(launchCheckEdges(sc->dev, (const double *)c->in0.ptr, (const double *)c->in1.ptr,
                                (const unsigned *)c->steps.ptr, n, (unsigned *)c->dead.ptr, (uint8_t *)c->out.ptr,

@@ -36,6 +36,10 @@ struct CallCtx {
     // host->device copy, the kernels, one device->host copy.
     unsigned char *hStage = nullptr, *hCtl = nullptr;   // pinned
     DevBuf stage, ctl;
+    // large inputs in pageable memory: two pinned bounce buffers filled by all cores while the previous one is on
+    // the wire (cudaMemcpyAsync on pageable memory stages through one thread at ~10 GB/s)
+    unsigned char *hBounce[2] = {nullptr, nullptr};
+    cudaEvent_t bounceDone[2] = {nullptr, nullptr};
     unsigned long long *hWater = nullptr;  // pinned: per-slice arrival marks of a streamed batch
     std::vector<uint32_t> hSteps;
     ~CallCtx();
