@@ -226,3 +226,44 @@ def test_degenerate_configurations_match_brute_force(oracle):
     assert 0.05 < want.mean() < 0.95
     st = s.stats()
     assert st["exact_tests"] > 0          # the exact path really was exercised
+
+
+def test_edge_step_count_extremes(scenes, oracle):
+    """Edges with 0, 1, 2, ... 70 interpolation steps (around the 32-interval split), very long edges (10^5 steps
+    at a fine resolution) and a needle-thin obstacle that only a few samples of a long edge touch: the interval
+    scheme must return the reference's discrete verdict in every case."""
+    env, robot = scenes["twistycool"]
+    sc = SE3_SCENES["twistycool"]
+    s = M.SE3RigidBodyScenario(env, robot, sc["goal"], sc["min"], sc["max"], 0.1)
+    orc = oracle.SE3Oracle(env, robot, check_resolution=0.1)
+    P = se3_poses(4096, sc["min"], sc["max"], 5)
+    A = P[s.check_states(P)][:600]
+    rng = np.random.default_rng(3)
+    # short motions: translate by k * 0.1 * (0.999 .. 1.001) along a random direction, no rotation -> steps ~ k
+    B = A.copy()
+    k = np.arange(len(A)) % 72
+    d = rng.normal(size=(len(A), 3)); d /= np.linalg.norm(d, axis=1)[:, None]
+    B[:, 4:] += d * (k * 0.1 * rng.uniform(0.999, 1.001, len(A)))[:, None]
+    steps = s.edge_steps(A, B)
+    assert steps.min() == 0 and steps.max() >= 70 and len(np.unique(steps)) > 60
+    assert (s.check_edges(A, B) == orc.check_edges(A, B)).all()
+    # very long edges: resolution 0.002 -> ~10^5 .. 4 x 10^5 steps each
+    fine = M.SE3RigidBodyScenario(env, robot, sc["goal"], sc["min"], sc["max"], 0.002)
+    forc = oracle.SE3Oracle(env, robot, check_resolution=0.002)
+    C = se3_poses(48, sc["min"], sc["max"], 6)
+    st = fine.edge_steps(A[:48], C)
+    assert st.max() > 100000
+    got, chk = fine.check_edges(A[:48], C, return_states_checked=True)
+    assert (got == forc.check_edges(A[:48], C)).all()
+    assert chk < st.sum() // 20            # far from enumerating them
+    # a needle: one thin triangle crossing the path of a small robot; only ~3 of ~2000 samples touch it
+    needle = np.array([[[0.0, -5, -5], [0.0, 5, -5], [0.004, 0, 5]]])
+    tet = np.array([[[0, 0, 0], [.2, 0, 0], [0, .2, 0.0]], [[0, 0, 0], [.2, 0, 0], [0, 0, .2]], [[0, 0, 0], [0, .2, 0], [0, 0, .2]],
+                    [[.2, 0, 0], [0, .2, 0], [0, 0, .2]]]) - 0.05
+    ns = M.SE3RigidBodyScenario(needle, tet, [0, 0, 0, 1, 0, 0, 0], [-200, -10, -10], [200, 10, 10], 0.1)
+    norc = oracle.SE3Oracle(needle, tet, check_resolution=0.1)
+    F = np.tile(np.array([0, 0, 0, 1, -100.0, 0, 0]), (64, 1)); T = np.tile(np.array([0, 0, 0, 1, 100.0, 0, 0]), (64, 1))
+    F[:, 5] = np.linspace(-6, 6, 64); T[:, 5] = np.linspace(-6, 6, 64)      # some pass the needle, some miss it (|y| > 5)
+    got = ns.check_edges(F, T)
+    assert (got == norc.check_edges(F, T)).all()
+    assert 0 < got.sum() < 64
