@@ -58,8 +58,19 @@ static_assert(kSmallStates <= kCtlTail && kSmallEdges * 4 <= kCtlTail, "control 
 
 constexpr size_t kBounceBytes = 8u << 20;
 
+int CallCtx::reserveRes(int i, size_t bytes) {
+    if (bytes <= hResCap[i]) return MPLB_OK;
+    if (hRes[i]) cudaFreeHost(hRes[i]);
+    hRes[i] = nullptr;
+    hResCap[i] = 0;
+    if (cudaMallocHost((void **)&hRes[i], bytes) != cudaSuccess) return fail(MPLB_ERR_NOMEM, "out of pinned host memory");
+    hResCap[i] = bytes;
+    return MPLB_OK;
+}
+
 CallCtx::~CallCtx() {
     for (int i = 0; i < 2; ++i) {
+        if (hRes[i]) cudaFreeHost(hRes[i]);
         if (hBounce[i]) cudaFreeHost(hBounce[i]);
         if (bounceDone[i]) cudaEventDestroy(bounceDone[i]);
     }

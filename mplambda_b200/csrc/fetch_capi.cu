@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -80,7 +82,8 @@ struct FetchScene : SceneBase {
         const size_t pc = fetchPairCap(n), lc = fetchLeafCap(n);
         if ((rc = c->aux0.reserve(n * 144 * sizeof(double))) || (rc = c->aux1.reserve(n)) ||
             (rc = c->aux2.reserve(n * sizeof(unsigned))) || (rc = c->aux4.reserve(pc * 8)) ||
-            (rc = c->aux5.reserve(lc * 8)) || (rc = c->aux6.reserve(n * sizeof(unsigned))) || (rc = c->work.reserve(64)))
+            (rc = c->aux5.reserve(lc * 8)) || (rc = c->aux6.reserve(n * sizeof(unsigned))) || (rc = c->work.reserve(64)) ||
+            (rc = c->out.reserve(n)))
             return rc;
         w.frames = (double *)c->aux0.ptr;
         w.selfHit = (unsigned char *)c->aux1.ptr;
@@ -91,6 +94,7 @@ struct FetchScene : SceneBase {
         w.pairCap = pc;
         w.leafCap = lc;
         w.counts = (unsigned *)c->work.ptr;
+        w.touched = (unsigned char *)c->out.ptr;   // (checkStates reuses the buffer for its verdicts afterwards)
         return MPLB_OK;
     }
 
@@ -130,9 +134,12 @@ struct FetchScene : SceneBase {
         return finish(c);
     }
 
-    // isValid(from,to) (fetch_scenario.hpp:120-173): verdict = valid(to) AND every interpolated sample.
-    // Pass 1 tests `to` and up to 15 evenly spread samples of every edge; pass 2 the remaining samples
-    // of the edges still alive (the device skips samples of edges that died meanwhile).
+    // isValid(from,to) (fetch_scenario.hpp:120-173): verdict = valid(to) AND every interpolated sample.  The samples
+    // are not enumerated: an item is `to`, or an INTERVAL [lo, hi] of samples evaluated at its middle one with every
+    // box test inflated by how far each geometry can stray over the interval (FetchSceneDev::reach).  An interval
+    // that nothing comes within reach of is certified free as a whole; otherwise its middle sample has been tested
+    // exactly and the two halves go into the next round.  Every sample is the middle of exactly one interval, so the
+    // verdict is the reference's discrete one.  Rounds are host driven (the work lists live on the host).
     int checkEdges(const double *from, const double *to, size_t n, uint8_t *valid, uint64_t *statesChecked) override {
         MPLB_CUDA(cudaSetDevice(device));
         CallCtx *c = acquire();
@@ -144,7 +151,8 @@ struct FetchScene : SceneBase {
         const size_t sb = n * 8 * sizeof(double);
         FetchScratch w{};
         if ((rc = c->in0.reserve(sb)) || (rc = c->in1.reserve(sb)) || (rc = c->steps.reserve(n * 4)) ||
-            (rc = c->dead.reserve(n * 4)) || (rc = c->aux3.reserve(kBatch * 8)) || (rc = reserveScratch(c, kBatch, w)))
+            (rc = c->dead.reserve(n * 4)) || (rc = c->aux3.reserve(kBatch * 8)) || (rc = c->stage.reserve(kBatch * sizeof(float2))) ||
+            (rc = reserveScratch(c, kBatch, w)))
             return rc;
         MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(FetchCounters), c->stream));
         MPLB_CUDA(cudaMemsetAsync(c->dead.ptr, 0, n * 4, c->stream));
@@ -152,68 +160,124 @@ struct FetchScene : SceneBase {
         MPLB_CUDA(cudaMemcpyAsync(c->in1.ptr, to, sb, cudaMemcpyHostToDevice, c->stream));
         MPLB_CUDA(cudaMemcpyAsync(c->steps.ptr, c->hSteps.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
 
+        struct Interval { uint32_t e, lo, hi; };   // lo == hi == steps: the edge's `to`
+        std::vector<Interval> cur, next;
         std::vector<unsigned long long> items;
+        std::vector<float2> slack;
         std::vector<unsigned> dead(n, 0);
-        items.reserve(kBatch);
         uint64_t launched = 0;
-        auto flush = [&]() -> int {
-            if (items.empty()) return MPLB_OK;
-            // the item buffer is reused: wait for the previous group before overwriting it
-            MPLB_CUDA(cudaStreamSynchronize(c->stream));
+        // joint motion over the whole edge: torso (prismatic) and the arm joints (L1)
+        std::vector<float> dTorso(n), dArm(n);
+        for (size_t e = 0; e < n; ++e) {
+            double a = 0;
+            for (int j = 1; j < 8; ++j) a += std::fabs(to[8 * e + j] - from[8 * e + j]);
+            dTorso[e] = (float)(std::fabs(to[8 * e] - from[8 * e]) * 1.000001);
+            dArm[e] = (float)(a * 1.000001);
+        }
+        // Two batches are in flight: while the device works on one, the host turns the results of the previous one
+        // into next-round intervals and builds the following one.  Results land in pinned buffers (slot = batch & 1).
+        const size_t resBytes = kBatch + n * 4;
+        for (int i = 0; i < 2; ++i)
+            if ((rc = c->reserveRes(i, resBytes))) return rc;
+        while (c->events.size() < 2) {
+            cudaEvent_t ev;
+            MPLB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            c->events.push_back(ev);
+        }
+        std::vector<Interval> inflight[2];
+        std::vector<unsigned char> forced[2] = {std::vector<unsigned char>(kBatch), std::vector<unsigned char>(kBatch)};
+        unsigned long long dbgHist[16][32] = {};
+        auto submit = [&](int slot) -> int {
+            std::vector<Interval> &b = inflight[slot];
+            items.resize(b.size());
+            slack.resize(b.size());
+            for (size_t i = 0; i < b.size(); ++i) {
+                const Interval &v = b[i];
+                const uint32_t st = c->hSteps[v.e], mid = v.lo + (v.hi - v.lo) / 2;
+                items[i] = ((unsigned long long)v.e << 32) | mid;
+                float f = 0.f;
+                if (v.hi > v.lo) f = (float)((double)std::max(v.hi - mid, mid - v.lo) / (double)st * 1.000001);
+                slack[i] = make_float2(dTorso[v.e] * f, dArm[v.e] * f);
+                // an interval over which the gripper can stray by more than ~12 cm is practically never certified
+                // (measured: 0-2 % from 32 samples up) and its inflated traversal costs more than a plain test:
+                // evaluate its middle sample plainly and split it unconditionally
+                forced[slot][i] = v.hi > v.lo && slack[i].x + slack[i].y * 1.2f > 0.12f;
+                if (forced[slot][i]) slack[i] = make_float2(0.f, 0.f);
+            }
             MPLB_CUDA(cudaMemcpyAsync(c->aux3.ptr, items.data(), items.size() * 8, cudaMemcpyHostToDevice, c->stream));
+            MPLB_CUDA(cudaMemcpyAsync(c->stage.ptr, slack.data(), slack.size() * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
             MPLB_CUDA(launchFetchEdgeItems(dev, (const double *)c->in0.ptr, (const double *)c->in1.ptr,
                                            (const unsigned *)c->steps.ptr, (const unsigned long long *)c->aux3.ptr,
-                                           items.size(), (unsigned *)c->dead.ptr, w, (FetchCounters *)c->ctr.ptr, numSms,
-                                           c->stream));
+                                           (const float2 *)c->stage.ptr, items.size(), (unsigned *)c->dead.ptr, w,
+                                           (FetchCounters *)c->ctr.ptr, numSms, c->stream));
             hLaunches += 6;
             launched += items.size();
-            MPLB_CUDA(cudaStreamSynchronize(c->stream));
-            items.clear();
+            MPLB_CUDA(cudaMemcpyAsync(c->hRes[slot], w.touched, items.size(), cudaMemcpyDeviceToHost, c->stream));
+            MPLB_CUDA(cudaMemcpyAsync(c->hRes[slot] + kBatch, c->dead.ptr, n * 4, cudaMemcpyDeviceToHost, c->stream));
+            MPLB_CUDA(cudaEventRecord(c->events[slot], c->stream));
             return MPLB_OK;
         };
-        auto refreshDead = [&]() -> int {
-            MPLB_CUDA(cudaMemcpyAsync(dead.data(), c->dead.ptr, n * 4, cudaMemcpyDeviceToHost, c->stream));
-            MPLB_CUDA(cudaStreamSynchronize(c->stream));
-            return MPLB_OK;
-        };
-        auto isCoarse = [](uint32_t k, uint32_t st) {  // k = round-down(j * st / 16) for some j in 1..15
-            if (st < 2) return false;
-            for (uint32_t j = 1; j < 16; ++j)
-                if ((uint64_t)j * st / 16 == k) return k >= 1 && k < st;
-            return false;
-        };
-        // pass 1
-        for (size_t e = 0; e < n; ++e) {
-            const uint32_t st = c->hSteps[e];
-            items.push_back(((unsigned long long)e << 32) | st);  // `to`
-            uint32_t prev = 0;
-            for (uint32_t j = 1; j < 16 && st >= 2; ++j) {
-                const uint32_t k = (uint32_t)((uint64_t)j * st / 16);
-                if (k >= 1 && k < st && k != prev) items.push_back(((unsigned long long)e << 32) | k);
-                prev = k;
-            }
-            if (items.size() + 16 > kBatch && (rc = flush())) return rc;
-        }
-        if ((rc = flush()) || (rc = refreshDead())) return rc;
-        // pass 2
-        size_t sinceRefresh = 0;
-        for (size_t e = 0; e < n; ++e) {
-            if (dead[e]) continue;
-            const uint32_t st = c->hSteps[e];
-            for (uint32_t k = 1; k < st; ++k) {
-                if (isCoarse(k, st)) continue;
-                items.push_back(((unsigned long long)e << 32) | k);
-                if (items.size() == kBatch) {
-                    if ((rc = flush())) return rc;
-                    if (++sinceRefresh >= 4) {
-                        if ((rc = refreshDead())) return rc;
-                        sinceRefresh = 0;
-                        if (dead[e]) break;
-                    }
+        auto collect = [&](int slot) -> int {
+            std::vector<Interval> &b = inflight[slot];
+            if (b.empty()) return MPLB_OK;
+            MPLB_CUDA(cudaEventSynchronize(c->events[slot]));
+            const unsigned char *t = c->hRes[slot];
+            std::memcpy(dead.data(), c->hRes[slot] + kBatch, n * 4);
+            static const bool dbg = std::getenv("MPLB_FETCH_DEBUG") != nullptr;
+            for (size_t i = 0; i < b.size(); ++i) {
+                const Interval &v = b[i];
+                if (dbg && !dead[v.e] && v.hi > v.lo) {
+                    int cls = 0;
+                    for (uint32_t len = v.hi - v.lo + 1; len > 1; len >>= 1) ++cls;
+                    ++dbgHist[std::min(cls, 15)][t[i] & 31];
                 }
+                if (dead[v.e] || v.hi <= v.lo || !(t[i] || forced[slot][i])) continue;   // dead, a single sample, or certified
+                const uint32_t mid = v.lo + (v.hi - v.lo) / 2;
+                if (mid > v.lo) next.push_back({v.e, v.lo, mid - 1});
+                if (mid < v.hi) next.push_back({v.e, mid + 1, v.hi});
+            }
+            b.clear();
+            return MPLB_OK;
+        };
+        // round 0: `to` and up to 16 equal intervals of the samples [1, steps - 1] of every edge
+        for (size_t e = 0; e < n; ++e) {
+            const uint32_t st = c->hSteps[e];
+            cur.push_back({(uint32_t)e, st, st});
+            const uint64_t m = st ? st - 1 : 0;
+            for (uint64_t k = 0; k < 16; ++k) {
+                const uint32_t lo = 1u + (uint32_t)((k * m) >> 4), hi = (uint32_t)(((k + 1) * m) >> 4);
+                if (lo <= hi) cur.push_back({(uint32_t)e, lo, hi});
             }
         }
-        if ((rc = flush()) || (rc = refreshDead())) return rc;
+        int slot = 0;
+        while (!cur.empty()) {
+            size_t pos = 0;
+            while (pos < cur.size()) {
+                std::vector<Interval> &b = inflight[slot];
+                while (pos < cur.size() && b.size() < kBatch) {
+                    if (!dead[cur[pos].e]) b.push_back(cur[pos]);
+                    ++pos;
+                }
+                if (b.empty()) break;
+                if ((rc = submit(slot)) || (rc = collect(slot ^ 1))) return rc;
+                slot ^= 1;
+            }
+            if ((rc = collect(slot ^ 1)) || (rc = collect(slot))) return rc;   // the round is complete
+            cur.swap(next);
+            next.clear();
+        }
+        if (std::getenv("MPLB_FETCH_DEBUG"))
+            for (int cls = 0; cls < 16; ++cls) {
+                unsigned long long tot = 0, by[5] = {0, 0, 0, 0, 0};
+                for (int f = 0; f < 32; ++f) {
+                    tot += dbgHist[cls][f];
+                    for (int bit = 0; bit < 5; ++bit)
+                        if (f >> bit & 1) by[bit] += dbgHist[cls][f];
+                }
+                if (tot)
+                    std::fprintf(stderr, "[fetch intervals] length ~2^%d: %llu, certified %llu; touched by floor %llu, pair near %llu, pair overlap %llu, env near %llu, env overlap %llu\n",
+                                 cls, tot, dbgHist[cls][0], by[0], by[1], by[2], by[3], by[4]);
+            }
         for (size_t e = 0; e < n; ++e) valid[e] = dead[e] ? 0 : 1;
         hChecks += launched;
         if (statesChecked) *statesChecked = launched;
@@ -276,6 +340,22 @@ static int createFetch(const double *envTris, size_t nEnv, const double envFrame
     d.shapes[9] = {0, (0.12 + 0.0625 * 2) / 2, 0.125 / 2, 0.075 / 2};
     d.shapes[10] = {1, 0.085 * 1.1, (0.04 * 1.1) / 2, 0};
     d.shapes[11] = {2, 0.24 * 1.05, (0.115 * 1.05) / 2, 0};
+    {
+        // FetchSceneDev::lift / reach.  Chain lengths from the shoulder pan joint's origin to each arm link's origin
+        // (norms of the joint offsets in fetchFkKernel), plus the geometry's origin offset and bounding radius.
+        const double chain[8] = {0, 0.13149, 0.35049, 0.48349, 0.68049, 0.80499, 0.94349, 0.94349 + 0.0765};   // pan .. gripper link
+        for (int k = 0; k < 12; ++k) {
+            d.lift[k] = k == 0 ? 0.f : 1.f;
+            d.reach[k] = 0.f;
+            if (k < 2 || k > 9) continue;   // base, torso, neck, head: the arm joints do not move them
+            const FetchShape &sh = d.shapes[k];
+            const double rad = sh.type == 0 ? std::sqrt(sh.a * sh.a + sh.b * sh.b + sh.c * sh.c)
+                                            : sh.type == 1 ? sh.a + sh.b : std::sqrt(sh.a * sh.a + sh.b * sh.b);
+            const double *o = d.origins + 12 * k;
+            const double off = std::sqrt(o[3] * o[3] + o[7] * o[7] + o[11] * o[11]);
+            d.reach[k] = (float)((chain[k - 2] + off + rad) * 1.0001);
+        }
+    }
     sc->envNodeCount = env.nodes.size();
     sc->robotNodeCount = 12;
     {

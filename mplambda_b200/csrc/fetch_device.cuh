@@ -19,6 +19,10 @@ struct FetchSceneDev {
     double envFrame[12];       // row-major 3x4 [R|t]: environment-local -> world
     double origins[12 * 12];   // link frame -> geometry frame (fetch_robot.hpp:217-274), row-major 3x4 each
     FetchShape shapes[12];
+    // Interval certificates for edges: while the joints move by dq, no point of geometry k moves farther than
+    // |dq_torso| * lift[k] + sum_{arm joints} |dq_j| * reach[k]  (reach = largest distance from the shoulder pan
+    // axis' origin -- hence from any arm joint's axis -- to a point of the geometry; 0 for what the arm does not move)
+    float lift[12], reach[12];
 };
 
 struct FetchCounters {
@@ -35,6 +39,7 @@ struct FetchScratch {
     unsigned long long *pairItems, *leafItems;
     size_t pairCap, leafCap;
     unsigned *counts;            // [4]: pair list, leaf list, survivor list lengths, env item counter
+    unsigned char *touched;      // [n] interval items: something came within reach, the interval is not certified
 };
 inline size_t fetchPairCap(size_t n) { return n * 8; }
 inline size_t fetchLeafCap(size_t n) { return n * 16; }
@@ -42,9 +47,11 @@ inline size_t fetchLeafCap(size_t n) { return n * 16; }
 cudaError_t launchFetchStates(const FetchSceneDev &sc, const double *dStates, size_t n, const FetchScratch &w,
                               uint8_t *dValid, FetchCounters *dCtr, int numSms, cudaStream_t stream);
 
-// items: (edge << 32) | sample index k; k >= steps[edge] means the edge's `to` state
+// items: (edge << 32) | sample index k; k >= steps[edge] means the edge's `to` state.  dSlack (optional, [nItems]):
+// the item stands for an interval of samples around k over which the torso joint moves by at most .x and the arm
+// joints together by at most .y (radians, L1); w.touched[i] = 1 unless the whole interval is certainly free.
 cudaError_t launchFetchEdgeItems(const FetchSceneDev &sc, const double *dFrom, const double *dTo, const unsigned *dSteps,
-                                 const unsigned long long *dItems, size_t nItems, unsigned *dDead, const FetchScratch &w,
-                                 FetchCounters *dCtr, int numSms, cudaStream_t stream);
+                                 const unsigned long long *dItems, const float2 *dSlack, size_t nItems, unsigned *dDead,
+                                 const FetchScratch &w, FetchCounters *dCtr, int numSms, cudaStream_t stream);
 
 }  // namespace mplb

@@ -330,6 +330,66 @@ __device__ __forceinline__ void shapeExtents(const FetchShape &s, float e[3]) {
 }
 constexpr float kCullSlack = 1e-4f;  // metres; FP32 error of these tests is ~1e-6
 
+// A sphere-swept segment that contains the shape: exact for a capsule, the cylinder with its rim rounded, a box
+// swept along its longest side.  For the slender arm links this bounds distances far better than their boxes.
+__device__ __forceinline__ void shapeSweep(const FetchShape &s, int &axis, float &half, float &radius) {
+    if (s.type != 0) {
+        axis = 2;
+        half = (float)s.b;
+        radius = (float)s.a * 1.00001f;
+        return;
+    }
+    const float a = (float)s.a, b = (float)s.b, c = (float)s.c;
+    axis = (a >= b && a >= c) ? 0 : (b >= c ? 1 : 2);
+    half = axis == 0 ? a : axis == 1 ? b : c;
+    const float o1 = axis == 0 ? b : a, o2 = axis == 2 ? b : c;
+    radius = sqrtf(o1 * o1 + o2 * o2) * 1.00001f;
+}
+
+// distance between the segments c1 +- h1 u1 and c2 +- h2 u2 (Ericson, Real-Time Collision Detection 5.1.9)
+__device__ __forceinline__ float segmentDistance(const float c1[3], const float u1[3], float h1, const float c2[3],
+                                                 const float u2[3], float h2) {
+    float d1[3], d2[3], r[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        d1[i] = 2.f * h1 * u1[i];
+        d2[i] = 2.f * h2 * u2[i];
+        r[i] = (c1[i] - h1 * u1[i]) - (c2[i] - h2 * u2[i]);
+    }
+    const float a = d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2], e = d2[0] * d2[0] + d2[1] * d2[1] + d2[2] * d2[2];
+    const float f = d2[0] * r[0] + d2[1] * r[1] + d2[2] * r[2], c = d1[0] * r[0] + d1[1] * r[1] + d1[2] * r[2];
+    const float b = d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2];
+    float sN = 0.f, tN = 0.f;
+    const float eps = 1e-12f;
+    if (a <= eps && e <= eps) {
+        sN = tN = 0.f;
+    } else if (a <= eps) {
+        tN = fminf(fmaxf(f / e, 0.f), 1.f);
+    } else {
+        if (e <= eps) {
+            sN = fminf(fmaxf(-c / a, 0.f), 1.f);
+        } else {
+            const float den = a * e - b * b;
+            sN = den > eps * a * e ? fminf(fmaxf((b * f - c * e) / den, 0.f), 1.f) : 0.f;
+            tN = (b * sN + f) / e;
+            if (tN < 0.f) {
+                tN = 0.f;
+                sN = fminf(fmaxf(-c / a, 0.f), 1.f);
+            } else if (tN > 1.f) {
+                tN = 1.f;
+                sN = fminf(fmaxf((b - c) / a, 0.f), 1.f);
+            }
+        }
+    }
+    float dd = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float w = r[i] + sN * d1[i] - tN * d2[i];
+        dd += w * w;
+    }
+    return sqrtf(dd);
+}
+
 // boxes of two shapes given by their world frames: certainly disjoint?
 __device__ bool shapeBoxesDisjoint(const FetchShape &s1, const FrameD &f1, const FetchShape &s2, const FrameD &f2) {
     float e1[3], e2[3];
@@ -431,11 +491,15 @@ __device__ int exactLeaf(const FetchSceneDev &sc, const double *frames, unsigned
 __global__ void __launch_bounds__(128)
 fetchFkKernel(FetchSceneDev sc, const double *__restrict__ states, const double *__restrict__ from,
               const double *__restrict__ to, const unsigned *__restrict__ steps,
-              const unsigned long long *__restrict__ edgeItems, const unsigned *__restrict__ dead, unsigned long long n,
-              double *__restrict__ frames /* [n][12][12] */, unsigned char *__restrict__ selfHit, WorkList pairs,
-              FetchCounters *ctr) {
+              const unsigned long long *__restrict__ edgeItems, const float2 *__restrict__ slack,
+              const unsigned *__restrict__ dead, unsigned long long n, double *__restrict__ frames /* [n][12][12] */,
+              unsigned char *__restrict__ selfHit, unsigned char *__restrict__ touched, WorkList pairs, FetchCounters *ctr) {
     const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
+    // interval item: how far each geometry can stray from its pose at this sample (see FetchSceneDev::reach)
+    const float2 sl = slack ? slack[i] : make_float2(0.f, 0.f);
+    const bool interval = sl.x > 0.f || sl.y > 0.f;
+    unsigned near = 0;   // why the interval is not certified: 1 floor, 2 pair within reach, 4 pair boxes overlap, 8 / 16 same for the environment
     double q[8];
     if (edgeItems) {
         const unsigned long long it = edgeItems[i];
@@ -516,6 +580,8 @@ fetchFkKernel(FetchSceneDev sc, const double *__restrict__ states, const double 
     // selfCollision(): fetch_robot.hpp:502-584.  The floor test is exact here; pairs whose boxes are not
     // certainly disjoint go to the exact kernel (the verdict is an OR, so the order does not matter).
     int hit = gripperAxisZ < 0.30 ? 1 : 0;              // floorClearance_, fetch_robot.hpp:105,580
+    // (the gripper axis point moves like the gripper geometry at most)
+    if (interval && gripperAxisZ - 0.30 <= (double)(sl.x * sc.lift[9] + sl.y * sc.reach[9]) * 1.0001) near |= 1u;
     if (!hit) {
         for (int k = 0; k < 24; ++k) {
             const int a = kSelfPairs[k][0], b = kSelfPairs[k][1];
@@ -533,11 +599,28 @@ fetchFkKernel(FetchSceneDev sc, const double *__restrict__ states, const double 
             }
             float dist2;
             const float4 u0 = make_float4(1, 0, 0, 0), u1 = make_float4(0, 1, 0, 0), u2 = make_float4(0, 0, 1, 0);
-            if (!obbOverlap(u0, u1, u2, make_float4(e1[0] * 1.00001f, e1[1] * 1.00001f, e1[2] * 1.00001f, 0), u0, u1, u2,
-                            make_float4(e2[0] * 1.00001f, e2[1] * 1.00001f, e2[2] * 1.00001f, 0),
-                            make_float4(R[0][0], R[0][1], R[0][2], T[0]), make_float4(R[1][0], R[1][1], R[1][2], T[1]),
-                            make_float4(R[2][0], R[2][1], R[2][2], T[2]), kCullSlack, dist2))
+            const float gap = obbGap(u0, u1, u2, make_float4(e1[0] * 1.00001f, e1[1] * 1.00001f, e1[2] * 1.00001f, 0), u0, u1, u2,
+                                     make_float4(e2[0] * 1.00001f, e2[1] * 1.00001f, e2[2] * 1.00001f, 0),
+                                     make_float4(R[0][0], R[0][1], R[0][2], T[0]), make_float4(R[1][0], R[1][1], R[1][2], T[1]),
+                                     make_float4(R[2][0], R[2][1], R[2][2], T[2]), dist2);
+            // a second lower bound of the distance between the shapes: their swept segments
+            float clear = gap;
+            {
+                int ax1, ax2;
+                float h1, r1, h2, r2;
+                shapeSweep(sc.shapes[a], ax1, h1, r1);
+                shapeSweep(sc.shapes[b], ax2, h2, r2);
+                const float u1[3] = {A[ax1], A[3 + ax1], A[6 + ax1]}, u2[3] = {B[ax2], B[3 + ax2], B[6 + ax2]};
+                const float seg = segmentDistance(A + 9, u1, h1, B + 9, u2, h2) * 0.99999f - (r1 + r2) - 2e-6f;
+                clear = fmaxf(clear, seg);
+            }
+            if (clear > kCullSlack) {
+                // disjoint here; over the interval the two shapes approach by at most the sum of their displacements
+                if (interval && clear <= kCullSlack + ((sl.x * (sc.lift[a] + sc.lift[b]) + sl.y * (sc.reach[a] + sc.reach[b])) * 1.0001f + 1e-6f))
+                    near |= 2u;
                 continue;
+            }
+            near |= 4u;
             if (!listPush(pairs, (i << 8) | (unsigned)k)) {   // list full: decide it here
                 const int r = exactPair(sc, frames, i, k);
                 if (r < 0) atomicExch(&ctr->error, 1u);
@@ -549,6 +632,7 @@ fetchFkKernel(FetchSceneDev sc, const double *__restrict__ states, const double 
         }
     }
     selfHit[i] = (unsigned char)hit;
+    if (touched && near) touched[i] = (unsigned char)near;
 }
 
 // Kernel 2, one thread per listed (state, pair): exact shape-shape test
@@ -594,8 +678,8 @@ __global__ void fetchSurvivorsKernel(const unsigned char *__restrict__ selfHit, 
 // culled go to the exact kernel.
 __global__ void __launch_bounds__(128)
 fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsigned *__restrict__ survivors,
-               const unsigned *__restrict__ nSurvivors, unsigned *__restrict__ envHit, WorkList leaves,
-               unsigned *itemCounter, FetchCounters *ctr) {
+               const unsigned *__restrict__ nSurvivors, const float2 *__restrict__ slack, unsigned char *__restrict__ touched,
+               unsigned *__restrict__ envHit, WorkList leaves, unsigned *itemCounter, FetchCounters *ctr) {
     if (sc.nEnvNodes == 0) return;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned nItems = *nSurvivors * 12u;
@@ -611,6 +695,7 @@ fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsign
     float4 a0, a1, a2, ae;
     unsigned long long state = 0;
     int g = 0;
+    float reachSlack = kCullSlack;   // interval items: the box test is inflated by the geometry's displacement
     unsigned bv = 0;
     bool exhausted = false;
     for (;;) {
@@ -635,6 +720,11 @@ fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsign
                     a1 = make_float4((float)fp[1], (float)fp[5], (float)fp[9], (float)fp[7]);
                     a2 = make_float4((float)fp[2], (float)fp[6], (float)fp[10], (float)fp[11]);
                     ae = make_float4(e[0] * 1.00001f, e[1] * 1.00001f, e[2] * 1.00001f, 0);
+                    reachSlack = kCullSlack;
+                    if (slack) {
+                        const float2 sl = slack[state];
+                        reachSlack += (sl.x * sc.lift[g] + sl.y * sc.reach[g]) * 1.0001f + 1e-6f;
+                    }
                     stack[sp++][tx] = 0;
                 }
             }
@@ -651,7 +741,8 @@ fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsign
             ldg8(pn + 2, b2, be);
             ++bv;
             float dist2;
-            if (obbOverlap(a0, a1, a2, ae, b0, b1, b2, be, x0, x1, x2, kCullSlack, dist2)) {
+            const float gap = obbGap(a0, a1, a2, ae, b0, b1, b2, be, x0, x1, x2, dist2);
+            if (gap <= reachSlack) {
                 const int link = __float_as_int(be.w);
                 if (link >= 0) {
                     if (sp + 2 > 40) {
@@ -661,7 +752,10 @@ fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsign
                         stack[sp++][tx] = link + 1;
                         stack[sp++][tx] = link;
                     }
+                } else if (gap > kCullSlack) {
+                    touched[state] |= 8;   // a triangle's box within reach of the interval, but not of this sample
                 } else {
+                    if (touched) touched[state] |= 16;
                     const unsigned tri = (unsigned)(-(link + 1));
                     if (!listPush(leaves, (state << 28) | ((unsigned long long)g << 24) | tri)) {   // list full: decide it here
                         const int r = exactLeafSlow(sc, frames, state, g, tri);
@@ -714,20 +808,26 @@ __global__ void fetchEdgeReduceKernel(const unsigned char *__restrict__ selfHit,
 
 // the exact kernels' grids do not depend on the list lengths (grid-stride over the device-side counts)
 cudaError_t runFetch(const FetchSceneDev &sc, const double *dStates, const double *dFrom, const double *dTo,
-                     const unsigned *dSteps, const unsigned long long *dItems, const unsigned *dDead, size_t n,
-                     const FetchScratch &w, FetchCounters *dCtr, int numSms, cudaStream_t stream) {
+                     const unsigned *dSteps, const unsigned long long *dItems, const float2 *dSlack, const unsigned *dDead,
+                     size_t n, const FetchScratch &w, FetchCounters *dCtr, int numSms, cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(w.envHit, 0, n * sizeof(unsigned), stream);
     if (e != cudaSuccess) return e;
+    unsigned char *touched = dSlack ? w.touched : nullptr;
+    if (touched) {
+        e = cudaMemsetAsync(touched, 0, n, stream);
+        if (e != cudaSuccess) return e;
+    }
     e = cudaMemsetAsync(w.counts, 0, 4 * sizeof(unsigned), stream);
     if (e != cudaSuccess) return e;
     WorkList pairs{w.pairItems, w.counts, (unsigned)std::min<size_t>(w.pairCap, 0xffffffffu)};
     WorkList leaves{w.leafItems, w.counts + 1, (unsigned)std::min<size_t>(w.leafCap, 0xffffffffu)};
     const int exactGrid = numSms * 8;
-    fetchFkKernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(sc, dStates, dFrom, dTo, dSteps, dItems, dDead, n, w.frames,
-                                                                   w.selfHit, pairs, dCtr);
+    fetchFkKernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(sc, dStates, dFrom, dTo, dSteps, dItems, dSlack, dDead, n,
+                                                                   w.frames, w.selfHit, touched, pairs, dCtr);
     fetchPairKernel<<<exactGrid, 128, 0, stream>>>(sc, w.frames, pairs, w.selfHit, dCtr);
     fetchSurvivorsKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w.selfHit, n, w.survivors, w.counts + 2);
-    fetchEnvKernel<<<exactGrid, 128, 0, stream>>>(sc, w.frames, w.survivors, w.counts + 2, w.envHit, leaves, w.counts + 3, dCtr);
+    fetchEnvKernel<<<exactGrid, 128, 0, stream>>>(sc, w.frames, w.survivors, w.counts + 2, dSlack, touched, w.envHit, leaves,
+                                                  w.counts + 3, dCtr);
     fetchLeafKernel<<<exactGrid, 128, 0, stream>>>(sc, w.frames, leaves, w.envHit, dCtr);
     return cudaGetLastError();
 }
@@ -738,17 +838,17 @@ cudaError_t launchFetchStates(const FetchSceneDev &sc, const double *dStates, si
                               uint8_t *dValid, FetchCounters *dCtr, int numSms, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     if (n >= (1ull << 36)) return cudaErrorInvalidValue;   // work descriptors keep 36 bits for the state index
-    cudaError_t e = runFetch(sc, dStates, nullptr, nullptr, nullptr, nullptr, nullptr, n, w, dCtr, numSms, stream);
+    cudaError_t e = runFetch(sc, dStates, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, n, w, dCtr, numSms, stream);
     if (e != cudaSuccess) return e;
     fetchCombineKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w.selfHit, w.envHit, n, dValid);
     return cudaGetLastError();
 }
 
 cudaError_t launchFetchEdgeItems(const FetchSceneDev &sc, const double *dFrom, const double *dTo, const unsigned *dSteps,
-                                 const unsigned long long *dItems, size_t nItems, unsigned *dDead, const FetchScratch &w,
-                                 FetchCounters *dCtr, int numSms, cudaStream_t stream) {
+                                 const unsigned long long *dItems, const float2 *dSlack, size_t nItems, unsigned *dDead,
+                                 const FetchScratch &w, FetchCounters *dCtr, int numSms, cudaStream_t stream) {
     if (nItems == 0) return cudaSuccess;
-    cudaError_t e = runFetch(sc, nullptr, dFrom, dTo, dSteps, dItems, dDead, nItems, w, dCtr, numSms, stream);
+    cudaError_t e = runFetch(sc, nullptr, dFrom, dTo, dSteps, dItems, dSlack, dDead, nItems, w, dCtr, numSms, stream);
     if (e != cudaSuccess) return e;
     fetchEdgeReduceKernel<<<(unsigned)((nItems + 255) / 256), 256, 0, stream>>>(w.selfHit, w.envHit, dItems, nItems, dDead, dCtr);
     return cudaGetLastError();

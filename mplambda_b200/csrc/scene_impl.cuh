@@ -40,6 +40,10 @@ struct CallCtx {
     // the wire (cudaMemcpyAsync on pageable memory stages through one thread at ~10 GB/s)
     unsigned char *hBounce[2] = {nullptr, nullptr};
     cudaEvent_t bounceDone[2] = {nullptr, nullptr};
+    // pinned result buffers of pipelined rounds (Fetch edge intervals), grown on demand
+    unsigned char *hRes[2] = {nullptr, nullptr};
+    size_t hResCap[2] = {0, 0};
+    int reserveRes(int i, size_t bytes);
     unsigned long long *hWater = nullptr;  // pinned: per-slice arrival marks of a streamed batch
     std::vector<uint32_t> hSteps;
     ~CallCtx();
