@@ -77,3 +77,24 @@ def test_empty_environment_only_self_collision(oracle):
     Q = fetch_configs(20000, SEED + 1)
     want = np.array([oracle.FetchOracle.self_collision(q) == 0 for q in Q])
     assert (s.check_states(Q) == want).all()
+
+
+def test_edge_interval_certificates_at_extremes(autolab, oracle):
+    """isValid(from,to) is decided through interval certificates: zero-length and few-step edges, an empty batch,
+    a single edge, and a very fine resolution (~60 000 samples per edge) must still give the discrete verdict."""
+    frame = frame_from_option(FETCH_TASKS["fetch_task_001"]["env_frame"])
+    f = M.FetchScenario(frame, autolab, checkResolution=0.01)
+    orc = oracle.FetchOracle(autolab, frame, 0.01)
+    Q = fetch_configs(4096, SEED)
+    A = Q[f.check_states(Q)][:64]
+    assert f.check_edges(A, A).all()                                         # steps == 0: only `to`
+    B = A.copy()
+    B[:, 3] += np.arange(64) % 6 * 0.01 * 0.999                               # 0 .. 5 steps
+    assert (f.check_edges(A, B) == orc.check_edges(A, B)).all()
+    assert f.check_edges(np.zeros((0, 8)), np.zeros((0, 8))).shape == (0,)
+    C = fetch_configs(64, SEED + 9)
+    assert (f.check_edges(A[:1], C[:1]) == orc.check_edges(A[:1], C[:1])).all()
+    fine = M.FetchScenario(frame, autolab, checkResolution=0.0005)
+    got, evaluated = fine.check_edges(A[:32], C[:32], return_states_checked=True)
+    assert (got == oracle.FetchOracle(autolab, frame, 0.0005).check_edges(A[:32], C[:32])).all()
+    assert evaluated < fine.edge_steps(A[:32], C[:32]).sum() // 10             # certified, not enumerated

@@ -110,3 +110,32 @@ def test_clustered_keys_near_ties(oracle):
     idx, dist = nn.knearest(qs, 20)
     widx, wdist = oracle.nn_knearest(keys, qs, 20)
     assert (idx == widx).all() and (dist == wdist).all()
+
+
+def test_knearest_small_sets_and_duplicates(oracle):
+    """k larger than / equal to the number of keys, an empty query batch, odd k values around the sampled-threshold
+    path, and many identical keys (ties to the lowest index)."""
+    keys = se3_poses(37, LO, HI, 3)
+    qs = se3_poses(9, LO, HI, 4)
+    nn = M.Nigh(M.nn.SE3)
+    nn.insert(keys)
+    i, d = nn.knearest(qs, 50)
+    wi, wd = oracle.nn_knearest(keys, qs, 50)
+    assert (i == wi).all() and (d[:, :37] == wd[:, :37]).all() and (i[:, 37:] == -1).all() and np.isinf(d[:, 37:]).all()
+    i, d = nn.knearest(qs, 37)
+    wi, wd = oracle.nn_knearest(keys, qs, 37)
+    assert (i == wi).all() and (d == wd).all()
+    assert nn.knearest(qs[:0], 5)[0].shape == (0, 5)
+    keys = se3_poses(5000, LO, HI, 5)
+    nn2 = M.Nigh(M.nn.SE3)
+    nn2.insert(keys)
+    for k in (2, 3, 17, 64):
+        i, d = nn2.knearest(qs, k)
+        wi, wd = oracle.nn_knearest(keys, qs, k)
+        assert (i == wi).all() and (d == wd).all(), k
+    dup = np.repeat(keys[:10], 50, axis=0)
+    nn3 = M.Nigh(M.nn.SE3)
+    nn3.insert(dup)
+    i, d = nn3.knearest(keys[:10], 20)
+    wi, wd = oracle.nn_knearest(dup, keys[:10], 20)
+    assert (i == wi).all() and (d == wd).all()
