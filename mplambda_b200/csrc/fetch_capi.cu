@@ -184,9 +184,10 @@ struct FetchScene : SceneBase {
             MPLB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             c->events.push_back(ev);
         }
+        static const float kCap = std::getenv("MPLB_FETCH_CAP") ? (float)std::atof(std::getenv("MPLB_FETCH_CAP")) : 0.2f;
         std::vector<Interval> inflight[2];
         std::vector<unsigned char> forced[2] = {std::vector<unsigned char>(kBatch), std::vector<unsigned char>(kBatch)};
-        unsigned long long dbgHist[16][32] = {};
+        unsigned long long dbgHist[16][32] = {}, dbgPair[32] = {};
         auto submit = [&](int slot) -> int {
             std::vector<Interval> &b = inflight[slot];
             items.resize(b.size());
@@ -201,7 +202,7 @@ struct FetchScene : SceneBase {
                 // an interval over which the gripper can stray by more than ~12 cm is practically never certified
                 // (measured: 0-2 % from 32 samples up) and its inflated traversal costs more than a plain test:
                 // evaluate its middle sample plainly and split it unconditionally
-                forced[slot][i] = v.hi > v.lo && slack[i].x + slack[i].y * 1.2f > 0.12f;
+                forced[slot][i] = v.hi > v.lo && slack[i].x + slack[i].y * 1.2f > kCap;
                 if (forced[slot][i]) slack[i] = make_float2(0.f, 0.f);
             }
             MPLB_CUDA(cudaMemcpyAsync(c->aux3.ptr, items.data(), items.size() * 8, cudaMemcpyHostToDevice, c->stream));
@@ -230,11 +231,25 @@ struct FetchScene : SceneBase {
                     int cls = 0;
                     for (uint32_t len = v.hi - v.lo + 1; len > 1; len >>= 1) ++cls;
                     ++dbgHist[std::min(cls, 15)][t[i] & 31];
+                    if (t[i] & 0x80) ++dbgPair[t[i] & 31];
                 }
                 if (dead[v.e] || v.hi <= v.lo || !(t[i] || forced[slot][i])) continue;   // dead, a single sample, or certified
                 const uint32_t mid = v.lo + (v.hi - v.lo) / 2;
-                if (mid > v.lo) next.push_back({v.e, v.lo, mid - 1});
-                if (mid < v.hi) next.push_back({v.e, mid + 1, v.hi});
+                // a split that was forced goes straight to pieces short enough to stand a chance (<= 2 H + 1 samples,
+                // H the half width at which the gripper's stray reaches the cap), not through log2 plain halvings
+                uint32_t piece = 0xffffffffu;
+                if (forced[slot][i]) {
+                    const double perSample = ((double)dArm[v.e] * 1.2 + (double)dTorso[v.e]) / (double)c->hSteps[v.e];
+                    const double H = perSample > 0 ? std::floor((double)kCap / perSample) : 1e9;
+                    piece = (uint32_t)std::min(1e9, 2.0 * std::max(H, 1.0) + 1.0);
+                }
+                auto cut = [&](uint32_t lo, uint32_t hi) {   // [lo, hi] into equal pieces of at most `piece` samples
+                    const uint64_t len = (uint64_t)hi - lo + 1, parts = (len + piece - 1) / piece;
+                    for (uint64_t p = 0; p < parts; ++p)
+                        next.push_back({v.e, lo + (uint32_t)(p * len / parts), lo + (uint32_t)((p + 1) * len / parts) - 1});
+                };
+                if (mid > v.lo) cut(v.lo, mid - 1);
+                if (mid < v.hi) cut(mid + 1, v.hi);
             }
             b.clear();
             return MPLB_OK;
@@ -266,6 +281,9 @@ struct FetchScene : SceneBase {
             cur.swap(next);
             next.clear();
         }
+        if (std::getenv("MPLB_FETCH_DEBUG"))
+            for (int k = 0; k < 24; ++k)
+                if (dbgPair[k]) std::fprintf(stderr, "[fetch intervals] pair %d kept %llu intervals from being certified\n", k, dbgPair[k]);
         if (std::getenv("MPLB_FETCH_DEBUG"))
             for (int cls = 0; cls < 16; ++cls) {
                 unsigned long long tot = 0, by[5] = {0, 0, 0, 0, 0};

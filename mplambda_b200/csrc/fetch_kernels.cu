@@ -346,6 +346,31 @@ __device__ __forceinline__ void shapeSweep(const FetchShape &s, int &axis, float
     radius = sqrtf(o1 * o1 + o2 * o2) * 1.00001f;
 }
 
+// lower bound of the distance between the segment p0 p1 and the box [-e, e], both in the box's frame: the distance
+// from a point of the segment to the box is convex along the segment and 1-Lipschitz, so a ternary search brackets
+// its minimum and the bracket's length bounds what the search can still be off by
+// (cylinder == true: the solid is the cylinder of radius e[0] and half length e[2] around the frame's z axis)
+__device__ __forceinline__ float segmentBoxDistance(const float p0[3], const float p1[3], const float e[3], bool cylinder = false) {
+    auto at = [&](float t) {
+        const float x = p0[0] + t * (p1[0] - p0[0]), y = p0[1] + t * (p1[1] - p0[1]), z = p0[2] + t * (p1[2] - p0[2]);
+        if (cylinder) {
+            const float dr = fmaxf(sqrtf(x * x + y * y) - e[0], 0.f), dz = fmaxf(fabsf(z) - e[2], 0.f);
+            return sqrtf(dr * dr + dz * dz);
+        }
+        const float wx = fmaxf(fabsf(x) - e[0], 0.f), wy = fmaxf(fabsf(y) - e[1], 0.f), wz = fmaxf(fabsf(z) - e[2], 0.f);
+        return sqrtf(wx * wx + wy * wy + wz * wz);
+    };
+    float lo = 0.f, hi = 1.f;
+#pragma unroll 1
+    for (int it = 0; it < 14; ++it) {
+        const float m1 = lo + (hi - lo) * (1.f / 3.f), m2 = hi - (hi - lo) * (1.f / 3.f);
+        if (at(m1) <= at(m2)) hi = m2;
+        else lo = m1;
+    }
+    const float len = sqrtf((p1[0] - p0[0]) * (p1[0] - p0[0]) + (p1[1] - p0[1]) * (p1[1] - p0[1]) + (p1[2] - p0[2]) * (p1[2] - p0[2]));
+    return at(0.5f * (lo + hi)) - (hi - lo) * len;
+}
+
 // distance between the segments c1 +- h1 u1 and c2 +- h2 u2 (Ericson, Real-Time Collision Detection 5.1.9)
 __device__ __forceinline__ float segmentDistance(const float c1[3], const float u1[3], float h1, const float c2[3],
                                                  const float u2[3], float h2) {
@@ -499,6 +524,9 @@ fetchFkKernel(FetchSceneDev sc, const double *__restrict__ states, const double 
     // interval item: how far each geometry can stray from its pose at this sample (see FetchSceneDev::reach)
     const float2 sl = slack ? slack[i] : make_float2(0.f, 0.f);
     const bool interval = sl.x > 0.f || sl.y > 0.f;
+#ifdef MPLB_FETCH_PAIRDBG
+    int firstOverlap = 0;
+#endif
     unsigned near = 0;   // why the interval is not certified: 1 floor, 2 pair within reach, 4 pair boxes overlap, 8 / 16 same for the environment
     double q[8];
     if (edgeItems) {
@@ -613,6 +641,41 @@ fetchFkKernel(FetchSceneDev sc, const double *__restrict__ states, const double 
                 const float u1[3] = {A[ax1], A[3 + ax1], A[6 + ax1]}, u2[3] = {B[ax2], B[3 + ax2], B[6 + ax2]};
                 const float seg = segmentDistance(A + 9, u1, h1, B + 9, u2, h2) * 0.99999f - (r1 + r2) - 2e-6f;
                 clear = fmaxf(clear, seg);
+                // One shape a box (torso, gripper) or a wide cylinder (base, head), whose swept segment is a poor bound
+                // (the head's would add a 25 cm dome above and below it): the other shape's segment against the solid
+                // itself.  boxA / boxB: "use this shape as the solid".
+                const bool wideA = sc.shapes[a].type == 2 && sc.shapes[a].a > 0.1, wideB = sc.shapes[b].type == 2 && sc.shapes[b].a > 0.1;
+                bool boxA = sc.shapes[a].type == 0, boxB = sc.shapes[b].type == 0;
+                bool cyl = false;
+                if (!boxA && !boxB && wideA != wideB) {
+                    boxA = wideA;
+                    boxB = wideB;
+                    cyl = true;
+                } else if (boxA != boxB && (boxA ? wideB : wideA)) {   // box against wide cylinder: the cylinder is the solid
+                    boxA = wideA;
+                    boxB = wideB;
+                    cyl = true;
+                }
+                if (boxA != boxB) {
+                    const float *X = boxA ? A : B, *Y = boxA ? B : A;           // X: the box, Y: the swept segment
+                    const float *uy = boxA ? u2 : u1;
+                    const float hy = boxA ? h2 : h1, ry = boxA ? r2 : r1;
+                    float p0[3], p1[3];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {   // X^T (y - cx): box axes are the columns of X's rotation
+                        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float dc = Y[9 + c] - X[9 + c];
+                            s0 += X[3 * c + r] * (dc - hy * uy[c]);
+                            s1 += X[3 * c + r] * (dc + hy * uy[c]);
+                        }
+                        p0[r] = s0;
+                        p1[r] = s1;
+                    }
+                    const float *ex = boxA ? e1 : e2;   // (a cylinder's extents are radius, radius, half length)
+                    clear = fmaxf(clear, segmentBoxDistance(p0, p1, ex, cyl) * 0.99999f - ry - 4e-6f);
+                }
             }
             if (clear > kCullSlack) {
                 // disjoint here; over the interval the two shapes approach by at most the sum of their displacements
@@ -620,6 +683,9 @@ fetchFkKernel(FetchSceneDev sc, const double *__restrict__ states, const double 
                     near |= 2u;
                 continue;
             }
+#ifdef MPLB_FETCH_PAIRDBG
+            if (!(near & 4u)) firstOverlap = k;
+#endif
             near |= 4u;
             if (!listPush(pairs, (i << 8) | (unsigned)k)) {   // list full: decide it here
                 const int r = exactPair(sc, frames, i, k);
@@ -632,6 +698,9 @@ fetchFkKernel(FetchSceneDev sc, const double *__restrict__ states, const double 
         }
     }
     selfHit[i] = (unsigned char)hit;
+#ifdef MPLB_FETCH_PAIRDBG
+    if (touched && (near & 4u)) near = 0x80u | (unsigned)firstOverlap;   // diagnostic build: which pair could not be bounded away
+#endif
     if (touched && near) touched[i] = (unsigned char)near;
 }
 
