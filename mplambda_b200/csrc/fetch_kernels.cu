@@ -524,9 +524,6 @@ fetchFkKernel(FetchSceneDev sc, const double *__restrict__ states, const double 
     // interval item: how far each geometry can stray from its pose at this sample (see FetchSceneDev::reach)
     const float2 sl = slack ? slack[i] : make_float2(0.f, 0.f);
     const bool interval = sl.x > 0.f || sl.y > 0.f;
-#ifdef MPLB_FETCH_PAIRDBG
-    int firstOverlap = 0;
-#endif
     unsigned near = 0;   // why the interval is not certified: 1 floor, 2 pair within reach, 4 pair boxes overlap, 8 / 16 same for the environment
     double q[8];
     if (edgeItems) {
@@ -631,63 +628,13 @@ fetchFkKernel(FetchSceneDev sc, const double *__restrict__ states, const double 
                                      make_float4(e2[0] * 1.00001f, e2[1] * 1.00001f, e2[2] * 1.00001f, 0),
                                      make_float4(R[0][0], R[0][1], R[0][2], T[0]), make_float4(R[1][0], R[1][1], R[1][2], T[1]),
                                      make_float4(R[2][0], R[2][1], R[2][2], T[2]), dist2);
-            // a second lower bound of the distance between the shapes: their swept segments
-            float clear = gap;
-            {
-                int ax1, ax2;
-                float h1, r1, h2, r2;
-                shapeSweep(sc.shapes[a], ax1, h1, r1);
-                shapeSweep(sc.shapes[b], ax2, h2, r2);
-                const float u1[3] = {A[ax1], A[3 + ax1], A[6 + ax1]}, u2[3] = {B[ax2], B[3 + ax2], B[6 + ax2]};
-                const float seg = segmentDistance(A + 9, u1, h1, B + 9, u2, h2) * 0.99999f - (r1 + r2) - 2e-6f;
-                clear = fmaxf(clear, seg);
-                // One shape a box (torso, gripper) or a wide cylinder (base, head), whose swept segment is a poor bound
-                // (the head's would add a 25 cm dome above and below it): the other shape's segment against the solid
-                // itself.  boxA / boxB: "use this shape as the solid".
-                const bool wideA = sc.shapes[a].type == 2 && sc.shapes[a].a > 0.1, wideB = sc.shapes[b].type == 2 && sc.shapes[b].a > 0.1;
-                bool boxA = sc.shapes[a].type == 0, boxB = sc.shapes[b].type == 0;
-                bool cyl = false;
-                if (!boxA && !boxB && wideA != wideB) {
-                    boxA = wideA;
-                    boxB = wideB;
-                    cyl = true;
-                } else if (boxA != boxB && (boxA ? wideB : wideA)) {   // box against wide cylinder: the cylinder is the solid
-                    boxA = wideA;
-                    boxB = wideB;
-                    cyl = true;
-                }
-                if (boxA != boxB) {
-                    const float *X = boxA ? A : B, *Y = boxA ? B : A;           // X: the box, Y: the swept segment
-                    const float *uy = boxA ? u2 : u1;
-                    const float hy = boxA ? h2 : h1, ry = boxA ? r2 : r1;
-                    float p0[3], p1[3];
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {   // X^T (y - cx): box axes are the columns of X's rotation
-                        float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            const float dc = Y[9 + c] - X[9 + c];
-                            s0 += X[3 * c + r] * (dc - hy * uy[c]);
-                            s1 += X[3 * c + r] * (dc + hy * uy[c]);
-                        }
-                        p0[r] = s0;
-                        p1[r] = s1;
-                    }
-                    const float *ex = boxA ? e1 : e2;   // (a cylinder's extents are radius, radius, half length)
-                    clear = fmaxf(clear, segmentBoxDistance(p0, p1, ex, cyl) * 0.99999f - ry - 4e-6f);
-                }
-            }
-            if (clear > kCullSlack) {
-                // disjoint here; over the interval the two shapes approach by at most the sum of their displacements
-                if (interval && clear <= kCullSlack + ((sl.x * (sc.lift[a] + sc.lift[b]) + sl.y * (sc.reach[a] + sc.reach[b])) * 1.0001f + 1e-6f))
-                    near |= 2u;
-                continue;
-            }
-#ifdef MPLB_FETCH_PAIRDBG
-            if (!(near & 4u)) firstOverlap = k;
-#endif
-            near |= 4u;
+            // how far the pair has to be apart for this item to be done with it (the interval's reach on top of the cull slack)
+            const float need = kCullSlack + (interval ? (sl.x * (sc.lift[a] + sc.lift[b]) + sl.y * (sc.reach[a] + sc.reach[b])) * 1.0001f + 1e-6f : 0.f);
+            // Boxes farther apart than that: nothing to do.  Otherwise the exact kernel looks closer (tighter distance
+            // bounds first, MPR if those do not separate the shapes either) and reports back through `touched`.
+            if (gap > need) continue;
             if (!listPush(pairs, (i << 8) | (unsigned)k)) {   // list full: decide it here
+                near |= 4u;
                 const int r = exactPair(sc, frames, i, k);
                 if (r < 0) atomicExch(&ctr->error, 1u);
                 if (r == 1) {
@@ -698,23 +645,97 @@ fetchFkKernel(FetchSceneDev sc, const double *__restrict__ states, const double 
         }
     }
     selfHit[i] = (unsigned char)hit;
-#ifdef MPLB_FETCH_PAIRDBG
-    if (touched && (near & 4u)) near = 0x80u | (unsigned)firstOverlap;   // diagnostic build: which pair could not be bounded away
-#endif
     if (touched && near) touched[i] = (unsigned char)near;
 }
 
-// Kernel 2, one thread per listed (state, pair): exact shape-shape test
+// Lower bound of the distance between geometries a and b of one state, from their FP32 frames (rotation row-major in
+// [0..8], centre in [9..11]): the distance of the two swept segments, and -- when one shape is a box (torso, gripper)
+// or a wide cylinder (base, head), whose swept segment is a poor bound (the head's adds a 25 cm dome above and below
+// it) -- the distance from the other's segment to that solid itself.
+__device__ float pairClearance(const FetchSceneDev &sc, int a, int b, const float *A, const float *B) {
+    float e1[3], e2[3];
+    shapeExtents(sc.shapes[a], e1);
+    shapeExtents(sc.shapes[b], e2);
+    int ax1, ax2;
+    float h1, r1, h2, r2;
+    shapeSweep(sc.shapes[a], ax1, h1, r1);
+    shapeSweep(sc.shapes[b], ax2, h2, r2);
+    const float u1[3] = {A[ax1], A[3 + ax1], A[6 + ax1]}, u2[3] = {B[ax2], B[3 + ax2], B[6 + ax2]};
+    float clear = segmentDistance(A + 9, u1, h1, B + 9, u2, h2) * 0.99999f - (r1 + r2) - 2e-6f;
+    const bool wideA = sc.shapes[a].type == 2 && sc.shapes[a].a > 0.1, wideB = sc.shapes[b].type == 2 && sc.shapes[b].a > 0.1;
+    bool solidA = sc.shapes[a].type == 0, solidB = sc.shapes[b].type == 0;   // "use this shape as the solid"
+    bool cyl = false;
+    if (!solidA && !solidB && wideA != wideB) {
+        solidA = wideA;
+        solidB = wideB;
+        cyl = true;
+    } else if (solidA != solidB && (solidA ? wideB : wideA)) {   // box against wide cylinder: the cylinder is the solid
+        solidA = wideA;
+        solidB = wideB;
+        cyl = true;
+    }
+    if (solidA != solidB) {
+        const float *X = solidA ? A : B, *Y = solidA ? B : A;           // X: the solid, Y: the swept segment
+        const float *uy = solidA ? u2 : u1;
+        const float hy = solidA ? h2 : h1, ry = solidA ? r2 : r1;
+        float p0[3], p1[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {   // X^T (y - cx): the solid's axes are the columns of X's rotation
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float dc = Y[9 + c] - X[9 + c];
+                s0 += X[3 * c + r] * (dc - hy * uy[c]);
+                s1 += X[3 * c + r] * (dc + hy * uy[c]);
+            }
+            p0[r] = s0;
+            p1[r] = s1;
+        }
+        const float *ex = solidA ? e1 : e2;   // (a cylinder's extents are radius, radius, half length)
+        clear = fmaxf(clear, segmentBoxDistance(p0, p1, ex, cyl) * 0.99999f - ry - 4e-6f);
+    }
+    return clear;
+}
+
+// Kernel 2, one thread per listed (state, pair) whose boxes are within reach of each other: tighter distance bounds
+// first (they settle most of them), the exact shape-shape test if the shapes may touch at this very state
 __global__ void __launch_bounds__(128)
-fetchPairKernel(FetchSceneDev sc, const double *__restrict__ frames, WorkList pairs, unsigned char *selfHit,
-                FetchCounters *ctr) {
+fetchPairKernel(FetchSceneDev sc, const double *__restrict__ frames, WorkList pairs, const float2 *__restrict__ slack,
+                unsigned char *touched, unsigned char *selfHit, FetchCounters *ctr) {
     const unsigned n = min(*pairs.count, pairs.capacity);
     unsigned tested = 0;
     for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         const unsigned long long v = pairs.items[j];
         const unsigned long long state = v >> 8;
         if (selfHit[state]) continue;   // already colliding (floor, or another pair)
-        const int r = exactPair(sc, frames, state, (int)(v & 255));
+        const int k = (int)(v & 255), a = kSelfPairs[k][0], b = kSelfPairs[k][1];
+        float A[12], B[12];
+        {
+            const double *fa = frames + state * 144 + 12 * a, *fb = frames + state * 144 + 12 * b;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    A[3 * r + c] = (float)fa[4 * r + c];
+                    B[3 * r + c] = (float)fb[4 * r + c];
+                }
+                A[9 + r] = (float)fa[4 * r + 3];
+                B[9 + r] = (float)fb[4 * r + 3];
+            }
+        }
+        float need = kCullSlack;
+        if (slack) {
+            const float2 sl = slack[state];
+            need += (sl.x * (sc.lift[a] + sc.lift[b]) + sl.y * (sc.reach[a] + sc.reach[b])) * 1.0001f + 1e-6f;
+        }
+        const float clear = pairClearance(sc, a, b, A, B);
+        if (clear > need) continue;                  // apart, and over the whole interval
+        if (clear > kCullSlack) {                    // apart here, but not certainly over the interval
+            if (touched) touched[state] |= 2;
+            continue;
+        }
+        if (touched) touched[state] |= 4;
+        const int r = exactPair(sc, frames, state, k);
         ++tested;
         if (r < 0) atomicExch(&ctr->error, 1u);
         if (r == 1) selfHit[state] = 1;
@@ -893,7 +914,7 @@ cudaError_t runFetch(const FetchSceneDev &sc, const double *dStates, const doubl
     const int exactGrid = numSms * 8;
     fetchFkKernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(sc, dStates, dFrom, dTo, dSteps, dItems, dSlack, dDead, n,
                                                                    w.frames, w.selfHit, touched, pairs, dCtr);
-    fetchPairKernel<<<exactGrid, 128, 0, stream>>>(sc, w.frames, pairs, w.selfHit, dCtr);
+    fetchPairKernel<<<exactGrid, 128, 0, stream>>>(sc, w.frames, pairs, dSlack, touched, w.selfHit, dCtr);
     fetchSurvivorsKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w.selfHit, n, w.survivors, w.counts + 2);
     fetchEnvKernel<<<exactGrid, 128, 0, stream>>>(sc, w.frames, w.survivors, w.counts + 2, dSlack, touched, w.envHit, leaves,
                                                   w.counts + 3, dCtr);
