@@ -766,11 +766,23 @@ __global__ void fetchSurvivorsKernel(const unsigned char *__restrict__ selfHit, 
 // tests against one shape's box) at a time and takes the next (surviving state, geometry) item the moment
 // its stack runs dry, so lanes stay busy although traversal depths differ wildly.  Leaves that cannot be
 // culled go to the exact kernel.
-__global__ void __launch_bounds__(128)
+// kSmemNodes: the whole environment hierarchy is staged in shared memory (80-byte node stride: conflict free for
+// lanes on different nodes).  The traversals are a dozen box tests long and were bound by the latency of the node
+// loads (ncu: long-scoreboard 6.8 warps per issue at 10 warps / SM), which shared memory cuts by an order of
+// magnitude; AUTOLAB's 1 256 nodes take 100 KB.  Larger environments use the global-memory variant.
+constexpr int kEnvThreads = 384, kEnvStack = 40;
+template <bool kSmemNodes>
+__global__ void __launch_bounds__(kSmemNodes ? kEnvThreads : 128)
 fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsigned *__restrict__ survivors,
                const unsigned *__restrict__ nSurvivors, const float2 *__restrict__ slack, unsigned char *__restrict__ touched,
                unsigned *__restrict__ envHit, WorkList leaves, unsigned *itemCounter, FetchCounters *ctr) {
     if (sc.nEnvNodes == 0) return;
+    extern __shared__ __align__(16) unsigned char envSmem[];
+    float4 *nodesS = reinterpret_cast<float4 *>(envSmem);
+    if (kSmemNodes) {
+        for (int i = threadIdx.x; i < sc.nEnvNodes * 4; i += blockDim.x) nodesS[(i >> 2) * 5 + (i & 3)] = __ldg(sc.envNodes + i);
+        __syncthreads();
+    }
     const unsigned lane = threadIdx.x & 31u;
     const unsigned nItems = *nSurvivors * 12u;
     const float4 x0 = make_float4((float)sc.envFrame[0], (float)sc.envFrame[1], (float)sc.envFrame[2], (float)sc.envFrame[3]);
@@ -778,9 +790,11 @@ fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsign
     const float4 x2 = make_float4((float)sc.envFrame[8], (float)sc.envFrame[9], (float)sc.envFrame[10], (float)sc.envFrame[11]);
     // the per-lane stack lives in shared memory ([level][thread]: conflict free); as a local array it cost
     // 15 M local-memory sectors and 111 MB of DRAM write-back per 65,536-state launch (ncu)
-    __shared__ int stackS[40][128];
-    int (*stack)[128] = stackS;
-    const unsigned tx = threadIdx.x;
+    __shared__ int stackG[kSmemNodes ? 1 : kEnvStack][kSmemNodes ? 1 : 128];
+    // [level][thread]; with the nodes in shared memory the stack follows them in the dynamic allocation
+    int *stackBase = kSmemNodes ? reinterpret_cast<int *>(nodesS + (size_t)sc.nEnvNodes * 5) : &stackG[0][0];
+    const unsigned tx = threadIdx.x, nThreads = blockDim.x;
+    auto stackAt = [&](int level) -> int & { return stackBase[level * nThreads + tx]; };
     int sp = 0;
     float4 a0, a1, a2, ae;
     unsigned long long state = 0;
@@ -815,7 +829,7 @@ fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsign
                         const float2 sl = slack[state];
                         reachSlack += (sl.x * sc.lift[g] + sl.y * sc.reach[g]) * 1.0001f + 1e-6f;
                     }
-                    stack[sp++][tx] = 0;
+                    stackAt(sp++) = 0;
                 }
             }
         }
@@ -824,23 +838,28 @@ fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsign
             continue;
         }
         if (sp > 0) {
-            const int node = stack[--sp][tx];
-            const float4 *pn = sc.envNodes + 4 * (size_t)node;
+            const int node = stackAt(--sp);
             float4 b0, b1, b2, be;
-            ldg8(pn, b0, b1);
-            ldg8(pn + 2, b2, be);
+            if (kSmemNodes) {
+                const float4 *pn = nodesS + 5 * (size_t)node;
+                b0 = pn[0]; b1 = pn[1]; b2 = pn[2]; be = pn[3];
+            } else {
+                const float4 *pn = sc.envNodes + 4 * (size_t)node;
+                ldg8(pn, b0, b1);
+                ldg8(pn + 2, b2, be);
+            }
             ++bv;
             float dist2;
             const float gap = obbGap(a0, a1, a2, ae, b0, b1, b2, be, x0, x1, x2, dist2);
             if (gap <= reachSlack) {
                 const int link = __float_as_int(be.w);
                 if (link >= 0) {
-                    if (sp + 2 > 40) {
+                    if (sp + 2 > kEnvStack) {
                         atomicExch(&ctr->error, 1u);
                         sp = 0;
                     } else {
-                        stack[sp++][tx] = link + 1;
-                        stack[sp++][tx] = link;
+                        stackAt(sp++) = link + 1;
+                        stackAt(sp++) = link;
                     }
                 } else if (gap > kCullSlack) {
                     touched[state] |= 8;   // a triangle's box within reach of the interval, but not of this sample
@@ -916,8 +935,16 @@ cudaError_t runFetch(const FetchSceneDev &sc, const double *dStates, const doubl
                                                                    w.frames, w.selfHit, touched, pairs, dCtr);
     fetchPairKernel<<<exactGrid, 128, 0, stream>>>(sc, w.frames, pairs, dSlack, touched, w.selfHit, dCtr);
     fetchSurvivorsKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w.selfHit, n, w.survivors, w.counts + 2);
-    fetchEnvKernel<<<exactGrid, 128, 0, stream>>>(sc, w.frames, w.survivors, w.counts + 2, dSlack, touched, w.envHit, leaves,
-                                                  w.counts + 3, dCtr);
+    const size_t envSmemBytes = (size_t)sc.nEnvNodes * 80 + (size_t)kEnvStack * kEnvThreads * sizeof(int);
+    if (envSmemBytes <= 200 * 1024) {
+        e = cudaFuncSetAttribute(fetchEnvKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)envSmemBytes);
+        if (e != cudaSuccess) return e;
+        fetchEnvKernel<true><<<numSms, kEnvThreads, envSmemBytes, stream>>>(sc, w.frames, w.survivors, w.counts + 2, dSlack, touched,
+                                                                           w.envHit, leaves, w.counts + 3, dCtr);
+    } else {
+        fetchEnvKernel<false><<<exactGrid, 128, 0, stream>>>(sc, w.frames, w.survivors, w.counts + 2, dSlack, touched, w.envHit,
+                                                             leaves, w.counts + 3, dCtr);
+    }
     fetchLeafKernel<<<exactGrid, 128, 0, stream>>>(sc, w.frames, leaves, w.envHit, dCtr);
     return cudaGetLastError();
 }
