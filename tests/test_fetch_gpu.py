@@ -98,3 +98,22 @@ def test_edge_interval_certificates_at_extremes(autolab, oracle):
     got, evaluated = fine.check_edges(A[:32], C[:32], return_states_checked=True)
     assert (got == oracle.FetchOracle(autolab, frame, 0.0005).check_edges(A[:32], C[:32])).all()
     assert evaluated < fine.edge_steps(A[:32], C[:32]).sum() // 10             # certified, not enumerated
+
+
+def test_large_environment_uses_the_global_memory_traversal(scenes, oracle):
+    """An environment whose hierarchy does not fit in shared memory (the Apartment mesh, 74 228 nodes, shrunk to
+    room size around the robot) goes through the global-memory variant of the environment kernel."""
+    env = scenes["apartment"][0] * 0.012
+    env = env - env.reshape(-1, 3).mean(axis=0) + np.array([0.9, 0.0, 0.6])
+    frame = np.hstack([np.eye(3), np.zeros((3, 1))])
+    f = M.FetchScenario(frame, env, checkResolution=0.01)
+    orc = oracle.FetchOracle(env, frame, 0.01)
+    Q = fetch_configs(6000, SEED + 3)
+    got = f.check_states(Q)
+    want = orc.check_states(Q)
+    assert (got == want).all(), np.nonzero(got != want)[0][:10]
+    self_only = np.array([oracle.FetchOracle.self_collision(q) == 0 for q in Q[:2000]])
+    assert (want[:2000] != self_only).any()                                   # the environment really decides some
+    A = Q[got][:200]
+    B = fetch_configs(len(A), SEED + 4)
+    assert (f.check_edges(A, B) == orc.check_edges(A, B)).all()
