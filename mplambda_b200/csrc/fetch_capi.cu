@@ -187,12 +187,14 @@ struct FetchScene : SceneBase {
         static const float kCap = std::getenv("MPLB_FETCH_CAP") ? (float)std::atof(std::getenv("MPLB_FETCH_CAP")) : 0.2f;
         std::vector<Interval> inflight[2];
         std::vector<unsigned char> forced[2] = {std::vector<unsigned char>(kBatch), std::vector<unsigned char>(kBatch)};
-        unsigned long long dbgHist[16][32] = {}, dbgPair[32] = {};
+        unsigned long long dbgHist[16][32] = {};
         auto submit = [&](int slot) -> int {
             std::vector<Interval> &b = inflight[slot];
             items.resize(b.size());
             slack.resize(b.size());
-            for (size_t i = 0; i < b.size(); ++i) {
+            // (the host side of a round is as much work as the device side: all cores)
+#pragma omp parallel for schedule(static) if (b.size() >= 4096)
+            for (long long i = 0; i < (long long)b.size(); ++i) {
                 const Interval &v = b[i];
                 const uint32_t st = c->hSteps[v.e], mid = v.lo + (v.hi - v.lo) / 2;
                 items[i] = ((unsigned long long)v.e << 32) | mid;
@@ -225,31 +227,37 @@ struct FetchScene : SceneBase {
             const unsigned char *t = c->hRes[slot];
             std::memcpy(dead.data(), c->hRes[slot] + kBatch, n * 4);
             static const bool dbg = std::getenv("MPLB_FETCH_DEBUG") != nullptr;
-            for (size_t i = 0; i < b.size(); ++i) {
-                const Interval &v = b[i];
-                if (dbg && !dead[v.e] && v.hi > v.lo) {
-                    int cls = 0;
-                    for (uint32_t len = v.hi - v.lo + 1; len > 1; len >>= 1) ++cls;
-                    ++dbgHist[std::min(cls, 15)][t[i] & 31];
-                    if (t[i] & 0x80) ++dbgPair[t[i] & 31];
+#pragma omp parallel if (b.size() >= 4096 && !dbg)
+            {
+                std::vector<Interval> mine;
+#pragma omp for schedule(static) nowait
+                for (long long i = 0; i < (long long)b.size(); ++i) {
+                    const Interval &v = b[i];
+                    if (dbg && !dead[v.e] && v.hi > v.lo) {
+                        int cls = 0;
+                        for (uint32_t len = v.hi - v.lo + 1; len > 1; len >>= 1) ++cls;
+                        ++dbgHist[std::min(cls, 15)][t[i] & 31];
+                    }
+                    if (dead[v.e] || v.hi <= v.lo || !(t[i] || forced[slot][i])) continue;   // dead, a single sample, or certified
+                    const uint32_t mid = v.lo + (v.hi - v.lo) / 2;
+                    // a split that was forced goes straight to pieces short enough to stand a chance (<= 2 H + 1 samples,
+                    // H the half width at which the gripper's stray reaches the cap), not through log2 plain halvings
+                    uint32_t piece = 0xffffffffu;
+                    if (forced[slot][i]) {
+                        const double perSample = ((double)dArm[v.e] * 1.2 + (double)dTorso[v.e]) / (double)c->hSteps[v.e];
+                        const double H = perSample > 0 ? std::floor((double)kCap / perSample) : 1e9;
+                        piece = (uint32_t)std::min(1e9, 2.0 * std::max(H, 1.0) + 1.0);
+                    }
+                    auto cut = [&](uint32_t lo, uint32_t hi) {   // [lo, hi] into equal pieces of at most `piece` samples
+                        const uint64_t len = (uint64_t)hi - lo + 1, parts = (len + piece - 1) / piece;
+                        for (uint64_t p = 0; p < parts; ++p)
+                            mine.push_back({v.e, lo + (uint32_t)(p * len / parts), lo + (uint32_t)((p + 1) * len / parts) - 1});
+                    };
+                    if (mid > v.lo) cut(v.lo, mid - 1);
+                    if (mid < v.hi) cut(mid + 1, v.hi);
                 }
-                if (dead[v.e] || v.hi <= v.lo || !(t[i] || forced[slot][i])) continue;   // dead, a single sample, or certified
-                const uint32_t mid = v.lo + (v.hi - v.lo) / 2;
-                // a split that was forced goes straight to pieces short enough to stand a chance (<= 2 H + 1 samples,
-                // H the half width at which the gripper's stray reaches the cap), not through log2 plain halvings
-                uint32_t piece = 0xffffffffu;
-                if (forced[slot][i]) {
-                    const double perSample = ((double)dArm[v.e] * 1.2 + (double)dTorso[v.e]) / (double)c->hSteps[v.e];
-                    const double H = perSample > 0 ? std::floor((double)kCap / perSample) : 1e9;
-                    piece = (uint32_t)std::min(1e9, 2.0 * std::max(H, 1.0) + 1.0);
-                }
-                auto cut = [&](uint32_t lo, uint32_t hi) {   // [lo, hi] into equal pieces of at most `piece` samples
-                    const uint64_t len = (uint64_t)hi - lo + 1, parts = (len + piece - 1) / piece;
-                    for (uint64_t p = 0; p < parts; ++p)
-                        next.push_back({v.e, lo + (uint32_t)(p * len / parts), lo + (uint32_t)((p + 1) * len / parts) - 1});
-                };
-                if (mid > v.lo) cut(v.lo, mid - 1);
-                if (mid < v.hi) cut(mid + 1, v.hi);
+#pragma omp critical(mplb_fetch_next)
+                next.insert(next.end(), mine.begin(), mine.end());
             }
             b.clear();
             return MPLB_OK;
@@ -281,9 +289,6 @@ struct FetchScene : SceneBase {
             cur.swap(next);
             next.clear();
         }
-        if (std::getenv("MPLB_FETCH_DEBUG"))
-            for (int k = 0; k < 24; ++k)
-                if (dbgPair[k]) std::fprintf(stderr, "[fetch intervals] pair %d kept %llu intervals from being certified\n", k, dbgPair[k]);
         if (std::getenv("MPLB_FETCH_DEBUG"))
             for (int cls = 0; cls < 16; ++cls) {
                 unsigned long long tot = 0, by[5] = {0, 0, 0, 0, 0};
