@@ -22,9 +22,14 @@
 //     the FP64 CPU path instead of "equal up to an epsilon band";
 //   * hit/ready/free slot sets are warp-uniform bit masks maintained with ballot/reduce_or; a
 //     slot is recycled once its search is over and none of its leaf pairs is still queued.
-// Node and triangle fetches are 128-bit read-only loads (4 per 64-byte node, 3 per triangle);
-// the hierarchy is small enough to live in L1/L2, HBM only sees states
-// in and verdict bytes out.
+//   * lanes with nothing left steal the bottom pair of a busy lane (the largest pending subtree);
+//   * work is handed out by an atomic counter in guided chunks, so the end of a batch -- and all
+//     of a small one -- spreads over the whole grid; edges are handed out as intervals of samples
+//     that are certified free as a whole where possible (EdgeSource), in three passes.
+// Node fetches are 256-bit read-only loads (2 per 64-byte node; sm_100's LDG.E.256), triangles
+// one 256-bit and one 128-bit load: a scattered load costs one L1 wavefront per lane and
+// instruction whatever its width, and the L1 data pipe is what binds the box-pair step.  The
+// hierarchy lives in L1/L2, HBM only sees states in and verdict bytes out.
 #include "se3_device.cuh"
 #include "device_math.cuh"
 
