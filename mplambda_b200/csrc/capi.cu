@@ -375,13 +375,15 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
         }
         if (timeline) cudaEventRecord(tl[0], c->copyStream);
         MPLB_CUDA(cudaMemsetAsync(dIn, 0xFF, bytes, c->copyStream));
+        static const bool precopy = std::getenv("MPLB_STREAM_PRECOPY") != nullptr;   // diagnostic: the streamed kernel on data that is already there
+        if (precopy && (rc = hostToDevice(c, dIn, states, bytes, c->copyStream))) return rc;
         MPLB_CUDA(cudaEventRecord(c->events[0], c->copyStream));
         MPLB_CUDA(cudaStreamWaitEvent(c->stream, c->events[0], 0));
         if (timeline) cudaEventRecord(tl[1], c->stream);
         MPLB_CUDA(launchCheckStates(sc->dev, dIn, n, dOut, (DevCounters *)c->ctr.ptr, (unsigned *)c->work.ptr, sc->numSms,
                                     c->stream, true));
         if (timeline) cudaEventRecord(tl[3], c->stream);
-        if ((rc = hostToDevice(c, dIn, states, bytes, c->copyStream))) return rc;
+        if (!precopy && (rc = hostToDevice(c, dIn, states, bytes, c->copyStream))) return rc;
         if (timeline) cudaEventRecord(tl[2], c->copyStream);
     }
     sc->hLaunches += 1;

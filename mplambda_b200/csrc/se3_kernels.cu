@@ -40,6 +40,9 @@
 namespace mplb {
 namespace {
 
+#ifndef MPLB_CLAIM_MIN
+#define MPLB_CLAIM_MIN 4
+#endif
 #ifndef MPLB_WARPS_PER_CTA
 #define MPLB_WARPS_PER_CTA 8
 #endif
@@ -431,7 +434,7 @@ struct StateSource {
         }
         waitSpins = 0;
         backoff = 1000;
-        claim = waited ? max(claim / 2, 4) : min(claim * 2, 32);
+        claim = waited ? max(claim / 2, MPLB_CLAIM_MIN) : min(claim * 2, 32);
         base = pendBase;
         const int got = pendCount;
         pendCount = 0;
