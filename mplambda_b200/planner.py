@@ -111,6 +111,133 @@ class BatchedRRT:
         return np.asarray(out[::-1])
 
 
+class BatchedRRTStar(BatchedRRT):
+    """The asymptotically optimal loop of the reference's second planner, `Planner<Scenario, PCForest>`
+    (include/mpl/pcforest.hpp:487-567, one C-FOREST shard), applied to B samples at once:
+
+        sample -> nearest -> isValid(nearest, q)                                  (addSample, pcforest.hpp:487-506)
+        k nearest tree nodes, k = ceil(e (1 + 1/d) ln(n + 1))                     (pcforest.hpp:80-87,138)
+        parent = the neighbour with the cheapest valid connection                 (pcforest.hpp:512-540)
+        rewire every neighbour that gets cheaper through the new node             (pcforest.hpp:548-566)
+
+    The reference tries parent candidates one by one in increasing cost and stops at the first valid motion; here
+    all candidate motions of all new nodes are one `check_edges` batch (and all rewiring motions another), and the
+    cheapest valid one wins -- the same choice.  Samples of one batch do not see each other, like the reference's
+    concurrent threads.  As in the reference an Edge is immutable (node, parent edge, length, path cost): rewiring a
+    node gives it a new edge, its descendants keep pointing at the old one, so every stored cost is the length of a
+    path that exists.  nn needs `knearest` besides insert / nearest; distances come from scenario.space()."""
+
+    def __init__(self, scenario, nn, start, batch=1024, goal_bias=0.01, seed=1, capacity=1 << 16, dimension=6):
+        super().__init__(scenario, nn, start, batch, goal_bias, seed, capacity)
+        self.dimension = dimension
+        # edges: node, parent edge (-1: root), path cost; node -> its current edge
+        self.edge_node = [0]
+        self.edge_parent = [-1]
+        self.edge_cost = [0.0]
+        self.node_edge = np.zeros(len(self.nodes), dtype=np.int64)
+        self.is_goal = np.zeros(len(self.nodes), dtype=bool)
+        self.best_edge, self.best_cost = -1, float("inf")
+        self.stats["rewired"] = 0
+
+    def _cost(self, nodes):
+        return np.asarray(self.edge_cost)[self.node_edge[nodes]]
+
+    def _new_edge(self, node, parent_edge, cost):
+        self.edge_node.append(int(node)); self.edge_parent.append(int(parent_edge)); self.edge_cost.append(float(cost))
+        return len(self.edge_cost) - 1
+
+    def step(self):
+        sc = self.scenario
+        q, known = self._draw()
+        near, dnear = self.nn.nearest(self._scale(q))
+        cand = np.nonzero(dnear > 0)[0]
+        self.stats["samples"] += self.batch
+        if len(cand) == 0:
+            return
+        ok = sc.check_edges(self.nodes[near[cand]], q[cand])
+        self.stats["edges_checked"] += len(cand)
+        new = cand[ok]
+        if len(new) == 0:
+            return
+        qn, m = q[new], len(new)
+        k = int(np.ceil(np.e * (1.0 + 1.0 / self.dimension) * np.log(self.n + 1)))
+        nbr, ndist = self.nn.knearest(self._scale(qn), k)                    # ascending distance, -1 padded
+        have = nbr >= 0
+        nbr_safe = np.where(have, nbr, 0)
+        via = np.where(have, self._cost(nbr_safe) + ndist, np.inf)           # path cost through each neighbour
+        parent_cost = self._cost(near[new]) + dnear[new]
+        parent = near[new].copy()
+        parent_dist = dnear[new].copy()
+        # ---- parent selection: every neighbour that would be cheaper than the nearest node
+        rows, cols = np.nonzero(via < parent_cost[:, None])
+        rejected = np.zeros_like(have)
+        if len(rows):
+            v = sc.check_edges(self.nodes[nbr[rows, cols]], qn[rows])
+            self.stats["edges_checked"] += len(rows)
+            rejected[rows[~v], cols[~v]] = True                               # pcforest.hpp:527,555-556
+            for r, c in zip(rows[v], cols[v]):
+                if via[r, c] < parent_cost[r]:
+                    parent_cost[r], parent[r], parent_dist[r] = via[r, c], nbr[r, c], ndist[r, c]
+        # ---- insert
+        if self.n + m > len(self.nodes):
+            grow = max(len(self.nodes), m)
+            self.nodes = np.concatenate([self.nodes, np.empty((grow, self.dim))])
+            self.parent = np.concatenate([self.parent, np.empty(grow, dtype=np.int64)])
+            self.node_edge = np.concatenate([self.node_edge, np.zeros(grow, dtype=np.int64)])
+            self.is_goal = np.concatenate([self.is_goal, np.zeros(grow, dtype=bool)])
+        first = self.n
+        ids = np.arange(first, first + m)
+        self.nodes[ids], self.parent[ids] = qn, parent
+        goal = known[new].copy()
+        if hasattr(sc, "is_goal_batch"):
+            goal |= sc.is_goal_batch(qn)
+        else:
+            goal |= np.array([bool(sc.isGoal(x)) for x in qn])
+        self.is_goal[ids] = goal
+        for i in range(m):
+            self.node_edge[first + i] = self._new_edge(first + i, self.node_edge[parent[i]], parent_cost[i])
+        self.n += m
+        self.nn.insert(self._scale(qn))
+        for i in np.nonzero(goal)[0]:                                         # updateSolution, pcforest.hpp:542-543
+            if parent_cost[i] < self.best_cost:
+                self.best_cost, self.best_edge, self.solution = float(parent_cost[i]), int(self.node_edge[first + i]), first + int(i)
+        # ---- rewiring: neighbours that get cheaper through the new node (not the ones already found unreachable)
+        through = parent_cost[:, None] + ndist
+        rows, cols = np.nonzero(have & ~rejected & (through < np.where(have, self._cost(nbr_safe), -np.inf)))
+        if len(rows):
+            v = sc.check_edges(qn[rows], self.nodes[nbr[rows, cols]])
+            self.stats["edges_checked"] += len(rows)
+            for r, c in zip(rows[v], cols[v]):
+                node, cost = int(nbr[r, c]), float(through[r, c])
+                if cost < self.edge_cost[self.node_edge[node]]:               # setEdge keeps the cheaper one, pcforest.hpp:569-581
+                    self.node_edge[node] = self._new_edge(node, self.node_edge[first + r], cost)
+                    self.parent[node] = first + r
+                    self.stats["rewired"] += 1
+                    if self.is_goal[node] and cost < self.best_cost:
+                        self.best_cost, self.best_edge, self.solution = cost, int(self.node_edge[node]), node
+
+    def solve(self, time_limit=60.0, max_iterations=10 ** 9, stop_at_first=False):
+        """Anytime: runs until the limit and keeps the cheapest path found (stop_at_first: return at the first one)."""
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < time_limit and self.stats["iterations"] < max_iterations:
+            if stop_at_first and self.solution >= 0:
+                break
+            self.step()
+            self.stats["iterations"] += 1
+        self.stats["seconds"] = time.perf_counter() - t0
+        self.stats["nodes"] = self.n
+        return self.path()
+
+    def path(self):
+        if self.best_edge < 0:
+            return None
+        out, e = [], self.best_edge
+        while e >= 0:                                                         # an edge chain is an existing path
+            out.append(self.nodes[self.edge_node[e]].copy())
+            e = self.edge_parent[e]
+        return np.asarray(out[::-1])
+
+
 def path_cost(scenario, path):
     sp = scenario.space()
     return float(sum(sp.distance(a, b) for a, b in zip(path[:-1], path[1:])))

@@ -42,6 +42,9 @@ class CpuNN:
     def nearest(self, q):
         return O.nn_nearest(self.keys, q, threads=self.threads)
 
+    def knearest(self, q, k):
+        return O.nn_knearest(self.keys, q, k, threads=self.threads)
+
 
 class _Space:
     def __init__(self, orc):

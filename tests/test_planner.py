@@ -83,3 +83,54 @@ def test_knn_then_connect_matches_oracle(scenes, oracle):
     want = oracle.SE3Oracle(env, robot, check_resolution=0.1).check_edges(frm, to)
     assert (got == want).all()
     assert 0 < got.sum() < len(got)
+
+
+def _star_invariants(rrt, sc, orc_scenario):
+    """Every edge chain is an existing, valid path whose length is the stored cost."""
+    sp = orc_scenario.space()
+    path = rrt.path()
+    _check_path(path, sc, orc_scenario)
+    length = sum(sp.distance(a, b) for a, b in zip(path[:-1], path[1:]))
+    assert abs(length - rrt.best_cost) <= 1e-9 * max(1.0, length)
+    cost = np.asarray(rrt.edge_cost)
+    par = np.asarray(rrt.edge_parent)
+    node = np.asarray(rrt.edge_node)
+    child = np.nonzero(par >= 0)[0]
+    assert (cost[child] > cost[par[child]]).all()                 # costs grow along every chain
+    # a node's current edge is its cheapest one
+    for n in np.random.default_rng(0).integers(0, rrt.n, 200):
+        assert cost[rrt.node_edge[n]] == cost[node == n].min()
+
+
+def test_cpu_rrt_star_improves_the_path(scenes):
+    from mplambda_b200.planner import BatchedRRTStar
+    env, robot = scenes["cubicles"]
+    sc = SE3_SCENES["cubicles"]
+    scen = CpuScenario(env, robot, sc)
+    rrt = BatchedRRTStar(scen, CpuNN(), sc["start"], batch=256, seed=2)
+    rrt.solve(time_limit=120, stop_at_first=True)
+    assert rrt.solution >= 0
+    first = rrt.best_cost
+    rrt.solve(time_limit=120, max_iterations=rrt.stats["iterations"] + 6)
+    assert rrt.best_cost <= first
+    _star_invariants(rrt, sc, scen)
+
+
+@pytest.mark.gpu
+def test_gpu_rrt_star_matches_cpu_rrt_star(scenes):
+    import mplambda_b200 as M
+    from mplambda_b200.planner import BatchedRRTStar
+    env, robot = scenes["cubicles"]
+    sc = SE3_SCENES["cubicles"]
+    g = M.SE3RigidBodyScenario(env, robot, sc["goal"], sc["min"], sc["max"], 0.1)
+    rg = BatchedRRTStar(g, M.Nigh(M.nn.SE3), sc["start"], batch=512, seed=4)
+    rg.solve(time_limit=300, stop_at_first=True)
+    rg.solve(time_limit=300, max_iterations=rg.stats["iterations"] + 5)      # a few improving rounds after the first path
+    c = CpuScenario(env, robot, sc)
+    rc = BatchedRRTStar(c, CpuNN(), sc["start"], batch=512, seed=4)
+    rc.solve(time_limit=900, max_iterations=rg.stats["iterations"])
+    assert rg.n == rc.n and rg.stats["rewired"] == rc.stats["rewired"] and rg.stats["rewired"] > 0
+    np.testing.assert_array_equal(rg.nodes[:rg.n], rc.nodes[:rc.n])
+    np.testing.assert_array_equal(np.asarray(rg.edge_cost), np.asarray(rc.edge_cost))
+    assert rg.best_cost == rc.best_cost < float("inf")
+    _star_invariants(rg, sc, c)
