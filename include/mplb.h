@@ -88,8 +88,10 @@ int mplb_check_states(mplb_scene *scene, const double *states, size_t n, uint8_t
 
 /* isValid(from, to) for n edges (se3...:134-178): valid[i] = isValid(to_i) AND every
  * interpolated state at i/steps, steps = ceil(distance(from,to)/checkResolution).  `from` is
- * assumed valid like the reference's assert.  states_checked (optional) receives the number of
- * states actually evaluated on the device (<= sum of steps thanks to early exit). */
+ * assumed valid like the reference's assert.  The verdict is exactly that conjunction, but the
+ * samples are not enumerated: intervals of samples that nothing can reach are certified free as a
+ * whole.  states_checked (optional) receives the number of states actually evaluated on the
+ * device (a small fraction of the sum of steps). */
 int mplb_check_edges(mplb_scene *scene, const double *from, const double *to, size_t n,
                      uint8_t *valid, uint64_t *states_checked);
 
@@ -105,6 +107,7 @@ int mplb_check_states_device(mplb_scene *scene, const double *d_states, size_t n
  * se3...:139 (host libm, bit-identical to the CPU path). */
 int mplb_edges_plan(mplb_scene *scene, const double *from, const double *to, size_t n,
                     uint32_t *steps);
+/* (max_steps is accepted for compatibility and ignored.  SE(3) scenes only.) */
 int mplb_check_edges_device(mplb_scene *scene, const double *d_from, const double *d_to,
                             const uint32_t *d_steps, size_t n, uint32_t max_steps,
                             uint8_t *d_valid, void *stream);
