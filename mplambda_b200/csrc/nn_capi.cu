@@ -175,9 +175,11 @@ int mplb_nn_insert(mplb_nn *nn, const double *keys, size_t n) {
             const double qn = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
             if (!(std::fabs(qn - 1.0) < 1e-3)) nn->keysAbsMax = INFINITY;
         }
-    MPLB_CUDA(cudaMemcpy(nn->dKeys + nn->count * nn->dim, keys, n * nn->dim * 8, cudaMemcpyHostToDevice));
-    MPLB_CUDA(launchNnToFloat(nn->dKeys + nn->count * nn->dim, nn->dKeys32 + nn->count * nn->dim, n * nn->dim, nullptr));
-    MPLB_CUDA(cudaDeviceSynchronize());
+    // on the structure's own stream (queries are ordered behind it); no device-wide synchronisation: other threads'
+    // scenes keep running
+    MPLB_CUDA(cudaMemcpyAsync(nn->dKeys + nn->count * nn->dim, keys, n * nn->dim * 8, cudaMemcpyHostToDevice, nn->stream));
+    MPLB_CUDA(launchNnToFloat(nn->dKeys + nn->count * nn->dim, nn->dKeys32 + nn->count * nn->dim, n * nn->dim, nn->stream));
+    MPLB_CUDA(cudaStreamSynchronize(nn->stream));
     nn->hKeys.insert(nn->hKeys.end(), keys, keys + n * nn->dim);
     nn->count += n;
     return MPLB_OK;
