@@ -69,6 +69,8 @@ int CallCtx::reserveRes(int i, size_t bytes) {
 }
 
 CallCtx::~CallCtx() {
+    if (graphState) cudaGraphExecDestroy(graphState);
+    if (graphEdge) cudaGraphExecDestroy(graphEdge);
     for (int i = 0; i < 2; ++i) {
         if (hRes[i]) cudaFreeHost(hRes[i]);
         if (hBounce[i]) cudaFreeHost(hBounce[i]);
@@ -286,6 +288,45 @@ static int hostToDevice(CallCtx *c, void *dst, const void *src, size_t bytes, cu
     return MPLB_OK;
 }
 
+// Runs `enqueue` (asynchronous work on c->stream, fixed addresses and sizes) through a cached CUDA graph: replayed if
+// there is one for these buffers, captured + instantiated on the context's second such call, enqueued directly
+// otherwise (and whenever capturing fails: graphs are an optimisation, never a requirement).
+template <class Enqueue>
+static int runScalar(CallCtx *c, cudaGraphExec_t &exec, void **key, const void *const *now, int nKeys, unsigned &calls,
+                     Enqueue enqueue) {
+    static const bool off = std::getenv("MPLB_NO_GRAPHS") != nullptr;
+    bool same = exec != nullptr;
+    for (int i = 0; i < nKeys && same; ++i) same = key[i] == now[i];
+    if (same) {
+        MPLB_CUDA(cudaGraphLaunch(exec, c->stream));
+        return MPLB_OK;
+    }
+    if (off || c->graphsOff || ++calls < 2) return enqueue();
+    if (exec) {
+        cudaGraphExecDestroy(exec);
+        exec = nullptr;
+    }
+    if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        c->graphsOff = true;
+        return enqueue();
+    }
+    const int rc = enqueue();
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    if (rc != MPLB_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        exec = nullptr;
+        c->graphsOff = true;
+        return enqueue();   // nothing has run yet: do it the plain way
+    }
+    cudaGraphDestroy(graph);
+    for (int i = 0; i < nKeys; ++i) key[i] = const_cast<void *>(now[i]);
+    MPLB_CUDA(cudaGraphLaunch(exec, c->stream));
+    return MPLB_OK;
+}
+
 static int account(SceneBase *sc, const DevCounters &k, size_t checks, uint64_t *statesOut) {
     if (k.overflow) return fail(MPLB_ERR_CUDA, "device traversal bookkeeping error (pair stack / slot accounting)");
     sc->hBv += k.bvTests;
@@ -342,12 +383,21 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
     if (n <= kSmallStates) {
         std::memcpy(c->hStage, states, bytes);
         unsigned char *ctl = (unsigned char *)c->ctl.ptr;
-        MPLB_CUDA(cudaMemsetAsync(ctl, 0, kCtlHeader, c->stream));
-        MPLB_CUDA(cudaMemcpyAsync(c->stage.ptr, c->hStage, bytes, cudaMemcpyHostToDevice, c->stream));
-        MPLB_CUDA(launchCheckStates(sc->dev, (const double *)c->stage.ptr, n, ctl + kCtlHeader, (DevCounters *)ctl,
-                                    (unsigned *)(ctl + kCtlHeader - 128), sc->numSms, c->stream, false, true));
+        auto enqueue = [&]() -> int {
+            MPLB_CUDA(cudaMemsetAsync(ctl, 0, kCtlHeader, c->stream));
+            MPLB_CUDA(cudaMemcpyAsync(c->stage.ptr, c->hStage, bytes, cudaMemcpyHostToDevice, c->stream));
+            MPLB_CUDA(launchCheckStates(sc->dev, (const double *)c->stage.ptr, n, ctl + kCtlHeader, (DevCounters *)ctl,
+                                        (unsigned *)(ctl + kCtlHeader - 128), sc->numSms, c->stream, false, true));
+            MPLB_CUDA(cudaMemcpyAsync(c->hCtl, ctl, kCtlHeader + n, cudaMemcpyDeviceToHost, c->stream));
+            return MPLB_OK;
+        };
+        if (n == 1) {
+            const void *now[2] = {c->stage.ptr, c->ctl.ptr};
+            if ((rc = runScalar(c, c->graphState, c->graphStateKey, now, 2, c->scalarStates, enqueue))) return rc;
+        } else if ((rc = enqueue())) {
+            return rc;
+        }
         sc->hLaunches += 1;
-        MPLB_CUDA(cudaMemcpyAsync(c->hCtl, ctl, kCtlHeader + n, cudaMemcpyDeviceToHost, c->stream));
         MPLB_CUDA(cudaStreamSynchronize(c->stream));
         std::memcpy(valid, c->hCtl + kCtlHeader, n);
         return account(sc, *(const DevCounters *)c->hCtl, n, nullptr);
@@ -456,14 +506,23 @@ static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, siz
         std::memcpy(c->hStage + sb, to, sb);
         std::memcpy(c->hStage + 2 * sb, c->hSteps.data(), n * 4);
         unsigned char *ctl = (unsigned char *)c->ctl.ptr, *in = (unsigned char *)c->stage.ptr;
-        MPLB_CUDA(cudaMemsetAsync(ctl, 0, kCtlHeader + n * 4, c->stream));
-        MPLB_CUDA(cudaMemcpyAsync(in, c->hStage, 2 * sb + n * 4, cudaMemcpyHostToDevice, c->stream));
-        MPLB_CUDA(launchCheckEdges(sc->dev, (const double *)in, (const double *)(in + sb), (const unsigned *)(in + 2 * sb), n,
-                                   (unsigned *)(ctl + kCtlHeader), nullptr, (DevCounters *)ctl,
-                                   (unsigned long long *)(ctl + kCtlHeader - 128), c->aux0.ptr, stackBytes,
-                                   (double *)(in + ((2 * sb + n * 4 + 7) & ~(size_t)7)), sc->numSms, c->stream, true));
+        auto enqueue = [&]() -> int {
+            MPLB_CUDA(cudaMemsetAsync(ctl, 0, kCtlHeader + n * 4, c->stream));
+            MPLB_CUDA(cudaMemcpyAsync(in, c->hStage, 2 * sb + n * 4, cudaMemcpyHostToDevice, c->stream));
+            MPLB_CUDA(launchCheckEdges(sc->dev, (const double *)in, (const double *)(in + sb), (const unsigned *)(in + 2 * sb), n,
+                                       (unsigned *)(ctl + kCtlHeader), nullptr, (DevCounters *)ctl,
+                                       (unsigned long long *)(ctl + kCtlHeader - 128), c->aux0.ptr, stackBytes,
+                                       (double *)(in + ((2 * sb + n * 4 + 7) & ~(size_t)7)), sc->numSms, c->stream, true));
+            MPLB_CUDA(cudaMemcpyAsync(c->hCtl, ctl, kCtlHeader + n * 4, cudaMemcpyDeviceToHost, c->stream));
+            return MPLB_OK;
+        };
+        if (n == 1) {
+            const void *now[3] = {c->stage.ptr, c->ctl.ptr, c->aux0.ptr};
+            if ((rc = runScalar(c, c->graphEdge, c->graphEdgeKey, now, 3, c->scalarEdges, enqueue))) return rc;
+        } else if ((rc = enqueue())) {
+            return rc;
+        }
         sc->hLaunches += 4;   // per-edge constants + three passes
-        MPLB_CUDA(cudaMemcpyAsync(c->hCtl, ctl, kCtlHeader + n * 4, cudaMemcpyDeviceToHost, c->stream));
         MPLB_CUDA(cudaStreamSynchronize(c->stream));
         const unsigned *dead = (const unsigned *)(c->hCtl + kCtlHeader);
         for (size_t i = 0; i < n; ++i) valid[i] = dead[i] ? 0 : 1;

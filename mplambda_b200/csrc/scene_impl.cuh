@@ -40,6 +40,13 @@ struct CallCtx {
     // the wire (cudaMemcpyAsync on pageable memory stages through one thread at ~10 GB/s)
     unsigned char *hBounce[2] = {nullptr, nullptr};
     cudaEvent_t bounceDone[2] = {nullptr, nullptr};
+    // The reference's scalar calls (one state, one edge) replay a captured CUDA graph: memset + copy in + kernels +
+    // copy out are one launch instead of four to eight.  Captured on a context's second scalar call; the keys are the
+    // device buffers the graph was captured with (a reallocation invalidates it).
+    cudaGraphExec_t graphState = nullptr, graphEdge = nullptr;
+    void *graphStateKey[2] = {nullptr, nullptr}, *graphEdgeKey[3] = {nullptr, nullptr, nullptr};
+    unsigned scalarStates = 0, scalarEdges = 0;
+    bool graphsOff = false;
     // pinned result buffers of pipelined rounds (Fetch edge intervals), grown on demand
     unsigned char *hRes[2] = {nullptr, nullptr};
     size_t hResCap[2] = {0, 0};
