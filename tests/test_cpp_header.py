@@ -105,3 +105,31 @@ def test_cpp_planner_solves_and_path_is_valid(tmp_path, scenes, oracle, name):
     assert orc.distance(path[-1], np.array(sc["goal"], dtype=np.float64)) <= 0.1      # isGoal, se3...:100-104
     assert orc.check_states(path).all()
     assert orc.check_edges(path[:-1], path[1:]).all()
+
+
+@pytest.mark.gpu
+def test_cpp_rrt_star_path_is_valid_and_costed(tmp_path, scenes, oracle):
+    """mplb::BatchedRRTStar (PCForest's loop in C++): the returned path is valid under the oracle, its length is the
+    cost the planner reports, and the improving rounds never make it worse."""
+    import numpy as np
+    from mplambda_b200.workload import SE3_SCENES
+    exe = _build_rrt(tmp_path)
+    env, robot = scenes["cubicles"]
+    sc = SE3_SCENES["cubicles"]
+    np.ascontiguousarray(env, dtype=np.float64).tofile(tmp_path / "env.bin")
+    np.ascontiguousarray(robot, dtype=np.float64).tofile(tmp_path / "robot.bin")
+    nums = list(sc["start"]) + list(sc["goal"]) + list(sc["min"]) + list(sc["max"])
+    out = subprocess.run([str(exe), str(tmp_path / "env.bin"), str(tmp_path / "robot.bin")] + ["%.17g" % x for x in nums] +
+                         ["1024", "3", "60", "star"], capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.strip().splitlines()
+    head = lines[0].split()
+    first, best = float(head[head.index("first") + 1]), float(head[head.index("best") + 1])
+    assert best <= first
+    path = np.array([[float(x) for x in ln.split()] for ln in lines[1:]])
+    orc = oracle.SE3Oracle(env, robot, check_resolution=0.1)
+    np.testing.assert_array_equal(path[0], np.array(sc["start"], dtype=np.float64))
+    assert orc.distance(path[-1], np.array(sc["goal"], dtype=np.float64)) <= 0.1
+    assert orc.check_states(path).all() and orc.check_edges(path[:-1], path[1:]).all()
+    length = sum(orc.distance(a, b) for a, b in zip(path[:-1], path[1:]))
+    assert abs(length - best) <= 1e-9 * max(1.0, length)
