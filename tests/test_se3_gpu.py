@@ -267,3 +267,31 @@ def test_edge_step_count_extremes(scenes, oracle):
     got = ns.check_edges(F, T)
     assert (got == norc.check_edges(F, T)).all()
     assert 0 < got.sum() < 64
+
+
+def test_concurrent_scalar_calls(scenes, golden, oracle):
+    """The reference's planner threads call isValid(q) / isValid(from,to) one at a time, concurrently (prrt.hpp:140-152);
+    from a context's second scalar call on these replay a captured CUDA graph, each thread on its own context."""
+    import threading
+    s = make(scenes, "twistycool")
+    env, robot = scenes["twistycool"]
+    want = golden["twistycool_valid"]
+    sc = SE3_SCENES["twistycool"]
+    P = se3_poses(len(want), sc["min"], sc["max"], SEED)
+    A = P[want][:64]
+    B = se3_poses(64, sc["min"], sc["max"], SEED + 7)
+    edge_want = oracle.SE3Oracle(env, robot, check_resolution=0.1).check_edges(A, B)
+    errs = []
+
+    def work(k):
+        for r in range(40):
+            i = (k * 53 + r * 17) % 2000
+            if s.isValid(P[i]) != bool(want[i]):
+                errs.append(("state", k, i))
+            j = (k * 7 + r) % 64
+            if s.isValid(A[j], B[j]) != bool(edge_want[j]):
+                errs.append(("edge", k, j))
+    th = [threading.Thread(target=work, args=(k,)) for k in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs[:5]
