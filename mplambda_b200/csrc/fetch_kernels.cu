@@ -448,21 +448,21 @@ __constant__ unsigned char kSelfPairs[24][2] = {
     {0, 6}, {0, 7}, {0, 8}, {0, 9}, {1, 6}, {1, 7}, {1, 8}, {1, 9}, {2, 6}, {2, 7}, {2, 8}, {2, 9},
     {3, 8}, {4, 8}, {4, 9}, {4, 11}, {5, 11}, {6, 11}, {7, 10}, {7, 11}, {8, 10}, {8, 11}, {9, 10}, {9, 11}};
 
+// A frame is three 32-byte rows (R[i][0..2], t[i]), 32-byte aligned: one 256-bit access per row (sm_100) instead of
+// four 64-bit ones -- every thread works on its own state, so each access is a separate L1 wavefront either way
 __device__ void loadFrame(const double *src, FrameD &f) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) f.R[i][j] = src[4 * i + j];
-        f.t[i] = src[4 * i + 3];
-    }
+    for (int i = 0; i < 3; ++i)
+        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(f.R[i][0]), "=d"(f.R[i][1]), "=d"(f.R[i][2]), "=d"(f.t[i])
+                     : "l"(src + 4 * i));
 }
 __device__ void storeFrame(double *dst, const FrameD &f) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) dst[4 * i + j] = f.R[i][j];
-        dst[4 * i + 3] = f.t[i];
-    }
+    for (int i = 0; i < 3; ++i)
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(dst + 4 * i), "d"(f.R[i][0]), "d"(f.R[i][1]), "d"(f.R[i][2]),
+                     "d"(f.t[i])
+                     : "memory");
 }
 
 // Work lists filled by the culling kernels and drained by the exact (FP64 MPR) kernels: separating the
@@ -495,7 +495,12 @@ __device__ int exactPair(const FetchSceneDev &sc, const double *frames, unsigned
 __device__ int exactLeaf(const FetchSceneDev &sc, const double *frames, unsigned long long state, int g, unsigned tri) {
     FrameD f, ef;
     loadFrame(frames + state * 144 + 12 * g, f);
-    loadFrame(sc.envFrame, ef);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {   // (kernel-parameter space, not global memory)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) ef.R[i][j] = sc.envFrame[4 * i + j];
+        ef.t[i] = sc.envFrame[4 * i + 3];
+    }
     CcdObj shapeObj, t;
     makeShapeObj(sc.shapes[g], f, shapeObj);
     const double *tp = sc.envTris64 + 9 * (size_t)tri;
@@ -711,16 +716,18 @@ fetchPairKernel(FetchSceneDev sc, const double *__restrict__ frames, WorkList pa
         const int k = (int)(v & 255), a = kSelfPairs[k][0], b = kSelfPairs[k][1];
         float A[12], B[12];
         {
-            const double *fa = frames + state * 144 + 12 * a, *fb = frames + state * 144 + 12 * b;
+            FrameD fa, fb;
+            loadFrame(frames + state * 144 + 12 * a, fa);
+            loadFrame(frames + state * 144 + 12 * b, fb);
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    A[3 * r + c] = (float)fa[4 * r + c];
-                    B[3 * r + c] = (float)fb[4 * r + c];
+                    A[3 * r + c] = (float)fa.R[r][c];
+                    B[3 * r + c] = (float)fb.R[r][c];
                 }
-                A[9 + r] = (float)fa[4 * r + 3];
-                B[9 + r] = (float)fb[4 * r + 3];
+                A[9 + r] = (float)fa.t[r];
+                B[9 + r] = (float)fb.t[r];
             }
         }
         float need = kCullSlack;
@@ -816,13 +823,14 @@ fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsign
                 if (item < nItems) {
                     state = survivors[item / 12u];
                     g = (int)(item % 12u);
-                    const double *fp = frames + state * 144 + 12 * g;
+                    FrameD fr;
+                    loadFrame(frames + state * 144 + 12 * g, fr);
                     float e[3];
                     shapeExtents(sc.shapes[g], e);
                     // shape box in world coordinates: axes = columns of R
-                    a0 = make_float4((float)fp[0], (float)fp[4], (float)fp[8], (float)fp[3]);
-                    a1 = make_float4((float)fp[1], (float)fp[5], (float)fp[9], (float)fp[7]);
-                    a2 = make_float4((float)fp[2], (float)fp[6], (float)fp[10], (float)fp[11]);
+                    a0 = make_float4((float)fr.R[0][0], (float)fr.R[1][0], (float)fr.R[2][0], (float)fr.t[0]);
+                    a1 = make_float4((float)fr.R[0][1], (float)fr.R[1][1], (float)fr.R[2][1], (float)fr.t[1]);
+                    a2 = make_float4((float)fr.R[0][2], (float)fr.R[1][2], (float)fr.R[2][2], (float)fr.t[2]);
                     ae = make_float4(e[0] * 1.00001f, e[1] * 1.00001f, e[2] * 1.00001f, 0);
                     reachSlack = kCullSlack;
                     if (slack) {
