@@ -778,6 +778,10 @@ __global__ void fetchSurvivorsKernel(const unsigned char *__restrict__ selfHit, 
 // loads (ncu: long-scoreboard 6.8 warps per issue at 10 warps / SM), which shared memory cuts by an order of
 // magnitude; AUTOLAB's 1 256 nodes take 100 KB.  Larger environments use the global-memory variant.
 constexpr int kEnvThreads = 384, kEnvStack = 40;
+#ifndef MPLB_ENV_CHUNK
+#define MPLB_ENV_CHUNK 32
+#endif
+constexpr unsigned kEnvChunk = MPLB_ENV_CHUNK;
 template <bool kSmemNodes>
 __global__ void __launch_bounds__(kSmemNodes ? kEnvThreads : 128)
 fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsigned *__restrict__ survivors,
@@ -790,6 +794,19 @@ fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsign
         for (int i = threadIdx.x; i < sc.nEnvNodes * 4; i += blockDim.x) nodesS[(i >> 2) * 5 + (i & 3)] = __ldg(sc.envNodes + i);
         __syncthreads();
     }
+    // per-geometry constants in shared memory: indexing the kernel parameters with a lane-varying geometry index
+    // serialises in the constant cache (8 % of this kernel's samples)
+    __shared__ float geomS[12][8];   // box half extents (x 1.00001), lift, reach
+    if (threadIdx.x < 12) {
+        float e[3];
+        shapeExtents(sc.shapes[threadIdx.x], e);
+        geomS[threadIdx.x][0] = e[0] * 1.00001f;
+        geomS[threadIdx.x][1] = e[1] * 1.00001f;
+        geomS[threadIdx.x][2] = e[2] * 1.00001f;
+        geomS[threadIdx.x][3] = sc.lift[threadIdx.x];
+        geomS[threadIdx.x][4] = sc.reach[threadIdx.x];
+    }
+    __syncthreads();
     const unsigned lane = threadIdx.x & 31u;
     const unsigned nItems = *nSurvivors * 12u;
     const float4 x0 = make_float4((float)sc.envFrame[0], (float)sc.envFrame[1], (float)sc.envFrame[2], (float)sc.envFrame[3]);
@@ -809,33 +826,41 @@ fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsign
     float reachSlack = kCullSlack;   // interval items: the box test is inflated by the geometry's displacement
     unsigned bv = 0;
     bool exhausted = false;
+    unsigned chunkBase = 0, chunkLeft = 0;
     for (;;) {
         // refill the lanes whose traversal is over
         const unsigned need = __ballot_sync(0xffffffffu, sp == 0);
         if (need && !exhausted) {
-            unsigned base = 0;
-            const int leader = __ffs(need) - 1;
-            if ((int)lane == leader) base = atomicAdd(itemCounter, (unsigned)__popc(need));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (base + __popc(need) >= nItems) exhausted = true;
-            if (sp == 0) {
-                const unsigned item = base + __popc(need & ((1u << lane) - 1u));
-                if (item < nItems) {
+            // items are claimed kEnvChunk at a time per warp and dealt out from registers: some lane runs dry in
+            // nearly every iteration, and a global atomic per iteration sat on the loop's critical path
+            if (chunkLeft == 0) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(itemCounter, kEnvChunk);
+                chunkBase = __shfl_sync(0xffffffffu, base, 0);
+                chunkLeft = chunkBase < nItems ? min(kEnvChunk, nItems - chunkBase) : 0u;
+                if (chunkLeft == 0) exhausted = true;
+            }
+            const unsigned rank = __popc(need & ((1u << lane) - 1u));
+            const unsigned take = min((unsigned)__popc(need), chunkLeft);
+            const unsigned base = chunkBase;
+            chunkBase += take;
+            chunkLeft -= take;
+            if (sp == 0 && rank < take) {
+                const unsigned item = base + rank;
+                {
                     state = survivors[item / 12u];
                     g = (int)(item % 12u);
                     FrameD fr;
                     loadFrame(frames + state * 144 + 12 * g, fr);
-                    float e[3];
-                    shapeExtents(sc.shapes[g], e);
                     // shape box in world coordinates: axes = columns of R
                     a0 = make_float4((float)fr.R[0][0], (float)fr.R[1][0], (float)fr.R[2][0], (float)fr.t[0]);
                     a1 = make_float4((float)fr.R[0][1], (float)fr.R[1][1], (float)fr.R[2][1], (float)fr.t[1]);
                     a2 = make_float4((float)fr.R[0][2], (float)fr.R[1][2], (float)fr.R[2][2], (float)fr.t[2]);
-                    ae = make_float4(e[0] * 1.00001f, e[1] * 1.00001f, e[2] * 1.00001f, 0);
+                    ae = make_float4(geomS[g][0], geomS[g][1], geomS[g][2], 0);
                     reachSlack = kCullSlack;
                     if (slack) {
                         const float2 sl = slack[state];
-                        reachSlack += (sl.x * sc.lift[g] + sl.y * sc.reach[g]) * 1.0001f + 1e-6f;
+                        reachSlack += (sl.x * geomS[g][3] + sl.y * geomS[g][4]) * 1.0001f + 1e-6f;
                     }
                     stackAt(sp++) = 0;
                 }
