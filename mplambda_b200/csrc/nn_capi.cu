@@ -69,7 +69,7 @@ static int nnSearch(mplb_nn *nn, const double *queries, bool deviceQueries, size
     if (slices > 1 && ((rc = nn->partDist.reserve(nq * slices * k * 8)) || (rc = nn->partIdx.reserve(nq * slices * k * 8))))
         return rc;
     // k == 1: [nq][slices] bounds; k > 1: [nq][k] sample distances + [nq][8] counts + [nq] chosen levels
-    if ((rc = nn->partVal.reserve(std::max<size_t>(nq * slices * k * 4, nq * ((size_t)k + 9) * 4))) || (rc = nn->thr.reserve(nq * 4)))
+    if ((rc = nn->partVal.reserve(std::max<size_t>(nq * slices * k * 4, nq * ((size_t)k + 17) * 4))) || (rc = nn->thr.reserve(nq * 4)))
         return rc;
     const double *dQ = queries;
     double *dDist = dist;

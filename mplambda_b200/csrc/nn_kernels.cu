@@ -145,7 +145,10 @@ nnBound32Kernel(const float *__restrict__ keys32, unsigned long long n, int dim,
 // of the keys (nnBound32Kernel, cheap) is such a threshold -- with about k n / m keys under it -- and this kernel
 // COUNTS, over all keys, how many lie under each of kNnLevels fractions of T0 (registers only); the smallest
 // level that still holds k keys becomes the threshold of pass 2.
-constexpr int kNnLevels = 8;
+#ifndef MPLB_NN_LEVELS
+#define MPLB_NN_LEVELS 8
+#endif
+constexpr int kNnLevels = MPLB_NN_LEVELS;
 constexpr int kNnCandCap = 128;   // candidates a thread notes before it works them off (more simply means another round)
 
 __global__ void __launch_bounds__(kNnThreads)
