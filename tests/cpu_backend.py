@@ -1,5 +1,5 @@
 """Test infrastructure: oracle-backed stand-ins with the scenario / nearest-neighbour interface, used to
-run the batch-issuing planner on the CPU (tests, tools/rrt_compare.py).  Never used by the product."""
+run the batch-issuing planner on the CPU (tests, tests/tools/rrt_compare.py).  Never used by the product."""
 import numpy as np
 
 from oracle import oracle_py as O

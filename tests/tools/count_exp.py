@@ -1,6 +1,6 @@
 """Dev experiment: BV/tri test counts per check for valid vs colliding poses, GPU vs oracle."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import mplambda_b200 as M
 from mplambda_b200.workload import SE3_SCENES, SEED, se3_poses

@@ -1,6 +1,6 @@
 """Dev timing of edge batches (config 3 of BASELINE.json): 65,536 seeded edges per scene."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import mplambda_b200 as M
 from mplambda_b200.workload import SE3_SCENES, SEED, se3_poses

@@ -1,6 +1,6 @@
 """Dev: Fetch edge batch (BASELINE config 5) timing + parity on a prefix."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import mplambda_b200 as M
 from mplambda_b200.workload import *

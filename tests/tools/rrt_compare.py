@@ -2,7 +2,7 @@
 GPU nearest neighbour vs the CPU oracle on all host cores as the validity/NN backend.  The secondary half
 of BASELINE.json's metric ("RRT time-to-solution vs FCL CPU")."""
 import sys, os, time, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import mplambda_b200 as M
 from mplambda_b200.planner import BatchedRRT
@@ -10,7 +10,7 @@ from mplambda_b200.workload import SE3_SCENES
 from oracle import oracle_py as O
 
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cpu_backend import CpuNN, CpuScenario  # noqa: E402
 
 

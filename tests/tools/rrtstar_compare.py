@@ -1,12 +1,12 @@
 """Anytime planning: BatchedRRTStar (PCForest's loop, mplambda_b200/planner.py) for a fixed wall-clock budget with
 the GPU scenario + GPU nearest neighbours vs the CPU oracle on all host cores: tree size and best path cost."""
 import sys, os, json
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import mplambda_b200 as M
 from mplambda_b200.planner import BatchedRRTStar
 from mplambda_b200.workload import SE3_SCENES
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from cpu_backend import CpuNN, CpuScenario  # noqa: E402
 
 budget = float(os.environ.get("BUDGET", 1.0))

@@ -1,6 +1,6 @@
 """Wide parity sweep (GPU box): every scene, 2^20 poses and 65,536 edges per seed, all compared with the oracle."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import mplambda_b200 as M
 from mplambda_b200.workload import SE3_SCENES, SEED, se3_poses

@@ -1,7 +1,7 @@
 """How much of a pose-batch launch is tail?  time(n) for n = 2^17..2^22 device-resident poses, and the
 per-pose work distribution (BV tests) from the oracle on a sample.  Development tool."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import mplambda_b200 as M
 from mplambda_b200.workload import SE3_SCENES, SEED, se3_poses
