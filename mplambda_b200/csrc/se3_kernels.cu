@@ -36,6 +36,7 @@
 #include <cfloat>
 #include <map>
 #include <mutex>
+#include <tuple>
 
 namespace mplb {
 namespace {
@@ -61,6 +62,7 @@ constexpr unsigned kPhaseBSub = 1u << kIntervalBits;    // intervals an edge's s
 #define MPLB_SPILL_KEEP 0
 #endif
 constexpr unsigned kSpillKeep = MPLB_SPILL_KEEP;    // interval pieces a warp keeps for itself once the item pool has drained
+constexpr size_t kLatencyBelow = 1u << 17;   // poses: below this checkStatesKernel's latency variant is launched
 constexpr int kStepsPerRound = 4;   // depth-first steps between two rounds of slot bookkeeping
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -748,7 +750,9 @@ struct EdgeSource {
 
 // ---- the per-warp engine -----------------------------------------------------------------------
 
-template <typename E, typename Source>
+// kLatency: the variant launched for small pose batches, where the time to the last verdict is the latency of the
+// heaviest pose and not throughput (see the end of the step loop)
+template <typename E, bool kLatency = false, typename Source>
 __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCounters &cnt) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned ltMask = (1u << lane) - 1u;
@@ -1115,6 +1119,12 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
             }
             __syncwarp();
             nActive = __popc(__ballot_sync(kFull, sp > bot));
+            // Once the batch is handed out nothing but stealing can fill idle lanes, and the last poses' latency is
+            // all that is left: go back to the bookkeeping as soon as an idle lane could take a pair from a busy one
+            // (1 024 random Alpha poses 75 -> 57 us, a 1 000-test pose alone 55 -> 45 us).  Not in the throughput
+            // variant: the two extra votes per step cost 3 % on 2^20-pose batches.
+            if constexpr (kLatency)
+                if (src.done() && nActive < 32 && __any_sync(kFull, sp - bot >= 2)) break;
         }
     }
 }
@@ -1140,7 +1150,7 @@ __device__ __forceinline__ void flushCounters(const WarpCounters &c, DevCounters
     }
 }
 
-template <typename E>
+template <typename E, bool kLatency>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MPLB_MIN_CTAS)
 checkStatesKernel(SceneDev sc, const double *states, unsigned long long n, uint8_t *__restrict__ valid,
                   DevCounters *ctr, unsigned long long *workCounter, int streamed, unsigned guidedShare) {
@@ -1153,7 +1163,7 @@ checkStatesKernel(SceneDev sc, const double *states, unsigned long long n, uint8
     auto now = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
     if ((threadIdx.x & 31u) == 0) atomicMax(&ctr->negStart, ~now());
 #endif
-    runWarp<E>(sm, sc, src, cnt);
+    runWarp<E, kLatency>(sm, sc, src, cnt);
 #ifdef MPLB_WARP_TIMES
     if ((threadIdx.x & 31u) == 0) {
         atomicMax(&ctr->negFirstDry, ~src.dryAt);
@@ -1224,23 +1234,24 @@ size_t smemBytes(const SceneDev &sc) { return WarpSmem<E>::bytes(sc.stackLevels)
 template <typename K>
 cudaError_t gridFor(K kernel, size_t smem, int numSms, int *grid) {
     static std::mutex mu;
-    static std::map<std::pair<int, size_t>, int> cache;
+    static std::map<std::tuple<const void *, int, size_t>, int> cache;   // (kernels of one signature share this instantiation)
     int dev = 0;
     cudaError_t err = cudaGetDevice(&dev);
     if (err != cudaSuccess) return err;
     std::lock_guard<std::mutex> g(mu);
-    auto it = cache.find({dev, smem});
+    const void *fn = reinterpret_cast<const void *>(kernel);
+    auto it = cache.find({fn, dev, smem});
     if (it == cache.end()) {
-        // the attribute is per device: keep it at the largest size any scene on this device needs
+        // the attribute is per kernel and device: keep it at the largest size any scene on this device needs
         size_t most = smem;
         for (const auto &kv : cache)
-            if (kv.first.first == dev) most = std::max(most, kv.first.second);
+            if (std::get<0>(kv.first) == fn && std::get<1>(kv.first) == dev) most = std::max(most, std::get<2>(kv.first));
         err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most);
         if (err != cudaSuccess) return err;
         int perSm = 0;
         err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kWarpsPerCta * 32, smem);
         if (err != cudaSuccess) return err;
-        it = cache.emplace(std::make_pair(dev, smem), std::max(perSm, 1) * numSms).first;
+        it = cache.emplace(std::make_tuple(fn, dev, smem), std::max(perSm, 1) * numSms).first;
     }
     *grid = it->second;
     return cudaSuccess;
@@ -1249,7 +1260,8 @@ cudaError_t gridFor(K kernel, size_t smem, int numSms, int *grid) {
 template <typename E>
 cudaError_t launchStatesT(const SceneDev &sc, const double *dStates, size_t n, uint8_t *dValid, DevCounters *dCtr,
                           unsigned long long *dWork, bool streamed, int numSms, cudaStream_t stream) {
-    auto k = checkStatesKernel<E>;
+    // batches that leave most of the grid idle are latency bound
+    auto k = n < kLatencyBelow ? checkStatesKernel<E, true> : checkStatesKernel<E, false>;
     const size_t smem = smemBytes<E>(sc);
     int grid = 0;
     cudaError_t err = gridFor(k, smem, numSms, &grid);

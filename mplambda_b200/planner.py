@@ -125,26 +125,57 @@ class BatchedRRTStar(BatchedRRT):
     cheapest valid one wins -- the same choice.  Samples of one batch do not see each other, like the reference's
     concurrent threads.  As in the reference an Edge is immutable (node, parent edge, length, path cost): rewiring a
     node gives it a new edge, its descendants keep pointing at the old one, so every stored cost is the length of a
-    path that exists.  nn needs `knearest` besides insert / nearest; distances come from scenario.space()."""
+    path that exists.  nn needs `knearest` besides insert / nearest; distances come from the nearest-neighbour
+    structure (the space's metric).  All host work per iteration is vectorised numpy."""
 
     def __init__(self, scenario, nn, start, batch=1024, goal_bias=0.01, seed=1, capacity=1 << 16, dimension=6):
         super().__init__(scenario, nn, start, batch, goal_bias, seed, capacity)
         self.dimension = dimension
         # edges: node, parent edge (-1: root), path cost; node -> its current edge
-        self.edge_node = [0]
-        self.edge_parent = [-1]
-        self.edge_cost = [0.0]
+        self._edge_node = np.zeros(capacity, dtype=np.int64)
+        self._edge_parent = np.full(capacity, -1, dtype=np.int64)
+        self._edge_cost = np.zeros(capacity)
+        self.n_edges = 1
         self.node_edge = np.zeros(len(self.nodes), dtype=np.int64)
         self.is_goal = np.zeros(len(self.nodes), dtype=bool)
         self.best_edge, self.best_cost = -1, float("inf")
         self.stats["rewired"] = 0
 
-    def _cost(self, nodes):
-        return np.asarray(self.edge_cost)[self.node_edge[nodes]]
+    edge_node = property(lambda self: self._edge_node[:self.n_edges])
+    edge_parent = property(lambda self: self._edge_parent[:self.n_edges])
+    edge_cost = property(lambda self: self._edge_cost[:self.n_edges])
 
-    def _new_edge(self, node, parent_edge, cost):
-        self.edge_node.append(int(node)); self.edge_parent.append(int(parent_edge)); self.edge_cost.append(float(cost))
-        return len(self.edge_cost) - 1
+    def _cost(self, nodes):
+        return self._edge_cost[self.node_edge[nodes]]
+
+    def _new_edges(self, nodes, parent_edges, costs):
+        m, first = len(nodes), self.n_edges
+        if first + m > len(self._edge_cost):
+            grow = max(len(self._edge_cost), m)
+            self._edge_node = np.concatenate([self._edge_node, np.zeros(grow, dtype=np.int64)])
+            self._edge_parent = np.concatenate([self._edge_parent, np.full(grow, -1, dtype=np.int64)])
+            self._edge_cost = np.concatenate([self._edge_cost, np.zeros(grow)])
+        self._edge_node[first:first + m], self._edge_parent[first:first + m] = nodes, parent_edges
+        self._edge_cost[first:first + m] = costs
+        self.n_edges += m
+        return np.arange(first, first + m)
+
+    def _better_goal(self, nodes):
+        """updateSolution (pcforest.hpp:542-543): the cheapest goal node among `nodes` if it beats the incumbent."""
+        nodes = nodes[self.is_goal[nodes]]
+        if len(nodes):
+            c = self._cost(nodes)
+            i = int(np.argmin(c))
+            if c[i] < self.best_cost:
+                self.best_cost, self.solution = float(c[i]), int(nodes[i])
+                self.best_edge = int(self.node_edge[nodes[i]])
+
+    @staticmethod
+    def _first_per_key(keys, costs):
+        """indices of the cheapest entry of every distinct key (ties: the earliest entry)"""
+        order = np.lexsort((costs, keys))
+        k = keys[order]
+        return order[np.concatenate([[True], k[1:] != k[:-1]])]
 
     def step(self):
         sc = self.scenario
@@ -164,10 +195,10 @@ class BatchedRRTStar(BatchedRRT):
         nbr, ndist = self.nn.knearest(self._scale(qn), k)                    # ascending distance, -1 padded
         have = nbr >= 0
         nbr_safe = np.where(have, nbr, 0)
-        via = np.where(have, self._cost(nbr_safe) + ndist, np.inf)           # path cost through each neighbour
+        nbr_cost = np.where(have, self._cost(nbr_safe), np.inf)
+        via = nbr_cost + ndist                                               # path cost through each neighbour
         parent_cost = self._cost(near[new]) + dnear[new]
         parent = near[new].copy()
-        parent_dist = dnear[new].copy()
         # ---- parent selection: every neighbour that would be cheaper than the nearest node
         rows, cols = np.nonzero(via < parent_cost[:, None])
         rejected = np.zeros_like(have)
@@ -175,9 +206,10 @@ class BatchedRRTStar(BatchedRRT):
             v = sc.check_edges(self.nodes[nbr[rows, cols]], qn[rows])
             self.stats["edges_checked"] += len(rows)
             rejected[rows[~v], cols[~v]] = True                               # pcforest.hpp:527,555-556
-            for r, c in zip(rows[v], cols[v]):
-                if via[r, c] < parent_cost[r]:
-                    parent_cost[r], parent[r], parent_dist[r] = via[r, c], nbr[r, c], ndist[r, c]
+            r, c = rows[v], cols[v]
+            if len(r):
+                best = self._first_per_key(r, via[r, c])
+                parent_cost[r[best]], parent[r[best]] = via[r[best], c[best]], nbr[r[best], c[best]]
         # ---- insert
         if self.n + m > len(self.nodes):
             grow = max(len(self.nodes), m)
@@ -194,27 +226,24 @@ class BatchedRRTStar(BatchedRRT):
         else:
             goal |= np.array([bool(sc.isGoal(x)) for x in qn])
         self.is_goal[ids] = goal
-        for i in range(m):
-            self.node_edge[first + i] = self._new_edge(first + i, self.node_edge[parent[i]], parent_cost[i])
+        self.node_edge[ids] = self._new_edges(ids, self.node_edge[parent], parent_cost)
         self.n += m
         self.nn.insert(self._scale(qn))
-        for i in np.nonzero(goal)[0]:                                         # updateSolution, pcforest.hpp:542-543
-            if parent_cost[i] < self.best_cost:
-                self.best_cost, self.best_edge, self.solution = float(parent_cost[i]), int(self.node_edge[first + i]), first + int(i)
+        self._better_goal(ids)
         # ---- rewiring: neighbours that get cheaper through the new node (not the ones already found unreachable)
         through = parent_cost[:, None] + ndist
-        rows, cols = np.nonzero(have & ~rejected & (through < np.where(have, self._cost(nbr_safe), -np.inf)))
+        rows, cols = np.nonzero(have & ~rejected & (through < np.where(have, nbr_cost, -np.inf)))
         if len(rows):
             v = sc.check_edges(qn[rows], self.nodes[nbr[rows, cols]])
             self.stats["edges_checked"] += len(rows)
-            for r, c in zip(rows[v], cols[v]):
-                node, cost = int(nbr[r, c]), float(through[r, c])
-                if cost < self.edge_cost[self.node_edge[node]]:               # setEdge keeps the cheaper one, pcforest.hpp:569-581
-                    self.node_edge[node] = self._new_edge(node, self.node_edge[first + r], cost)
-                    self.parent[node] = first + r
-                    self.stats["rewired"] += 1
-                    if self.is_goal[node] and cost < self.best_cost:
-                        self.best_cost, self.best_edge, self.solution = cost, int(self.node_edge[node]), node
+            r, c = rows[v], cols[v]
+            if len(r):
+                best = self._first_per_key(nbr[r, c], through[r, c])          # several new nodes, one neighbour: the cheapest
+                node, cost, via_new = nbr[r[best], c[best]], through[r[best], c[best]], first + r[best]
+                self.node_edge[node] = self._new_edges(node, self.node_edge[via_new], cost)   # setEdge, pcforest.hpp:569-581
+                self.parent[node] = via_new
+                self.stats["rewired"] += len(node)
+                self._better_goal(node)
 
     def solve(self, time_limit=60.0, max_iterations=10 ** 9, stop_at_first=False):
         """Anytime: runs until the limit and keeps the cheapest path found (stop_at_first: return at the first one)."""
@@ -233,8 +262,8 @@ class BatchedRRTStar(BatchedRRT):
             return None
         out, e = [], self.best_edge
         while e >= 0:                                                         # an edge chain is an existing path
-            out.append(self.nodes[self.edge_node[e]].copy())
-            e = self.edge_parent[e]
+            out.append(self.nodes[self._edge_node[e]].copy())
+            e = int(self._edge_parent[e])
         return np.asarray(out[::-1])
 
 
