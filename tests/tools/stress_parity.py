@@ -27,3 +27,20 @@ for name in sys.argv[1:] or ["twistycool", "alpha15", "cubicles", "home", "apart
         print("%-10s seed %d: poses %d mismatches %d (gpu %.1f ms, cpu %.0f ms) | edges %d mismatches %d (gpu %.1f ms, cpu %.0f ms)" % (
             name, k, n, pm, tg * 1e3, tc * 1e3, len(A), em, teg * 1e3, tec * 1e3), flush=True)
 print(tot)
+
+# ---- Fetch: 2^18 configurations per seed and 16,384 edges, both environment frames
+from mplambda_b200.workload import FETCH_TASKS, fetch_configs, frame_from_option
+env = np.load("tests/golden/scenes/autolab.npz")["env"]
+ftot = dict(states=0, state_mis=0, edges=0, edge_mis=0)
+for task in sorted(FETCH_TASKS):
+    frame = frame_from_option(FETCH_TASKS[task]["env_frame"])
+    f = M.FetchScenario(frame, env, checkResolution=0.01)
+    forc = O.FetchOracle(env, frame, 0.01)
+    for k in seeds:
+        Q = fetch_configs(1 << 18, SEED + 100 * k)
+        v = f.check_states(Q); w = forc.check_states(Q, threads=thr)
+        A = Q[v][:16384]; B = fetch_configs(len(A), SEED + 100 * k + 1)
+        ev = f.check_edges(A, B); ew = forc.check_edges(A, B, threads=thr)
+        ftot["states"] += len(Q); ftot["state_mis"] += int((v != w).sum()); ftot["edges"] += len(A); ftot["edge_mis"] += int((ev != ew).sum())
+        print("%s seed %d: states %d mismatches %d | edges %d mismatches %d" % (task, k, len(Q), int((v != w).sum()), len(A), int((ev != ew).sum())), flush=True)
+print("fetch", ftot)
