@@ -12,6 +12,9 @@ sampled poses of the Alpha 1.5 puzzle scene (BASELINE.json config
          FCL-order traversal) / kernel time vs the measured HBM peak
   cpu_baseline   the FP64 oracle (oracle/, FCL restatement, OpenMP over all host cores) on a
          bounded sample of the same poses
+  extras (N = 1 only)   the other rows of the path, each next to the CPU path and with its mismatch count:
+         edge batches (config 3), nearest neighbour and k-NN + connect (config 4), Fetch states and edges
+         (config 5), and RRT time-to-solution with the GPU and with the CPU backend (the metric's second half)
 
 `--impl reference` times that CPU path alone (the reference's own FCL path cannot be built:
 FCL/libccd/Eigen/nigh/assimp are absent).  Multi-GPU: one process per GPU under
@@ -232,6 +235,29 @@ def extras(local_rank):
                            "cpu_baseline": {"value": m / dc, "unit": "checks/s", "cores": thr, "kind": "port",
                                             "sample": "first %d configurations" % m},
                            "verdict_mismatches_vs_cpu": int((w != v[:m]).sum())}
+    # ---- the metric's second half: RRT time-to-solution, the same batch-issuing planner (mplambda_b200/planner.py) with the
+    #      GPU scenario + GPU nearest neighbours and with the CPU path (oracle on all host cores) as its backend
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from cpu_backend import CpuNN, CpuScenario
+    from mplambda_b200.planner import BatchedRRT
+    for name in ("cubicles", "twistycool"):
+        env_, robot_ = load_scene(name)
+        sc_ = SE3_SCENES[name]
+        g = M.SE3RigidBodyScenario(env_, robot_, sc_["goal"], sc_["min"], sc_["max"], 0.1, device=local_rank)
+        tg, tc, same = [], [], True
+        for seed in (1, 2, 3):
+            rg = BatchedRRT(g, M.Nigh(M.nn.SE3, device=local_rank), sc_["start"], batch=2048, seed=seed)
+            pg = rg.solve(time_limit=30)
+            rc = BatchedRRT(CpuScenario(env_, robot_, sc_, thr), CpuNN(thr), sc_["start"], batch=2048, seed=seed)
+            pc = rc.solve(time_limit=120)
+            tg.append(rg.stats["seconds"]); tc.append(rc.stats["seconds"])
+            same = same and pg is not None and pc is not None and rg.n == rc.n and np.array_equal(pg, pc)
+        out["rrt_" + name] = {"metric": "RRT time-to-solution (batch-issuing PRRT loop, batch 2048, median of 3 seeds)",
+                              "value": float(np.median(tg)), "unit": "s", "higher_is_better": False,
+                              "cpu_baseline": {"value": float(np.median(tc)), "unit": "s", "cores": thr, "kind": "port",
+                                               "sample": "the same planner, seeds and batches on the oracle"},
+                              "identical_trees_and_paths": bool(same)}
+        g.close()
     # ---- config 5 edges: 16,384 motions between random configurations (valid start), resolution 0.01
     A = Q[v][:1 << 14]
     B = fetch_configs(len(A), SEED + 1)
