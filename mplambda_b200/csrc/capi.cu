@@ -256,7 +256,7 @@ static int createSe3(const double *envTris, size_t nEnv, const double *robotTris
 
 // Host -> device copy of a caller's buffer on `stream`.  Pinned memory goes straight to the copy engine; pageable
 // memory is copied by all cores into two pinned bounce buffers, chunk i + 1 being filled while chunk i is on the wire.
-static int hostToDevice(CallCtx *c, void *dst, const void *src, size_t bytes, cudaStream_t stream) {
+int hostToDevice(CallCtx *c, void *dst, const void *src, size_t bytes, cudaStream_t stream) {
     cudaPointerAttributes at{};
     const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
     cudaGetLastError();   // (older drivers report plain malloc memory as an error)

@@ -119,19 +119,36 @@ struct FetchScene : SceneBase {
         const size_t nb = std::min(n, kBatch);
         int rc;
         FetchScratch w{};
-        if ((rc = c->in0.reserve(nb * 8 * sizeof(double))) || (rc = c->out.reserve(nb)) || (rc = reserveScratch(c, nb, w)))
+        // chunks of kBatch states: the input of chunk i + 1 crosses the link (copy stream, second buffer) while chunk i
+        // is being checked; the verdicts of all chunks go back in one copy at the end
+        if ((rc = c->in0.reserve(nb * 8 * sizeof(double))) || (rc = c->in1.reserve(nb * 8 * sizeof(double))) ||
+            (rc = c->dead.reserve(n)) || (rc = reserveScratch(c, nb, w)))
             return rc;
-        MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(FetchCounters), c->stream));
-        for (size_t lo = 0; lo < n; lo += kBatch) {
-            const size_t cnt = std::min(kBatch, n - lo);
-            MPLB_CUDA(cudaMemcpyAsync(c->in0.ptr, states + 8 * lo, cnt * 8 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-            MPLB_CUDA(launchFetchStates(dev, (const double *)c->in0.ptr, cnt, w, (uint8_t *)c->out.ptr,
-                                        (FetchCounters *)c->ctr.ptr, numSms, c->stream));
-            hLaunches += 6;
-            MPLB_CUDA(cudaMemcpyAsync(valid + lo, c->out.ptr, cnt, cudaMemcpyDeviceToHost, c->stream));
+        while (c->events.size() < 4) {
+            cudaEvent_t ev;
+            MPLB_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            c->events.push_back(ev);
         }
+        MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(FetchCounters), c->stream));
+        size_t chunk = 0;
+        for (size_t lo = 0; lo < n; lo += kBatch, ++chunk) {
+            const size_t cnt = std::min(kBatch, n - lo);
+            const int b = (int)(chunk & 1);
+            double *in = (double *)(b ? c->in1.ptr : c->in0.ptr);
+            if (chunk >= 2) MPLB_CUDA(cudaStreamWaitEvent(c->copyStream, c->events[2 + b], 0));   // the buffer's previous chunk is done
+            if ((rc = hostToDevice(c, in, states + 8 * lo, cnt * 8 * sizeof(double), c->copyStream))) return rc;
+            MPLB_CUDA(cudaEventRecord(c->events[b], c->copyStream));
+            MPLB_CUDA(cudaStreamWaitEvent(c->stream, c->events[b], 0));
+            MPLB_CUDA(launchFetchStates(dev, in, cnt, w, (uint8_t *)c->dead.ptr + lo, (FetchCounters *)c->ctr.ptr, numSms,
+                                        c->stream));
+            MPLB_CUDA(cudaEventRecord(c->events[2 + b], c->stream));
+            hLaunches += 6;
+        }
+        MPLB_CUDA(cudaMemcpyAsync(valid, c->dead.ptr, n, cudaMemcpyDeviceToHost, c->stream));
         hChecks += n;
-        return finish(c);
+        rc = finish(c);
+        cudaStreamSynchronize(c->copyStream);
+        return rc;
     }
 
     // isValid(from,to) (fetch_scenario.hpp:120-173): verdict = valid(to) AND every interpolated sample.  The samples

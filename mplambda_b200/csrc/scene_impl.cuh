@@ -56,6 +56,10 @@ struct CallCtx {
     ~CallCtx();
 };
 
+// Host -> device copy of a caller's buffer on `stream`: pinned memory goes straight to the copy engine, pageable memory
+// through two pinned bounce buffers filled by all cores (capi.cu)
+int hostToDevice(CallCtx *c, void *dst, const void *src, size_t bytes, cudaStream_t stream);
+
 struct SceneBase {
     int device = 0;
     int numSms = 0;
