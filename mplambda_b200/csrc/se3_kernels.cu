@@ -347,7 +347,8 @@ struct WarpCounters {
 // and is told the verdict when the slot retires.
 
 // isValid(q) over an array: states are taken in index order from a global counter.
-struct StateSource {
+template <bool kStreamed>
+struct StateSourceT {
     static constexpr bool kIntervals = false;  // every slot is a single state
     const double *states;
     unsigned long long n;
@@ -358,7 +359,7 @@ struct StateSource {
     // background; a lane picks its state up the moment none of its 7 doubles shows the pattern any more
     // (aligned 8-byte words are never torn by the copy engine).  The wait is bounded: a copy that never
     // arrives -- or a state that really holds the reserved pattern -- is reported, not spun on.
-    bool streamed = false;
+    static constexpr bool streamed = kStreamed;   // compile time: the resident kernel carries none of the streaming state
     unsigned stalled = 0;
     unsigned long long base = 0;
     bool exhausted = false;
@@ -464,7 +465,7 @@ struct StateSource {
             }
             if (here) return true;
             if (spins >= (1u << 18)) {   // ~0.5 s
-                const_cast<StateSource *>(this)->stalled = 1;
+                const_cast<StateSourceT *>(this)->stalled = 1;
                 return false;
             }
             __nanosleep(2000);
@@ -1150,13 +1151,13 @@ __device__ __forceinline__ void flushCounters(const WarpCounters &c, DevCounters
     }
 }
 
-template <typename E, bool kLatency>
+template <typename E, bool kLatency, bool kStreamed>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MPLB_MIN_CTAS)
 checkStatesKernel(SceneDev sc, const double *states, unsigned long long n, uint8_t *__restrict__ valid,
-                  DevCounters *ctr, unsigned long long *workCounter, int streamed, unsigned guidedShare) {
+                  DevCounters *ctr, unsigned long long *workCounter, unsigned guidedShare) {
     WarpSmem<E> sm = warpSmem<E>(sc.stackLevels);
-    StateSource src;
-    src.states = states; src.n = n; src.valid = valid; src.counter = workCounter; src.streamed = streamed != 0;
+    StateSourceT<kStreamed> src;
+    src.states = states; src.n = n; src.valid = valid; src.counter = workCounter;
     src.crew = (unsigned long long)gridDim.x * kWarpsPerCta * guidedShare;
     WarpCounters cnt;
 #ifdef MPLB_WARP_TIMES
@@ -1261,7 +1262,8 @@ template <typename E>
 cudaError_t launchStatesT(const SceneDev &sc, const double *dStates, size_t n, uint8_t *dValid, DevCounters *dCtr,
                           unsigned long long *dWork, bool streamed, int numSms, cudaStream_t stream) {
     // batches that leave most of the grid idle are latency bound
-    auto k = n < kLatencyBelow ? checkStatesKernel<E, true> : checkStatesKernel<E, false>;
+    auto k = streamed ? checkStatesKernel<E, false, true>   // (streamed batches are >= 65,536 states: see capi.cu)
+                      : n < kLatencyBelow ? checkStatesKernel<E, true, false> : checkStatesKernel<E, false, false>;
     const size_t smem = smemBytes<E>(sc);
     int grid = 0;
     cudaError_t err = gridFor(k, smem, numSms, &grid);
@@ -1269,8 +1271,7 @@ cudaError_t launchStatesT(const SceneDev &sc, const double *dStates, size_t n, u
     // small batches are latency bound: one state per warp, spread over as many SMs as there are
     grid = (int)std::min<unsigned long long>(grid, (n + kWarpsPerCta - 1) / kWarpsPerCta);
     constexpr unsigned guidedShare = 2;   // a warp takes at most 1/(2 x warps) of what is left (1, 4, 8 measured no better)
-    k<<<std::max(grid, 1), kWarpsPerCta * 32, smem, stream>>>(sc, dStates, n, dValid, dCtr, dWork, streamed ? 1 : 0,
-                                                              guidedShare);
+    k<<<std::max(grid, 1), kWarpsPerCta * 32, smem, stream>>>(sc, dStates, n, dValid, dCtr, dWork, guidedShare);
     return cudaGetLastError();
 }
 
