@@ -415,28 +415,6 @@ __device__ __forceinline__ float segmentDistance(const float c1[3], const float 
     return sqrtf(dd);
 }
 
-// boxes of two shapes given by their world frames: certainly disjoint?
-__device__ bool shapeBoxesDisjoint(const FetchShape &s1, const FrameD &f1, const FetchShape &s2, const FrameD &f2) {
-    float e1[3], e2[3];
-    shapeExtents(s1, e1);
-    shapeExtents(s2, e2);
-    // box axes are the frame's columns; express box 2 in frame 1: R = R1^T R2, T = R1^T (t2 - t1)
-    const float4 a0 = make_float4(1, 0, 0, 0), a1 = make_float4(0, 1, 0, 0), a2 = make_float4(0, 0, 1, 0);
-    const float4 ae = make_float4(e1[0] * 1.00001f, e1[1] * 1.00001f, e1[2] * 1.00001f, 0);
-    const float4 be = make_float4(e2[0] * 1.00001f, e2[1] * 1.00001f, e2[2] * 1.00001f, 0);
-    float R[3][3], T[3];
-    const float d[3] = {(float)(f2.t[0] - f1.t[0]), (float)(f2.t[1] - f1.t[1]), (float)(f2.t[2] - f1.t[2])};
-    for (int i = 0; i < 3; ++i) {
-        for (int j = 0; j < 3; ++j)
-            R[i][j] = (float)f1.R[0][i] * (float)f2.R[0][j] + (float)f1.R[1][i] * (float)f2.R[1][j] + (float)f1.R[2][i] * (float)f2.R[2][j];
-        T[i] = (float)f1.R[0][i] * d[0] + (float)f1.R[1][i] * d[1] + (float)f1.R[2][i] * d[2];
-    }
-    float dist2;
-    return !obbOverlap(a0, a1, a2, ae, a0, a1, a2, be, make_float4(R[0][0], R[0][1], R[0][2], T[0]),
-                       make_float4(R[1][0], R[1][1], R[1][2], T[1]), make_float4(R[2][0], R[2][1], R[2][2], T[2]), kCullSlack,
-                       dist2);
-}
-
 __device__ void makeShapeObj(const FetchShape &s, const FrameD &f, CcdObj &o) {
     o.kind = s.type;
     o.a = s.a; o.b = s.b; o.c = s.c;
