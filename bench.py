@@ -113,6 +113,59 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class HostMemoryNearGpu:
+    """`numactl --preferred=<the GPU's NUMA node>` for the allocations made inside the block: the pinned batches of
+    rank r are placed in the memory of the socket GPU r hangs off, so that with 8 ranks the input copies do not all
+    read one socket's DRAM (and half of them across the socket link).  Best effort: a host that exposes no NUMA
+    topology, or a cpuset that does not allow the node, leaves the placement as it was and says so."""
+    MPOL_DEFAULT, MPOL_PREFERRED, SYS_SET_MEMPOLICY = 0, 1, 238   # x86_64
+
+    def __init__(self, device, enabled=True):
+        self.node, self.note = -1, "default placement"
+        if not enabled:
+            self.note = "default placement (--no-numa)"
+            return
+        try:
+            import ctypes
+            import platform
+            if platform.machine() != "x86_64":
+                raise OSError("syscall number known for x86_64 only")
+            buf = ctypes.create_string_buffer(32)
+            rt = ctypes.CDLL("libcudart.so.12")
+            if rt.cudaDeviceGetPCIBusId(buf, 32, int(device)) != 0:
+                raise OSError("cudaDeviceGetPCIBusId failed")
+            with open("/sys/bus/pci/devices/%s/numa_node" % buf.value.decode().lower()) as f:
+                self.node = int(f.read())
+            if self.node < 0:
+                self.note = "default placement (the host reports no NUMA node for the GPU)"
+        except (OSError, ValueError) as e:
+            self.node, self.note = -1, "default placement (%s)" % e
+
+    def _policy(self, mode, node):
+        import ctypes
+        libc = ctypes.CDLL(None, use_errno=True)
+        if node < 0:
+            return libc.syscall(self.SYS_SET_MEMPOLICY, mode, None, 0)
+        mask = (ctypes.c_ulong * 16)()
+        mask[node // 64] = 1 << (node % 64)
+        return libc.syscall(self.SYS_SET_MEMPOLICY, mode, mask, 16 * 64 + 1)
+
+    def __enter__(self):
+        if self.node >= 0:
+            if self._policy(self.MPOL_PREFERRED, self.node) == 0:
+                self.note = "pinned batches preferred on NUMA node %d (the GPU's)" % self.node
+            else:
+                import ctypes
+                self.note = "default placement (set_mempolicy: errno %d)" % ctypes.get_errno()
+                self.node = -1
+        return self
+
+    def __exit__(self, *exc):
+        if self.node >= 0:
+            self._policy(self.MPOL_DEFAULT, -1)
+        return False
+
+
 def cpu_baseline(env, robot, poses, threads, target_seconds=12.0):
     """Oracle O2 (FCL traversal order, first-hit exit) on a bounded sample sized for ~10-20 s."""
     from oracle import oracle_py as O
@@ -313,6 +366,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-numa", action="store_true", help="leave the pinned host batches where the OS puts them")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "mplb" else args.warmup
 
@@ -343,8 +397,11 @@ def main():
     host = [se3_poses(N_POSES, sc["min"], sc["max"], SEED, start=base + r * N_POSES) for r in range(ROTATE)]
     dev = [torch.from_numpy(h).cuda() for h in host]
     out = torch.empty(N_POSES, dtype=torch.uint8, device="cuda")
-    pinned = [torch.from_numpy(h).pin_memory() for h in host]
-    pinned_out = torch.empty(N_POSES, dtype=torch.uint8).pin_memory()
+    with HostMemoryNearGpu(local_rank, not args.no_numa) as placement:
+        pinned = [torch.from_numpy(h).pin_memory() for h in host]
+        pinned_out = torch.empty(N_POSES, dtype=torch.uint8).pin_memory()
+    if world > 1:
+        print("rank %d: %s" % (rank, placement.note), file=sys.stderr)
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -426,7 +483,7 @@ def main():
                        "sharding": "pose stream split by rank, BVH replicated, no collective"},
             "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "checks/s", "h2d_bytes_per_step": N_POSES * 56,
                     "d2h_bytes_per_step": N_POSES, "ms_per_step": e2e_ms / args.steps,
-                    "api": "mplb_check_states (pinned host buffers)",
+                    "api": "mplb_check_states (pinned host buffers)", "host_memory": placement.note,
                     "h2d_copy_alone_ms": h2d_ms, "h2d_gbs": N_POSES * 56 / (h2d_ms * 1e-3) / 1e9,
                     "note": "the 56 B/pose input copy is the longer leg; the kernel runs underneath it and picks states up as they land"},
             "gpu_launches": int(st["launches"]),
