@@ -2,10 +2,19 @@
 repository holds.  PARITY UNPINNED: no golden vectors exist; the anchors are
   * test/fetch_robot_jacobian_test.cpp's use of fk(): reproduced as closed-form frame checks;
   * the scripted start states (scripts/fetch_task_00{1,2}.sh) must be valid;
-  * src/mpl_fetch.cpp:36-220 holds ten joint-space paths recorded by the authors; six of them
-    (003,004,005,008,009,010) validate completely (every waypoint, every discretised edge at
-    resolution 0.01) under the task-001 environment frame, three more up to their last edge
-    (the approach into the grasp), 001 predates the current environment."""
+  * src/mpl_fetch.cpp:36-220 holds ten joint-space paths recorded by the authors, all from the rest
+    configuration to the task-001 grasp point (gripper link at 0.73, 0.17, 0.88).  Under the task-001
+    environment frame (scripts/fetch_task_001.sh:33) six of them (003,004,005,008,009,010) validate
+    completely (every waypoint, every discretised edge at resolution 0.01); 002, 006 and 007 validate
+    in every waypoint and every edge but the last, where the gripper box passes 0.4-14 mm inside the
+    44-triangle cylinder standing on the table next to the grasp point for 21 of 671 (002) and 24 of
+    186 (006 = 007) interpolated samples; 001 is in collision from its fourth waypoint on (forearm /
+    wrist / gripper against the table objects).  Under the task-002 frame (scripts/fetch_task_002.sh:39,
+    src/mpl_fetch.cpp:235) every path but 008 ENDS in collision, so task 001 is the frame they were
+    recorded in.  What the three grazing approaches were recorded against (an earlier AUTOLAB.dae /
+    collision box, or an FCL behaviour the restatement lacks) cannot be decided without FCL: see
+    DESIGN.md section 2.  test_recorded_paths pins all of the above so that any change of the
+    restatement that moves it shows."""
 import os
 
 import numpy as np
@@ -67,10 +76,26 @@ def test_recorded_paths(autolab, oracle):
         P = paths[name]
         assert orc.check_states(P).all(), name
         assert orc.check_edges(P[:-1], P[1:]).all(), name
-    for name in ("makePath002", "makePath006", "makePath007"):
+    for name, steps, bad in (("makePath002", 671, (637, 657)), ("makePath006", 186, (129, 152)),
+                             ("makePath007", 186, (129, 152))):
         P = paths[name]
         assert orc.check_states(P).all(), name
         assert orc.check_edges(P[:-2], P[1:-1]).all(), name
+        # the last edge: exactly one run of samples collides, and only the gripper box (geometry 9) with the mesh
+        a, b = P[-2], P[-1]
+        assert orc.edge_steps(a, b) == steps and not orc.check_edges(a[None], b[None])[0]
+        S = np.array([a + (b - a) * (i / float(steps)) for i in range(1, steps)])
+        hit = np.nonzero(~orc.check_states(S))[0] + 1
+        assert (hit[0], hit[-1]) == bad and len(hit) == bad[1] - bad[0] + 1, (name, hit)
+        assert {orc.why(S[i - 1]) for i in hit} == {110}
+    # 001: valid up to its third waypoint only
+    P = paths["makePath001"]
+    assert list(orc.check_states(P)) == [True, True, True, False, False, True]
+    assert [orc.why(q) for q in P[3:5]] == [108, 107]
+    # the other frame the reference holds (task 002) is not the one these paths were recorded in
+    orc2 = oracle.FetchOracle(autolab, frame_from_option(FETCH_TASKS["fetch_task_002"]["env_frame"]), 0.01)
+    ends = {name: bool(orc2.check_states(paths[name][-1:])[0]) for name in paths.files}
+    assert [n for n, v in ends.items() if v] == ["makePath008"]
 
 
 def test_known_answers_are_stable(autolab, oracle):
