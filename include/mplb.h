@@ -122,6 +122,12 @@ typedef struct {
     uint64_t exact_tests; /* FP64 exact re-evaluations of uncertain triangle pairs             */
     uint64_t launches;    /* kernels launched                                                  */
     uint64_t env_tris, robot_tris, env_nodes, robot_nodes;
+    uint64_t stream_stalls;   /* large host batches whose input did not arrive under the running kernel and were
+                                 repeated copy-then-kernel (a profiler serialising launches); 0 in normal operation */
+    uint64_t streaming_off;   /* 1 while the scene sends large host batches copy-then-kernel because of such stalls */
+    uint64_t ambiguous_steps; /* index-named edges whose device-planned step count was within rounding of an integer
+                                 and was re-planned with host libm (mplb_check_edges_indexed)                          */
+    uint64_t coalesced_calls; /* scalar calls that shared a launch with other threads' calls (see mplb_scene_set_coalescing) */
 } mplb_stats_t;
 int mplb_scene_stats(mplb_scene *scene, mplb_stats_t *out, int reset);
 

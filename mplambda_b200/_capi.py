@@ -13,7 +13,8 @@ OK, ERR_INVALID, ERR_IO, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4
 
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("checks", "bv_tests", "tri_tests", "exact_tests", "launches",
-                                           "env_tris", "robot_tris", "env_nodes", "robot_nodes")]
+                                           "env_tris", "robot_tris", "env_nodes", "robot_nodes",
+                                           "stream_stalls", "streaming_off", "ambiguous_steps", "coalesced_calls")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -5,6 +5,8 @@
 #include "se3_device.cuh"
 #include "scene_impl.cuh"
 
+#include <cuda.h>   // types of the stream memory operation only: the entry point is resolved at run time
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -140,7 +142,8 @@ int selectDevice(int device, int *numSms) {
 
 struct Se3Scene : SceneBase {
     double so3w = 50, l2w = 1, invStep = 10;
-    std::atomic<bool> streamingOff{false};   // set when a streamed batch's copy could not overlap its kernel
+    // streamed batches whose input did not arrive under the kernel, in a row: two switch streaming off (capi.cu)
+    std::atomic<unsigned> streamStallsInARow{0}, unstreamedCalls{0};
     SceneDev dev{};
     DevBuf robotNodes, envNodes, robotTris, envTris, robotTris64, envTris64;
     size_t nEnvTris = 0, nRobotTris = 0;
@@ -254,14 +257,19 @@ static int createSe3(const double *envTris, size_t nEnv, const double *robotTris
     return MPLB_OK;
 }
 
-// Host -> device copy of a caller's buffer on `stream`.  Pinned memory goes straight to the copy engine; pageable
-// memory is copied by all cores into two pinned bounce buffers, chunk i + 1 being filled while chunk i is on the wire.
-int hostToDevice(CallCtx *c, void *dst, const void *src, size_t bytes, cudaStream_t stream) {
+bool isPinned(const void *p) {
     cudaPointerAttributes at{};
-    const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    const bool pinned = cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost;
     cudaGetLastError();   // (older drivers report plain malloc memory as an error)
+    return pinned;
+}
+
+// Host -> device copy of a caller's buffer on `stream`.  Pinned memory goes straight to the copy engine; pageable
+// memory is copied by all cores into two pinned bounce buffers, piece i + 1 being filled while piece i is on the wire
+// (the buffers alternate across calls too: c->bounceNext).
+int hostToDevice(CallCtx *c, void *dst, const void *src, size_t bytes, cudaStream_t stream) {
     static const bool off = std::getenv("MPLB_NO_BOUNCE") != nullptr;   // diagnostic: let the driver stage pageable memory
-    if (pinned || off || bytes < (1u << 20)) {
+    if (bytes < (1u << 20) || off || isPinned(src)) {
         MPLB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
         return MPLB_OK;
     }
@@ -270,11 +278,12 @@ int hostToDevice(CallCtx *c, void *dst, const void *src, size_t bytes, cudaStrea
             MPLB_CUDA(cudaMallocHost((void **)&c->hBounce[i], kBounceBytes));
             MPLB_CUDA(cudaEventCreateWithFlags(&c->bounceDone[i], cudaEventDisableTiming));
         }
-    int b = 0;
-    for (size_t off = 0; off < bytes; off += kBounceBytes, b ^= 1) {
-        const size_t len = std::min(kBounceBytes, bytes - off);
-        MPLB_CUDA(cudaEventSynchronize(c->bounceDone[b]));   // the buffer's previous chunk has left
-        const unsigned char *s = (const unsigned char *)src + off;
+    for (size_t at = 0; at < bytes; at += kBounceBytes) {
+        const int b = c->bounceNext;
+        c->bounceNext ^= 1;
+        const size_t len = std::min(kBounceBytes, bytes - at);
+        MPLB_CUDA(cudaEventSynchronize(c->bounceDone[b]));   // the buffer's previous piece has left
+        const unsigned char *s = (const unsigned char *)src + at;
         unsigned char *d = c->hBounce[b];
         const long long parts = (long long)((len + (1u << 20) - 1) >> 20);
 #pragma omp parallel for schedule(static)
@@ -282,7 +291,7 @@ int hostToDevice(CallCtx *c, void *dst, const void *src, size_t bytes, cudaStrea
             const size_t lo = (size_t)p << 20, n = std::min((size_t)1 << 20, len - lo);
             std::memcpy(d + lo, s + lo, n);
         }
-        MPLB_CUDA(cudaMemcpyAsync((unsigned char *)dst + off, d, len, cudaMemcpyHostToDevice, stream));
+        MPLB_CUDA(cudaMemcpyAsync((unsigned char *)dst + at, d, len, cudaMemcpyHostToDevice, stream));
         MPLB_CUDA(cudaEventRecord(c->bounceDone[b], stream));
     }
     return MPLB_OK;
@@ -360,17 +369,77 @@ static int finishCall(SceneBase *sc, CallCtx *c, size_t checks, uint64_t *states
     return account(sc, *c->hCtr, checks, statesOut);
 }
 
-// Large host batches stream in under the running kernel: the device input buffer is pre-filled with an
-// all-ones pattern, the kernel is launched right away and ONE host->device copy overwrites the buffer in
-// the background; the kernel hands out states in index order and each lane picks its state up when it has
-// landed.  The input is 56 B/state and the kernel needs ~1 ns/state, so the call costs about one
-// host->device copy of the batch.
+// ---- stream memory operations: cuStreamWriteValue32 resolved at run time (no link-time dependency on libcuda)
+typedef CUresult (*WriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static WriteValue32Fn streamWriteValue32() {
+    static const WriteValue32Fn fn = []() -> WriteValue32Fn {
+        if (std::getenv("MPLB_NO_STREAM_MEMOPS")) return nullptr;   // diagnostic: exercise the chunked fallback
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (WriteValue32Fn)p;
+    }();
+    return fn;
+}
+
+// Large host batches stream in under the running kernel.  The batch is copied in chunks on the context's copy stream
+// and, behind each chunk on that stream, a stream memory operation (cuStreamWriteValue32: ordered after the copy, with
+// a system-wide fence in front of the write) sets that chunk's arrival flag to this call's epoch.  The kernel is
+// launched first on the compute stream, hands states out in index order and picks a claim up once its chunk's flag is
+// there (acquire load).  The input is 56 B/state and the kernel needs ~1 ns/state, so the call costs about one
+// host->device copy of the batch.  Without stream memory operations -- or when a kernel reports that its input did not
+// arrive in time (a profiler serialising the kernel and the copies) -- the batch goes chunk by chunk copy-then-kernel.
 static bool streamBatch(size_t n) {
     static const long forced = [] {
         const char *e = std::getenv("MPLB_STREAM_MIN");
         return e ? std::atol(e) : 0L;
     }();
     return n >= (size_t)(forced > 0 ? forced : 65536);
+}
+
+constexpr size_t kMaxChunks = 256;
+static size_t chunkStatesFor(size_t n) {
+    static const long forced = [] {
+        const char *e = std::getenv("MPLB_STREAM_CHUNK");
+        return e ? std::atol(e) : 0L;
+    }();
+    size_t c = forced > 0 ? (size_t)forced : std::min<size_t>(32768, std::max<size_t>(8192, ((n / 16) + 1023) & ~(size_t)1023));
+    c = std::max(c, (n + kMaxChunks - 1) / kMaxChunks);
+    return c;
+}
+
+// both streams idle before the context goes back to the pool, whatever path the call leaves by
+struct StreamsQuiet {
+    CallCtx *c;
+    ~StreamsQuiet() {
+        cudaStreamSynchronize(c->copyStream);
+        cudaStreamSynchronize(c->stream);
+    }
+};
+
+// copy-then-kernel in a few pieces: piece i + 1 is on the wire while piece i is being checked
+static int se3StatesPipelined(Se3Scene *sc, CallCtx *c, const double *states, size_t n, double *dIn, uint8_t *dOut) {
+    const size_t pieces = n >= 4 * 16384 ? 4 : 1, per = (n + pieces - 1) / pieces;
+    while (c->events.size() < pieces) {
+        cudaEvent_t e;
+        MPLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->events.push_back(e);
+    }
+    int rc;
+    for (size_t p = 0, lo = 0; lo < n; ++p, lo += per) {
+        const size_t cnt = std::min(per, n - lo);
+        if ((rc = hostToDevice(c, dIn + 7 * lo, states + 7 * lo, cnt * 7 * sizeof(double), c->copyStream))) return rc;
+        MPLB_CUDA(cudaEventRecord(c->events[p], c->copyStream));
+        MPLB_CUDA(cudaStreamWaitEvent(c->stream, c->events[p], 0));
+        MPLB_CUDA(launchCheckStates(sc->dev, dIn + 7 * lo, cnt, dOut + lo, (DevCounters *)c->ctr.ptr, (unsigned *)c->work.ptr,
+                                    sc->numSms, c->stream));
+        sc->hLaunches += 1;
+    }
+    return MPLB_OK;
 }
 
 static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t *valid) {
@@ -387,7 +456,7 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
             MPLB_CUDA(cudaMemsetAsync(ctl, 0, kCtlHeader, c->stream));
             MPLB_CUDA(cudaMemcpyAsync(c->stage.ptr, c->hStage, bytes, cudaMemcpyHostToDevice, c->stream));
             MPLB_CUDA(launchCheckStates(sc->dev, (const double *)c->stage.ptr, n, ctl + kCtlHeader, (DevCounters *)ctl,
-                                        (unsigned *)(ctl + kCtlHeader - 128), sc->numSms, c->stream, false, true));
+                                        (unsigned *)(ctl + kCtlHeader - 128), sc->numSms, c->stream, StreamedInput(), true));
             MPLB_CUDA(cudaMemcpyAsync(c->hCtl, ctl, kCtlHeader + n, cudaMemcpyDeviceToHost, c->stream));
             return MPLB_OK;
         };
@@ -405,63 +474,71 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
     if ((rc = c->in0.reserve(bytes)) || (rc = c->out.reserve(n))) return rc;
     double *dIn = (double *)c->in0.ptr;
     uint8_t *dOut = (uint8_t *)c->out.ptr;
-    const bool streamed = streamBatch(n) && !sc->streamingOff.load(std::memory_order_relaxed);
+    const WriteValue32Fn writeValue = streamWriteValue32();
+    const bool streamed = streamBatch(n) && writeValue && sc->streamStallsInARow.load(std::memory_order_relaxed) < 2;
     // MPLB_TIMELINE=1: print where a streamed call's time goes (diagnostic)
     static const bool timeline = std::getenv("MPLB_TIMELINE") != nullptr;
     static thread_local cudaEvent_t tl[5] = {};
     const auto h0 = std::chrono::steady_clock::now();
     if (timeline && !tl[0])
         for (auto &e : tl) cudaEventCreate(&e);
+    StreamsQuiet quiet{c};
     MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(DevCounters), c->stream));
     if (!streamed) {
-        if ((rc = hostToDevice(c, dIn, states, bytes, c->stream))) return rc;
-        MPLB_CUDA(launchCheckStates(sc->dev, dIn, n, dOut, (DevCounters *)c->ctr.ptr, (unsigned *)c->work.ptr, sc->numSms,
-                                    c->stream));
+        if ((rc = se3StatesPipelined(sc, c, states, n, dIn, dOut))) return rc;
     } else {
-        if (c->events.empty()) {
-            cudaEvent_t e;
-            MPLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            c->events.push_back(e);
+        const size_t chunk = chunkStatesFor(n), nChunks = (n + chunk - 1) / chunk;
+        if (!c->flags.ptr) {
+            if ((rc = c->flags.reserve(kMaxChunks * sizeof(unsigned)))) return rc;
+            MPLB_CUDA(cudaMemsetAsync(c->flags.ptr, 0, kMaxChunks * sizeof(unsigned), c->stream));
         }
+        if (++c->epoch == 0) c->epoch = 1;   // (flags start at 0)
+        StreamedInput in;
+        in.flags = (const unsigned *)c->flags.ptr;
+        in.epoch = c->epoch;
+        in.chunkStates = (unsigned)chunk;
         if (timeline) cudaEventRecord(tl[0], c->copyStream);
-        MPLB_CUDA(cudaMemsetAsync(dIn, 0xFF, bytes, c->copyStream));
-        static const bool precopy = std::getenv("MPLB_STREAM_PRECOPY") != nullptr;   // diagnostic: the streamed kernel on data that is already there
-        if (precopy && (rc = hostToDevice(c, dIn, states, bytes, c->copyStream))) return rc;
-        MPLB_CUDA(cudaEventRecord(c->events[0], c->copyStream));
-        MPLB_CUDA(cudaStreamWaitEvent(c->stream, c->events[0], 0));
         if (timeline) cudaEventRecord(tl[1], c->stream);
         MPLB_CUDA(launchCheckStates(sc->dev, dIn, n, dOut, (DevCounters *)c->ctr.ptr, (unsigned *)c->work.ptr, sc->numSms,
-                                    c->stream, true));
+                                    c->stream, in));
+        sc->hLaunches += 1;
         if (timeline) cudaEventRecord(tl[3], c->stream);
-        if (!precopy && (rc = hostToDevice(c, dIn, states, bytes, c->copyStream))) return rc;
+        for (size_t k = 0; k < nChunks; ++k) {
+            const size_t lo = k * chunk, cnt = std::min(chunk, n - lo);
+            if ((rc = hostToDevice(c, dIn + 7 * lo, states + 7 * lo, cnt * 7 * sizeof(double), c->copyStream))) return rc;
+            const CUresult wr = writeValue((CUstream)c->copyStream, (CUdeviceptr)((unsigned *)c->flags.ptr + k), c->epoch, 0);
+            if (wr != CUDA_SUCCESS) return fail(MPLB_ERR_CUDA, "cuStreamWriteValue32 failed (%d)", (int)wr);
+        }
         if (timeline) cudaEventRecord(tl[2], c->copyStream);
     }
-    sc->hLaunches += 1;
     MPLB_CUDA(cudaMemcpyAsync(valid, dOut, n, cudaMemcpyDeviceToHost, c->stream));
     if (timeline && streamed) cudaEventRecord(tl[4], c->stream);
     int frc = finishCall(sc, c, n, nullptr);
     if (streamed) cudaStreamSynchronize(c->copyStream);
     if (timeline && streamed) {
-        float a, b, k, d;
-        cudaEventElapsedTime(&a, tl[0], tl[1]);
+        float b, k, d;
         cudaEventElapsedTime(&b, tl[0], tl[2]);
-        cudaEventElapsedTime(&k, tl[0], tl[3]);
-        cudaEventElapsedTime(&d, tl[0], tl[4]);
-        std::fprintf(stderr, "[mplb timeline] n=%zu  pattern fill done %.3f ms, copy done %.3f, kernel done %.3f, verdicts back %.3f, host %.3f\n",
-                     n, a, b, k, d, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());
+        cudaEventElapsedTime(&k, tl[1], tl[3]);
+        cudaEventElapsedTime(&d, tl[1], tl[4]);
+        std::fprintf(stderr, "[mplb timeline] n=%zu  copies done %.3f ms, kernel done %.3f, verdicts back %.3f, host %.3f\n",
+                     n, b, k, d, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());
     }
     if (streamed && c->hCtr->pad) {
-        // The copy never reached the waiting kernel: something (a profiler replaying or serialising launches, a
-        // debugger) keeps the two from overlapping.  Repeat this batch copy-then-kernel and stay with that.
-        sc->streamingOff.store(true, std::memory_order_relaxed);
+        // The chunks did not reach the waiting kernel in time: something (a profiler replaying or serialising launches,
+        // a debugger) keeps the copies from running under it.  This batch is repeated copy-then-kernel; two such calls
+        // in a row switch the scene to that order until a later probe (every 64th large call) streams again.
+        sc->hStreamStalls += 1;
+        sc->streamStallsInARow.fetch_add(1, std::memory_order_relaxed);
         if (frc == MPLB_OK) sc->hChecks -= n;   // counted again below
         MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(DevCounters), c->stream));
-        MPLB_CUDA(cudaMemcpyAsync(dIn, states, bytes, cudaMemcpyHostToDevice, c->stream));
-        MPLB_CUDA(launchCheckStates(sc->dev, dIn, n, dOut, (DevCounters *)c->ctr.ptr, (unsigned *)c->work.ptr, sc->numSms,
-                                    c->stream));
-        sc->hLaunches += 1;
+        if ((rc = se3StatesPipelined(sc, c, states, n, dIn, dOut))) return rc;
         MPLB_CUDA(cudaMemcpyAsync(valid, dOut, n, cudaMemcpyDeviceToHost, c->stream));
         return finishCall(sc, c, n, nullptr);
+    }
+    if (streamed) {
+        sc->streamStallsInARow.store(0, std::memory_order_relaxed);
+    } else if (streamBatch(n) && writeValue && (sc->unstreamedCalls.fetch_add(1, std::memory_order_relaxed) & 63u) == 63u) {
+        sc->streamStallsInARow.store(1, std::memory_order_relaxed);   // probe: the next large call streams again
     }
     return frc;
 }
@@ -718,13 +795,18 @@ int mplb_scene_stats(mplb_scene *scene, mplb_stats_t *out, int reset) {
     out->launches = b->hLaunches;
     out->env_nodes = b->envNodeCount;
     out->robot_nodes = b->robotNodeCount;
+    out->stream_stalls = b->hStreamStalls;
+    out->ambiguous_steps = b->hAmbiguous;
+    out->coalesced_calls = b->hCoalesced;
     if (auto *s = dynamic_cast<Se3Scene *>(b)) {
         out->env_tris = s->nEnvTris;
         out->robot_tris = s->nRobotTris;
+        out->streaming_off = s->streamStallsInARow.load(std::memory_order_relaxed) >= 2;
     }
     if (reset) {
         MPLB_CUDA(cudaMemset(b->globalCtr.ptr, 0, sizeof(DevCounters)));
         b->hChecks = b->hBv = b->hTri = b->hExact = b->hLaunches = 0;
+        b->hStreamStalls = b->hAmbiguous = b->hCoalesced = 0;
     }
     return MPLB_OK;
 }

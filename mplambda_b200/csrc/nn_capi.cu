@@ -21,12 +21,19 @@ struct mplb_nn {
     float *dKeys32 = nullptr;      // FP32 copy for the candidate pass
     double keysAbsMax = 0;         // largest |translation coordinate| (SE3) / |coordinate| (L1) inserted
     std::vector<double> hKeys;     // host mirror: reported distances are recomputed with host libm
+    size_t hCount = 0;             // keys mirrored so far (keys inserted from device memory are fetched on demand)
     cudaStream_t stream = nullptr;
-    DevBuf queries, partDist, partIdx, dist, idx, partVal, thr;
+    // the scan scratch below is shared by every query on this structure, whatever stream it runs on: each search waits
+    // for the previous one's event before it touches the scratch and records its own behind its last kernel
+    cudaEvent_t scratchDone = nullptr;
+    float *hKeyStats = nullptr;    // pinned: {largest |coordinate|, non-unit quaternion seen} of a device-side insert
+    DevBuf queries, partDist, partIdx, dist, idx, partVal, thr, keyStats;
 
     ~mplb_nn() {
         if (dKeys) cudaFree(dKeys);
         if (dKeys32) cudaFree(dKeys32);
+        if (hKeyStats) cudaFreeHost(hKeyStats);
+        if (scratchDone) cudaEventDestroy(scratchDone);
         if (stream) cudaStreamDestroy(stream);
     }
     // nigh SE3Space / L1Space distance, operation order of oracle/mplb_oracle.c
@@ -42,6 +49,47 @@ struct mplb_nn {
         return s;
     }
 };
+
+// room for `total` keys; existing keys move with the arrays (device pointers handed out before are stale afterwards)
+static int nnEnsureCapacity(mplb_nn *nn, size_t total) {
+    if (total <= nn->capacity) return MPLB_OK;
+    size_t cap = std::max<size_t>(1024, nn->capacity);
+    while (cap < total) cap *= 2;
+    MPLB_CUDA(cudaDeviceSynchronize());   // (rare: the arrays double) nothing may still be reading or filling the old ones
+    double *p = nullptr;
+    float *p32 = nullptr;
+    cudaError_t e = cudaMalloc((void **)&p, cap * nn->dim * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&p32, cap * nn->dim * 4);
+    if (e == cudaSuccess && nn->count) e = cudaMemcpy(p, nn->dKeys, nn->count * nn->dim * 8, cudaMemcpyDeviceToDevice);
+    if (e == cudaSuccess && nn->count) e = cudaMemcpy(p32, nn->dKeys32, nn->count * nn->dim * 4, cudaMemcpyDeviceToDevice);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        if (p) cudaFree(p);
+        if (p32) cudaFree(p32);
+        return fail(MPLB_ERR_NOMEM, "growing the key arrays to %zu keys failed: %s", cap, cudaGetErrorString(e));
+    }
+    if (nn->dKeys) cudaFree(nn->dKeys);
+    if (nn->dKeys32) cudaFree(nn->dKeys32);
+    nn->dKeys = p;
+    nn->dKeys32 = p32;
+    nn->capacity = cap;
+    return MPLB_OK;
+}
+
+// host copies of the keys that were inserted from device memory (the host-facing queries report host-libm distances)
+static int nnSyncMirror(mplb_nn *nn) {
+    if (nn->hCount == nn->count) return MPLB_OK;
+    nn->hKeys.resize(nn->count * nn->dim);
+    MPLB_CUDA(cudaMemcpy(nn->hKeys.data() + nn->hCount * nn->dim, nn->dKeys + nn->hCount * nn->dim,
+                         (nn->count - nn->hCount) * nn->dim * 8, cudaMemcpyDeviceToHost));
+    nn->hCount = nn->count;
+    return MPLB_OK;
+}
+
+static void nnNoteKeyStats(mplb_nn *nn, double absMax, bool nonUnit) {
+    if (nonUnit || !std::isfinite(absMax)) nn->keysAbsMax = INFINITY;
+    else if (std::isfinite(nn->keysAbsMax)) nn->keysAbsMax = std::max(nn->keysAbsMax, absMax);
+}
 
 static int nnSearch(mplb_nn *nn, const double *queries, bool deviceQueries, size_t nq, int k, int64_t *idx,
                     double *dist, bool deviceOut, cudaStream_t userStream) {
@@ -66,6 +114,8 @@ static int nnSearch(mplb_nn *nn, const double *queries, bool deviceQueries, size
     }
     const int slices = nnSlices(nq, nn->count, nn->numSms);
     int rc;
+    if (!deviceQueries && (rc = nnSyncMirror(nn))) return rc;
+    MPLB_CUDA(cudaStreamWaitEvent(st, nn->scratchDone, 0));
     if (slices > 1 && ((rc = nn->partDist.reserve(nq * slices * k * 8)) || (rc = nn->partIdx.reserve(nq * slices * k * 8))))
         return rc;
     // k == 1: [nq][slices] bounds; k > 1: [nq][k] sample distances + [nq][8] counts + [nq] chosen levels
@@ -87,6 +137,7 @@ static int nnSearch(mplb_nn *nn, const double *queries, bool deviceQueries, size
                              nn->metric, nn->so3w, nn->l2w, dQ, nq, k, slices, (float *)nn->partVal.ptr,
                              (float *)nn->thr.ptr, (double *)nn->partDist.ptr, (long long *)nn->partIdx.ptr, dDist, dIdx,
                              nullptr, st));
+    MPLB_CUDA(cudaEventRecord(nn->scratchDone, st));
     if (deviceQueries) return MPLB_OK;
     MPLB_CUDA(cudaMemcpyAsync(idx, dIdx, nq * k * 8, cudaMemcpyDeviceToHost, st));
     MPLB_CUDA(cudaStreamSynchronize(st));
@@ -125,9 +176,11 @@ int mplb_nn_create(int metric, int dim, double so3_weight, double l2_weight, int
     nn->dim = dim;
     nn->so3w = so3_weight;
     nn->l2w = l2_weight;
-    if (cudaStreamCreateWithFlags(&nn->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&nn->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&nn->scratchDone, cudaEventDisableTiming) != cudaSuccess ||
+        cudaMallocHost((void **)&nn->hKeyStats, 2 * sizeof(float)) != cudaSuccess || nn->keyStats.reserve(2 * sizeof(float))) {
         delete nn;
-        return fail(MPLB_ERR_CUDA, "cudaStreamCreate failed");
+        return fail(MPLB_ERR_CUDA, "could not create the structure's stream / event / pinned scratch");
     }
     *out = nn;
     return MPLB_OK;
@@ -146,23 +199,8 @@ int mplb_nn_insert(mplb_nn *nn, const double *keys, size_t n) {
     if (!keys) return fail(MPLB_ERR_INVALID, "null keys");
     std::lock_guard<std::mutex> g(nn->mu);
     MPLB_CUDA(cudaSetDevice(nn->device));
-    if (nn->count + n > nn->capacity) {
-        size_t cap = std::max<size_t>(1024, nn->capacity);
-        while (cap < nn->count + n) cap *= 2;
-        double *p = nullptr;
-        cudaError_t e = cudaMalloc((void **)&p, cap * nn->dim * 8);
-        if (e != cudaSuccess) return fail(MPLB_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", cap * nn->dim * 8, cudaGetErrorString(e));
-        if (nn->count) MPLB_CUDA(cudaMemcpy(p, nn->dKeys, nn->count * nn->dim * 8, cudaMemcpyDeviceToDevice));
-        if (nn->dKeys) cudaFree(nn->dKeys);
-        nn->dKeys = p;
-        float *p32 = nullptr;
-        e = cudaMalloc((void **)&p32, cap * nn->dim * 4);
-        if (e != cudaSuccess) return fail(MPLB_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", cap * nn->dim * 4, cudaGetErrorString(e));
-        if (nn->count) MPLB_CUDA(cudaMemcpy(p32, nn->dKeys32, nn->count * nn->dim * 4, cudaMemcpyDeviceToDevice));
-        if (nn->dKeys32) cudaFree(nn->dKeys32);
-        nn->dKeys32 = p32;
-        nn->capacity = cap;
-    }
+    int rc;
+    if ((rc = nnEnsureCapacity(nn, nn->count + n)) || (rc = nnSyncMirror(nn))) return rc;
     for (size_t i = 0; i < n; ++i)
         for (int d = (nn->metric == 0 ? 4 : 0); d < nn->dim; ++d) {
             const double v = std::fabs(keys[i * nn->dim + d]);
@@ -182,6 +220,7 @@ int mplb_nn_insert(mplb_nn *nn, const double *keys, size_t n) {
     MPLB_CUDA(cudaStreamSynchronize(nn->stream));
     nn->hKeys.insert(nn->hKeys.end(), keys, keys + n * nn->dim);
     nn->count += n;
+    nn->hCount = nn->count;
     return MPLB_OK;
 }
 
@@ -208,4 +247,86 @@ int mplb_nn_nearest_device(mplb_nn *nn, const double *d_queries, size_t nq, int6
     return nnSearch(nn, d_queries, true, nq, 1, d_idx, d_dist, true, (cudaStream_t)stream);
 }
 
+int mplb_nn_knearest_device(mplb_nn *nn, const double *d_queries, size_t nq, int k, int64_t *d_idx, double *d_dist,
+                            void *stream) {
+    if (!nn) return fail(MPLB_ERR_INVALID, "nn is null");
+    if (nq == 0) return MPLB_OK;
+    if (!d_queries || !d_idx || !d_dist) return fail(MPLB_ERR_INVALID, "null buffer");
+    return nnSearch(nn, d_queries, true, nq, k, d_idx, d_dist, true, (cudaStream_t)stream);
+}
+
+int mplb_nn_reserve(mplb_nn *nn, size_t capacity) {
+    if (!nn) return fail(MPLB_ERR_INVALID, "nn is null");
+    std::lock_guard<std::mutex> g(nn->mu);
+    MPLB_CUDA(cudaSetDevice(nn->device));
+    return nnEnsureCapacity(nn, capacity);
+}
+
+size_t mplb_nn_capacity(const mplb_nn *nn) { return nn ? nn->capacity : 0; }
+
+const double *mplb_nn_keys_device(const mplb_nn *nn) { return nn ? nn->dKeys : nullptr; }
+
+int mplb_nn_insert_device(mplb_nn *nn, const double *d_keys, size_t n, void *stream) {
+    if (!nn) return fail(MPLB_ERR_INVALID, "nn is null");
+    if (n == 0) return MPLB_OK;
+    if (!d_keys) return fail(MPLB_ERR_INVALID, "null keys");
+    std::lock_guard<std::mutex> g(nn->mu);
+    MPLB_CUDA(cudaSetDevice(nn->device));
+    int rc;
+    if ((rc = nnEnsureCapacity(nn, nn->count + n))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    double *dst = nn->dKeys + nn->count * nn->dim;
+    MPLB_CUDA(cudaMemcpyAsync(dst, d_keys, n * nn->dim * 8, cudaMemcpyDeviceToDevice, st));
+    MPLB_CUDA(launchNnToFloat(dst, nn->dKeys32 + nn->count * nn->dim, n * nn->dim, st));
+    MPLB_CUDA(launchNnKeyStats(dst, n, nn->dim, nn->metric, (float *)nn->keyStats.ptr, st));
+    MPLB_CUDA(cudaMemcpyAsync(nn->hKeyStats, nn->keyStats.ptr, 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    MPLB_CUDA(cudaStreamSynchronize(st));
+    if (!(nn->hKeyStats[0] < INFINITY)) return fail(MPLB_ERR_INVALID, "non-finite key in a device-side insert");
+    nnNoteKeyStats(nn, nn->hKeyStats[0], nn->hKeyStats[1] != 0.f);
+    nn->count += n;
+    return MPLB_OK;
+}
+
 }  // extern "C"
+
+// ---- used by the device-resident planner loop (rrt_capi.cu): keys appended in place by a kernel
+namespace mplb {
+int nnLock(mplb_nn *nn, size_t room, double **keys, float **keys32, size_t *count) {
+    nn->mu.lock();
+    int rc = nnEnsureCapacity(nn, nn->count + room);
+    if (rc != MPLB_OK) {
+        nn->mu.unlock();
+        return rc;
+    }
+    *keys = nn->dKeys;
+    *keys32 = nn->dKeys32;
+    *count = nn->count;
+    return MPLB_OK;
+}
+void nnUnlock(mplb_nn *nn, size_t added, double absMaxBound) {
+    if (added) nnNoteKeyStats(nn, absMaxBound, false);
+    nn->count += added;
+    nn->mu.unlock();
+}
+int nnSearchDeviceLocked(mplb_nn *nn, const double *dQueries, size_t nq, int k, long long *dIdx, double *dDist,
+                         cudaStream_t st) {
+    if (nn->count == 0) return fail(MPLB_ERR_INVALID, "nearest-neighbour structure is empty");
+    const int slices = nnSlices(nq, nn->count, nn->numSms);
+    int rc;
+    if (slices > 1 && ((rc = nn->partDist.reserve(nq * slices * k * 8)) || (rc = nn->partIdx.reserve(nq * slices * k * 8))))
+        return rc;
+    if ((rc = nn->partVal.reserve(std::max<size_t>(nq * slices * k * 4, nq * ((size_t)k + 17) * 4))) || (rc = nn->thr.reserve(nq * 4)))
+        return rc;
+    MPLB_CUDA(cudaStreamWaitEvent(st, nn->scratchDone, 0));
+    MPLB_CUDA(launchNnSearch(nn->dKeys, nn->dKeys32, (std::isfinite(nn->keysAbsMax) ? std::nextafterf((float)nn->keysAbsMax, INFINITY) : INFINITY), nn->count, nn->dim,
+                             nn->metric, nn->so3w, nn->l2w, dQueries, nq, k, slices, (float *)nn->partVal.ptr,
+                             (float *)nn->thr.ptr, (double *)nn->partDist.ptr, (long long *)nn->partIdx.ptr, dDist, dIdx,
+                             nullptr, st));
+    MPLB_CUDA(cudaEventRecord(nn->scratchDone, st));
+    return MPLB_OK;
+}
+int nnInfo(const mplb_nn *nn, int *device, int *metric, int *dim, double *so3w, double *l2w) {
+    *device = nn->device; *metric = nn->metric; *dim = nn->dim; *so3w = nn->so3w; *l2w = nn->l2w;
+    return MPLB_OK;
+}
+}  // namespace mplb

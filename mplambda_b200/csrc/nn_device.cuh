@@ -10,6 +10,9 @@ namespace mplb {
 int nnSlices(size_t nq, size_t n, int numSms);
 
 cudaError_t launchNnToFloat(const double *dSrc, float *dDst, size_t n, cudaStream_t stream);
+// dOut[2] = {largest |translation coordinate| (SE3) / |coordinate| (L1) rounded up -- NaN/inf if a key is not finite --,
+// 1.0f if an SE3 key's quaternion is not unit} of n keys in device memory
+cudaError_t launchNnKeyStats(const double *dKeys, size_t n, int dim, int metric, float *dOut, cudaStream_t stream);
 
 // metric 0: SE3 (7-double keys), 1: L1 (dim doubles).  dDist/dIdx: [nq][k].  dKeys32 is the FP32 copy of the
 // keys, keysAbsMax the largest |translation coordinate| (SE3) / |coordinate| (L1) among them; dPartVal

@@ -349,6 +349,35 @@ __global__ void nnToFloatKernel(const double *__restrict__ src, float *__restric
 }
 
 // one thread per query: merge `slices` ascending lists of length k into one (ties -> lower index)
+// {largest |translation coordinate| (SE3) / |coordinate| (L1), 1 if an SE3 key's quaternion is not unit} of keys that
+// arrived in device memory; non-negative floats order like their bit patterns (a NaN or an infinity ends up on top)
+__global__ void nnKeyStatsKernel(const double *__restrict__ keys, unsigned long long n, int dim, int metric,
+                                 unsigned *__restrict__ out) {
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    float m = 0.f;
+    unsigned nonUnit = 0;
+    if (i < n) {
+        const double *q = keys + i * dim;
+        for (int d = (metric == 0 ? 4 : 0); d < dim; ++d) {
+            const float v = __double2float_ru(fabs(q[d]));
+            m = (v > m || v != v) ? v : m;
+        }
+        if (metric == 0) {
+            const double qn = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+            nonUnit = !(fabs(qn - 1.0) < 1e-3);
+        }
+    }
+    unsigned bits = __float_as_uint(m);
+    for (int o = 16; o; o >>= 1) {
+        bits = max(bits, __shfl_xor_sync(0xffffffffu, bits, o));
+        nonUnit |= __shfl_xor_sync(0xffffffffu, nonUnit, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(out, bits);
+        if (nonUnit) atomicExch(out + 1, __float_as_uint(1.f));
+    }
+}
+
 __global__ void nnMergeKernel(const double *__restrict__ inDist, const long long *__restrict__ inIdx,
                               unsigned long long nq, int slices, int k, double *__restrict__ outDist,
                               long long *__restrict__ outIdx) {
@@ -392,6 +421,13 @@ int nnSlices(size_t nq, size_t n, int numSms) {
 cudaError_t launchNnToFloat(const double *dSrc, float *dDst, size_t n, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     nnToFloatKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dSrc, dDst, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launchNnKeyStats(const double *dKeys, size_t n, int dim, int metric, float *dOut, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(dOut, 0, 2 * sizeof(float), stream);
+    if (e != cudaSuccess || n == 0) return e;
+    nnKeyStatsKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dKeys, n, dim, metric, (unsigned *)dOut);
     return cudaGetLastError();
 }
 

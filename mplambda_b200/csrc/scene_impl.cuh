@@ -40,6 +40,11 @@ struct CallCtx {
     // the wire (cudaMemcpyAsync on pageable memory stages through one thread at ~10 GB/s)
     unsigned char *hBounce[2] = {nullptr, nullptr};
     cudaEvent_t bounceDone[2] = {nullptr, nullptr};
+    int bounceNext = 0;                 // the bounce buffer the next piece goes through
+    // streamed batches (capi.cu): one arrival flag per chunk, written behind the chunk's copy with a stream memory
+    // operation; `epoch` names the call, so the flags never need clearing
+    DevBuf flags;
+    unsigned epoch = 0;
     // The reference's scalar calls (one state, one edge) replay a captured CUDA graph: memset + copy in + kernels +
     // copy out are one launch instead of four to eight.  Captured on a context's second scalar call; the keys are the
     // device buffers the graph was captured with (a reallocation invalidates it).
@@ -59,6 +64,8 @@ struct CallCtx {
 // Host -> device copy of a caller's buffer on `stream`: pinned memory goes straight to the copy engine, pageable memory
 // through two pinned bounce buffers filled by all cores (capi.cu)
 int hostToDevice(CallCtx *c, void *dst, const void *src, size_t bytes, cudaStream_t stream);
+// true when `p` is page-locked host memory the copy engine can read directly
+bool isPinned(const void *p);
 
 struct SceneBase {
     int device = 0;
@@ -68,6 +75,7 @@ struct SceneBase {
     std::vector<CallCtx *> freeCtx;
     DevBuf globalCtr, globalWork, globalDead, globalStacks, globalEdgeConst;  // used by the *_device entry points
     std::atomic<uint64_t> hChecks{0}, hBv{0}, hTri{0}, hExact{0}, hLaunches{0};
+    std::atomic<uint64_t> hStreamStalls{0}, hAmbiguous{0}, hCoalesced{0};
     size_t envNodeCount = 0, robotNodeCount = 0;
 
     CallCtx *acquire();

@@ -27,9 +27,15 @@ struct SceneDev {
     unsigned rootEntry;         // LIFO entry that expands the root pair (se3_kernels.cu)
 };
 
+constexpr unsigned kAmbiguousListed = 14;   // ambiguous edges listed by index (more are only counted)
+
 struct DevCounters {
     unsigned long long bvTests, triTests, exactTests, states;
     unsigned overflow, pad;   // pad: 1 = a streamed batch's input never arrived (see StateSource)
+    // device-planned edges (edgeGatherPlanKernel): distance * invStep within a few ulp of an integer, where CUDA's and
+    // glibc's acos could round `steps` differently -- the caller re-plans those with host libm; badEdges: non-finite
+    unsigned ambiguous, badEdges;
+    unsigned ambiguousEdge[kAmbiguousListed];
 #ifdef MPLB_WARP_TIMES   // diagnostic build: when did the warps start / run out of new work / finish (globaltimer, ns)
     unsigned long long negStart, negFirstDry, negFirstDone, lastDone;   // neg*: ~t, so that atomicMax finds the minimum
     unsigned long long warpDone[4096];
@@ -37,12 +43,18 @@ struct DevCounters {
 #endif
 };
 
-// streamed: dStates was pre-filled with the all-ones pattern and is being overwritten by a host->device copy
-// on another stream; the kernel picks each state up when it has landed (se3_kernels.cu: StateSource)
+// A batch that is still being copied in while the kernel runs: the host copies it in chunks of `chunkStates` states
+// and writes flags[c] = epoch behind chunk c on the copy's stream (a stream memory operation); the kernel hands
+// states out in index order and picks each claim up once its chunk's flag is there (se3_kernels.cu: StateSource).
+// flags == nullptr: the batch is resident.
+struct StreamedInput {
+    const unsigned *flags = nullptr;
+    unsigned epoch = 0, chunkStates = 0;
+};
 // workZeroed: the caller has already zeroed the first work counter
 cudaError_t launchCheckStates(const SceneDev &sc, const double *dStates, size_t n, uint8_t *dValid,
                               DevCounters *dCtr, unsigned *dWork, int numSms, cudaStream_t stream,
-                              bool streamed = false, bool workZeroed = false);
+                              StreamedInput streamed = StreamedInput(), bool workZeroed = false);
 
 // scratch for the per-warp interval LIFOs of checkEdgesKernel
 size_t edgeStackBytes(int numSms);
@@ -53,6 +65,27 @@ cudaError_t launchCheckEdges(const SceneDev &sc, const double *dFrom, const doub
                              bool zeroed = false);
 // dEdgeConst: edgeConstBytes(n) of scratch for the per-edge interpolation constants
 size_t edgeConstBytes(size_t n);
+
+// Edges named by index into state pools (device memory): edge e runs from row (fromIdx ? fromIdx[e] : e / fromDiv)
+// of fromPool to row (toIdx ? toIdx[e] : e / toDiv) of toPool.
+struct EdgeGather {
+    const double *fromPool, *toPool;       // [rows][7]
+    const long long *fromIdx, *toIdx;      // [n] or null
+    unsigned long long fromRows, toRows;   // pool sizes: an index outside [0, rows) makes the edge invalid
+    unsigned fromDiv, toDiv;               // >= 1
+};
+// scratch the indexed call needs besides the interval stacks: dense end states, steps, per-edge constants
+size_t edgeGatherBytes(size_t n);
+// dScratch: edgeGatherBytes(n).  Verdicts as launchCheckEdges.  Steps are planned on the device (se3_kernels.cu:
+// edgeGatherPlanKernel); ambiguous ones are reported in dCtr.
+cudaError_t launchCheckEdgesIndexed(const SceneDev &sc, const EdgeGather &g, size_t n, double so3w, double l2w,
+                                    double invStep, unsigned *dDead, uint8_t *dValid, DevCounters *dCtr,
+                                    unsigned long long *dWork, void *dStacks, size_t stackBytes, void *dScratch,
+                                    int numSms, cudaStream_t stream, bool zeroed = false);
+// where the indexed call keeps edge e's planned step count / dense end states inside dScratch (for host re-planning)
+unsigned *edgeGatherSteps(void *dScratch, size_t n);
+double *edgeGatherFrom(void *dScratch, size_t n);
+double *edgeGatherTo(void *dScratch, size_t n);
 // zeroed: dWork (16 counters) and dDead are already zero.  dValid == nullptr: leave the verdicts as dDead flags.
 
 }  // namespace mplb

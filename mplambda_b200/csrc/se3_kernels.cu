@@ -191,11 +191,8 @@ __device__ __forceinline__ void interpolateWith(const double *from, const double
     for (int i = 4; i < 7; ++i) out[i] = dadd(from[i], dmul(dsub(to[i], from[i]), t));
 }
 
-__global__ void edgeConstKernel(const double *__restrict__ from, const double *__restrict__ to, unsigned long long n,
-                                float robotRadius, double *__restrict__ out) {
-    const unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    const double *a = from + 7 * e, *b = to + 7 * e;
+// per-edge constants of edge (a -> b) into o[kEdgeConst]
+__device__ __forceinline__ void edgeConstOf(const double *a, const double *b, float robotRadius, double *o) {
     const double d = dadd(dadd(dadd(dmul(a[0], b[0]), dmul(a[1], b[1])), dmul(a[2], b[2])), dmul(a[3], b[3]));
     const double absD = fabs(d);
     double theta = -1.0, sinTheta = 0.0;
@@ -218,12 +215,68 @@ __global__ void edgeConstKernel(const double *__restrict__ from, const double *_
     const double scale = fmax(1.0, fmax(na, nb));
     const double thetaM = acos(fmin(1.0, absD / sqrt(na * nb)));
     const double R = (double)robotRadius * scale;
-    double *o = out + kEdgeConst * e;
     o[0] = d;
     o[1] = theta;
     o[2] = sinTheta;
     o[3] = sqrt(dt2) + 2.0 * thetaM * R;
     o[4] = fabs(scale - 1.0) * 4.0 * R * 1.000001 + 1e-6 * R;
+}
+
+__global__ void edgeConstKernel(const double *__restrict__ from, const double *__restrict__ to, unsigned long long n,
+                                float robotRadius, double *__restrict__ out) {
+    const unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    edgeConstOf(from + 7 * e, to + 7 * e, robotRadius, out + kEdgeConst * e);
+}
+
+// Edges named by index (the planner's "node i of the tree -> sample j" without the states crossing PCIe): gathers both
+// end states into dense arrays the edge kernel reads, and plans the edge on the device --
+//   steps = ceil(distance(from, to) * invStepSize)        (se3_rigid_body_scenario.hpp:139, nigh SE3Space distance)
+// in the host path's operation order.  Every operation but acos is correctly rounded on both sides; CUDA's acos may
+// differ from glibc's in the last bits, which changes `steps` only when distance * invStep lies within a few ulp of an
+// integer: such edges are counted and listed (DevCounters::ambiguous) so that the caller can plan them with host libm --
+// they are never silently different.  An index < 0 or past its pool, or a non-finite distance, kills the edge.
+__global__ void edgeGatherPlanKernel(EdgeGather g, unsigned long long n, double so3w, double l2w, double invStep,
+                                     float robotRadius, double *__restrict__ from, double *__restrict__ to,
+                                     unsigned *__restrict__ steps, unsigned *__restrict__ dead,
+                                     double *__restrict__ edgeConst, DevCounters *ctr) {
+    const unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const long long ia = g.fromIdx ? g.fromIdx[e] : (long long)(e / g.fromDiv);
+    const long long ib = g.toIdx ? g.toIdx[e] : (long long)(e / g.toDiv);
+    double a[7], b[7];
+    const bool okIdx = ia >= 0 && ib >= 0 && (unsigned long long)ia < g.fromRows && (unsigned long long)ib < g.toRows;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        a[k] = okIdx ? g.fromPool[7 * ia + k] : 0.0;
+        b[k] = okIdx ? g.toPool[7 * ib + k] : 0.0;
+        from[7 * e + k] = a[k];
+        to[7 * e + k] = b[k];
+    }
+    if (!okIdx) {
+        steps[e] = 0;
+        dead[e] = 1u;
+#pragma unroll
+        for (int k = 0; k < kEdgeConst; ++k) edgeConst[kEdgeConst * e + k] = 0.0;
+        return;
+    }
+    edgeConstOf(a, b, robotRadius, edgeConst + kEdgeConst * e);
+    const double d = fabs(edgeConst[kEdgeConst * e]);
+    const double so3 = d < 1.0 ? acos(d) : 0.0;
+    const double dx = dsub(a[4], b[4]), dy = dsub(a[5], b[5]), dz = dsub(a[6], b[6]);
+    const double l2 = sqrt(dadd(dadd(dmul(dx, dx), dmul(dy, dy)), dmul(dz, dz)));
+    const double x = dmul(dadd(dmul(so3w, so3), dmul(l2w, l2)), invStep);
+    if (!(x < 2147483648.0)) {   // non-finite state: the host path rejects the batch, here the edge is invalid
+        steps[e] = 0;
+        dead[e] = 1u;
+        atomicAdd(&ctr->badEdges, 1u);
+        return;
+    }
+    steps[e] = (unsigned)ceil(x);
+    if (d < 1.0 && fabs(x - rint(x)) <= x * 2e-15 + 1e-11) {
+        const unsigned at = atomicAdd(&ctr->ambiguous, 1u);
+        if (at < kAmbiguousListed) ctr->ambiguousEdge[at] = (unsigned)e;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -354,11 +407,16 @@ struct StateSourceT {
     unsigned long long n;
     uint8_t *valid;
     unsigned long long *counter;
-    // Host batches stream in while the kernel runs (`streamed`): the input buffer is pre-filled with an
-    // all-ones pattern (a NaN no sampler produces) and ONE host->device copy overwrites it in the
-    // background; a lane picks its state up the moment none of its 7 doubles shows the pattern any more
-    // (aligned 8-byte words are never torn by the copy engine).  The wait is bounded: a copy that never
-    // arrives -- or a state that really holds the reserved pattern -- is reported, not spun on.
+    // Host batches stream in while the kernel runs (`streamed`): the host copies the batch in chunks and, behind each
+    // chunk on the same stream, writes that chunk's flag with a stream memory operation (cuStreamWriteValue32 --
+    // ordered after the copy it follows, visible to running kernels).  States are handed out in index order and a
+    // warp picks its claim up once the flag of the chunk holding the claim's last state shows this call's epoch
+    // (acquire load at system scope; flags are written in chunk order).  The wait is bounded: a copy that never
+    // arrives is reported, not spun on.
+    const unsigned *chunkFlags = nullptr;
+    unsigned epoch = 0;
+    unsigned chunkStates = 1;
+    unsigned long long landed = 0;   // states [0, landed) are known to be there
     static constexpr bool streamed = kStreamed;   // compile time: the resident kernel carries none of the streaming state
     unsigned stalled = 0;
     unsigned long long base = 0;
@@ -416,13 +474,22 @@ struct StateSourceT {
             pendCount = want;
             waited = false;
         }
-        // one lane looks at the last word of the claim (the copy engine fills the buffer front to back), at
-        // most once per back-off period so that thousands of waiting warps do not crowd the L2 the copy
-        // writes into
-        if (waited && !mayBlock && clock64() - polledAt < (long long)backoff) return 0;
-        int here = 0;
-        if (lane == 0) here = __double_as_longlong(__ldcv(states + 7 * (pendBase + pendCount) - 1)) != -1ll;
-        here = __shfl_sync(kFull, here, 0);
+        // one lane looks at the flag of the claim's last chunk, at most once per back-off period so that thousands
+        // of waiting warps do not crowd the L2 line the flag lives in
+        const unsigned long long last = pendBase + pendCount - 1;
+        int here = last < landed;
+        if (!here) {
+            if (waited && !mayBlock && clock64() - polledAt < (long long)backoff) return 0;
+            const unsigned chunk = (unsigned)(last / chunkStates);
+            if (lane == 0) {
+                unsigned f;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(chunkFlags + chunk) : "memory");
+                here = f == epoch;
+            }
+            here = __shfl_sync(kFull, here, 0);
+            __syncwarp();   // orders the other lanes' loads of the claim behind lane 0's acquire
+            if (here) landed = min(n, (unsigned long long)(chunk + 1) * chunkStates);
+        }
         if (!here) {
             waited = true;
             polledAt = clock64();
@@ -451,25 +518,8 @@ struct StateSourceT {
         t[1] = (unsigned)(i >> 32);
         t[2] = t[3] = 0;
         extraSlack = 0.f;
-        if (!streamed) {
-            stateOf(t[0], t[1], s);
-            return true;
-        }
-        const double *src = states + 7 * i;
-        for (unsigned spins = 0;; ++spins) {
-            bool here = true;
-#pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                s[k] = __ldcv(src + k);
-                here &= __double_as_longlong(s[k]) != -1ll;
-            }
-            if (here) return true;
-            if (spins >= (1u << 18)) {   // ~0.5 s
-                const_cast<StateSourceT *>(this)->stalled = 1;
-                return false;
-            }
-            __nanosleep(2000);
-        }
+        stateOf(t[0], t[1], s);   // (streamed: the claim's chunk flag has been seen by acquire())
+        return true;
     }
     __device__ void stateOf(unsigned t0, unsigned t1, double s[7]) const {
         const double *src = states + 7 * (((unsigned long long)t1 << 32) | t0);
@@ -560,7 +610,11 @@ struct EdgeSource {
                     globalDone = poolDry = true;
                 } else {
                     const int got = (int)min((unsigned long long)take, nDesc - f);
-                    if ((int)lane < got) sm.work[count + lane] = descIn[f + lane];
+                    if ((int)lane < got) {
+                        uint4 w = descIn[f + lane];
+                        if (w.x >= nEdges) w = make_uint4(0, 1, 0, 0);   // never read out of range (lo > hi: no samples)
+                        sm.work[count + lane] = w;
+                    }
                     count += got;
                     first = f + got;
                 }
@@ -708,14 +762,25 @@ struct EdgeSource {
         const unsigned total = __shfl_sync(kFull, incl, 31);
         if (total == 0) return;
         if (spillOut && (poolDry || globalDone) && stackCount + total > kSpillKeep) {
-            unsigned long long pos = 0;
-            if (lane == 0) pos = atomicAdd(spillCount, (unsigned long long)total);
+            // reserve [pos, pos + total) only if it fits: the count never runs past the capacity, so what the next
+            // pass reads (min(count, cap) descriptors) is exactly what was written -- no reservation is ever undone
+            unsigned long long pos = ~0ull;
+            if (lane == 0) {
+                unsigned long long seen = *(volatile unsigned long long *)spillCount;
+                while (seen + total <= spillCap) {
+                    const unsigned long long was = atomicCAS(spillCount, seen, seen + total);
+                    if (was == seen) {
+                        pos = seen;
+                        break;
+                    }
+                    seen = was;
+                }
+            }
             pos = __shfl_sync(kFull, pos, 0);
-            if (pos + total <= spillCap) {   // (a reservation past the end is undone; nobody succeeds meanwhile)
+            if (pos != ~0ull) {
                 for (unsigned k = 0; k < cnt; ++k) spillOut[pos + incl - cnt + k] = kids[k];
                 return;
             }
-            if (lane == 0) atomicAdd(spillCount, ~(unsigned long long)total + 1ull);
         }
         if (stackCount + total > stackCap) {
             error = 1;  // reported by the host call; never silent
@@ -1154,10 +1219,11 @@ __device__ __forceinline__ void flushCounters(const WarpCounters &c, DevCounters
 template <typename E, bool kLatency, bool kStreamed>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MPLB_MIN_CTAS)
 checkStatesKernel(SceneDev sc, const double *states, unsigned long long n, uint8_t *__restrict__ valid,
-                  DevCounters *ctr, unsigned long long *workCounter, unsigned guidedShare) {
+                  DevCounters *ctr, unsigned long long *workCounter, unsigned guidedShare, StreamedInput in) {
     WarpSmem<E> sm = warpSmem<E>(sc.stackLevels);
     StateSourceT<kStreamed> src;
     src.states = states; src.n = n; src.valid = valid; src.counter = workCounter;
+    src.chunkFlags = in.flags; src.epoch = in.epoch; src.chunkStates = in.chunkStates ? in.chunkStates : 1u;
     src.crew = (unsigned long long)gridDim.x * kWarpsPerCta * guidedShare;
     WarpCounters cnt;
 #ifdef MPLB_WARP_TIMES
@@ -1260,7 +1326,8 @@ cudaError_t gridFor(K kernel, size_t smem, int numSms, int *grid) {
 
 template <typename E>
 cudaError_t launchStatesT(const SceneDev &sc, const double *dStates, size_t n, uint8_t *dValid, DevCounters *dCtr,
-                          unsigned long long *dWork, bool streamed, int numSms, cudaStream_t stream) {
+                          unsigned long long *dWork, const StreamedInput &in, int numSms, cudaStream_t stream) {
+    const bool streamed = in.flags != nullptr;
     // batches that leave most of the grid idle are latency bound
     auto k = streamed ? checkStatesKernel<E, false, true>   // (streamed batches are >= 65,536 states: see capi.cu)
                       : n < kLatencyBelow ? checkStatesKernel<E, true, false> : checkStatesKernel<E, false, false>;
@@ -1271,7 +1338,7 @@ cudaError_t launchStatesT(const SceneDev &sc, const double *dStates, size_t n, u
     // small batches are latency bound: one state per warp, spread over as many SMs as there are
     grid = (int)std::min<unsigned long long>(grid, (n + kWarpsPerCta - 1) / kWarpsPerCta);
     constexpr unsigned guidedShare = 2;   // a warp takes at most 1/(2 x warps) of what is left (1, 4, 8 measured no better)
-    k<<<std::max(grid, 1), kWarpsPerCta * 32, smem, stream>>>(sc, dStates, n, dValid, dCtr, dWork, guidedShare);
+    k<<<std::max(grid, 1), kWarpsPerCta * 32, smem, stream>>>(sc, dStates, n, dValid, dCtr, dWork, guidedShare, in);
     return cudaGetLastError();
 }
 
@@ -1314,7 +1381,7 @@ cudaError_t launchEdgesT(const SceneDev &sc, const double *dFrom, const double *
 }  // namespace
 
 cudaError_t launchCheckStates(const SceneDev &sc, const double *dStates, size_t n, uint8_t *dValid,
-                              DevCounters *dCtr, unsigned *dWork, int numSms, cudaStream_t stream, bool streamed,
+                              DevCounters *dCtr, unsigned *dWork, int numSms, cudaStream_t stream, StreamedInput streamed,
                               bool workZeroed) {
     if (n == 0) return cudaSuccess;
     cudaError_t err = workZeroed ? cudaSuccess : cudaMemsetAsync(dWork, 0, sizeof(unsigned long long), stream);
@@ -1346,6 +1413,36 @@ cudaError_t launchCheckEdges(const SceneDev &sc, const double *dFrom, const doub
                   : launchEdgesT<unsigned>(sc, dFrom, dTo, dEdgeConst, dSteps, n, dDead, dCtr, dWork, (uint4 *)dStacks, stackBytes, numSms, stream);
     if (err != cudaSuccess) return err;
     if (dValid) deadToValidKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dDead, n, dValid);   // null: the caller reads dDead
+    return cudaGetLastError();
+}
+
+// dScratch layout of the indexed call: from [n][7] | to [n][7] | edgeConst [n][kEdgeConst] | steps [n]
+size_t edgeGatherBytes(size_t n) { return n * (14 + kEdgeConst) * sizeof(double) + n * sizeof(unsigned) + 64; }
+double *edgeGatherFrom(void *dScratch, size_t) { return (double *)dScratch; }
+double *edgeGatherTo(void *dScratch, size_t n) { return (double *)dScratch + 7 * n; }
+static double *edgeGatherConst(void *dScratch, size_t n) { return (double *)dScratch + 14 * n; }
+unsigned *edgeGatherSteps(void *dScratch, size_t n) { return (unsigned *)((double *)dScratch + (14 + kEdgeConst) * n); }
+
+cudaError_t launchCheckEdgesIndexed(const SceneDev &sc, const EdgeGather &g, size_t n, double so3w, double l2w,
+                                    double invStep, unsigned *dDead, uint8_t *dValid, DevCounters *dCtr,
+                                    unsigned long long *dWork, void *dStacks, size_t stackBytes, void *dScratch,
+                                    int numSms, cudaStream_t stream, bool zeroed) {
+    if (n == 0) return cudaSuccess;
+    cudaError_t err = cudaSuccess;
+    if (!zeroed) {
+        err = cudaMemsetAsync(dWork, 0, 16 * sizeof(unsigned long long), stream);
+        if (err != cudaSuccess) return err;
+        err = cudaMemsetAsync(dDead, 0, sizeof(unsigned) * n, stream);
+        if (err != cudaSuccess) return err;
+    }
+    double *dFrom = edgeGatherFrom(dScratch, n), *dTo = edgeGatherTo(dScratch, n), *dConst = edgeGatherConst(dScratch, n);
+    unsigned *dSteps = edgeGatherSteps(dScratch, n);
+    edgeGatherPlanKernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(g, n, so3w, l2w, invStep, sc.robotRadius, dFrom, dTo,
+                                                                       dSteps, dDead, dConst, dCtr);
+    err = sc.wide ? launchEdgesT<unsigned long long>(sc, dFrom, dTo, dConst, dSteps, n, dDead, dCtr, dWork, (uint4 *)dStacks, stackBytes, numSms, stream)
+                  : launchEdgesT<unsigned>(sc, dFrom, dTo, dConst, dSteps, n, dDead, dCtr, dWork, (uint4 *)dStacks, stackBytes, numSms, stream);
+    if (err != cudaSuccess) return err;
+    if (dValid) deadToValidKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dDead, n, dValid);
     return cudaGetLastError();
 }
 

@@ -135,6 +135,87 @@ def test_concurrent_callers(scenes, golden):
     assert not errs
 
 
+def test_concurrent_streamed_batches(scenes, oracle):
+    """Four host threads, each with a 2^18-state call (large enough to stream in under the running kernel), on one
+    scene and on two scenes at once: verdicts against the oracle, no stall, streaming still on, and the concurrent
+    calls take no longer than 1.5 x the same calls one after another."""
+    import threading
+    import time
+    n = 1 << 18
+    names = ["twistycool", "cubicles"]
+    sc = {k: make(scenes, k) for k in names}
+    P = {k: [se3_poses(n, SE3_SCENES[k]["min"], SE3_SCENES[k]["max"], SEED + 40 + t) for t in range(4)] for k in names}
+    want = {k: [oracle.SE3Oracle(*scenes[k]).check_states(p, oracle.BVH) for p in P[k]] for k in names}
+    for k in names:
+        sc[k].check_states(P[k][0])   # first-use costs (buffers) outside the timing
+
+    def run(jobs, threaded):
+        got = [None] * len(jobs)
+
+        def work(i):
+            k, t = jobs[i]
+            got[i] = sc[k].check_states(P[k][t])
+        t0 = time.perf_counter()
+        if threaded:
+            th = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+            [t.start() for t in th]
+            [t.join() for t in th]
+        else:
+            for i in range(len(jobs)):
+                work(i)
+        dt = time.perf_counter() - t0
+        for i, (k, t) in enumerate(jobs):
+            bad = np.nonzero(got[i] != want[k][t])[0]
+            assert len(bad) == 0, "%s batch %d: %d verdicts differ (threaded=%s)" % (k, t, len(bad), threaded)
+        return dt
+
+    one = [("twistycool", t) for t in range(4)]
+    two = [(names[t % 2], t) for t in range(4)]
+    for jobs in (one, two):
+        run(jobs, True)   # warm: per-thread call contexts
+        serial = min(run(jobs, False) for _ in range(3))
+        conc = min(run(jobs, True) for _ in range(3))
+        assert conc <= 1.5 * serial + 2e-3, "concurrent %.2f ms vs serial %.2f ms" % (conc * 1e3, serial * 1e3)
+    for k in names:
+        st = sc[k].stats()
+        assert st["stream_stalls"] == 0 and st["streaming_off"] == 0, st
+
+
+def test_streamed_batch_without_stream_memops(scenes, golden):
+    """Without stream memory operations (MPLB_NO_STREAM_MEMOPS: read once per process, hence the child process) large
+    batches go copy-then-kernel in pieces: same verdicts."""
+    import subprocess
+    import sys
+    code = ("import numpy as np, sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import mplambda_b200 as M\n"
+            "from mplambda_b200.workload import SE3_SCENES, SEED, se3_poses\n"
+            "d = np.load(%r); sc = SE3_SCENES['twistycool']\n"
+            "s = M.SE3RigidBodyScenario(d['env'], d['robot'], sc['goal'], sc['min'], sc['max'], 0.1)\n"
+            "want = np.load(%r)['twistycool_valid']\n"
+            "P = se3_poses(len(want), sc['min'], sc['max'], SEED)\n"
+            "big = np.concatenate([P] * 40)[:150000]; wbig = np.concatenate([want] * 40)[:150000]\n"
+            "assert (s.check_states(big) == wbig).all(); st = s.stats()\n"
+            "assert st['launches'] >= 4 and st['stream_stalls'] == 0, st\nprint('ok')\n"
+            % (os.path.dirname(GOLDEN) + "/..", os.path.dirname(GOLDEN), os.path.join(GOLDEN, "scenes", "twistycool.npz"),
+               os.path.join(GOLDEN, "se3_verdicts.npz")))
+    env = dict(os.environ, MPLB_NO_STREAM_MEMOPS="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_streamed_and_pipelined_sizes(scenes, golden):
+    """Batch sizes either side of the streaming threshold, pinned-or-not inputs: same verdicts."""
+    s = make(scenes, "twistycool")
+    want = golden["twistycool_valid"]
+    P = se3_poses(len(want), SE3_SCENES["twistycool"]["min"], SE3_SCENES["twistycool"]["max"], SEED)
+    big = np.concatenate([P] * (70000 // len(P) + 1))[:70000]      # > 65 536: streamed
+    wbig = np.concatenate([want] * (70000 // len(P) + 1))[:70000]
+    assert (s.check_states(big) == wbig).all()
+    assert (s.check_states(big[:60000]) == wbig[:60000]).all()     # < 65 536: pipelined copy-then-kernel
+    pageable = np.array(big, copy=True)                             # ordinary memory: through the bounce buffers
+    assert (s.check_states(pageable) == wbig).all()
+
+
 def test_device_resident_batch(scenes, golden):
     import torch
     s = make(scenes, "twistycool")
