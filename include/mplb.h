@@ -151,6 +151,74 @@ int mplb_nn_knearest(mplb_nn *nn, const double *queries, size_t nq, int k, int64
 int mplb_nn_nearest_device(mplb_nn *nn, const double *d_queries, size_t nq, int64_t *d_idx,
                            double *d_dist, void *stream);
 
+/* k-NN on device-resident queries: d_idx / d_dist are [nq][k] device arrays (layout and order as mplb_nn_knearest;
+ * distances device-evaluated).  The *_device searches of one structure share its scan scratch; they are ordered among
+ * themselves by an event the structure keeps, whatever streams they are enqueued on. */
+int mplb_nn_knearest_device(mplb_nn *nn, const double *d_queries, size_t nq, int k, int64_t *d_idx,
+                            double *d_dist, void *stream);
+/* Keys that already sit in device memory (new tree nodes picked on the device); returns when they are in. */
+int mplb_nn_insert_device(mplb_nn *nn, const double *d_keys, size_t n, void *stream);
+/* The structure's key array in device memory, [size][dim] float64 in insertion order: the pool index-named edges
+ * (below) read tree nodes from.  The pointer changes when the array grows past mplb_nn_capacity: reserve first. */
+int mplb_nn_reserve(mplb_nn *nn, size_t capacity);
+size_t mplb_nn_capacity(const mplb_nn *nn);
+const double *mplb_nn_keys_device(const mplb_nn *nn);
+
+/* ---------------------------------------------------------------------------------------- */
+/* Device-resident planner iteration: sample -> nearest -> isValid(from, to) -> insert with only indices and counts
+ * crossing PCIe (prrt.hpp:280-299; pcforest.hpp:507-567 issues the same motions for every neighbour).
+ *
+ * Scenario::randomSample (se3...:107-113, randomize.hpp:12-38; Fetch: fetch_robot.hpp:163-175) for n states written
+ * to device memory: state i is a pure function of (seed, first + i) -- Philox4x32-10, the generator of
+ * mplambda_b200/workload.py.  min/max: 3 translation bounds (SE3) or 8 joint bounds (Fetch). */
+int mplb_sample_states_device(mplb_scene *scene, const double *min, const double *max, uint64_t seed,
+                              uint64_t first, size_t n, double *d_states, void *stream);
+
+/* isValid(from, to) for n edges named by index: edge e runs from row (from_idx ? from_idx[e] : e / from_div) of
+ * d_from_pool to row (to_idx ? to_idx[e] : e / to_div) of d_to_pool (device arrays [rows][7], e.g.
+ * mplb_nn_keys_device: the tree's nodes).  An index outside its pool makes the edge invalid.  steps =
+ * ceil(distance/resolution) is planned on the device; where the device's acos could round it differently from the
+ * host's, the edge is planned and checked again through the host path, so verdicts equal mplb_check_edges' on the
+ * same states (mplb_stats_t.ambiguous_steps counts those edges).  The index arrays are host memory (copied in: 8 B
+ * per end point instead of 56) or, with idx_on_device != 0, device memory; `valid` may be host or device memory.
+ * Synchronous.  SE(3) scenes. */
+int mplb_check_edges_indexed(mplb_scene *scene, const double *d_from_pool, size_t from_rows,
+                             const int64_t *from_idx, uint32_t from_div, const double *d_to_pool,
+                             size_t to_rows, const int64_t *to_idx, uint32_t to_div, size_t n,
+                             int idx_on_device, uint8_t *valid, uint64_t *states_checked);
+/* The same enqueued on `stream` without synchronisation, every pointer device memory.  Ambiguous step counts are only
+ * counted (mplb_stats_t.ambiguous_steps after mplb_scene_stats), not re-planned; shares the per-scene scratch of the
+ * other *_device calls (one stream per scene). */
+int mplb_check_edges_indexed_device(mplb_scene *scene, const double *d_from_pool, size_t from_rows,
+                                    const int64_t *d_from_idx, uint32_t from_div,
+                                    const double *d_to_pool, size_t to_rows, const int64_t *d_to_idx,
+                                    uint32_t to_div, size_t n, uint8_t *d_valid, void *stream);
+
+/* Planner<Scenario, PRRT>'s loop (prrt.hpp:280-299) run on the device, `batch` samples per iteration: the tree's
+ * nodes are the keys of `nn` (which must be empty, on the scene's device, SE3 metric with the scene's weights), node
+ * i's parent is parent[i].  Per iteration the host reads a 24-byte status.  Samples of one batch do not see each
+ * other (like the reference's concurrent threads); accepted samples become nodes in sample order, so the tree is a
+ * pure function of (scene, start, goal, bounds, seed, batch, goal_bias).  Sample s of iteration t is draw t * batch + s
+ * of mplb_sample_states_device's stream, replaced by `goal` when its seventh uniform is < goal_bias
+ * (prrt.hpp:301-315).  Fails with MPLB_ERR_INVALID when `start` is not valid (prrt.hpp:109-110). */
+typedef struct mplb_rrt mplb_rrt;
+typedef struct {
+    uint64_t iterations, samples, edges_checked, nodes;
+    int64_t solution; /* first goal node (-1: none yet) */
+    double seconds;   /* wall time of the last mplb_rrt_run */
+} mplb_rrt_status_t;
+int mplb_rrt_create(mplb_scene *scene, mplb_nn *nn, const double *start, const double *goal,
+                    double goal_radius, const double *min, const double *max, uint64_t seed,
+                    size_t batch, double goal_bias, mplb_rrt **out);
+void mplb_rrt_destroy(mplb_rrt *rrt);
+/* runs until a goal node exists, max_iterations more iterations have run or time_limit_s (> 0) has passed */
+int mplb_rrt_run(mplb_rrt *rrt, uint64_t max_iterations, double time_limit_s, mplb_rrt_status_t *status);
+/* the tree: nodes [count][7] and parent [count] (root: -1), at most `capacity` of them; *count = nodes there are */
+int mplb_rrt_tree(mplb_rrt *rrt, double *nodes, int64_t *parent, size_t capacity, size_t *count);
+/* the sample batch of iteration `iteration` as the loop draws it ([batch][7], [batch] goal-sample flags): lets a CPU
+ * planner replay the same inputs (tests) */
+int mplb_rrt_samples(mplb_rrt *rrt, uint64_t iteration, double *states, uint8_t *is_goal_sample);
+
 #ifdef __cplusplus
 }
 #endif

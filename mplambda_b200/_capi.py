@@ -20,6 +20,14 @@ class Stats(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+class RrtStatus(C.Structure):
+    _fields_ = [("iterations", C.c_uint64), ("samples", C.c_uint64), ("edges_checked", C.c_uint64), ("nodes", C.c_uint64),
+                ("solution", C.c_int64), ("seconds", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 class MplbError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("libmplb error %d: %s" % (code, msg))
@@ -62,6 +70,22 @@ _SIGNATURES = {
     "mplb_nn_nearest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "mplb_nn_knearest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
     "mplb_nn_nearest_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mplb_nn_knearest_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mplb_nn_insert_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "mplb_nn_reserve": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "mplb_nn_capacity": (C.c_size_t, [C.c_void_p]),
+    "mplb_nn_keys_device": (C.c_void_p, [C.c_void_p]),
+    "mplb_sample_states_device": (C.c_int, [C.c_void_p, dp, dp, C.c_uint64, C.c_uint64, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "mplb_check_edges_indexed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t,
+                                           C.c_void_p, C.c_uint32, C.c_size_t, C.c_int, C.c_void_p, u64p]),
+    "mplb_check_edges_indexed_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p,
+                                                  C.c_size_t, C.c_void_p, C.c_uint32, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "mplb_rrt_create": (C.c_int, [C.c_void_p, C.c_void_p, dp, dp, C.c_double, dp, dp, C.c_uint64, C.c_size_t, C.c_double,
+                                  C.POINTER(C.c_void_p)]),
+    "mplb_rrt_destroy": (None, [C.c_void_p]),
+    "mplb_rrt_run": (C.c_int, [C.c_void_p, C.c_uint64, C.c_double, C.POINTER(RrtStatus)]),
+    "mplb_rrt_tree": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "mplb_rrt_samples": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
 }
 
 

@@ -84,6 +84,7 @@ CallCtx::~CallCtx() {
     if (hWater) cudaFreeHost(hWater);
     for (auto e : events) cudaEventDestroy(e);
     if (copyStream) cudaStreamDestroy(copyStream);
+    if (copyStream2) cudaStreamDestroy(copyStream2);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -99,6 +100,7 @@ CallCtx *SceneBase::acquire() {
     auto *c = new CallCtx();
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copyStream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaMallocHost((void **)&c->hCtr, sizeof(DevCounters)) != cudaSuccess ||
         cudaMallocHost((void **)&c->hWater, 64 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMallocHost((void **)&c->hStage, kStageBytes) != cudaSuccess ||
@@ -139,39 +141,6 @@ int selectDevice(int device, int *numSms) {
     *numSms = prop.multiProcessorCount;
     return MPLB_OK;
 }
-
-struct Se3Scene : SceneBase {
-    double so3w = 50, l2w = 1, invStep = 10;
-    // streamed batches whose input did not arrive under the kernel, in a row: two switch streaming off (capi.cu)
-    std::atomic<unsigned> streamStallsInARow{0}, unstreamedCalls{0};
-    SceneDev dev{};
-    DevBuf robotNodes, envNodes, robotTris, envTris, robotTris64, envTris64;
-    size_t nEnvTris = 0, nRobotTris = 0;
-
-    Se3Scene() { stateDim = 7; }
-    int checkStates(const double *states, size_t n, uint8_t *valid) override;
-    int checkEdges(const double *from, const double *to, size_t n, uint8_t *valid, uint64_t *statesChecked) override;
-    int planEdges(const double *from, const double *to, size_t n, uint32_t *steps) const override {
-        for (size_t i = 0; i < n; ++i) {
-            uint64_t st = edgeSteps(from + 7 * i, to + 7 * i);
-            if (!(st < (1ull << 31))) return fail(MPLB_ERR_INVALID, "edge %zu: step count out of range", i);
-            steps[i] = (uint32_t)st;
-        }
-        return MPLB_OK;
-    }
-
-    double distance(const double *a, const double *b) const override {
-        // nigh SE3Space<S,so3w,l2w> [EXT]: so3w * acos(|qa . qb|) + l2w * ||ta - tb||
-        double d = std::fabs(((a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]) + a[3] * b[3]);
-        double so3 = d < 1.0 ? std::acos(d) : 0.0;
-        double dx = a[4] - b[4], dy = a[5] - b[5], dz = a[6] - b[6];
-        return so3w * so3 + l2w * std::sqrt((dx * dx + dy * dy) + dz * dz);
-    }
-    // se3_rigid_body_scenario.hpp:139
-    uint64_t edgeSteps(const double *a, const double *b) const {
-        return (uint64_t)std::ceil(distance(a, b) * invStep);
-    }
-};
 
 static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t *valid);
 static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, size_t n, uint8_t *valid,
@@ -417,6 +386,7 @@ struct StreamsQuiet {
     CallCtx *c;
     ~StreamsQuiet() {
         cudaStreamSynchronize(c->copyStream);
+        cudaStreamSynchronize(c->copyStream2);
         cudaStreamSynchronize(c->stream);
     }
 };
@@ -474,8 +444,19 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
     if ((rc = c->in0.reserve(bytes)) || (rc = c->out.reserve(n))) return rc;
     double *dIn = (double *)c->in0.ptr;
     uint8_t *dOut = (uint8_t *)c->out.ptr;
+    // mode of a large batch: 2 = the kernel pulls the batch out of mapped page-locked host memory itself, 1 = chunked
+    // copies with arrival flags under the running kernel, 0 = copy-then-kernel in pieces
+    static const int forcedMode = [] { const char *e = std::getenv("MPLB_STREAM_MODE"); return e ? std::atoi(e) : -1; }();
     const WriteValue32Fn writeValue = streamWriteValue32();
-    const bool streamed = streamBatch(n) && writeValue && sc->streamStallsInARow.load(std::memory_order_relaxed) < 2;
+    void *mapped = nullptr;
+    if (streamBatch(n) && forcedMode != 0 && forcedMode != 1 && isPinned(states)) {
+        if (cudaHostGetDevicePointer(&mapped, const_cast<double *>(states), 0) != cudaSuccess) {
+            cudaGetLastError();
+            mapped = nullptr;
+        }
+    }
+    const bool streamed = !mapped && streamBatch(n) && forcedMode != 0 && writeValue &&
+                          sc->streamStallsInARow.load(std::memory_order_relaxed) < 2;
     // MPLB_TIMELINE=1: print where a streamed call's time goes (diagnostic)
     static const bool timeline = std::getenv("MPLB_TIMELINE") != nullptr;
     static thread_local cudaEvent_t tl[5] = {};
@@ -484,7 +465,13 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
         for (auto &e : tl) cudaEventCreate(&e);
     StreamsQuiet quiet{c};
     MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(DevCounters), c->stream));
-    if (!streamed) {
+    if (mapped) {
+        StreamedInput in;
+        in.host = (const double *)mapped;
+        MPLB_CUDA(launchCheckStates(sc->dev, dIn, n, dOut, (DevCounters *)c->ctr.ptr, (unsigned *)c->work.ptr, sc->numSms,
+                                    c->stream, in));
+        sc->hLaunches += 1;
+    } else if (!streamed) {
         if ((rc = se3StatesPipelined(sc, c, states, n, dIn, dOut))) return rc;
     } else {
         const size_t chunk = chunkStatesFor(n), nChunks = (n + chunk - 1) / chunk;
@@ -503,18 +490,29 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
                                     c->stream, in));
         sc->hLaunches += 1;
         if (timeline) cudaEventRecord(tl[3], c->stream);
+        // chunks alternate over two copy streams: the next chunk's copy is already queued at the copy engine while
+        // this chunk's flag is being written (one stream leaves a gap per chunk: measured 1.4-1.8 ms for the 58.7 MB
+        // of 2^20 states in 32 chunks against 1.06 ms in one piece)
+        static const int lanes = [] { const char *e = std::getenv("MPLB_STREAM_LANES"); return e ? std::atoi(e) : 2; }();
         for (size_t k = 0; k < nChunks; ++k) {
             const size_t lo = k * chunk, cnt = std::min(chunk, n - lo);
-            if ((rc = hostToDevice(c, dIn + 7 * lo, states + 7 * lo, cnt * 7 * sizeof(double), c->copyStream))) return rc;
-            const CUresult wr = writeValue((CUstream)c->copyStream, (CUdeviceptr)((unsigned *)c->flags.ptr + k), c->epoch, 0);
+            cudaStream_t cs = (lanes > 1 && (k & 1)) ? c->copyStream2 : c->copyStream;
+            if ((rc = hostToDevice(c, dIn + 7 * lo, states + 7 * lo, cnt * 7 * sizeof(double), cs))) return rc;
+            const CUresult wr = writeValue((CUstream)cs, (CUdeviceptr)((unsigned *)c->flags.ptr + k), c->epoch, 0);
             if (wr != CUDA_SUCCESS) return fail(MPLB_ERR_CUDA, "cuStreamWriteValue32 failed (%d)", (int)wr);
         }
-        if (timeline) cudaEventRecord(tl[2], c->copyStream);
+        if (timeline) {
+            cudaStreamSynchronize(c->copyStream2);   // (diagnostic only)
+            cudaEventRecord(tl[2], c->copyStream);
+        }
     }
     MPLB_CUDA(cudaMemcpyAsync(valid, dOut, n, cudaMemcpyDeviceToHost, c->stream));
     if (timeline && streamed) cudaEventRecord(tl[4], c->stream);
     int frc = finishCall(sc, c, n, nullptr);
-    if (streamed) cudaStreamSynchronize(c->copyStream);
+    if (streamed) {
+        cudaStreamSynchronize(c->copyStream);
+        cudaStreamSynchronize(c->copyStream2);
+    }
     if (timeline && streamed) {
         float b, k, d;
         cudaEventElapsedTime(&b, tl[0], tl[2]);
@@ -626,6 +624,10 @@ static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, siz
     if (timeline)
         std::fprintf(stderr, "[mplb timeline] %zu edges: steps planned %.3f ms, enqueued %.3f, done %.3f\n", n, tPlan, tEnq, sinceMs());
     return rc;
+}
+
+int se3CheckEdgesHost(Se3Scene *sc, const double *from, const double *to, size_t n, uint8_t *valid, uint64_t *statesChecked) {
+    return se3CheckEdges(sc, from, to, n, valid, statesChecked);
 }
 
 int Se3Scene::checkStates(const double *states, size_t n, uint8_t *valid) { return se3CheckStates(this, states, n, valid); }

@@ -2,10 +2,12 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <atomic>
+#include <cmath>
 #include <cstdint>
 #include <mutex>
 #include <string>
 #include <vector>
+#include "../../include/mplb.h"
 #include "se3_device.cuh"
 
 namespace mplb {
@@ -28,6 +30,7 @@ struct DevBuf {
 struct CallCtx {
     cudaStream_t stream = nullptr;      // kernels + verdict read-back
     cudaStream_t copyStream = nullptr;  // host->device input copies of pipelined batches
+    cudaStream_t copyStream2 = nullptr; // streamed batches alternate their chunks over both copy streams
     std::vector<cudaEvent_t> events;    // one per pipeline stage
     DevBuf in0, in1, steps, dead, out, ctr, work, aux0, aux1, aux2, aux3, aux4, aux5, aux6;
     DevCounters *hCtr = nullptr;  // pinned
@@ -86,6 +89,40 @@ struct SceneBase {
     virtual int checkEdges(const double *from, const double *to, size_t n, uint8_t *valid, uint64_t *statesChecked) = 0;
     virtual double distance(const double *a, const double *b) const = 0;
     virtual int planEdges(const double *from, const double *to, size_t n, uint32_t *steps) const = 0;
+};
+
+// the SE(3) rigid-body scene (capi.cu; the device-resident planner loop of planner_capi.cu works on it too)
+struct Se3Scene : SceneBase {
+    double so3w = 50, l2w = 1, invStep = 10;
+    // streamed batches whose input did not arrive under the kernel, in a row: two switch streaming off (capi.cu)
+    std::atomic<unsigned> streamStallsInARow{0}, unstreamedCalls{0};
+    SceneDev dev{};
+    DevBuf robotNodes, envNodes, robotTris, envTris, robotTris64, envTris64;
+    size_t nEnvTris = 0, nRobotTris = 0;
+
+    Se3Scene() { stateDim = 7; }
+    int checkStates(const double *states, size_t n, uint8_t *valid) override;
+    int checkEdges(const double *from, const double *to, size_t n, uint8_t *valid, uint64_t *statesChecked) override;
+    int planEdges(const double *from, const double *to, size_t n, uint32_t *steps) const override {
+        for (size_t i = 0; i < n; ++i) {
+            uint64_t st = edgeSteps(from + 7 * i, to + 7 * i);
+            if (!(st < (1ull << 31))) return fail(MPLB_ERR_INVALID, "edge %zu: step count out of range", i);
+            steps[i] = (uint32_t)st;
+        }
+        return MPLB_OK;
+    }
+
+    double distance(const double *a, const double *b) const override {
+        // nigh SE3Space<S,so3w,l2w> [EXT]: so3w * acos(|qa . qb|) + l2w * ||ta - tb||
+        double d = std::fabs(((a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]) + a[3] * b[3]);
+        double so3 = d < 1.0 ? std::acos(d) : 0.0;
+        double dx = a[4] - b[4], dy = a[5] - b[5], dz = a[6] - b[6];
+        return so3w * so3 + l2w * std::sqrt((dx * dx + dy * dy) + dz * dz);
+    }
+    // se3_rigid_body_scenario.hpp:139
+    uint64_t edgeSteps(const double *a, const double *b) const {
+        return (uint64_t)std::ceil(distance(a, b) * invStep);
+    }
 };
 
 struct CtxGuard {

@@ -48,6 +48,8 @@ struct DevCounters {
 // states out in index order and picks each claim up once its chunk's flag is there (se3_kernels.cu: StateSource).
 // flags == nullptr: the batch is resident.
 struct StreamedInput {
+    const double *host = nullptr;   // zero-copy: the batch in mapped page-locked host memory (device-visible address);
+                                    // the kernel pulls claims over PCIe itself and mirrors them into dStates
     const unsigned *flags = nullptr;
     unsigned epoch = 0, chunkStates = 0;
 };
@@ -73,6 +75,7 @@ struct EdgeGather {
     const long long *fromIdx, *toIdx;      // [n] or null
     unsigned long long fromRows, toRows;   // pool sizes: an index outside [0, rows) makes the edge invalid
     unsigned fromDiv, toDiv;               // >= 1
+    unsigned forceAmbiguousEvery = 0;      // test hook: report every k-th edge as ambiguous (0: off)
 };
 // scratch the indexed call needs besides the interval stacks: dense end states, steps, per-edge constants
 size_t edgeGatherBytes(size_t n);

@@ -273,7 +273,9 @@ __global__ void edgeGatherPlanKernel(EdgeGather g, unsigned long long n, double 
         return;
     }
     steps[e] = (unsigned)ceil(x);
-    if (d < 1.0 && fabs(x - rint(x)) <= x * 2e-15 + 1e-11) {
+    // |x_device - x_host| <= so3w * invStep * (acos: 2 + 1 ulp of pi/2) + rounding of the two products and the sum
+    const bool near = d < 1.0 && fabs(x - rint(x)) <= dmul(dmul(so3w, invStep), 2e-15) + x * 2e-15;
+    if (near || (g.forceAmbiguousEvery && e % g.forceAmbiguousEvery == 0)) {
         const unsigned at = atomicAdd(&ctr->ambiguous, 1u);
         if (at < kAmbiguousListed) ctr->ambiguousEdge[at] = (unsigned)e;
     }
@@ -413,10 +415,11 @@ struct StateSourceT {
     // warp picks its claim up once the flag of the chunk holding the claim's last state shows this call's epoch
     // (acquire load at system scope; flags are written in chunk order).  The wait is bounded: a copy that never
     // arrives is reported, not spun on.
+    const double *hostStates = nullptr;   // zero-copy source (mapped page-locked host memory) or null
     const unsigned *chunkFlags = nullptr;
     unsigned epoch = 0;
     unsigned chunkStates = 1;
-    unsigned long long landed = 0;   // states [0, landed) are known to be there
+    unsigned long long landedLo = 0, landedHi = 0;   // states [landedLo, landedHi) are known to be there
     static constexpr bool streamed = kStreamed;   // compile time: the resident kernel carries none of the streaming state
     unsigned stalled = 0;
     unsigned long long base = 0;
@@ -450,7 +453,7 @@ struct StateSourceT {
             if (exhausted) return 0;
             const unsigned long long left = n - min(seen, n);
             want = (int)min((unsigned long long)want, left / crew + 1);
-            if (streamed) want = min(want, claim);
+            if (streamed && !hostStates) want = min(want, claim);
             unsigned long long b = 0;
             if (lane == 0) b = atomicAdd(counter, (unsigned long long)want);
             b = __shfl_sync(kFull, b, 0);
@@ -470,25 +473,48 @@ struct StateSourceT {
                 base = b;
                 return want;
             }
+            if (hostStates) {
+                // Zero-copy: the batch sits in page-locked host memory mapped into the device's address space.  The warp
+                // pulls its claim over PCIe itself -- 56 B x want contiguous bytes, lane-contiguous 8-byte words, so the
+                // requests are full lines -- and leaves a copy in device memory for the exact path's re-reads.  The
+                // kernel's own progress paces the transfer; no copy engine, no arrival flags.
+                const double *src = hostStates + 7 * b;
+                double *dst = const_cast<double *>(states) + 7 * b;
+                const int words = 7 * want;
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    const int w = k * 32 + (int)lane;
+                    if (w < words) __stcg(dst + w, __ldcs(src + w));
+                }
+                __syncwarp();   // the claim's device copy is complete for every lane of the warp
+                base = b;
+                return want;
+            }
             pendBase = b;
             pendCount = want;
             waited = false;
         }
-        // one lane looks at the flag of the claim's last chunk, at most once per back-off period so that thousands
-        // of waiting warps do not crowd the L2 line the flag lives in
-        const unsigned long long last = pendBase + pendCount - 1;
-        int here = last < landed;
+        // one lane looks at the flags of the chunks the claim lies in (one, or two when it straddles a boundary; the
+        // chunks may land in any order), at most once per back-off period so that thousands of waiting warps do not
+        // crowd the L2 line the flags live in
+        const unsigned long long first = pendBase, last = pendBase + pendCount - 1;
+        int here = first >= landedLo && last < landedHi;
         if (!here) {
             if (waited && !mayBlock && clock64() - polledAt < (long long)backoff) return 0;
-            const unsigned chunk = (unsigned)(last / chunkStates);
+            const unsigned c0 = (unsigned)(first / chunkStates), c1 = (unsigned)(last / chunkStates);
             if (lane == 0) {
-                unsigned f;
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(chunkFlags + chunk) : "memory");
-                here = f == epoch;
+                unsigned f0, f1;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f0) : "l"(chunkFlags + c0) : "memory");
+                f1 = f0;
+                if (c1 != c0) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f1) : "l"(chunkFlags + c1) : "memory");
+                here = f0 == epoch && f1 == epoch;
             }
             here = __shfl_sync(kFull, here, 0);
             __syncwarp();   // orders the other lanes' loads of the claim behind lane 0's acquire
-            if (here) landed = min(n, (unsigned long long)(chunk + 1) * chunkStates);
+            if (here) {
+                landedLo = (unsigned long long)c0 * chunkStates;
+                landedHi = ((unsigned long long)c1 + 1) * chunkStates;
+            }
         }
         if (!here) {
             waited = true;
@@ -1223,7 +1249,7 @@ checkStatesKernel(SceneDev sc, const double *states, unsigned long long n, uint8
     WarpSmem<E> sm = warpSmem<E>(sc.stackLevels);
     StateSourceT<kStreamed> src;
     src.states = states; src.n = n; src.valid = valid; src.counter = workCounter;
-    src.chunkFlags = in.flags; src.epoch = in.epoch; src.chunkStates = in.chunkStates ? in.chunkStates : 1u;
+    src.hostStates = in.host; src.chunkFlags = in.flags; src.epoch = in.epoch; src.chunkStates = in.chunkStates ? in.chunkStates : 1u;
     src.crew = (unsigned long long)gridDim.x * kWarpsPerCta * guidedShare;
     WarpCounters cnt;
 #ifdef MPLB_WARP_TIMES
@@ -1327,7 +1353,7 @@ cudaError_t gridFor(K kernel, size_t smem, int numSms, int *grid) {
 template <typename E>
 cudaError_t launchStatesT(const SceneDev &sc, const double *dStates, size_t n, uint8_t *dValid, DevCounters *dCtr,
                           unsigned long long *dWork, const StreamedInput &in, int numSms, cudaStream_t stream) {
-    const bool streamed = in.flags != nullptr;
+    const bool streamed = in.flags != nullptr || in.host != nullptr;
     // batches that leave most of the grid idle are latency bound
     auto k = streamed ? checkStatesKernel<E, false, true>   // (streamed batches are >= 65,536 states: see capi.cu)
                       : n < kLatencyBelow ? checkStatesKernel<E, true, false> : checkStatesKernel<E, false, false>;

@@ -67,3 +67,23 @@ class Nigh:
 
     def nearest_device(self, d_queries_ptr, nq, d_idx_ptr, d_dist_ptr, stream=0):
         _capi.check(_capi.lib().mplb_nn_nearest_device(self._h, d_queries_ptr, nq, d_idx_ptr, d_dist_ptr, stream))
+
+    def knearest_device(self, d_queries_ptr, nq, k, d_idx_ptr, d_dist_ptr, stream=0):
+        """k-NN on device-resident queries: [nq, k] int64 / float64 device arrays, enqueued on `stream`."""
+        _capi.check(_capi.lib().mplb_nn_knearest_device(self._h, d_queries_ptr, nq, int(k), d_idx_ptr, d_dist_ptr, stream))
+
+    def insert_device(self, d_keys_ptr, n, stream=0):
+        """keys that already sit in device memory; returns the index of the first inserted key."""
+        first = self.size()
+        _capi.check(_capi.lib().mplb_nn_insert_device(self._h, d_keys_ptr, n, stream))
+        return first
+
+    def reserve(self, capacity):
+        _capi.check(_capi.lib().mplb_nn_reserve(self._h, int(capacity)))
+
+    def capacity(self):
+        return int(_capi.lib().mplb_nn_capacity(self._h))
+
+    def keys_device(self):
+        """device pointer of the key array [size, dim] float64 (the pool index-named edges read tree nodes from)."""
+        return _capi.lib().mplb_nn_keys_device(self._h) or 0

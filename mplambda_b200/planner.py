@@ -85,12 +85,14 @@ class BatchedRRT:
         self.parent[first:first + len(new)] = idx[new]
         self.n += len(new)
         self.nn.insert(self._scale(q[new]))
-        goal = known[new]
-        if not goal.any() and hasattr(self.scenario, "is_goal_batch"):
-            goal = self.scenario.is_goal_batch(q[new])
-        hit = np.nonzero(goal)[0]
+        hit = np.nonzero(self._goals(q[new], known[new]))[0]
         if len(hit):
             self.solution = first + int(hit[0])
+
+    def _goals(self, q_new, known_new):
+        if not known_new.any() and hasattr(self.scenario, "is_goal_batch"):
+            return self.scenario.is_goal_batch(q_new)
+        return known_new
 
     def solve(self, time_limit=60.0, max_iterations=10 ** 9):
         t0 = time.perf_counter()
@@ -109,6 +111,93 @@ class BatchedRRT:
             out.append(self.nodes[i].copy())
             i = int(self.parent[i])
         return np.asarray(out[::-1])
+
+
+class DeviceRRT:
+    """The same loop run on the device (libmplb's mplb_rrt_*: sampler, nearest neighbour, index-named motion check and
+    node selection are kernels; the host reads a 24-byte status per iteration and the tree once at the end).
+    scenario: an SE3RigidBodyScenario; the tree's nodes are the keys of `nn` (an empty SE3 Nigh)."""
+
+    def __init__(self, scenario, nn, start, batch=2048, goal_bias=0.01, seed=1):
+        import ctypes as C
+        from . import _capi
+        self._C, self._capi = C, _capi
+        self.scenario, self.nn, self.batch = scenario, nn, int(batch)
+        self._h = C.c_void_p()
+        start = np.ascontiguousarray(start, dtype=np.float64).reshape(7)
+        goal = np.ascontiguousarray(scenario.goal_, dtype=np.float64)
+        rc = _capi.lib().mplb_rrt_create(scenario._h, nn._h, start.ctypes.data_as(_capi.dp), goal.ctypes.data_as(_capi.dp),
+                                         scenario.goalRadius_, scenario.min_.ctypes.data_as(_capi.dp),
+                                         scenario.max_.ctypes.data_as(_capi.dp), int(seed), self.batch, float(goal_bias),
+                                         C.byref(self._h))
+        if rc == _capi.ERR_INVALID:
+            raise ValueError(_capi.lib().mplb_last_error().decode("utf-8", "replace"))   # prrt.hpp:109-110
+        _capi.check(rc)
+        self.solution = -1
+        self.stats = dict(iterations=0, samples=0, edges_checked=0, nodes=1, seconds=0.0)
+        self.nodes = self.parent = None
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._capi.lib().mplb_rrt_destroy(self._h)
+            self._h = self._C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def solve(self, time_limit=60.0, max_iterations=10 ** 9):
+        st = self._capi.RrtStatus()
+        self._capi.check(self._capi.lib().mplb_rrt_run(self._h, int(max_iterations), float(time_limit), self._C.byref(st)))
+        self.stats.update(st.as_dict())
+        self.solution = int(st.solution)
+        self.n = int(st.nodes)
+        return self.path()
+
+    def tree(self):
+        n = self._C.c_size_t()
+        self._capi.check(self._capi.lib().mplb_rrt_tree(self._h, None, None, 0, self._C.byref(n)))
+        nodes = np.empty((n.value, 7))
+        parent = np.empty(n.value, dtype=np.int64)
+        self._capi.check(self._capi.lib().mplb_rrt_tree(self._h, nodes.ctypes.data_as(self._C.c_void_p),
+                                                        parent.ctypes.data_as(self._C.c_void_p), n.value, self._C.byref(n)))
+        self.nodes, self.parent, self.n = nodes, parent, n.value
+        return nodes, parent
+
+    def samples(self, iteration):
+        """(states [batch, 7], goal-sample flags [batch]) of iteration `iteration`, as the device loop draws them."""
+        q = np.empty((self.batch, 7))
+        g = np.empty(self.batch, dtype=np.uint8)
+        self._capi.check(self._capi.lib().mplb_rrt_samples(self._h, int(iteration), q.ctypes.data_as(self._C.c_void_p),
+                                                           g.ctypes.data_as(self._C.c_void_p)))
+        return q, g.astype(bool)
+
+    def path(self):
+        if self.solution < 0:
+            return None
+        nodes, parent = self.tree()
+        out, i = [], self.solution
+        while i >= 0:
+            out.append(nodes[i].copy())
+            i = int(parent[i])
+        return np.asarray(out[::-1])
+
+
+class ReplayRRT(BatchedRRT):
+    """BatchedRRT fed with the sample batches a DeviceRRT draws (iteration by iteration), on any backend: the tree it
+    builds must be the device loop's tree (tests)."""
+
+    def __init__(self, scenario, nn, start, device_rrt):
+        super().__init__(scenario, nn, start, batch=device_rrt.batch, goal_bias=0.0, seed=0)
+        self._src = device_rrt
+
+    def _draw(self):
+        return self._src.samples(self.stats["iterations"])
+
+    def _goals(self, q_new, known_new):   # the device loop's rule: isGoal(q) (se3...:115-117); sampled goals satisfy it
+        return known_new | np.array([bool(self.scenario.isGoal(x)) for x in q_new], dtype=bool)
 
 
 class BatchedRRTStar(BatchedRRT):

@@ -175,6 +175,47 @@ class SE3RigidBodyScenario:
         _capi.check(_capi.lib().mplb_check_edges_device(self._h, d_from, d_to, d_steps, n, int(max_steps), d_valid,
                                                         stream))
 
+    def sample_states_device(self, seed, first, n, d_states_ptr, stream=0):
+        """randomSample for n states into device memory: draw first + i of the Philox stream keyed by `seed`
+        (the stream of mplambda_b200.workload.se3_poses)."""
+        _capi.check(_capi.lib().mplb_sample_states_device(self._h, self.min_.ctypes.data_as(_capi.dp),
+                                                          self.max_.ctypes.data_as(_capi.dp), int(seed), int(first), int(n),
+                                                          d_states_ptr, stream))
+
+    def check_edges_indexed(self, d_from_pool, from_rows, from_idx, d_to_pool, to_rows, to_idx, n=None, from_div=1, to_div=1,
+                            return_states_checked=False):
+        """isValid(from, to) for edges named by index into device-resident state pools (device pointers, e.g.
+        Nigh.keys_device()): edge e = from_pool[from_idx[e] or e // from_div] -> to_pool[to_idx[e] or e // to_div].
+        from_idx / to_idx: int64 numpy arrays (copied in, 8 B per end point) or None."""
+        def idx(a):
+            if a is None:
+                return None, None
+            a = np.ascontiguousarray(a, dtype=np.int64)
+            return a, _ptr(a)
+        fi, fp = idx(from_idx)
+        ti, tp = idx(to_idx)
+        if n is None:
+            n = len(fi) if fi is not None else len(ti)
+        out = np.empty(n, dtype=np.uint8)
+        checked = C.c_uint64()
+        _capi.check(_capi.lib().mplb_check_edges_indexed(self._h, d_from_pool, from_rows, fp, from_div, d_to_pool, to_rows,
+                                                         tp, to_div, n, 0, _ptr(out), C.byref(checked)))
+        if return_states_checked:
+            return out.astype(bool), checked.value
+        return out.astype(bool)
+
+    def check_edges_indexed_device(self, d_from_pool, from_rows, d_from_idx, d_to_pool, to_rows, d_to_idx, n, d_valid,
+                                   from_div=1, to_div=1, stream=0, synchronous=False):
+        """the same with index arrays and verdicts in device memory; synchronous=True resolves ambiguous step counts
+        like the host call, otherwise the work is only enqueued on `stream`."""
+        L = _capi.lib()
+        if synchronous:
+            _capi.check(L.mplb_check_edges_indexed(self._h, d_from_pool, from_rows, d_from_idx, from_div, d_to_pool, to_rows,
+                                                   d_to_idx, to_div, n, 1, d_valid, None))
+        else:
+            _capi.check(L.mplb_check_edges_indexed_device(self._h, d_from_pool, from_rows, d_from_idx, from_div, d_to_pool,
+                                                          to_rows, d_to_idx, to_div, n, d_valid, stream))
+
     def stats(self, reset=False):
         st = _capi.Stats()
         _capi.check(_capi.lib().mplb_scene_stats(self._h, C.byref(st), int(reset)))
