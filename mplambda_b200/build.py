@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "_obj")
+OBJ = os.environ.get("MPLB_OBJ") or os.path.join(HERE, "_obj")
 LIB = os.environ.get("MPLB_LIB") or os.path.join(HERE, "libmplb.so")
 SOURCES = ["capi.cu", "se3_kernels.cu", "nn_capi.cu", "nn_kernels.cu", "fetch_capi.cu", "fetch_kernels.cu",
            "planner_capi.cu", "planner_kernels.cu", "bvh_build.cpp", "collada.cpp", "bvh_cache.cpp"]

@@ -332,7 +332,26 @@ static int finishCall(SceneBase *sc, CallCtx *c, size_t checks, uint64_t *states
         for (size_t i = 0; i < ord.size() && i < 6; ++i)
             std::fprintf(stderr, "    warp %4d done %.1f us: states %u bv %u tri %u\n", ord[i], ((double)k.warpDone[ord[i]] - t0) * 1e-3,
                          k.warpStates[ord[i]], k.warpBv[ord[i]], k.warpTri[ord[i]]);
-        if (!ord.empty()) std::fprintf(stderr, "    median warp done %.1f us (%zu warps)\n", ((double)k.warpDone[ord[ord.size() / 2]] - t0) * 1e-3, ord.size());
+        if (!ord.empty()) {
+            std::fprintf(stderr, "    warps done (us) by percentile, %zu warps:", ord.size());
+            for (int pc : {0, 10, 25, 50, 75, 90, 95, 99, 100})
+                std::fprintf(stderr, " p%d %.0f", pc, ((double)k.warpDone[ord[(ord.size() - 1) * (100 - pc) / 100]] - t0) * 1e-3);
+            std::vector<double> dry, gap;
+            for (int w : ord)
+                if (k.warpDry[w] != ~0ull && k.warpDry[w]) {
+                    dry.push_back(((double)k.warpDry[w] - t0) * 1e-3);
+                    gap.push_back(((double)k.warpDone[w] - (double)k.warpDry[w]) * 1e-3);
+                }
+            std::sort(dry.begin(), dry.end());
+            std::sort(gap.begin(), gap.end());
+            if (!dry.empty()) {
+                std::fprintf(stderr, "\n    warps dry (us):");
+                for (int pc : {0, 10, 50, 90, 100}) std::fprintf(stderr, " p%d %.0f", pc, dry[(dry.size() - 1) * pc / 100]);
+                std::fprintf(stderr, "\n    dry -> done (us):");
+                for (int pc : {0, 10, 25, 50, 75, 90, 99, 100}) std::fprintf(stderr, " p%d %.0f", pc, gap[(gap.size() - 1) * pc / 100]);
+            }
+            std::fprintf(stderr, "\n");
+        }
     }
 #endif
     return account(sc, *c->hCtr, checks, statesOut);
@@ -355,30 +374,38 @@ static WriteValue32Fn streamWriteValue32() {
     return fn;
 }
 
-// Large host batches stream in under the running kernel.  The batch is copied in chunks on the context's copy stream
-// and, behind each chunk on that stream, a stream memory operation (cuStreamWriteValue32: ordered after the copy, with
-// a system-wide fence in front of the write) sets that chunk's arrival flag to this call's epoch.  The kernel is
-// launched first on the compute stream, hands states out in index order and picks a claim up once its chunk's flag is
-// there (acquire load).  The input is 56 B/state and the kernel needs ~1 ns/state, so the call costs about one
-// host->device copy of the batch.  Without stream memory operations -- or when a kernel reports that its input did not
-// arrive in time (a profiler serialising the kernel and the copies) -- the batch goes chunk by chunk copy-then-kernel.
+// Large host batches stream in under the running kernel.  The batch is copied in pieces on the context's copy stream
+// and, behind each piece on that stream, a stream memory operation (cuStreamWriteValue32: ordered after the copy, with
+// a system-wide fence in front of the write) advances the call's watermark word.  The kernel is launched first on the
+// compute stream, hands states out in index order and picks a claim up once the watermark covers it (acquire load).
+// The input is 56 B/state and the kernel needs ~1 ns/state, so the call costs about one host->device copy of the batch.
+// Without stream memory operations the watermark travels as a 4-byte copy on the same stream (stream order: it starts
+// after the piece's copy has completed).  When a kernel reports that its input did not arrive in time (a profiler
+// serialising the kernel and the copies) the batch is repeated piece by piece copy-then-kernel.
 static bool streamBatch(size_t n) {
     static const long forced = [] {
         const char *e = std::getenv("MPLB_STREAM_MIN");
         return e ? std::atol(e) : 0L;
     }();
-    return n >= (size_t)(forced > 0 ? forced : 65536);
+    return n >= (size_t)(forced > 0 ? forced : 65536) && n < ((size_t)1 << 32);
 }
 
-constexpr size_t kMaxChunks = 256;
-static size_t chunkStatesFor(size_t n) {
+// Pieces a streamed batch is copied in (states per piece, multiples of 1024).  Measured on 2^20 Alpha poses: the copy is
+// the longer leg (1.06 ms in one piece, 1.11 ms in eight with the watermark writes on a side stream, 1.35 ms in 64); the
+// kernel finishes ~0.23 ms after the last piece whatever the piece size or order (halving pieces at the end, small
+// pieces in front, 64 K or 256 K pieces: all within 2 %) -- that is the time a warp needs to drain the states it
+// holds, not the size of the last piece.
+constexpr size_t kMaxPieces = 128;   // (CallCtx::hWater holds 128 words)
+static std::vector<size_t> streamPieces(size_t n) {
     static const long forced = [] {
         const char *e = std::getenv("MPLB_STREAM_CHUNK");
         return e ? std::atol(e) : 0L;
     }();
-    size_t c = forced > 0 ? (size_t)forced : std::min<size_t>(32768, std::max<size_t>(8192, ((n / 16) + 1023) & ~(size_t)1023));
-    c = std::max(c, (n + kMaxChunks - 1) / kMaxChunks);
-    return c;
+    auto up = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
+    const size_t piece = std::max(up(forced > 0 ? (size_t)forced : 131072), up(n / (kMaxPieces - 1)));
+    std::vector<size_t> pieces;
+    for (size_t left = n; left > 0; left -= pieces.back()) pieces.push_back(std::min(piece, left));
+    return pieces;
 }
 
 // both streams idle before the context goes back to the pool, whatever path the call leaves by
@@ -449,13 +476,13 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
     static const int forcedMode = [] { const char *e = std::getenv("MPLB_STREAM_MODE"); return e ? std::atoi(e) : -1; }();
     const WriteValue32Fn writeValue = streamWriteValue32();
     void *mapped = nullptr;
-    if (streamBatch(n) && forcedMode != 0 && forcedMode != 1 && isPinned(states)) {
+    if (streamBatch(n) && forcedMode == 2 && isPinned(states)) {
         if (cudaHostGetDevicePointer(&mapped, const_cast<double *>(states), 0) != cudaSuccess) {
             cudaGetLastError();
             mapped = nullptr;
         }
     }
-    const bool streamed = !mapped && streamBatch(n) && forcedMode != 0 && writeValue &&
+    const bool streamed = !mapped && streamBatch(n) && forcedMode != 0 &&
                           sc->streamStallsInARow.load(std::memory_order_relaxed) < 2;
     // MPLB_TIMELINE=1: print where a streamed call's time goes (diagnostic)
     static const bool timeline = std::getenv("MPLB_TIMELINE") != nullptr;
@@ -474,36 +501,58 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
     } else if (!streamed) {
         if ((rc = se3StatesPipelined(sc, c, states, n, dIn, dOut))) return rc;
     } else {
-        const size_t chunk = chunkStatesFor(n), nChunks = (n + chunk - 1) / chunk;
         if (!c->flags.ptr) {
-            if ((rc = c->flags.reserve(kMaxChunks * sizeof(unsigned)))) return rc;
-            MPLB_CUDA(cudaMemsetAsync(c->flags.ptr, 0, kMaxChunks * sizeof(unsigned), c->stream));
+            if ((rc = c->flags.reserve(128))) return rc;
+            MPLB_CUDA(cudaMemsetAsync(c->flags.ptr, 0, 128, c->stream));
         }
-        if (++c->epoch == 0) c->epoch = 1;   // (flags start at 0)
+        c->epoch = c->epoch % 1000u + 1u;   // never 0 (the word starts at 0), never the previous call's
         StreamedInput in;
-        in.flags = (const unsigned *)c->flags.ptr;
+        in.water = (const unsigned *)c->flags.ptr;
         in.epoch = c->epoch;
-        in.chunkStates = (unsigned)chunk;
+        // MPLB_STREAM_PRECOPY (diagnostic): the streamed kernel on a batch that is already there
+        static const bool precopy = std::getenv("MPLB_STREAM_PRECOPY") != nullptr;
+        auto launch = [&]() -> int {
+            if (timeline) cudaEventRecord(tl[1], c->stream);
+            MPLB_CUDA(launchCheckStates(sc->dev, dIn, n, dOut, (DevCounters *)c->ctr.ptr, (unsigned *)c->work.ptr, sc->numSms,
+                                        c->stream, in));
+            sc->hLaunches += 1;
+            if (timeline) cudaEventRecord(tl[3], c->stream);
+            return MPLB_OK;
+        };
         if (timeline) cudaEventRecord(tl[0], c->copyStream);
-        if (timeline) cudaEventRecord(tl[1], c->stream);
-        MPLB_CUDA(launchCheckStates(sc->dev, dIn, n, dOut, (DevCounters *)c->ctr.ptr, (unsigned *)c->work.ptr, sc->numSms,
-                                    c->stream, in));
-        sc->hLaunches += 1;
-        if (timeline) cudaEventRecord(tl[3], c->stream);
-        // chunks alternate over two copy streams: the next chunk's copy is already queued at the copy engine while
-        // this chunk's flag is being written (one stream leaves a gap per chunk: measured 1.4-1.8 ms for the 58.7 MB
-        // of 2^20 states in 32 chunks against 1.06 ms in one piece)
-        static const int lanes = [] { const char *e = std::getenv("MPLB_STREAM_LANES"); return e ? std::atoi(e) : 2; }();
-        for (size_t k = 0; k < nChunks; ++k) {
-            const size_t lo = k * chunk, cnt = std::min(chunk, n - lo);
-            cudaStream_t cs = (lanes > 1 && (k & 1)) ? c->copyStream2 : c->copyStream;
-            if ((rc = hostToDevice(c, dIn + 7 * lo, states + 7 * lo, cnt * 7 * sizeof(double), cs))) return rc;
-            const CUresult wr = writeValue((CUstream)cs, (CUdeviceptr)((unsigned *)c->flags.ptr + k), c->epoch, 0);
-            if (wr != CUDA_SUCCESS) return fail(MPLB_ERR_CUDA, "cuStreamWriteValue32 failed (%d)", (int)wr);
+        if (!precopy && (rc = launch())) return rc;
+        // MPLB_STREAM_FLAGCOPY (diagnostic): the watermark goes over as a 4-byte copy from page-locked memory instead
+        static const bool flagCopy = std::getenv("MPLB_STREAM_FLAGCOPY") != nullptr;
+        const std::vector<size_t> pieces = streamPieces(n);
+        while (c->events.size() < pieces.size()) {
+            cudaEvent_t e;
+            MPLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->events.push_back(e);
         }
-        if (timeline) {
-            cudaStreamSynchronize(c->copyStream2);   // (diagnostic only)
-            cudaEventRecord(tl[2], c->copyStream);
+        // The pieces go back to back on the copy stream with an event behind each; the watermark writes wait for those
+        // events on a second stream, so the copy engine never waits for a write between two pieces.
+        size_t lo = 0;
+        for (size_t k = 0; k < pieces.size(); ++k) {
+            const size_t cnt = pieces[k];
+            if ((rc = hostToDevice(c, dIn + 7 * lo, states + 7 * lo, cnt * 7 * sizeof(double), c->copyStream))) return rc;
+            lo += cnt;
+            MPLB_CUDA(cudaEventRecord(c->events[k], c->copyStream));
+            MPLB_CUDA(cudaStreamWaitEvent(c->copyStream2, c->events[k], 0));
+            cudaStream_t ws = c->copyStream2;
+            const unsigned mark = c->epoch << kWaterShift | (unsigned)((lo + 1023) >> kWaterUnitBits);
+            if (flagCopy || !writeValue) {
+                unsigned *h = (unsigned *)c->hWater + k;
+                *h = mark;
+                MPLB_CUDA(cudaMemcpyAsync(c->flags.ptr, h, sizeof(unsigned), cudaMemcpyHostToDevice, ws));
+            } else {
+                const CUresult wr = writeValue((CUstream)ws, (CUdeviceptr)c->flags.ptr, mark, 0);
+                if (wr != CUDA_SUCCESS) return fail(MPLB_ERR_CUDA, "cuStreamWriteValue32 failed (%d)", (int)wr);
+            }
+        }
+        if (timeline) cudaEventRecord(tl[2], c->copyStream);
+        if (precopy) {
+            MPLB_CUDA(cudaStreamSynchronize(c->copyStream));
+            if ((rc = launch())) return rc;
         }
     }
     MPLB_CUDA(cudaMemcpyAsync(valid, dOut, n, cudaMemcpyDeviceToHost, c->stream));
@@ -535,7 +584,7 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
     }
     if (streamed) {
         sc->streamStallsInARow.store(0, std::memory_order_relaxed);
-    } else if (streamBatch(n) && writeValue && (sc->unstreamedCalls.fetch_add(1, std::memory_order_relaxed) & 63u) == 63u) {
+    } else if (streamBatch(n) && (sc->unstreamedCalls.fetch_add(1, std::memory_order_relaxed) & 63u) == 63u) {
         sc->streamStallsInARow.store(1, std::memory_order_relaxed);   // probe: the next large call streams again
     }
     return frc;
@@ -610,19 +659,33 @@ static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, siz
         (rc = c->dead.reserve(n * 4)) || (rc = c->out.reserve(n)) || (rc = c->aux0.reserve(stackBytes)) ||
         (rc = c->aux1.reserve(edgeConstBytes(n))))
         return rc;
+    static thread_local cudaEvent_t tl[4] = {};
+    if (timeline && !tl[0])
+        for (auto &e : tl) cudaEventCreate(&e);
+    if (timeline) cudaEventRecord(tl[0], c->stream);
     MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(DevCounters), c->stream));
     if ((rc = hostToDevice(c, c->in0.ptr, from, sb, c->stream)) || (rc = hostToDevice(c, c->in1.ptr, to, sb, c->stream))) return rc;
     MPLB_CUDA(cudaMemcpyAsync(c->steps.ptr, c->hSteps.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+    if (timeline) cudaEventRecord(tl[1], c->stream);
     MPLB_CUDA(launchCheckEdges(sc->dev, (const double *)c->in0.ptr, (const double *)c->in1.ptr,
                                (const unsigned *)c->steps.ptr, n, (unsigned *)c->dead.ptr, (uint8_t *)c->out.ptr,
                                (DevCounters *)c->ctr.ptr, (unsigned long long *)c->work.ptr, c->aux0.ptr, stackBytes,
                                (double *)c->aux1.ptr, sc->numSms, c->stream));
     sc->hLaunches += 5;   // per-edge constants, three passes, the verdict kernel
+    if (timeline) cudaEventRecord(tl[2], c->stream);
+    const double tLaunched = sinceMs();
     MPLB_CUDA(cudaMemcpyAsync(valid, c->out.ptr, n, cudaMemcpyDeviceToHost, c->stream));
+    if (timeline) cudaEventRecord(tl[3], c->stream);
     const double tEnq = sinceMs();
     rc = finishCall(sc, c, 0, statesChecked);
-    if (timeline)
-        std::fprintf(stderr, "[mplb timeline] %zu edges: steps planned %.3f ms, enqueued %.3f, done %.3f\n", n, tPlan, tEnq, sinceMs());
+    if (timeline) {
+        float a, b, d;
+        cudaEventElapsedTime(&a, tl[0], tl[1]);
+        cudaEventElapsedTime(&b, tl[1], tl[2]);
+        cudaEventElapsedTime(&d, tl[2], tl[3]);
+        std::fprintf(stderr, "[mplb timeline] %zu edges: steps planned %.3f ms, launched %.3f, enqueued %.3f, done %.3f; device: copies in %.3f, kernels %.3f, verdicts out %.3f\n",
+                     n, tPlan, tLaunched, tEnq, sinceMs(), a, b, d);
+    }
     return rc;
 }
 

@@ -38,20 +38,22 @@ struct DevCounters {
     unsigned ambiguousEdge[kAmbiguousListed];
 #ifdef MPLB_WARP_TIMES   // diagnostic build: when did the warps start / run out of new work / finish (globaltimer, ns)
     unsigned long long negStart, negFirstDry, negFirstDone, lastDone;   // neg*: ~t, so that atomicMax finds the minimum
-    unsigned long long warpDone[4096];
+    unsigned long long warpDone[4096], warpDry[4096];
     unsigned warpStates[4096], warpBv[4096], warpTri[4096];
 #endif
 };
 
-// A batch that is still being copied in while the kernel runs: the host copies it in chunks of `chunkStates` states
-// and writes flags[c] = epoch behind chunk c on the copy's stream (a stream memory operation); the kernel hands
-// states out in index order and picks each claim up once its chunk's flag is there (se3_kernels.cu: StateSource).
-// flags == nullptr: the batch is resident.
+// A batch that is still being copied in while the kernel runs: the host copies it in pieces on one stream and writes
+// *water = epoch << kWaterShift | (states landed so far) >> kWaterUnitBits behind each piece (a stream memory
+// operation); the kernel hands states out in index order and picks each claim up once the watermark covers it
+// (se3_kernels.cu: StateSource).  Pieces end on multiples of 1024 states (the last one is rounded up), and the epoch
+// changes with every call on the word, so the word never needs clearing.  water == nullptr: the batch is resident.
+constexpr unsigned kWaterShift = 22, kWaterUnitBits = 10;
 struct StreamedInput {
     const double *host = nullptr;   // zero-copy: the batch in mapped page-locked host memory (device-visible address);
                                     // the kernel pulls claims over PCIe itself and mirrors them into dStates
-    const unsigned *flags = nullptr;
-    unsigned epoch = 0, chunkStates = 0;
+    const unsigned *water = nullptr;
+    unsigned epoch = 0;
 };
 // workZeroed: the caller has already zeroed the first work counter
 cudaError_t launchCheckStates(const SceneDev &sc, const double *dStates, size_t n, uint8_t *dValid,

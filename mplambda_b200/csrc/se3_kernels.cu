@@ -33,6 +33,8 @@
 #include "se3_device.cuh"
 #include "device_math.cuh"
 
+#include <algorithm>
+#include <cstdlib>
 #include <cfloat>
 #include <map>
 #include <mutex>
@@ -409,17 +411,15 @@ struct StateSourceT {
     unsigned long long n;
     uint8_t *valid;
     unsigned long long *counter;
-    // Host batches stream in while the kernel runs (`streamed`): the host copies the batch in chunks and, behind each
-    // chunk on the same stream, writes that chunk's flag with a stream memory operation (cuStreamWriteValue32 --
-    // ordered after the copy it follows, visible to running kernels).  States are handed out in index order and a
-    // warp picks its claim up once the flag of the chunk holding the claim's last state shows this call's epoch
-    // (acquire load at system scope; flags are written in chunk order).  The wait is bounded: a copy that never
-    // arrives is reported, not spun on.
+    // Host batches stream in while the kernel runs (`streamed`): the host copies the batch in pieces on one stream and,
+    // behind each piece, writes the watermark word -- call epoch << 22 | states landed so far / 1024 -- with a stream
+    // memory operation (cuStreamWriteValue32: ordered after the copy it follows, visible to running kernels).  States
+    // are handed out in index order and a warp picks its claim up once the watermark covers the claim's last state
+    // (acquire load at system scope).  The wait is bounded: a copy that never arrives is reported, not spun on.
     const double *hostStates = nullptr;   // zero-copy source (mapped page-locked host memory) or null
-    const unsigned *chunkFlags = nullptr;
+    const unsigned *water = nullptr;
     unsigned epoch = 0;
-    unsigned chunkStates = 1;
-    unsigned long long landedLo = 0, landedHi = 0;   // states [landedLo, landedHi) are known to be there
+    unsigned long long landed = 0;   // states [0, landed) are known to be there
     static constexpr bool streamed = kStreamed;   // compile time: the resident kernel carries none of the streaming state
     unsigned stalled = 0;
     unsigned long long base = 0;
@@ -494,27 +494,19 @@ struct StateSourceT {
             pendCount = want;
             waited = false;
         }
-        // one lane looks at the flags of the chunks the claim lies in (one, or two when it straddles a boundary; the
-        // chunks may land in any order), at most once per back-off period so that thousands of waiting warps do not
-        // crowd the L2 line the flags live in
-        const unsigned long long first = pendBase, last = pendBase + pendCount - 1;
-        int here = first >= landedLo && last < landedHi;
+        // one lane looks at the watermark, at most once per back-off period so that thousands of waiting warps do not
+        // crowd the L2 line it lives in
+        const unsigned long long last = pendBase + pendCount - 1;
+        int here = last < landed;
         if (!here) {
             if (waited && !mayBlock && clock64() - polledAt < (long long)backoff) return 0;
-            const unsigned c0 = (unsigned)(first / chunkStates), c1 = (unsigned)(last / chunkStates);
-            if (lane == 0) {
-                unsigned f0, f1;
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f0) : "l"(chunkFlags + c0) : "memory");
-                f1 = f0;
-                if (c1 != c0) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f1) : "l"(chunkFlags + c1) : "memory");
-                here = f0 == epoch && f1 == epoch;
-            }
-            here = __shfl_sync(kFull, here, 0);
+            // (a relaxed poll with a fence on every new watermark value was measured slower: 1.56 against 1.43 ms)
+            unsigned w = 0;
+            if (lane == 0) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(w) : "l"(water) : "memory");
+            w = __shfl_sync(kFull, w, 0);
             __syncwarp();   // orders the other lanes' loads of the claim behind lane 0's acquire
-            if (here) {
-                landedLo = (unsigned long long)c0 * chunkStates;
-                landedHi = ((unsigned long long)c1 + 1) * chunkStates;
-            }
+            if ((w >> kWaterShift) == epoch) landed = (unsigned long long)(w & ((1u << kWaterShift) - 1u)) << kWaterUnitBits;
+            here = last < landed;
         }
         if (!here) {
             waited = true;
@@ -788,25 +780,19 @@ struct EdgeSource {
         const unsigned total = __shfl_sync(kFull, incl, 31);
         if (total == 0) return;
         if (spillOut && (poolDry || globalDone) && stackCount + total > kSpillKeep) {
-            // reserve [pos, pos + total) only if it fits: the count never runs past the capacity, so what the next
-            // pass reads (min(count, cap) descriptors) is exactly what was written -- no reservation is ever undone
-            unsigned long long pos = ~0ull;
-            if (lane == 0) {
-                unsigned long long seen = *(volatile unsigned long long *)spillCount;
-                while (seen + total <= spillCap) {
-                    const unsigned long long was = atomicCAS(spillCount, seen, seen + total);
-                    if (was == seen) {
-                        pos = seen;
-                        break;
-                    }
-                    seen = was;
-                }
-            }
+            // One atomicAdd per reservation and no reservation is ever undone (a compare-and-swap loop on the one
+            // counter made thousands of warps retry against each other: 65,536 Cubicles edges 1.0 -> 3.3 ms).  The
+            // count may run past the capacity; the next pass reads min(count, cap) descriptors.  At most one failed
+            // reservation starts below the capacity: that warp fills [pos, cap) with empty descriptors (lo > hi), so
+            // every slot the next pass reads was written by this pass, and keeps its pieces on its own LIFO.
+            unsigned long long pos = 0;
+            if (lane == 0) pos = atomicAdd(spillCount, (unsigned long long)total);
             pos = __shfl_sync(kFull, pos, 0);
-            if (pos != ~0ull) {
+            if (pos + total <= spillCap) {
                 for (unsigned k = 0; k < cnt; ++k) spillOut[pos + incl - cnt + k] = kids[k];
                 return;
             }
+            for (unsigned long long at = pos + lane; at < spillCap; at += 32) spillOut[at] = make_uint4(0, 1, 0, 0);
         }
         if (stackCount + total > stackCap) {
             error = 1;  // reported by the host call; never silent
@@ -1249,7 +1235,7 @@ checkStatesKernel(SceneDev sc, const double *states, unsigned long long n, uint8
     WarpSmem<E> sm = warpSmem<E>(sc.stackLevels);
     StateSourceT<kStreamed> src;
     src.states = states; src.n = n; src.valid = valid; src.counter = workCounter;
-    src.hostStates = in.host; src.chunkFlags = in.flags; src.epoch = in.epoch; src.chunkStates = in.chunkStates ? in.chunkStates : 1u;
+    src.hostStates = in.host; src.water = in.water; src.epoch = in.epoch;
     src.crew = (unsigned long long)gridDim.x * kWarpsPerCta * guidedShare;
     WarpCounters cnt;
 #ifdef MPLB_WARP_TIMES
@@ -1262,6 +1248,14 @@ checkStatesKernel(SceneDev sc, const double *states, unsigned long long n, uint8
         atomicMax(&ctr->negFirstDry, ~src.dryAt);
         atomicMax(&ctr->negFirstDone, ~now());
         atomicMax(&ctr->lastDone, now());
+        const unsigned w = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+        if (w < 4096) {
+            ctr->warpDone[w] = now();
+            ctr->warpDry[w] = src.dryAt;
+            ctr->warpStates[w] = (unsigned)cnt.states;
+            ctr->warpBv[w] = (unsigned)cnt.bv;
+            ctr->warpTri[w] = (unsigned)cnt.tri;
+        }
     }
 #endif
     // a streamed batch whose copy did not arrive (e.g. a profiler serialising the kernel and the copy): reported
@@ -1353,9 +1347,13 @@ cudaError_t gridFor(K kernel, size_t smem, int numSms, int *grid) {
 template <typename E>
 cudaError_t launchStatesT(const SceneDev &sc, const double *dStates, size_t n, uint8_t *dValid, DevCounters *dCtr,
                           unsigned long long *dWork, const StreamedInput &in, int numSms, cudaStream_t stream) {
-    const bool streamed = in.flags != nullptr || in.host != nullptr;
+    const bool streamed = in.water != nullptr || in.host != nullptr;
     // batches that leave most of the grid idle are latency bound
-    auto k = streamed ? checkStatesKernel<E, false, true>   // (streamed batches are >= 65,536 states: see capi.cu)
+    // streamed batches (>= 65,536 states, capi.cu) wait for the host link, not for the SMs: they take the latency
+    // variant, whose extra votes per step cost nothing under the copy and whose tail after the last piece has landed
+    // is a third of the throughput variant's; a kernel slower than the copy (Apartment) loses ~3 %
+    static const bool streamedThroughput = std::getenv("MPLB_STREAM_THROUGHPUT") != nullptr;   // diagnostic
+    auto k = streamed ? (streamedThroughput ? checkStatesKernel<E, false, true> : checkStatesKernel<E, true, true>)
                       : n < kLatencyBelow ? checkStatesKernel<E, true, false> : checkStatesKernel<E, false, false>;
     const size_t smem = smemBytes<E>(sc);
     int grid = 0;
@@ -1395,11 +1393,16 @@ cudaError_t launchEdgesT(const SceneDev &sc, const double *dFrom, const double *
     uint4 *spill[2] = {dStacks + (stackBytes / sizeof(uint4) - 2 * (size_t)kSpillCap), nullptr};
     spill[1] = spill[0] + kSpillCap;
     const int threads = kWarpsPerCta * 32;
+    // MPLB_SPILL_CAP (diagnostic, tests): a small capacity makes the reservations overflow
+    static const unsigned spillCap = [] {
+        const char *e = std::getenv("MPLB_SPILL_CAP");
+        return e ? std::min<unsigned>(kSpillCap, (unsigned)std::max(1, std::atoi(e))) : kSpillCap;
+    }();
     for (int p = 0; p < kEdgePasses; ++p) {
         const bool last = p == kEdgePasses - 1;
         k<<<grid, threads, smem, stream>>>(sc, dFrom, dTo, dEdgeConst, dSteps, n, dDead, dStacks, kEdgeStackCap, dCtr, dWork + p,
                                            p ? spill[(p - 1) & 1] : nullptr, p ? dWork + 8 + (p - 1) : nullptr,
-                                           last ? nullptr : spill[p & 1], last ? nullptr : dWork + 8 + p, kSpillCap);
+                                           last ? nullptr : spill[p & 1], last ? nullptr : dWork + 8 + p, spillCap);
     }
     return cudaGetLastError();
 }

@@ -181,26 +181,49 @@ def test_concurrent_streamed_batches(scenes, oracle):
         assert st["stream_stalls"] == 0 and st["streaming_off"] == 0, st
 
 
-def test_streamed_batch_without_stream_memops(scenes, golden):
-    """Without stream memory operations (MPLB_NO_STREAM_MEMOPS: read once per process, hence the child process) large
-    batches go copy-then-kernel in pieces: same verdicts."""
+def _child(code, env):
     import subprocess
     import sys
-    code = ("import numpy as np, sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
-            "import mplambda_b200 as M\n"
-            "from mplambda_b200.workload import SE3_SCENES, SEED, se3_poses\n"
-            "d = np.load(%r); sc = SE3_SCENES['twistycool']\n"
-            "s = M.SE3RigidBodyScenario(d['env'], d['robot'], sc['goal'], sc['min'], sc['max'], 0.1)\n"
-            "want = np.load(%r)['twistycool_valid']\n"
-            "P = se3_poses(len(want), sc['min'], sc['max'], SEED)\n"
-            "big = np.concatenate([P] * 40)[:150000]; wbig = np.concatenate([want] * 40)[:150000]\n"
-            "assert (s.check_states(big) == wbig).all(); st = s.stats()\n"
-            "assert st['launches'] >= 4 and st['stream_stalls'] == 0, st\nprint('ok')\n"
-            % (os.path.dirname(GOLDEN) + "/..", os.path.dirname(GOLDEN), os.path.join(GOLDEN, "scenes", "twistycool.npz"),
-               os.path.join(GOLDEN, "se3_verdicts.npz")))
-    env = dict(os.environ, MPLB_NO_STREAM_MEMOPS="1")
-    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    pre = ("import numpy as np, sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+           "import mplambda_b200 as M\n"
+           "from mplambda_b200.workload import SE3_SCENES, SEED, se3_poses\n"
+           "GOLDEN = %r\n" % (os.path.dirname(GOLDEN) + "/..", os.path.dirname(GOLDEN), GOLDEN))
+    out = subprocess.run([sys.executable, "-c", pre + code], env=dict(os.environ, **env), capture_output=True, text=True,
+                         timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("env,launches", [({"MPLB_NO_STREAM_MEMOPS": "1"}, 1), ({"MPLB_STREAM_MODE": "0"}, 4),
+                                          ({"MPLB_STREAM_MODE": "2"}, 1), ({"MPLB_STREAM_CHUNK": "4096"}, 1)])
+def test_large_batch_modes(env, launches):
+    """The ways a large host batch can travel (the switches are read once per process, hence the child process):
+    watermark written by a 4-byte copy when stream memory operations are unavailable, copy-then-kernel in pieces, the
+    kernel pulling from mapped page-locked memory, many small pieces -- same verdicts, pinned or pageable input."""
+    _child("import torch, os\n"
+           "d = np.load(os.path.join(GOLDEN, 'scenes', 'twistycool.npz')); sc = SE3_SCENES['twistycool']\n"
+           "s = M.SE3RigidBodyScenario(d['env'], d['robot'], sc['goal'], sc['min'], sc['max'], 0.1)\n"
+           "want = np.load(os.path.join(GOLDEN, 'se3_verdicts.npz'))['twistycool_valid']\n"
+           "P = se3_poses(len(want), sc['min'], sc['max'], SEED)\n"
+           "big = np.concatenate([P] * 40)[:150000]; wbig = np.concatenate([want] * 40)[:150000]\n"
+           "s.stats(reset=True)\n"
+           "assert (s.check_states(big) == wbig).all(); st = s.stats()\n"
+           "assert st['launches'] == %d and st['stream_stalls'] == 0, st\n"
+           "pin = torch.from_numpy(big).pin_memory()\n"
+           "for _ in range(3): assert (s.check_states(pin.numpy()) == wbig).all()\n"
+           "assert s.stats()['stream_stalls'] == 0\nprint('ok')\n" % launches, env)
+
+
+def test_edge_spill_overflow():
+    """MPLB_SPILL_CAP=64: the descriptor lists between the passes of checkEdgesKernel overflow at once; the warps keep
+    what does not fit, the next pass reads only written slots -- verdicts as the oracle's."""
+    _child("import os\nfrom oracle import oracle_py as O\n"
+           "d = np.load(os.path.join(GOLDEN, 'scenes', 'cubicles.npz')); sc = SE3_SCENES['cubicles']\n"
+           "s = M.SE3RigidBodyScenario(d['env'], d['robot'], sc['goal'], sc['min'], sc['max'], 0.1)\n"
+           "P = se3_poses(40000, sc['min'], sc['max'], SEED)\n"
+           "A = P[s.check_states(P)][:3000]; B = se3_poses(len(A), sc['min'], sc['max'], SEED + 1)\n"
+           "want = O.SE3Oracle(d['env'], d['robot'], check_resolution=0.1).check_edges(A, B, O.BVH)\n"
+           "for _ in range(3): assert (s.check_edges(A, B) == want).all()\n"
+           "assert (s.check_edges(A[:700], B[:700]) == want[:700]).all()\nprint('ok')\n", {"MPLB_SPILL_CAP": "64"})
 
 
 def test_streamed_and_pipelined_sizes(scenes, golden):
