@@ -6,20 +6,27 @@ include/mpl/demo/se3_rigid_body_scenario.hpp:119-126) over one batch of 2^20 see
 sampled poses of the Alpha 1.5 puzzle scene (BASELINE.json configs[1]).
 
   value  device-resident poses -> verdict bytes, one checkStatesKernel launch per step
-  e2e    the same batch through the C-ABI call mplb_check_states with pinned HOST buffers
-         (H2D of the poses and D2H of the verdicts inside the timed region)
-  roofline   algorithmic bytes (28 + 1 + 120 n_bv + 72 n_tri per check, n_* from the oracle's
-         FCL-order traversal) / kernel time vs the measured HBM peak
-  cpu_baseline   the FP64 oracle (oracle/, FCL restatement, OpenMP over all host cores) on a
-         bounded sample of the same poses
-  extras (N = 1 only)   the other rows of the path, each next to the CPU path and with its mismatch count:
-         edge batches (config 3), nearest neighbour and k-NN + connect (config 4), Fetch states and edges
-         (config 5), and RRT time-to-solution with the GPU and with the CPU backend (the metric's second half)
+  e2e    the same batches through the C-ABI call mplb_check_states with pinned HOST buffers (H2D of the
+         poses and D2H of the verdicts inside the timed region), issued by two caller threads the way the
+         reference's OpenMP planner threads call isValid (prrt.hpp:140-152): one call's verdict read-back and
+         drain overlap the next call's input copy.  `e2e.single_caller` is the same with one caller.
+  e2e_device_sampled   the same metric when the poses never cross PCIe: mplb_sample_states_device (the same
+         Philox stream) + mplb_check_states_device, only the verdict bytes come back
+  roofline   HBM bytes the device's own traversal would need uncached (28 + 1 + 120 n_bv + 72 n_tri per
+         check, n_* = the device counters) / kernel time vs the measured HBM peak, next to the physical DRAM
+         traffic and the units that actually bind (ncu, profiles/)
+  cpu_baseline   the FP64 oracle (oracle/, FCL restatement, OpenMP over all host cores) on the same batch
+  extras (N = 1)   the other rows of the path, each next to the CPU path and with its mismatch count: a
+         Twistycool 2^20-pose line (the north-star target), edge batches (config 3), nearest neighbour and
+         k-NN + connect (config 4), Fetch states and edges (config 5), RRT time-to-solution
+  multi_gpu (N > 1)   configs 3-5 sharded over the ranks (edge batches balanced by step count, Fetch
+         configurations, Home k-NN + connect) and independent planner shards exchanging their solution
+         over NCCL (SolutionExchange), each with the whole-job throughput at this N
 
-`--impl reference` times that CPU path alone (the reference's own FCL path cannot be built:
-FCL/libccd/Eigen/nigh/assimp are absent).  Multi-GPU: one process per GPU under
-torchrun, BVHs replicated, each rank checks its own 2^20-pose shard of the stream (weak
-scaling, no data-path collective); time = max over ranks.
+`--impl reference` times the CPU path alone on the same 2^20-pose batches (the reference's own FCL path
+cannot be built: FCL/libccd/Eigen/nigh/assimp are absent).  Multi-GPU: one process per GPU
+under torchrun, BVHs replicated, each rank checks its own 2^20-pose shard of the stream (weak scaling, no
+data-path collective); time = max over ranks.
 """
 import argparse
 import json
@@ -62,13 +69,30 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(workload):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+def ncu_facts(workload):
+    """What the committed ncu capture of the dominant kernel says (profiles/traffic.json): DRAM bytes per launch and the
+    utilisation of the units that bind, or {}."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get(workload)
+            d = json.load(f)
+        v = d.get(workload)
+        return v if isinstance(v, dict) else ({"dram_bytes": v} if v else {})
     except Exception:
-        return None
+        return {}
+
+
+def hbm_roofline(kernel, bytes_per_unit, units, ms, note, facts=None):
+    """roofline block: algorithmic bytes / kernel time against the measured HBM peak."""
+    peak, how = measured_peak()
+    achieved = bytes_per_unit * units / (ms * 1e-3) / 1e9
+    facts = facts or {}
+    out = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+           "traffic": facts.get("dram_bytes"), "peak_source": how, "kernel": kernel, "kernel_ms": ms,
+           "algorithmic_bytes_per_unit": bytes_per_unit, "note": note}
+    if facts.get("binding_units"):
+        out["binding_units"] = facts["binding_units"]
+        out["ncu_summary"] = facts.get("summary")
+    return out
 
 
 class ClockSampler:
@@ -190,22 +214,74 @@ def cpu_baseline(env, robot, poses, threads, target_seconds=12.0):
             "valid_fraction": float(valid.mean())}, valid, n
 
 
-def extras(local_rank):
+def best(fn, reps=3):
+    ts = []
+    for _ in range(reps):
+        t = time.perf_counter(); r = fn(); ts.append(time.perf_counter() - t)
+    return min(ts), r
+
+
+def pose_batch_line(name, local_rank, cpu_seconds):
+    """A 2^20-pose batch of another scene measured like the contract line: device resident, through the C ABI, CPU."""
+    import torch
+    import mplambda_b200 as M
+    env, robot = load_scene(name)
+    sc = SE3_SCENES[name]
+    s = M.SE3RigidBodyScenario(env, robot, sc["goal"], sc["min"], sc["max"], 0.1, device=local_rank)
+    host = [se3_poses(N_POSES, sc["min"], sc["max"], SEED, start=r * N_POSES) for r in range(ROTATE)]
+    dev = [torch.from_numpy(h).cuda() for h in host]
+    pin = [torch.from_numpy(h).pin_memory() for h in host]
+    out = torch.empty(N_POSES, dtype=torch.uint8, device="cuda")
+    pout = torch.empty(N_POSES, dtype=torch.uint8).pin_memory()
+    st = torch.cuda.current_stream()
+    for k in range(2 * ROTATE):   # every pinned batch crosses the link before the timing (see main)
+        s.check_states_device(dev[k % ROTATE].data_ptr(), N_POSES, out.data_ptr(), st.cuda_stream)
+        s.check_states_ptr(pin[k % ROTATE].data_ptr(), N_POSES, pout.data_ptr())
+    torch.cuda.synchronize()
+    s.stats(reset=True)
+    steps = 8
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for k in range(steps):
+        s.check_states_device(dev[k % ROTATE].data_ptr(), N_POSES, out.data_ptr(), st.cuda_stream)
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    cnt = s.stats(reset=True)
+    t = time.perf_counter()
+    for k in range(steps):
+        s.check_states_ptr(pin[k % ROTATE].data_ptr(), N_POSES, pout.data_ptr())
+    e2e_ms = (time.perf_counter() - t) / steps * 1e3
+    cb, cpu_valid, _ = cpu_baseline(env, robot, host[0], 0, cpu_seconds)
+    got = s.check_states(host[0])
+    nbv, ntri = cnt["bv_tests"] / (steps * N_POSES), cnt["tri_tests"] / (steps * N_POSES)
+    line = {"metric": "collision checks/sec (pose batch)", "workload": "%s, 2^20 uniformly sampled poses per step" % name,
+            "value": N_POSES / (ms * 1e-3), "unit": "checks/s", "ms_per_step": ms,
+            "e2e": {"value": N_POSES / (e2e_ms * 1e-3), "unit": "checks/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": N_POSES * 56, "d2h_bytes_per_step": N_POSES,
+                    "api": "mplb_check_states (pinned host buffers, one caller)"},
+            "cpu_baseline": cb, "verdict_mismatches_vs_cpu": int((got != cpu_valid).sum()),
+            "device_vs_cpu": N_POSES / (ms * 1e-3) / cb["value"], "e2e_vs_cpu": N_POSES / (e2e_ms * 1e-3) / cb["value"],
+            "roofline": hbm_roofline("checkStatesKernel", 29 + 120 * nbv + 72 * ntri, N_POSES, ms,
+                                     "device traversal counts (%.1f box / %.2f triangle tests per check); the hierarchy is "
+                                     "cache resident, what binds is the SM (see the contract line)" % (nbv, ntri))}
+    s.close()
+    return line
+
+
+def extras(local_rank, cpu_seconds):
     """The other rows of the hot path, each timed end to end through the C ABI next to the
     oracle on the host cores: edge batches (config 3), nearest neighbour (config 4), Fetch (config 5).
     Reported under "extras"; the contract metric above is unaffected."""
+    import torch
     import mplambda_b200 as M
     from mplambda_b200.workload import FETCH_TASKS, fetch_configs, frame_from_option
     from oracle import oracle_py as O
     thr = host_threads()
     out = {}
 
-    def best(fn, reps=3):
-        ts = []
-        for _ in range(reps):
-            t = time.perf_counter(); r = fn(); ts.append(time.perf_counter() - t)
-        return min(ts), r
-
+    # ---- the north-star target line: Twistycool pose batches (BASELINE.json "Target")
+    out["poses_twistycool"] = pose_batch_line("twistycool", local_rank, min(cpu_seconds, 6.0))
     # ---- isValid(from,to) batches: 65,536 seeded edges (valid start, random end), resolution 0.1
     for name in ("cubicles", "apartment"):
         env, robot = load_scene(name)
@@ -215,17 +291,40 @@ def extras(local_rank):
         A = P[s.check_states(P)][:1 << 16]
         B = se3_poses(len(A), sc["min"], sc["max"], SEED + 1)
         s.check_edges(A[:512], B[:512])
+        s.check_edges(A, B)
+        s.stats(reset=True)
         dt, (v, checked) = best(lambda: s.check_edges(A, B, return_states_checked=True))
+        cnt = s.stats()
         steps = s.edge_steps(A, B)
+        # device resident: the three passes of checkEdgesKernel alone
+        dA, dB = torch.from_numpy(A).cuda(), torch.from_numpy(B).cuda()
+        dS = torch.from_numpy(steps.astype(np.int32)).cuda()
+        dV = torch.empty(len(A), dtype=torch.uint8, device="cuda")
+        cs = torch.cuda.current_stream()
+        for _ in range(2):
+            s.check_edges_device(dA.data_ptr(), dB.data_ptr(), dS.data_ptr(), len(A), int(steps.max()), dV.data_ptr(), cs.cuda_stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(cs)
+        for _ in range(5):
+            s.check_edges_device(dA.data_ptr(), dB.data_ptr(), dS.data_ptr(), len(A), int(steps.max()), dV.data_ptr(), cs.cuda_stream)
+        e1.record(cs)
+        torch.cuda.synchronize()
+        kms = e0.elapsed_time(e1) / 5
         orc = O.SE3Oracle(env, robot, check_resolution=0.1)
         m = 4096
         t = time.perf_counter(); w = orc.check_edges(A[:m], B[:m], O.BVH, threads=thr); dc = time.perf_counter() - t
+        per_state = 29 + (120 * cnt["bv_tests"] + 72 * cnt["tri_tests"]) / max(1, 3 * checked)
         out["edges_" + name] = {
             "metric": "edge validity checks/sec (isValid(from,to), resolution 0.1)", "value": len(A) / dt, "unit": "edges/s",
             "edges": int(len(A)), "interpolated_states": int(steps.sum()), "device_state_evaluations": int(checked),
-            "valid_fraction": float(v.mean()), "ms": dt * 1e3,
+            "valid_fraction": float(v.mean()), "ms": dt * 1e3, "device_resident_ms": kms,
+            "device_resident_value": len(A) / (kms * 1e-3),
             "cpu_baseline": {"value": m / dc, "unit": "edges/s", "cores": thr, "kind": "port", "sample": "first %d edges" % m},
-            "verdict_mismatches_vs_cpu": int((w != v[:m]).sum())}
+            "verdict_mismatches_vs_cpu": int((w != v[:m]).sum()),
+            "roofline": hbm_roofline("checkEdgesKernel (3 passes) + edgeConstKernel", per_state + 0.0, int(checked), kms,
+                                     "bytes of the %d states the device evaluates (%.2f %% of the interpolated states: the rest "
+                                     "is certified per interval); bound by instruction fetch and latency, not by HBM "
+                                     "(profiles/r1_edges_cubicles_v4_ncu_summary.txt)" % (checked, 100.0 * checked / steps.sum()))}
         s.close()
     # ---- nearest neighbour: 65,536 queries against 16,384 keys (SE3 metric), 1-NN and k-NN (k = 32)
     sc = SE3_SCENES["home"]
@@ -236,17 +335,36 @@ def extras(local_rank):
     nn.nearest(qs[:256])
     dt, (idx, dist) = best(lambda: nn.nearest(qs))
     dtk, _ = best(lambda: nn.knearest(qs[:1 << 14], 32), reps=2)
+    dq = torch.from_numpy(qs).cuda()
+    di = torch.empty(len(qs), dtype=torch.int64, device="cuda")
+    dd = torch.empty(len(qs), dtype=torch.float64, device="cuda")
+    cs = torch.cuda.current_stream()
+    nn.nearest_device(dq.data_ptr(), len(qs), di.data_ptr(), dd.data_ptr(), cs.cuda_stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(cs)
+    for _ in range(5):
+        nn.nearest_device(dq.data_ptr(), len(qs), di.data_ptr(), dd.data_ptr(), cs.cuda_stream)
+    e1.record(cs)
+    torch.cuda.synchronize()
+    nms = e0.elapsed_time(e1) / 5
     m = 2048
     t = time.perf_counter(); widx, wdist = O.nn_nearest(keys, qs[:m], threads=thr); dc = time.perf_counter() - t
     out["nn_home"] = {"metric": "nearest-neighbour queries/sec (brute force, SE3 metric)", "value": len(qs) / dt,
                       "unit": "queries/s", "keys": int(len(keys)), "queries": int(len(qs)), "ms": dt * 1e3,
-                      "knn32_queries_per_s": (1 << 14) / dtk,
+                      "device_resident_ms": nms, "knn32_queries_per_s": (1 << 14) / dtk,
                       "cpu_baseline": {"value": m / dc, "unit": "queries/s", "cores": thr, "kind": "port",
                                        "sample": "first %d queries, brute force" % m},
                       "index_mismatches_vs_cpu": int((widx != idx[:m]).sum()),
-                      "distance_mismatches_vs_cpu": int((wdist != dist[:m]).sum())}
+                      "distance_mismatches_vs_cpu": int((wdist != dist[:m]).sum()),
+                      "roofline": hbm_roofline("nnBound32Kernel + nnThresholdKernel + nnRefineKernel + nnMergeKernel",
+                                               28.0 * len(keys) / 128 + 56 + 16, len(qs), nms,
+                                               "key tiles are staged in shared memory and shared by the 128 queries of a CTA: n x "
+                                               "28 B / 128 of key reads per query + the query in + (index, distance) out; the scan "
+                                               "is bound by FP32 issue (%.0f G pair distances/s), not by HBM"
+                                               % (len(qs) * len(keys) / (nms * 1e-3) / 1e9))}
     # ---- config 4: the addNodeNear pattern batched (pcforest.hpp:512-566) on Home: k-NN of each new node in the
-    #      tree, then the motion from the node to each of its k neighbours
+    #      tree, then the motion from the node to each of its k neighbours.  Only indices move: the new nodes go up
+    #      once (56 B each), the neighbours are named by index into the tree's device-resident keys.
     env, robot = load_scene("home")
     s = M.SE3RigidBodyScenario(env, robot, sc["goal"], sc["min"], sc["max"], 0.1, device=local_rank)
     tree = keys[s.check_states(keys)]
@@ -254,13 +372,33 @@ def extras(local_rank):
     k = int(math.ceil(math.e * (7.0 / 6.0) * math.log(len(tree) + 1)))
     nn2 = M.Nigh(M.nn.SE3, device=local_rank)
     nn2.insert(tree)
+    h_new = torch.from_numpy(new).pin_memory()
+    d_new = torch.empty((len(new), 7), dtype=torch.float64, device="cuda")
+    d_i = torch.empty((len(new), k), dtype=torch.int64, device="cuda")
+    d_d = torch.empty((len(new), k), dtype=torch.float64, device="cuda")
+    d_v = torch.empty(len(new) * k, dtype=torch.uint8, device="cuda")
+    h_i = torch.empty((len(new), k), dtype=torch.int64).pin_memory()
+    h_v = torch.empty(len(new) * k, dtype=torch.uint8).pin_memory()
 
-    def near_and_connect(q):
-        ki, _ = nn2.knearest(q, k)
-        frm = np.repeat(q, k, axis=0)
-        return ki, s.check_edges(frm, tree[ki.reshape(-1)])
-    near_and_connect(new[:64])
-    dt, (ki, ev) = best(lambda: near_and_connect(new), reps=2)
+    def near_and_connect():
+        d_new.copy_(h_new, non_blocking=True)
+        nn2.knearest_device(d_new.data_ptr(), len(new), k, d_i.data_ptr(), d_d.data_ptr(), cs.cuda_stream)
+        s.check_edges_indexed_device(d_new.data_ptr(), len(new), None, nn2.keys_device(), nn2.size(), d_i.data_ptr(),
+                                     len(new) * k, d_v.data_ptr(), from_div=k, stream=cs.cuda_stream)
+        h_i.copy_(d_i, non_blocking=True)
+        h_v.copy_(d_v, non_blocking=True)
+        cs.synchronize()
+        return h_i.numpy(), h_v.numpy().astype(bool)
+
+    def near_and_connect_host():   # round 1's path: neighbours to the host, both end states of every motion back up
+        ki_, _ = nn2.knearest(new, k)
+        return ki_, s.check_edges(np.repeat(new, k, axis=0), tree[ki_.reshape(-1)])
+    near_and_connect()
+    s.stats(reset=True)
+    dt, (ki, ev) = best(near_and_connect, reps=3)
+    amb = s.stats()["ambiguous_steps"]
+    near_and_connect_host()
+    dth, (kih, evh) = best(near_and_connect_host, reps=2)
     m = 48
     orc = O.SE3Oracle(env, robot, check_resolution=0.1)
     t = time.perf_counter()
@@ -271,6 +409,9 @@ def extras(local_rank):
         "metric": "new nodes/sec through k-NN + k motion checks (PCForest addNodeNear pattern)", "value": len(new) / dt,
         "unit": "nodes/s", "tree_nodes": int(len(tree)), "new_nodes": int(len(new)), "k": k, "edges": int(len(new) * k),
         "edge_valid_fraction": float(ev.mean()), "ms": dt * 1e3,
+        "api": "mplb_nn_knearest_device + mplb_check_edges_indexed_device; H2D 56 B per new node, D2H k x 9 B per node",
+        "host_staged_ms": dth * 1e3, "host_staged_value": len(new) / dth,
+        "ambiguous_step_counts": int(amb), "verdicts_equal_host_staged_path": bool((ev == evh).all() and (ki == kih).all()),
         "cpu_baseline": {"value": m / dc, "unit": "nodes/s", "cores": thr, "kind": "port", "sample": "first %d new nodes" % m},
         "neighbour_mismatches_vs_cpu": int((wi != ki[:m]).sum()), "verdict_mismatches_vs_cpu": int((wv != ev[:m * k]).sum())}
     s.close()
@@ -280,6 +421,7 @@ def extras(local_rank):
     f = M.FetchScenario(frame, env, checkResolution=0.01, device=local_rank)
     Q = fetch_configs(1 << 18, SEED)
     f.check_states(Q[:1024])
+    f.check_states(Q)
     dt, v = best(lambda: f.check_states(Q))
     m = 1 << 15
     t = time.perf_counter(); w = O.FetchOracle(env, frame, 0.01).check_states(Q[:m], threads=thr); dc = time.perf_counter() - t
@@ -287,28 +429,41 @@ def extras(local_rank):
                            "unit": "checks/s", "configs": int(len(Q)), "valid_fraction": float(v.mean()), "ms": dt * 1e3,
                            "cpu_baseline": {"value": m / dc, "unit": "checks/s", "cores": thr, "kind": "port",
                                             "sample": "first %d configurations" % m},
-                           "verdict_mismatches_vs_cpu": int((w != v[:m]).sum())}
+                           "verdict_mismatches_vs_cpu": int((w != v[:m]).sum()),
+                           "roofline": hbm_roofline("fetchFkKernel .. fetchLeafKernel (through mplb_check_states)",
+                                                    64 + 1 + 12 * 96, len(Q), dt * 1e3,
+                                                    "64 B in, 1 B out and the 12 link frames (96 B each) written and read once per "
+                                                    "configuration; the time is end to end (copies included); the kernels are FP64 "
+                                                    "MPR at 9 of 32 lanes (profiles/r1_fetch_states_ncu_summary.txt), nowhere near HBM")}
     # ---- the metric's second half: RRT time-to-solution, the same batch-issuing planner (mplambda_b200/planner.py) with the
-    #      GPU scenario + GPU nearest neighbours and with the CPU path (oracle on all host cores) as its backend
+    #      GPU scenario + GPU nearest neighbours and with the CPU path (oracle on all host cores) as its backend; and the
+    #      device-resident loop (mplb_rrt_*)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from cpu_backend import CpuNN, CpuScenario
-    from mplambda_b200.planner import BatchedRRT
+    from mplambda_b200.planner import BatchedRRT, DeviceRRT
     for name in ("cubicles", "twistycool"):
         env_, robot_ = load_scene(name)
         sc_ = SE3_SCENES[name]
         g = M.SE3RigidBodyScenario(env_, robot_, sc_["goal"], sc_["min"], sc_["max"], 0.1, device=local_rank)
-        tg, tc, same = [], [], True
+        tg, tc, td, same = [], [], [], True
         for seed in (1, 2, 3):
             rg = BatchedRRT(g, M.Nigh(M.nn.SE3, device=local_rank), sc_["start"], batch=2048, seed=seed)
             pg = rg.solve(time_limit=30)
             rc = BatchedRRT(CpuScenario(env_, robot_, sc_, thr), CpuNN(thr), sc_["start"], batch=2048, seed=seed)
             pc = rc.solve(time_limit=120)
+            rd = DeviceRRT(g, M.Nigh(M.nn.SE3, device=local_rank), sc_["start"], batch=2048, seed=seed)
+            pd = rd.solve(time_limit=30)
             tg.append(rg.stats["seconds"]); tc.append(rc.stats["seconds"])
+            if pd is not None:
+                td.append(rd.stats["seconds"])
             same = same and pg is not None and pc is not None and rg.n == rc.n and np.array_equal(pg, pc)
+            rd.close()
         out["rrt_" + name] = {"metric": "RRT time-to-solution (batch-issuing PRRT loop, batch 2048, median of 3 seeds)",
                               "value": float(np.median(tg)), "unit": "s", "higher_is_better": False,
+                              "device_resident_loop_s": float(np.median(td)) if td else None,
                               "cpu_baseline": {"value": float(np.median(tc)), "unit": "s", "cores": thr, "kind": "port",
-                                               "sample": "the same planner, seeds and batches on the oracle"},
+                                               "sample": "the same batch-issuing planner (this repo's BatchedRRT, not the "
+                                                         "reference's PRRT), seeds and batches, on the oracle"},
                               "identical_trees_and_paths": bool(same)}
         g.close()
     # ---- config 5 edges: 16,384 motions between random configurations (valid start), resolution 0.01
@@ -326,7 +481,153 @@ def extras(local_rank):
     return out
 
 
+def multi_gpu_extras(rank, world, local_rank):
+    """BASELINE configs 3-5 at N > 1: fixed batches split over the ranks (strong scaling; the scene is replicated, a
+    rank checks its contiguous share through the C ABI, no collective on the check path), and independent planner
+    shards that exchange their solution over NCCL.  Times are max over ranks between two barriers."""
+    import torch
+    import torch.distributed as dist
+    import mplambda_b200 as M
+    from mplambda_b200 import sharding
+    from mplambda_b200.planner import BatchedRRT, solve_sharded
+    from mplambda_b200.workload import FETCH_TASKS, fetch_configs, frame_from_option
+    out = {}
+
+    def timed(fn, reps=3):
+        ts = []
+        for _ in range(reps):
+            dist.barrier(); torch.cuda.synchronize()
+            t = time.perf_counter(); r = fn(); torch.cuda.synchronize(); dt = time.perf_counter() - t
+            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ts.append(float(tt.item()))
+        return min(ts), r
+
+    def total(x):
+        tt = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt)
+        return float(tt.item())
+
+    # ---- config 3: 65,536-edge batches, cut where the summed step counts balance
+    for name in ("cubicles", "apartment"):
+        env, robot = load_scene(name)
+        sc = SE3_SCENES[name]
+        s = M.SE3RigidBodyScenario(env, robot, sc["goal"], sc["min"], sc["max"], 0.1, device=local_rank)
+        P = se3_poses(8 << 16, sc["min"], sc["max"], SEED)
+        A = P[s.check_states(P)][:1 << 16]
+        B = se3_poses(len(A), sc["min"], sc["max"], SEED + 1)
+        lo, hi = sharding.balanced_edge_bounds(s.edge_steps(A, B), world)[rank]
+        a, b = np.ascontiguousarray(A[lo:hi]), np.ascontiguousarray(B[lo:hi])
+        s.check_edges(a, b)
+        dt, v = timed(lambda: s.check_edges(a, b))
+        out["edges_" + name] = {"metric": "edge validity checks/sec (isValid(from,to), resolution 0.1)", "unit": "edges/s",
+                                "value": len(A) / dt, "edges": int(len(A)), "ms": dt * 1e3, "scaling": "strong",
+                                "valid_fraction": total(v.sum()) / len(A),
+                                "sharding": "contiguous shares balanced by step count (balanced_edge_bounds)"}
+        s.close()
+    # ---- config 4: Home, k-NN of the new nodes in the replicated tree + the k motions per node; new nodes split by rank
+    sc = SE3_SCENES["home"]
+    env, robot = load_scene("home")
+    s = M.SE3RigidBodyScenario(env, robot, sc["goal"], sc["min"], sc["max"], 0.1, device=local_rank)
+    keys = se3_poses(1 << 14, sc["min"], sc["max"], SEED)
+    qs = se3_poses(1 << 16, sc["min"], sc["max"], SEED + 2)
+    tree = keys[s.check_states(keys)]
+    allnew = qs[s.check_states(qs)][:32768]
+    lo, hi = sharding.shard_bounds(len(allnew), rank, world)
+    new = np.ascontiguousarray(allnew[lo:hi])
+    k = int(math.ceil(math.e * (7.0 / 6.0) * math.log(len(tree) + 1)))
+    nn = M.Nigh(M.nn.SE3, device=local_rank)
+    nn.insert(tree)
+    cs = torch.cuda.current_stream()
+    h_new = torch.from_numpy(new).pin_memory()
+    d_new = torch.empty((len(new), 7), dtype=torch.float64, device="cuda")
+    d_i = torch.empty((len(new), k), dtype=torch.int64, device="cuda")
+    d_d = torch.empty((len(new), k), dtype=torch.float64, device="cuda")
+    d_v = torch.empty(len(new) * k, dtype=torch.uint8, device="cuda")
+    h_i = torch.empty((len(new), k), dtype=torch.int64).pin_memory()
+    h_v = torch.empty(len(new) * k, dtype=torch.uint8).pin_memory()
+
+    def near_and_connect():
+        d_new.copy_(h_new, non_blocking=True)
+        nn.knearest_device(d_new.data_ptr(), len(new), k, d_i.data_ptr(), d_d.data_ptr(), cs.cuda_stream)
+        s.check_edges_indexed_device(d_new.data_ptr(), len(new), None, nn.keys_device(), nn.size(), d_i.data_ptr(),
+                                     len(new) * k, d_v.data_ptr(), from_div=k, stream=cs.cuda_stream)
+        h_i.copy_(d_i, non_blocking=True)
+        h_v.copy_(d_v, non_blocking=True)
+        cs.synchronize()
+        return h_v.numpy().astype(bool)
+    near_and_connect()
+    dt, ev = timed(near_and_connect)
+    out["knn_connect_home"] = {"metric": "new nodes/sec through k-NN + k motion checks (PCForest addNodeNear pattern)",
+                               "unit": "nodes/s", "value": len(allnew) / dt, "new_nodes": int(len(allnew)), "k": k,
+                               "tree_nodes": int(len(tree)), "ms": dt * 1e3, "scaling": "strong",
+                               "edge_valid_fraction": total(ev.sum()) / (len(allnew) * k)}
+    s.close()
+    # ---- config 5: Fetch, 2^20 configurations split by rank
+    env = np.load(os.path.join(ROOT, "tests", "golden", "scenes", "autolab.npz"))["env"]
+    frame = frame_from_option(FETCH_TASKS["fetch_task_001"]["env_frame"])
+    f = M.FetchScenario(frame, env, checkResolution=0.01, device=local_rank)
+    nq = 1 << 20
+    lo, hi = sharding.shard_bounds(nq, rank, world)
+    Q = fetch_configs(hi - lo, SEED, start=lo)
+    f.check_states(Q)
+    dt, v = timed(lambda: f.check_states(Q))
+    out["fetch_states"] = {"metric": "Fetch validity checks/sec (FK + 24 MPR pairs + 12 shapes vs mesh)", "unit": "checks/s",
+                           "value": nq / dt, "configs": nq, "ms": dt * 1e3, "scaling": "strong",
+                           "valid_fraction": total(v.sum()) / nq}
+    f.close()
+    # ---- planner shards (the reference's lambdas, mpl_coordinator.cpp:591-600): one RRT per rank, seeded per rank, the
+    #      Done flag and the winning path travel over NCCL (SolutionExchange) instead of the coordinator's TCP relays
+    name = "twistycool"
+    env_, robot_ = load_scene(name)
+    sc_ = SE3_SCENES[name]
+    g = M.SE3RigidBodyScenario(env_, robot_, sc_["goal"], sc_["min"], sc_["max"], 0.1, device=local_rank)
+    ex = sharding.SolutionExchange(state_dim=7)
+    spent = {"done_polls": 0, "done_s": 0.0, "publish_s": 0.0}
+    any_done, publish = ex.any_done, ex.publish
+
+    def any_done_timed(flag):
+        t = time.perf_counter(); r = any_done(flag); spent["done_s"] += time.perf_counter() - t; spent["done_polls"] += 1
+        return r
+
+    def publish_timed(cost, path):
+        t = time.perf_counter(); r = publish(cost, path); spent["publish_s"] += time.perf_counter() - t
+        return r
+    ex.any_done, ex.publish = any_done_timed, publish_timed
+    ex.any_done(False)   # first collective of the group outside the timing
+    spent.update(done_polls=0, done_s=0.0)
+    secs = []
+    for seed in (1, 2, 3):
+        dist.barrier()
+        t = time.perf_counter()
+        cost, who, path, rrt = solve_sharded(
+            lambda r: BatchedRRT(g, M.Nigh(M.nn.SE3, device=local_rank), sc_["start"], batch=2048, seed=1000 * seed + r),
+            ex, time_limit=30, sync_every=1)
+        secs.append(time.perf_counter() - t)
+    ok = path is not None and bool(g.check_edges(path[:-1], path[1:]).all()) and bool(g.isGoal(path[-1]))
+    out["sharded_rrt_" + name] = {"metric": "time to first solution, one RRT shard per GPU (seeded per rank), Done flag and "
+                                            "winning path exchanged over NCCL", "unit": "s", "higher_is_better": False,
+                                  "value": float(np.median(secs)), "shards": world, "last_winner_rank": int(who),
+                                  "last_path_waypoints": 0 if path is None else int(len(path)), "last_path_valid": ok,
+                                  "exchange_us_per_done_poll": 1e6 * spent["done_s"] / max(1, spent["done_polls"]),
+                                  "exchange_us_per_publish": 1e6 * spent["publish_s"] / 3,
+                                  "note": "all_reduce(MAX) of one int32 after every planner iteration; all_gather of (cost, "
+                                          "length) + broadcast of the winner's waypoints once per solve"}
+    g.close()
+    return out
+
+
+def contract_config(workload, env, robot):
+    return {"workload": "%s SE(3) rigid body, 2^20 uniformly sampled poses per GPU per step "
+                        "(randomize.hpp distribution, Philox seed 0x6d706c62)" % workload,
+            "env_tris": int(len(env)), "robot_tris": int(len(robot)), "poses_per_step_per_gpu": N_POSES,
+            "l2": "inputs rotate over %d distinct 58.7 MB pose batches (> 126 MB L2); the BVH itself is "
+                  "L2/L1 resident by design" % ROTATE,
+            "sharding": "pose stream split by rank, BVH replicated, no collective"}
+
+
 def run_reference(args, rank, world):
+    """The CPU path on the contract workload: the same 2^20-pose batches, one batch per step, all host cores."""
     if rank != 0:
         return
     from oracle import oracle_py as O
@@ -337,20 +638,24 @@ def run_reference(args, rank, world):
     sample = args.ref_sample
     batches = [se3_poses(sample, sc["min"], sc["max"], SEED, start=r * N_POSES) for r in range(ROTATE)]
     for w in range(args.warmup):
-        orc.check_states(batches[w % ROTATE][:min(sample, 16384)], O.BVH, threads=threads)
+        orc.check_states(batches[w % ROTATE][:min(sample, 65536)], O.BVH, threads=threads)
     t = time.perf_counter()
     for k in range(args.steps):
         orc.check_states(batches[k % ROTATE], O.BVH, threads=threads)
     dt = time.perf_counter() - t
     v = args.steps * sample / dt
+    cfg = contract_config(args.workload, env, robot)
+    if sample != N_POSES:
+        cfg["workload"] += " [--ref-sample: %d-pose sample of each step]" % sample
     print(json.dumps({
         "impl": "reference", "metric": "collision checks/sec (pose batch)", "value": v, "unit": "checks/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s SE(3) pose batch, %d-pose sample of the 2^20-pose step" % (args.workload, sample)},
+        "config": cfg,
         "cpu_baseline": {"value": v, "unit": "checks/s", "cores": threads, "kind": "port",
-                         "sample": "%d poses per step, oracle O2 (FP64 restatement of FCL's OBB traversal + "
-                                   "17-axis tri-tri; FCL itself is not installable here)" % sample},
+                         "sample": "%d poses per step (the whole step), oracle O2 (FP64 restatement of FCL's OBB traversal + "
+                                   "17-axis tri-tri; FCL itself is not installable here); rank 0's host cores only, whatever N"
+                                   % sample},
         "e2e": {"value": v, "unit": "checks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
 
@@ -362,7 +667,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mplb", choices=["mplb", "reference"])
     ap.add_argument("--workload", default="alpha15", choices=sorted(SE3_SCENES))
-    ap.add_argument("--ref-sample", type=int, default=1 << 17)
+    ap.add_argument("--ref-sample", type=int, default=N_POSES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-extras", action="store_true")
@@ -377,6 +682,12 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+
+    if world > 1:
+        # torchrun exports OMP_NUM_THREADS=1; libmplb's host side (edge step planning, copies out of pageable memory)
+        # uses OpenMP: give every rank its share of the host cores (set before libgomp is loaded)
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        os.environ["OMP_NUM_THREADS"] = str(max(1, host_threads() // max(1, local_world)))
 
     import torch
     import torch.distributed as dist
@@ -399,7 +710,7 @@ def main():
     out = torch.empty(N_POSES, dtype=torch.uint8, device="cuda")
     with HostMemoryNearGpu(local_rank, not args.no_numa) as placement:
         pinned = [torch.from_numpy(h).pin_memory() for h in host]
-        pinned_out = torch.empty(N_POSES, dtype=torch.uint8).pin_memory()
+        pinned_out = [torch.empty(N_POSES, dtype=torch.uint8).pin_memory() for _ in range(2)]
     if world > 1:
         print("rank %d: %s" % (rank, placement.note), file=sys.stderr)
     stream = torch.cuda.current_stream()
@@ -412,8 +723,25 @@ def main():
     def step_device(k):
         scen.check_states_device(dev[k % ROTATE].data_ptr(), N_POSES, out.data_ptr(), stream.cuda_stream)
 
-    def step_e2e(k):
-        scen.check_states_ptr(pinned[k % ROTATE].data_ptr(), N_POSES, pinned_out.data_ptr())
+    def step_e2e(k, slot=0):
+        scen.check_states_ptr(pinned[k % ROTATE].data_ptr(), N_POSES, pinned_out[slot].data_ptr())
+
+    def steps_e2e_two_callers(n):
+        """n calls issued by two host threads (ctypes releases the GIL): step k goes to caller k % 2."""
+        def caller(t):
+            for k in range(t, n, 2):
+                step_e2e(k, t)
+        th = [threading.Thread(target=caller, args=(t,)) for t in range(2)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+
+    def step_sampled(k):
+        # the poses of batch k % ROTATE drawn on the device (the same Philox stream as `host`), checked, verdicts back
+        scen.sample_states_device(SEED, base + (k % ROTATE) * N_POSES, N_POSES, sampled.data_ptr(), stream.cuda_stream)
+        scen.check_states_device(sampled.data_ptr(), N_POSES, out.data_ptr(), stream.cuda_stream)
+        pinned_out[0].copy_(out, non_blocking=True)
+        stream.synchronize()
+    sampled = torch.empty((N_POSES, 7), dtype=torch.float64, device="cuda")
 
     # setup, not a step: every pinned batch crosses the link once so that none of them meets the DMA engine for the
     # first time inside the timed region (the first transfers from a fresh pinned allocation run at ~70 % speed)
@@ -425,6 +753,8 @@ def main():
     for k in range(args.warmup):
         step_device(k)
         step_e2e(k)
+        step_sampled(k)
+    steps_e2e_two_callers(4)
     barrier()
     scen.stats(reset=True)
 
@@ -441,14 +771,28 @@ def main():
     total_ms = ev[0].elapsed_time(ev[-1])
     kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     st = scen.stats(reset=True)
-    # ---- end to end through the C ABI with host buffers
+    # ---- end to end through the C ABI with host buffers: two callers, then one
+    barrier()
+    t0 = time.perf_counter()
+    steps_e2e_two_callers(args.steps)
+    barrier()
+    e2e_s = time.perf_counter() - t0
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
         step_e2e(k)
     barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e1_s = time.perf_counter() - t0
+    st_e2e = scen.stats(reset=True)
+    # ---- the poses never cross PCIe: sampled on the device, verdicts back
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        step_sampled(k)
+    barrier()
+    samp_s = time.perf_counter() - t0
     clocks = sampler.stop()
+    same_as_host = bool((pinned_out[0].numpy() == scen.check_states(host[(args.steps - 1) % ROTATE]).astype(np.uint8)).all())
     # context for the e2e number: what the host link itself sustains for this step's input
     hev0, hev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scratch = torch.empty_like(dev[0])
@@ -462,10 +806,21 @@ def main():
     h2d_ms = hev0.elapsed_time(hev1) / 4
     valid_frac = float(out.float().mean().item())
 
-    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    t = torch.tensor([total_ms, e2e_s * 1e3, e2e1_s * 1e3, samp_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = t.tolist()
+    total_ms, e2e_ms, e2e1_ms, samp_ms = t.tolist()
+
+    multi = None
+    if world > 1 and not args.no_extras:
+        try:
+            multi = multi_gpu_extras(rank, world, local_rank)
+        except Exception as e:  # the contract line must survive an extras failure
+            multi = {"error": repr(e)}
+            try:
+                dist.barrier()
+            except Exception:
+                pass
 
     if rank == 0:
         units = args.steps * N_POSES * world
@@ -475,49 +830,56 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
             "data": "synthetic",
-            "config": {"workload": "%s SE(3) rigid body, 2^20 uniformly sampled poses per GPU per step "
-                                   "(randomize.hpp distribution, Philox seed 0x6d706c62)" % args.workload,
-                       "env_tris": int(len(env)), "robot_tris": int(len(robot)), "poses_per_step_per_gpu": N_POSES,
-                       "l2": "inputs rotate over %d distinct 58.7 MB pose batches (> 126 MB L2); the BVH itself is "
-                             "L2/L1 resident by design" % ROTATE,
-                       "sharding": "pose stream split by rank, BVH replicated, no collective"},
+            "config": contract_config(args.workload, env, robot),
             "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "checks/s", "h2d_bytes_per_step": N_POSES * 56,
                     "d2h_bytes_per_step": N_POSES, "ms_per_step": e2e_ms / args.steps,
-                    "api": "mplb_check_states (pinned host buffers)", "host_memory": placement.note,
+                    "api": "mplb_check_states (pinned host buffers), calls issued by two host threads per GPU like the "
+                           "reference's OpenMP planner threads (prrt.hpp:140-152); every call copies its 2^20 poses in "
+                           "and its verdicts out",
+                    "single_caller": {"value": units / (e2e1_ms * 1e-3), "ms_per_step": e2e1_ms / args.steps},
+                    "host_memory": placement.note,
                     "h2d_copy_alone_ms": h2d_ms, "h2d_gbs": N_POSES * 56 / (h2d_ms * 1e-3) / 1e9,
-                    "note": "the 56 B/pose input copy is the longer leg; the kernel runs underneath it and picks states up as they land"},
+                    "note": "the 56 B/pose input copy is the longer leg; the kernel runs underneath it and picks states up "
+                            "as the copy's watermark advances"},
+            "e2e_device_sampled": {"value": units / (samp_ms * 1e-3), "unit": "checks/s", "ms_per_step": samp_ms / args.steps,
+                                   "h2d_bytes_per_step": 0, "d2h_bytes_per_step": N_POSES,
+                                   "api": "mplb_sample_states_device + mplb_check_states_device + verdict read-back: the "
+                                          "planner's samples are drawn on the device (same Philox stream), only verdicts "
+                                          "cross PCIe", "verdicts_equal_host_batch": same_as_host},
             "gpu_launches": int(st["launches"]),
             "clocks": clocks,
             "valid_fraction": valid_frac,
             "device_counters_per_check": {"bv_tests": st["bv_tests"] / (args.steps * N_POSES),
                                           "tri_tests": st["tri_tests"] / (args.steps * N_POSES),
                                           "exact_fp64_tests": st["exact_tests"] / (args.steps * N_POSES)},
+            "stream_stalls": int(st_e2e["stream_stalls"]),
         }
-        peak, how = measured_peak()
-        nbv = ntri = None
+        nbv = st["bv_tests"] / (args.steps * N_POSES)
+        ntri = st["tri_tests"] / (args.steps * N_POSES)
         if not args.no_cpu_baseline:
             cb, cpu_valid, ncpu = cpu_baseline(env, robot, host[0], 0, args.cpu_seconds)
             got = scen.check_states(host[0][:ncpu])
             cb["verdict_mismatches_vs_gpu"] = int((got != cpu_valid).sum())
-            nbv, ntri = cb["n_bv_per_check"], cb["n_tri_per_check"]
             line["cpu_baseline"] = cb
-        else:
-            nbv, ntri = st["bv_tests"] / (args.steps * N_POSES), st["tri_tests"] / (args.steps * N_POSES)
-        bytes_per_check = 28 + 1 + 120 * nbv + 72 * ntri
         kms = float(np.mean(kernel_ms))
-        achieved = bytes_per_check * N_POSES / (kms * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                            "traffic": ncu_traffic(args.workload), "peak_source": how,
-                            "kernel": "checkStatesKernel", "kernel_ms": kms,
-                            "algorithmic_bytes_per_check": bytes_per_check,
-                            "note": "algorithmic bytes follow the reference's (FCL-order) traversal counts; the "
-                                    "hierarchy is cache resident (ncu: 64 MB of DRAM traffic per launch, L2 hit rate 97 %), so the fraction can exceed 1; "
-                                    "the units that bind are the L1 data pipe (63 %) and the issue slots (55 %), profiles/r1_states_alpha15_v3_ncu_summary.txt"}
+        rl = hbm_roofline("checkStatesKernel", 28 + 1 + 120 * nbv + 72 * ntri, N_POSES, kms,
+                          "algorithmic bytes = what the device's own traversal reads (%.1f box tests x 120 B, %.2f triangle "
+                          "tests x 72 B per check) if nothing were cached; the hierarchy is L1/L2 resident, DRAM sees the poses "
+                          "in and the verdicts out (`traffic`), so the kernel is bound by the SM, not by HBM: see "
+                          "binding_units" % (nbv, ntri), ncu_facts(args.workload))
+        if "cpu_baseline" in line:
+            cbv = line["cpu_baseline"]
+            rl["frac_with_reference_order_counts"] = (29 + 120 * cbv["n_bv_per_check"] + 72 * cbv["n_tri_per_check"]) * N_POSES \
+                / (kms * 1e-3) / 1e9 / rl["peak"]
+        line["roofline"] = rl
         if world == 1 and not args.no_extras and not args.no_cpu_baseline:
             try:
-                line["extras"] = extras(local_rank)
+                line["extras"] = extras(local_rank, args.cpu_seconds)
             except Exception as e:  # the contract line must survive an extras failure
-                line["extras"] = {"error": repr(e)}
+                import traceback
+                line["extras"] = {"error": repr(e), "where": traceback.format_exc()[-600:]}
+        if multi is not None:
+            line["multi_gpu"] = multi
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

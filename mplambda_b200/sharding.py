@@ -64,31 +64,31 @@ class SolutionExchange:
 
     def __init__(self, state_dim, max_waypoints=256, group=None):
         self.group = group
-        self.dim, self.cap = state_dim, max_waypoints
+        self.dim, self.cap = state_dim, max_waypoints   # cap: kept for callers; paths of any length are relayed
         self.dev = _device_for(group)
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
 
     def publish(self, cost, path):
         """cost: float (inf when this rank has no solution); path: [m, dim] array or None.
-        -> (best_cost, best_rank, best_path or None), identical on every rank."""
-        mine = torch.tensor([float(cost)], dtype=torch.float64, device=self.dev)
-        costs = [torch.empty_like(mine) for _ in range(self.world)]
-        dist.all_gather(costs, mine, group=self.group)
-        costs = torch.cat(costs).cpu().numpy()
+        -> (best_cost, best_rank, best_path or None), identical on every rank.  Costs and path lengths travel
+        together, so the broadcast buffer is sized from the winner's length on every rank: no rank can fail
+        (and leave the others waiting in the broadcast) because of a long path."""
+        p = None if path is None else np.asarray(path, dtype=np.float64).reshape(-1, self.dim)
+        mine = torch.tensor([float(cost), 0.0 if p is None else float(len(p))], dtype=torch.float64, device=self.dev)
+        both = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(both, mine, group=self.group)
+        both = torch.stack(both).cpu().numpy()
+        costs = both[:, 0]
         if not np.isfinite(costs).any():
             return float("inf"), -1, None
         best = int(np.argmin(costs))          # first minimum = lowest rank on ties
-        buf = torch.zeros(1 + self.cap * self.dim, dtype=torch.float64, device=self.dev)
-        if self.rank == best:
-            p = np.asarray(path, dtype=np.float64).reshape(-1, self.dim)
-            if len(p) > self.cap:
-                raise ValueError("path has %d waypoints, capacity is %d" % (len(p), self.cap))
-            buf[0] = len(p)
-            buf[1:1 + p.size] = torch.from_numpy(p.reshape(-1)).to(self.dev)
+        m = int(both[best, 1])
+        buf = torch.zeros(max(1, m * self.dim), dtype=torch.float64, device=self.dev)
+        if self.rank == best and m:
+            buf[:p.size] = torch.from_numpy(p.reshape(-1)).to(self.dev)
         src = best if self.group is None else dist.get_global_rank(self.group, best)
         dist.broadcast(buf, src=src, group=self.group)
-        m = int(buf[0].item())
-        return float(costs[best]), best, buf[1:1 + m * self.dim].cpu().numpy().reshape(m, self.dim)
+        return float(costs[best]), best, buf[:m * self.dim].cpu().numpy().reshape(m, self.dim)
 
     def any_done(self, done):
         flag = torch.tensor([1 if done else 0], dtype=torch.int32, device=self.dev)

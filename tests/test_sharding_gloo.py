@@ -66,6 +66,10 @@ def _worker(rank, world, port, q):
         assert who == 0 and best.shape == (3, 7)
         cost, who, best = ex.publish(float("inf") if rank == 0 else 7.5, path)
         assert (cost, who) == (7.5, 1)
+        # a path longer than max_waypoints is relayed, not an error on the winner with the others stuck in the broadcast
+        long = np.arange(40 * 7, dtype=np.float64).reshape(40, 7)
+        cost, who, best = ex.publish(1.0 if rank == 1 else 2.0, long)
+        assert who == 1 and best.shape == (40, 7) and (best == long).all()
         # 3. done flag (replaces the coordinator's Done broadcast)
         assert ex.any_done(False) is False
         assert ex.any_done(rank == 1) is True
