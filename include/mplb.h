@@ -50,6 +50,14 @@ int mplb_mesh_load_collada(const char *path, int shift_to_center, int identity_r
                            double **tris, size_t *ntris, double center[3]);
 void mplb_free(void *p);
 
+/* On-disk cache of imported meshes and built hierarchies.  The reference re-imports the .dae files and rebuilds both BVHs
+ * in every lambda it starts (load_mesh.hpp:232-293, se3_rigid_body_scenario.hpp:58-59); with a cache directory set,
+ * mplb_scene_create_* look both up by content (file bytes / triangle bytes + format version) and only import / build on a
+ * miss.  Entries are checksummed and replaced atomically; a stale or damaged entry is rebuilt.  dir == NULL or "" turns the
+ * cache off (the default unless the environment names one in MPLB_CACHE_DIR).  Hits/misses are process-wide counts. */
+int mplb_set_cache_dir(const char *dir);
+void mplb_cache_stats(uint64_t *hits, uint64_t *misses);
+
 /* ---------------------------------------------------------------------------------------- */
 /* SE(3) rigid-body scene: replaces SE3RigidBodyScenario's constructor
  * (se3_rigid_body_scenario.hpp:51-64).  Triangles are the robot mesh (already shifted to its

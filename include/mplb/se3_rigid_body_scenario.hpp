@@ -3,9 +3,10 @@
 // Mirrors mpl::demo::SE3RigidBodyScenario<S, so3weight, l2weight>
 // (reference include/mpl/demo/se3_rigid_body_scenario.hpp:15-179): same constructor arguments,
 // same Scenario-concept members (scale, space, maxSteering, sampleGoal, randomSample, isGoal,
-// isValid(q), isValid(from,to)), so Planner<Scenario, PRRT/PCForest> (prrt.hpp:52-76,
-// pcforest.hpp:80-104) and runPlanner (src/mpl/demo/lambda_common.cpp:59-214) compile against it
-// unchanged.  The two isValid overloads forward to libmplb.so; the batched members are what the
+// isValid(q), isValid(from,to)).  Planner<Scenario, PRRT/PCForest> (prrt.hpp:35-76, pcforest.hpp:42-104)
+// instantiate nigh on Scenario::Space: with nigh -- or include/mplb/shim, which resolves nigh's names to
+// the GPU nearest-neighbour structure -- on the include path, Space is nigh's SE3Space and those planners
+// compile against this class unchanged (tests/cpp/prrt_pattern_test.cpp).  The two isValid overloads forward to libmplb.so; the batched members are what the
 // GPU path adds underneath.  With Eigen available State is the reference's
 // std::tuple<Eigen::Quaternion<S>, Eigen::Matrix<S,3,1>>; without it a 7-double array in the same
 // coefficient order (qx,qy,qz,qw,tx,ty,tz).
@@ -22,6 +23,7 @@
 #include <random>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../mplb.h"
@@ -31,6 +33,12 @@
 #include <Eigen/Dense>
 #include <tuple>
 #define MPLB_HAVE_EIGEN 1
+#endif
+// nigh itself, or include/mplb/shim (the stand-in that routes nigh's names to the GPU structure), on the include path:
+// Scenario::Space is then the very type the reference planners instantiate nigh with (prrt.hpp:23,35-42)
+#if __has_include(<nigh/se3_space.hpp>)
+#include <nigh/se3_space.hpp>
+#define MPLB_HAVE_NIGH_SPACE 1
 #endif
 #endif
 
@@ -81,6 +89,10 @@ public:
     using Bound = std::array<S, 3>;
 #endif
 
+#ifdef MPLB_HAVE_NIGH_SPACE
+    using Space = unc::robotics::nigh::SE3Space<S, so3weight, l2weight>;   // se3_rigid_body_scenario.hpp:18
+    static_assert(std::is_same<typename Space::Type, State>::value, "nigh's SE3 state type differs from the drop-in's");
+#else
     // nigh::SE3Space<S, so3weight, l2weight> as far as the planners use it (distance only)
     class Space {
         const mplb_scene *scene_ = nullptr;
@@ -95,6 +107,7 @@ public:
         }
         static constexpr unsigned dimensions() { return 6; }
     };
+#endif
 
 private:
     mplb_scene *scene_ = nullptr;
@@ -105,6 +118,11 @@ private:
     Distance invStepSize_;
     mutable std::atomic<unsigned> calls_{0};
 
+    void bindSpace() {
+#ifndef MPLB_HAVE_NIGH_SPACE
+        space_.scene_ = scene_;
+#endif
+    }
     [[noreturn]] static void raise(int rc) {
         const std::string msg = mplb_last_error();
         if (rc == MPLB_ERR_IO || rc == MPLB_ERR_INVALID) throw std::invalid_argument(msg);  // load_mesh.hpp:250-254
@@ -123,7 +141,7 @@ public:
         int rc = mplb_scene_create_se3_files(envMesh.c_str(), robotMesh.c_str(), double(so3weight), double(l2weight),
                                              double(checkResolution), device, &scene_);
         if (rc != MPLB_OK) raise(rc);
-        space_.scene_ = scene_;
+        bindSpace();
     }
     // the same scene from explicit triangle soups (float64 [n][3][3], robot already centred): what
     // load(envMesh,false,false) / load(robotMesh,true,false) would have produced (se3...:58-59)
@@ -138,7 +156,7 @@ public:
         int rc = mplb_scene_create_se3(envTris, nEnv, robotTris, nRobot, double(so3weight), double(l2weight),
                                        double(checkResolution), device, &scene_);
         if (rc != MPLB_OK) raise(rc);
-        space_.scene_ = scene_;
+        bindSpace();
     }
     SE3RigidBodyScenario(const SE3RigidBodyScenario &) = delete;
     SE3RigidBodyScenario &operator=(const SE3RigidBodyScenario &) = delete;

@@ -82,6 +82,8 @@ _SIGNATURES = {
                                                   C.c_size_t, C.c_void_p, C.c_uint32, C.c_size_t, C.c_void_p, C.c_void_p]),
     "mplb_rrt_create": (C.c_int, [C.c_void_p, C.c_void_p, dp, dp, C.c_double, dp, dp, C.c_uint64, C.c_size_t, C.c_double,
                                   C.POINTER(C.c_void_p)]),
+    "mplb_set_cache_dir": (C.c_int, [C.c_char_p]),
+    "mplb_cache_stats": (None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "mplb_rrt_destroy": (None, [C.c_void_p]),
     "mplb_rrt_run": (C.c_int, [C.c_void_p, C.c_uint64, C.c_double, C.POINTER(RrtStatus)]),
     "mplb_rrt_tree": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -160,7 +160,7 @@ static int createSe3(const double *envTris, size_t nEnv, const double *robotTris
     int rc = selectDevice(device, &numSms);
     if (rc != MPLB_OK) return rc;
 
-    FlatBvh env = buildBvh(envTris, nEnv), robot = buildBvh(robotTris, nRobot);
+    FlatBvh env = buildBvhCached(envTris, nEnv), robot = buildBvhCached(robotTris, nRobot);
     auto sc = std::make_unique<Se3Scene>();
     sc->device = device;
     sc->numSms = numSms;
@@ -720,13 +720,20 @@ int mplb_device_count(void) {
 
 void mplb_free(void *p) { std::free(p); }
 
+int mplb_set_cache_dir(const char *dir) {
+    if (setCacheDir(dir) != 0) return fail(MPLB_ERR_IO, "cannot use %s as the cache directory", dir ? dir : "(null)");
+    return MPLB_OK;
+}
+
+void mplb_cache_stats(uint64_t *hits, uint64_t *misses) { cacheStats(hits, misses); }
+
 int mplb_mesh_load_collada(const char *path, int shift_to_center, int identity_root_transform, double **tris,
                            size_t *ntris, double center[3]) {
     if (!path || !tris || !ntris) return fail(MPLB_ERR_INVALID, "null argument");
     *tris = nullptr;
     *ntris = 0;
     try {
-        TriangleSoup s = loadCollada(path, shift_to_center != 0, identity_root_transform != 0);
+        TriangleSoup s = loadColladaCached(path, shift_to_center != 0, identity_root_transform != 0);
         double *buf = (double *)std::malloc(std::max<size_t>(1, s.tris.size()) * sizeof(double));
         if (!buf) return fail(MPLB_ERR_NOMEM, "out of memory");
         std::memcpy(buf, s.tris.data(), s.tris.size() * sizeof(double));
@@ -756,8 +763,8 @@ int mplb_scene_create_se3_files(const char *env_path, const char *robot_path, do
     if (!env_path || !robot_path) return fail(MPLB_ERR_INVALID, "null path");
     try {
         // se3_rigid_body_scenario.hpp:58-59: env load(false,false), robot load(true,false)
-        TriangleSoup env = loadCollada(env_path, false, false);
-        TriangleSoup robot = loadCollada(robot_path, true, false);
+        TriangleSoup env = loadColladaCached(env_path, false, false);
+        TriangleSoup robot = loadColladaCached(robot_path, true, false);
         return createSe3(env.tris.data(), env.size(), robot.tris.data(), robot.size(), so3_weight, l2_weight,
                          check_resolution, device, out);
     } catch (const std::invalid_argument &e) {

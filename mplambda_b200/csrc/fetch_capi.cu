@@ -339,7 +339,7 @@ static int createFetch(const double *envTris, size_t nEnv, const double envFrame
     int numSms = 0;
     int rc = selectDevice(device, &numSms);
     if (rc != MPLB_OK) return rc;
-    FlatBvh env = buildBvh(envTris, nEnv);
+    FlatBvh env = buildBvhCached(envTris, nEnv);
     if (env.depth > 36) return fail(MPLB_ERR_INVALID, "environment hierarchy too deep (%d levels)", env.depth);
     auto sc = std::make_unique<FetchScene>();
     sc->device = device;
@@ -429,7 +429,7 @@ int mplb_scene_create_fetch_file(const char *env_path, const double env_frame[12
     if (!env_path) return fail(MPLB_ERR_INVALID, "null path");
     try {
         // fetch_scenario.hpp:54: MeshLoad<Mesh>::load(envMesh, false, true)
-        TriangleSoup env = loadCollada(env_path, false, true);
+        TriangleSoup env = loadColladaCached(env_path, false, true);
         return createFetch(env.tris.data(), env.size(), env_frame, check_resolution, device, out);
     } catch (const std::invalid_argument &e) {
         return fail(MPLB_ERR_IO, "%s", e.what());

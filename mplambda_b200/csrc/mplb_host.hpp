@@ -46,4 +46,11 @@ struct FlatBvh {
 // longest box axis (balanced => depth <= ceil(log2 n), which bounds the device pair stack).
 FlatBvh buildBvh(const double *tris, size_t n);
 
+// The same two through the on-disk cache (bvh_cache.cpp): identical results, looked up by content when a cache
+// directory is set (mplb_set_cache_dir / MPLB_CACHE_DIR), plain calls otherwise.
+FlatBvh buildBvhCached(const double *tris, size_t n);
+TriangleSoup loadColladaCached(const std::string &path, bool shiftToCenter, bool identityRootTransform);
+int setCacheDir(const char *dir);   // 0, or -1 when the directory cannot be created
+void cacheStats(uint64_t *hits, uint64_t *misses);
+
 }  // namespace mplb

@@ -399,3 +399,30 @@ def test_concurrent_scalar_calls(scenes, golden, oracle):
     [t.start() for t in th]
     [t.join() for t in th]
     assert not errs, errs[:5]
+
+
+def test_hierarchy_cache_gives_the_same_scene(scenes, golden, tmp_path):
+    """mplb_set_cache_dir: the second construction of a scene takes both hierarchies from disk (two hits) and checks
+    exactly like the first."""
+    import ctypes as C
+    from mplambda_b200 import _capi
+    L = _capi.lib()
+
+    def counts():
+        h, m = C.c_uint64(), C.c_uint64()
+        L.mplb_cache_stats(C.byref(h), C.byref(m))
+        return h.value, m.value
+    want = golden["twistycool_valid"]
+    P = se3_poses(len(want), SE3_SCENES["twistycool"]["min"], SE3_SCENES["twistycool"]["max"], SEED)
+    try:
+        assert L.mplb_set_cache_dir(str(tmp_path / "cache").encode()) == 0
+        h0, m0 = counts()
+        a = make(scenes, "twistycool")
+        assert counts() == (h0, m0 + 2)
+        b = make(scenes, "twistycool")
+        assert counts() == (h0 + 2, m0 + 2)
+        assert (a.check_states(P) == want).all() and (b.check_states(P) == want).all()
+        sa, sb = a.stats(), b.stats()
+        assert sa["bv_tests"] == sb["bv_tests"] and sa["env_nodes"] == sb["env_nodes"]
+    finally:
+        L.mplb_set_cache_dir(None)
