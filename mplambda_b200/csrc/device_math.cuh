@@ -102,6 +102,66 @@ __device__ __forceinline__ float obbGap(const float4 a0, const float4 a1, const 
     return gap;
 }
 
+
+// The same test split in two, for a step that tests both children of one box against the same fixed box A: what
+// depends on A and the transform only -- M = A (R), t0 = A (T - centre_A), both in A's box axes -- is formed once
+// (39 operations), each child then costs B = M b^T (27), its centre M c_b + t0 (9) and the 15 axes.  Same quantities
+// as obbGap up to rounding (a few eps of the coordinates' magnitude, well inside the callers' slack).
+struct ObbFrame {
+    float M[3][3], t0[3], ea[3];
+};
+__device__ __forceinline__ void obbFrame(const float4 a0, const float4 a1, const float4 a2, const float4 ae,
+                                         const float4 x0, const float4 x1, const float4 x2, ObbFrame &F) {
+    const float4 a[3] = {a0, a1, a2};
+    const float dx = x0.w - a0.w, dy = x1.w - a1.w, dz = x2.w - a2.w;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        F.M[i][0] = fmaf(a[i].x, x0.x, fmaf(a[i].y, x1.x, a[i].z * x2.x));
+        F.M[i][1] = fmaf(a[i].x, x0.y, fmaf(a[i].y, x1.y, a[i].z * x2.y));
+        F.M[i][2] = fmaf(a[i].x, x0.z, fmaf(a[i].y, x1.z, a[i].z * x2.z));
+        F.t0[i] = fmaf(a[i].x, dx, fmaf(a[i].y, dy, a[i].z * dz));
+    }
+    F.ea[0] = ae.x; F.ea[1] = ae.y; F.ea[2] = ae.z;
+}
+__device__ __forceinline__ float obbGapFramed(const ObbFrame &F, const float4 b0, const float4 b1, const float4 b2,
+                                              const float4 be, float &dist2) {
+    float T[3], B[3][3], Bf[3][3];
+    const float4 b[3] = {b0, b1, b2};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        T[i] = fmaf(F.M[i][0], b0.w, fmaf(F.M[i][1], b1.w, fmaf(F.M[i][2], b2.w, F.t0[i])));
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            B[i][j] = fmaf(F.M[i][0], b[j].x, fmaf(F.M[i][1], b[j].y, F.M[i][2] * b[j].z));
+            Bf[i][j] = fabsf(B[i][j]);
+        }
+    }
+    dist2 = fmaf(T[0], T[0], fmaf(T[1], T[1], T[2] * T[2]));
+    const float *ea = F.ea;
+    const float eb[3] = {be.x, be.y, be.z};
+    float gap = -3.0e38f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        gap = fmaxf(gap, fabsf(T[i]) - (ea[i] + fmaf(eb[0], Bf[i][0], fmaf(eb[1], Bf[i][1], eb[2] * Bf[i][2]))));
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        float s = fmaf(T[0], B[0][j], fmaf(T[1], B[1][j], T[2] * B[2][j]));
+        gap = fmaxf(gap, fabsf(s) - (eb[j] + fmaf(ea[0], Bf[0][j], fmaf(ea[1], Bf[1][j], ea[2] * Bf[2][j]))));
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+            float s = fmaf(T[i2], B[i1][j], -T[i1] * B[i2][j]);
+            float r = fmaf(ea[i1], Bf[i2][j], fmaf(ea[i2], Bf[i1][j], fmaf(eb[j1], Bf[i][j2], eb[j2] * Bf[i][j1])));
+            gap = fmaxf(gap, fabsf(s) - r);
+        }
+    }
+    return gap;
+}
+
 __device__ __forceinline__ bool obbOverlap(const float4 a0, const float4 a1, const float4 a2, const float4 ae,
                                            const float4 b0, const float4 b1, const float4 b2, const float4 be,
                                            const float4 x0, const float4 x1, const float4 x2, float slack, float &dist2) {

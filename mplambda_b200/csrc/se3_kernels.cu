@@ -53,7 +53,10 @@ namespace {
 #define MPLB_MIN_CTAS 2
 #endif
 constexpr int kWarpsPerCta = MPLB_WARPS_PER_CTA;
-constexpr int kSlots = 64;          // state slots per warp
+#ifndef MPLB_SLOTS
+#define MPLB_SLOTS 64
+#endif
+constexpr int kSlots = MPLB_SLOTS;  // state slots per warp (64 or 32)
 constexpr int kQueueCap = 96;       // leaf / exact queue entries per warp
 #ifndef MPLB_EDGE_INTERVAL_BITS
 #define MPLB_EDGE_INTERVAL_BITS 5
@@ -65,7 +68,10 @@ constexpr unsigned kPhaseBSub = 1u << kIntervalBits;    // intervals an edge's s
 #endif
 constexpr unsigned kSpillKeep = MPLB_SPILL_KEEP;    // interval pieces a warp keeps for itself once the item pool has drained
 constexpr size_t kLatencyBelow = 1u << 17;   // poses: below this checkStatesKernel's latency variant is launched
-constexpr int kStepsPerRound = 4;   // depth-first steps between two rounds of slot bookkeeping
+#ifndef MPLB_STEPS_PER_ROUND
+#define MPLB_STEPS_PER_ROUND 4
+#endif
+constexpr int kStepsPerRound = MPLB_STEPS_PER_ROUND;   // depth-first steps between two rounds of slot bookkeeping
 constexpr unsigned kFull = 0xffffffffu;
 
 // Per-warp shared memory, carved from the dynamic allocation at run time: the LIFO only gets as
@@ -167,6 +173,17 @@ __device__ __noinline__ bool triTriExact(const double *P, const double *Q, const
     for (int i = 0; i < 3; ++i)
         if (!project6D(d3cross(f[i], m1), p1, p2, p3, q1, q2, q3)) return false;
     return true;
+}
+
+// The exact re-evaluation of one triangle pair, out of line: the state is rebuilt from the slot's tags by the source's
+// fetcher (a few pointers, passed by value) -- the FP64 code stays out of the hot loop's instruction footprint.
+template <typename Fetch>
+__device__ __noinline__ bool exactPairHit(const Fetch fetch, unsigned t0, unsigned t1, const double *P, const double *Q) {
+    double s[7];
+    fetch.stateOf(t0, t1, s);
+    XformD X;
+    stateToRelD(s, X);
+    return triTriExact(P, Q, X);
 }
 
 // interpolate.hpp:18-36 with Eigen's slerp; same statements as orc_se3_interpolate.  sin/acos are
@@ -289,20 +306,41 @@ __global__ void edgeGatherPlanKernel(EdgeGather g, unsigned long long n, double 
 // Round the FP64 relative transform to the FP32 slot and derive the error parameters.
 // extraSlack > 0 turns the slot into an interval certificate: every box test is inflated by the largest
 // displacement any robot point can have, relative to this pose, over the interval the slot stands for.
-__device__ void makeSlot(const double s[7], const SceneDev &sc, float4 *xf, float extraSlack = 0.f) {
+__device__ __forceinline__ void makeSlot(const double s[7], float envRadius, float robotRadius, float4 *xf, float extraSlack = 0.f) {
     XformD X;
     stateToRelD(s, X);
     double qn = s[0] * s[0] + s[1] * s[1] + s[2] * s[2] + s[3] * s[3];
     double scale = fmax(1.0, qn);  // |R| for non-unit quaternions
     double tn = sqrt(s[4] * s[4] + s[5] * s[5] + s[6] * s[6]);
-    double mag = scale * ((double)sc.envRadius + tn) + (double)sc.robotRadius;
+    double mag = scale * ((double)envRadius + tn) + (double)robotRadius;
     float eta = (float)(8.0 * FLT_EPSILON * mag) * 1.0000002f;
-    float slack = (float)(64.0 * FLT_EPSILON * (mag + 4.0 * scale * (double)sc.envRadius +
-                                                4.0 * (double)sc.robotRadius));
+    float slack = (float)(64.0 * FLT_EPSILON * (mag + 4.0 * scale * (double)envRadius +
+                                                4.0 * (double)robotRadius));
     xf[0] = make_float4((float)X.R[0][0], (float)X.R[0][1], (float)X.R[0][2], (float)X.T[0]);
     xf[1] = make_float4((float)X.R[1][0], (float)X.R[1][1], (float)X.R[1][2], (float)X.T[1]);
     xf[2] = make_float4((float)X.R[2][0], (float)X.R[2][1], (float)X.R[2][2], (float)X.T[2]);
     xf[3] = make_float4(slack + extraSlack, eta, slack, 0.f);  // .z keeps the plain slack
+}
+
+// One new slot: the source's loader -- a few pointers, by value -- rebuilds the state of work item `rank` (`work`: its
+// descriptor, for sources that use one), the slot's transform and tags are written to shared memory (tags: tag0 +
+// slot; tag1..3 and pending follow at kSlots strides, see WarpSmem).  -> false: the item needs no work.
+// (Out of line it was measured slower, 0.786 -> 0.805 ms per 2^20 Alpha poses: the call's register traffic costs more
+// than the ~300 FP64 instructions take from the instruction cache.)
+template <typename Loader>
+__device__ __forceinline__ bool fillSlot(const Loader ld, const uint4 work, int rank, float envRadius, float robotRadius,
+                                      float4 *xf, unsigned *tags) {
+    double s[7];
+    unsigned t[4];
+    float extraSlack;
+    if (!ld.load(rank, work, s, t, extraSlack)) return false;
+    makeSlot(s, envRadius, robotRadius, xf, extraSlack);
+    tags[0] = t[0];
+    tags[kSlots] = t[1];
+    tags[2 * kSlots] = t[2];
+    tags[3 * kSlots] = t[3];
+    tags[4 * kSlots] = 0;   // pending
+    return true;
 }
 
 enum TriVerdict : int { kTriNo = 0, kTriYes = 1, kTriUnsure = 2 };
@@ -340,27 +378,34 @@ __device__ __forceinline__ void axisTest(F3 ax, F3 p2, F3 p3, F3 q1, F3 q2, F3 q
 // Certain answers need no FP64 work; kTriUnsure pairs are re-evaluated exactly.
 __device__ __forceinline__ int triTriFilter(F3 p2, F3 p3, F3 q1, F3 f1, F3 f2, float eta) {
     const F3 q2 = f3(q1.x + f1.x, q1.y + f1.y, q1.z + f1.z), q3 = f3(q1.x + f2.x, q1.y + f2.y, q1.z + f2.z);
-    const F3 e[3] = {p2, p3 - p2, f3(-p3.x, -p3.y, -p3.z)};
-    const F3 f[3] = {f1, f2 - f1, f3(-f2.x, -f2.y, -f2.z)};
-    const float Me = fmaxf(absMax(e[0]), fmaxf(absMax(e[1]), absMax(e[2])));
-    const float Mf = fmaxf(absMax(f[0]), fmaxf(absMax(f[1]), absMax(f[2])));
+    F3 e0 = p2, e1 = p3 - p2, e2 = f3(-p3.x, -p3.y, -p3.z);
+    F3 g0 = f1, g1 = f2 - f1, g2 = f3(-f2.x, -f2.y, -f2.z);
+    const float Me = fmaxf(absMax(e0), fmaxf(absMax(e1), absMax(e2)));
+    const float Mf = fmaxf(absMax(g0), fmaxf(absMax(g1), absMax(g2)));
     const float U = fmaxf(fmaxf(fmaxf(absMax(p2), absMax(p3)), fmaxf(absMax(q1), absMax(q2))), absMax(q3));
     const float S = fmaf(79.f * FLT_EPSILON, U, eta);
     const float eu = FLT_EPSILON * U;
     const float Kn = 120.f * eu * Me * Me, Km = 792.f * eu * Mf * Mf, Kef = 456.f * eu * Me * Mf;
     const float Kg = 384.f * eu * Me * Me * Me, Kh = 2400.f * eu * Mf * Mf * Mf;
-    const F3 n1 = cross(e[0], e[1]), m1 = cross(f[0], f[1]);
+    const F3 n1 = cross(e0, e1), m1 = cross(g0, g1);
     AxisState st{false, false};
     axisTest(n1, p2, p3, q1, q2, q3, S, Kn, st);
     axisTest(m1, p2, p3, q1, q2, q3, S, Km, st);
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) axisTest(cross(e[i], f[j]), p2, p3, q1, q2, q3, S, Kef, st);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) axisTest(cross(e[i], n1), p2, p3, q1, q2, q3, S, Kg, st);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) axisTest(cross(f[i], m1), p2, p3, q1, q2, q3, S, Kh, st);
+    // The other 15 axes as three rounds of five -- e_i x f_i, e_i x f_i+1, e_i x f_i+2, e_i x n1, f_i x m1 -- with the
+    // edge vectors rotated through fixed registers between rounds: a third of the code of the unrolled form (the
+    // kernels are bound by instruction fetch: their hot loop does not fit the 32 KB instruction cache), same axes,
+    // same arithmetic per axis; the order of the axes does not matter to the verdict.
+#pragma unroll 1
+    for (int i = 0; i < 3; ++i) {
+        axisTest(cross(e0, g0), p2, p3, q1, q2, q3, S, Kef, st);
+        axisTest(cross(e0, g1), p2, p3, q1, q2, q3, S, Kef, st);
+        axisTest(cross(e0, g2), p2, p3, q1, q2, q3, S, Kef, st);
+        axisTest(cross(e0, n1), p2, p3, q1, q2, q3, S, Kg, st);
+        axisTest(cross(g0, m1), p2, p3, q1, q2, q3, S, Kh, st);
+        const F3 te = e0, tg = g0;
+        e0 = e1; e1 = e2; e2 = te;
+        g0 = g1; g1 = g2; g2 = tg;
+    }
     if (st.sep) return kTriNo;
     return st.unsure ? kTriUnsure : kTriYes;
 }
@@ -528,27 +573,36 @@ struct StateSourceT {
         pendCount = 0;
         return got;
     }
-    // -> false when the item turned out to need no work
-    template <typename SM>
-    __device__ bool load(int rank, double s[7], unsigned t[4], float &extraSlack, const SM &) const {
-        const unsigned long long i = base + rank;
-        t[0] = (unsigned)i;
-        t[1] = (unsigned)(i >> 32);
-        t[2] = t[3] = 0;
-        extraSlack = 0.f;
-        stateOf(t[0], t[1], s);   // (streamed: the claim's chunk flag has been seen by acquire())
-        return true;
-    }
-    __device__ void stateOf(unsigned t0, unsigned t1, double s[7]) const {
-        const double *src = states + 7 * (((unsigned long long)t1 << 32) | t0);
-        if (streamed) {   // freshly DMA-written memory: read through L2, not the non-coherent path
-#pragma unroll
-            for (int k = 0; k < 7; ++k) s[k] = __ldcg(src + k);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 7; ++k) s[k] = __ldg(src + k);
+    struct Loader {
+        const double *states;
+        unsigned long long base;
+        // -> false when the item turned out to need no work
+        __device__ bool load(int rank, const uint4 &, double s[7], unsigned t[4], float &extraSlack) const {
+            const unsigned long long i = base + rank;
+            t[0] = (unsigned)i;
+            t[1] = (unsigned)(i >> 32);
+            t[2] = t[3] = 0;
+            extraSlack = 0.f;
+            Fetch{states}.stateOf(t[0], t[1], s);   // (streamed: the claim's watermark has been seen by acquire())
+            return true;
         }
-    }
+    };
+    __device__ Loader loader() const { return Loader{states, base}; }
+    struct Fetch {   // what it takes to read a state again (exact path), small enough to pass by value
+        const double *states;
+        __device__ void stateOf(unsigned t0, unsigned t1, double s[7]) const {
+            const double *src = states + 7 * (((unsigned long long)t1 << 32) | t0);
+            if (kStreamed) {   // freshly DMA-written memory: read through L2, not the non-coherent path
+#pragma unroll
+                for (int k = 0; k < 7; ++k) s[k] = __ldcg(src + k);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 7; ++k) s[k] = __ldg(src + k);
+            }
+        }
+    };
+    __device__ Fetch fetcher() const { return Fetch{states}; }
+    __device__ void stateOf(unsigned t0, unsigned t1, double s[7]) const { fetcher().stateOf(t0, t1, s); }
     // warp-collective: slots `lane` (r0) and `lane + 32` (r1) retire
     template <typename SM>
     __device__ void retire(SM &sm, unsigned lane, bool r0, bool r1, const Masks64 &hit, const Masks64 &, unsigned &) const {
@@ -689,7 +743,19 @@ struct EdgeSource {
         return count;
     }
     // sample index `steps` stands for `to` itself
+    struct Fetch {
+        const double *from, *to, *edgeConst;
+        const unsigned *steps;
+        __device__ void stateOf(unsigned t0, unsigned t1, double s[7]) const {
+            EdgeSource::sampleStateOf(from, to, edgeConst, t0, t1, __ldg(steps + t0), s);
+        }
+    };
+    __device__ Fetch fetcher() const { return Fetch{from, to, edgeConst, steps}; }
     __device__ void sampleState(unsigned e, unsigned i, unsigned st, double s[7]) const {
+        sampleStateOf(from, to, edgeConst, e, i, st, s);
+    }
+    static __device__ void sampleStateOf(const double *from, const double *to, const double *edgeConst, unsigned e,
+                                         unsigned i, unsigned st, double s[7]) {
         const double *b = to + 7 * (size_t)e;
         if (i >= st) {
 #pragma unroll
@@ -705,23 +771,26 @@ struct EdgeSource {
         }
         interpolateWith(fa, fb, dmul((double)i, __ddiv_rn(1.0, (double)st)), __ldg(c), __ldg(c + 1), __ldg(c + 2), s);
     }
-    template <typename SM>
-    __device__ bool load(int rank, double s[7], unsigned t[4], float &extraSlack, const SM &sm) const {
-        const uint4 w = sm.work[rank];
-        const unsigned e = w.x, lo = w.y, hi = w.z;
-        if (((volatile unsigned *)dead)[e]) return false;
-        const unsigned st = __ldg(steps + e);
-        const unsigned mid = lo + (hi - lo) / 2;
-        sampleState(e, mid, st, s);
-        extraSlack = 0.f;
-        if (hi > lo) {
-            const double *c = edgeConst + kEdgeConst * (size_t)e;
-            const double reach = (double)max(hi - mid, mid - lo) / (double)st;
-            extraSlack = __double2float_ru((reach * __ldg(c + 3)) * 1.000001 + __ldg(c + 4));
+    struct Loader {
+        const double *from, *to, *edgeConst;
+        const unsigned *steps, *dead;
+        __device__ bool load(int, const uint4 &w, double s[7], unsigned t[4], float &extraSlack) const {
+            const unsigned e = w.x, lo = w.y, hi = w.z;
+            if (((volatile const unsigned *)dead)[e]) return false;
+            const unsigned st = __ldg(steps + e);
+            const unsigned mid = lo + (hi - lo) / 2;
+            EdgeSource::sampleStateOf(from, to, edgeConst, e, mid, st, s);
+            extraSlack = 0.f;
+            if (hi > lo) {
+                const double *c = edgeConst + kEdgeConst * (size_t)e;
+                const double reach = (double)max(hi - mid, mid - lo) / (double)st;
+                extraSlack = __double2float_ru((reach * __ldg(c + 3)) * 1.000001 + __ldg(c + 4));
+            }
+            t[0] = e; t[1] = mid; t[2] = lo; t[3] = hi;
+            return true;
         }
-        t[0] = e; t[1] = mid; t[2] = lo; t[3] = hi;
-        return true;
-    }
+    };
+    __device__ Loader loader() const { return Loader{from, to, edgeConst, steps, dead}; }
     __device__ void stateOf(unsigned t0, unsigned t1, double s[7]) const { sampleState(t0, t1, __ldg(steps + t0), s); }
 
     // warp-collective.  A hit kills the edge; an interval whose traversal reached leaf pairs (touched) and
@@ -819,7 +888,7 @@ struct EdgeSource {
             const unsigned e = sm.tag0[s];
             if (lane == 0) dead[e] = 1u;
             const bool k0 = inUse.test(lane) && sm.tag0[lane] == e;
-            const bool k1 = inUse.test(lane + 32) && sm.tag0[lane + 32] == e;
+            const bool k1 = kSlots > 32 && inUse.test(lane + 32) && sm.tag0[lane + 32] == e;
             hit.lo |= __ballot_sync(kFull, k0);
             hit.hi |= __ballot_sync(kFull, k1);
         }
@@ -837,11 +906,11 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
     const Codec<E> cd{6 + sc.bitsA};
     const int bitsA = sc.bitsA;
     const unsigned maskA = (1u << bitsA) - 1u;
-    Masks64 freeM{~0u, ~0u}, readyM{0, 0}, hitM{0, 0}, doneM{0, 0}, touchedM{0, 0};  // touched: reached a leaf pair
+    Masks64 freeM{~0u, kSlots > 32 ? ~0u : 0u}, readyM{0, 0}, hitM{0, 0}, doneM{0, 0}, touchedM{0, 0};  // touched: reached a leaf pair
     // this lane's LIFO holds entries [bot, sp); thieves take from the bottom (the largest subtree)
     int nt = 0, nx = 0, sp = 0, bot = 0, mySlot = -1;
     const int triMin = sc.triBatchMin, triEager = sc.triEagerLanes;
-    unsigned idleSpins = 0;
+    unsigned idleSpins = 0, stepsLane = 0;
     // compact the set bits of a 64-slot mask into sm.list (lane s looks after slots s and s + 32)
     auto buildList = [&](const Masks64 &m) {
         if ((m.lo >> lane) & 1u) sm.list[__popc(m.lo & ltMask)] = lane;
@@ -866,7 +935,7 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
         // ---- retire finished slots whose queued leaf pairs are all resolved
         {
             const bool r0 = ((doneM.lo >> lane) & 1u) && sm.pending[lane] == 0;
-            const bool r1 = ((doneM.hi >> lane) & 1u) && sm.pending[lane + 32] == 0;
+            const bool r1 = kSlots > 32 && ((doneM.hi >> lane) & 1u) && sm.pending[lane + 32] == 0;
             const unsigned m0 = __ballot_sync(kFull, r0), m1 = __ballot_sync(kFull, r1);
             if (m0 | m1) {
                 src.retire(sm, lane, r0, r1, hitM, touchedM, cnt.error);
@@ -886,18 +955,8 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
                 unsigned slot = 0;
                 if (take) {
                     slot = sm.list[lane];
-                    double s[7];
-                    unsigned t[4];
-                    float extraSlack;
-                    take = src.load((int)lane, s, t, extraSlack, sm);
-                    if (take) {
-                        makeSlot(s, sc, sm.xf[slot], extraSlack);
-                        sm.tag0[slot] = t[0];
-                        sm.tag1[slot] = t[1];
-                        sm.tag2[slot] = t[2];
-                        sm.tag3[slot] = t[3];
-                        sm.pending[slot] = 0;
-                    }
+                    take = fillSlot(src.loader(), Source::kIntervals ? sm.work[lane] : make_uint4(0, 0, 0, 0), (int)lane, sc.envRadius, sc.robotRadius, sm.xf[slot],
+                                    sm.tag0 + slot);
                 }
                 const Masks64 t = slotBits(take, slot);
                 freeM.lo &= ~t.lo; freeM.hi &= ~t.hi;
@@ -1029,13 +1088,9 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
             const unsigned slot = cd.slot(en);
             const bool act = act0 && !hitM.test(slot);
             bool hit = false;
-            if (act) {
-                double s[7];
-                src.stateOf(sm.tag0[slot], sm.tag1[slot], s);
-                XformD X;
-                stateToRelD(s, X);
-                hit = triTriExact(sc.robotTris64 + 9 * (size_t)cd.a(en), sc.envTris64 + 9 * (size_t)cd.b(en), X);
-            }
+            if (act)
+                hit = exactPairHit(src.fetcher(), sm.tag0[slot], sm.tag1[slot], sc.robotTris64 + 9 * (size_t)cd.a(en),
+                                   sc.envTris64 + 9 * (size_t)cd.b(en));
             cnt.exact += __popc(__ballot_sync(kFull, act));
             if (act0) atomicSub(&sm.pending[slot], 1);
             const Masks64 fresh = slotBits(hit, slot);
@@ -1093,15 +1148,21 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
                 const float4 y1 = descendA ? make_float4(x0.y, x1.y, x2.y, -fmaf(x0.y, x0.w, fmaf(x1.y, x1.w, x2.y * x2.w))) : x1;
                 const float4 y2 = descendA ? make_float4(x0.z, x1.z, x2.z, -fmaf(x0.z, x0.w, fmaf(x1.z, x1.w, x2.z * x2.w))) : x2;
                 float g0 = 0.f, g1 = 0.f;
-                if constexpr (Source::kIntervals) {
-                    // one copy of the ~200-instruction test, run twice: checkEdgesKernel is bound by instruction
-                    // fetch (ncu: stall_no_inst; its warps alternate between this loop and the FP64 sample
-                    // conversion), not by the dependent FMA chains the two inlined copies overlap (+9 %)
+                // what depends on the fixed box and the pose only is formed once for both children (device_math.cuh)
+                ObbFrame F;
+                obbFrame(f0, f1, f2, fe, y0, y1, y2, F);
+#ifndef MPLB_OBB_LOOP
+#define MPLB_OBB_LOOP 0
+#endif
+                if constexpr (Source::kIntervals || MPLB_OBB_LOOP) {
+                    // one copy of the per-child test, run twice: checkEdgesKernel is bound by instruction fetch (ncu:
+                    // stall_no_inst; its warps alternate between this loop and the FP64 sample conversion), not by
+                    // the dependent FMA chains the two inlined copies overlap
                     float4 b0 = c00, b1 = c01, b2 = c02, be = c0e;
 #pragma unroll 1
                     for (int k = 0; k < 2; ++k) {
                         float dd;
-                        const float g = obbGap(f0, f1, f2, fe, b0, b1, b2, be, y0, y1, y2, dd);
+                        const float g = obbGapFramed(F, b0, b1, b2, be, dd);
                         if (k == 0) {
                             g0 = g; d0 = dd;
                             b0 = c10; b1 = c11; b2 = c12; be = c1e;
@@ -1110,8 +1171,8 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
                         }
                     }
                 } else {
-                    g0 = obbGap(f0, f1, f2, fe, c00, c01, c02, c0e, y0, y1, y2, d0);
-                    g1 = obbGap(f0, f1, f2, fe, c10, c11, c12, c1e, y0, y1, y2, d1);
+                    g0 = obbGapFramed(F, c00, c01, c02, c0e, d0);
+                    g1 = obbGapFramed(F, c10, c11, c12, c1e, d1);
                 }
                 ov0 = g0 <= x3.x;   // within reach (plain slack, or inflated for an interval certificate)
                 ov1 = g1 <= x3.x;
@@ -1132,7 +1193,7 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
                 sz1 = fmaf(c1e.x, c1e.x, fmaf(c1e.y, c1e.y, c1e.z * c1e.z));
                 szF = fmaf(fe.x, fe.x, fmaf(fe.y, fe.y, fe.z * fe.z));
             }
-            cnt.bv += 2ull * __popc(__ballot_sync(kFull, act));
+            stepsLane += act ? 1u : 0u;   // box tests are counted per lane and summed when the warp is through
             // leaf-leaf survivors -> shared triangle queue
             // a leaf pair within reach means the interval cannot be certified (touched); only pairs that
             // overlap at this very sample need the triangle test
@@ -1201,10 +1262,14 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
             // all that is left: go back to the bookkeeping as soon as an idle lane could take a pair from a busy one
             // (1 024 random Alpha poses 75 -> 57 us, a 1 000-test pose alone 55 -> 45 us).  Not in the throughput
             // variant: the two extra votes per step cost 3 % on 2^20-pose batches.
-            if constexpr (kLatency)
+#ifndef MPLB_TAIL_STEAL
+#define MPLB_TAIL_STEAL 0
+#endif
+            if constexpr (kLatency || MPLB_TAIL_STEAL)
                 if (src.done() && nActive < 32 && __any_sync(kFull, sp - bot >= 2)) break;
         }
     }
+    cnt.bv += 2ull * __reduce_add_sync(kFull, stepsLane);
 }
 
 template <typename E>
@@ -1213,7 +1278,7 @@ __device__ __forceinline__ WarpSmem<E> warpSmem(int levels) {
     WarpSmem<E> sm;
     sm.carve(smemRaw + (threadIdx.x >> 5) * WarpSmem<E>::bytes(levels), levels);
     sm.pending[threadIdx.x & 31u] = 0;
-    sm.pending[(threadIdx.x & 31u) + 32] = 0;
+    if (kSlots > 32) sm.pending[(threadIdx.x & 31u) + 32] = 0;
     __syncwarp();
     return sm;
 }

