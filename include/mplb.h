@@ -139,6 +139,15 @@ typedef struct {
 } mplb_stats_t;
 int mplb_scene_stats(mplb_scene *scene, mplb_stats_t *out, int reset);
 
+/* Scalar calls (n == 1: the reference's isValid(q) / isValid(from, to), issued one per OpenMP planner thread,
+ * prrt.hpp:140-152, 280-299) go to the device as ONE kernel launch each: the kernel reads the state from pinned host
+ * memory, writes the verdict there and rings the calling thread, which spins on it (no copy engine, no stream
+ * synchronisation; 24-30 us per isValid(q), 16 threads: 400 k calls/s).  With coalescing on, scalar calls that arrive
+ * while earlier ones of the same scene are on the device share a launch (up to 64); a lone caller is never delayed.
+ * Off by default (MPLB_COALESCE=1 in the environment: on by default): with every thread on its own stream sharing
+ * only pays once there are more calling threads than the driver launches side by side.  Returns MPLB_OK. */
+int mplb_scene_set_coalescing(mplb_scene *scene, int on);
+
 /* ---------------------------------------------------------------------------------------- */
 /* Nearest neighbour: replaces nigh::Nigh<Node*,Space,NodeKey,Concurrent,...> as used by the
  * planners (prrt.hpp:42,61,67,115; pcforest.hpp:51,81,86,107,193).  Keys are the scaled states

@@ -63,6 +63,7 @@ _SIGNATURES = {
                                           C.c_void_p, C.c_void_p]),
     "mplb_distance": (C.c_double, [C.c_void_p, dp, dp]),
     "mplb_scene_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats), C.c_int]),
+    "mplb_scene_set_coalescing": (C.c_int, [C.c_void_p, C.c_int]),
     "mplb_nn_create": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_void_p)]),
     "mplb_nn_destroy": (None, [C.c_void_p]),
     "mplb_nn_insert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <chrono>
 #include <memory>
+#include <thread>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -49,6 +50,14 @@ int DevBuf::reserve(size_t bytes) {
 }
 DevBuf::~DevBuf() {
     if (ptr) cudaFree(ptr);
+}
+
+static inline void cpuRelax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#else
+    std::this_thread::yield();
+#endif
 }
 
 constexpr size_t kStageBytes = 160 * 1024;                 // inputs of a small call
@@ -110,7 +119,42 @@ CallCtx *SceneBase::acquire() {
         delete c;
         return nullptr;
     }
+    static const bool noDirect = std::getenv("MPLB_NO_DIRECT_RETURN") != nullptr;   // diagnostic
+    void *ds = nullptr, *dc = nullptr;
+    if (!noDirect && cudaHostGetDevicePointer(&ds, c->hStage, 0) == cudaSuccess &&
+        cudaHostGetDevicePointer(&dc, c->hCtl, 0) == cudaSuccess) {
+        c->dStageHost = (unsigned char *)ds;
+        c->dCtlHost = (unsigned char *)dc;
+    } else {
+        cudaGetLastError();
+    }
+    std::memset(c->hCtl, 0, kCtlHeader + kCtlTail);
     return c;
+}
+
+// Waits for a direct-return kernel to ring (HostReturn): the calling thread spins on the flag in pinned memory -- the
+// whole call is tens of microseconds, a blocking synchronisation alone costs that much -- and looks at the stream now
+// and then, so that a failed launch or a device fault ends the wait with an error instead of a hang.
+static int awaitRing(CallCtx *c, unsigned seq) {
+    volatile unsigned *flag = (volatile unsigned *)(c->hCtl + kCtlHeader - 64);
+    for (unsigned spins = 1;; ++spins) {
+        if (*flag == seq) break;
+        if ((spins & 0xfffu) == 0) {
+            const cudaError_t q = cudaStreamQuery(c->stream);
+            if (q == cudaSuccess) {
+                if (*flag == seq) break;
+                c->ctlDirty = true;
+                return fail(MPLB_ERR_CUDA, "direct-return kernel finished without ringing the host");
+            }
+            if (q != cudaErrorNotReady) {
+                c->ctlDirty = true;
+                return fail(MPLB_ERR_CUDA, "device work failed: %s", cudaGetErrorString(q));
+            }
+        }
+        cpuRelax();
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return MPLB_OK;
 }
 void SceneBase::release(CallCtx *c) {
     std::lock_guard<std::mutex> g(mu);
@@ -118,6 +162,81 @@ void SceneBase::release(CallCtx *c) {
 }
 SceneBase::~SceneBase() {
     for (auto *c : freeCtx) delete c;
+}
+
+// One scalar call through the combiner.  The first caller of a batch leads it: it takes the batch to the device as
+// soon as fewer than `maxInflight` batches of this kind are there (at once when the scene is idle, so a single-threaded
+// planner pays nothing), and whoever arrives in the meantime joins; the others wait for the leader's launch, spinning
+// first (the wait is tens of microseconds; a futex wake-up alone costs that much).  A failed launch is not shared:
+// every caller of that batch repeats its own call, so one thread's bad state never fails another's.
+int SceneBase::combined(int kind, const double *a, const double *b, uint8_t *valid) {
+    static const int maxInflight = [] { const char *e = std::getenv("MPLB_COALESCE_INFLIGHT"); return e ? std::max(1, std::atoi(e)) : 2; }();
+    Combiner &cb = comb[kind];
+    const size_t w = (size_t)stateDim;
+    std::shared_ptr<Combiner::Batch> bt;
+    int i;
+    {
+        std::lock_guard<std::mutex> g(cb.mu);
+        if (!cb.open) {
+            if (!cb.spare.empty()) {
+                cb.open = std::move(cb.spare.back());
+                cb.spare.pop_back();
+            } else {
+                cb.open = std::make_shared<Combiner::Batch>();
+                cb.open->a.resize(Combiner::kMax * w);
+                cb.open->b.resize(Combiner::kMax * w);
+            }
+            cb.open->n = 0;
+            cb.open->filled.store(0, std::memory_order_relaxed);
+            cb.open->done.store(0, std::memory_order_relaxed);
+            cb.open->left.store(0, std::memory_order_relaxed);
+        }
+        bt = cb.open;
+        i = bt->n++;
+        if (bt->n == Combiner::kMax) cb.open.reset();   // full: newcomers start the next one
+    }
+    std::memcpy(&bt->a[i * w], a, w * sizeof(double));
+    if (kind) std::memcpy(&bt->b[i * w], b, w * sizeof(double));
+    bt->filled.fetch_add(1, std::memory_order_release);
+    if (i == 0) {
+        while (cb.inflight.load(std::memory_order_acquire) >= maxInflight) {
+            bool full;
+            {
+                std::lock_guard<std::mutex> g(cb.mu);
+                full = bt->n == Combiner::kMax;
+            }
+            if (full) break;
+            cpuRelax();
+        }
+        int n;
+        {
+            std::lock_guard<std::mutex> g(cb.mu);
+            if (cb.open == bt) cb.open.reset();   // closed
+            n = bt->n;
+        }
+        cb.inflight.fetch_add(1, std::memory_order_acq_rel);
+        while (bt->filled.load(std::memory_order_acquire) < n) cpuRelax();   // (a joiner still copying its state in)
+        const int rc = kind ? checkEdges(bt->a.data(), bt->b.data(), (size_t)n, bt->out, nullptr)
+                            : checkStates(bt->a.data(), (size_t)n, bt->out);
+        cb.inflight.fetch_sub(1, std::memory_order_acq_rel);
+        if (n > 1) hCoalesced += (uint64_t)n;
+        bt->done.store(rc == MPLB_OK ? 1 : 2, std::memory_order_release);
+    } else {
+        for (unsigned spins = 0; bt->done.load(std::memory_order_acquire) == 0; ++spins) {
+            if (spins < 4096) cpuRelax();
+            else std::this_thread::yield();
+        }
+    }
+    const bool ok = bt->done.load(std::memory_order_acquire) == 1;
+    const uint8_t v = bt->out[i];
+    // bt->n is final (the batch was closed before its launch); the last caller out hands the batch back for reuse
+    if (bt->left.fetch_add(1, std::memory_order_acq_rel) + 1 == bt->n) {
+        std::lock_guard<std::mutex> g(cb.mu);
+        if (cb.spare.size() < 8) cb.spare.push_back(std::move(bt));
+    }
+    if (!ok) return kind ? checkEdges(a, b, 1, valid, nullptr) : checkStates(a, 1, valid);
+    *valid = v;
+    return MPLB_OK;
 }
 
 int bitsFor(size_t n) {
@@ -449,6 +568,25 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
     if (n <= kSmallStates) {
         std::memcpy(c->hStage, states, bytes);
         unsigned char *ctl = (unsigned char *)c->ctl.ptr;
+        if (c->dStageHost) {
+            // direct return: one launch, no copy engine, no stream synchronisation (se3_device.cuh: HostReturn)
+            if (c->ctlDirty) {
+                MPLB_CUDA(cudaMemsetAsync(ctl, 0, kCtlHeader + kCtlTail, c->stream));
+                c->ctlDirty = false;
+            }
+            StreamedInput in;
+            in.ret.hostCtr = (DevCounters *)c->dCtlHost;
+            in.ret.flag = (unsigned *)(c->dCtlHost + kCtlHeader - 64);
+            in.ret.seq = ++c->seq;
+            in.ret.clearWords = (unsigned)((kCtlHeader - sizeof(DevCounters)) / 4);
+            MPLB_CUDA(launchCheckStates(sc->dev, (const double *)c->dStageHost, n, c->dCtlHost + kCtlHeader, (DevCounters *)ctl,
+                                        (unsigned *)(ctl + kCtlHeader - 128), sc->numSms, c->stream, in, true));
+            sc->hLaunches += 1;
+            if ((rc = awaitRing(c, in.ret.seq))) return rc;
+            std::memcpy(valid, c->hCtl + kCtlHeader, n);
+            return account(sc, *(const DevCounters *)c->hCtl, n, nullptr);
+        }
+        c->ctlDirty = true;
         auto enqueue = [&]() -> int {
             MPLB_CUDA(cudaMemsetAsync(ctl, 0, kCtlHeader, c->stream));
             MPLB_CUDA(cudaMemcpyAsync(c->stage.ptr, c->hStage, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -482,7 +620,11 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
             mapped = nullptr;
         }
     }
-    const bool streamed = !mapped && streamBatch(n) && forcedMode != 0 &&
+    // Streaming (the kernel picks the batch up while it is still arriving) is for page-locked inputs only: there the
+    // host thread merely enqueues asynchronous copies.  A pageable input goes through the bounce buffers, filled by this
+    // thread's OpenMP team -- with several callers at once that team can be descheduled for longer than a resident
+    // kernel should ever wait for its input, so those batches go copy-then-kernel in pieces.
+    const bool streamed = !mapped && streamBatch(n) && forcedMode != 0 && isPinned(states) &&
                           sc->streamStallsInARow.load(std::memory_order_relaxed) < 2;
     // MPLB_TIMELINE=1: print where a streamed call's time goes (diagnostic)
     static const bool timeline = std::getenv("MPLB_TIMELINE") != nullptr;
@@ -520,7 +662,9 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
             return MPLB_OK;
         };
         if (timeline) cudaEventRecord(tl[0], c->copyStream);
-        if (!precopy && (rc = launch())) return rc;
+        // The copies are enqueued before the kernel is launched: the copy engine starts at once and the kernel joins a
+        // few tens of microseconds later (the copy is the longer leg by far), and a host thread that loses the processor
+        // in between leaves nothing on the device waiting for it.
         // MPLB_STREAM_FLAGCOPY (diagnostic): the watermark goes over as a 4-byte copy from page-locked memory instead
         static const bool flagCopy = std::getenv("MPLB_STREAM_FLAGCOPY") != nullptr;
         const std::vector<size_t> pieces = streamPieces(n);
@@ -550,10 +694,8 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
             }
         }
         if (timeline) cudaEventRecord(tl[2], c->copyStream);
-        if (precopy) {
-            MPLB_CUDA(cudaStreamSynchronize(c->copyStream));
-            if ((rc = launch())) return rc;
-        }
+        if (precopy) MPLB_CUDA(cudaStreamSynchronize(c->copyStream));
+        if ((rc = launch())) return rc;
     }
     MPLB_CUDA(cudaMemcpyAsync(valid, dOut, n, cudaMemcpyDeviceToHost, c->stream));
     if (timeline && streamed) cudaEventRecord(tl[4], c->stream);
@@ -630,6 +772,48 @@ static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, siz
         std::memcpy(c->hStage + sb, to, sb);
         std::memcpy(c->hStage + 2 * sb, c->hSteps.data(), n * 4);
         unsigned char *ctl = (unsigned char *)c->ctl.ptr, *in = (unsigned char *)c->stage.ptr;
+        if (c->dStageHost) {
+            // direct return (se3_device.cuh: HostReturn): the first kernel pulls the edges out of mapped host memory,
+            // the last pass's last warp hands dead flags and counters back and rings; no copy engine, no stream sync
+            if (c->ctlDirty) {
+                MPLB_CUDA(cudaMemsetAsync(ctl, 0, kCtlHeader + kCtlTail, c->stream));
+                c->ctlDirty = false;
+            }
+            HostReturn ret;
+            ret.hostCtr = (DevCounters *)c->dCtlHost;
+            ret.flag = (unsigned *)(c->dCtlHost + kCtlHeader - 64);
+            // the call's number travels through pinned memory (the word after the flag), not through the launch
+            // parameters: the scalar call's four kernels replay as one captured graph
+            const unsigned seq = ++c->seq;
+            *(volatile unsigned *)(c->hCtl + kCtlHeader - 60) = seq;
+            ret.seqAt = (const unsigned *)(c->dCtlHost + kCtlHeader - 60);
+            ret.clearWords = (unsigned)((kCtlHeader - sizeof(DevCounters)) / 4 + n);
+            ret.tailAt = (unsigned)(kCtlHeader / 4);
+            ret.tailWords = (unsigned)n;
+            auto enqueueDirect = [&]() -> int {
+                MPLB_CUDA(launchCheckEdges(sc->dev, (const double *)in, (const double *)(in + sb), (const unsigned *)(in + 2 * sb), n,
+                                           (unsigned *)(ctl + kCtlHeader), nullptr, (DevCounters *)ctl,
+                                           (unsigned long long *)(ctl + kCtlHeader - 128), c->aux0.ptr, stackBytes,
+                                           (double *)(in + ((2 * sb + n * 4 + 7) & ~(size_t)7)), sc->numSms, c->stream, true, ret,
+                                           c->dStageHost));
+                return MPLB_OK;
+            };
+            if (n == 1) {
+                const void *now[3] = {c->stage.ptr, c->ctl.ptr, c->aux0.ptr};
+                if ((rc = runScalar(c, c->graphEdge, c->graphEdgeKey, now, 3, c->scalarEdges, enqueueDirect))) return rc;
+            } else if ((rc = enqueueDirect())) {
+                return rc;
+            }
+            sc->hLaunches += 4;
+            if ((rc = awaitRing(c, seq))) return rc;
+            const unsigned *dead = (const unsigned *)(c->hCtl + kCtlHeader);
+            for (size_t i = 0; i < n; ++i) valid[i] = dead[i] ? 0 : 1;
+            rc = account(sc, *(const DevCounters *)c->hCtl, 0, statesChecked);
+            if (timeline)
+                std::fprintf(stderr, "[mplb timeline] %zu edges (small call, direct return): steps planned %.3f ms, done %.3f\n", n, tPlan, sinceMs());
+            return rc;
+        }
+        c->ctlDirty = true;
         auto enqueue = [&]() -> int {
             MPLB_CUDA(cudaMemsetAsync(ctl, 0, kCtlHeader + n * 4, c->stream));
             MPLB_CUDA(cudaMemcpyAsync(in, c->hStage, 2 * sb + n * 4, cudaMemcpyHostToDevice, c->stream));
@@ -782,12 +966,19 @@ void mplb_scene_destroy(mplb_scene *scene) {
     delete b;
 }
 
+static bool coalescing(const SceneBase *b) {
+    static const bool envOn = std::getenv("MPLB_COALESCE") != nullptr;
+    const int c = b->coalesce.load(std::memory_order_relaxed);
+    return c < 0 ? envOn : c != 0;
+}
+
 int mplb_scene_state_dim(const mplb_scene *scene) { return scene ? base(scene)->stateDim : 0; }
 
 int mplb_check_states(mplb_scene *scene, const double *states, size_t n, uint8_t *valid) {
     if (!scene) return fail(MPLB_ERR_INVALID, "scene is null");
     if (n == 0) return MPLB_OK;
     if (!states || !valid) return fail(MPLB_ERR_INVALID, "null buffer");
+    if (n == 1 && coalescing(base(scene))) return base(scene)->combined(0, states, nullptr, valid);
     return base(scene)->checkStates(states, n, valid);
 }
 
@@ -797,6 +988,8 @@ int mplb_check_edges(mplb_scene *scene, const double *from, const double *to, si
     if (states_checked) *states_checked = 0;
     if (n == 0) return MPLB_OK;
     if (!from || !to || !valid) return fail(MPLB_ERR_INVALID, "null buffer");
+    if (n == 1 && !states_checked && coalescing(base(scene)))
+        return base(scene)->combined(1, from, to, valid);
     return base(scene)->checkEdges(from, to, n, valid, states_checked);
 }
 
@@ -849,6 +1042,12 @@ int mplb_check_edges_device(mplb_scene *scene, const double *d_from, const doubl
 double mplb_distance(const mplb_scene *scene, const double *a, const double *b) {
     if (!scene || !a || !b) return NAN;
     return base(scene)->distance(a, b);
+}
+
+int mplb_scene_set_coalescing(mplb_scene *scene, int on) {
+    if (!scene) return fail(MPLB_ERR_INVALID, "scene is null");
+    base(scene)->coalesce.store(on ? 1 : 0, std::memory_order_relaxed);
+    return MPLB_OK;
 }
 
 int mplb_scene_stats(mplb_scene *scene, mplb_stats_t *out, int reset) {

@@ -67,7 +67,10 @@ struct FetchScene : SceneBase {
         for (int i = 0; i < 8; ++i) s += std::fabs(a[i] - b[i]);
         return s;
     }
-    uint64_t edgeSteps(const double *a, const double *b) const { return (uint64_t)std::ceil(distance(a, b) * invStep); }
+    uint64_t edgeSteps(const double *a, const double *b) const {
+        const double x = std::ceil(distance(a, b) * invStep);   // (non-finite: rejected by the callers, never converted)
+        return x < 9.0e18 ? (uint64_t)x : ~0ull;
+    }
     int planEdges(const double *from, const double *to, size_t n, uint32_t *steps) const override {
         for (size_t i = 0; i < n; ++i) {
             const uint64_t st = edgeSteps(from + 8 * i, to + 8 * i);

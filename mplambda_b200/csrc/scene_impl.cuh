@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <atomic>
+#include <memory>
 #include <cmath>
 #include <cstdint>
 #include <mutex>
@@ -39,6 +40,12 @@ struct CallCtx {
     // host->device copy, the kernels, one device->host copy.
     unsigned char *hStage = nullptr, *hCtl = nullptr;   // pinned
     DevBuf stage, ctl;
+    // Direct return (se3_device.cuh: HostReturn): the device's view of the two pinned buffers (null: not mapped), the
+    // call counter the kernel rings back, and whether the device control block still has to be cleared (it is left
+    // clean by every direct-return call; the older copy-in / copy-out sequences clear it themselves on entry)
+    unsigned char *dStageHost = nullptr, *dCtlHost = nullptr;
+    unsigned seq = 0;
+    bool ctlDirty = true;
     // large inputs in pageable memory: two pinned bounce buffers filled by all cores while the previous one is on
     // the wire (cudaMemcpyAsync on pageable memory stages through one thread at ~10 GB/s)
     unsigned char *hBounce[2] = {nullptr, nullptr};
@@ -81,6 +88,30 @@ struct SceneBase {
     std::atomic<uint64_t> hStreamStalls{0}, hAmbiguous{0}, hCoalesced{0};
     size_t envNodeCount = 0, robotNodeCount = 0;
 
+    // Scalar calls -- the reference's isValid(q) / isValid(from, to), one per OpenMP planner thread (prrt.hpp:140-152,
+    // 280-299) -- can share launches (capi.cu: combined()): calls that arrive while earlier ones are on the device ride
+    // together, a lone caller is never delayed.  Off by default: every caller already has its own context and stream,
+    // the device runs their one-CTA kernels side by side, and with T threads at most T calls are in flight, so sharing
+    // a launch only adds the wait for it (measured, 16 threads: 408 k calls/s apart, 274 k shared).  It pays when
+    // launches, not latency, are what is short: more threads than the driver launches concurrently.  [0] states, [1] edges.
+    struct Combiner {
+        static constexpr int kMax = 64;   // calls per launch
+        struct Batch {
+            std::vector<double> a, b;     // [kMax][stateDim] states (or edge starts), edge ends
+            uint8_t out[kMax];
+            int n = 0;                    // under Combiner::mu
+            std::atomic<int> filled{0};   // items whose payload has been copied in
+            std::atomic<int> left{0};     // callers that have read their verdict
+            std::atomic<int> done{0};     // 1: verdicts are there, 2: the launch failed (every caller repeats its own call)
+        };
+        std::mutex mu;
+        std::shared_ptr<Batch> open;      // the batch newcomers join (null: the next caller starts one)
+        std::vector<std::shared_ptr<Batch>> spare;
+        std::atomic<int> inflight{0};     // batches on the device
+    } comb[2];
+    std::atomic<int> coalesce{-1};    // -1: default (off unless MPLB_COALESCE is set), 0 / 1: mplb_scene_set_coalescing
+    int combined(int kind, const double *a, const double *b, uint8_t *valid);
+
     CallCtx *acquire();
     void release(CallCtx *c);
     virtual ~SceneBase();
@@ -121,7 +152,10 @@ struct Se3Scene : SceneBase {
     }
     // se3_rigid_body_scenario.hpp:139
     uint64_t edgeSteps(const double *a, const double *b) const {
-        return (uint64_t)std::ceil(distance(a, b) * invStep);
+        // (a non-finite or huge distance must not reach the integer conversion: that is undefined, and yields 0 for
+        // +inf with the usual x86 sequence -- the callers reject anything >= 2^31)
+        const double x = std::ceil(distance(a, b) * invStep);
+        return x < 9.0e18 ? (uint64_t)x : ~0ull;
     }
 };
 

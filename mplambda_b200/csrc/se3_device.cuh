@@ -36,6 +36,7 @@ struct DevCounters {
     // glibc's acos could round `steps` differently -- the caller re-plans those with host libm; badEdges: non-finite
     unsigned ambiguous, badEdges;
     unsigned ambiguousEdge[kAmbiguousListed];
+    unsigned ticket, ticketPad;   // warps that have finished (direct-return calls, see HostReturn)
 #ifdef MPLB_WARP_TIMES   // diagnostic build: when did the warps start / run out of new work / finish (globaltimer, ns)
     unsigned long long negStart, negFirstDry, negFirstDone, lastDone;   // neg*: ~t, so that atomicMax finds the minimum
     unsigned long long warpDone[4096], warpDry[4096];
@@ -49,11 +50,29 @@ struct DevCounters {
 // (se3_kernels.cu: StateSource).  Pieces end on multiples of 1024 states (the last one is rounded up), and the epoch
 // changes with every call on the word, so the word never needs clearing.  water == nullptr: the batch is resident.
 constexpr unsigned kWaterShift = 22, kWaterUnitBits = 10;
+// Small host calls (the reference's scalar isValid and small planner batches) skip the copy engine both ways: the kernel
+// reads the states from mapped page-locked host memory, writes the verdicts to mapped host memory, and its last warp
+// copies the counters to the host, clears the device control block for the next call (counters, work counters, ticket)
+// and rings the host: *flag = seq, a release store at system scope the calling thread spins on.  One kernel launch per
+// call instead of memset + copy in + kernel + copy out + stream synchronisation.
+struct HostReturn {
+    DevCounters *hostCtr = nullptr;      // mapped host memory
+    unsigned *flag = nullptr;            // mapped host memory
+    unsigned seq = 0;
+    const unsigned *seqAt = nullptr;     // non-null: the value to ring with is read from here (mapped host memory) when
+                                         // the kernel ends -- the launch parameters stay the same from call to call, so
+                                         // a captured graph of the call can be replayed
+    unsigned clearWords = 0;             // 32-bit words to clear after the DevCounters block (work counters, dead flags)
+    unsigned tailAt = 0, tailWords = 0;  // words [tailAt, tailAt + tailWords) of the control block (an edge call's dead
+                                         // flags) are copied to the same place behind hostCtr before they are cleared
+};
+
 struct StreamedInput {
     const double *host = nullptr;   // zero-copy: the batch in mapped page-locked host memory (device-visible address);
                                     // the kernel pulls claims over PCIe itself and mirrors them into dStates
     const unsigned *water = nullptr;
     unsigned epoch = 0;
+    HostReturn ret;                 // flag != nullptr: a direct-return call
 };
 // workZeroed: the caller has already zeroed the first work counter
 cudaError_t launchCheckStates(const SceneDev &sc, const double *dStates, size_t n, uint8_t *dValid,
@@ -66,7 +85,9 @@ size_t edgeStackBytes(int numSms);
 cudaError_t launchCheckEdges(const SceneDev &sc, const double *dFrom, const double *dTo, const unsigned *dSteps,
                              size_t n, unsigned *dDead, uint8_t *dValid, DevCounters *dCtr, unsigned long long *dWork,
                              void *dStacks, size_t stackBytes, double *dEdgeConst, int numSms, cudaStream_t stream,
-                             bool zeroed = false);
+                             bool zeroed = false, HostReturn ret = HostReturn(), const void *hostInputs = nullptr);
+// hostInputs (direct-return calls): from [n][7] | to [n][7] | steps [n] in mapped host memory; the first kernel copies
+// them to dFrom / dTo / dSteps (device memory the passes read again and again) while it forms the per-edge constants
 // dEdgeConst: edgeConstBytes(n) of scratch for the per-edge interpolation constants
 size_t edgeConstBytes(size_t n);
 

@@ -248,6 +248,25 @@ __global__ void edgeConstKernel(const double *__restrict__ from, const double *_
     edgeConstOf(from + 7 * e, to + 7 * e, robotRadius, out + kEdgeConst * e);
 }
 
+// Direct-return host calls: the end states and host-planned step counts arrive in mapped host memory; they are read
+// across the link once, here, and left in device memory for the passes (which read an edge's ends once per sample).
+__global__ void edgeStageKernel(const double *__restrict__ hostIn, unsigned long long n, float robotRadius,
+                                double *__restrict__ from, double *__restrict__ to, unsigned *__restrict__ steps,
+                                double *__restrict__ out) {
+    const unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double a[7], b[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        a[k] = hostIn[7 * e + k];
+        b[k] = hostIn[7 * (n + e) + k];
+        from[7 * e + k] = a[k];
+        to[7 * e + k] = b[k];
+    }
+    steps[e] = reinterpret_cast<const unsigned *>(hostIn + 14 * n)[e];
+    edgeConstOf(a, b, robotRadius, out + kEdgeConst * e);
+}
+
 // Edges named by index (the planner's "node i of the tree -> sample j" without the states crossing PCIe): gathers both
 // end states into dense arrays the edge kernel reads, and plans the edge on the device --
 //   steps = ceil(distance(from, to) * invStepSize)        (se3_rigid_body_scenario.hpp:139, nigh SE3Space distance)
@@ -751,9 +770,6 @@ struct EdgeSource {
         }
     };
     __device__ Fetch fetcher() const { return Fetch{from, to, edgeConst, steps}; }
-    __device__ void sampleState(unsigned e, unsigned i, unsigned st, double s[7]) const {
-        sampleStateOf(from, to, edgeConst, e, i, st, s);
-    }
     static __device__ void sampleStateOf(const double *from, const double *to, const double *edgeConst, unsigned e,
                                          unsigned i, unsigned st, double s[7]) {
         const double *b = to + 7 * (size_t)e;
@@ -791,7 +807,6 @@ struct EdgeSource {
         }
     };
     __device__ Loader loader() const { return Loader{from, to, edgeConst, steps, dead}; }
-    __device__ void stateOf(unsigned t0, unsigned t1, double s[7]) const { sampleState(t0, t1, __ldg(steps + t0), s); }
 
     // warp-collective.  A hit kills the edge; an interval whose traversal reached leaf pairs (touched) and
     // whose middle sample is free hands its two halves to the LIFO; anything else is finished.
@@ -1293,6 +1308,33 @@ __device__ __forceinline__ void flushCounters(const WarpCounters &c, DevCounters
     }
 }
 
+// Direct-return calls (HostReturn): every warp publishes its verdict stores and counter updates, the grid's last warp
+// hands the counters to the host, leaves the device control block clean for the next call and rings the host.
+__device__ __forceinline__ void ringHost(const HostReturn &ret, DevCounters *ctr) {
+    if (!ret.flag) return;
+    const unsigned lane = threadIdx.x & 31u;
+    __threadfence_system();
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(&ctr->ticket, 1u);
+    t = __shfl_sync(kFull, t, 0);
+    if (t != gridDim.x * (blockDim.x >> 5) - 1) return;
+    __threadfence();
+    const unsigned words = sizeof(DevCounters) / 4;
+    unsigned *src = reinterpret_cast<unsigned *>(ctr), *dst = reinterpret_cast<unsigned *>(ret.hostCtr);
+    for (unsigned w = lane; w < words; w += 32) {
+        dst[w] = __ldcg(src + w);
+        src[w] = 0u;
+    }
+    for (unsigned w = lane; w < ret.tailWords; w += 32) dst[ret.tailAt + w] = __ldcg(src + ret.tailAt + w);
+    for (unsigned w = lane; w < ret.clearWords; w += 32) src[words + w] = 0u;
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+        const unsigned seq = ret.seqAt ? *(const volatile unsigned *)ret.seqAt : ret.seq;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ret.flag), "r"(seq) : "memory");
+    }
+}
+
 template <typename E, bool kLatency, bool kStreamed>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MPLB_MIN_CTAS)
 checkStatesKernel(SceneDev sc, const double *states, unsigned long long n, uint8_t *__restrict__ valid,
@@ -1327,6 +1369,7 @@ checkStatesKernel(SceneDev sc, const double *states, unsigned long long n, uint8
     // separately so that the host repeats the batch copy-then-kernel instead of failing
     if (__any_sync(kFull, src.stalled != 0) && (threadIdx.x & 31u) == 0) atomicExch(&ctr->pad, 1u);
     flushCounters(cnt, ctr, false);
+    if constexpr (!kStreamed) ringHost(in.ret, ctr);
 }
 
 template <typename E>
@@ -1336,8 +1379,11 @@ checkEdgesKernel(SceneDev sc, const double *__restrict__ from, const double *__r
                  unsigned *dead,
                  uint4 *stacks, unsigned stackCap, DevCounters *ctr, unsigned long long *workCounter,
                  const uint4 *descIn, const unsigned long long *descCount, uint4 *spillOut,
-                 unsigned long long *spillCount, unsigned spillCap) {
-    if (descIn && *descCount == 0) return;   // nothing was spilled by the previous pass
+                 unsigned long long *spillCount, unsigned spillCap, HostReturn ret) {
+    if (descIn && *descCount == 0) {   // nothing was spilled by the previous pass
+        ringHost(ret, ctr);
+        return;
+    }
     WarpSmem<E> sm = warpSmem<E>(sc.stackLevels);
     EdgeSource src;
     src.from = from; src.to = to; src.edgeConst = edgeConst; src.steps = steps; src.nEdges = nEdges;
@@ -1370,6 +1416,7 @@ checkEdgesKernel(SceneDev sc, const double *__restrict__ from, const double *__r
     }
 #endif
     flushCounters(cnt, ctr, true);
+    ringHost(ret, ctr);
 }
 
 __global__ void deadToValidKernel(const unsigned *__restrict__ dead, unsigned long long n, uint8_t *__restrict__ valid) {
@@ -1442,7 +1489,7 @@ constexpr int kMaxCtasPerSm = 3;
 template <typename E>
 cudaError_t launchEdgesT(const SceneDev &sc, const double *dFrom, const double *dTo, const double *dEdgeConst,
                          const unsigned *dSteps, size_t n, unsigned *dDead, DevCounters *dCtr, unsigned long long *dWork, uint4 *dStacks,
-                         size_t stackBytes, int numSms, cudaStream_t stream) {
+                         size_t stackBytes, int numSms, cudaStream_t stream, const HostReturn &ret = HostReturn()) {
     auto k = checkEdgesKernel<E>;
     const size_t smem = smemBytes<E>(sc);
     int grid = 0;
@@ -1467,7 +1514,8 @@ cudaError_t launchEdgesT(const SceneDev &sc, const double *dFrom, const double *
         const bool last = p == kEdgePasses - 1;
         k<<<grid, threads, smem, stream>>>(sc, dFrom, dTo, dEdgeConst, dSteps, n, dDead, dStacks, kEdgeStackCap, dCtr, dWork + p,
                                            p ? spill[(p - 1) & 1] : nullptr, p ? dWork + 8 + (p - 1) : nullptr,
-                                           last ? nullptr : spill[p & 1], last ? nullptr : dWork + 8 + p, spillCap);
+                                           last ? nullptr : spill[p & 1], last ? nullptr : dWork + 8 + p, spillCap,
+                                           last ? ret : HostReturn());   // the last pass's last warp rings the host
     }
     return cudaGetLastError();
 }
@@ -1493,7 +1541,7 @@ size_t edgeConstBytes(size_t n) { return n * kEdgeConst * sizeof(double); }
 cudaError_t launchCheckEdges(const SceneDev &sc, const double *dFrom, const double *dTo, const unsigned *dSteps,
                              size_t n, unsigned *dDead, uint8_t *dValid, DevCounters *dCtr, unsigned long long *dWork,
                              void *dStacks, size_t stackBytes, double *dEdgeConst, int numSms, cudaStream_t stream,
-                             bool zeroed) {
+                             bool zeroed, HostReturn ret, const void *hostInputs) {
     if (n == 0) return cudaSuccess;
     cudaError_t err = cudaSuccess;
     if (!zeroed) {   // (small host calls zero their one control block -- counters, work counters, dead flags -- at once)
@@ -1502,9 +1550,14 @@ cudaError_t launchCheckEdges(const SceneDev &sc, const double *dFrom, const doub
         err = cudaMemsetAsync(dDead, 0, sizeof(unsigned) * n, stream);
         if (err != cudaSuccess) return err;
     }
-    edgeConstKernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(dFrom, dTo, n, sc.robotRadius, dEdgeConst);
-    err = sc.wide ? launchEdgesT<unsigned long long>(sc, dFrom, dTo, dEdgeConst, dSteps, n, dDead, dCtr, dWork, (uint4 *)dStacks, stackBytes, numSms, stream)
-                  : launchEdgesT<unsigned>(sc, dFrom, dTo, dEdgeConst, dSteps, n, dDead, dCtr, dWork, (uint4 *)dStacks, stackBytes, numSms, stream);
+    if (hostInputs)
+        edgeStageKernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>((const double *)hostInputs, n, sc.robotRadius,
+                                                                      const_cast<double *>(dFrom), const_cast<double *>(dTo),
+                                                                      const_cast<unsigned *>(dSteps), dEdgeConst);
+    else
+        edgeConstKernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(dFrom, dTo, n, sc.robotRadius, dEdgeConst);
+    err = sc.wide ? launchEdgesT<unsigned long long>(sc, dFrom, dTo, dEdgeConst, dSteps, n, dDead, dCtr, dWork, (uint4 *)dStacks, stackBytes, numSms, stream, ret)
+                  : launchEdgesT<unsigned>(sc, dFrom, dTo, dEdgeConst, dSteps, n, dDead, dCtr, dWork, (uint4 *)dStacks, stackBytes, numSms, stream, ret);
     if (err != cudaSuccess) return err;
     if (dValid) deadToValidKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dDead, n, dValid);   // null: the caller reads dDead
     return cudaGetLastError();

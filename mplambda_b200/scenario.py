@@ -153,7 +153,9 @@ class SE3RigidBodyScenario:
             raise ValueError("from/to shape mismatch")
         out = np.empty(len(a), dtype=np.uint8)
         checked = C.c_uint64()
-        _capi.check(_capi.lib().mplb_check_edges(self._h, _ptr(a), _ptr(b), len(a), _ptr(out), C.byref(checked)))
+        # (states_checked is only asked for when wanted: scalar calls that ask for it do not share launches)
+        _capi.check(_capi.lib().mplb_check_edges(self._h, _ptr(a), _ptr(b), len(a), _ptr(out),
+                                                 C.byref(checked) if return_states_checked else None))
         if return_states_checked:
             return out.astype(bool), checked.value
         return out.astype(bool)
@@ -215,6 +217,10 @@ class SE3RigidBodyScenario:
         else:
             _capi.check(L.mplb_check_edges_indexed_device(self._h, d_from_pool, from_rows, d_from_idx, from_div, d_to_pool,
                                                           to_rows, d_to_idx, to_div, n, d_valid, stream))
+
+    def set_coalescing(self, on):
+        """Concurrent scalar isValid calls share launches (on by default; mplb_scene_set_coalescing)."""
+        _capi.check(_capi.lib().mplb_scene_set_coalescing(self._h, int(bool(on))))
 
     def stats(self, reset=False):
         st = _capi.Stats()
@@ -304,7 +310,9 @@ class FetchScenario:
             raise ValueError("from/to shape mismatch")
         out = np.empty(len(a), dtype=np.uint8)
         checked = C.c_uint64()
-        _capi.check(_capi.lib().mplb_check_edges(self._h, _ptr(a), _ptr(b), len(a), _ptr(out), C.byref(checked)))
+        # (states_checked is only asked for when wanted: scalar calls that ask for it do not share launches)
+        _capi.check(_capi.lib().mplb_check_edges(self._h, _ptr(a), _ptr(b), len(a), _ptr(out),
+                                                 C.byref(checked) if return_states_checked else None))
         if return_states_checked:
             return out.astype(bool), checked.value
         return out.astype(bool)

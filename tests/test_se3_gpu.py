@@ -135,17 +135,22 @@ def test_concurrent_callers(scenes, golden):
     assert not errs
 
 
-def test_concurrent_streamed_batches(scenes, oracle):
-    """Four host threads, each with a 2^18-state call (large enough to stream in under the running kernel), on one
-    scene and on two scenes at once: verdicts against the oracle, no stall, streaming still on, and the concurrent
-    calls take no longer than 1.5 x the same calls one after another."""
+@pytest.mark.parametrize("pinned", [True, False])
+def test_concurrent_streamed_batches(scenes, oracle, pinned):
+    """Four host threads, each with a 2^18-state call, on one scene and on two scenes at once: verdicts against the
+    oracle, no stall, streaming still on, and the concurrent calls take no longer than 1.5 x the same calls one after
+    another.  Page-locked inputs stream in under the running kernel; pageable ones (plain numpy arrays) go through the
+    bounce buffers copy-then-kernel."""
     import threading
     import time
+    import torch
     n = 1 << 18
     names = ["twistycool", "cubicles"]
     sc = {k: make(scenes, k) for k in names}
     P = {k: [se3_poses(n, SE3_SCENES[k]["min"], SE3_SCENES[k]["max"], SEED + 40 + t) for t in range(4)] for k in names}
     want = {k: [oracle.SE3Oracle(*scenes[k]).check_states(p, oracle.BVH) for p in P[k]] for k in names}
+    hp = {k: [torch.from_numpy(p).pin_memory() for p in P[k]] for k in names} if pinned else None
+    hv = {k: [torch.empty(n, dtype=torch.uint8).pin_memory() for _ in P[k]] for k in names} if pinned else None
     for k in names:
         sc[k].check_states(P[k][0])   # first-use costs (buffers) outside the timing
 
@@ -154,7 +159,11 @@ def test_concurrent_streamed_batches(scenes, oracle):
 
         def work(i):
             k, t = jobs[i]
-            got[i] = sc[k].check_states(P[k][t])
+            if pinned:
+                sc[k].check_states_ptr(hp[k][t].data_ptr(), n, hv[k][t].data_ptr())
+                got[i] = hv[k][t].numpy().astype(bool)
+            else:
+                got[i] = sc[k].check_states(P[k][t])
         t0 = time.perf_counter()
         if threaded:
             th = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
@@ -205,12 +214,14 @@ def test_large_batch_modes(env, launches):
            "want = np.load(os.path.join(GOLDEN, 'se3_verdicts.npz'))['twistycool_valid']\n"
            "P = se3_poses(len(want), sc['min'], sc['max'], SEED)\n"
            "big = np.concatenate([P] * 40)[:150000]; wbig = np.concatenate([want] * 40)[:150000]\n"
-           "s.stats(reset=True)\n"
-           "assert (s.check_states(big) == wbig).all(); st = s.stats()\n"
-           "assert st['launches'] == %d and st['stream_stalls'] == 0, st\n"
            "pin = torch.from_numpy(big).pin_memory()\n"
+           "s.stats(reset=True)\n"
+           "assert (s.check_states(pin.numpy()) == wbig).all(); st = s.stats()\n"
+           "assert st['launches'] == %d and st['stream_stalls'] == 0, st\n"
            "for _ in range(3): assert (s.check_states(pin.numpy()) == wbig).all()\n"
-           "assert s.stats()['stream_stalls'] == 0\nprint('ok')\n" % launches, env)
+           "s.stats(reset=True)\n"
+           "assert (s.check_states(big) == wbig).all(); st = s.stats()   # pageable: bounce buffers, copy-then-kernel\n"
+           "assert st['launches'] == 4 and st['stream_stalls'] == 0, st\nprint('ok')\n" % launches, env)
 
 
 def test_edge_spill_overflow():
@@ -399,6 +410,67 @@ def test_concurrent_scalar_calls(scenes, golden, oracle):
     [t.start() for t in th]
     [t.join() for t in th]
     assert not errs, errs[:5]
+
+
+@pytest.mark.parametrize("on", [True, False])
+def test_concurrent_scalar_calls_mixed(scenes, golden, oracle, on):
+    """16 threads x mixed isValid(q) / isValid(from,to) scalar calls (unchanged PRRT threads, prrt.hpp:140-152, 280-299),
+    direct-return launches, with and without launch sharing: the verdicts are the oracle's either way, and a non-finite
+    state fails only its own call."""
+    import threading
+    s = make(scenes, "cubicles")
+    s.set_coalescing(on)
+    env, robot = scenes["cubicles"]
+    want = golden["cubicles_valid"]
+    sc = SE3_SCENES["cubicles"]
+    P = se3_poses(len(want), sc["min"], sc["max"], SEED)
+    A = P[want][:96]
+    B = se3_poses(96, sc["min"], sc["max"], SEED + 11)
+    edge_want = oracle.SE3Oracle(env, robot, check_resolution=0.1).check_edges(A, B)
+    errs, raised = [], []
+
+    def work(k):
+        for r in range(60):
+            i = (k * 131 + r * 29) % len(want)
+            if s.isValid(P[i]) != bool(want[i]):
+                errs.append(("state", k, i))
+            if r % 3 == 0:
+                j = (k * 5 + r) % 96
+                if s.isValid(A[j], B[j]) != bool(edge_want[j]):
+                    errs.append(("edge", k, j))
+            if k == 3 and r % 20 == 7:   # one thread feeds garbage now and then: its call raises, nobody else's does
+                worse = B[0].copy(); worse[4] = np.inf
+                try:
+                    s.isValid(A[0], worse)
+                    errs.append(("no error for a non-finite edge", k, r))
+                except Exception:
+                    raised.append(r)
+    th = [threading.Thread(target=work, args=(k,)) for k in range(16)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs[:5]
+    assert len(raised) == 3
+    if not on:
+        assert s.stats()["coalesced_calls"] == 0
+
+
+def test_scalar_calls_from_native_threads(scenes):
+    """The same from 16 native threads (tools/scalar_calls.cpp: no interpreter lock between the callers, so calls really
+    meet on the device): every verdict equals the batched call's, no call fails, and with sharing on calls do share."""
+    import re
+    import subprocess
+    import sys
+    env = dict(os.environ, MPLB_SCALAR_VERIFY="1")
+    out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.dirname(GOLDEN)), "tools", "scalar_calls.py"), "twistycool", "16"],
+                         capture_output=True, text=True, env=env, timeout=300)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("isValid")]
+    assert len(lines) == 4, out.stdout + out.stderr
+    for l in lines:
+        m = re.search(r"coalesce (\d): (\d+) calls/s .* errors (\d+), wrong (\d+), .* coalesced (\d+)", l)
+        assert m, l
+        co, rate, errors, wrong, shared = (int(x) for x in m.groups())
+        assert errors == 0 and wrong == 0 and rate > 1000, l
+        assert (shared > 0) == (co == 1), l
 
 
 def test_hierarchy_cache_gives_the_same_scene(scenes, golden, tmp_path):
