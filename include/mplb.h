@@ -163,6 +163,15 @@ int mplb_nn_nearest(mplb_nn *nn, const double *queries, size_t nq, int64_t *idx,
 /* nearest(nbh, q, k): [nq][k] ascending by (distance, index), padded with -1 / +inf */
 int mplb_nn_knearest(mplb_nn *nn, const double *queries, size_t nq, int k, int64_t *idx,
                      double *dist);
+/* Beyond brute force (nigh's KD-tree strategy, prrt.hpp:35-42): from 16 384 SE(3) keys on the searches go through a
+ * uniform grid over the keys' translations (the metric's translation term bounds the distance from below), rebuilt
+ * when the keys inserted since outgrow a quarter of it; those are searched by brute force meanwhile and the lists
+ * merged.  Results are the brute-force ones bit for bit.  mplb_nn_set_index(nn, 0) keeps a structure on brute force;
+ * mplb_nn_index_info reports the keys indexed, the grid's cells, the FP64 distance evaluations of the indexed searches
+ * so far and the queries that needed the slow exact selection (more candidates than a warp's list holds: duplicates). */
+int mplb_nn_set_index(mplb_nn *nn, int on);
+int mplb_nn_index_info(mplb_nn *nn, size_t *indexed, size_t *cells, uint64_t *exact_evaluations,
+                       uint64_t *slow_queries);
 /* device-resident 1-NN: queries/idx/dist are device pointers, enqueued on `stream`, not synchronised;
  * d_dist holds the device-evaluated distance (CUDA acos: may differ from the host value in the last bit) */
 int mplb_nn_nearest_device(mplb_nn *nn, const double *d_queries, size_t nq, int64_t *d_idx,

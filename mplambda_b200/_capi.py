@@ -67,6 +67,8 @@ _SIGNATURES = {
     "mplb_nn_create": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_void_p)]),
     "mplb_nn_destroy": (None, [C.c_void_p]),
     "mplb_nn_insert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "mplb_nn_set_index": (C.c_int, [C.c_void_p, C.c_int]),
+    "mplb_nn_index_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), u64p, u64p]),
     "mplb_nn_size": (C.c_size_t, [C.c_void_p]),
     "mplb_nn_nearest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "mplb_nn_knearest": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.environ.get("MPLB_OBJ") or os.path.join(HERE, "_obj")
 LIB = os.environ.get("MPLB_LIB") or os.path.join(HERE, "libmplb.so")
-SOURCES = ["capi.cu", "se3_kernels.cu", "nn_capi.cu", "nn_kernels.cu", "fetch_capi.cu", "fetch_kernels.cu",
+SOURCES = ["capi.cu", "se3_kernels.cu", "nn_capi.cu", "nn_kernels.cu", "nn_grid.cu", "fetch_capi.cu", "fetch_kernels.cu",
            "planner_capi.cu", "planner_kernels.cu", "bvh_build.cpp", "collada.cpp", "bvh_cache.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall,-ffp-contract=off,-fopenmp"]

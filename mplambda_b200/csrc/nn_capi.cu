@@ -28,11 +28,21 @@ struct mplb_nn {
     cudaEvent_t scratchDone = nullptr;
     float *hKeyStats = nullptr;    // pinned: {largest |coordinate|, non-unit quaternion seen} of a device-side insert
     DevBuf queries, partDist, partIdx, dist, idx, partVal, thr, keyStats;
+    // Spatial index over the translations of SE(3) keys (nn_grid.cu): keys [0, gridBuilt) are indexed, the ones inserted
+    // since are searched by the brute-force kernels and the two lists merged; rebuilt when that tail outgrows a quarter
+    // of the index.  gridOn: mplb_nn_set_index (default: on from kGridMin keys); gridTried: key count of the last
+    // attempt that found nothing worth indexing (all translations in a handful of cells)
+    bool gridOn = true;
+    size_t gridBuilt = 0, gridTried = 0, gridCells = 0;
+    NnGridGeom grid{};
+    unsigned *hGridBounds = nullptr;   // pinned
+    DevBuf gridBounds, gridStart, gridPerm, gridSorted, gridCellOf, gridCounts, gridDist, gridIdx, tailDist, tailIdx, gridStats;
 
     ~mplb_nn() {
         if (dKeys) cudaFree(dKeys);
         if (dKeys32) cudaFree(dKeys32);
         if (hKeyStats) cudaFreeHost(hKeyStats);
+        if (hGridBounds) cudaFreeHost(hGridBounds);
         if (scratchDone) cudaEventDestroy(scratchDone);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -91,6 +101,126 @@ static void nnNoteKeyStats(mplb_nn *nn, double absMax, bool nonUnit) {
     else if (std::isfinite(nn->keysAbsMax)) nn->keysAbsMax = std::max(nn->keysAbsMax, absMax);
 }
 
+// ---- spatial index ---------------------------------------------------------------------------------------------
+static size_t nnGridMin() {
+    static const size_t v = [] {
+        const char *e = std::getenv("MPLB_NN_GRID_MIN");
+        return e ? (size_t)std::max(1L, std::atol(e)) : (size_t)16384;
+    }();
+    return v;
+}
+
+// (re)builds the index over all keys there are, on `st`; leaves gridBuilt == 0 when the keys do not spread over enough
+// cells to be worth it
+static int nnGridRebuild(mplb_nn *nn, cudaStream_t st) {
+    const size_t n = nn->count;
+    nn->gridTried = n;
+    int rc;
+    if (!nn->hGridBounds && cudaMallocHost((void **)&nn->hGridBounds, 6 * sizeof(unsigned)) != cudaSuccess)
+        return fail(MPLB_ERR_NOMEM, "pinned scratch for the index bounds");
+    if ((rc = nn->gridBounds.reserve(6 * sizeof(unsigned))) || (rc = nn->gridStats.reserve(16))) return rc;
+    MPLB_CUDA(launchNnGridBounds(nn->dKeys, n, (unsigned *)nn->gridBounds.ptr, st));
+    MPLB_CUDA(cudaMemcpyAsync(nn->hGridBounds, nn->gridBounds.ptr, 6 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    MPLB_CUDA(cudaStreamSynchronize(st));
+    double lo[3], ext[3], maxExt = 0;
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = nnGridOrderedToFloat(nn->hGridBounds[a]);
+        ext[a] = (double)nnGridOrderedToFloat(nn->hGridBounds[3 + a]) - lo[a];
+        if (!(ext[a] >= 0) || !std::isfinite(ext[a])) return MPLB_OK;   // (non-finite keys never get here; be safe)
+        maxExt = std::max(maxExt, ext[a]);
+    }
+    int nd = 0;
+    double vol = 1;
+    for (int a = 0; a < 3; ++a)
+        if (ext[a] > 1e-9 * maxExt && ext[a] > 0) {
+            vol *= ext[a];
+            ++nd;
+        }
+    nn->gridBuilt = 0;
+    if (nd == 0) return MPLB_OK;
+    // ~8 keys per cell on average; at most 1024 cells per axis and 2^22 in all
+    double cells = std::min((double)n / 8.0, 4194304.0);
+    double cell = std::pow(vol / cells, 1.0 / nd);
+    NnGridGeom g{};
+    for (int tries = 0; tries < 8; ++tries) {
+        size_t total = 1;
+        for (int a = 0; a < 3; ++a) {
+            g.dims[a] = (int)std::min(1024.0, std::max(1.0, std::ceil(ext[a] / cell * 1.0000001 + 1e-9)));
+            total *= (size_t)g.dims[a];
+        }
+        if (total <= 4194304) break;
+        cell *= 1.3;
+    }
+    const size_t total = (size_t)g.dims[0] * g.dims[1] * g.dims[2];
+    if (total < 64 || total > 4194304) return MPLB_OK;
+    for (int a = 0; a < 3; ++a) {
+        // a cell wide enough for the axis even when the 1024-cell cap is what set dims
+        cell = std::max(cell, ext[a] / g.dims[a] * 1.0000001);
+    }
+    for (int a = 0; a < 3; ++a) g.origin[a] = lo[a] - 1e-6 * cell;
+    g.cell = cell;
+    g.invCell = 1.0 / cell;
+    if ((rc = nn->gridStart.reserve((total + 1) * 4)) || (rc = nn->gridCounts.reserve(total * 4)) ||
+        (rc = nn->gridPerm.reserve(n * 4)) || (rc = nn->gridCellOf.reserve(n * 4)) || (rc = nn->gridSorted.reserve(n * 32)))
+        return rc;
+    MPLB_CUDA(launchNnGridBuild(nn->dKeys, n, g, (unsigned *)nn->gridCellOf.ptr, (unsigned *)nn->gridCounts.ptr,
+                                (unsigned *)nn->gridStart.ptr, (unsigned *)nn->gridPerm.ptr, (float4 *)nn->gridSorted.ptr, st));
+    nn->grid = g;
+    nn->gridBuilt = n;
+    nn->gridCells = total;
+    return MPLB_OK;
+}
+
+// The search itself on `st`, every pointer device memory: through the index (plus the brute-force kernels over the keys
+// inserted since it was built) or by brute force alone.  The caller holds nn->mu and has ordered `st` behind the
+// previous search (the scratch is shared).
+static int nnLaunchSearch(mplb_nn *nn, const double *dQ, size_t nq, int k, double *dDist, long long *dIdx, cudaStream_t st) {
+    int rc;
+    const float absMax = std::isfinite(nn->keysAbsMax) ? std::nextafterf((float)nn->keysAbsMax, INFINITY) : INFINITY;
+    const bool gridOk = nn->gridOn && nn->metric == 0 && std::isfinite(nn->keysAbsMax) && nn->count >= nnGridMin() &&
+                        nn->count < ((size_t)1 << 31);
+    if (!gridOk) nn->gridBuilt = 0;
+    if (gridOk) {
+        const size_t since = nn->count - std::max(nn->gridBuilt, nn->gridTried);
+        if ((nn->gridBuilt == 0 && (nn->gridTried == 0 || since > nn->gridTried)) ||
+            (nn->gridBuilt != 0 && nn->count - nn->gridBuilt > std::max<size_t>(4096, nn->gridBuilt / 4)))
+            if ((rc = nnGridRebuild(nn, st))) return rc;
+    }
+    auto brute = [&](size_t first, double *oDist, long long *oIdx) -> int {
+        const size_t n = nn->count - first;
+        const int slices = nnSlices(nq, n, nn->numSms);
+        int r;
+        if (slices > 1 && ((r = nn->partDist.reserve(nq * slices * k * 8)) || (r = nn->partIdx.reserve(nq * slices * k * 8))))
+            return r;
+        // k == 1: [nq][slices] bounds; k > 1: [nq][k] sample distances + [nq][8] counts + [nq] chosen levels
+        if ((r = nn->partVal.reserve(std::max<size_t>(nq * slices * k * 4, nq * ((size_t)k + 17) * 4))) || (r = nn->thr.reserve(nq * 4)))
+            return r;
+        MPLB_CUDA(launchNnSearch(nn->dKeys + first * nn->dim, nn->dKeys32 + first * nn->dim, absMax, n, nn->dim, nn->metric,
+                                 nn->so3w, nn->l2w, dQ, nq, k, slices, (float *)nn->partVal.ptr, (float *)nn->thr.ptr,
+                                 (double *)nn->partDist.ptr, (long long *)nn->partIdx.ptr, oDist, oIdx, nullptr, st));
+        return MPLB_OK;
+    };
+    if (!gridOk || nn->gridBuilt == 0) return brute(0, dDist, dIdx);
+    const size_t tail = nn->count - nn->gridBuilt;
+    double *gd = dDist;
+    long long *gi = dIdx;
+    if (tail) {
+        if ((rc = nn->gridDist.reserve(nq * k * 8)) || (rc = nn->gridIdx.reserve(nq * k * 8)) ||
+            (rc = nn->tailDist.reserve(nq * k * 8)) || (rc = nn->tailIdx.reserve(nq * k * 8)))
+            return rc;
+        gd = (double *)nn->gridDist.ptr;
+        gi = (long long *)nn->gridIdx.ptr;
+    }
+    MPLB_CUDA(launchNnGridSearch(nn->grid, (const unsigned *)nn->gridStart.ptr, (const unsigned *)nn->gridPerm.ptr,
+                                 (const float4 *)nn->gridSorted.ptr, nn->dKeys, nn->gridBuilt, nn->so3w, nn->l2w, absMax, dQ, nq,
+                                 k, gd, gi, (unsigned long long *)nn->gridStats.ptr, st));
+    if (!tail) return MPLB_OK;
+    if ((rc = brute(nn->gridBuilt, (double *)nn->tailDist.ptr, (long long *)nn->tailIdx.ptr))) return rc;
+    MPLB_CUDA(launchNnMerge2(gd, gi, (const double *)nn->tailDist.ptr, (const long long *)nn->tailIdx.ptr,
+                             (long long)nn->gridBuilt, nq, k, dDist, dIdx, st));
+    return MPLB_OK;
+}
+
 static int nnSearch(mplb_nn *nn, const double *queries, bool deviceQueries, size_t nq, int k, int64_t *idx,
                     double *dist, bool deviceOut, cudaStream_t userStream) {
     if (k < 1 || k > 64) return fail(MPLB_ERR_INVALID, "k must be in [1, 64], got %d", k);
@@ -112,15 +242,9 @@ static int nnSearch(mplb_nn *nn, const double *queries, bool deviceQueries, size
         }
         return MPLB_OK;
     }
-    const int slices = nnSlices(nq, nn->count, nn->numSms);
     int rc;
     if (!deviceQueries && (rc = nnSyncMirror(nn))) return rc;
     MPLB_CUDA(cudaStreamWaitEvent(st, nn->scratchDone, 0));
-    if (slices > 1 && ((rc = nn->partDist.reserve(nq * slices * k * 8)) || (rc = nn->partIdx.reserve(nq * slices * k * 8))))
-        return rc;
-    // k == 1: [nq][slices] bounds; k > 1: [nq][k] sample distances + [nq][8] counts + [nq] chosen levels
-    if ((rc = nn->partVal.reserve(std::max<size_t>(nq * slices * k * 4, nq * ((size_t)k + 17) * 4))) || (rc = nn->thr.reserve(nq * 4)))
-        return rc;
     const double *dQ = queries;
     double *dDist = dist;
     long long *dIdx = (long long *)idx;
@@ -133,10 +257,7 @@ static int nnSearch(mplb_nn *nn, const double *queries, bool deviceQueries, size
         dDist = (double *)nn->dist.ptr;
         dIdx = (long long *)nn->idx.ptr;
     }
-    MPLB_CUDA(launchNnSearch(nn->dKeys, nn->dKeys32, (std::isfinite(nn->keysAbsMax) ? std::nextafterf((float)nn->keysAbsMax, INFINITY) : INFINITY), nn->count, nn->dim,
-                             nn->metric, nn->so3w, nn->l2w, dQ, nq, k, slices, (float *)nn->partVal.ptr,
-                             (float *)nn->thr.ptr, (double *)nn->partDist.ptr, (long long *)nn->partIdx.ptr, dDist, dIdx,
-                             nullptr, st));
+    if ((rc = nnLaunchSearch(nn, dQ, nq, k, dDist, dIdx, st))) return rc;
     MPLB_CUDA(cudaEventRecord(nn->scratchDone, st));
     if (deviceQueries) return MPLB_OK;
     MPLB_CUDA(cudaMemcpyAsync(idx, dIdx, nq * k * 8, cudaMemcpyDeviceToHost, st));
@@ -182,7 +303,33 @@ int mplb_nn_create(int metric, int dim, double so3_weight, double l2_weight, int
         delete nn;
         return fail(MPLB_ERR_CUDA, "could not create the structure's stream / event / pinned scratch");
     }
+    if (nn->gridStats.reserve(16) || cudaMemset(nn->gridStats.ptr, 0, 16) != cudaSuccess) {
+        delete nn;
+        return fail(MPLB_ERR_CUDA, "could not create the structure's index counters");
+    }
     *out = nn;
+    return MPLB_OK;
+}
+
+int mplb_nn_set_index(mplb_nn *nn, int on) {
+    if (!nn) return fail(MPLB_ERR_INVALID, "nn is null");
+    std::lock_guard<std::mutex> g(nn->mu);
+    nn->gridOn = on != 0;
+    if (!on) nn->gridBuilt = nn->gridTried = 0;
+    return MPLB_OK;
+}
+
+int mplb_nn_index_info(mplb_nn *nn, size_t *indexed, size_t *cells, uint64_t *exact_evaluations, uint64_t *slow_queries) {
+    if (!nn) return fail(MPLB_ERR_INVALID, "nn is null");
+    std::lock_guard<std::mutex> g(nn->mu);
+    MPLB_CUDA(cudaSetDevice(nn->device));
+    unsigned long long st[2] = {0, 0};
+    MPLB_CUDA(cudaDeviceSynchronize());
+    MPLB_CUDA(cudaMemcpy(st, nn->gridStats.ptr, sizeof(st), cudaMemcpyDeviceToHost));
+    if (indexed) *indexed = nn->gridBuilt;
+    if (cells) *cells = nn->gridBuilt ? nn->gridCells : 0;
+    if (exact_evaluations) *exact_evaluations = st[0];
+    if (slow_queries) *slow_queries = st[1];
     return MPLB_OK;
 }
 
@@ -311,17 +458,9 @@ void nnUnlock(mplb_nn *nn, size_t added, double absMaxBound) {
 int nnSearchDeviceLocked(mplb_nn *nn, const double *dQueries, size_t nq, int k, long long *dIdx, double *dDist,
                          cudaStream_t st) {
     if (nn->count == 0) return fail(MPLB_ERR_INVALID, "nearest-neighbour structure is empty");
-    const int slices = nnSlices(nq, nn->count, nn->numSms);
     int rc;
-    if (slices > 1 && ((rc = nn->partDist.reserve(nq * slices * k * 8)) || (rc = nn->partIdx.reserve(nq * slices * k * 8))))
-        return rc;
-    if ((rc = nn->partVal.reserve(std::max<size_t>(nq * slices * k * 4, nq * ((size_t)k + 17) * 4))) || (rc = nn->thr.reserve(nq * 4)))
-        return rc;
     MPLB_CUDA(cudaStreamWaitEvent(st, nn->scratchDone, 0));
-    MPLB_CUDA(launchNnSearch(nn->dKeys, nn->dKeys32, (std::isfinite(nn->keysAbsMax) ? std::nextafterf((float)nn->keysAbsMax, INFINITY) : INFINITY), nn->count, nn->dim,
-                             nn->metric, nn->so3w, nn->l2w, dQueries, nq, k, slices, (float *)nn->partVal.ptr,
-                             (float *)nn->thr.ptr, (double *)nn->partDist.ptr, (long long *)nn->partIdx.ptr, dDist, dIdx,
-                             nullptr, st));
+    if ((rc = nnLaunchSearch(nn, dQueries, nq, k, dDist, dIdx, st))) return rc;
     MPLB_CUDA(cudaEventRecord(nn->scratchDone, st));
     return MPLB_OK;
 }

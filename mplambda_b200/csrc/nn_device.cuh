@@ -22,4 +22,27 @@ cudaError_t launchNnSearch(const double *dKeys, const float *dKeys32, float keys
                            float *dPartVal, float *dThr, double *dPartDist, long long *dPartIdx, double *dDist,
                            long long *dIdx, unsigned long long *dExactCount, cudaStream_t stream);
 
+// ---- spatial index over the SE(3) keys' translations (nn_grid.cu)
+struct NnGridGeom {
+    double origin[3];    // lower corner of the grid
+    double cell, invCell;
+    int dims[3];         // cells per axis (x fastest in memory)
+};
+// {min x, y, z, max x, y, z} of the translations of n keys as order-preserving bit patterns (nnGridOrderedToFloat)
+cudaError_t launchNnGridBounds(const double *dKeys, size_t n, unsigned *dOut6, cudaStream_t stream);
+float nnGridOrderedToFloat(unsigned bits);
+// counting sort of keys [0, n) by cell: dStart [cells + 1], dPerm [n] (sorted position -> key index), dSorted [n][2]
+// float4 (FP32 copy in sorted order); dCellOf [n] and dCounts [cells] are scratch
+cudaError_t launchNnGridBuild(const double *dKeys, size_t n, const NnGridGeom &g, unsigned *dCellOf, unsigned *dCounts,
+                              unsigned *dStart, unsigned *dPerm, float4 *dSorted, cudaStream_t stream);
+// exact k nearest among the nBuilt indexed keys, one warp per query: dDist / dIdx [nq][k] ascending by (distance,
+// index), padded with (+inf, -1); dStats (optional): {FP64 evaluations, queries that took the slow selection}
+cudaError_t launchNnGridSearch(const NnGridGeom &g, const unsigned *dStart, const unsigned *dPerm, const float4 *dSorted,
+                               const double *dKeys, size_t nBuilt, double so3w, double l2w, float keysAbsMax,
+                               const double *dQueries, size_t nq, int k, double *dDist, long long *dIdx,
+                               unsigned long long *dStats, cudaStream_t stream);
+// merges two ascending lists per query (B's indices are relative to offB)
+cudaError_t launchNnMerge2(const double *dA, const long long *iA, const double *dB, const long long *iB, long long offB,
+                           size_t nq, int k, double *outD, long long *outI, cudaStream_t stream);
+
 }  // namespace mplb

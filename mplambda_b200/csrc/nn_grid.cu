@@ -20,6 +20,7 @@
 
 #include <cfloat>
 #include <cmath>
+#include <cstring>
 
 namespace mplb {
 namespace {
@@ -143,7 +144,8 @@ struct Cube {
 };
 
 // Visits the keys of the cells of `cube` that are not in `inner` (inner.lo[0] > inner.hi[0]: nothing excluded), a row
-// of cells (contiguous keys) at a time, lanes striding over the keys: f(position in the sorted arrays).
+// of cells (contiguous keys) at a time, lanes striding over the keys: f(position in the sorted arrays, position valid);
+// every lane of the warp makes every call.
 template <typename F>
 __device__ __forceinline__ void forKeys(const NnGridGeom &g, const unsigned *__restrict__ start, const Cube &cube,
                                         const Cube &inner, unsigned lane, F f) {
@@ -158,7 +160,7 @@ __device__ __forceinline__ void forKeys(const NnGridGeom &g, const unsigned *__r
                 const int x1 = split ? (part == 0 ? inner.lo[0] - 1 : cube.hi[0]) : cube.hi[0];
                 if (x0 > x1) continue;
                 const unsigned b = __ldg(start + row + x0), e = __ldg(start + row + x1 + 1);
-                for (unsigned p = b + lane; p < e; p += 32) f(p);
+                for (unsigned at = b; at < e; at += 32) f(at + lane, at + lane < e);   // (warp-uniform trip count)
             }
         }
 }
@@ -197,7 +199,17 @@ nnGridSearchKernel(NnGridGeom g, const unsigned *__restrict__ start, const unsig
 #pragma unroll
     for (int a = 0; a < 3; ++a) c[a] = cellCoord(q[4 + a], g.origin[a], g.invCell, g.dims[a]);
     // histogram levels: level j holds distances <= d0 * 2^(j / 6)
-    const float d0 = fmaxf(l2w32 * (float)g.cell * 0.125f, 1e-20f);
+    // (the top level covers every key there is: the full rotation range plus the way to the farthest corner of the
+    // grid, so that a query far outside the keys' box -- whose cube ends up being the whole grid -- still gets a finite
+    // threshold; 64 levels span a factor 2^(63/6) = 1448 below that)
+    float far2 = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float lo = fabsf((float)(q[4 + a] - g.origin[a])), hi = fabsf((float)(g.origin[a] + g.dims[a] * g.cell - q[4 + a]));
+        far2 = fmaf(fmaxf(lo, hi), fmaxf(lo, hi), far2);
+    }
+    const float dTop = (so3w32 * 1.5708f + l2w32 * sqrtf(far2)) * 1.01f;
+    const float d0 = fmaxf(dTop * (1.f / 1448.f), 1e-20f);
     const float invD0 = 1.f / d0;
     for (int j = lane; j < kGridBins; j += 32) hist[w][j] = 0u;
     if (lane == 0) candN[w] = 0u;
@@ -205,7 +217,8 @@ nnGridSearchKernel(NnGridGeom g, const unsigned *__restrict__ start, const unsig
 
     Cube cube, inner;
     inner.lo[0] = 1; inner.hi[0] = 0;   // nothing scanned yet
-    float T = INFINITY;                 // candidate threshold (FP32 distance)
+    float T = INFINITY, Tlo = 0.f;      // candidate threshold (FP32 distance); (Tlo, T] is the level it came from
+    unsigned under = 0;                 // keys counted under T
     bool whole = false;                 // the cube is the whole grid
     for (int r = 0; !exactOnly; ++r) {
         whole = true;
@@ -227,7 +240,8 @@ nnGridSearchKernel(NnGridGeom g, const unsigned *__restrict__ start, const unsig
                 reach = fminf(reach, (float)((g.origin[a] + (cube.hi[a] + 1) * g.cell) - q[4 + a]));
             }
         }
-        forKeys(g, start, cube, inner, lane, [&](unsigned p) {
+        forKeys(g, start, cube, inner, lane, [&](unsigned p, bool have) {
+            if (!have) return;
             const float4 ka = __ldg(sorted + 2ull * p), kb = __ldg(sorted + 2ull * p + 1);
             const float d = gridDist32(q32, ka, kb, so3w32, l2w32);
             // level of d: smallest j with d <= d0 * 2^(j/6)
@@ -254,6 +268,9 @@ nnGridSearchKernel(NnGridGeom g, const unsigned *__restrict__ start, const unsig
             // rounding of the cell assignment is far more than needed and costs nothing)
             if (whole || t + 2.f * m + 8e-6f * t < l2w32 * reach * 0.999999f) {
                 T = t;
+                Tlo = lvl > 0 ? d0 * exp2f((float)(lvl - 1) * (1.f / 6.f)) * 0.9999f : 0.f;
+                // keys under T: all of the levels up to lvl (the last one is what a finer threshold could shed)
+                under = __shfl_sync(kFullMask, before + h0 + ((lvl & 1) ? h1 : 0u), lvl >> 1);
                 break;
             }
         }
@@ -266,24 +283,64 @@ nnGridSearchKernel(NnGridGeom g, const unsigned *__restrict__ start, const unsig
             cube.hi[a] = g.dims[a] - 1;
         }
     }
+    // A level is 12 % wide.  Around a query inside the keys' cloud that is a factor two in keys; for a query far from it
+    // one level can hold thousands (a thin shell of a large sphere cuts a whole slab out of the cloud).  While far more
+    // keys than k lie under T the level (Tlo, T] is cut into 64 equal parts and the part holding the k-th key becomes
+    // the new level: every key under T is inside the cube, so a pass over the cube sees them all.
+    for (int refine = 0; refine < 3 && T < INFINITY && under > (unsigned)k + kGridCand / 3u; ++refine) {
+        for (int j = lane; j < kGridBins; j += 32) hist[w][j] = 0u;
+        __syncwarp();
+        const float scale = (float)kGridBins / (T - Tlo);
+        unsigned belowLane = 0;
+        inner.lo[0] = 1; inner.hi[0] = 0;
+        forKeys(g, start, cube, inner, lane, [&](unsigned p, bool have) {
+            if (!have) return;
+            const float4 ka = __ldg(sorted + 2ull * p), kb = __ldg(sorted + 2ull * p + 1);
+            const float d = gridDist32(q32, ka, kb, so3w32, l2w32);
+            if (d <= Tlo) ++belowLane;
+            else if (d <= T) atomicAdd(&hist[w][min(kGridBins - 1, (int)((d - Tlo) * scale))], 1u);
+        });
+        __syncwarp();
+        const unsigned below = __reduce_add_sync(kFullMask, belowLane);
+        const unsigned h0 = hist[w][2 * lane], h1 = hist[w][2 * lane + 1];
+        unsigned incl = h0 + h1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned v = __shfl_up_sync(kFullMask, incl, d);
+            if ((int)lane >= d) incl += v;
+        }
+        const unsigned before = below + incl - h0 - h1;
+        int part = before + h0 >= (unsigned)k ? 2 * (int)lane : before + h0 + h1 >= (unsigned)k ? 2 * (int)lane + 1 : 1 << 20;
+        part = __reduce_min_sync(kFullMask, part);
+        if (part >= kGridBins) break;   // (cannot happen: at least k keys lie under T) keep the level as it is
+        if (below >= (unsigned)k) {     // (rounding at the lower edge) the k-th key is not above Tlo after all
+            T = Tlo * 1.0001f;
+            break;
+        }
+        const float width = (T - Tlo) * (1.f / (float)kGridBins);
+        const float newLo = Tlo + width * (float)part * 0.99999f;
+        const float newT = fminf(T, (Tlo + width * (float)(part + 1)) * 1.00001f);
+        under = __shfl_sync(kFullMask, before + h0 + ((part & 1) ? h1 : 0u), part >> 1);
+        Tlo = fminf(newLo, newT);
+        T = newT;
+        if (!(T > Tlo)) break;
+    }
     const float limit = exactOnly ? INFINITY : T + 2.f * m + 8e-6f * fabsf(T);
     inner.lo[0] = 1; inner.hi[0] = 0;
     // pass 2: exact distances of the candidates
     unsigned exact = 0;
-    forKeys(g, start, cube, inner, lane, [&](unsigned p) {
-        bool cand = true;
-        if (!exactOnly) {
+    forKeys(g, start, cube, inner, lane, [&](unsigned p, bool have) {
+        bool cand = have;
+        if (have && !exactOnly) {
             const float4 ka = __ldg(sorted + 2ull * p), kb = __ldg(sorted + 2ull * p + 1);
             cand = gridDist32(q32, ka, kb, so3w32, l2w32) <= limit;
         }
-        // (lanes of the warp may have left the loop: aggregate over the lanes still here)
-        const unsigned act = __activemask();
-        const unsigned mk = __ballot_sync(act, cand);
+        const unsigned mk = __ballot_sync(kFullMask, cand);
         if (!mk) return;
         unsigned base = 0;
         const int leader = __ffs(mk) - 1;
         if ((int)lane == leader) base = atomicAdd(&candN[w], (unsigned)__popc(mk));
-        base = __shfl_sync(act, base, leader);
+        base = __shfl_sync(kFullMask, base, leader);
         if (cand) {
             const unsigned at = base + __popc(mk & ((1u << lane) - 1u));
             if (at < (unsigned)kGridCand) {
@@ -328,7 +385,8 @@ nnGridSearchKernel(NnGridGeom g, const unsigned *__restrict__ start, const unsig
         for (int r = 0; r < k; ++r) {
             double bd = INFINITY;
             long long bi = -1;
-            forKeys(g, start, cube, inner, lane, [&](unsigned p) {
+            forKeys(g, start, cube, inner, lane, [&](unsigned p, bool have) {
+                if (!have) return;
                 if (!exactOnly) {
                     const float4 ka = __ldg(sorted + 2ull * p), kb = __ldg(sorted + 2ull * p + 1);
                     if (!(gridDist32(q32, ka, kb, so3w32, l2w32) <= limit)) return;

@@ -87,3 +87,14 @@ class Nigh:
     def keys_device(self):
         """device pointer of the key array [size, dim] float64 (the pool index-named edges read tree nodes from)."""
         return _capi.lib().mplb_nn_keys_device(self._h) or 0
+
+    def set_index(self, on):
+        """Spatial index on / off (mplb_nn_set_index; on by default from 16 384 SE(3) keys)."""
+        _capi.check(_capi.lib().mplb_nn_set_index(self._h, int(bool(on))))
+
+    def index_info(self):
+        """{indexed keys, cells, FP64 evaluations of indexed searches, queries that took the slow exact selection}"""
+        a, b = C.c_size_t(), C.c_size_t()
+        e, s = C.c_uint64(), C.c_uint64()
+        _capi.check(_capi.lib().mplb_nn_index_info(self._h, C.byref(a), C.byref(b), C.byref(e), C.byref(s)))
+        return {"indexed": a.value, "cells": b.value, "exact_evaluations": e.value, "slow_queries": s.value}

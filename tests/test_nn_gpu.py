@@ -139,3 +139,101 @@ def test_knearest_small_sets_and_duplicates(oracle):
     i, d = nn3.knearest(keys[:10], 20)
     wi, wd = oracle.nn_knearest(dup, keys[:10], 20)
     assert (i == wi).all() and (d == wd).all()
+
+
+# ---- the spatial index (nn_grid.cu): same results as brute force, bit for bit -------------------------------------------
+
+def _both(keys, batches=None):
+    """the same keys in an indexed structure and in one kept on brute force"""
+    a, b = M.Nigh(M.nn.SE3), M.Nigh(M.nn.SE3)
+    b.set_index(False)
+    for part in (batches or [keys]):
+        a.insert(part)
+        b.insert(part)
+    return a, b
+
+
+@pytest.mark.parametrize("k", [1, 8, 45, 64])
+def test_index_equals_brute_force(k, oracle):
+    n = 200000
+    keys = se3_poses(n, LO, HI, 51)
+    qs = np.concatenate([se3_poses(1500, LO, HI, 52),
+                         se3_poses(300, [-900, -700, -500], [900, 700, 500], 53),   # queries far outside the keys' box
+                         keys[:200]])                                              # queries that are keys
+    a, b = _both(keys)
+    ia, da = a.knearest(qs, k)
+    ib, db = b.knearest(qs, k)
+    assert a.index_info()["indexed"] == n and b.index_info()["indexed"] == 0
+    assert (ia == ib).all() and (da == db).all()
+    if k == 1:
+        i1, d1 = a.nearest(qs)
+        assert (i1 == ia[:, 0]).all() and (d1 == da[:, 0]).all()
+    sub = slice(0, 40)
+    wi, wd = oracle.nn_knearest(keys, qs[sub], k)
+    assert (ia[sub] == wi).all() and (da[sub] == wd).all()
+    # far fewer exact evaluations than keys x queries, and no query needed the slow selection
+    info = a.index_info()
+    assert info["exact_evaluations"] < 0.001 * n * len(qs) and info["slow_queries"] == 0, info
+
+
+def test_index_with_inserts_in_between():
+    """The planner's pattern: search, insert a few nodes, search again -- the keys inserted since the last build are
+    searched by brute force and merged; the index is rebuilt when they outgrow a quarter of it."""
+    keys = se3_poses(90000, LO, HI, 61)
+    qs = se3_poses(700, LO, HI, 62)
+    a, b = _both(keys[:30000])
+    for lo, hi in ((30000, 30000), (30000, 33000), (33000, 36500), (36500, 60000), (60000, 90000)):
+        if hi > lo:
+            a.insert(keys[lo:hi]); b.insert(keys[lo:hi])
+        for k in (1, 20):
+            ia, da = a.knearest(qs, k)
+            ib, db = b.knearest(qs, k)
+            assert (ia == ib).all() and (da == db).all(), (lo, hi, k)
+        info = a.index_info()
+        assert 0 < info["indexed"] <= hi and hi - info["indexed"] <= max(4096, info["indexed"] // 4)
+
+
+def test_index_duplicates_ties_and_odd_queries():
+    keys = se3_poses(40000, LO, HI, 71)
+    keys[1000:1700] = keys[999]                       # 701 copies of one key: more candidates than a warp's list holds
+    keys[5000:5040, 4:] = keys[4999, 4:]              # same translation, different rotations
+    qs = np.concatenate([keys[999:1001], keys[4999:5001], se3_poses(50, LO, HI, 72)])
+    odd = se3_poses(6, LO, HI, 73)
+    odd[:3, :4] *= 1.7                                # non-unit quaternions: no FP32 filtering, everything exact
+    qs = np.concatenate([qs, odd])
+    a, b = _both(keys)
+    for k in (1, 64):
+        ia, da = a.knearest(qs, k)
+        ib, db = b.knearest(qs, k)
+        assert (ia == ib).all() and (da == db).all()
+    assert (a.knearest(qs[:1], 64)[0][0] == np.arange(999, 999 + 64)).all()   # ties in insertion order
+    assert a.index_info()["slow_queries"] > 0
+
+
+def test_index_needs_spread_out_translations():
+    """All keys at (nearly) one translation: nothing to index, brute force answers."""
+    keys = se3_poses(20000, LO, HI, 81)
+    keys[:, 4:] = [1.0, 2.0, 3.0]
+    qs = se3_poses(100, LO, HI, 82)
+    a, b = _both(keys)
+    ia, da = a.knearest(qs, 5)
+    ib, db = b.knearest(qs, 5)
+    assert a.index_info()["indexed"] == 0
+    assert (ia == ib).all() and (da == db).all()
+
+
+def test_index_device_queries():
+    import torch
+    keys = se3_poses(60000, LO, HI, 91)
+    qs = se3_poses(512, LO, HI, 92)
+    a, b = _both(keys)
+    dq = torch.from_numpy(qs).cuda()
+    k = 12
+    di = torch.empty((len(qs), k), dtype=torch.int64, device="cuda")
+    dd = torch.empty((len(qs), k), dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    a.knearest_device(dq.data_ptr(), len(qs), k, di.data_ptr(), dd.data_ptr(), st)
+    torch.cuda.synchronize()
+    ib, db = b.knearest(qs, k)
+    assert (di.cpu().numpy() == ib).all()
+    assert np.allclose(dd.cpu().numpy(), db, rtol=0, atol=1e-9)   # device acos vs host libm: last bits
