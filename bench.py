@@ -331,6 +331,7 @@ def extras(local_rank, cpu_seconds):
     keys = se3_poses(1 << 14, sc["min"], sc["max"], SEED)
     qs = se3_poses(1 << 16, sc["min"], sc["max"], SEED + 2)
     nn = M.Nigh(M.nn.SE3, device=local_rank)
+    nn.set_index(False)   # this row is the brute-force scan (16,384 keys is where the index takes over by default)
     nn.insert(keys)
     nn.nearest(qs[:256])
     dt, (idx, dist) = best(lambda: nn.nearest(qs))
@@ -349,7 +350,7 @@ def extras(local_rank, cpu_seconds):
     nms = e0.elapsed_time(e1) / 5
     m = 2048
     t = time.perf_counter(); widx, wdist = O.nn_nearest(keys, qs[:m], threads=thr); dc = time.perf_counter() - t
-    out["nn_home"] = {"metric": "nearest-neighbour queries/sec (brute force, SE3 metric)", "value": len(qs) / dt,
+    out["nn_home"] = {"metric": "nearest-neighbour queries/sec (brute-force scan, SE3 metric, index off)", "value": len(qs) / dt,
                       "unit": "queries/s", "keys": int(len(keys)), "queries": int(len(qs)), "ms": dt * 1e3,
                       "device_resident_ms": nms, "knn32_queries_per_s": (1 << 14) / dtk,
                       "cpu_baseline": {"value": m / dc, "unit": "queries/s", "cores": thr, "kind": "port",
@@ -362,6 +363,51 @@ def extras(local_rank, cpu_seconds):
                                                "28 B / 128 of key reads per query + the query in + (index, distance) out; the scan "
                                                "is bound by FP32 issue (%.0f G pair distances/s), not by HBM"
                                                % (len(qs) * len(keys) / (nms * 1e-3) / 1e9))}
+    # ---- beyond brute force (nigh's KD-tree strategy, prrt.hpp:35-42): 10^6 keys, through the grid index
+    #      and with the index off; k = 45 is PCForest's k at that tree size (pcforest.hpp:512-520)
+    big = se3_poses(1000000, sc["min"], sc["max"], SEED + 5)
+    q1k = qs[:1024]
+    dq1 = dq[:1024]
+    kk = 45
+    dik = torch.empty((1024, kk), dtype=torch.int64, device="cuda")
+    ddk = torch.empty((1024, kk), dtype=torch.float64, device="cuda")
+    row = {}
+    for label, on in (("index", True), ("brute_force", False)):
+        nb = M.Nigh(M.nn.SE3, device=local_rank)
+        nb.set_index(on)
+        nb.insert(big)
+        nb.knearest_device(dq1.data_ptr(), 1024, kk, dik.data_ptr(), ddk.data_ptr(), cs.cuda_stream)
+        nb.nearest_device(dq.data_ptr(), len(qs), di.data_ptr(), dd.data_ptr(), cs.cuda_stream)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record(cs)
+        for _ in range(3):
+            nb.knearest_device(dq1.data_ptr(), 1024, kk, dik.data_ptr(), ddk.data_ptr(), cs.cuda_stream)
+        ev[1].record(cs)
+        nb.nearest_device(dq.data_ptr(), len(qs), di.data_ptr(), dd.data_ptr(), cs.cuda_stream)
+        ev[2].record(cs)
+        torch.cuda.synchronize()
+        row[label] = {"knn45_1024_queries_ms": ev[0].elapsed_time(ev[1]) / 3, "nearest_65536_queries_ms": ev[1].elapsed_time(ev[2]),
+                      "idx": dik.cpu().numpy().copy(), "idx1": di.cpu().numpy().copy(), "info": nb.index_info()}
+        nb.close()
+    m = 32
+    t = time.perf_counter(); wi, _ = O.nn_knearest(big, q1k[:m], kk, threads=thr); dc = time.perf_counter() - t
+    ims = row["index"]["knn45_1024_queries_ms"]
+    out["nn_index_1m"] = {
+        "metric": "k-NN queries/sec against 10^6 SE(3) keys through the grid index (k = 45, 1,024 queries per call, device resident)",
+        "value": 1024 / (ims * 1e-3), "unit": "queries/s", "ms": ims, "brute_force_ms": row["brute_force"]["knn45_1024_queries_ms"],
+        "nearest_65536_queries_ms": row["index"]["nearest_65536_queries_ms"],
+        "nearest_65536_queries_brute_force_ms": row["brute_force"]["nearest_65536_queries_ms"],
+        "cells": int(row["index"]["info"]["cells"]), "slow_queries": int(row["index"]["info"]["slow_queries"]),
+        "equal_to_brute_force": bool((row["index"]["idx"] == row["brute_force"]["idx"]).all()
+                                     and (row["index"]["idx1"] == row["brute_force"]["idx1"]).all()),
+        "cpu_baseline": {"value": m / dc, "unit": "queries/s", "cores": thr, "kind": "port", "sample": "first %d queries, brute force" % m},
+        "neighbour_mismatches_vs_cpu": int((wi != row["index"]["idx"][:m]).sum()),
+        "roofline": hbm_roofline("nnGridSearchKernel", 32.0 * 2 * 4000 + 56 + 16 * kk, 1024, ims,
+                                 "per query: the FP32 keys (32 B) of the ~4,000 keys in reach, read twice (threshold pass, "
+                                 "candidate pass), the query in and k (index, distance) pairs out; one warp per query, bound by "
+                                 "the latency of its dependent row scans, not by HBM")}
+    del big
     # ---- config 4: the addNodeNear pattern batched (pcforest.hpp:512-566) on Home: k-NN of each new node in the
     #      tree, then the motion from the node to each of its k neighbours.  Only indices move: the new nodes go up
     #      once (56 B each), the neighbours are named by index into the tree's device-resident keys.

@@ -125,3 +125,59 @@ def test_sharded_planners_agree_on_the_winner():
     assert isinstance(res[0], tuple) and isinstance(res[1], tuple), res
     assert res[0] == res[1]                  # same cost, same winner, same waypoints on both shards
     assert res[0][3] is True and res[0][1] in (0, 1)
+
+
+def _bridge_worker(rank, world, port, coord_port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mplambda_b200 import bridge
+        link = bridge.CoordinatorLink(77, "127.0.0.1", coord_port) if rank == 0 else None
+        bx = bridge.BridgedExchange(sharding.SolutionExchange(state_dim=7), link)
+        # rank 1 solves first: rank 0 forwards the group's best upstream (once)
+        mine = np.full((3, 7), 1.0 + rank)
+        cost, who, best = bx.publish(float("inf") if rank == 0 else 8.0, mine, solve_millis=40)
+        assert (cost, who) == (8.0, 1)
+        cost, who, best = bx.publish(float("inf") if rank == 0 else 8.0, mine, solve_millis=50)   # no improvement: not re-sent
+        # the coordinator relays another lambda's cheaper path (the stand-in sends it after the first path it
+        # receives): it joins the exchange as rank 0's candidate and wins on every rank
+        import time
+        for _ in range(100):
+            cost, who, best = bx.publish(float("inf") if rank == 0 else 8.0, mine, solve_millis=60)
+            if cost < 8.0:
+                break
+            time.sleep(0.02)
+        assert (cost, who) == (2.5, 0) and best.shape == (2, 7) and (best[:, 4] == [4.0, 5.0]).all()
+        assert bx.any_done(False) is False
+        assert bx.any_done(rank == 1) is True        # rank 0 tells the coordinator
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_group_best_goes_upstream_and_foreign_paths_come_down():
+    """BridgedExchange: two ranks over gloo, rank 0 linked to a stand-in coordinator speaking packet.hpp's format."""
+    import threading
+    from test_bridge import _coordinator
+    server = socket.socket()
+    server.bind(("127.0.0.1", 0))
+    server.listen(1)
+    log = []
+    foreign = (2.5, np.array([[0, 0, 0, 1.0, 4, 0, 0], [0, 0, 0, 1.0, 5, 0, 0]]))
+    t = threading.Thread(target=_coordinator, args=(server, log, foreign), daemon=True)
+    t.start()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bridge_worker, args=(r, 2, port, server.getsockname()[1], q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    t.join(10)
+    server.close()
+    assert res == {0: "ok", 1: "ok"}, res
+    kinds = [p[0] for p in log]
+    assert kinds == ["hello", "path", "done"], kinds      # one Hello, the group's best once, Done
+    assert log[0][1] == 77 and log[1][1] == 8.0 and log[1][2] == 40 and (log[1][3] == 2.0).all()
