@@ -136,8 +136,17 @@ typedef struct {
     uint64_t ambiguous_steps; /* index-named edges whose device-planned step count was within rounding of an integer
                                  and was re-planned with host libm (mplb_check_edges_indexed)                          */
     uint64_t coalesced_calls; /* scalar calls that shared a launch with other threads' calls (see mplb_scene_set_coalescing) */
+    double min_exact_margin;  /* with mplb_scene_track_margins on: the smallest relative margin |G| any exact (FP64)
+                                 triangle-pair decision had since the last reset -- G = the largest gap an axis leaves
+                                 between the projections over |axis|_1 x the largest coordinate; the pair is disjoint iff
+                                 G > 0.  +inf: none recorded.  The device's sin/acos differ from glibc's by <= 2 ulp (edge
+                                 samples): a verdict could only depend on that if this were ~1e-15 or less.               */
 } mplb_stats_t;
 int mplb_scene_stats(mplb_scene *scene, mplb_stats_t *out, int reset);
+/* Diagnostic: the exact path evaluates all 17 axes of every uncertain pair (no early exit) and records the decision's
+ * margin (mplb_stats_t.min_exact_margin); verdicts are unchanged.  SE(3) scenes; off by default (costs ~2x in the exact
+ * path, which is a few per cent of a batch). */
+int mplb_scene_track_margins(mplb_scene *scene, int on);
 
 /* Scalar calls (n == 1: the reference's isValid(q) / isValid(from, to), issued one per OpenMP planner thread,
  * prrt.hpp:140-152, 280-299) go to the device as ONE kernel launch each: the kernel reads the state from pinned host

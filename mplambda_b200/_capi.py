@@ -14,10 +14,11 @@ OK, ERR_INVALID, ERR_IO, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("checks", "bv_tests", "tri_tests", "exact_tests", "launches",
                                            "env_tris", "robot_tris", "env_nodes", "robot_nodes",
-                                           "stream_stalls", "streaming_off", "ambiguous_steps", "coalesced_calls")]
+                                           "stream_stalls", "streaming_off", "ambiguous_steps", "coalesced_calls")] + \
+               [("min_exact_margin", C.c_double)]
 
     def as_dict(self):
-        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+        return {n: (float if n == "min_exact_margin" else int)(getattr(self, n)) for n, _ in self._fields_}
 
 
 class RrtStatus(C.Structure):
@@ -64,6 +65,7 @@ _SIGNATURES = {
     "mplb_distance": (C.c_double, [C.c_void_p, dp, dp]),
     "mplb_scene_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats), C.c_int]),
     "mplb_scene_set_coalescing": (C.c_int, [C.c_void_p, C.c_int]),
+    "mplb_scene_track_margins": (C.c_int, [C.c_void_p, C.c_int]),
     "mplb_nn_create": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_void_p)]),
     "mplb_nn_destroy": (None, [C.c_void_p]),
     "mplb_nn_insert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),

@@ -1044,6 +1044,21 @@ double mplb_distance(const mplb_scene *scene, const double *a, const double *b) 
     return base(scene)->distance(a, b);
 }
 
+int mplb_scene_track_margins(mplb_scene *scene, int on) {
+    if (!scene) return fail(MPLB_ERR_INVALID, "scene is null");
+    auto *s = dynamic_cast<Se3Scene *>(base(scene));
+    if (!s) return fail(MPLB_ERR_INVALID, "margins are tracked for SE(3) scenes");
+    MPLB_CUDA(cudaSetDevice(s->device));
+    MPLB_CUDA(cudaDeviceSynchronize());
+    if (on && !s->marginWord.ptr) {
+        int rc = s->marginWord.reserve(sizeof(unsigned));
+        if (rc) return rc;
+        MPLB_CUDA(cudaMemset(s->marginWord.ptr, 0, sizeof(unsigned)));
+    }
+    s->dev.minMargin = on ? (unsigned *)s->marginWord.ptr : nullptr;
+    return MPLB_OK;
+}
+
 int mplb_scene_set_coalescing(mplb_scene *scene, int on) {
     if (!scene) return fail(MPLB_ERR_INVALID, "scene is null");
     base(scene)->coalesce.store(on ? 1 : 0, std::memory_order_relaxed);
@@ -1069,7 +1084,19 @@ int mplb_scene_stats(mplb_scene *scene, mplb_stats_t *out, int reset) {
     out->stream_stalls = b->hStreamStalls;
     out->ambiguous_steps = b->hAmbiguous;
     out->coalesced_calls = b->hCoalesced;
+    out->min_exact_margin = INFINITY;
     if (auto *s = dynamic_cast<Se3Scene *>(b)) {
+        if (s->marginWord.ptr) {
+            unsigned w = 0;
+            MPLB_CUDA(cudaMemcpy(&w, s->marginWord.ptr, sizeof(w), cudaMemcpyDeviceToHost));
+            if (w) {
+                const unsigned bits = ~w;
+                float f;
+                std::memcpy(&f, &bits, sizeof(f));
+                out->min_exact_margin = f;
+            }
+            if (reset) MPLB_CUDA(cudaMemset(s->marginWord.ptr, 0, sizeof(unsigned)));
+        }
         out->env_tris = s->nEnvTris;
         out->robot_tris = s->nRobotTris;
         out->streaming_off = s->streamStallsInARow.load(std::memory_order_relaxed) >= 2;

@@ -129,6 +129,7 @@ struct Se3Scene : SceneBase {
     std::atomic<unsigned> streamStallsInARow{0}, unstreamedCalls{0};
     SceneDev dev{};
     DevBuf robotNodes, envNodes, robotTris, envTris, robotTris64, envTris64;
+    DevBuf marginWord;   // mplb_scene_track_margins: the device word SceneDev::minMargin points at
     size_t nEnvTris = 0, nRobotTris = 0;
 
     Se3Scene() { stateDim = 7; }

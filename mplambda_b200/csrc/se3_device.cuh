@@ -25,6 +25,8 @@ struct SceneDev {
     int triEagerLanes;          // ... or any queued pair once at most this many lanes still search
     int stackLevels;            // per-lane LIFO levels = depthA + depthB + 2 (rounded up)
     unsigned rootEntry;         // LIFO entry that expands the root pair (se3_kernels.cu)
+    unsigned *minMargin;        // diagnostic (mplb_scene_track_margins): ~bits of the smallest relative margin of an exact
+                                // triangle-pair decision so far; null: not tracked (the exact path exits early)
 };
 
 constexpr unsigned kAmbiguousListed = 14;   // ambiguous edges listed by index (more are only counted)

@@ -175,15 +175,57 @@ __device__ __noinline__ bool triTriExact(const double *P, const double *Q, const
     return true;
 }
 
+// Diagnostic twin of triTriExact (SceneDev::trackMargins): all 17 axes, no early exit, and besides the verdict the
+// decision's margin -- G = the largest gap any axis leaves between the two projections, relative to |axis|_1 times the
+// largest coordinate (the scale rounding errors of the coordinates enter with).  The pair is disjoint iff G > 0; |G|
+// says how far the inputs were from the other verdict.  CUDA's sin/acos (edge samples) differ from glibc's by <= 2 ulp,
+// ~1e-16 relative: a verdict can only depend on that when |G| is of that order.
+__device__ __noinline__ bool triTriExactMargin(const double *P, const double *Q, const XformD &X, float &margin) {
+    D3 P1 = {P[0], P[1], P[2]}, P2 = {P[3], P[4], P[5]}, P3 = {P[6], P[7], P[8]};
+    D3 Q1 = xfApplyD(X, {Q[0], Q[1], Q[2]}), Q2 = xfApplyD(X, {Q[3], Q[4], Q[5]}), Q3 = xfApplyD(X, {Q[6], Q[7], Q[8]});
+    D3 p1 = d3sub(P1, P1), p2 = d3sub(P2, P1), p3 = d3sub(P3, P1);
+    D3 q1 = d3sub(Q1, P1), q2 = d3sub(Q2, P1), q3 = d3sub(Q3, P1);
+    D3 e[3] = {d3sub(p2, p1), d3sub(p3, p2), d3sub(p1, p3)};
+    D3 f[3] = {d3sub(q2, q1), d3sub(q3, q2), d3sub(q1, q3)};
+    D3 n1 = d3cross(e[0], e[1]), m1 = d3cross(f[0], f[1]);
+    auto amax = [](D3 a) { return fmax(fabs(a.x), fmax(fabs(a.y), fabs(a.z))); };
+    const double U = fmax(fmax(fmax(amax(p2), amax(p3)), fmax(amax(q1), amax(q2))), amax(q3));
+    double G = -1e300;
+    bool sep = false;
+    auto axis = [&](D3 ax) {
+        const double a1 = fabs(ax.x) + fabs(ax.y) + fabs(ax.z);
+        double Pv1 = d3dot(ax, p1), Pv2 = d3dot(ax, p2), Pv3 = d3dot(ax, p3);
+        double Qv1 = d3dot(ax, q1), Qv2 = d3dot(ax, q2), Qv3 = d3dot(ax, q3);
+        double mx1 = fmax(Pv1, fmax(Pv2, Pv3)), mn1 = fmin(Pv1, fmin(Pv2, Pv3));
+        double mx2 = fmax(Qv1, fmax(Qv2, Qv3)), mn2 = fmin(Qv1, fmin(Qv2, Qv3));
+        if (mn1 > mx2 || mn2 > mx1) sep = true;   // the reference's comparisons, unchanged
+        if (a1 > 0 && U > 0) G = fmax(G, fmax(mn1 - mx2, mn2 - mx1) / (a1 * U));
+    };
+    axis(n1);
+    axis(m1);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) axis(d3cross(e[i], f[j]));
+    for (int i = 0; i < 3; ++i) axis(d3cross(e[i], n1));
+    for (int i = 0; i < 3; ++i) axis(d3cross(f[i], m1));
+    margin = G > -1e299 ? (float)fabs(G) : INFINITY;
+    return !sep;
+}
+
 // The exact re-evaluation of one triangle pair, out of line: the state is rebuilt from the slot's tags by the source's
 // fetcher (a few pointers, passed by value) -- the FP64 code stays out of the hot loop's instruction footprint.
 template <typename Fetch>
-__device__ __noinline__ bool exactPairHit(const Fetch fetch, unsigned t0, unsigned t1, const double *P, const double *Q) {
+__device__ __noinline__ bool exactPairHit(const Fetch fetch, unsigned t0, unsigned t1, const double *P, const double *Q,
+                                          unsigned *minMargin) {
     double s[7];
     fetch.stateOf(t0, t1, s);
     XformD X;
     stateToRelD(s, X);
-    return triTriExact(P, Q, X);
+    if (!minMargin) return triTriExact(P, Q, X);
+    float margin;
+    const bool hit = triTriExactMargin(P, Q, X, margin);
+    // smallest margin so far, kept as ~bits so that the zeroed counter block means "none yet"
+    atomicMax(minMargin, ~__float_as_uint(margin));
+    return hit;
 }
 
 // interpolate.hpp:18-36 with Eigen's slerp; same statements as orc_se3_interpolate.  sin/acos are
@@ -1105,7 +1147,7 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
             bool hit = false;
             if (act)
                 hit = exactPairHit(src.fetcher(), sm.tag0[slot], sm.tag1[slot], sc.robotTris64 + 9 * (size_t)cd.a(en),
-                                   sc.envTris64 + 9 * (size_t)cd.b(en));
+                                   sc.envTris64 + 9 * (size_t)cd.b(en), sc.minMargin);
             cnt.exact += __popc(__ballot_sync(kFull, act));
             if (act0) atomicSub(&sm.pending[slot], 1);
             const Masks64 fresh = slotBits(hit, slot);

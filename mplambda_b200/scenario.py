@@ -218,6 +218,10 @@ class SE3RigidBodyScenario:
             _capi.check(L.mplb_check_edges_indexed_device(self._h, d_from_pool, from_rows, d_from_idx, from_div, d_to_pool,
                                                           to_rows, d_to_idx, to_div, n, d_valid, stream))
 
+    def track_margins(self, on):
+        """Diagnostic: record the smallest margin of the exact triangle-pair decisions (stats()["min_exact_margin"])."""
+        _capi.check(_capi.lib().mplb_scene_track_margins(self._h, int(bool(on))))
+
     def set_coalescing(self, on):
         """Concurrent scalar isValid calls share launches (on by default; mplb_scene_set_coalescing)."""
         _capi.check(_capi.lib().mplb_scene_set_coalescing(self._h, int(bool(on))))

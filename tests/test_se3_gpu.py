@@ -473,6 +473,39 @@ def test_scalar_calls_from_native_threads(scenes):
         assert (shared > 0) == (co == 1), l
 
 
+def test_margins_of_exact_decisions(scenes, golden, oracle):
+    """mplb_scene_track_margins: the exact path runs all 17 axes and records the smallest relative margin; verdicts do not
+    change, random poses and edges stay far from the 1e-13 band the device's sin/acos could matter in, and a pair that
+    touches exactly reports a margin of zero."""
+    s = make(scenes, "cubicles")
+    want = golden["cubicles_valid"]
+    sc = SE3_SCENES["cubicles"]
+    P = se3_poses(len(want), sc["min"], sc["max"], SEED)
+    assert s.stats()["min_exact_margin"] == float("inf")
+    s.track_margins(True)
+    s.stats(reset=True)
+    assert (s.check_states(P) == want).all()
+    st = s.stats(reset=True)
+    assert st["exact_tests"] > 0 and 1e-13 < st["min_exact_margin"] < 1.0, st
+    A = P[want][:400]
+    B = se3_poses(len(A), sc["min"], sc["max"], SEED + 3)
+    env, robot = scenes["cubicles"]
+    assert (s.check_edges(A, B) == oracle.SE3Oracle(env, robot, check_resolution=0.1).check_edges(A, B)).all()
+    st = s.stats(reset=True)
+    assert st["min_exact_margin"] > 1e-13, st
+    s.track_margins(False)
+    s.check_states(P[:2000])
+    assert s.stats()["min_exact_margin"] == float("inf")
+    # two triangles sharing exactly one point: every axis has gap 0 at best -> intersecting, margin 0
+    tri = np.array([[[0.0, 0, 0], [1, 0, 0], [0, 1, 0]]])
+    other = np.array([[[0.0, 0, 0], [-1, 0, 1], [0, -1, 1]]])
+    t = M.SE3RigidBodyScenario(tri, other, [0, 0, 0, 1, 0, 0, 0], [-1, -1, -1], [1, 1, 1], 0.1)
+    t.track_margins(True)
+    q = np.array([[0, 0, 0, 1.0, 0, 0, 0]])
+    assert (t.check_states(q) == oracle.SE3Oracle(tri, other).check_states(q)).all()
+    assert t.stats()["min_exact_margin"] == 0.0
+
+
 def test_hierarchy_cache_gives_the_same_scene(scenes, golden, tmp_path):
     """mplb_set_cache_dir: the second construction of a scene takes both hierarchies from disk (two hits) and checks
     exactly like the first."""
