@@ -624,7 +624,7 @@ static int se3CheckStates(Se3Scene *sc, const double *states, size_t n, uint8_t 
     // host thread merely enqueues asynchronous copies.  A pageable input goes through the bounce buffers, filled by this
     // thread's OpenMP team -- with several callers at once that team can be descheduled for longer than a resident
     // kernel should ever wait for its input, so those batches go copy-then-kernel in pieces.
-    const bool streamed = !mapped && streamBatch(n) && forcedMode != 0 && isPinned(states) &&
+    const bool streamed = !mapped && streamBatch(n) && forcedMode != 0 && isPinned(states) && !sc->dev.minMargin &&
                           sc->streamStallsInARow.load(std::memory_order_relaxed) < 2;
     // MPLB_TIMELINE=1: print where a streamed call's time goes (diagnostic)
     static const bool timeline = std::getenv("MPLB_TIMELINE") != nullptr;

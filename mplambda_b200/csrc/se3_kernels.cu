@@ -214,13 +214,22 @@ __device__ __noinline__ bool triTriExactMargin(const double *P, const double *Q,
 // The exact re-evaluation of one triangle pair, out of line: the state is rebuilt from the slot's tags by the source's
 // fetcher (a few pointers, passed by value) -- the FP64 code stays out of the hot loop's instruction footprint.
 template <typename Fetch>
-__device__ __noinline__ bool exactPairHit(const Fetch fetch, unsigned t0, unsigned t1, const double *P, const double *Q,
-                                          unsigned *minMargin) {
+__device__ __noinline__ bool exactPairHit(const Fetch fetch, unsigned t0, unsigned t1, const double *P, const double *Q) {
     double s[7];
     fetch.stateOf(t0, t1, s);
     XformD X;
     stateToRelD(s, X);
-    if (!minMargin) return triTriExact(P, Q, X);
+    return triTriExact(P, Q, X);
+}
+// the same with the decision's margin recorded (diagnostic; a function of its own so that the one above -- and the
+// kernel around its call -- compile exactly as they do without the diagnostic: an extra argument there cost 25 %)
+template <typename Fetch>
+__device__ __noinline__ bool exactPairHitMargin(const Fetch fetch, unsigned t0, unsigned t1, const double *P, const double *Q,
+                                                unsigned *minMargin) {
+    double s[7];
+    fetch.stateOf(t0, t1, s);
+    XformD X;
+    stateToRelD(s, X);
     float margin;
     const bool hit = triTriExactMargin(P, Q, X, margin);
     // smallest margin so far, kept as ~bits so that the zeroed counter block means "none yet"
@@ -389,8 +398,8 @@ __device__ __forceinline__ void makeSlot(const double s[7], float envRadius, flo
 // (Out of line it was measured slower, 0.786 -> 0.805 ms per 2^20 Alpha poses: the call's register traffic costs more
 // than the ~300 FP64 instructions take from the instruction cache.)
 template <typename Loader>
-__device__ __forceinline__ bool fillSlot(const Loader ld, const uint4 work, int rank, float envRadius, float robotRadius,
-                                      float4 *xf, unsigned *tags) {
+__device__ __forceinline__ bool fillSlotBody(const Loader ld, const uint4 work, int rank, float envRadius, float robotRadius,
+                                             float4 *xf, unsigned *tags) {
     double s[7];
     unsigned t[4];
     float extraSlack;
@@ -402,6 +411,21 @@ __device__ __forceinline__ bool fillSlot(const Loader ld, const uint4 work, int 
     tags[3 * kSlots] = t[3];
     tags[4 * kSlots] = 0;   // pending
     return true;
+}
+
+#ifndef MPLB_EDGE_FILL_OUTLINE
+#define MPLB_EDGE_FILL_OUTLINE 0
+#endif
+template <typename Loader>
+__device__ __noinline__ bool fillSlotOutOfLine(const Loader ld, const uint4 work, int rank, float envRadius, float robotRadius,
+                                               float4 *xf, unsigned *tags) {
+    return fillSlotBody(ld, work, rank, envRadius, robotRadius, xf, tags);
+}
+template <bool kOutline, typename Loader>
+__device__ __forceinline__ bool fillSlot(const Loader ld, const uint4 work, int rank, float envRadius, float robotRadius,
+                                         float4 *xf, unsigned *tags) {
+    if constexpr (kOutline) return fillSlotOutOfLine(ld, work, rank, envRadius, robotRadius, xf, tags);
+    else return fillSlotBody(ld, work, rank, envRadius, robotRadius, xf, tags);
 }
 
 enum TriVerdict : int { kTriNo = 0, kTriYes = 1, kTriUnsure = 2 };
@@ -686,6 +710,39 @@ struct StateSourceT {
 // 65 traversals per edge.  The verdict is the reference's discrete one.
 // Motion bound: translation is a lerp and Eigen's slerp turns at constant rate, so between samples i and m
 // a robot point x moves at most |i-m|/steps * (||dt|| + 2 theta |x|), theta = acos|qa.qb|.
+// pieces of the sample interval [a, b] (a <= b) after `extra` bisections into kids[cnt...], the split points last (they
+// are popped, and can kill the edge, first).  Out of line and rolled up: it runs for a few lanes of a few retirements,
+// and inlined four times with its loops unrolled it was a fifth of checkEdgesKernel's instructions -- a kernel that
+// waits for instruction fetch more than for anything else.
+__device__ __noinline__ unsigned splitHalf(unsigned e, unsigned a, unsigned b, int extra, uint4 *kids, unsigned cnt) {
+    unsigned pa[4], pb[4], np = 1, pts[3], npts = 0;
+    pa[0] = a; pb[0] = b;
+#pragma unroll 1
+    for (int lvl = 0; lvl < extra; ++lvl) {
+        const unsigned cur = np;
+#pragma unroll 1
+        for (unsigned i = 0; i < cur; ++i) {
+            const unsigned x = pa[i], y = pb[i];
+            if (y - x < 2) continue;
+            const unsigned m = x + (y - x) / 2;
+            pts[npts++] = m;
+            pb[i] = m - 1;       // m > x because y - x >= 2
+            pa[np] = m + 1;      // m < y
+            pb[np++] = y;
+        }
+    }
+#pragma unroll 1
+    for (unsigned i = 0; i < np; ++i) kids[cnt++] = make_uint4(e, pa[i], pb[i], 0);
+#pragma unroll 1
+    for (unsigned i = 0; i < npts; ++i) kids[cnt++] = make_uint4(e, pts[i], pts[i], 0);
+    return cnt;
+}
+// (phase, edge) of item f when the item count needs 64 bits: the 64-bit division is a few hundred instructions
+__device__ __noinline__ void itemOf64(unsigned long long f, unsigned long long nEdges, unsigned &ph, unsigned long long &e) {
+    ph = (unsigned)(f / nEdges);
+    e = f % nEdges;
+}
+
 struct EdgeSource {
     static constexpr bool kIntervals = true;   // slots may stand for a whole interval of samples
     const double *from, *to;
@@ -773,8 +830,7 @@ struct EdgeSource {
                 ph = (unsigned)f / (unsigned)nEdges;
                 e = (unsigned)f - ph * (unsigned)nEdges;
             } else {
-                ph = (unsigned)(f / nEdges);
-                e = f % nEdges;
+                itemOf64(f, nEdges, ph, e);
             }
             e += lane;
             while (e >= nEdges) {   // the grab runs into the next phase (lane < 32: more than once only for tiny batches)
@@ -863,25 +919,6 @@ struct EdgeSource {
         // to certify the larger pieces and shortens the chain (measured: 256 Cubicles edges 0.63 -> 0.50 ms
         // with one extra level).
         const int extra = !(poolDry || globalDone) ? 0 : stackCount < 8 ? 2 : stackCount < 32 ? 1 : 0;
-        auto half = [&](unsigned e, unsigned a, unsigned b) {   // a <= b
-            // pieces of [a, b] after `extra` bisections, points last (they are popped, and can kill the edge, first)
-            unsigned pa[4], pb[4], np = 1, pts[3], npts = 0;
-            pa[0] = a; pb[0] = b;
-            for (int lvl = 0; lvl < extra; ++lvl) {
-                const unsigned cur = np;
-                for (unsigned i = 0; i < cur; ++i) {
-                    const unsigned x = pa[i], y = pb[i];
-                    if (y - x < 2) continue;
-                    const unsigned m = x + (y - x) / 2;
-                    pts[npts++] = m;
-                    pb[i] = m - 1;       // m > x because y - x >= 2
-                    pa[np] = m + 1;      // m < y
-                    pb[np++] = y;
-                }
-            }
-            for (unsigned i = 0; i < np; ++i) kids[cnt++] = make_uint4(e, pa[i], pb[i], 0);
-            for (unsigned i = 0; i < npts; ++i) kids[cnt++] = make_uint4(e, pts[i], pts[i], 0);
-        };
         auto one = [&](bool r, unsigned slot, bool isHit, bool isTouched) {
             if (!r) return;
             const unsigned e = sm.tag0[slot], mid = sm.tag1[slot], lo = sm.tag2[slot], hi = sm.tag3[slot];
@@ -890,8 +927,8 @@ struct EdgeSource {
                 return;
             }
             if (hi > lo && isTouched && !((volatile unsigned *)dead)[e]) {
-                if (mid > lo) half(e, lo, mid - 1);
-                if (mid < hi) half(e, mid + 1, hi);
+                if (mid > lo) cnt = splitHalf(e, lo, mid - 1, extra, kids, cnt);
+                if (mid < hi) cnt = splitHalf(e, mid + 1, hi, extra, kids, cnt);
             }
         };
         one(r0, lane, (hit.lo >> lane) & 1u, (touched.lo >> lane) & 1u);
@@ -956,7 +993,7 @@ struct EdgeSource {
 
 // kLatency: the variant launched for small pose batches, where the time to the last verdict is the latency of the
 // heaviest pose and not throughput (see the end of the step loop)
-template <typename E, bool kLatency = false, typename Source>
+template <typename E, bool kLatency = false, bool kMargins = false, typename Source>
 __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCounters &cnt) {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned ltMask = (1u << lane) - 1u;
@@ -1012,7 +1049,7 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
                 unsigned slot = 0;
                 if (take) {
                     slot = sm.list[lane];
-                    take = fillSlot(src.loader(), Source::kIntervals ? sm.work[lane] : make_uint4(0, 0, 0, 0), (int)lane, sc.envRadius, sc.robotRadius, sm.xf[slot],
+                    take = fillSlot<Source::kIntervals && MPLB_EDGE_FILL_OUTLINE>(src.loader(), Source::kIntervals ? sm.work[lane] : make_uint4(0, 0, 0, 0), (int)lane, sc.envRadius, sc.robotRadius, sm.xf[slot],
                                     sm.tag0 + slot);
                 }
                 const Masks64 t = slotBits(take, slot);
@@ -1146,8 +1183,14 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
             const bool act = act0 && !hitM.test(slot);
             bool hit = false;
             if (act)
-                hit = exactPairHit(src.fetcher(), sm.tag0[slot], sm.tag1[slot], sc.robotTris64 + 9 * (size_t)cd.a(en),
-                                   sc.envTris64 + 9 * (size_t)cd.b(en), sc.minMargin);
+                // (the margin-recording twin is only ever referenced from the kMargins instantiations: its mere presence in
+                // the call graph of the regular kernels cost them 25 % -- 0.80 -> 1.01 ms per 2^20 Alpha poses)
+                if constexpr (kMargins)
+                    hit = exactPairHitMargin(src.fetcher(), sm.tag0[slot], sm.tag1[slot], sc.robotTris64 + 9 * (size_t)cd.a(en),
+                                             sc.envTris64 + 9 * (size_t)cd.b(en), sc.minMargin);
+                else
+                    hit = exactPairHit(src.fetcher(), sm.tag0[slot], sm.tag1[slot], sc.robotTris64 + 9 * (size_t)cd.a(en),
+                                       sc.envTris64 + 9 * (size_t)cd.b(en));
             cnt.exact += __popc(__ballot_sync(kFull, act));
             if (act0) atomicSub(&sm.pending[slot], 1);
             const Masks64 fresh = slotBits(hit, slot);
@@ -1377,7 +1420,7 @@ __device__ __forceinline__ void ringHost(const HostReturn &ret, DevCounters *ctr
     }
 }
 
-template <typename E, bool kLatency, bool kStreamed>
+template <typename E, bool kLatency, bool kStreamed, bool kMargins = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MPLB_MIN_CTAS)
 checkStatesKernel(SceneDev sc, const double *states, unsigned long long n, uint8_t *__restrict__ valid,
                   DevCounters *ctr, unsigned long long *workCounter, unsigned guidedShare, StreamedInput in) {
@@ -1391,7 +1434,7 @@ checkStatesKernel(SceneDev sc, const double *states, unsigned long long n, uint8
     auto now = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
     if ((threadIdx.x & 31u) == 0) atomicMax(&ctr->negStart, ~now());
 #endif
-    runWarp<E, kLatency>(sm, sc, src, cnt);
+    runWarp<E, kLatency, kMargins>(sm, sc, src, cnt);
 #ifdef MPLB_WARP_TIMES
     if ((threadIdx.x & 31u) == 0) {
         atomicMax(&ctr->negFirstDry, ~src.dryAt);
@@ -1414,7 +1457,7 @@ checkStatesKernel(SceneDev sc, const double *states, unsigned long long n, uint8
     if constexpr (!kStreamed) ringHost(in.ret, ctr);
 }
 
-template <typename E>
+template <typename E, bool kMargins = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, MPLB_MIN_CTAS)
 checkEdgesKernel(SceneDev sc, const double *__restrict__ from, const double *__restrict__ to,
                  const double *__restrict__ edgeConst, const unsigned *__restrict__ steps, unsigned long long nEdges,
@@ -1444,7 +1487,7 @@ checkEdgesKernel(SceneDev sc, const double *__restrict__ from, const double *__r
     auto now = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
     if ((threadIdx.x & 31u) == 0) atomicMax(&ctr->negStart, ~now());
 #endif
-    runWarp<E>(sm, sc, src, cnt);
+    runWarp<E, false, kMargins>(sm, sc, src, cnt);
 #ifdef MPLB_WARP_TIMES
     if ((threadIdx.x & 31u) == 0) {
         const unsigned w = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
@@ -1509,6 +1552,7 @@ cudaError_t launchStatesT(const SceneDev &sc, const double *dStates, size_t n, u
     static const bool streamedThroughput = std::getenv("MPLB_STREAM_THROUGHPUT") != nullptr;   // diagnostic
     auto k = streamed ? (streamedThroughput ? checkStatesKernel<E, false, true> : checkStatesKernel<E, true, true>)
                       : n < kLatencyBelow ? checkStatesKernel<E, true, false> : checkStatesKernel<E, false, false>;
+    if (sc.minMargin && !streamed) k = checkStatesKernel<E, false, false, true>;   // diagnostic: margins of the exact decisions
     const size_t smem = smemBytes<E>(sc);
     int grid = 0;
     cudaError_t err = gridFor(k, smem, numSms, &grid);
@@ -1532,7 +1576,7 @@ template <typename E>
 cudaError_t launchEdgesT(const SceneDev &sc, const double *dFrom, const double *dTo, const double *dEdgeConst,
                          const unsigned *dSteps, size_t n, unsigned *dDead, DevCounters *dCtr, unsigned long long *dWork, uint4 *dStacks,
                          size_t stackBytes, int numSms, cudaStream_t stream, const HostReturn &ret = HostReturn()) {
-    auto k = checkEdgesKernel<E>;
+    auto k = sc.minMargin ? checkEdgesKernel<E, true> : checkEdgesKernel<E, false>;
     const size_t smem = smemBytes<E>(sc);
     int grid = 0;
     cudaError_t err = gridFor(k, smem, numSms, &grid);
