@@ -46,13 +46,20 @@ namespace {
 #ifndef MPLB_CLAIM_MIN
 #define MPLB_CLAIM_MIN 4
 #endif
+// One CTA per SM, 12 warps: the kernels need ~170 registers to run without spilling their warp state (slot masks, work
+// source, counters) to local memory, and 12 x 32 x 170 is what a register file holds.  Measured against 2 CTAs x 8 warps
+// at 128 registers (2^20 poses): Alpha 0.794 -> 0.744 ms, Cubicles 0.99 -> 0.95, Apartment 4.18 -> 3.40; 65,536 Cubicles
+// edges 0.93 -> 0.79 ms.  (6 x 2, 10, 11, 14 and 16 warps were measured too; 14 and 16 no longer fit Apartment's stacks.)
 #ifndef MPLB_WARPS_PER_CTA
-#define MPLB_WARPS_PER_CTA 8
+#define MPLB_WARPS_PER_CTA 12
+#endif
+#ifndef MPLB_EDGE_WARPS
+#define MPLB_EDGE_WARPS 12
 #endif
 #ifndef MPLB_MIN_CTAS
-#define MPLB_MIN_CTAS 2
+#define MPLB_MIN_CTAS 1
 #endif
-constexpr int kWarpsPerCta = MPLB_WARPS_PER_CTA;
+constexpr int kWarpsStates = MPLB_WARPS_PER_CTA, kWarpsEdges = MPLB_EDGE_WARPS;
 #ifndef MPLB_SLOTS
 #define MPLB_SLOTS 64
 #endif
@@ -1421,14 +1428,14 @@ __device__ __forceinline__ void ringHost(const HostReturn &ret, DevCounters *ctr
 }
 
 template <typename E, bool kLatency, bool kStreamed, bool kMargins = false>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, MPLB_MIN_CTAS)
+__global__ void __launch_bounds__(kWarpsStates * 32, MPLB_MIN_CTAS)
 checkStatesKernel(SceneDev sc, const double *states, unsigned long long n, uint8_t *__restrict__ valid,
                   DevCounters *ctr, unsigned long long *workCounter, unsigned guidedShare, StreamedInput in) {
     WarpSmem<E> sm = warpSmem<E>(sc.stackLevels);
     StateSourceT<kStreamed> src;
     src.states = states; src.n = n; src.valid = valid; src.counter = workCounter;
     src.hostStates = in.host; src.water = in.water; src.epoch = in.epoch;
-    src.crew = (unsigned long long)gridDim.x * kWarpsPerCta * guidedShare;
+    src.crew = (unsigned long long)gridDim.x * (blockDim.x >> 5) * guidedShare;
     WarpCounters cnt;
 #ifdef MPLB_WARP_TIMES
     auto now = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
@@ -1440,7 +1447,7 @@ checkStatesKernel(SceneDev sc, const double *states, unsigned long long n, uint8
         atomicMax(&ctr->negFirstDry, ~src.dryAt);
         atomicMax(&ctr->negFirstDone, ~now());
         atomicMax(&ctr->lastDone, now());
-        const unsigned w = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+        const unsigned w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
         if (w < 4096) {
             ctr->warpDone[w] = now();
             ctr->warpDry[w] = src.dryAt;
@@ -1457,8 +1464,11 @@ checkStatesKernel(SceneDev sc, const double *states, unsigned long long n, uint8
     if constexpr (!kStreamed) ringHost(in.ret, ctr);
 }
 
+#ifndef MPLB_EDGE_MIN_CTAS
+#define MPLB_EDGE_MIN_CTAS MPLB_MIN_CTAS
+#endif
 template <typename E, bool kMargins = false>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, MPLB_MIN_CTAS)
+__global__ void __launch_bounds__(kWarpsEdges * 32, MPLB_EDGE_MIN_CTAS)
 checkEdgesKernel(SceneDev sc, const double *__restrict__ from, const double *__restrict__ to,
                  const double *__restrict__ edgeConst, const unsigned *__restrict__ steps, unsigned long long nEdges,
                  unsigned *dead,
@@ -1473,12 +1483,12 @@ checkEdgesKernel(SceneDev sc, const double *__restrict__ from, const double *__r
     EdgeSource src;
     src.from = from; src.to = to; src.edgeConst = edgeConst; src.steps = steps; src.nEdges = nEdges;
     src.dead = dead;
-    src.crew = 2ull * gridDim.x * kWarpsPerCta;
+    src.crew = 2ull * gridDim.x * (blockDim.x >> 5);
     src.counter = workCounter;
     src.descIn = descIn;
     if (descIn) src.nDesc = min(*descCount, (unsigned long long)spillCap);
     src.spillOut = spillOut; src.spillCount = spillCount; src.spillCap = spillCap;
-    src.stack = stacks + (size_t)(blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)) * stackCap;
+    src.stack = stacks + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * stackCap;
     src.stackCap = stackCap;
     src.robotRadius = sc.robotRadius;
     src.errorFlag = &ctr->overflow;
@@ -1490,7 +1500,7 @@ checkEdgesKernel(SceneDev sc, const double *__restrict__ from, const double *__r
     runWarp<E, false, kMargins>(sm, sc, src, cnt);
 #ifdef MPLB_WARP_TIMES
     if ((threadIdx.x & 31u) == 0) {
-        const unsigned w = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+        const unsigned w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
         atomicMax(&ctr->lastDone, now());
         if (w < 4096) {
             ctr->warpDone[w] = now();
@@ -1510,13 +1520,13 @@ __global__ void deadToValidKernel(const unsigned *__restrict__ dead, unsigned lo
 }
 
 template <typename E>
-size_t smemBytes(const SceneDev &sc) { return WarpSmem<E>::bytes(sc.stackLevels) * kWarpsPerCta; }
+size_t smemBytes(const SceneDev &sc, int warps) { return WarpSmem<E>::bytes(sc.stackLevels) * warps; }
 
 // Resident grid of `kernel` with `smem` bytes of dynamic shared memory on the current device.  The answer (and
 // the opt-in to that much shared memory) is cached per device and size: a scalar isValid(q) is one ~8 us
 // launch, two extra runtime calls in front of it are not free.
 template <typename K>
-cudaError_t gridFor(K kernel, size_t smem, int numSms, int *grid) {
+cudaError_t gridFor(K kernel, size_t smem, int threads, int numSms, int *grid) {
     static std::mutex mu;
     static std::map<std::tuple<const void *, int, size_t>, int> cache;   // (kernels of one signature share this instantiation)
     int dev = 0;
@@ -1533,7 +1543,7 @@ cudaError_t gridFor(K kernel, size_t smem, int numSms, int *grid) {
         err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)most);
         if (err != cudaSuccess) return err;
         int perSm = 0;
-        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kWarpsPerCta * 32, smem);
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, threads, smem);
         if (err != cudaSuccess) return err;
         it = cache.emplace(std::make_tuple(fn, dev, smem), std::max(perSm, 1) * numSms).first;
     }
@@ -1553,14 +1563,14 @@ cudaError_t launchStatesT(const SceneDev &sc, const double *dStates, size_t n, u
     auto k = streamed ? (streamedThroughput ? checkStatesKernel<E, false, true> : checkStatesKernel<E, true, true>)
                       : n < kLatencyBelow ? checkStatesKernel<E, true, false> : checkStatesKernel<E, false, false>;
     if (sc.minMargin && !streamed) k = checkStatesKernel<E, false, false, true>;   // diagnostic: margins of the exact decisions
-    const size_t smem = smemBytes<E>(sc);
+    const size_t smem = smemBytes<E>(sc, kWarpsStates);
     int grid = 0;
-    cudaError_t err = gridFor(k, smem, numSms, &grid);
+    cudaError_t err = gridFor(k, smem, kWarpsStates * 32, numSms, &grid);
     if (err != cudaSuccess) return err;
     // small batches are latency bound: one state per warp, spread over as many SMs as there are
-    grid = (int)std::min<unsigned long long>(grid, (n + kWarpsPerCta - 1) / kWarpsPerCta);
+    grid = (int)std::min<unsigned long long>(grid, (n + kWarpsStates - 1) / kWarpsStates);
     constexpr unsigned guidedShare = 2;   // a warp takes at most 1/(2 x warps) of what is left (1, 4, 8 measured no better)
-    k<<<std::max(grid, 1), kWarpsPerCta * 32, smem, stream>>>(sc, dStates, n, dValid, dCtr, dWork, guidedShare, in);
+    k<<<std::max(grid, 1), kWarpsStates * 32, smem, stream>>>(sc, dStates, n, dValid, dCtr, dWork, guidedShare, in);
     return cudaGetLastError();
 }
 
@@ -1570,27 +1580,27 @@ constexpr unsigned kEdgeStackCap = 2048;   // interval LIFO entries per warp
 #endif
 constexpr int kEdgePasses = MPLB_EDGE_PASSES;   // <= 8
 constexpr unsigned kSpillCap = 1u << 18;   // descriptors one pass can hand to the next (beyond that a warp keeps its own)
-constexpr int kMaxCtasPerSm = 3;
+constexpr int kMaxCtasPerSm = 2;
 
 template <typename E>
 cudaError_t launchEdgesT(const SceneDev &sc, const double *dFrom, const double *dTo, const double *dEdgeConst,
                          const unsigned *dSteps, size_t n, unsigned *dDead, DevCounters *dCtr, unsigned long long *dWork, uint4 *dStacks,
                          size_t stackBytes, int numSms, cudaStream_t stream, const HostReturn &ret = HostReturn()) {
     auto k = sc.minMargin ? checkEdgesKernel<E, true> : checkEdgesKernel<E, false>;
-    const size_t smem = smemBytes<E>(sc);
+    const size_t smem = smemBytes<E>(sc, kWarpsEdges);
     int grid = 0;
-    cudaError_t err = gridFor(k, smem, numSms, &grid);
+    cudaError_t err = gridFor(k, smem, kWarpsEdges * 32, numSms, &grid);
     if (err != cudaSuccess) return err;
     grid = std::min(grid, kMaxCtasPerSm * numSms);
     const unsigned long long nItems = (1ull + kPhaseBSub) * n;   // `to` + the intervals of every edge
-    grid = (int)std::min<unsigned long long>(grid, (nItems + kWarpsPerCta - 1) / kWarpsPerCta);
+    grid = (int)std::min<unsigned long long>(grid, (nItems + kWarpsEdges - 1) / kWarpsEdges);
     grid = std::max(grid, 1);
-    const size_t lifoBytes = (size_t)grid * kWarpsPerCta * kEdgeStackCap * sizeof(uint4);
+    const size_t lifoBytes = (size_t)grid * kWarpsEdges * kEdgeStackCap * sizeof(uint4);
     if (lifoBytes + 2 * (size_t)kSpillCap * sizeof(uint4) > stackBytes) return cudaErrorInvalidValue;
     // dWork: [p] item counter of pass p, [8 + p] number of descriptors spilled by pass p
     uint4 *spill[2] = {dStacks + (stackBytes / sizeof(uint4) - 2 * (size_t)kSpillCap), nullptr};
     spill[1] = spill[0] + kSpillCap;
-    const int threads = kWarpsPerCta * 32;
+    const int threads = kWarpsEdges * 32;
     // MPLB_SPILL_CAP (diagnostic, tests): a small capacity makes the reservations overflow
     static const unsigned spillCap = [] {
         const char *e = std::getenv("MPLB_SPILL_CAP");
@@ -1619,7 +1629,7 @@ cudaError_t launchCheckStates(const SceneDev &sc, const double *dStates, size_t 
 }
 
 size_t edgeStackBytes(int numSms) {
-    return (size_t)numSms * kMaxCtasPerSm * kWarpsPerCta * kEdgeStackCap * sizeof(uint4) + 2 * (size_t)kSpillCap * sizeof(uint4);
+    return (size_t)numSms * kMaxCtasPerSm * kWarpsEdges * kEdgeStackCap * sizeof(uint4) + 2 * (size_t)kSpillCap * sizeof(uint4);
 }
 
 size_t edgeConstBytes(size_t n) { return n * kEdgeConst * sizeof(double); }
