@@ -158,9 +158,10 @@ private:
 //     parent = the neighbour with the cheapest valid connection             (pcforest.hpp:512-540)
 //     rewire every neighbour that gets cheaper through the new node         (pcforest.hpp:548-566)
 //
-// The reference tries parent candidates one by one in increasing cost and stops at the first valid motion; here all
-// candidate motions of all new nodes are ONE isValidBatch call (all rewiring motions another) and the cheapest valid
-// one wins -- the same choice.  Samples of one batch do not see each other, like the reference's concurrent threads.
+// The reference collects parent candidates walking the neighbours in ascending distance up to the first one that is not
+// cheaper than the nearest node, tries them in increasing cost and stops at the first valid motion; here the same
+// candidates of all new nodes are ONE isValidBatch call (all rewiring motions another) and the cheapest valid one wins
+// -- the same choice.  Samples of one batch do not see each other, like the reference's concurrent threads.
 // As in the reference an edge is immutable (node, parent edge, path cost): rewiring gives a node a new edge, its
 // descendants keep the old chain, so every stored cost is the length of a path that exists.
 // (mplambda_b200/planner.py BatchedRRTStar is the same loop; tests/test_planner.py checks it against the CPU oracle.)
@@ -244,7 +245,8 @@ public:
         std::vector<std::int64_t> nbr(m * (std::size_t)k);
         std::vector<double> nd(m * (std::size_t)k);
         check(mplb_nn_knearest(nn_, newKeys.data(), m, k, nbr.data(), nd.data()));
-        // ---- parent selection over every neighbour that would be cheaper than the nearest node
+        // ---- parent selection: the neighbours, in ascending distance, up to the first one that would not be cheaper
+        //      than the nearest node (pcforest.hpp:519-526 stops there: `if (nbrPathCost >= parentCost) break`)
         std::vector<std::uint8_t> rejected(nbr.size(), 0);
         std::vector<std::size_t> at;
         from.clear();
@@ -252,11 +254,10 @@ public:
         for (std::size_t r = 0; r < m; ++r)
             for (int c = 0; c < k; ++c) {
                 const std::size_t x = r * (std::size_t)k + c;
-                if (nbr[x] >= 0 && cost((std::size_t)nbr[x]) + nd[x] < parentCost[r]) {
-                    from.push_back(nodes_[(std::size_t)nbr[x]]);
-                    to.push_back(qn[r]);
-                    at.push_back(x);
-                }
+                if (!(nbr[x] >= 0 && cost((std::size_t)nbr[x]) + nd[x] < parentCost[r])) break;
+                from.push_back(nodes_[(std::size_t)nbr[x]]);
+                to.push_back(qn[r]);
+                at.push_back(x);
             }
         if (!at.empty()) {
             ok = scenario_.isValidBatch(from, to);

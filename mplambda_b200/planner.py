@@ -209,9 +209,12 @@ class BatchedRRTStar(BatchedRRT):
         parent = the neighbour with the cheapest valid connection                 (pcforest.hpp:512-540)
         rewire every neighbour that gets cheaper through the new node             (pcforest.hpp:548-566)
 
-    The reference tries parent candidates one by one in increasing cost and stops at the first valid motion; here
-    all candidate motions of all new nodes are one `check_edges` batch (and all rewiring motions another), and the
-    cheapest valid one wins -- the same choice.  Samples of one batch do not see each other, like the reference's
+    The reference collects parent candidates walking the neighbours in ascending distance up to the first one that is
+    not cheaper than the nearest node, then tries them in increasing cost and stops at the first valid motion; here the
+    same candidates of all new nodes are one `check_edges` batch (and all rewiring motions another), and the cheapest
+    valid one wins -- the same choice.  (Candidates the reference never gets to test, because a cheaper one was valid,
+    are tested here; an invalid one among them is then also skipped in the rewiring step, where the reference would find
+    the reverse motion invalid.)  Samples of one batch do not see each other, like the reference's
     concurrent threads.  As in the reference an Edge is immutable (node, parent edge, length, path cost): rewiring a
     node gives it a new edge, its descendants keep pointing at the old one, so every stored cost is the length of a
     path that exists.  nn needs `knearest` besides insert / nearest; distances come from the nearest-neighbour
@@ -288,8 +291,9 @@ class BatchedRRTStar(BatchedRRT):
         via = nbr_cost + ndist                                               # path cost through each neighbour
         parent_cost = self._cost(near[new]) + dnear[new]
         parent = near[new].copy()
-        # ---- parent selection: every neighbour that would be cheaper than the nearest node
-        rows, cols = np.nonzero(via < parent_cost[:, None])
+        # ---- parent selection: the neighbours, in ascending distance, up to the first one that would not be cheaper
+        #      than the nearest node (pcforest.hpp:519-526 stops there: `if (nbrPathCost >= parentCost) break`)
+        rows, cols = np.nonzero(np.logical_and.accumulate(via < parent_cost[:, None], axis=1))
         rejected = np.zeros_like(have)
         if len(rows):
             v = sc.check_edges(self.nodes[nbr[rows, cols]], qn[rows])
