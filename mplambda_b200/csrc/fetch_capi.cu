@@ -84,7 +84,8 @@ struct FetchScene : SceneBase {
         int rc;
         const size_t pc = fetchPairCap(n), lc = fetchLeafCap(n);
         if ((rc = c->aux0.reserve(n * 144 * sizeof(double))) || (rc = c->aux1.reserve(n)) ||
-            (rc = c->aux2.reserve(n * sizeof(unsigned))) || (rc = c->aux4.reserve(pc * 8)) ||
+            (rc = c->aux2.reserve(n * sizeof(unsigned))) || (rc = c->aux4.reserve(2 * pc * 8)) ||   // the pair list, and behind it the pairs that need MPR
+            
             (rc = c->aux5.reserve(lc * 8)) || (rc = c->aux6.reserve(n * sizeof(unsigned))) || (rc = c->work.reserve(64)) ||
             (rc = c->out.reserve(n)))
             return rc;

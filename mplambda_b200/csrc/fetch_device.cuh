@@ -36,9 +36,10 @@ struct FetchScratch {
     unsigned char *selfHit;      // [n]
     unsigned *envHit;            // [n]
     unsigned *survivors;         // [n] indices of the states that passed the self-collision tests
-    unsigned long long *pairItems, *leafItems;
+    unsigned long long *pairItems, *leafItems;   // pairItems: 2 x pairCap (the pairs that need the exact test follow the list)
     size_t pairCap, leafCap;
-    unsigned *counts;            // [4]: pair list, leaf list, survivor list lengths, env item counter
+    unsigned *counts;            // [8]: pair list, leaf list, survivor list lengths, env item counter, exact-pair list
+                                 //      length, the two fetchMprKernel item cursors
     unsigned char *touched;      // [n] interval items: something came within reach, the interval is not certified
 };
 inline size_t fetchPairCap(size_t n) { return n * 8; }

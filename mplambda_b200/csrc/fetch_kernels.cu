@@ -23,6 +23,7 @@
 //   4 fetchLeafKernel (thread per surviving leaf)   exact shape-triangle MPR
 // Survivors travel through device-side work lists; a full list degrades to inline exact tests.
 #include "fetch_device.cuh"
+#include <cstdlib>
 #include "device_math.cuh"
 
 #include <algorithm>
@@ -287,6 +288,126 @@ __device__ __noinline__ int mprIntersect(const CcdObj &o1, const CcdObj &o2) {
     return r == 0 ? 1 : 0;
 }
 
+// ---- the same algorithm, resumable: one support evaluation per call ---------------------------------------------------
+// ccdMPRIntersect is a chain of Minkowski support evaluations (two shape supports each, by far the bulk of the
+// arithmetic) with a few cross and dot products in between that decide whether it goes on.  Run to completion per lane,
+// a warp serialises over the lanes' different iteration counts (ncu: 8.7 of 32 lanes).  MprState holds what survives
+// between two support evaluations -- the portal, the next direction and where in the algorithm the lane is -- so that a
+// warp can evaluate one support for all of its lanes together, whatever phase each is in, and hand a lane the next work
+// item the moment its test is decided (fetchMprKernel).  Every operation and its order are those of mprDiscoverPortal /
+// mprRefinePortal above: same results, bit for bit.
+struct MprState {
+    D3 P[4];
+    D3 dir;
+    int phase;   // 0 idle, 1..3 discoverPortal's three stages, 4 refinePortal
+    int guard;
+};
+enum : int { kMprIdle = 0, kMprD1 = 1, kMprD2 = 2, kMprD3 = 3, kMprR = 4 };
+
+__device__ __forceinline__ void mprBegin(const CcdObj &o1, const CcdObj &o2, MprState &m) {
+    const D3 origin = {0, 0, 0};
+    m.P[0] = d3sub(objCenter(o1), objCenter(o2));
+    if (ccdVecEq(m.P[0], origin)) m.P[0] = d3add(m.P[0], D3{dmul(kCcdEps, 10.0), 0, 0});
+    m.dir = ccdNormalize(d3neg(m.P[0]));
+    m.phase = kMprD1;
+    m.guard = 0;
+}
+// refinePortal's loop head: the portal's direction, and whether the origin already lies inside -> true: intersecting
+__device__ __forceinline__ bool mprRefineHead(MprState &m) {
+    m.dir = ccdNormalize(d3cross(d3sub(m.P[2], m.P[1]), d3sub(m.P[3], m.P[1])));
+    const double dot = d3dot(m.dir, m.P[1]);
+    return ccdIsZero(dot) || dot > 0;
+}
+// S = support of the Minkowski difference in m.dir.  -> -2: goes on (m.dir is the next direction), 1 intersect,
+// 0 disjoint, -1 iteration guard tripped
+__device__ __forceinline__ int mprAdvance(MprState &m, const D3 S) {
+    double dot;
+    D3 va, vb;
+    if (m.phase == kMprD1) {
+        m.P[1] = S;
+        dot = d3dot(m.P[1], m.dir);
+        if (ccdIsZero(dot) || dot < 0) return 0;
+        m.dir = d3cross(m.P[0], m.P[1]);
+        if (ccdIsZero(d3dot(m.dir, m.dir))) return 1;   // (discoverPortal's 1 and 2 both mean "intersecting")
+        m.dir = ccdNormalize(m.dir);
+        m.phase = kMprD2;
+        return -2;
+    }
+    if (m.phase == kMprD2) {
+        m.P[2] = S;
+        dot = d3dot(m.P[2], m.dir);
+        if (ccdIsZero(dot) || dot < 0) return 0;
+        va = d3sub(m.P[1], m.P[0]);
+        vb = d3sub(m.P[2], m.P[0]);
+        m.dir = ccdNormalize(d3cross(va, vb));
+        dot = d3dot(m.dir, m.P[0]);
+        if (dot > 0) {
+            const D3 t = m.P[1];
+            m.P[1] = m.P[2];
+            m.P[2] = t;
+            m.dir = d3neg(m.dir);
+        }
+        m.phase = kMprD3;
+        m.guard = 0;
+        return -2;
+    }
+    if (m.phase == kMprD3) {
+        bool cont = false;
+        m.P[3] = S;
+        dot = d3dot(m.P[3], m.dir);
+        if (ccdIsZero(dot) || dot < 0) return 0;
+        va = d3cross(m.P[1], m.P[3]);
+        dot = d3dot(va, m.P[0]);
+        if (dot < 0 && !ccdIsZero(dot)) {
+            m.P[2] = m.P[3];
+            cont = true;
+        }
+        if (!cont) {
+            va = d3cross(m.P[3], m.P[2]);
+            dot = d3dot(va, m.P[0]);
+            if (dot < 0 && !ccdIsZero(dot)) {
+                m.P[1] = m.P[3];
+                cont = true;
+            }
+        }
+        if (!cont) {   // portal found: on to refinePortal
+            m.phase = kMprR;
+            m.guard = 0;
+            return mprRefineHead(m) ? 1 : -2;
+        }
+        if (++m.guard >= 10000) return -1;
+        va = d3sub(m.P[1], m.P[0]);
+        vb = d3sub(m.P[2], m.P[0]);
+        m.dir = ccdNormalize(d3cross(va, vb));
+        return -2;
+    }
+    // refinePortal, after its support
+    const D3 v4 = S;
+    dot = d3dot(v4, m.dir);
+    if (!(ccdIsZero(dot) || dot > 0)) return 0;
+    {
+        const double dv1 = d3dot(m.P[1], m.dir), dv2 = d3dot(m.P[2], m.dir), dv3 = d3dot(m.P[3], m.dir), dv4 = d3dot(v4, m.dir);
+        double d1 = dsub(dv4, dv1);
+        const double d2 = dsub(dv4, dv2), d3 = dsub(dv4, dv3);
+        d1 = fmin(d1, d2);
+        d1 = fmin(d1, d3);
+        if (ccdEq(d1, 1e-6) || d1 < 1e-6) return 0;
+    }
+    {
+        const D3 v4v0 = d3cross(v4, m.P[0]);
+        dot = d3dot(m.P[1], v4v0);
+        if (dot > 0) {
+            dot = d3dot(m.P[2], v4v0);
+            if (dot > 0) m.P[1] = v4; else m.P[3] = v4;
+        } else {
+            dot = d3dot(m.P[3], v4v0);
+            if (dot > 0) m.P[2] = v4; else m.P[1] = v4;
+        }
+    }
+    if (++m.guard >= 10000) return -1;
+    return mprRefineHead(m) ? 1 : -2;
+}
+
 // ---- [EXT] fcl boxBox2 reduced to its boolean result
 __device__ bool boxBoxIntersect(const FetchShape &s1, const FrameD &f1, const FetchShape &s2, const FrameD &f2) {
     const double p[3] = {dsub(f2.t[0], f1.t[0]), dsub(f2.t[1], f1.t[1]), dsub(f2.t[2], f1.t[2])};
@@ -468,6 +589,43 @@ __device__ int exactPair(const FetchSceneDev &sc, const double *frames, unsigned
     makeShapeObj(sa, fa, o1);
     makeShapeObj(sb, fb, o2);
     return mprIntersect(o1, o2);
+}
+
+// the two libccd objects of a (state, geometry, triangle) item / of a (state, pair) item
+// (the triangle's frame is the environment's: its quaternion and inverse are the same for every item -- envObjFrame
+// forms them once per thread, leafObjects only fills in the triangle)
+__device__ void envObjFrame(const FetchSceneDev &sc, CcdObj &t) {
+    FrameD ef;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {   // (kernel-parameter space, not global memory)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) ef.R[i][j] = sc.envFrame[4 * i + j];
+        ef.t[i] = sc.envFrame[4 * i + 3];
+    }
+    t.kind = 3;
+    t.a = t.b = t.c = 0;
+    objSetFrame(t, ef);
+}
+__device__ void leafObjects(const FetchSceneDev &sc, const double *frames, unsigned long long state, int g, unsigned tri,
+                            CcdObj &shapeObj, CcdObj &t) {
+    FrameD f;
+    loadFrame(frames + state * 144 + 12 * g, f);
+    makeShapeObj(sc.shapes[g], f, shapeObj);
+    const double *tp = sc.envTris64 + 9 * (size_t)tri;
+    t.p[0] = {tp[0], tp[1], tp[2]};
+    t.p[1] = {tp[3], tp[4], tp[5]};
+    t.p[2] = {tp[6], tp[7], tp[8]};
+    t.cen = {__ddiv_rn(dadd(dadd(tp[0], tp[3]), tp[6]), 3.0), __ddiv_rn(dadd(dadd(tp[1], tp[4]), tp[7]), 3.0),
+             __ddiv_rn(dadd(dadd(tp[2], tp[5]), tp[8]), 3.0)};
+}
+__device__ void pairObjects(const FetchSceneDev &sc, const double *frames, unsigned long long state, int k, CcdObj &o1,
+                            CcdObj &o2) {
+    const int a = kSelfPairs[k][0], b = kSelfPairs[k][1];
+    FrameD fa, fb;
+    loadFrame(frames + state * 144 + 12 * a, fa);
+    loadFrame(frames + state * 144 + 12 * b, fb);
+    makeShapeObj(sc.shapes[a], fa, o1);
+    makeShapeObj(sc.shapes[b], fb, o2);
 }
 
 __device__ int exactLeaf(const FetchSceneDev &sc, const double *frames, unsigned long long state, int g, unsigned tri) {
@@ -683,8 +841,8 @@ __device__ float pairClearance(const FetchSceneDev &sc, int a, int b, const floa
 // Kernel 2, one thread per listed (state, pair) whose boxes are within reach of each other: tighter distance bounds
 // first (they settle most of them), the exact shape-shape test if the shapes may touch at this very state
 __global__ void __launch_bounds__(128)
-fetchPairKernel(FetchSceneDev sc, const double *__restrict__ frames, WorkList pairs, const float2 *__restrict__ slack,
-                unsigned char *touched, unsigned char *selfHit, FetchCounters *ctr) {
+fetchPairKernel(FetchSceneDev sc, const double *__restrict__ frames, WorkList pairs, WorkList exact,
+                const float2 *__restrict__ slack, unsigned char *touched, unsigned char *selfHit, FetchCounters *ctr) {
     const unsigned n = min(*pairs.count, pairs.capacity);
     unsigned tested = 0;
     for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
@@ -720,12 +878,79 @@ fetchPairKernel(FetchSceneDev sc, const double *__restrict__ frames, WorkList pa
             continue;
         }
         if (touched) touched[state] |= 4;
+        // MPR pairs go on to fetchMprKernel (a lane there never waits for another lane's longer test); the one Box x Box
+        // pair -- and whatever does not fit the list -- is decided here
+        if (!(sc.shapes[a].type == 0 && sc.shapes[b].type == 0) && listPush(exact, v)) continue;
         const int r = exactPair(sc, frames, state, k);
         ++tested;
         if (r < 0) atomicExch(&ctr->error, 1u);
         if (r == 1) selfHit[state] = 1;
     }
     if (tested) atomicAdd(&ctr->pairTests, (unsigned long long)tested);
+}
+
+// Kernels 2b / 4, persistent: the exact shape-shape (kLeaf == false: items (state << 8) | pair) and shape-triangle
+// (kLeaf == true: items (state << 28) | geometry << 24 | triangle) tests as resumable MPR.  Every trip through the loop
+// evaluates one Minkowski support for all the lanes of the warp; a lane whose test is decided takes the next item of the
+// list at once.  hit: selfHit (bytes) / envHit (words) per state.
+template <bool kLeaf>
+__global__ void __launch_bounds__(128)
+fetchMprKernel(FetchSceneDev sc, const double *__restrict__ frames, WorkList list, unsigned *cursor, unsigned char *selfHit,
+               unsigned *envHit, FetchCounters *ctr) {
+    const unsigned n = min(*list.count, list.capacity);
+    const unsigned lane = threadIdx.x & 31u;
+    CcdObj o1, o2;
+    MprState m;
+    m.phase = kMprIdle;
+    if (kLeaf) envObjFrame(sc, o2);
+    unsigned long long state = 0;
+    unsigned tested = 0, chunkBase = 0, chunkLeft = 0;
+    bool exhausted = false;
+    for (;;) {
+        const unsigned need = __ballot_sync(0xffffffffu, m.phase == kMprIdle);
+        if (need && !exhausted) {
+            if (chunkLeft == 0) {   // items are claimed 64 per warp and dealt out from registers
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(cursor, 64u);
+                chunkBase = __shfl_sync(0xffffffffu, base, 0);
+                chunkLeft = chunkBase < n ? min(64u, n - chunkBase) : 0u;
+                if (chunkLeft == 0) exhausted = true;
+            }
+            const unsigned rank = __popc(need & ((1u << lane) - 1u));
+            const unsigned take = min((unsigned)__popc(need), chunkLeft);
+            const unsigned at = chunkBase + rank;
+            chunkBase += take;
+            chunkLeft -= take;
+            if (m.phase == kMprIdle && rank < take) {
+                const unsigned long long v = list.items[at];
+                state = kLeaf ? v >> 28 : v >> 8;
+                const bool decided = kLeaf ? envHit[state] != 0u : selfHit[state] != 0;   // by another item of the state
+                if (!decided) {
+                    if (kLeaf) leafObjects(sc, frames, state, (int)((v >> 24) & 15), (unsigned)(v & 0xffffff), o1, o2);
+                    else pairObjects(sc, frames, state, (int)(v & 255), o1, o2);
+                    mprBegin(o1, o2, m);
+                    ++tested;
+                }
+            }
+        }
+        const bool active = m.phase != kMprIdle;
+        if (__ballot_sync(0xffffffffu, active) == 0) {
+            if (exhausted) break;
+            continue;
+        }
+        if (active) {
+            const int r = mprAdvance(m, minkSupport(o1, o2, m.dir));
+            if (r != -2) {
+                if (r < 0) atomicExch(&ctr->error, 1u);
+                if (r == 1) {
+                    if (kLeaf) envHit[state] = 1u;
+                    else selfHit[state] = 1;
+                }
+                m.phase = kMprIdle;
+            }
+        }
+    }
+    if (tested) atomicAdd(kLeaf ? &ctr->leafTests : &ctr->pairTests, (unsigned long long)tested);
 }
 
 __device__ __noinline__ int exactLeafSlow(const FetchSceneDev &sc, const double *frames, unsigned long long state, int g,
@@ -798,13 +1023,19 @@ fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsign
     const unsigned tx = threadIdx.x, nThreads = blockDim.x;
     auto stackAt = [&](int level) -> int & { return stackBase[level * nThreads + tx]; };
     int sp = 0;
-    float4 a0, a1, a2, ae;
+    // What depends on the shape's box and the (constant) environment frame only is formed once per item (device_math.cuh:
+    // obbFrame); a stack entry >= 0 names a PAIR of sibling nodes (entry, entry + 1) whose parent is within reach -- both
+    // are tested in one step, two independent chains of arithmetic per trip through the loop -- and ~node < 0 a single
+    // node (an environment that is one triangle).  The root's own box is not tested: its children are, right away.
+    ObbFrame F;
     unsigned long long state = 0;
     int g = 0;
     float reachSlack = kCullSlack;   // interval items: the box test is inflated by the geometry's displacement
     unsigned bv = 0;
     bool exhausted = false;
     unsigned chunkBase = 0, chunkLeft = 0;
+    const int rootLink = __float_as_int(__ldg(sc.envNodes + 3).w);
+    const int rootEntry = rootLink >= 0 ? rootLink : ~0;
     for (;;) {
         // refill the lanes whose traversal is over
         const unsigned need = __ballot_sync(0xffffffffu, sp == 0);
@@ -831,16 +1062,16 @@ fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsign
                     FrameD fr;
                     loadFrame(frames + state * 144 + 12 * g, fr);
                     // shape box in world coordinates: axes = columns of R
-                    a0 = make_float4((float)fr.R[0][0], (float)fr.R[1][0], (float)fr.R[2][0], (float)fr.t[0]);
-                    a1 = make_float4((float)fr.R[0][1], (float)fr.R[1][1], (float)fr.R[2][1], (float)fr.t[1]);
-                    a2 = make_float4((float)fr.R[0][2], (float)fr.R[1][2], (float)fr.R[2][2], (float)fr.t[2]);
-                    ae = make_float4(geomS[g][0], geomS[g][1], geomS[g][2], 0);
+                    const float4 a0 = make_float4((float)fr.R[0][0], (float)fr.R[1][0], (float)fr.R[2][0], (float)fr.t[0]);
+                    const float4 a1 = make_float4((float)fr.R[0][1], (float)fr.R[1][1], (float)fr.R[2][1], (float)fr.t[1]);
+                    const float4 a2 = make_float4((float)fr.R[0][2], (float)fr.R[1][2], (float)fr.R[2][2], (float)fr.t[2]);
+                    obbFrame(a0, a1, a2, make_float4(geomS[g][0], geomS[g][1], geomS[g][2], 0), x0, x1, x2, F);
                     reachSlack = kCullSlack;
                     if (slack) {
                         const float2 sl = slack[state];
                         reachSlack += (sl.x * geomS[g][3] + sl.y * geomS[g][4]) * 1.0001f + 1e-6f;
                     }
-                    stackAt(sp++) = 0;
+                    stackAt(sp++) = rootEntry;
                 }
             }
         }
@@ -849,27 +1080,35 @@ fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsign
             continue;
         }
         if (sp > 0) {
-            const int node = stackAt(--sp);
-            float4 b0, b1, b2, be;
+            const int entry = stackAt(--sp);
+            const bool pair = entry >= 0;
+            const int node = pair ? entry : ~entry;
+            float4 b0, b1, b2, be, c0, c1, c2, ce;
             if (kSmemNodes) {
                 const float4 *pn = nodesS + 5 * (size_t)node;
                 b0 = pn[0]; b1 = pn[1]; b2 = pn[2]; be = pn[3];
+                const float4 *pm = pair ? pn + 5 : pn;
+                c0 = pm[0]; c1 = pm[1]; c2 = pm[2]; ce = pm[3];
             } else {
                 const float4 *pn = sc.envNodes + 4 * (size_t)node;
                 ldg8(pn, b0, b1);
                 ldg8(pn + 2, b2, be);
+                const float4 *pm = pair ? pn + 4 : pn;
+                ldg8(pm, c0, c1);
+                ldg8(pm + 2, c2, ce);
             }
-            ++bv;
+            bv += pair ? 2u : 1u;
             float dist2;
-            const float gap = obbGap(a0, a1, a2, ae, b0, b1, b2, be, x0, x1, x2, dist2);
-            if (gap <= reachSlack) {
-                const int link = __float_as_int(be.w);
+            const float gapB = obbGapFramed(F, b0, b1, b2, be, dist2);
+            const float gapC = pair ? obbGapFramed(F, c0, c1, c2, ce, dist2) : 3.0e38f;
+            // one survivor at a time: inner nodes hand their children pair to the stack, leaves go to the exact kernel
+            auto survivor = [&](float gap, int link) {
+                if (gap > reachSlack) return;
                 if (link >= 0) {
-                    if (sp + 2 > kEnvStack) {
+                    if (sp + 1 > kEnvStack) {
                         atomicExch(&ctr->error, 1u);
                         sp = 0;
                     } else {
-                        stackAt(sp++) = link + 1;
                         stackAt(sp++) = link;
                     }
                 } else if (gap > kCullSlack) {
@@ -886,7 +1125,9 @@ fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsign
                         }
                     }
                 }
-            }
+            };
+            survivor(gapC, __float_as_int(ce.w));
+            survivor(gapB, __float_as_int(be.w));
         }
     }
     atomicAdd(&ctr->bvTests, (unsigned long long)bv);
@@ -941,14 +1182,23 @@ cudaError_t runFetch(const FetchSceneDev &sc, const double *dStates, const doubl
         e = cudaMemsetAsync(touched, 0, n, stream);
         if (e != cudaSuccess) return e;
     }
-    e = cudaMemsetAsync(w.counts, 0, 4 * sizeof(unsigned), stream);
+    e = cudaMemsetAsync(w.counts, 0, 8 * sizeof(unsigned), stream);
     if (e != cudaSuccess) return e;
     WorkList pairs{w.pairItems, w.counts, (unsigned)std::min<size_t>(w.pairCap, 0xffffffffu)};
     WorkList leaves{w.leafItems, w.counts + 1, (unsigned)std::min<size_t>(w.leafCap, 0xffffffffu)};
     const int exactGrid = numSms * 8;
     fetchFkKernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(sc, dStates, dFrom, dTo, dSteps, dItems, dSlack, dDead, n,
                                                                    w.frames, w.selfHit, touched, pairs, dCtr);
-    fetchPairKernel<<<exactGrid, 128, 0, stream>>>(sc, w.frames, pairs, dSlack, touched, w.selfHit, dCtr);
+    // counts: [4] pairs that need MPR, [5] / [6] item cursors of the two fetchMprKernel launches
+    WorkList exactPairs{w.pairItems + pairs.capacity, w.counts + 4, pairs.capacity};
+    // (measured per 65,536 states: pairs decided inside fetchPairKernel 55-59 us; listed and run through fetchMprKernel
+    // 18 + 52-58 us -- a pair item is two object set-ups for one or two supports, the set-up is what diverges; the
+    // shape-triangle tests gain: 102 -> 85 us.  MPLB_FETCH_MPR_PAIRS=1 / MPLB_FETCH_INLINE_MPR=1 select the other ways.)
+    static const bool inlineMpr = std::getenv("MPLB_FETCH_INLINE_MPR") != nullptr;
+    static const bool mprPairs = std::getenv("MPLB_FETCH_MPR_PAIRS") != nullptr && !inlineMpr;
+    fetchPairKernel<<<exactGrid, 128, 0, stream>>>(sc, w.frames, pairs, mprPairs ? exactPairs : WorkList{nullptr, w.counts + 4, 0u},
+                                                   dSlack, touched, w.selfHit, dCtr);
+    if (mprPairs) fetchMprKernel<false><<<exactGrid, 128, 0, stream>>>(sc, w.frames, exactPairs, w.counts + 5, w.selfHit, w.envHit, dCtr);
     fetchSurvivorsKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w.selfHit, n, w.survivors, w.counts + 2);
     const size_t envSmemBytes = (size_t)sc.nEnvNodes * 80 + (size_t)kEnvStack * kEnvThreads * sizeof(int);
     if (envSmemBytes <= 200 * 1024) {
@@ -960,7 +1210,8 @@ cudaError_t runFetch(const FetchSceneDev &sc, const double *dStates, const doubl
         fetchEnvKernel<false><<<exactGrid, 128, 0, stream>>>(sc, w.frames, w.survivors, w.counts + 2, dSlack, touched, w.envHit,
                                                              leaves, w.counts + 3, dCtr);
     }
-    fetchLeafKernel<<<exactGrid, 128, 0, stream>>>(sc, w.frames, leaves, w.envHit, dCtr);
+    if (inlineMpr) fetchLeafKernel<<<exactGrid, 128, 0, stream>>>(sc, w.frames, leaves, w.envHit, dCtr);
+    else fetchMprKernel<true><<<exactGrid, 128, 0, stream>>>(sc, w.frames, leaves, w.counts + 6, w.selfHit, w.envHit, dCtr);
     return cudaGetLastError();
 }
 

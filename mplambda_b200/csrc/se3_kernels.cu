@@ -1569,7 +1569,10 @@ cudaError_t launchStatesT(const SceneDev &sc, const double *dStates, size_t n, u
     if (err != cudaSuccess) return err;
     // small batches are latency bound: one state per warp, spread over as many SMs as there are
     grid = (int)std::min<unsigned long long>(grid, (n + kWarpsStates - 1) / kWarpsStates);
-    constexpr unsigned guidedShare = 2;   // a warp takes at most 1/(2 x warps) of what is left (1, 4, 8 measured no better)
+#ifndef MPLB_GUIDED_SHARE
+#define MPLB_GUIDED_SHARE 2
+#endif
+    constexpr unsigned guidedShare = MPLB_GUIDED_SHARE;   // a warp takes at most 1/(2 x warps) of what is left (1, 4, 8 measured no better)
     k<<<std::max(grid, 1), kWarpsStates * 32, smem, stream>>>(sc, dStates, n, dValid, dCtr, dWork, guidedShare, in);
     return cudaGetLastError();
 }
