@@ -69,7 +69,8 @@ def test_edges_known_answers(name, scenes, golden):
     assert 0 < checked <= int(golden[name + "_edge_steps"].astype(np.int64).sum()) + len(A)
 
 
-@pytest.mark.parametrize("name,n", [("twistycool", 3000), ("cubicles", 1500), ("alpha15", 1500)])
+@pytest.mark.parametrize("name,n", [("twistycool", 3000), ("cubicles", 1500), ("alpha15", 1500), ("home", 1500),
+                                    ("apartment", 2000)])
 def test_edges_match_oracle(name, n, scenes, oracle):
     env, robot = scenes[name]
     sc = SE3_SCENES[name]
