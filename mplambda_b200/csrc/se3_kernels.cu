@@ -821,6 +821,7 @@ struct EdgeSource {
         }
         // implicit items: item f = (phase f / nEdges, edge f % nEdges), edge-minor so that neighbouring items are
         // different edges.  Each lane turns one item into its descriptor: one division per grab, none per item.
+#pragma unroll 1
         for (int tries = 0; tries < 4 && count < share && !globalDone; ++tries) {
             const int take = min(want, share) - count;
             unsigned long long f = 0;
@@ -938,8 +939,9 @@ struct EdgeSource {
                 if (mid < hi) cnt = splitHalf(e, mid + 1, hi, extra, kids, cnt);
             }
         };
-        one(r0, lane, (hit.lo >> lane) & 1u, (touched.lo >> lane) & 1u);
-        one(r1, lane + 32, (hit.hi >> lane) & 1u, (touched.hi >> lane) & 1u);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h)   // (rolled up: one copy of the slot's code, see splitHalf)
+            one(h ? r1 : r0, lane + 32u * h, ((h ? hit.hi : hit.lo) >> lane) & 1u, ((h ? touched.hi : touched.lo) >> lane) & 1u);
         // exclusive prefix of cnt over the warp
         unsigned incl = cnt;
 #pragma unroll
@@ -959,6 +961,7 @@ struct EdgeSource {
             if (lane == 0) pos = atomicAdd(spillCount, (unsigned long long)total);
             pos = __shfl_sync(kFull, pos, 0);
             if (pos + total <= spillCap) {
+#pragma unroll 1
                 for (unsigned k = 0; k < cnt; ++k) spillOut[pos + incl - cnt + k] = kids[k];
                 return;
             }
@@ -969,6 +972,7 @@ struct EdgeSource {
             return;
         }
         const unsigned at = stackCount + incl - cnt;
+#pragma unroll 1
         for (unsigned k = 0; k < cnt; ++k) stack[at + k] = kids[k];
         stackCount += total;
         __syncwarp();
@@ -1210,11 +1214,22 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
         };
         // The queues hold at most 31 leftovers plus what one step can add (64 leaf pairs, 32 unsure
         // pairs per triangle batch): drain them down below a batch before stepping again.
-        while (nt >= triMin || (nt > 0 && nActive <= triEager)) {
-            triBatch();
-            while (nx >= 32) exactBatch();
+        if constexpr (Source::kIntervals) {
+            // (edges: one call site per batch kind -- they are a few hundred instructions apiece and that kernel's loop
+            // does not fit the instruction cache: 65,536 Cubicles edges 0.790 -> 0.761 ms; poses measured 1 % slower)
+            for (;;) {
+                const bool wantTri = nt >= triMin || (nt > 0 && nActive <= triEager);
+                if (nx >= 32 || (!wantTri && nx > 0 && nActive <= triEager)) exactBatch();
+                else if (wantTri) triBatch();
+                else break;
+            }
+        } else {
+            while (nt >= triMin || (nt > 0 && nActive <= triEager)) {
+                triBatch();
+                while (nx >= 32) exactBatch();
+            }
+            if (nx > 0 && nActive <= triEager) exactBatch();
         }
-        if (nx > 0 && nActive <= triEager) exactBatch();
         // ---- depth-first steps: each lane pops a pair and tests both children of the larger box.
         //      A few steps run back to back before the slot bookkeeping above is revisited (a lane that
         //      finishes early idles for at most kStepsPerRound - 1 steps; the leaf queue is re-checked
