@@ -119,7 +119,8 @@ static int nnGridRebuild(mplb_nn *nn, cudaStream_t st) {
     if (!nn->hGridBounds && cudaMallocHost((void **)&nn->hGridBounds, 6 * sizeof(unsigned)) != cudaSuccess)
         return fail(MPLB_ERR_NOMEM, "pinned scratch for the index bounds");
     if ((rc = nn->gridBounds.reserve(6 * sizeof(unsigned))) || (rc = nn->gridStats.reserve(16))) return rc;
-    MPLB_CUDA(launchNnGridBounds(nn->dKeys, n, (unsigned *)nn->gridBounds.ptr, st));
+    const int coord0 = nn->metric == 0 ? 4 : 0;
+    MPLB_CUDA(launchNnGridBounds(nn->dKeys, n, nn->dim, coord0, (unsigned *)nn->gridBounds.ptr, st));
     MPLB_CUDA(cudaMemcpyAsync(nn->hGridBounds, nn->gridBounds.ptr, 6 * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     MPLB_CUDA(cudaStreamSynchronize(st));
     double lo[3], ext[3], maxExt = 0;
@@ -160,6 +161,9 @@ static int nnGridRebuild(mplb_nn *nn, cudaStream_t st) {
     for (int a = 0; a < 3; ++a) g.origin[a] = lo[a] - 1e-6 * cell;
     g.cell = cell;
     g.invCell = 1.0 / cell;
+    g.metric = nn->metric;
+    g.dim = nn->dim;
+    g.coord0 = coord0;
     if ((rc = nn->gridStart.reserve((total + 1) * 4)) || (rc = nn->gridCounts.reserve(total * 4)) ||
         (rc = nn->gridPerm.reserve(n * 4)) || (rc = nn->gridCellOf.reserve(n * 4)) || (rc = nn->gridSorted.reserve(n * 32)))
         return rc;
@@ -177,7 +181,7 @@ static int nnGridRebuild(mplb_nn *nn, cudaStream_t st) {
 static int nnLaunchSearch(mplb_nn *nn, const double *dQ, size_t nq, int k, double *dDist, long long *dIdx, cudaStream_t st) {
     int rc;
     const float absMax = std::isfinite(nn->keysAbsMax) ? std::nextafterf((float)nn->keysAbsMax, INFINITY) : INFINITY;
-    const bool gridOk = nn->gridOn && nn->metric == 0 && std::isfinite(nn->keysAbsMax) && nn->count >= nnGridMin() &&
+    const bool gridOk = nn->gridOn && (nn->metric == 0 || nn->dim >= 3) && std::isfinite(nn->keysAbsMax) && nn->count >= nnGridMin() &&
                         nn->count < ((size_t)1 << 31);
     if (!gridOk) nn->gridBuilt = 0;
     if (gridOk) {

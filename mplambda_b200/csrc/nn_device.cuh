@@ -27,9 +27,11 @@ struct NnGridGeom {
     double origin[3];    // lower corner of the grid
     double cell, invCell;
     int dims[3];         // cells per axis (x fastest in memory)
+    int metric;          // 0: SE3 keys (7 doubles; the grid is over the translation, coordinates 4..6), 1: L1 keys
+    int dim, coord0;     // doubles per key; first of the three key coordinates the grid is laid over (L1: 0..2)
 };
 // {min x, y, z, max x, y, z} of the translations of n keys as order-preserving bit patterns (nnGridOrderedToFloat)
-cudaError_t launchNnGridBounds(const double *dKeys, size_t n, unsigned *dOut6, cudaStream_t stream);
+cudaError_t launchNnGridBounds(const double *dKeys, size_t n, int dim, int coord0, unsigned *dOut6, cudaStream_t stream);
 float nnGridOrderedToFloat(unsigned bits);
 // counting sort of keys [0, n) by cell: dStart [cells + 1], dPerm [n] (sorted position -> key index), dSorted [n][2]
 // float4 (FP32 copy in sorted order); dCellOf [n] and dCounts [cells] are scratch

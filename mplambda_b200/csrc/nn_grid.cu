@@ -16,6 +16,8 @@
 // over the same cube -- exact, only slower.  The structure is rebuilt (three kernels and a scan, O(n)) when the keys
 // inserted since the last build exceed a quarter of it; until then they are searched by the brute-force kernels and
 // the two sorted lists are merged (nn_capi.cu), which keeps insertion O(1) amortised -- the log-structured pattern.
+// L1Space<S, dim> keys (the Fetch planners' joint space, fetch_scenario.hpp:19,42-45) are indexed the same way over
+// their first three coordinates: sum_i |x_i - y_i| >= the distance within any subset of the coordinates.
 #include "nn_device.cuh"
 
 #include <cfloat>
@@ -37,13 +39,13 @@ __device__ __forceinline__ unsigned orderedBits(float f) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-__global__ void nnGridBoundsKernel(const double *__restrict__ keys, unsigned n, unsigned *__restrict__ out) {
+__global__ void nnGridBoundsKernel(const double *__restrict__ keys, unsigned n, int dim, int coord0, unsigned *__restrict__ out) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned lo[3] = {~0u, ~0u, ~0u}, hi[3] = {0u, 0u, 0u};
     if (i < n) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const double v = keys[7ull * i + 4 + a];
+            const double v = keys[(unsigned long long)dim * i + coord0 + a];
             lo[a] = orderedBits(__double2float_rd(v));
             hi[a] = orderedBits(__double2float_ru(v));
         }
@@ -71,9 +73,10 @@ __global__ void nnGridCountKernel(const double *__restrict__ keys, unsigned n, N
                                   unsigned *__restrict__ counts) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int x = cellCoord(keys[7ull * i + 4], g.origin[0], g.invCell, g.dims[0]);
-    const int y = cellCoord(keys[7ull * i + 5], g.origin[1], g.invCell, g.dims[1]);
-    const int z = cellCoord(keys[7ull * i + 6], g.origin[2], g.invCell, g.dims[2]);
+    const double *k = keys + (unsigned long long)g.dim * i + g.coord0;
+    const int x = cellCoord(k[0], g.origin[0], g.invCell, g.dims[0]);
+    const int y = cellCoord(k[1], g.origin[1], g.invCell, g.dims[1]);
+    const int z = cellCoord(k[2], g.origin[2], g.invCell, g.dims[2]);
     const unsigned c = ((unsigned)z * g.dims[1] + y) * g.dims[0] + x;
     cellOf[i] = c;
     atomicAdd(counts + c, 1u);
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(1024) nnGridScanKernel(const unsigned *__restr
     if (threadIdx.x == 1023) start[n] = totals[1023];
 }
 
-__global__ void nnGridScatterKernel(const double *__restrict__ keys, unsigned n, const unsigned *__restrict__ cellOf,
+__global__ void nnGridScatterKernel(const double *__restrict__ keys, unsigned n, int dim, const unsigned *__restrict__ cellOf,
                                     const unsigned *__restrict__ start, unsigned *__restrict__ fill,
                                     unsigned *__restrict__ perm, float4 *__restrict__ sorted) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -110,9 +113,12 @@ __global__ void nnGridScatterKernel(const double *__restrict__ keys, unsigned n,
     const unsigned c = cellOf[i];
     const unsigned pos = start[c] + atomicAdd(fill + c, 1u);
     perm[pos] = i;
-    const double *k = keys + 7ull * i;
-    sorted[2ull * pos] = make_float4((float)k[0], (float)k[1], (float)k[2], (float)k[3]);
-    sorted[2ull * pos + 1] = make_float4((float)k[4], (float)k[5], (float)k[6], 0.f);
+    const double *k = keys + (unsigned long long)dim * i;
+    float f[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) f[d] = d < dim ? (float)k[d] : 0.f;
+    sorted[2ull * pos] = make_float4(f[0], f[1], f[2], f[3]);
+    sorted[2ull * pos + 1] = make_float4(f[4], f[5], f[6], f[7]);
 }
 
 __device__ __forceinline__ float sqrtApproxG(float x) {
@@ -120,23 +126,35 @@ __device__ __forceinline__ float sqrtApproxG(float x) {
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-// the FP32 estimate of nn_kernels.cu (same polynomial acos, same margin)
-__device__ __forceinline__ float gridDist32(const float q[7], const float4 ka, const float4 kb, float so3w, float l2w) {
-    const float dx = kb.x - q[4], dy = kb.y - q[5], dz = kb.z - q[6];
-    const float t2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    const float x = fabsf(fmaf(ka.w, q[3], fmaf(ka.z, q[2], fmaf(ka.y, q[1], ka.x * q[0]))));
-    const float p = fmaf(fmaf(fmaf(-0.0187293f, x, 0.0742610f), x, -0.2121144f), x, 1.5707288f);
-    const float so3 = x < 1.f ? sqrtApproxG(fmaxf(1.f - x, 0.f)) * p : 0.f;
-    return fmaf(so3w, so3, l2w * sqrtApproxG(t2));
+// the FP32 estimate of nn_kernels.cu (same polynomial acos, same margin) / the L1 sum
+template <int kMetric>
+__device__ __forceinline__ float gridDist32(const float q[8], const float4 ka, const float4 kb, float so3w, float l2w) {
+    if (kMetric == 0) {
+        const float dx = kb.x - q[4], dy = kb.y - q[5], dz = kb.z - q[6];
+        const float t2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+        const float x = fabsf(fmaf(ka.w, q[3], fmaf(ka.z, q[2], fmaf(ka.y, q[1], ka.x * q[0]))));
+        const float p = fmaf(fmaf(fmaf(-0.0187293f, x, 0.0742610f), x, -0.2121144f), x, 1.5707288f);
+        const float so3 = x < 1.f ? sqrtApproxG(fmaxf(1.f - x, 0.f)) * p : 0.f;
+        return fmaf(so3w, so3, l2w * sqrtApproxG(t2));
+    }
+    // (coordinates past the key's dimension are zero in both the sorted copy and q)
+    return ((fabsf(ka.x - q[0]) + fabsf(ka.y - q[1])) + (fabsf(ka.z - q[2]) + fabsf(ka.w - q[3]))) +
+           ((fabsf(kb.x - q[4]) + fabsf(kb.y - q[5])) + (fabsf(kb.z - q[6]) + fabsf(kb.w - q[7])));
 }
-__device__ __forceinline__ double gridDist64(const double q[7], const double *key, double so3w, double l2w) {
-    const double d = fabs(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(key[0], q[0]), __dmul_rn(key[1], q[1])),
-                                              __dmul_rn(key[2], q[2])),
-                                    __dmul_rn(key[3], q[3])));
-    const double so3 = d < 1.0 ? acos(d) : 0.0;
-    const double dx = __dsub_rn(key[4], q[4]), dy = __dsub_rn(key[5], q[5]), dz = __dsub_rn(key[6], q[6]);
-    const double l2 = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
-    return __dadd_rn(__dmul_rn(so3w, so3), __dmul_rn(l2w, l2));
+template <int kMetric>
+__device__ __forceinline__ double gridDist64(const double q[8], const double *key, int dim, double so3w, double l2w) {
+    if (kMetric == 0) {
+        const double d = fabs(__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(key[0], q[0]), __dmul_rn(key[1], q[1])),
+                                                  __dmul_rn(key[2], q[2])),
+                                        __dmul_rn(key[3], q[3])));
+        const double so3 = d < 1.0 ? acos(d) : 0.0;
+        const double dx = __dsub_rn(key[4], q[4]), dy = __dsub_rn(key[5], q[5]), dz = __dsub_rn(key[6], q[6]);
+        const double l2 = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+        return __dadd_rn(__dmul_rn(so3w, so3), __dmul_rn(l2w, l2));
+    }
+    double s = 0;   // nn_kernels.cu nnDistance: the oracle's order
+    for (int i = 0; i < dim; ++i) s = __dadd_rn(s, fabs(__dsub_rn(key[i], q[i])));
+    return s;
 }
 
 struct Cube {
@@ -166,6 +184,7 @@ __device__ __forceinline__ void forKeys(const NnGridGeom &g, const unsigned *__r
 }
 
 // one warp per query
+template <int kMetric>
 __global__ void __launch_bounds__(kGridWarps * 32)
 nnGridSearchKernel(NnGridGeom g, const unsigned *__restrict__ start, const unsigned *__restrict__ perm,
                    const float4 *__restrict__ sorted, const double *__restrict__ keys, unsigned nBuilt, double so3w,
@@ -179,25 +198,32 @@ nnGridSearchKernel(NnGridGeom g, const unsigned *__restrict__ start, const unsig
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const unsigned long long qi = blockIdx.x * (unsigned long long)kGridWarps + w;
     if (qi >= nq) return;
-    double q[7];
-    float q32[7];
+    const int dim = g.dim, c0 = g.coord0;
+    double q[8];
+    float q32[8];
 #pragma unroll
-    for (int i = 0; i < 7; ++i) {
-        q[i] = __ldg(queries + qi * 7 + i);
+    for (int i = 0; i < 8; ++i) {
+        q[i] = i < dim ? __ldg(queries + qi * dim + i) : 0.0;
         q32[i] = (float)q[i];
     }
-    const float so3w32 = (float)so3w, l2w32 = (float)l2w;
+    const float so3w32 = (float)so3w, l2w32 = kMetric == 0 ? (float)l2w : 1.f;   // (L1: the grid coordinates weigh 1)
     // |d32 - d64| <= m (nn_kernels.cu: nnMargin); a query whose quaternion is not unit, or that is not finite, gets no
     // FP32 filtering at all (everything in reach is evaluated exactly)
     float absMax = keysAbsMax;
 #pragma unroll
-    for (int i = 4; i < 7; ++i) absMax = fmaxf(absMax, fabsf(q32[i]) * 1.0000002f);
+    for (int i = (kMetric == 0 ? 4 : 0); i < (kMetric == 0 ? 7 : 8); ++i) absMax = fmaxf(absMax, fabsf(q32[i]) * 1.0000002f);
     const float qn = q32[0] * q32[0] + q32[1] * q32[1] + q32[2] * q32[2] + q32[3] * q32[3];
-    const bool exactOnly = !(fabsf(qn - 1.f) < 1e-3f) || !(absMax < INFINITY);
-    const float m = so3w32 * (2e-3f + 7e-5f) + l2w32 * 4e-6f * absMax + 1e-30f;
+    const bool exactOnly = (kMetric == 0 && !(fabsf(qn - 1.f) < 1e-3f)) || !(absMax < INFINITY);
+    const float m = kMetric == 0 ? so3w32 * (2e-3f + 7e-5f) + l2w32 * 4e-6f * absMax + 1e-30f
+                                 : (float)dim * 1e-6f * absMax + 1e-30f;   // nn_kernels.cu: nnMargin
+    // the three coordinates the grid is laid over
+    double qg[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) qg[a] = kMetric == 0 ? q[4 + a] : q[a];
+    (void)c0;
     int c[3];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) c[a] = cellCoord(q[4 + a], g.origin[a], g.invCell, g.dims[a]);
+    for (int a = 0; a < 3; ++a) c[a] = cellCoord(qg[a], g.origin[a], g.invCell, g.dims[a]);
     // histogram levels: level j holds distances <= d0 * 2^(j / 6)
     // (the top level covers every key there is: the full rotation range plus the way to the farthest corner of the
     // grid, so that a query far outside the keys' box -- whose cube ends up being the whole grid -- still gets a finite
@@ -205,10 +231,17 @@ nnGridSearchKernel(NnGridGeom g, const unsigned *__restrict__ start, const unsig
     float far2 = 0.f;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        const float lo = fabsf((float)(q[4 + a] - g.origin[a])), hi = fabsf((float)(g.origin[a] + g.dims[a] * g.cell - q[4 + a]));
-        far2 = fmaf(fmaxf(lo, hi), fmaxf(lo, hi), far2);
+        const float lo = fabsf((float)(qg[a] - g.origin[a])), hi = fabsf((float)(g.origin[a] + g.dims[a] * g.cell - qg[a]));
+        far2 = kMetric == 0 ? fmaf(fmaxf(lo, hi), fmaxf(lo, hi), far2) : far2 + fmaxf(lo, hi);
     }
-    const float dTop = (so3w32 * 1.5708f + l2w32 * sqrtf(far2)) * 1.01f;
+    float dTop;
+    if (kMetric == 0) {
+        dTop = (so3w32 * 1.5708f + l2w32 * sqrtf(far2)) * 1.01f;
+    } else {   // the grid coordinates' share plus, for every other coordinate, the farthest a key can be
+        dTop = far2;
+        for (int i = 3; i < dim; ++i) dTop += fabsf(q32[i]) + (keysAbsMax < INFINITY ? keysAbsMax : 0.f);
+        dTop *= 1.01f;
+    }
     const float d0 = fmaxf(dTop * (1.f / 1448.f), 1e-20f);
     const float invD0 = 1.f / d0;
     for (int j = lane; j < kGridBins; j += 32) hist[w][j] = 0u;
@@ -233,17 +266,17 @@ nnGridSearchKernel(NnGridGeom g, const unsigned *__restrict__ start, const unsig
             }
             if (cube.lo[a] > 0) {
                 whole = false;
-                reach = fminf(reach, (float)(q[4 + a] - (g.origin[a] + cube.lo[a] * g.cell)));
+                reach = fminf(reach, (float)(qg[a] - (g.origin[a] + cube.lo[a] * g.cell)));
             }
             if (cube.hi[a] < g.dims[a] - 1) {
                 whole = false;
-                reach = fminf(reach, (float)((g.origin[a] + (cube.hi[a] + 1) * g.cell) - q[4 + a]));
+                reach = fminf(reach, (float)((g.origin[a] + (cube.hi[a] + 1) * g.cell) - qg[a]));
             }
         }
         forKeys(g, start, cube, inner, lane, [&](unsigned p, bool have) {
             if (!have) return;
             const float4 ka = __ldg(sorted + 2ull * p), kb = __ldg(sorted + 2ull * p + 1);
-            const float d = gridDist32(q32, ka, kb, so3w32, l2w32);
+            const float d = gridDist32<kMetric>(q32, ka, kb, so3w32, l2w32);
             // level of d: smallest j with d <= d0 * 2^(j/6)
             int j = d <= d0 ? 0 : (int)ceilf(6.f * __log2f(d * invD0) * 1.000001f);
             if (j < kGridBins && d == d) atomicAdd(&hist[w][j], 1u);
@@ -296,7 +329,7 @@ nnGridSearchKernel(NnGridGeom g, const unsigned *__restrict__ start, const unsig
         forKeys(g, start, cube, inner, lane, [&](unsigned p, bool have) {
             if (!have) return;
             const float4 ka = __ldg(sorted + 2ull * p), kb = __ldg(sorted + 2ull * p + 1);
-            const float d = gridDist32(q32, ka, kb, so3w32, l2w32);
+            const float d = gridDist32<kMetric>(q32, ka, kb, so3w32, l2w32);
             if (d <= Tlo) ++belowLane;
             else if (d <= T) atomicAdd(&hist[w][min(kGridBins - 1, (int)((d - Tlo) * scale))], 1u);
         });
@@ -333,7 +366,7 @@ nnGridSearchKernel(NnGridGeom g, const unsigned *__restrict__ start, const unsig
         bool cand = have;
         if (have && !exactOnly) {
             const float4 ka = __ldg(sorted + 2ull * p), kb = __ldg(sorted + 2ull * p + 1);
-            cand = gridDist32(q32, ka, kb, so3w32, l2w32) <= limit;
+            cand = gridDist32<kMetric>(q32, ka, kb, so3w32, l2w32) <= limit;
         }
         const unsigned mk = __ballot_sync(kFullMask, cand);
         if (!mk) return;
@@ -345,10 +378,10 @@ nnGridSearchKernel(NnGridGeom g, const unsigned *__restrict__ start, const unsig
             const unsigned at = base + __popc(mk & ((1u << lane) - 1u));
             if (at < (unsigned)kGridCand) {
                 const unsigned ki = __ldg(perm + p);
-                double key[7];
+                double key[8];
 #pragma unroll
-                for (int i = 0; i < 7; ++i) key[i] = __ldg(keys + 7ull * ki + i);
-                candD[w][at] = gridDist64(q, key, so3w, l2w);
+                for (int i = 0; i < 8; ++i) key[i] = i < dim ? __ldg(keys + (unsigned long long)dim * ki + i) : 0.0;
+                candD[w][at] = gridDist64<kMetric>(q, key, dim, so3w, l2w);
                 candI[w][at] = ki;
                 ++exact;
             }
@@ -389,13 +422,13 @@ nnGridSearchKernel(NnGridGeom g, const unsigned *__restrict__ start, const unsig
                 if (!have) return;
                 if (!exactOnly) {
                     const float4 ka = __ldg(sorted + 2ull * p), kb = __ldg(sorted + 2ull * p + 1);
-                    if (!(gridDist32(q32, ka, kb, so3w32, l2w32) <= limit)) return;
+                    if (!(gridDist32<kMetric>(q32, ka, kb, so3w32, l2w32) <= limit)) return;
                 }
                 const unsigned ki = __ldg(perm + p);
-                double key[7];
+                double key[8];
 #pragma unroll
-                for (int i = 0; i < 7; ++i) key[i] = __ldg(keys + 7ull * ki + i);
-                const double d = gridDist64(q, key, so3w, l2w);
+                for (int i = 0; i < 8; ++i) key[i] = i < dim ? __ldg(keys + (unsigned long long)dim * ki + i) : 0.0;
+                const double d = gridDist64<kMetric>(q, key, dim, so3w, l2w);
                 ++exact;
                 const bool after = d > prevD || (d == prevD && (long long)ki > prevI);
                 if (after && (d < bd || (d == bd && (bi < 0 || (long long)ki < bi)))) {
@@ -465,12 +498,12 @@ __global__ void nnMerge2Kernel(const double *__restrict__ dA, const long long *_
 
 }  // namespace
 
-cudaError_t launchNnGridBounds(const double *dKeys, size_t n, unsigned *dOut6, cudaStream_t stream) {
+cudaError_t launchNnGridBounds(const double *dKeys, size_t n, int dim, int coord0, unsigned *dOut6, cudaStream_t stream) {
     // {min x, y, z; max x, y, z} as order-preserving bit patterns
     static const unsigned init[6] = {~0u, ~0u, ~0u, 0u, 0u, 0u};
     cudaError_t e = cudaMemcpyAsync(dOut6, init, sizeof(init), cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return e;
-    nnGridBoundsKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dKeys, (unsigned)n, dOut6);
+    nnGridBoundsKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dKeys, (unsigned)n, dim, coord0, dOut6);
     return cudaGetLastError();
 }
 
@@ -491,7 +524,7 @@ cudaError_t launchNnGridBuild(const double *dKeys, size_t n, const NnGridGeom &g
     nnGridScanKernel<<<1, 1024, 0, stream>>>(dCounts, (unsigned)cells, dStart);
     e = cudaMemsetAsync(dCounts, 0, cells * sizeof(unsigned), stream);
     if (e != cudaSuccess) return e;
-    nnGridScatterKernel<<<blocks, 256, 0, stream>>>(dKeys, (unsigned)n, dCellOf, dStart, dCounts, dPerm, dSorted);
+    nnGridScatterKernel<<<blocks, 256, 0, stream>>>(dKeys, (unsigned)n, g.dim, dCellOf, dStart, dCounts, dPerm, dSorted);
     return cudaGetLastError();
 }
 
@@ -500,9 +533,15 @@ cudaError_t launchNnGridSearch(const NnGridGeom &g, const unsigned *dStart, cons
                                const double *dQueries, size_t nq, int k, double *dDist, long long *dIdx,
                                unsigned long long *dStats, cudaStream_t stream) {
     if (nq == 0) return cudaSuccess;
-    nnGridSearchKernel<<<(unsigned)((nq + kGridWarps - 1) / kGridWarps), kGridWarps * 32, 0, stream>>>(
-        g, dStart, dPerm, dSorted, dKeys, (unsigned)nBuilt, so3w, l2w, keysAbsMax, dQueries, nq, k, dDist, dIdx,
-        (unsigned long long)k, dStats);
+    const unsigned blocks = (unsigned)((nq + kGridWarps - 1) / kGridWarps);
+    if (g.metric == 0)
+        nnGridSearchKernel<0><<<blocks, kGridWarps * 32, 0, stream>>>(g, dStart, dPerm, dSorted, dKeys, (unsigned)nBuilt, so3w, l2w,
+                                                                    keysAbsMax, dQueries, nq, k, dDist, dIdx,
+                                                                    (unsigned long long)k, dStats);
+    else
+        nnGridSearchKernel<1><<<blocks, kGridWarps * 32, 0, stream>>>(g, dStart, dPerm, dSorted, dKeys, (unsigned)nBuilt, so3w, l2w,
+                                                                    keysAbsMax, dQueries, nq, k, dDist, dIdx,
+                                                                    (unsigned long long)k, dStats);
     return cudaGetLastError();
 }
 

@@ -1016,6 +1016,25 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
     int nt = 0, nx = 0, sp = 0, bot = 0, mySlot = -1;
     const int triMin = sc.triBatchMin, triEager = sc.triEagerLanes;
     unsigned idleSpins = 0, stepsLane = 0;
+#ifndef MPLB_FIXED_REUSE
+#define MPLB_FIXED_REUSE 0
+#endif
+    // The fixed box of a lane's step is, more often than not, the fixed box of its previous step: the nearer surviving
+    // child is popped right away, and when it is that child's side that gets split again the other box stays (counted
+    // with -DMPLB_COUNT_FIXED: 52 % of the steps on Alpha 1.5, 78 % on Twistycool, 84 % on Cubicles).  With
+    // -DMPLB_FIXED_REUSE=1 its frame (ObbFrame: 15 floats), link and size are kept and such a step skips two of its six
+    // node loads and the slot's transform rows.  Built, verified against the oracle and measured: 2^20 poses Alpha
+    // 0.738 -> 0.744 ms, Cubicles 0.950 -> 0.931, Apartment 3.20 -> 3.15; edge batches 1 % slower.  A fifth fewer L1
+    // wavefronts buy nothing: the warps wait on each step's dependent chain (load -> frame -> 15 axes -> votes), not on
+    // the L1 pipe -- hence off.
+    ObbFrame keptF;
+    unsigned keptKey = ~0u;   // fixed node | role << 31 the kept frame belongs to (~0: none; reset when the slot changes)
+    int keptLink = 0;
+    float keptSz = 0.f;
+#ifdef MPLB_COUNT_FIXED
+    unsigned dbgPrev = ~0u, dbgSame = 0;
+    int dbgPrevSlot = -1;
+#endif
     // compact the set bits of a 64-slot mask into sm.list (lane s looks after slots s and s + 32)
     auto buildList = [&](const Masks64 &m) {
         if ((m.lo >> lane) & 1u) sm.list[__popc(m.lo & ltMask)] = lane;
@@ -1079,6 +1098,7 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
             if (take) {
                 slot = sm.list[rank];
                 mySlot = (int)slot;
+                keptKey = ~0u;
                 sm.workers[slot] = 1;
                 if (sc.haveGeometry && !sc.bothRootsLeaf) {
                     sm.stack[0][lane] = sc.rootEntry;  // root pair, expanded without testing itself
@@ -1121,6 +1141,7 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
                     bot = 0;
                     sp = 1;
                     mySlot = dslot;
+                    keptKey = ~0u;
                     atomicAdd(&sm.workers[dslot], 1);
                 }
                 if (give) ++bot;
@@ -1256,23 +1277,37 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
                 const unsigned r = en & maskA, e = (en & 0x7fffffffu) >> bitsA;
                 child = descendA ? r : e;
                 fixedIdx = descendA ? e : r;
+#ifdef MPLB_COUNT_FIXED   // diagnostic: how often a lane's next step has the same fixed box as its previous one
+                if (dbgPrev == (fixedIdx | (descendA ? 0x80000000u : 0u)) && dbgPrevSlot == (int)slot) ++dbgSame;
+                dbgPrev = fixedIdx | (descendA ? 0x80000000u : 0u);
+                dbgPrevSlot = (int)slot;
+#endif
                 const float4 *pc = (descendA ? sc.robotNodes : sc.envNodes) + 4 * (size_t)child;
                 const float4 *pf = (descendA ? sc.envNodes : sc.robotNodes) + 4 * (size_t)fixedIdx;
-                float4 f0, f1, f2, fe, c00, c01, c02, c0e, c10, c11, c12, c1e;
-                ldg8(pf, f0, f1); ldg8(pf + 2, f2, fe);
+                float4 c00, c01, c02, c0e, c10, c11, c12, c1e;
+                const unsigned key = fixedIdx | (descendA ? 0x80000000u : 0u);
+                const bool kept = MPLB_FIXED_REUSE && key == keptKey;
                 ldg8(pc, c00, c01); ldg8(pc + 2, c02, c0e);
                 ldg8(pc + 4, c10, c11); ldg8(pc + 6, c12, c1e);
-                const float4 x0 = sm.xf[slot][0], x1 = sm.xf[slot][1], x2 = sm.xf[slot][2], x3 = sm.xf[slot][3];
-                // The fixed box is always the first argument.  (R|T) maps env -> robot coordinates; when
-                // the fixed box is the environment's the test runs in its frame with the inverse map
-                // (R^T | -R^T T), so no per-role shuffling of the 3 x 16 node floats is needed.
-                const float4 y0 = descendA ? make_float4(x0.x, x1.x, x2.x, -fmaf(x0.x, x0.w, fmaf(x1.x, x1.w, x2.x * x2.w))) : x0;
-                const float4 y1 = descendA ? make_float4(x0.y, x1.y, x2.y, -fmaf(x0.y, x0.w, fmaf(x1.y, x1.w, x2.y * x2.w))) : x1;
-                const float4 y2 = descendA ? make_float4(x0.z, x1.z, x2.z, -fmaf(x0.z, x0.w, fmaf(x1.z, x1.w, x2.z * x2.w))) : x2;
+                const float4 x3 = sm.xf[slot][3];
+                if (!kept) {
+                    float4 f0, f1, f2, fe;
+                    ldg8(pf, f0, f1); ldg8(pf + 2, f2, fe);
+                    const float4 x0 = sm.xf[slot][0], x1 = sm.xf[slot][1], x2 = sm.xf[slot][2];
+                    // The fixed box is always the first argument.  (R|T) maps env -> robot coordinates; when
+                    // the fixed box is the environment's the test runs in its frame with the inverse map
+                    // (R^T | -R^T T), so no per-role shuffling of the 3 x 16 node floats is needed.
+                    const float4 y0 = descendA ? make_float4(x0.x, x1.x, x2.x, -fmaf(x0.x, x0.w, fmaf(x1.x, x1.w, x2.x * x2.w))) : x0;
+                    const float4 y1 = descendA ? make_float4(x0.y, x1.y, x2.y, -fmaf(x0.y, x0.w, fmaf(x1.y, x1.w, x2.y * x2.w))) : x1;
+                    const float4 y2 = descendA ? make_float4(x0.z, x1.z, x2.z, -fmaf(x0.z, x0.w, fmaf(x1.z, x1.w, x2.z * x2.w))) : x2;
+                    // what depends on the fixed box and the pose only is formed once for both children (device_math.cuh)
+                    obbFrame(f0, f1, f2, fe, y0, y1, y2, keptF);
+                    keptLink = __float_as_int(fe.w);
+                    keptSz = fmaf(fe.x, fe.x, fmaf(fe.y, fe.y, fe.z * fe.z));
+                    keptKey = key;
+                }
+                const ObbFrame &F = keptF;
                 float g0 = 0.f, g1 = 0.f;
-                // what depends on the fixed box and the pose only is formed once for both children (device_math.cuh)
-                ObbFrame F;
-                obbFrame(f0, f1, f2, fe, y0, y1, y2, F);
 #ifndef MPLB_OBB_LOOP
 #define MPLB_OBB_LOOP 0
 #endif
@@ -1307,13 +1342,13 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
                 }
                 link0 = __float_as_int(c0e.w);
                 link1 = __float_as_int(c1e.w);
-                fixedLink = __float_as_int(fe.w);
+                fixedLink = keptLink;
                 const bool fixedLeaf = fixedLink < 0;
                 leaf0 = fixedLeaf && link0 < 0;
                 leaf1 = fixedLeaf && link1 < 0;
                 sz0 = fmaf(c0e.x, c0e.x, fmaf(c0e.y, c0e.y, c0e.z * c0e.z));
                 sz1 = fmaf(c1e.x, c1e.x, fmaf(c1e.y, c1e.y, c1e.z * c1e.z));
-                szF = fmaf(fe.x, fe.x, fmaf(fe.y, fe.y, fe.z * fe.z));
+                szF = keptSz;
             }
             stepsLane += act ? 1u : 0u;   // box tests are counted per lane and summed when the warp is through
             // leaf-leaf survivors -> shared triangle queue
@@ -1392,6 +1427,9 @@ __device__ void runWarp(WarpSmem<E> &sm, const SceneDev &sc, Source &src, WarpCo
         }
     }
     cnt.bv += 2ull * __reduce_add_sync(kFull, stepsLane);
+#ifdef MPLB_COUNT_FIXED
+    cnt.exact += __reduce_add_sync(kFull, dbgSame);   // (reported in place of the exact-test count)
+#endif
 }
 
 template <typename E>

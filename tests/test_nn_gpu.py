@@ -237,3 +237,28 @@ def test_index_device_queries():
     ib, db = b.knearest(qs, k)
     assert (di.cpu().numpy() == ib).all()
     assert np.allclose(dd.cpu().numpy(), db, rtol=0, atol=1e-9)   # device acos vs host libm: last bits
+
+
+@pytest.mark.parametrize("k", [1, 9, 40])
+def test_l1_index_equals_brute_force(k, oracle):
+    """L1Space<S, 8> keys (the Fetch planners' scaled joint space): the grid lies over the first three coordinates."""
+    rng = np.random.default_rng(5)
+    scale = np.array([10, 4, 2, 1, 1, 1, 1, 1.0])                 # FetchScenario::scale (fetch_scenario.hpp:42-45)
+    lo = np.array([0.0, -1.6, -1.2, -3.1, -2.2, -3.1, -2.1, -3.1]) * scale
+    hi = np.array([0.38, 1.6, 1.5, 3.1, 2.2, 3.1, 2.1, 3.1]) * scale
+    keys = rng.uniform(lo, hi, size=(80000, 8))
+    keys[3000:3300] = keys[2999]                                  # duplicates: ties in insertion order
+    qs = np.concatenate([rng.uniform(lo, hi, size=(600, 8)), rng.uniform(lo - 5, hi + 5, size=(100, 8)), keys[2999:3001]])
+    a, b = M.Nigh(M.nn.L1, dim=8), M.Nigh(M.nn.L1, dim=8)
+    b.set_index(False)
+    a.insert(keys[:50000]); b.insert(keys[:50000])
+    assert (a.knearest(qs, k)[0] == b.knearest(qs, k)[0]).all()    # builds the index
+    a.insert(keys[50000:]); b.insert(keys[50000:])                # 30,000 more: rebuilt at the next search
+    ia, da = a.knearest(qs, k)
+    ib, db = b.knearest(qs, k)
+    assert a.index_info()["indexed"] == len(keys) and b.index_info()["indexed"] == 0
+    assert (ia == ib).all() and (da == db).all()
+    wi, wd = oracle.nn_knearest(keys, qs[:30], k, metric="l1")
+    assert (ia[:30] == wi).all() and (da[:30] == wd).all()
+    if k >= 9:
+        assert (ia[-2, :9] == np.arange(2999, 3008)).all()
