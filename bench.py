@@ -291,9 +291,14 @@ def extras(local_rank, cpu_seconds):
         A = P[s.check_states(P)][:1 << 16]
         B = se3_poses(len(A), sc["min"], sc["max"], SEED + 1)
         s.check_edges(A[:512], B[:512])
+        # end to end from page-locked host buffers (like the pose batches' e2e): the end states start crossing the link
+        # while the host plans the step counts; and from ordinary (pageable) arrays, through the bounce buffers
+        Ap, Bp = torch.from_numpy(A).pin_memory().numpy(), torch.from_numpy(B).pin_memory().numpy()
         s.check_edges(A, B)
+        dt_pageable, _ = best(lambda: s.check_edges(A, B))
+        s.check_edges(Ap, Bp)
         s.stats(reset=True)
-        dt, (v, checked) = best(lambda: s.check_edges(A, B, return_states_checked=True))
+        dt, (v, checked) = best(lambda: s.check_edges(Ap, Bp, return_states_checked=True))
         cnt = s.stats()
         steps = s.edge_steps(A, B)
         # device resident: the three passes of checkEdgesKernel alone
@@ -317,7 +322,8 @@ def extras(local_rank, cpu_seconds):
         out["edges_" + name] = {
             "metric": "edge validity checks/sec (isValid(from,to), resolution 0.1)", "value": len(A) / dt, "unit": "edges/s",
             "edges": int(len(A)), "interpolated_states": int(steps.sum()), "device_state_evaluations": int(checked),
-            "valid_fraction": float(v.mean()), "ms": dt * 1e3, "device_resident_ms": kms,
+            "valid_fraction": float(v.mean()), "ms": dt * 1e3, "api": "mplb_check_edges (pinned host buffers)",
+            "pageable_inputs_ms": dt_pageable * 1e3, "device_resident_ms": kms,
             "device_resident_value": len(A) / (kms * 1e-3),
             "cpu_baseline": {"value": m / dc, "unit": "edges/s", "cores": thr, "kind": "port", "sample": "first %d edges" % m},
             "verdict_mismatches_vs_cpu": int((w != v[:m]).sum()),

@@ -743,6 +743,30 @@ static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, siz
     static const bool timeline = std::getenv("MPLB_TIMELINE") != nullptr;
     const auto h0 = std::chrono::steady_clock::now();
     auto sinceMs = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count(); };
+    // Large batches from page-locked memory: the end states start crossing the link before the step counts are planned
+    // on the host (the copy engine needs no host thread), so the two overlap (65,536 edges: 0.11 + 0.16 ms -> 0.16 ms).
+    bool copiedEarly = false;
+    if (n > kSmallEdges && isPinned(from) && isPinned(to)) {
+        const size_t bytes = n * 7 * sizeof(double);
+        int rc0;
+        if ((rc0 = c->in0.reserve(bytes)) || (rc0 = c->in1.reserve(bytes))) return rc0;
+        if ((rc0 = hostToDevice(c, c->in0.ptr, from, bytes, c->copyStream)) || (rc0 = hostToDevice(c, c->in1.ptr, to, bytes, c->copyStream)))
+            return rc0;
+        if (c->events.empty()) {
+            cudaEvent_t e;
+            MPLB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->events.push_back(e);
+        }
+        MPLB_CUDA(cudaEventRecord(c->events[0], c->copyStream));
+        copiedEarly = true;
+    }
+    struct CopyQuiet {   // the copy stream is idle before the context goes back to the pool, whatever path the call leaves by
+        CallCtx *c;
+        bool on;
+        ~CopyQuiet() {
+            if (on) cudaStreamSynchronize(c->copyStream);
+        }
+    } copyQuiet{c, copiedEarly};
     {
         // se3...:139 on the host (same libm as the CPU path); large batches use the host's cores
         long long bad = -1;
@@ -848,7 +872,11 @@ static int se3CheckEdges(Se3Scene *sc, const double *from, const double *to, siz
         for (auto &e : tl) cudaEventCreate(&e);
     if (timeline) cudaEventRecord(tl[0], c->stream);
     MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(DevCounters), c->stream));
-    if ((rc = hostToDevice(c, c->in0.ptr, from, sb, c->stream)) || (rc = hostToDevice(c, c->in1.ptr, to, sb, c->stream))) return rc;
+    if (copiedEarly) {
+        MPLB_CUDA(cudaStreamWaitEvent(c->stream, c->events[0], 0));
+    } else if ((rc = hostToDevice(c, c->in0.ptr, from, sb, c->stream)) || (rc = hostToDevice(c, c->in1.ptr, to, sb, c->stream))) {
+        return rc;
+    }
     MPLB_CUDA(cudaMemcpyAsync(c->steps.ptr, c->hSteps.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
     if (timeline) cudaEventRecord(tl[1], c->stream);
     MPLB_CUDA(launchCheckEdges(sc->dev, (const double *)c->in0.ptr, (const double *)c->in1.ptr,
