@@ -48,7 +48,21 @@ void originFrame(double tx, double ty, double tz, double roll, double pitch, dou
     out[8] = txz - twy;       out[9] = tyz + twx;       out[10] = 1 - (txx + tyy); out[11] = tz;
 }
 
-constexpr size_t kBatch = 1u << 16;  // states per launch group (frames scratch: 144 doubles per state)
+// edge items per round (frames scratch: 144 doubles per item); MPLB_FETCH_EDGE_BATCH overrides (diagnostic)
+static const size_t kBatch = [] {
+    const char *e = std::getenv("MPLB_FETCH_EDGE_BATCH");
+    const long v = e ? std::atol(e) : 0;
+    return v >= 1024 ? (size_t)v : (size_t)1 << 16;
+}();
+// states per launch group of a state batch (151 MB of frames); MPLB_FETCH_BATCH overrides (diagnostic).  Measured for 2^18
+// configurations end to end: 32 K 2.52 ms, 64 K 1.81 ms, 128 K 1.56 ms, 256 K 1.58 ms -- six kernels per group, each with
+// a tail; beyond 128 K the first group's input copy is no longer hidden.  (Edge rounds stay at 64 K items: 128 K measured
+// 9.1 -> 16.8 ms for 16,384 edges.)
+static const size_t kStateBatch = [] {
+    const char *e = std::getenv("MPLB_FETCH_BATCH");
+    const long v = e ? std::atol(e) : 0;
+    return v >= 1024 ? (size_t)v : (size_t)1 << 17;
+}();
 
 }  // namespace
 
@@ -120,10 +134,10 @@ struct FetchScene : SceneBase {
         CallCtx *c = acquire();
         if (!c) return fail(MPLB_ERR_CUDA, "could not create a call context (stream / pinned memory)");
         CtxGuard g{this, c};
-        const size_t nb = std::min(n, kBatch);
+        const size_t nb = std::min(n, kStateBatch);
         int rc;
         FetchScratch w{};
-        // chunks of kBatch states: the input of chunk i + 1 crosses the link (copy stream, second buffer) while chunk i
+        // chunks of kStateBatch states: the input of chunk i + 1 crosses the link (copy stream, second buffer) while chunk i
         // is being checked; the verdicts of all chunks go back in one copy at the end
         if ((rc = c->in0.reserve(nb * 8 * sizeof(double))) || (rc = c->in1.reserve(nb * 8 * sizeof(double))) ||
             (rc = c->dead.reserve(n)) || (rc = reserveScratch(c, nb, w)))
@@ -135,8 +149,8 @@ struct FetchScene : SceneBase {
         }
         MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(FetchCounters), c->stream));
         size_t chunk = 0;
-        for (size_t lo = 0; lo < n; lo += kBatch, ++chunk) {
-            const size_t cnt = std::min(kBatch, n - lo);
+        for (size_t lo = 0; lo < n; lo += kStateBatch, ++chunk) {
+            const size_t cnt = std::min(kStateBatch, n - lo);
             const int b = (int)(chunk & 1);
             double *in = (double *)(b ? c->in1.ptr : c->in0.ptr);
             if (chunk >= 2) MPLB_CUDA(cudaStreamWaitEvent(c->copyStream, c->events[2 + b], 0));   // the buffer's previous chunk is done
