@@ -94,14 +94,23 @@ struct FetchScene : SceneBase {
         return MPLB_OK;
     }
 
-    int reserveScratch(CallCtx *c, size_t n, FetchScratch &w) {
+    // Work lists between the culling and the exact kernels: sized for the average (8 pairs, 16 leaf pairs per state; a
+    // state lists ~1.3).  A full pair list degrades gracefully (the pair is decided on the spot); a full leaf list drops
+    // leaf pairs and flags the group (FetchCounters::pad) -- the call is then repeated with `safe` lists that hold the
+    // worst case, every geometry against every triangle, in groups of safeGroup() states.
+    size_t envTris() const { return (envNodeCount + 1) / 2; }
+    size_t safeGroup() const {
+        const size_t perState = 12 * std::max<size_t>(envTris(), 1) * 8;
+        return std::max<size_t>(16, std::min<size_t>(8192, ((size_t)64 << 20) / perState));
+    }
+    int reserveScratch(CallCtx *c, size_t n, FetchScratch &w, bool safe = false) {
         int rc;
-        const size_t pc = fetchPairCap(n), lc = fetchLeafCap(n);
+        const size_t pc = safe ? 24 * n : fetchPairCap(n), lc = safe ? 12 * n * std::max<size_t>(envTris(), 1) : fetchLeafCap(n);
+        // aux4: the pair list, and behind it the pairs that need MPR; aux5: the leaf list
         if ((rc = c->aux0.reserve(n * 144 * sizeof(double))) || (rc = c->aux1.reserve(n)) ||
-            (rc = c->aux2.reserve(n * sizeof(unsigned))) || (rc = c->aux4.reserve(2 * pc * 8)) ||   // the pair list, and behind it the pairs that need MPR
-            
-            (rc = c->aux5.reserve(lc * 8)) || (rc = c->aux6.reserve(n * sizeof(unsigned))) || (rc = c->work.reserve(64)) ||
-            (rc = c->out.reserve(n)))
+            (rc = c->aux2.reserve(n * sizeof(unsigned))) || (rc = c->aux4.reserve(2 * pc * 8)) ||
+            (rc = c->aux5.reserve(lc * 8)) || (rc = c->aux6.reserve(n * sizeof(unsigned))) ||
+            (rc = c->work.reserve(64)) || (rc = c->out.reserve(n)))
             return rc;
         w.frames = (double *)c->aux0.ptr;
         w.selfHit = (unsigned char *)c->aux1.ptr;
@@ -109,13 +118,19 @@ struct FetchScene : SceneBase {
         w.survivors = (unsigned *)c->aux6.ptr;
         w.pairItems = (unsigned long long *)c->aux4.ptr;
         w.leafItems = (unsigned long long *)c->aux5.ptr;
-        w.pairCap = pc;
-        w.leafCap = lc;
+        // MPLB_FETCH_LIST_CAP (diagnostic, tests): tiny work lists, so that the overflow paths run
+        static const size_t listCap = [] {
+            const char *e = std::getenv("MPLB_FETCH_LIST_CAP");
+            return e ? (size_t)std::max(1L, std::atol(e)) : ~(size_t)0;
+        }();
+        w.pairCap = safe ? pc : std::min(pc, listCap);
+        w.leafCap = safe ? lc : std::min(lc, listCap);
         w.counts = (unsigned *)c->work.ptr;
         w.touched = (unsigned char *)c->out.ptr;   // (checkStates reuses the buffer for its verdicts afterwards)
         return MPLB_OK;
     }
 
+    static constexpr int kListOverflow = 1;   // finish(): a leaf list overflowed, the call has to be repeated with safe lists
     int finish(CallCtx *c) {
         FetchCounters h{};
         cudaError_t e = cudaMemcpyAsync(&h, c->ctr.ptr, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
@@ -126,21 +141,33 @@ struct FetchScene : SceneBase {
         hPairTests += h.pairTests;
         hLeafTests += h.leafTests;
         hTri += h.leafTests;
-        return MPLB_OK;
+        return h.pad ? kListOverflow : MPLB_OK;
     }
 
     int checkStates(const double *states, size_t n, uint8_t *valid) override {
+        int rc = checkStatesImpl(states, n, valid, false);
+        if (rc == kListOverflow) {
+            hListOverflows += 1;
+            rc = checkStatesImpl(states, n, valid, true);
+            if (rc == kListOverflow) return fail(MPLB_ERR_CUDA, "Fetch leaf list overflowed although it holds the worst case");
+        }
+        return rc;
+    }
+    std::atomic<uint64_t> hListOverflows{0};
+
+    int checkStatesImpl(const double *states, size_t n, uint8_t *valid, bool safe) {
         MPLB_CUDA(cudaSetDevice(device));
         CallCtx *c = acquire();
         if (!c) return fail(MPLB_ERR_CUDA, "could not create a call context (stream / pinned memory)");
         CtxGuard g{this, c};
+        const size_t kStateBatch = safe ? safeGroup() : ::mplb::kStateBatch;
         const size_t nb = std::min(n, kStateBatch);
         int rc;
         FetchScratch w{};
         // chunks of kStateBatch states: the input of chunk i + 1 crosses the link (copy stream, second buffer) while chunk i
         // is being checked; the verdicts of all chunks go back in one copy at the end
         if ((rc = c->in0.reserve(nb * 8 * sizeof(double))) || (rc = c->in1.reserve(nb * 8 * sizeof(double))) ||
-            (rc = c->dead.reserve(n)) || (rc = reserveScratch(c, nb, w)))
+            (rc = c->dead.reserve(n)) || (rc = reserveScratch(c, nb, w, safe)))
             return rc;
         while (c->events.size() < 4) {
             cudaEvent_t ev;
@@ -176,6 +203,16 @@ struct FetchScene : SceneBase {
     // exactly and the two halves go into the next round.  Every sample is the middle of exactly one interval, so the
     // verdict is the reference's discrete one.  Rounds are host driven (the work lists live on the host).
     int checkEdges(const double *from, const double *to, size_t n, uint8_t *valid, uint64_t *statesChecked) override {
+        int rc = checkEdgesImpl(from, to, n, valid, statesChecked, false);
+        if (rc == kListOverflow) {
+            hListOverflows += 1;
+            rc = checkEdgesImpl(from, to, n, valid, statesChecked, true);
+            if (rc == kListOverflow) return fail(MPLB_ERR_CUDA, "Fetch leaf list overflowed although it holds the worst case");
+        }
+        return rc;
+    }
+    int checkEdgesImpl(const double *from, const double *to, size_t n, uint8_t *valid, uint64_t *statesChecked, bool safe) {
+        const size_t kBatch = safe ? safeGroup() : ::mplb::kBatch;   // items per round
         MPLB_CUDA(cudaSetDevice(device));
         CallCtx *c = acquire();
         if (!c) return fail(MPLB_ERR_CUDA, "could not create a call context (stream / pinned memory)");
@@ -187,7 +224,7 @@ struct FetchScene : SceneBase {
         FetchScratch w{};
         if ((rc = c->in0.reserve(sb)) || (rc = c->in1.reserve(sb)) || (rc = c->steps.reserve(n * 4)) ||
             (rc = c->dead.reserve(n * 4)) || (rc = c->aux3.reserve(kBatch * 8)) || (rc = c->stage.reserve(kBatch * sizeof(float2))) ||
-            (rc = reserveScratch(c, kBatch, w)))
+            (rc = reserveScratch(c, kBatch, w, safe)))
             return rc;
         MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(FetchCounters), c->stream));
         MPLB_CUDA(cudaMemsetAsync(c->dead.ptr, 0, n * 4, c->stream));

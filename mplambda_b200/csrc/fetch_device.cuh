@@ -27,7 +27,7 @@ struct FetchSceneDev {
 
 struct FetchCounters {
     unsigned long long pairTests, bvTests, leafTests;
-    unsigned error, pad;
+    unsigned error, pad;   // pad: 1 = a work list overflowed and leaf pairs were dropped: the call must be repeated (fetch_capi.cu)
 };
 
 // per-call scratch (sized for the largest launch group of n states)
@@ -38,7 +38,7 @@ struct FetchScratch {
     unsigned *survivors;         // [n] indices of the states that passed the self-collision tests
     unsigned long long *pairItems, *leafItems;   // pairItems: 2 x pairCap (the pairs that need the exact test follow the list)
     size_t pairCap, leafCap;
-    unsigned *counts;            // [8]: pair list, leaf list, survivor list lengths, env item counter, exact-pair list
+    unsigned *counts;            // [12] ([7] redo list length, [8] its item cursor): pair list, leaf list, survivor list lengths, env item counter, exact-pair list
                                  //      length, the two fetchMprKernel item cursors
     unsigned char *touched;      // [n] interval items: something came within reach, the interval is not certified
 };

@@ -953,10 +953,6 @@ fetchMprKernel(FetchSceneDev sc, const double *__restrict__ frames, WorkList lis
     if (tested) atomicAdd(kLeaf ? &ctr->leafTests : &ctr->pairTests, (unsigned long long)tested);
 }
 
-__device__ __noinline__ int exactLeafSlow(const FetchSceneDev &sc, const double *frames, unsigned long long state, int g,
-                                          unsigned tri) {
-    return exactLeaf(sc, frames, state, g, tri);
-}
 
 // Kernel 3a: list the states that survived the self-collision tests (about half of a random batch)
 __global__ void fetchSurvivorsKernel(const unsigned char *__restrict__ selfHit, unsigned long long n, unsigned *list,
@@ -980,13 +976,18 @@ __global__ void fetchSurvivorsKernel(const unsigned char *__restrict__ selfHit, 
 // lanes on different nodes).  The traversals are a dozen box tests long and were bound by the latency of the node
 // loads (ncu: long-scoreboard 6.8 warps per issue at 10 warps / SM), which shared memory cuts by an order of
 // magnitude; AUTOLAB's 1 256 nodes take 100 KB.  Larger environments use the global-memory variant.
-constexpr int kEnvThreads = 384, kEnvStack = 40;
+// The kernel only culls: a leaf that cannot be culled goes to the exact kernel's list.  Should the list ever be full (it
+// holds 16 leaf pairs per state on average; a state lists ~1.3) the launch group is flagged (FetchCounters::pad) and the
+// host repeats the whole call in groups small enough for lists that hold the worst case (fetch_capi.cu).  Keeping the
+// exact test out of this kernel -- round 1 decided overflowing leaves on the spot -- takes it from 168 to 76 registers;
+// measured per 65,536 states at 384 / 512 / 768 threads per SM: 154 / 142 / 153 us.
+constexpr int kEnvThreadsMax = 512, kEnvStack = 40;
 #ifndef MPLB_ENV_CHUNK
 #define MPLB_ENV_CHUNK 32
 #endif
 constexpr unsigned kEnvChunk = MPLB_ENV_CHUNK;
 template <bool kSmemNodes>
-__global__ void __launch_bounds__(kSmemNodes ? kEnvThreads : 128)
+__global__ void __launch_bounds__(kSmemNodes ? kEnvThreadsMax : 128)
 fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsigned *__restrict__ survivors,
                const unsigned *__restrict__ nSurvivors, const float2 *__restrict__ slack, unsigned char *__restrict__ touched,
                unsigned *__restrict__ envHit, WorkList leaves, unsigned *itemCounter, FetchCounters *ctr) {
@@ -1116,14 +1117,8 @@ fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsign
                 } else {
                     if (touched) touched[state] |= 16;
                     const unsigned tri = (unsigned)(-(link + 1));
-                    if (!listPush(leaves, (state << 28) | ((unsigned long long)g << 24) | tri)) {   // list full: decide it here
-                        const int r = exactLeafSlow(sc, frames, state, g, tri);
-                        if (r < 0) atomicExch(&ctr->error, 1u);
-                        if (r == 1) {
-                            envHit[state] = 1u;
-                            sp = 0;
-                        }
-                    }
+                    // list full: flagged, the host repeats the call with lists that hold the worst case
+                    if (!listPush(leaves, (state << 28) | ((unsigned long long)g << 24) | tri)) atomicExch(&ctr->pad, 1u);
                 }
             };
             survivor(gapC, __float_as_int(ce.w));
@@ -1182,7 +1177,7 @@ cudaError_t runFetch(const FetchSceneDev &sc, const double *dStates, const doubl
         e = cudaMemsetAsync(touched, 0, n, stream);
         if (e != cudaSuccess) return e;
     }
-    e = cudaMemsetAsync(w.counts, 0, 8 * sizeof(unsigned), stream);
+    e = cudaMemsetAsync(w.counts, 0, 12 * sizeof(unsigned), stream);
     if (e != cudaSuccess) return e;
     WorkList pairs{w.pairItems, w.counts, (unsigned)std::min<size_t>(w.pairCap, 0xffffffffu)};
     WorkList leaves{w.leafItems, w.counts + 1, (unsigned)std::min<size_t>(w.leafCap, 0xffffffffu)};
@@ -1200,15 +1195,26 @@ cudaError_t runFetch(const FetchSceneDev &sc, const double *dStates, const doubl
                                                    dSlack, touched, w.selfHit, dCtr);
     if (mprPairs) fetchMprKernel<false><<<exactGrid, 128, 0, stream>>>(sc, w.frames, exactPairs, w.counts + 5, w.selfHit, w.envHit, dCtr);
     fetchSurvivorsKernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w.selfHit, n, w.survivors, w.counts + 2);
-    const size_t envSmemBytes = (size_t)sc.nEnvNodes * 80 + (size_t)kEnvStack * kEnvThreads * sizeof(int);
-    if (envSmemBytes <= 200 * 1024) {
+    // Shared-memory variant: as many warps (<= 512 threads) as the hierarchy leaves room for next to the per-thread
+    // stacks.  Small groups (edge rounds, scalar calls) take the global-memory variant: staging the hierarchy into every
+    // SM's shared memory -- and the carve-out switch the 160-odd KB ask for -- costs ~45 us before the first box test.
+    static const size_t smemFrom = [] {
+        const char *e = std::getenv("MPLB_ENV_SMEM_FROM");   // diagnostic: group size from which the hierarchy is staged
+        return e ? (size_t)std::atol(e) : (size_t)4096;
+    }();
+    int envThreads = 0;
+    for (int t : {512, 384, 256})
+        if (!envThreads && n >= smemFrom && (size_t)sc.nEnvNodes * 80 + (size_t)kEnvStack * t * sizeof(int) <= 224 * 1024) envThreads = t;
+    if (envThreads) {
+        const size_t envSmemBytes = (size_t)sc.nEnvNodes * 80 + (size_t)kEnvStack * envThreads * sizeof(int);
         e = cudaFuncSetAttribute(fetchEnvKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)envSmemBytes);
         if (e != cudaSuccess) return e;
-        fetchEnvKernel<true><<<numSms, kEnvThreads, envSmemBytes, stream>>>(sc, w.frames, w.survivors, w.counts + 2, dSlack, touched,
-                                                                           w.envHit, leaves, w.counts + 3, dCtr);
+        fetchEnvKernel<true><<<numSms, envThreads, envSmemBytes, stream>>>(sc, w.frames, w.survivors, w.counts + 2, dSlack, touched,
+                                                                          w.envHit, leaves, w.counts + 3, dCtr);
     } else {
-        fetchEnvKernel<false><<<exactGrid, 128, 0, stream>>>(sc, w.frames, w.survivors, w.counts + 2, dSlack, touched, w.envHit,
-                                                             leaves, w.counts + 3, dCtr);
+        const int grid = (int)std::min<size_t>((size_t)exactGrid, (n * 12 + 127) / 128);
+        fetchEnvKernel<false><<<std::max(grid, 1), 128, 0, stream>>>(sc, w.frames, w.survivors, w.counts + 2, dSlack, touched, w.envHit,
+                                                                     leaves, w.counts + 3, dCtr);
     }
     if (inlineMpr) fetchLeafKernel<<<exactGrid, 128, 0, stream>>>(sc, w.frames, leaves, w.envHit, dCtr);
     else fetchMprKernel<true><<<exactGrid, 128, 0, stream>>>(sc, w.frames, leaves, w.counts + 6, w.selfHit, w.envHit, dCtr);

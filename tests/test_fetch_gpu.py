@@ -117,3 +117,28 @@ def test_large_environment_uses_the_global_memory_traversal(scenes, oracle):
     A = Q[got][:200]
     B = fetch_configs(len(A), SEED + 4)
     assert (f.check_edges(A, B) == orc.check_edges(A, B)).all()
+
+
+def test_work_lists_overflow():
+    """MPLB_FETCH_LIST_CAP=64: the pair and leaf lists between the culling and the exact kernels overflow at once -- pairs
+    are then decided inside the culling kernel, (state, geometry) items whose leaves did not fit are done again by the
+    exact redo pass: verdicts as the oracle's, states and edges."""
+    import subprocess
+    import sys
+    from conftest import GOLDEN, ROOT
+    code = ("import numpy as np, sys, os; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import mplambda_b200 as M\n"
+            "from mplambda_b200.workload import FETCH_TASKS, SEED, fetch_configs, frame_from_option\n"
+            "from oracle import oracle_py as O\n"
+            "env = np.load(os.path.join(%r, 'scenes', 'autolab.npz'))['env']\n"
+            "frame = frame_from_option(FETCH_TASKS['fetch_task_001']['env_frame'])\n"
+            "f = M.FetchScenario(frame, env, checkResolution=0.01)\n"
+            "orc = O.FetchOracle(env, frame, 0.01)\n"
+            "Q = fetch_configs(30000, SEED + 5)\n"
+            "v = f.check_states(Q); w = orc.check_states(Q)\n"
+            "assert (v == w).all(), int((v != w).sum())\n"
+            "A = Q[v][:300]; B = fetch_configs(len(A), SEED + 6)\n"
+            "assert (f.check_edges(A, B) == orc.check_edges(A, B)).all()\nprint('ok')\n" % (ROOT, os.path.join(ROOT, "tests"), GOLDEN))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, MPLB_FETCH_LIST_CAP="64"), capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout[-500:] + out.stderr[-2000:]
