@@ -501,10 +501,12 @@ def extras(local_rank, cpu_seconds):
         for seed in (1, 2, 3):
             rg = BatchedRRT(g, M.Nigh(M.nn.SE3, device=local_rank), sc_["start"], batch=2048, seed=seed)
             pg = rg.solve(time_limit=30)
-            rc = BatchedRRT(CpuScenario(env_, robot_, sc_, thr), CpuNN(thr), sc_["start"], batch=2048, seed=seed)
-            pc = rc.solve(time_limit=120)
+            # (the two GPU planners back to back: after the CPU planner's half second the GPU has idled down, and a
+            # 7 ms run measured right behind it is mostly the clocks ramping up)
             rd = DeviceRRT(g, M.Nigh(M.nn.SE3, device=local_rank), sc_["start"], batch=2048, seed=seed)
             pd = rd.solve(time_limit=30)
+            rc = BatchedRRT(CpuScenario(env_, robot_, sc_, thr), CpuNN(thr), sc_["start"], batch=2048, seed=seed)
+            pc = rc.solve(time_limit=120)
             tg.append(rg.stats["seconds"]); tc.append(rc.stats["seconds"])
             if pd is not None:
                 td.append(rd.stats["seconds"])
