@@ -183,8 +183,11 @@ def test_concurrent_streamed_batches(scenes, oracle, pinned):
     two = [(names[t % 2], t) for t in range(4)]
     for jobs in (one, two):
         run(jobs, True)   # warm: per-thread call contexts
-        serial = min(run(jobs, False) for _ in range(3))
-        conc = min(run(jobs, True) for _ in range(3))
+        for attempt in range(2):   # (wall-clock comparison on a shared box: one repeat before it counts as a failure)
+            serial = min(run(jobs, False) for _ in range(3))
+            conc = min(run(jobs, True) for _ in range(3))
+            if conc <= 1.5 * serial + 2e-3:
+                break
         assert conc <= 1.5 * serial + 2e-3, "concurrent %.2f ms vs serial %.2f ms" % (conc * 1e3, serial * 1e3)
     for k in names:
         st = sc[k].stats()
