@@ -202,14 +202,91 @@ struct FetchScene : SceneBase {
     // that nothing comes within reach of is certified free as a whole; otherwise its middle sample has been tested
     // exactly and the two halves go into the next round.  Every sample is the middle of exactly one interval, so the
     // verdict is the reference's discrete one.  Rounds are host driven (the work lists live on the host).
+    static constexpr int kIntervalOverflow = 2;   // checkEdgesDevice: the device-side interval lists did not hold a round
     int checkEdges(const double *from, const double *to, size_t n, uint8_t *valid, uint64_t *statesChecked) override {
-        int rc = checkEdgesImpl(from, to, n, valid, statesChecked, false);
-        if (rc == kListOverflow) {
+        static const bool hostRounds = std::getenv("MPLB_FETCH_HOST_ROUNDS") != nullptr;   // diagnostic: round 1's host-side lists
+        bool onHost = hostRounds || n >= ((size_t)1 << 31);
+        int rc = kIntervalOverflow;
+        for (int safe = 0; safe < 2; ++safe) {
+            if (!onHost) rc = checkEdgesDevice(from, to, n, valid, statesChecked, safe != 0);
+            if (onHost || rc == kIntervalOverflow) {
+                onHost = true;
+                rc = checkEdgesImpl(from, to, n, valid, statesChecked, safe != 0);
+            }
+            if (rc != kListOverflow) return rc;
             hListOverflows += 1;
-            rc = checkEdgesImpl(from, to, n, valid, statesChecked, true);
-            if (rc == kListOverflow) return fail(MPLB_ERR_CUDA, "Fetch leaf list overflowed although it holds the worst case");
         }
-        return rc;
+        return fail(MPLB_ERR_CUDA, "Fetch leaf list overflowed although it holds the worst case");
+    }
+
+    // isValid(from,to) with the interval lists on the device (fetch_kernels.cu: fetchRound0Kernel .. fetchSplitKernel): per
+    // round the host launches the groups -- items from intervals, the six validity kernels, the split of what was neither
+    // certified nor killed into the next round's list -- and reads the next round's length back.  Same intervals, same
+    // tests and the same verdicts as the host-side rounds below, which remain as the fallback for a round that outgrows
+    // the device lists.
+    int checkEdgesDevice(const double *from, const double *to, size_t n, uint8_t *valid, uint64_t *statesChecked, bool safe) {
+        const size_t B = safe ? safeGroup() : ::mplb::kBatch;   // items per launch group
+        MPLB_CUDA(cudaSetDevice(device));
+        CallCtx *c = acquire();
+        if (!c) return fail(MPLB_ERR_CUDA, "could not create a call context (stream / pinned memory)");
+        CtxGuard g{this, c};
+        c->hSteps.resize(n);
+        int rc = planEdges(from, to, n, c->hSteps.data());
+        if (rc != MPLB_OK) return rc;
+        const size_t sb = n * 8 * sizeof(double);
+        const size_t listCap = std::min<size_t>(std::max<size_t>(17 * n + 1024, 64 * n), (size_t)1 << 26);
+        const size_t offForced = (n * sizeof(float2) + 255) & ~(size_t)255, offCounts = (offForced + B + 255) & ~(size_t)255;
+        FetchScratch w{};
+        if ((rc = c->in0.reserve(sb)) || (rc = c->in1.reserve(sb)) || (rc = c->steps.reserve(n * 4)) ||
+            (rc = c->dead.reserve(n * 4)) || (rc = c->aux3.reserve(B * 8)) || (rc = c->stage.reserve(B * sizeof(float2))) ||
+            (rc = c->ivA.reserve(listCap * sizeof(uint4))) || (rc = c->ivB.reserve(listCap * sizeof(uint4))) ||
+            (rc = c->ivMisc.reserve(offCounts + 64)) || (rc = reserveScratch(c, B, w, safe)))
+            return rc;
+        uint4 *list[2] = {(uint4 *)c->ivA.ptr, (uint4 *)c->ivB.ptr};
+        float2 *motion = (float2 *)c->ivMisc.ptr;
+        unsigned char *forced = (unsigned char *)c->ivMisc.ptr + offForced;
+        unsigned *counts = (unsigned *)((unsigned char *)c->ivMisc.ptr + offCounts);   // [0], [1]: list lengths, [2]: overflow
+        volatile unsigned *hCounts = (volatile unsigned *)c->hWater;                 // pinned
+        static const float kCap = std::getenv("MPLB_FETCH_CAP") ? (float)std::atof(std::getenv("MPLB_FETCH_CAP")) : 0.2f;
+        MPLB_CUDA(cudaMemsetAsync(c->ctr.ptr, 0, sizeof(FetchCounters), c->stream));
+        MPLB_CUDA(cudaMemsetAsync(c->dead.ptr, 0, n * 4, c->stream));
+        MPLB_CUDA(cudaMemsetAsync(counts, 0, 16, c->stream));
+        int hrc;
+        if ((hrc = hostToDevice(c, c->in0.ptr, from, sb, c->stream)) || (hrc = hostToDevice(c, c->in1.ptr, to, sb, c->stream))) return hrc;
+        MPLB_CUDA(cudaMemcpyAsync(c->steps.ptr, c->hSteps.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+        MPLB_CUDA(launchFetchEdgeMotion((const double *)c->in0.ptr, (const double *)c->in1.ptr, n, motion, c->stream));
+        MPLB_CUDA(launchFetchRound0((const unsigned *)c->steps.ptr, n, list[0], counts, (unsigned)listCap, counts + 2, c->stream));
+        uint64_t launched = 0;
+        for (int cur = 0;; cur ^= 1) {
+            MPLB_CUDA(cudaMemcpyAsync((void *)hCounts, counts, 16, cudaMemcpyDeviceToHost, c->stream));
+            MPLB_CUDA(cudaStreamSynchronize(c->stream));
+            if (hCounts[2]) return kIntervalOverflow;
+            const size_t cnt = hCounts[cur];
+            if (cnt == 0) break;
+            MPLB_CUDA(cudaMemsetAsync(counts + (cur ^ 1), 0, sizeof(unsigned), c->stream));
+            for (size_t first = 0; first < cnt; first += B) {
+                const size_t m = std::min(B, cnt - first);
+                MPLB_CUDA(launchFetchItems(list[cur] + first, m, (const unsigned *)c->steps.ptr, motion, kCap,
+                                           (unsigned long long *)c->aux3.ptr, (float2 *)c->stage.ptr, forced, c->stream));
+                MPLB_CUDA(launchFetchEdgeItems(dev, (const double *)c->in0.ptr, (const double *)c->in1.ptr,
+                                               (const unsigned *)c->steps.ptr, (const unsigned long long *)c->aux3.ptr,
+                                               (const float2 *)c->stage.ptr, m, (unsigned *)c->dead.ptr, w,
+                                               (FetchCounters *)c->ctr.ptr, numSms, c->stream));
+                MPLB_CUDA(launchFetchSplit(list[cur] + first, m, w.touched, forced, (const unsigned *)c->dead.ptr,
+                                           (const unsigned *)c->steps.ptr, motion, kCap, list[cur ^ 1], counts + (cur ^ 1),
+                                           (unsigned)listCap, counts + 2, c->stream));
+                hLaunches += 8;
+                launched += m;
+            }
+        }
+        c->hSteps.resize(n);   // (reused as the landing buffer of the dead flags)
+        MPLB_CUDA(cudaMemcpyAsync(c->hSteps.data(), c->dead.ptr, n * 4, cudaMemcpyDeviceToHost, c->stream));
+        rc = finish(c);
+        if (rc != MPLB_OK) return rc;
+        for (size_t e = 0; e < n; ++e) valid[e] = c->hSteps[e] ? 0 : 1;
+        hChecks += launched;
+        if (statesChecked) *statesChecked = launched;
+        return MPLB_OK;
     }
     int checkEdgesImpl(const double *from, const double *to, size_t n, uint8_t *valid, uint64_t *statesChecked, bool safe) {
         const size_t kBatch = safe ? safeGroup() : ::mplb::kBatch;   // items per round

@@ -55,4 +55,16 @@ cudaError_t launchFetchEdgeItems(const FetchSceneDev &sc, const double *dFrom, c
                                  const unsigned long long *dItems, const float2 *dSlack, size_t nItems, unsigned *dDead,
                                  const FetchScratch &w, FetchCounters *dCtr, int numSms, cudaStream_t stream);
 
+// Interval lists of an edge batch kept on the device (fetch_kernels.cu): per-edge joint motion, the first round's
+// intervals (`to` + up to 16 per edge), a group's intervals -> items / slacks / forced flags, and the split of what a
+// group could neither certify nor kill into the next round's list.  *dOverflow is set when a list does not hold it all.
+cudaError_t launchFetchEdgeMotion(const double *dFrom, const double *dTo, size_t n, float2 *dMotion, cudaStream_t stream);
+cudaError_t launchFetchRound0(const unsigned *dSteps, size_t n, uint4 *dList, unsigned *dCount, unsigned cap, unsigned *dOverflow,
+                              cudaStream_t stream);
+cudaError_t launchFetchItems(const uint4 *dList, size_t cnt, const unsigned *dSteps, const float2 *dMotion, float cap,
+                             unsigned long long *dItems, float2 *dSlack, unsigned char *dForced, cudaStream_t stream);
+cudaError_t launchFetchSplit(const uint4 *dList, size_t cnt, const unsigned char *dTouched, const unsigned char *dForced,
+                             const unsigned *dDead, const unsigned *dSteps, const float2 *dMotion, float cap, uint4 *dNext,
+                             unsigned *dNextCount, unsigned nextCap, unsigned *dOverflow, cudaStream_t stream);
+
 }  // namespace mplb

@@ -1221,7 +1221,132 @@ cudaError_t runFetch(const FetchSceneDev &sc, const double *dStates, const doubl
     return cudaGetLastError();
 }
 
+// ---- interval bookkeeping of edge batches on the device --------------------------------------------------------------
+// fetch_capi.cu used to keep the interval lists on the host: per round an OpenMP pass to build the items, two copies
+// down, two copies up and another pass to split what could not be certified -- half of an edge batch's time.  Here the
+// lists stay in device memory; per round the host launches the groups and reads one count back.
+// An interval is (edge, lo, hi, -): samples lo..hi of the edge, lo == hi == steps standing for `to` itself.
+
+// how far the torso (prismatic) and the arm joints (L1) move over the whole edge, rounded up
+__global__ void fetchEdgeMotionKernel(const double *__restrict__ from, const double *__restrict__ to, unsigned n,
+                                      float2 *__restrict__ motion) {
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double a = 0;
+    for (int j = 1; j < 8; ++j) a += fabs(to[8 * (size_t)e + j] - from[8 * (size_t)e + j]);
+    motion[e] = make_float2((float)(fabs(to[8 * (size_t)e] - from[8 * (size_t)e]) * 1.000001), (float)(a * 1.000001));
+}
+// round 0: `to` and up to 16 equal intervals of the samples [1, steps - 1] of every edge
+__global__ void fetchRound0Kernel(const unsigned *__restrict__ steps, unsigned n, uint4 *__restrict__ list, unsigned *count,
+                                  unsigned cap, unsigned *overflow) {
+    const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const unsigned st = steps[e];
+    const unsigned long long m = st ? st - 1 : 0;
+    unsigned k = 1;
+    for (unsigned long long j = 0; j < 16; ++j) k += (1u + (unsigned)((j * m) >> 4)) <= (unsigned)(((j + 1) * m) >> 4) ? 1u : 0u;
+    unsigned at = atomicAdd(count, k);
+    if (at + k > cap) {
+        atomicExch(overflow, 1u);
+        return;
+    }
+    list[at++] = make_uint4(e, st, st, 0);
+    for (unsigned long long j = 0; j < 16; ++j) {
+        const unsigned lo = 1u + (unsigned)((j * m) >> 4), hi = (unsigned)(((j + 1) * m) >> 4);
+        if (lo <= hi) list[at++] = make_uint4(e, lo, hi, 0);
+    }
+}
+// one group of intervals -> the items / slacks runFetch takes.  An interval over which the gripper can stray by more
+// than `cap` is practically never certified and its inflated traversal costs more than a plain test: its middle sample
+// is evaluated plainly (slack 0) and it is split unconditionally (forced).
+__global__ void fetchItemsKernel(const uint4 *__restrict__ list, unsigned cnt, const unsigned *__restrict__ steps,
+                                 const float2 *__restrict__ motion, float cap, unsigned long long *__restrict__ items,
+                                 float2 *__restrict__ slack, unsigned char *__restrict__ forced) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const uint4 v = list[i];
+    const unsigned st = steps[v.x], mid = v.y + (v.z - v.y) / 2;
+    items[i] = ((unsigned long long)v.x << 32) | mid;
+    float f = 0.f;
+    if (v.z > v.y) f = (float)((double)max(v.z - mid, mid - v.y) / (double)st * 1.000001);
+    const float2 mo = motion[v.x];
+    float2 sl = make_float2(mo.x * f, mo.y * f);
+    const bool fo = v.z > v.y && sl.x + sl.y * 1.2f > cap;
+    forced[i] = fo ? 1 : 0;
+    slack[i] = fo ? make_float2(0.f, 0.f) : sl;
+}
+// after the group's tests: what is left of every interval that was neither certified nor killed goes to the next round
+__global__ void fetchSplitKernel(const uint4 *__restrict__ list, unsigned cnt, const unsigned char *__restrict__ touched,
+                                 const unsigned char *__restrict__ forced, const unsigned *__restrict__ dead,
+                                 const unsigned *__restrict__ steps, const float2 *__restrict__ motion, float cap,
+                                 uint4 *__restrict__ next, unsigned *nextCount, unsigned nextCap, unsigned *overflow) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cnt) return;
+    const uint4 v = list[i];
+    if (dead[v.x] || v.z <= v.y || !(touched[i] || forced[i])) return;   // dead, a single sample, or certified
+    const unsigned mid = v.y + (v.z - v.y) / 2;
+    // a split that was forced goes straight to pieces short enough to stand a chance (<= 2 H + 1 samples, H the half width
+    // at which the gripper's stray reaches the cap), not through log2 plain halvings
+    unsigned long long piece = 0xffffffffull;
+    if (forced[i]) {
+        const float2 mo = motion[v.x];
+        const double perSample = ((double)mo.y * 1.2 + (double)mo.x) / (double)steps[v.x];
+        const double H = perSample > 0 ? floor((double)cap / perSample) : 1e9;
+        piece = (unsigned long long)fmin(1e9, 2.0 * fmax(H, 1.0) + 1.0);
+    }
+    unsigned long long parts[2] = {0, 0}, len[2] = {0, 0};
+    unsigned lo[2] = {v.y, mid + 1};
+    if (mid > v.y) {
+        len[0] = (unsigned long long)(mid - 1) - v.y + 1;
+        parts[0] = (len[0] + piece - 1) / piece;
+    }
+    if (mid < v.z) {
+        len[1] = (unsigned long long)v.z - (mid + 1) + 1;
+        parts[1] = (len[1] + piece - 1) / piece;
+    }
+    const unsigned long long total = parts[0] + parts[1];
+    if (total == 0) return;
+    if (total > 0x7fffffffull) {
+        atomicExch(overflow, 1u);
+        return;
+    }
+    unsigned at = atomicAdd(nextCount, (unsigned)total);
+    if ((unsigned long long)at + total > nextCap) {
+        atomicExch(overflow, 1u);
+        return;
+    }
+    for (int h = 0; h < 2; ++h)
+        for (unsigned long long p = 0; p < parts[h]; ++p)
+            next[at++] = make_uint4(v.x, lo[h] + (unsigned)(p * len[h] / parts[h]), lo[h] + (unsigned)((p + 1) * len[h] / parts[h]) - 1, 0);
+}
+
 }  // namespace
+
+cudaError_t launchFetchEdgeMotion(const double *dFrom, const double *dTo, size_t n, float2 *dMotion, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    fetchEdgeMotionKernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(dFrom, dTo, (unsigned)n, dMotion);
+    return cudaGetLastError();
+}
+cudaError_t launchFetchRound0(const unsigned *dSteps, size_t n, uint4 *dList, unsigned *dCount, unsigned cap, unsigned *dOverflow,
+                              cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    fetchRound0Kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(dSteps, (unsigned)n, dList, dCount, cap, dOverflow);
+    return cudaGetLastError();
+}
+cudaError_t launchFetchItems(const uint4 *dList, size_t cnt, const unsigned *dSteps, const float2 *dMotion, float cap,
+                             unsigned long long *dItems, float2 *dSlack, unsigned char *dForced, cudaStream_t stream) {
+    if (cnt == 0) return cudaSuccess;
+    fetchItemsKernel<<<(unsigned)((cnt + 255) / 256), 256, 0, stream>>>(dList, (unsigned)cnt, dSteps, dMotion, cap, dItems, dSlack, dForced);
+    return cudaGetLastError();
+}
+cudaError_t launchFetchSplit(const uint4 *dList, size_t cnt, const unsigned char *dTouched, const unsigned char *dForced,
+                             const unsigned *dDead, const unsigned *dSteps, const float2 *dMotion, float cap, uint4 *dNext,
+                             unsigned *dNextCount, unsigned nextCap, unsigned *dOverflow, cudaStream_t stream) {
+    if (cnt == 0) return cudaSuccess;
+    fetchSplitKernel<<<(unsigned)((cnt + 255) / 256), 256, 0, stream>>>(dList, (unsigned)cnt, dTouched, dForced, dDead, dSteps, dMotion,
+                                                                        cap, dNext, dNextCount, nextCap, dOverflow);
+    return cudaGetLastError();
+}
 
 cudaError_t launchFetchStates(const FetchSceneDev &sc, const double *dStates, size_t n, const FetchScratch &w,
                               uint8_t *dValid, FetchCounters *dCtr, int numSms, cudaStream_t stream) {

@@ -34,6 +34,7 @@ struct CallCtx {
     cudaStream_t copyStream2 = nullptr; // streamed batches alternate their chunks over both copy streams
     std::vector<cudaEvent_t> events;    // one per pipeline stage
     DevBuf in0, in1, steps, dead, out, ctr, work, aux0, aux1, aux2, aux3, aux4, aux5, aux6;
+    DevBuf ivA, ivB, ivMisc;   // Fetch edge batches: the two interval lists, and motion / forced flags / counts
     DevCounters *hCtr = nullptr;  // pinned
     // Small calls (the reference's scalar isValid) go through one pinned staging buffer each way and one
     // device control block [DevCounters | 16 work counters | verdicts or dead flags]: one memset, one
