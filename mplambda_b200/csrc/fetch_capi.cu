@@ -264,6 +264,12 @@ struct FetchScene : SceneBase {
             const size_t cnt = hCounts[cur];
             if (cnt == 0) break;
             MPLB_CUDA(cudaMemsetAsync(counts + (cur ^ 1), 0, sizeof(unsigned), c->stream));
+            // small rounds are all latency: cut what is left into more pieces per interval, for fewer rounds
+            static const unsigned smallRound = [] {
+                const char *e = std::getenv("MPLB_FETCH_SMALL_ROUND");   // diagnostic
+                return e ? (unsigned)std::atol(e) : 65536u;
+            }();
+            const unsigned minParts = cnt < smallRound / 4 ? 4u : cnt < smallRound ? 2u : 1u;
             for (size_t first = 0; first < cnt; first += B) {
                 const size_t m = std::min(B, cnt - first);
                 MPLB_CUDA(launchFetchItems(list[cur] + first, m, (const unsigned *)c->steps.ptr, motion, kCap,
@@ -273,7 +279,7 @@ struct FetchScene : SceneBase {
                                                (const float2 *)c->stage.ptr, m, (unsigned *)c->dead.ptr, w,
                                                (FetchCounters *)c->ctr.ptr, numSms, c->stream));
                 MPLB_CUDA(launchFetchSplit(list[cur] + first, m, w.touched, forced, (const unsigned *)c->dead.ptr,
-                                           (const unsigned *)c->steps.ptr, motion, kCap, list[cur ^ 1], counts + (cur ^ 1),
+                                           (const unsigned *)c->steps.ptr, motion, kCap, minParts, list[cur ^ 1], counts + (cur ^ 1),
                                            (unsigned)listCap, counts + 2, c->stream));
                 hLaunches += 8;
                 launched += m;

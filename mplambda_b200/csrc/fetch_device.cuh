@@ -64,7 +64,7 @@ cudaError_t launchFetchRound0(const unsigned *dSteps, size_t n, uint4 *dList, un
 cudaError_t launchFetchItems(const uint4 *dList, size_t cnt, const unsigned *dSteps, const float2 *dMotion, float cap,
                              unsigned long long *dItems, float2 *dSlack, unsigned char *dForced, cudaStream_t stream);
 cudaError_t launchFetchSplit(const uint4 *dList, size_t cnt, const unsigned char *dTouched, const unsigned char *dForced,
-                             const unsigned *dDead, const unsigned *dSteps, const float2 *dMotion, float cap, uint4 *dNext,
-                             unsigned *dNextCount, unsigned nextCap, unsigned *dOverflow, cudaStream_t stream);
+                             const unsigned *dDead, const unsigned *dSteps, const float2 *dMotion, float cap, unsigned minParts,
+                             uint4 *dNext, unsigned *dNextCount, unsigned nextCap, unsigned *dOverflow, cudaStream_t stream);
 
 }  // namespace mplb

@@ -1279,7 +1279,8 @@ __global__ void fetchItemsKernel(const uint4 *__restrict__ list, unsigned cnt, c
 __global__ void fetchSplitKernel(const uint4 *__restrict__ list, unsigned cnt, const unsigned char *__restrict__ touched,
                                  const unsigned char *__restrict__ forced, const unsigned *__restrict__ dead,
                                  const unsigned *__restrict__ steps, const float2 *__restrict__ motion, float cap,
-                                 uint4 *__restrict__ next, unsigned *nextCount, unsigned nextCap, unsigned *overflow) {
+                                 unsigned minParts, uint4 *__restrict__ next, unsigned *nextCount, unsigned nextCap,
+                                 unsigned *overflow) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cnt) return;
     const uint4 v = list[i];
@@ -1296,13 +1297,15 @@ __global__ void fetchSplitKernel(const uint4 *__restrict__ list, unsigned cnt, c
     }
     unsigned long long parts[2] = {0, 0}, len[2] = {0, 0};
     unsigned lo[2] = {v.y, mid + 1};
+    // (minParts > 1: a round with few intervals left is all latency -- eight kernels and a read-back for a few thousand
+    // items -- so each half is cut into several pieces at once and the rounds that remain are fewer)
     if (mid > v.y) {
         len[0] = (unsigned long long)(mid - 1) - v.y + 1;
-        parts[0] = (len[0] + piece - 1) / piece;
+        parts[0] = max((len[0] + piece - 1) / piece, min((unsigned long long)minParts, len[0]));
     }
     if (mid < v.z) {
         len[1] = (unsigned long long)v.z - (mid + 1) + 1;
-        parts[1] = (len[1] + piece - 1) / piece;
+        parts[1] = max((len[1] + piece - 1) / piece, min((unsigned long long)minParts, len[1]));
     }
     const unsigned long long total = parts[0] + parts[1];
     if (total == 0) return;
@@ -1340,11 +1343,11 @@ cudaError_t launchFetchItems(const uint4 *dList, size_t cnt, const unsigned *dSt
     return cudaGetLastError();
 }
 cudaError_t launchFetchSplit(const uint4 *dList, size_t cnt, const unsigned char *dTouched, const unsigned char *dForced,
-                             const unsigned *dDead, const unsigned *dSteps, const float2 *dMotion, float cap, uint4 *dNext,
-                             unsigned *dNextCount, unsigned nextCap, unsigned *dOverflow, cudaStream_t stream) {
+                             const unsigned *dDead, const unsigned *dSteps, const float2 *dMotion, float cap, unsigned minParts,
+                             uint4 *dNext, unsigned *dNextCount, unsigned nextCap, unsigned *dOverflow, cudaStream_t stream) {
     if (cnt == 0) return cudaSuccess;
     fetchSplitKernel<<<(unsigned)((cnt + 255) / 256), 256, 0, stream>>>(dList, (unsigned)cnt, dTouched, dForced, dDead, dSteps, dMotion,
-                                                                        cap, dNext, dNextCount, nextCap, dOverflow);
+                                                                        cap, minParts, dNext, dNextCount, nextCap, dOverflow);
     return cudaGetLastError();
 }
 
