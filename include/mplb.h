@@ -172,10 +172,11 @@ int mplb_nn_nearest(mplb_nn *nn, const double *queries, size_t nq, int64_t *idx,
 /* nearest(nbh, q, k): [nq][k] ascending by (distance, index), padded with -1 / +inf */
 int mplb_nn_knearest(mplb_nn *nn, const double *queries, size_t nq, int k, int64_t *idx,
                      double *dist);
-/* Beyond brute force (nigh's KD-tree strategy, prrt.hpp:35-42): from 16 384 keys on the searches go through a
+/* Beyond brute force (nigh's KD-tree strategy, prrt.hpp:35-42): from 256 keys on the searches go through a
  * uniform grid over the SE(3) keys' translations (the metric's translation term bounds the distance from below) or
- * the first three coordinates of L1 keys (a partial sum of the L1 distance), rebuilt
- * when the keys inserted since outgrow a quarter of it; those are searched by brute force meanwhile and the lists
+ * the first three coordinates of L1 keys (a partial sum of the L1 distance), rebuilt whenever keys have come in
+ * (structures of up to 65 536 keys: ~50 us) or when the keys inserted since outgrow a quarter of it (larger ones); those
+ * are searched by brute force meanwhile and the lists
  * merged.  Results are the brute-force ones bit for bit.  mplb_nn_set_index(nn, 0) keeps a structure on brute force;
  * mplb_nn_index_info reports the keys indexed, the grid's cells, the FP64 distance evaluations of the indexed searches
  * so far and the queries that needed the slow exact selection (more candidates than a warp's list holds: duplicates). */

@@ -105,7 +105,7 @@ static void nnNoteKeyStats(mplb_nn *nn, double absMax, bool nonUnit) {
 static size_t nnGridMin() {
     static const size_t v = [] {
         const char *e = std::getenv("MPLB_NN_GRID_MIN");
-        return e ? (size_t)std::max(1L, std::atol(e)) : (size_t)16384;
+        return e ? (size_t)std::max(1L, std::atol(e)) : (size_t)256;
     }();
     return v;
 }
@@ -186,8 +186,13 @@ static int nnLaunchSearch(mplb_nn *nn, const double *dQ, size_t nq, int k, doubl
     if (!gridOk) nn->gridBuilt = 0;
     if (gridOk) {
         const size_t since = nn->count - std::max(nn->gridBuilt, nn->gridTried);
-        if ((nn->gridBuilt == 0 && (nn->gridTried == 0 || since > nn->gridTried)) ||
-            (nn->gridBuilt != 0 && nn->count - nn->gridBuilt > std::max<size_t>(4096, nn->gridBuilt / 4)))
+        // Rebuilding is three small kernels, a scan and one 24-byte read-back (~50 us for a few thousand keys, ~0.15 ms
+        // for 65,536); searching the keys inserted since by brute force costs 0.1-0.9 ms whatever their number (that
+        // pipeline's fixed cost).  So a structure of up to 65,536 keys is re-indexed whenever keys have come in, a larger
+        // one when they outgrow a quarter of the index.
+        const size_t tail = nn->count - nn->gridBuilt;
+        if ((nn->gridBuilt == 0 && (nn->gridTried == 0 || since > nn->gridTried / 4)) ||
+            (nn->gridBuilt != 0 && tail > (nn->count <= 65536 ? (size_t)0 : std::max<size_t>(4096, nn->gridBuilt / 4))))
             if ((rc = nnGridRebuild(nn, st))) return rc;
     }
     auto brute = [&](size_t first, double *oDist, long long *oIdx) -> int {
