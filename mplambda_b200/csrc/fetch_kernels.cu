@@ -904,25 +904,60 @@ fetchMprKernel(FetchSceneDev sc, const double *__restrict__ frames, WorkList lis
     m.phase = kMprIdle;
     if (kLeaf) envObjFrame(sc, o2);
     unsigned long long state = 0;
-    unsigned tested = 0, chunkBase = 0, chunkLeft = 0;
+    unsigned tested = 0, chunkBase = 0, chunkLeft = 0, chunkStart = 0;
+    unsigned long long chunkItem = 0;   // item chunkStart + lane
+    unsigned nextBase = 0;              // (lane 0) the chunk claimed ahead
+    bool nextClaimed = false;
     bool exhausted = false;
     for (;;) {
         const unsigned need = __ballot_sync(0xffffffffu, m.phase == kMprIdle);
+        // (idle lanes waiting until several of them can set their tests up together made no difference: thresholds of
+        // 2 .. 16 lanes all measured within the noise of refilling at once)
         if (need && !exhausted) {
-            if (chunkLeft == 0) {   // items are claimed 64 per warp and dealt out from registers
+            // Items are claimed 32 per warp -- the next chunk while the current one still has items, so that the cursor's
+            // atomic is not waited for -- read one per lane, and what a lane will load when it is dealt the item (the
+            // shape's frame, the triangle) is prefetched: the refill of a single lane used to be a chain of three
+            // dependent global loads with the other lanes of the warp waiting (ncu: a fifth of this kernel's samples).
+            if (chunkLeft == 0) {
                 unsigned base = 0;
-                if (lane == 0) base = atomicAdd(cursor, 64u);
-                chunkBase = __shfl_sync(0xffffffffu, base, 0);
-                chunkLeft = chunkBase < n ? min(64u, n - chunkBase) : 0u;
+                if (lane == 0) base = nextClaimed ? nextBase : atomicAdd(cursor, 32u);
+                nextClaimed = false;
+                chunkBase = chunkStart = __shfl_sync(0xffffffffu, base, 0);
+                chunkLeft = chunkBase < n ? min(32u, n - chunkBase) : 0u;
                 if (chunkLeft == 0) exhausted = true;
+                if (lane < chunkLeft) {
+                    chunkItem = list.items[chunkBase + lane];
+                    const unsigned long long st = kLeaf ? chunkItem >> 28 : chunkItem >> 8;
+                    const double *fp = frames + st * 144;
+                    if (kLeaf) {
+                        fp += 12 * (int)((chunkItem >> 24) & 15);
+                        const double *tp = sc.envTris64 + 9 * (size_t)(chunkItem & 0xffffff);
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(tp));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + 8));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(fp));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(fp + 11));
+                    } else {
+                        const int k = (int)(chunkItem & 255);
+                        const double *fa = fp + 12 * kSelfPairs[k][0], *fb = fp + 12 * kSelfPairs[k][1];
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(fa));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(fa + 11));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(fb));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(fb + 11));
+                    }
+                }
             }
             const unsigned rank = __popc(need & ((1u << lane) - 1u));
             const unsigned take = min((unsigned)__popc(need), chunkLeft);
             const unsigned at = chunkBase + rank;
             chunkBase += take;
             chunkLeft -= take;
+            const unsigned long long mine = __shfl_sync(0xffffffffu, chunkItem, (at - chunkStart) & 31u);
+            if (chunkLeft < 12 && !nextClaimed && !exhausted) {
+                if (lane == 0) nextBase = atomicAdd(cursor, 32u);
+                nextClaimed = true;
+            }
             if (m.phase == kMprIdle && rank < take) {
-                const unsigned long long v = list.items[at];
+                const unsigned long long v = mine;
                 state = kLeaf ? v >> 28 : v >> 8;
                 const bool decided = kLeaf ? envHit[state] != 0u : selfHit[state] != 0;   // by another item of the state
                 if (!decided) {
@@ -1236,10 +1271,11 @@ cudaError_t runFetch(const FetchSceneDev &sc, const double *dStates, const doubl
     // counts: [4] pairs that need MPR, [5] / [6] item cursors of the two fetchMprKernel launches
     WorkList exactPairs{w.pairItems + pairs.capacity, w.counts + 4, pairs.capacity};
     // (measured per 65,536 states: pairs decided inside fetchPairKernel 55-59 us; listed and run through fetchMprKernel
-    // 18 + 52-58 us -- a pair item is two object set-ups for one or two supports, the set-up is what diverges; the
-    // shape-triangle tests gain: 102 -> 85 us.  MPLB_FETCH_MPR_PAIRS=1 / MPLB_FETCH_INLINE_MPR=1 select the other ways.)
+    // 15 + 35 us since that kernel prefetches its items (18 + 52-58 us before: a pair item is two object set-ups for one
+    // or two supports); the shape-triangle tests: 102 -> 80 us.  MPLB_FETCH_INLINE_PAIRS=1 / MPLB_FETCH_INLINE_MPR=1
+    // select the other ways.)
     static const bool inlineMpr = std::getenv("MPLB_FETCH_INLINE_MPR") != nullptr;
-    static const bool mprPairs = std::getenv("MPLB_FETCH_MPR_PAIRS") != nullptr && !inlineMpr;
+    static const bool mprPairs = std::getenv("MPLB_FETCH_INLINE_PAIRS") == nullptr && !inlineMpr;
     fetchPairKernel<<<exactGrid, 128, 0, stream>>>(sc, w.frames, pairs, mprPairs ? exactPairs : WorkList{nullptr, w.counts + 4, 0u},
                                                    dSlack, touched, w.selfHit, dCtr);
     if (mprPairs) fetchMprKernel<false><<<exactGrid, 128, 0, stream>>>(sc, w.frames, exactPairs, w.counts + 5, w.selfHit, w.envHit, dCtr);
