@@ -450,6 +450,52 @@ __device__ __forceinline__ void shapeExtents(const FetchShape &s, float e[3]) {
     else { e[0] = (float)s.a; e[1] = (float)s.a; e[2] = (float)s.b; }
 }
 constexpr float kCullSlack = 1e-4f;  // metres; FP32 error of these tests is ~1e-6
+#ifndef MPLB_FETCH_TRI_SAT
+#define MPLB_FETCH_TRI_SAT 1
+#endif
+
+// Separating-axis test of a shape's oriented box (half extents e, centred at the origin of its frame) against a triangle
+// whose vertices q[0..2] are given in that frame: the box's three axes, the triangle's normal, the nine edge cross
+// products.  true only when the two are farther apart than kCullSlack along one of them (|axis|_1 >= |axis|_2 scales the
+// slack; a vanishing cross product separates nothing), so -- the shape lying inside its box -- the exact test would
+// answer "disjoint": the same argument, slack and arithmetic as the box tests of the traversal.
+__device__ __forceinline__ bool boxTriangleApart(const float e[3], const float q[3][3]) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float mn = fminf(q[0][i], fminf(q[1][i], q[2][i])), mx = fmaxf(q[0][i], fmaxf(q[1][i], q[2][i]));
+        if (mn > e[i] + kCullSlack || mx < -e[i] - kCullSlack) return true;
+    }
+    float ed[3][3];   // edges q1 - q0, q2 - q1, q0 - q2
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        ed[0][i] = q[1][i] - q[0][i];
+        ed[1][i] = q[2][i] - q[1][i];
+        ed[2][i] = q[0][i] - q[2][i];
+    }
+    {
+        const float n[3] = {ed[0][1] * ed[1][2] - ed[0][2] * ed[1][1], ed[0][2] * ed[1][0] - ed[0][0] * ed[1][2],
+                            ed[0][0] * ed[1][1] - ed[0][1] * ed[1][0]};
+        const float d = n[0] * q[0][0] + n[1] * q[0][1] + n[2] * q[0][2];
+        const float a0 = fabsf(n[0]), a1 = fabsf(n[1]), a2 = fabsf(n[2]);
+        if (fabsf(d) > e[0] * a0 + e[1] * a1 + e[2] * a2 + kCullSlack * (a0 + a1 + a2)) return true;
+    }
+    bool apart = false;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float fx = ed[j][0], fy = ed[j][1], fz = ed[j][2];
+        const float L[3][3] = {{0.f, -fz, fy}, {fz, 0.f, -fx}, {-fy, fx, 0.f}};   // u_i x f for the three box axes
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float p0 = L[i][0] * q[0][0] + L[i][1] * q[0][1] + L[i][2] * q[0][2];
+            const float p1 = L[i][0] * q[1][0] + L[i][1] * q[1][1] + L[i][2] * q[1][2];
+            const float p2 = L[i][0] * q[2][0] + L[i][1] * q[2][1] + L[i][2] * q[2][2];
+            const float a0 = fabsf(L[i][0]), a1 = fabsf(L[i][1]), a2 = fabsf(L[i][2]);
+            const float r = e[0] * a0 + e[1] * a1 + e[2] * a2 + kCullSlack * (a0 + a1 + a2);
+            apart |= fminf(p0, fminf(p1, p2)) > r || fmaxf(p0, fmaxf(p1, p2)) < -r;
+        }
+    }
+    return apart;
+}
 
 // A sphere-swept segment that contains the shape: exact for a capsule, the cylinder with its rim rounded, a box
 // swept along its longest side.  For the slender arm links this bounds distances far better than their boxes.
@@ -1087,14 +1133,50 @@ fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsign
     const unsigned wid = threadIdx.x >> 5;
     if (lane == 0) pushCnt[wid] = 0;
     __syncwarp();
+    // The traversal culls against the LEAF'S BOX -- the triangle's bounding rectangle with some thickness.  Before a
+    // buffered leaf is listed its triangle itself is tested against the shape's box, one leaf per lane (the whole warp
+    // takes part: this is the one place where the kernel's lanes all have the same thing to do): a listed leaf costs the
+    // exact kernel an MPR set-up and one or two supports -- a few thousand dependent FP64 instructions of a lane whose
+    // warp waits for it -- and many of them are clear of the box all the same.
     auto flush = [&](unsigned held) {   // warp-collective
-        unsigned at = 0;
-        if (lane == 0) at = atomicAdd(leaves.count, held);
-        at = __shfl_sync(0xffffffffu, at, 0);
-        for (unsigned i = lane; i < held; i += 32) {
-            // list full: flagged, the host repeats the call with lists that hold the worst case
-            if (at + i < leaves.capacity) leaves.items[at + i] = pushBuf[wid][i];
-            else atomicExch(&ctr->pad, 1u);
+        for (unsigned i0 = 0; i0 < held; i0 += 32) {
+            const unsigned i = i0 + lane;
+            unsigned long long v = 0;
+            bool keep = false;
+            if (i < held) {
+                v = pushBuf[wid][i];
+                keep = true;
+                if (MPLB_FETCH_TRI_SAT) {
+                    const int gg = (int)((v >> 24) & 15);
+                    FrameD fr;
+                    loadFrame(frames + (v >> 28) * 144 + 12 * gg, fr);
+                    const double *tp = sc.envTris64 + 9 * (size_t)(v & 0xffffff);
+                    float q[3][3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const float px = (float)tp[3 * k], py = (float)tp[3 * k + 1], pz = (float)tp[3 * k + 2];
+                        // world coordinates relative to the box's centre, then onto its axes (the columns of R)
+                        const float wx = fmaf(x0.x, px, fmaf(x0.y, py, fmaf(x0.z, pz, x0.w))) - (float)fr.t[0];
+                        const float wy = fmaf(x1.x, px, fmaf(x1.y, py, fmaf(x1.z, pz, x1.w))) - (float)fr.t[1];
+                        const float wz = fmaf(x2.x, px, fmaf(x2.y, py, fmaf(x2.z, pz, x2.w))) - (float)fr.t[2];
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) q[k][a] = fmaf((float)fr.R[0][a], wx, fmaf((float)fr.R[1][a], wy, (float)fr.R[2][a] * wz));
+                    }
+                    const float e[3] = {geomS[gg][0], geomS[gg][1], geomS[gg][2]};
+                    keep = !boxTriangleApart(e, q);
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (m) {
+                unsigned at = 0;
+                if (lane == 0) at = atomicAdd(leaves.count, (unsigned)__popc(m));
+                at = __shfl_sync(0xffffffffu, at, 0) + __popc(m & ((1u << lane) - 1u));
+                if (keep) {
+                    // list full: flagged, the host repeats the call with lists that hold the worst case
+                    if (at < leaves.capacity) leaves.items[at] = v;
+                    else atomicExch(&ctr->pad, 1u);
+                }
+            }
         }
         __syncwarp();
         if (lane == 0) pushCnt[wid] = 0;
@@ -1196,6 +1278,11 @@ fetchEnvKernel(FetchSceneDev sc, const double *__restrict__ frames, const unsign
                     if (touched) touched[state] |= 16;
                     const unsigned tri = (unsigned)(-(link + 1));
                     pushBuf[wid][atomicAdd(&pushCnt[wid], 1u)] = (state << 28) | ((unsigned long long)g << 24) | tri;
+                    if (MPLB_FETCH_TRI_SAT) {   // the flush reads the triangle (72 bytes: may straddle two lines)
+                        const double *tp = sc.envTris64 + 9 * (size_t)tri;
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(tp));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + 8));
+                    }
                 }
             };
             survivor(gapC, __float_as_int(ce.w));
