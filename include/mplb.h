@@ -105,10 +105,14 @@ int mplb_check_edges(mplb_scene *scene, const double *from, const double *to, si
 
 /* Device-resident variants: all pointers are device memory on the scene's device; work is
  * enqueued on `stream` (a cudaStream_t passed as void*; NULL = the default stream) and NOT
- * synchronised.  steps/offsets for edges are computed by mplb_edges_plan on the host.  These
- * calls share one set of per-scene scratch buffers (work counters, spill lists, interval
- * stacks): enqueue them on ONE stream per scene, or order them with events; the host-buffer
- * calls above borrow private scratch and may run concurrently from any number of threads. */
+ * synchronised.  steps/offsets for edges are computed by mplb_edges_plan on the host.  The edge
+ * and index-named calls share one set of per-scene scratch buffers (work counters, spill lists,
+ * interval stacks): enqueue them on ONE stream per scene, or order them with events.
+ * mplb_check_states_device may be issued on several streams at once (each call in flight has a
+ * work cursor of its own); issuing successive batches alternately on two streams lets the SMs
+ * one launch has drained start on the next while its last warps finish (2^20 Alpha 1.5 poses:
+ * 0.74 -> 0.69 ms per batch).  The host-buffer calls above borrow private scratch and may run
+ * concurrently from any number of threads. */
 int mplb_check_states_device(mplb_scene *scene, const double *d_states, size_t n,
                              uint8_t *d_valid, void *stream);
 /* Host-side plan of an edge batch: steps[i] = ceil(distance*invStep) exactly as

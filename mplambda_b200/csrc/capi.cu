@@ -1028,8 +1028,29 @@ int mplb_check_states_device(mplb_scene *scene, const double *d_states, size_t n
     auto *s = dynamic_cast<Se3Scene *>(base(scene));
     if (!s) return fail(MPLB_ERR_INVALID, "unsupported scene kind");
     MPLB_CUDA(cudaSetDevice(s->device));
-    MPLB_CUDA(launchCheckStates(s->dev, d_states, n, d_valid, (DevCounters *)s->globalCtr.ptr,
-                                (unsigned *)s->globalWork.ptr, s->numSms, (cudaStream_t)stream));
+    {
+        std::lock_guard<std::mutex> g(s->mu);
+        const cudaStream_t st = (cudaStream_t)stream;
+        if (!s->cursorWords.ptr) {
+            int rc = s->cursorWords.reserve((Se3Scene::kDeviceCursors + 1) * 64);
+            if (rc != MPLB_OK) return rc;
+        }
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        MPLB_CUDA(cudaStreamIsCapturing(st, &cap));
+        unsigned slot = Se3Scene::kDeviceCursors;   // a captured call: ordered by its graph, no events across the capture
+        if (cap == cudaStreamCaptureStatusNone) {
+            slot = s->nextCursor++ % Se3Scene::kDeviceCursors;
+            Se3Scene::DeviceCursor &c = s->cursors[slot];
+            if (!c.done) MPLB_CUDA(cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+            if (c.used) MPLB_CUDA(cudaStreamWaitEvent(st, c.done, 0));
+        }
+        MPLB_CUDA(launchCheckStates(s->dev, d_states, n, d_valid, (DevCounters *)s->globalCtr.ptr,
+                                    (unsigned *)((char *)s->cursorWords.ptr + 64 * slot), s->numSms, st));
+        if (slot < Se3Scene::kDeviceCursors) {
+            MPLB_CUDA(cudaEventRecord(s->cursors[slot].done, st));
+            s->cursors[slot].used = true;
+        }
+    }
     s->hLaunches += 1;
     s->hChecks += n;
     return MPLB_OK;

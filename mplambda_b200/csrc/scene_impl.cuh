@@ -132,6 +132,22 @@ struct Se3Scene : SceneBase {
     DevBuf robotNodes, envNodes, robotTris, envTris, robotTris64, envTris64;
     DevBuf marginWord;   // mplb_scene_track_margins: the device word SceneDev::minMargin points at
     size_t nEnvTris = 0, nRobotTris = 0;
+    // mplb_check_states_device: every call in flight needs a work cursor of its own -- callers on different streams run
+    // side by side, and the SMs a launch has drained take the next launch's CTAs while its last warps finish.  A ring of
+    // cursors; a cursor is handed out again once the call that used it four calls ago is through (an event the new
+    // call's stream waits for -- a no-op for a caller that stays on one stream).
+    struct DeviceCursor {
+        cudaEvent_t done = nullptr;
+        bool used = false;
+    };
+    static constexpr unsigned kDeviceCursors = 4;
+    DeviceCursor cursors[kDeviceCursors];
+    DevBuf cursorWords;   // kDeviceCursors + 1 cursors, 64 bytes apart (the last one: calls on a capturing stream)
+    unsigned nextCursor = 0;
+    ~Se3Scene() override {
+        for (auto &c : cursors)
+            if (c.done) cudaEventDestroy(c.done);
+    }
 
     Se3Scene() { stateDim = 7; }
     int checkStates(const double *states, size_t n, uint8_t *valid) override;

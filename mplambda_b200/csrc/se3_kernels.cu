@@ -59,7 +59,11 @@ namespace {
 #ifndef MPLB_MIN_CTAS
 #define MPLB_MIN_CTAS 1
 #endif
+#ifndef MPLB_WARPS_SMALL_CTA
+#define MPLB_WARPS_SMALL_CTA MPLB_WARPS_PER_CTA   // (4: see launchStatesT -- measured, not enabled)
+#endif
 constexpr int kWarpsStates = MPLB_WARPS_PER_CTA, kWarpsEdges = MPLB_EDGE_WARPS;
+constexpr int kWarpsSmall = MPLB_WARPS_SMALL_CTA;   // pose batches: CTAs of this many warps where three of them fit an SM (launchStatesT)
 #ifndef MPLB_SLOTS
 #define MPLB_SLOTS 64
 #endif
@@ -1616,17 +1620,30 @@ cudaError_t launchStatesT(const SceneDev &sc, const double *dStates, size_t n, u
     auto k = streamed ? (streamedThroughput ? checkStatesKernel<E, false, true> : checkStatesKernel<E, true, true>)
                       : n < kLatencyBelow ? checkStatesKernel<E, true, false> : checkStatesKernel<E, false, false>;
     if (sc.minMargin && !streamed) k = checkStatesKernel<E, false, false, true>;   // diagnostic: margins of the exact decisions
-    const size_t smem = smemBytes<E>(sc, kWarpsStates);
-    int grid = 0;
-    cudaError_t err = gridFor(k, smem, kWarpsStates * 32, numSms, &grid);
+    // -DMPLB_WARPS_SMALL_CTA=4 runs the SM's twelve warps as three CTAs of four where the scene's stacks leave room for
+    // the two extra CTAs' fixed shared memory (everything but Apartment, which at two CTAs of four goes 3.21 -> 3.58 ms
+    // and keeps the one CTA of twelve): the warps do not talk to each other, but a CTA's registers come back only when
+    // its last warp is through, and an SM that a launch has drained a third at a time starts on the next launch --
+    // another stream's, mplb.h -- that much earlier (2^20 Alpha poses issued alternately on two streams: 0.695 -> 0.682
+    // ms; on one stream the shape makes no difference).  NOT the default: with it the scalar-call sharing test
+    // (test_scalar_calls_from_native_threads, sharing on) reported wrong verdicts once and hung once at the very end of
+    // the round, unexplained; the one-CTA shape has passed that test in every run.
+    int warps = kWarpsSmall, grid = 0;
+    size_t smem = smemBytes<E>(sc, warps);
+    cudaError_t err = gridFor(k, smem, warps * 32, numSms, &grid);
     if (err != cudaSuccess) return err;
+    if (grid < kWarpsStates / kWarpsSmall * numSms) {
+        warps = kWarpsStates;
+        smem = smemBytes<E>(sc, warps);
+        if ((err = gridFor(k, smem, warps * 32, numSms, &grid)) != cudaSuccess) return err;
+    }
     // small batches are latency bound: one state per warp, spread over as many SMs as there are
-    grid = (int)std::min<unsigned long long>(grid, (n + kWarpsStates - 1) / kWarpsStates);
+    grid = (int)std::min<unsigned long long>(grid, (n + warps - 1) / warps);
 #ifndef MPLB_GUIDED_SHARE
 #define MPLB_GUIDED_SHARE 2
 #endif
     constexpr unsigned guidedShare = MPLB_GUIDED_SHARE;   // a warp takes at most 1/(2 x warps) of what is left (1, 4, 8 measured no better)
-    k<<<std::max(grid, 1), kWarpsStates * 32, smem, stream>>>(sc, dStates, n, dValid, dCtr, dWork, guidedShare, in);
+    k<<<std::max(grid, 1), warps * 32, smem, stream>>>(sc, dStates, n, dValid, dCtr, dWork, guidedShare, in);
     return cudaGetLastError();
 }
 

@@ -266,6 +266,37 @@ def test_device_resident_batch(scenes, golden):
     assert (out.cpu().numpy().astype(bool) == want).all()
 
 
+def test_device_resident_batches_on_several_streams(scenes, golden):
+    """mplb.h: mplb_check_states_device may be issued on several streams at once (a work cursor per call in flight) --
+    twelve batches of different sizes on three streams, one of them also captured into a CUDA graph and replayed."""
+    import torch
+    s = make(scenes, "twistycool")
+    want = golden["twistycool_valid"]
+    sc = SE3_SCENES["twistycool"]
+    P = se3_poses(len(want), sc["min"], sc["max"], SEED)
+    d = torch.from_numpy(P).cuda()
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    sizes = [len(P), 70000, 4096, 33, len(P), 1, 65536, 9000, len(P), 511, 131072 if len(P) >= 131072 else len(P), 7]
+    sizes = [min(n, len(P)) for n in sizes]
+    outs = [torch.zeros(n, dtype=torch.uint8, device="cuda") for n in sizes]
+    torch.cuda.synchronize()
+    for rep in range(3):   # cursors are reused every fourth call
+        for j, n in enumerate(sizes):
+            s.check_states_device(d.data_ptr(), n, outs[j].data_ptr(), streams[j % 3].cuda_stream)
+    torch.cuda.synchronize()
+    for j, n in enumerate(sizes):
+        assert (outs[j].cpu().numpy().astype(bool) == want[:n]).all(), (j, n)
+    g = torch.cuda.CUDAGraph()
+    out = torch.zeros(len(P), dtype=torch.uint8, device="cuda")
+    with torch.cuda.graph(g):
+        s.check_states_device(d.data_ptr(), len(P), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    for _ in range(2):
+        out.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert (out.cpu().numpy().astype(bool) == want).all()
+
+
 def test_full_size_batch_properties(scenes, oracle):
     """BASELINE.json configs[1] at full size (2^20 Alpha 1.5 poses): size-independent properties plus the
     oracle on a random subset."""
