@@ -100,3 +100,54 @@ def filter_gaps(P, Q, states, env_radius, robot_radius):
     kinds = ["n", "m"] + ["ef"] * 9 + ["g"] * 3 + ["h"] * 3
     E = np.stack([np.abs(ax).sum(-1) * S + K[k] for ax, k in zip(axes, kinds)], axis=-1)
     return gaps, E.astype(F)
+
+
+# ---- Fetch: box-triangle separating-axis cull (mplambda_b200/csrc/fetch_kernels.cu: boxTriangleApart) ----------------
+CULL_SLACK = np.float32(1e-4)
+
+
+def box_triangle_apart32(e, q):
+    """float32 model of boxTriangleApart: e [n,3] box half extents, q [n,3,3] triangle vertices in the box's frame.
+    True = the device does not list the leaf for the exact test."""
+    f32 = np.float32
+    e = e.astype(f32); q = q.astype(f32)
+    mn, mx = q.min(1), q.max(1)
+    apart = ((mn > e + CULL_SLACK) | (mx < -e - CULL_SLACK)).any(1)
+    ed = np.stack([q[:, 1] - q[:, 0], q[:, 2] - q[:, 1], q[:, 0] - q[:, 2]], 1)
+    n = np.cross(ed[:, 0], ed[:, 1]).astype(f32)
+    d = (n * q[:, 0]).sum(1, dtype=f32)
+    a = np.abs(n)
+    apart |= np.abs(d) > (e * a).sum(1, dtype=f32) + CULL_SLACK * a.sum(1, dtype=f32)
+    for j in range(3):
+        fx, fy, fz = ed[:, j, 0], ed[:, j, 1], ed[:, j, 2]
+        z = np.zeros_like(fx)
+        for L in (np.stack([z, -fz, fy], 1), np.stack([fz, z, -fx], 1), np.stack([-fy, fx, z], 1)):
+            p = np.einsum("nk,nvk->nv", L, q).astype(f32)
+            al = np.abs(L)
+            r = (e * al).sum(1, dtype=f32) + CULL_SLACK * al.sum(1, dtype=f32)
+            apart |= (p.min(1) > r) | (p.max(1) < -r)
+    return apart
+
+
+def box_triangle_gap64(e, q):
+    """float64 specification: the largest separating gap in METRES over the 13 axes (normalised axes; > 0 iff the box
+    and the triangle are disjoint -- the 13 axes are necessary and sufficient for a box and a triangle)."""
+    e = e.astype(np.float64); q = q.astype(np.float64)
+    gaps = []
+    mn, mx = q.min(1), q.max(1)
+    gaps.append(np.maximum(mn - e, -mx - e).max(1))
+    ed = np.stack([q[:, 1] - q[:, 0], q[:, 2] - q[:, 1], q[:, 0] - q[:, 2]], 1)
+    axes = [np.cross(ed[:, 0], ed[:, 1])]
+    eye = np.eye(3)
+    for j in range(3):
+        for i in range(3):
+            axes.append(np.cross(np.broadcast_to(eye[i], ed[:, j].shape), ed[:, j]))
+    for L in axes:
+        ln = np.linalg.norm(L, axis=1)
+        ok = ln > 1e-12
+        Ln = L / np.where(ok, ln, 1.0)[:, None]
+        p = np.einsum("nk,nvk->nv", Ln, q)
+        r = (e * np.abs(Ln)).sum(1)
+        g = np.maximum(p.min(1) - r, -p.max(1) - r)
+        gaps.append(np.where(ok, g, -np.inf))
+    return np.max(np.stack(gaps, 1), 1)

@@ -47,3 +47,41 @@ def test_degenerate_parallel_edges_are_unsure_not_wrong():
     g32, E = filter_gaps(P, Q, st, 4.0, 2.0)
     assert (np.abs(g32 - g64) <= E).all()
     assert (g32 > E).any()       # separated along x with margin 1: certain
+
+
+def _box_triangle_cases(rng, n, size, spread, near):
+    from filter_model import box_triangle_apart32, box_triangle_gap64  # noqa: F401
+    e = rng.uniform(0.02, 0.35, size=(n, 3))                       # the Fetch shapes' boxes: 2 .. 35 cm half extents
+    c = rng.normal(size=(n, 1, 3)) * spread                        # triangle somewhere around the box ...
+    q = c + rng.normal(size=(n, 3, 3)) * size
+    # ... and a share of them pulled to the box's surface, where the decision is close
+    k = n // 2
+    s = np.sign(rng.normal(size=(k, 3)))
+    q[:k] += (s * e[:k] * (1 + rng.normal(size=(k, 1)) * near))[:, None, :] - c[:k]
+    return e, q
+
+
+@pytest.mark.parametrize("cfg", [(0.05, 0.5, 1e-3), (0.5, 1.0, 1e-4), (2.0, 0.5, 1e-2), (0.01, 0.3, 1e-5), (5.0, 3.0, 1e-3)])
+def test_box_triangle_cull_is_conservative(cfg):
+    """fetch_kernels.cu boxTriangleApart (FP32, slack 1e-4 m) may only drop a leaf when the FP64 13-axis test says box
+    and triangle are disjoint -- by the slack less the FP32 error, which must stay far below it at robot scale."""
+    from filter_model import box_triangle_apart32, box_triangle_gap64
+    rng = np.random.default_rng(hash(cfg) % 2**32)
+    e, q = _box_triangle_cases(rng, 200000, *cfg)
+    apart = box_triangle_apart32(e, q)
+    gap = box_triangle_gap64(e, q)
+    assert apart.any() and (~apart).any()
+    # never drops an intersecting or touching pair, and everything it drops is clear by most of the slack
+    assert (gap[apart] > 0).all()
+    assert gap[apart].min() > 0.5e-4, gap[apart].min()
+    # and it is not vacuous: pairs that are clear by a millimetre in the L1-scaled sense are dropped
+    assert apart[gap > 2e-3 * np.sqrt(3)].mean() > 0.99
+
+
+def test_box_triangle_cull_degenerate_triangles():
+    from filter_model import box_triangle_apart32
+    e = np.array([[0.1, 0.1, 0.1]] * 3)
+    q = np.array([[[0.05, 0, 0]] * 3,                                   # a point inside the box
+                  [[0.3, 0, 0], [0.3, 0, 0], [0.4, 0, 0]],              # a segment outside
+                  [[-1, 0, 0], [1, 0, 0], [0, 0, 0.0]]])                # a collinear triangle through the box
+    assert box_triangle_apart32(e, q).tolist() == [False, True, False]
