@@ -171,6 +171,8 @@ class SE3RigidBodyScenario:
         _capi.check(_capi.lib().mplb_check_states(self._h, host_states_ptr, n, host_valid_ptr))
 
     def check_states_device(self, d_states_ptr, n, d_valid_ptr, stream=0):
+        """Enqueued on `stream` (a cudaStream_t as int), not synchronised.  May be issued on several streams at once;
+        successive batches issued alternately on two streams overlap one launch's drain with the next one's start."""
         _capi.check(_capi.lib().mplb_check_states_device(self._h, d_states_ptr, n, d_valid_ptr, stream))
 
     def check_edges_device(self, d_from, d_to, d_steps, n, max_steps, d_valid, stream=0):
